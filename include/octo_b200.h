@@ -1,0 +1,201 @@
+/*
+ * octo_b200.h — C ABI of libocto_b200.so
+ *
+ * B200-native (sm_100a) replacement for ONE path of Octofitter.jl: the batched
+ * Keplerian orbit solve + epoch-vectorised Gaussian log-likelihood and its
+ * gradient, i.e. what the reference evaluates inside
+ *     ln_like_generated(system, θ)            src/likelihoods/system.jl:21-242
+ * for the observation types
+ *     PlanetRelAstromObs                       src/likelihoods/relative-astrometry.jl:104-253
+ *     StarAbsoluteRVObs (non-GP)               OctofitterRadialVelocity/src/rv-absolute.jl:135-204
+ *     MarginalizedStarAbsoluteRVObs            OctofitterRadialVelocity/src/rv-absolute-margin.jl:106-185
+ *     PlanetRelativeRVObs (non-GP)             OctofitterRadialVelocity/src/rv-relative.jl:121-211
+ * on Visual{KepOrbit} orbits (PlanetOrbits.jl 0.11: KepOrbit ctor, orbitsolve,
+ * kepler_solver(Markley), raoff/decoff/radvel), and what ForwardDiff computes
+ * for the same terms in ∇ℓπcallback (src/logdensitymodel.jl:169-177).
+ *
+ * The caller (Julia `ccall`, or the ctypes mirror in octofitter.jl_b200/) keeps
+ * priors, bijectors, derived variables and samplers; it hands this library a
+ * matrix of NATURAL-space kernel inputs, one row per chain, and gets back the
+ * epoch-summed log-likelihood per chain and its gradient w.r.t. those inputs.
+ *
+ * Conventions
+ *  - All numbers are IEEE float64. `in` and `g_in` are column-major
+ *    [n_chains x n_in] with leading dimension `ld` (>= n_chains): element
+ *    (chain c, input k) is at in[c + k*ld]. This is Julia's native layout for
+ *    an N x n_in Matrix{Float64} and makes chain the coalesced index on device.
+ *  - Every entry point returns 0 on success, non-zero on error; the message is
+ *    in octo_last_error() (thread-local). No C++ exception crosses the ABI.
+ *  - Numerical invalidity is NOT an error: a chain whose inputs are non-finite
+ *    or have e outside [0,1), a <= 0, M <= 0 or plx <= 0 gets ll = -Inf and a
+ *    zero gradient row (reference: non-finite θ => -Inf, logdensitymodel.jl:120-124;
+ *    orbit ctor failure => -Inf, system.jl:214-221).
+ *  - The library never falls back to the CPU: without a CUDA device
+ *    octo_create fails with OCTO_ERR_CUDA.
+ *  - Entry points are re-entrant. Concurrent calls on one OctoCtx are allowed
+ *    (Pigeons calls the target from many threads, ext/OctofitterPigeonsExt:118);
+ *    each call leases a private stream + workspace from the context's pool.
+ */
+#ifndef OCTO_B200_H
+#define OCTO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCTO_ABI_VERSION 1
+#define OCTO_MAX_PLANETS 4
+
+/* error codes */
+#define OCTO_OK            0
+#define OCTO_ERR_ARG       1   /* bad argument / unsupported layout            */
+#define OCTO_ERR_CUDA      2   /* CUDA runtime error or no device              */
+#define OCTO_ERR_NCCL      3   /* NCCL error / NCCL not loadable               */
+#define OCTO_ERR_STATE     4   /* call sequence error (e.g. pt round w/o init) */
+
+/*
+ * Physical constants of PlanetOrbits.jl. The source of PlanetOrbits is not part
+ * of the reference tree, so the Julia glue injects the live values
+ * (PlanetOrbits.kepler_year_to_julian_day_conversion_factor, .year2day_julian,
+ * .rad2as, .pc2au, .au2m, .sec2year_julian, .mjup2msol_IAU; names confirmed by
+ * in-tree use: src/parameterizations.jl:28,62-63,215-216; src/Octofitter.jl:43).
+ * octo_default_constants() fills in the recollected defaults.
+ */
+typedef struct OctoConstants {
+    double kepler_year_days;  /* 365.2568983840419                         */
+    double year2day;          /* 365.25                                    */
+    double rad2as;            /* 206265                                    */
+    double pc2au;             /* 206265                                    */
+    double au2m;              /* 1.495978707e11                            */
+    double sec2year;          /* 1/31557600                                */
+    double mjup2msol;         /* 0.0009545942339693249                     */
+} OctoConstants;
+
+/* observation kinds */
+#define OCTO_KIND_ASTROM_RADEC   0  /* PlanetRelAstromObs, (ra,dec,σ_ra,σ_dec[,cor])     */
+#define OCTO_KIND_ASTROM_PASEP   1  /* PlanetRelAstromObs, (pa,sep,σ_pa,σ_sep[,cor])     */
+#define OCTO_KIND_RV_STAR_ABS    2  /* StarAbsoluteRVObs, gaussian_process = nothing      */
+#define OCTO_KIND_RV_STAR_MARGIN 3  /* MarginalizedStarAbsoluteRVObs                      */
+#define OCTO_KIND_RV_PLANET_REL  4  /* PlanetRelativeRVObs, gaussian_process = nothing    */
+
+/*
+ * One observation table (SoA, host pointers; copied at octo_create, not retained).
+ *   kind 0: y1=ra  y2=dec  s1=σ_ra s2=σ_dec  cor optional       [mas]
+ *   kind 1: y1=pa  y2=sep  s1=σ_pa s2=σ_sep  cor optional       [rad, mas]
+ *   kind 2,3,4: y1=rv s1=σ_rv; y2,s2,cor must be NULL            [m/s]
+ * Rows must already be in the order the reference holds them (the astrometry
+ * ctor sorts by epoch, relative-astrometry.jl:46-47).
+ * idx_*: column of the per-observation variable in the input matrix, or -1 for
+ * the reference default (jitter 0, platescale 1, northangle 0, offset 0;
+ * relative-astrometry.jl:170-172, rv-absolute.jl:139,181). Kind 3 requires
+ * idx_jitter >= 0 (rv-absolute-margin.jl:149 reads θ_obs.jitter unconditionally).
+ * Only the default trend_function (identically zero) is supported.
+ */
+typedef struct OctoObsBlock {
+    int32_t kind;
+    int32_t planet;        /* 0-based planet index for kinds 0,1,4; -1 for system-level kinds 2,3 */
+    int32_t n_epochs;
+    int32_t has_cor;
+    const double* epoch;
+    const double* y1;
+    const double* y2;
+    const double* s1;
+    const double* s2;
+    const double* cor;
+    int32_t idx_jitter;
+    int32_t idx_platescale;
+    int32_t idx_northangle;
+    int32_t idx_offset;
+} OctoObsBlock;
+
+/*
+ * Where each orbital element of each planet lives in the input matrix.
+ * Orbit kwargs are merge(θ_system, θ_planet) (system.jl:117), so plx and M are
+ * per planet (they usually point at the same system-level column).
+ * idx_mass = -1 means the planet has no `mass` variable: it contributes no
+ * reflex motion (relative-astrometry.jl:121-123); kinds 2/3 then fail at create
+ * (the reference would throw on θ_system.planets[i].mass, rv-absolute.jl:147).
+ */
+typedef struct OctoLayout {
+    int32_t n_planets;
+    int32_t n_in;
+    int32_t idx_plx [OCTO_MAX_PLANETS];
+    int32_t idx_a   [OCTO_MAX_PLANETS];
+    int32_t idx_e   [OCTO_MAX_PLANETS];
+    int32_t idx_i   [OCTO_MAX_PLANETS];
+    int32_t idx_w   [OCTO_MAX_PLANETS];   /* ω  argument of periastron      */
+    int32_t idx_W   [OCTO_MAX_PLANETS];   /* Ω  longitude of ascending node */
+    int32_t idx_tp  [OCTO_MAX_PLANETS];
+    int32_t idx_M   [OCTO_MAX_PLANETS];
+    int32_t idx_mass[OCTO_MAX_PLANETS];   /* Mjup, or -1 */
+} OctoLayout;
+
+typedef struct OctoCtx OctoCtx;
+
+void octo_default_constants(OctoConstants* out);
+int  octo_abi_version(void);
+
+/*
+ * Build a context: validates the layout, copies the observation tables to
+ * `device` (CUDA ordinal), precomputes per-epoch weights, sizes the launch.
+ * Replaces the code generation of make_ln_like (system.jl:21-242): the epoch
+ * list is the concatenation, in `blocks` order, of every table's epochs.
+ */
+int  octo_create(const OctoConstants* consts, const OctoLayout* layout,
+                 const OctoObsBlock* blocks, int32_t n_blocks, int32_t device,
+                 OctoCtx** out);
+void octo_destroy(OctoCtx* ctx);
+
+/* value only (K1v) — what ℓπcallback adds at logdensitymodel.jl:134; HOST buffers */
+int  octo_logp(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, double* ll);
+/* value + gradient w.r.t. the inputs (K1) — replaces the ForwardDiff pass over
+ * the epoch loop (logdensitymodel.jl:169-177); HOST buffers */
+int  octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld,
+                    double* ll, double* g_in);
+
+/* Same, DEVICE buffers on the context's device, enqueued on `stream`
+ * (a cudaStream_t; NULL = the legacy default stream). Asynchronous: the caller
+ * synchronises. g_in may be NULL for value only. */
+int  octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n_chains, int64_t ld,
+                           double* d_ll, double* d_g_in, void* stream);
+
+/* introspection */
+int32_t octo_n_in(const OctoCtx* ctx);
+int32_t octo_n_planets(const OctoCtx* ctx);
+int64_t octo_total_epochs(const OctoCtx* ctx);   /* E: length of the concatenated epoch list      */
+int32_t octo_device(const OctoCtx* ctx);
+int64_t octo_kernel_launches(const OctoCtx* ctx); /* kernels launched so far through this context */
+/* launch geometry chosen for a batch of n_chains: grid.x, grid.y, block, slice length */
+int  octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]);
+
+/*
+ * Parallel-tempering swap round (replaces the replica exchange Pigeons does over
+ * threads / MPI, ext/OctofitterPigeonsExt/OctofitterPigeonsExt.jl:76-128).
+ * Replicas are block-partitioned over `world` ranks (one process per GPU).
+ * Each replica contributes (ℓ_ref, ℓ_target); one ncclAllGather of
+ * n_replicas x 2 float64 per round; every rank then computes the same
+ * deterministic even/odd swap decisions and swaps β INDICES, not states.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId (rank 0: octo_pt_unique_id).
+ */
+int  octo_pt_unique_id(void* out128);
+int  octo_pt_init(OctoCtx* ctx, const void* nccl_unique_id, int32_t rank, int32_t world,
+                  int32_t n_replicas_local, uint64_t seed);
+/*
+ * d_ll_pair: DEVICE [n_replicas_local x 2] (ℓ_ref, ℓ_target) row-major for the local replicas.
+ * beta: HOST [n_replicas_total] ladder (β by chain index, ascending).
+ * chain_of_replica: HOST in/out [n_replicas_total] — which ladder index each replica holds.
+ * round: swap round counter (even rounds pair (0,1),(2,3).., odd rounds (1,2),(3,4)..).
+ * accepted: HOST out [n_replicas_total-1] 0/1 per adjacent pair (may be NULL).
+ */
+int  octo_pt_swap_round(OctoCtx* ctx, const double* d_ll_pair, const double* beta,
+                        int32_t* chain_of_replica, int64_t round, int32_t* accepted);
+void octo_pt_finalize(OctoCtx* ctx);
+
+const char* octo_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCTO_B200_H */

@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+Same names and argument meaning as the Julia types the path sits behind
+(src/variables.jl:468-594 `Planet`/`System`; src/likelihoods/relative-astrometry.jl:19-93
+`PlanetRelAstromObs`; OctofitterRadialVelocity/src/rv-*.jl; src/logdensitymodel.jl
+`LogDensityModel`), reduced to what the path needs: the observation tables, which natural-space
+variables exist, and where they sit in the kernel's input matrix.  Priors, bijectors, derived
+expressions and samplers stay with the caller (SURVEY.md §8b "split"): the caller passes
+NATURAL-space values of every variable.
+
+The compute is exclusively libocto_b200.so (hand-written sm_100a kernels).  Nothing here
+evaluates a likelihood on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _abi
+
+astrom_cols1 = ("epoch", "ra", "dec", "σ_ra", "σ_dec")
+astrom_cols3 = ("epoch", "pa", "sep", "σ_pa", "σ_sep")
+rv_cols = ("epoch", "rv", "σ_rv")
+_ALIASES = {"sigma_ra": "σ_ra", "sigma_dec": "σ_dec", "sigma_pa": "σ_pa", "sigma_sep": "σ_sep",
+            "sigma_rv": "σ_rv", "omega": "ω", "Omega": "Ω", "w": "ω", "W": "Ω"}
+_MJD_1950, _MJD_2050 = 33282.0, 69807.0
+
+
+class OctoError(RuntimeError):
+    pass
+
+
+def Table(rows=None, **cols):
+    """TypedTables-like constructor: Table(epoch=[...], ra=[...]) or Table([{...}, {...}])."""
+    if rows is not None:
+        if isinstance(rows, dict):
+            cols = dict(rows)
+        else:
+            keys = list(rows[0].keys())
+            cols = {k: [r[k] for r in rows] for k in keys}
+    out = {}
+    for k, v in cols.items():
+        out[_ALIASES.get(k, k)] = np.atleast_1d(np.asarray(v, dtype=np.float64)).copy()
+    return out
+
+
+def _check_table(table, name):
+    table = Table(table) if not all(isinstance(v, np.ndarray) for v in table.values()) else dict(table)
+    n = {len(v) for v in table.values()}
+    if len(n) > 1:
+        raise ValueError("The columns in the input data do not all have the same length")
+    ep = table.get("epoch")
+    if ep is not None and len(ep) and (np.any(ep >= _MJD_2050) or np.any(ep <= _MJD_1950)):
+        warnings.warn("The data you entered fell outside the range year 1950 to year 2050. "
+                      "The expected input format is MJD (modified julian date).")
+    return table
+
+
+class AbstractObs:
+    kind = -1
+    allowed_variables = ()
+
+    def _set_variables(self, variables):
+        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        for v in self.variables:
+            if v not in self.allowed_variables:
+                raise ValueError(f"{type(self).__name__} '{self.name}': variable '{v}' is not offloadable "
+                                 f"(supported: {self.allowed_variables}); keep such terms in the host model")
+
+
+class PlanetRelAstromObs(AbstractObs):
+    """Relative astrometry of a planet (relative-astrometry.jl:19-93).
+
+    Columns: epoch plus (ra, dec, σ_ra, σ_dec) or (pa, sep, σ_pa, σ_sep), optional cor.
+    Units: mas / rad.  The table is sorted by epoch, as the reference ctor does (:46-47).
+    variables: any of "jitter", "platescale", "northangle" that are sampled/defined.
+    """
+    allowed_variables = ("jitter", "platescale", "northangle")
+
+    def __init__(self, observations, *, name, variables=()):
+        self.name = str(name)
+        table = _check_table(observations, name)
+        c1 = set(astrom_cols1) <= set(table)
+        c3 = set(astrom_cols3) <= set(table)
+        if not (c1 or c3):
+            raise ValueError(f"Expected columns {astrom_cols1} or {astrom_cols3}")
+        ii = np.argsort(table["epoch"], kind="stable")
+        table = {k: v[ii] for k, v in table.items()}
+        if "pa" in table and "sep" in table:
+            self.kind = _abi.KIND_ASTROM_PASEP
+            if np.any(table["pa"] >= 2 * np.pi) or np.any(table["pa"] <= -2 * np.pi):
+                warnings.warn("The data you entered fell outside the range [-2pi, +2pi]. "
+                              "The expected input format is radians.")
+        else:
+            self.kind = _abi.KIND_ASTROM_RADEC
+        if "cor" in table and np.any(np.abs(table["cor"]) > 1 - 1e-5):
+            raise ValueError(f"Correlation values may not be well-specified: {table['cor']}")
+        self.table = table
+        self._set_variables(variables)
+
+    def _columns(self):
+        t = self.table
+        if self.kind == _abi.KIND_ASTROM_PASEP:
+            return t["epoch"], t["pa"], t["sep"], t["σ_pa"], t["σ_sep"], t.get("cor")
+        return t["epoch"], t["ra"], t["dec"], t["σ_ra"], t["σ_dec"], t.get("cor")
+
+
+PlanetRelAstromLikelihood = PlanetRelAstromObs
+
+
+class _RVObs(AbstractObs):
+    def __init__(self, observations, *, name, variables=None, trend_function=None, gaussian_process=None):
+        self.name = str(name)
+        if gaussian_process is not None:
+            raise ValueError("gaussian_process likelihoods are out of scope for the offloaded path "
+                             "(SURVEY.md §2: celerite GP branch stays in the reference)")
+        if trend_function is not None:
+            raise ValueError("only the default (zero) trend_function is supported by the offloaded path")
+        table = _check_table(observations, name)
+        if not set(rv_cols) <= set(table):
+            raise ValueError(f"Expected columns {rv_cols}")
+        self.table = table
+        self._set_variables(self.default_variables if variables is None else variables)
+
+    def _columns(self):
+        t = self.table
+        return t["epoch"], t["rv"], None, t["σ_rv"], None, None
+
+
+class StarAbsoluteRVObs(_RVObs):
+    """Absolute RV of the star, no GP (rv-absolute.jl:55-112, 135-204)."""
+    kind = _abi.KIND_RV_STAR_ABS
+    allowed_variables = ("offset", "jitter")
+    default_variables = ("offset", "jitter")      # rv-absolute.jl:74-79 default priors
+
+
+class MarginalizedStarAbsoluteRVObs(_RVObs):
+    """Absolute RV with the zero point marginalised analytically (rv-absolute-margin.jl:140-185)."""
+    kind = _abi.KIND_RV_STAR_MARGIN
+    allowed_variables = ("jitter",)
+    default_variables = ("jitter",)
+
+    def __init__(self, observations, *, name, variables=None, trend_function=None):
+        super().__init__(observations, name=name, variables=variables, trend_function=trend_function)
+        if "jitter" not in self.variables:
+            raise ValueError("MarginalizedStarAbsoluteRVObs requires a `jitter` variable")
+
+
+class PlanetRelativeRVObs(_RVObs):
+    """RV of a planet relative to its star, no GP (rv-relative.jl:121-211)."""
+    kind = _abi.KIND_RV_PLANET_REL
+    allowed_variables = ("offset", "jitter")
+    default_variables = ("jitter",)
+
+
+StarAbsoluteRVLikelihood = StarAbsoluteRVObs
+MarginalizedStarAbsoluteRVLikelihood = MarginalizedStarAbsoluteRVObs
+PlanetRelativeRVLikelihood = PlanetRelativeRVObs
+
+_ELEMS = ("a", "e", "i", "ω", "Ω", "tp", "M", "plx")
+
+
+class Planet:
+    """Planet(name=, basis=, variables=, observations=) — src/variables.jl:468-508.
+
+    variables: names of this planet's natural-space variables (e.g. "a","e","i","ω","Ω","tp","mass").
+    Only the Visual{KepOrbit} basis is offloaded.
+    """
+
+    def __init__(self, *, name, basis="Visual{KepOrbit}", variables, observations=()):
+        if basis not in ("Visual{KepOrbit}", "VisualKepOrbit"):
+            raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}}")
+        self.name = str(name)
+        self.basis = "Visual{KepOrbit}"
+        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        self.observations = list(observations)
+        for o in self.observations:
+            if o.kind in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN):
+                raise ValueError(f"{type(o).__name__} is a system-level observation")
+
+
+class System:
+    """System(name=, variables=, companions=, observations=) — src/variables.jl:544-594."""
+
+    def __init__(self, *, name, variables, companions, observations=()):
+        self.name = str(name)
+        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        self.planets = list(companions)
+        self.observations = list(observations)
+        names = [p.name for p in self.planets]
+        if len(set(names)) != len(names):
+            raise ValueError("planet names must be unique")
+        for o in self.observations:
+            if o.kind not in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN):
+                raise ValueError(f"{type(o).__name__} must be attached to a planet")
+
+
+def _normalizename(s):
+    # src/variables.jl:1068-1073: non-identifier characters become underscores
+    out = "".join(ch if (ch.isalnum() or ch == "_") else "_" for ch in s)
+    return out
+
+
+class ModelSpec:
+    """What make_ln_like (system.jl:21-110) derives from a System: the epoch tables in summation
+    order and the position of every variable in the kernel-input matrix.  Pure host bookkeeping.
+
+    `input_names` lists the kernel-input columns in the reference's parameter order: system
+    variables, system-observation variables, then per planet its variables followed by its
+    observations' variables (src/variables.jl:691-730).
+    Observation blocks are listed in the order the reference sums them: planet observations
+    first, then system observations (system.jl:223-236).
+    """
+
+    def __init__(self, system: System):
+        self.system = system
+        names = list(system.variables)
+        col = {n: k for k, n in enumerate(names)}
+        obs_cols = {}
+        for o in system.observations:
+            for v in o.variables:
+                key = f"{_normalizename(o.name)}.{v}"
+                obs_cols[(id(o), v)] = len(names)
+                names.append(key)
+        planets_layout = []
+        for p in system.planets:
+            pcol = {}
+            for v in p.variables:
+                pcol[v] = len(names)
+                names.append(f"{p.name}.{v}")
+            for o in p.observations:
+                for v in o.variables:
+                    obs_cols[(id(o), v)] = len(names)
+                    names.append(f"{p.name}.{_normalizename(o.name)}.{v}")
+            merged = dict(col)
+            merged.update(pcol)          # merge(θ_system, θ_planet): planet wins (system.jl:117)
+            missing = [e for e in _ELEMS if e not in merged]
+            if missing:
+                raise OctoError(f"planet {p.name}: missing orbital variables {missing} for Visual{{KepOrbit}}")
+            planets_layout.append({"plx": merged["plx"], "a": merged["a"], "e": merged["e"], "i": merged["i"],
+                                   "w": merged["ω"], "W": merged["Ω"], "tp": merged["tp"], "M": merged["M"],
+                                   "mass": pcol.get("mass", -1)})
+        self.input_names = tuple(names)
+        self.n_in = len(names)
+        blocks = []
+        for ip, p in enumerate(system.planets):
+            for o in p.observations:
+                blocks.append(self._block(o, ip, obs_cols))
+        for o in system.observations:
+            blocks.append(self._block(o, -1, obs_cols))
+        self.layout_dict = {"n_in": self.n_in, "planets": planets_layout}
+        self.block_dicts = blocks
+        self.packed = _abi.pack(self.layout_dict, blocks)
+        self.total_epochs = sum(len(b["epoch"]) for b in blocks)
+
+    def column(self, name):
+        return self.input_names.index(name)
+
+    @staticmethod
+    def _block(o, ip, obs_cols):
+        ep, y1, y2, s1, s2, cor = o._columns()
+        g = lambda v: obs_cols.get((id(o), v), -1)
+        return {"kind": o.kind, "planet": ip, "epoch": ep, "y1": y1, "y2": y2, "s1": s1, "s2": s2, "cor": cor,
+                "idx_jitter": g("jitter"), "idx_platescale": g("platescale"),
+                "idx_northangle": g("northangle"), "idx_offset": g("offset"), "name": o.name}
+
+
+class LogDensityModel:
+    """The sampler-facing surface for the offloaded terms (src/logdensitymodel.jl:5-24, 252-256),
+    backed by libocto_b200.so on one CUDA device."""
+
+    def __init__(self, system, *, device: int = 0, constants=None, lib=None):
+        self.spec = system if isinstance(system, ModelSpec) else ModelSpec(system)
+        self.system = self.spec.system
+        self.input_names = self.spec.input_names
+        self.D = self.n_in = self.spec.n_in
+        self.packed = self.spec.packed
+        self.constants = constants if constants is not None else _abi.default_constants()
+        self._lib = lib if lib is not None else _abi.load_library()
+        h = C.c_void_p()
+        rc = self._lib.octo_create(C.byref(self.constants), C.byref(self.packed.layout), self.packed.blocks,
+                                   self.packed.n_blocks, int(device), C.byref(h))
+        if rc != 0:
+            raise OctoError(f"octo_create failed ({rc}): {self._lib.octo_last_error().decode()}")
+        self._h = h
+        self.device = int(device)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.octo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- evaluation -------------------------------------------------------------------
+    @property
+    def total_epochs(self) -> int:
+        return int(self._lib.octo_total_epochs(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.octo_kernel_launches(self._h))
+
+    def launch_geometry(self, n_chains):
+        out = (C.c_int32 * 4)()
+        self._lib.octo_launch_geometry(self._h, int(n_chains), C.byref(out))
+        return tuple(out)
+
+    def _as_in(self, theta):
+        th = np.asarray(theta, dtype=np.float64)
+        single = th.ndim == 1
+        if single:
+            th = th[None, :]
+        if th.ndim != 2 or th.shape[1] != self.n_in:
+            raise ValueError(f"expected (n_chains, {self.n_in}) natural-space inputs, got {th.shape}")
+        return np.asfortranarray(th), single     # column-major [n_chains x n_in]: chain index fastest
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OctoError(f"libocto_b200 error {rc}: {self._lib.octo_last_error().decode()}")
+
+    def ln_like(self, theta):
+        """Epoch-summed log-likelihood per chain (value-only kernel K1v)."""
+        x, single = self._as_in(theta)
+        n = x.shape[0]
+        ll = np.empty(n)
+        self._check(self._lib.octo_logp(self._h, x.ctypes.data, n, n, ll.ctypes.data))
+        return ll[0] if single else ll
+
+    def ln_like_and_gradient(self, theta):
+        """(ll, ∂ll/∂inputs) per chain (fused kernel K1)."""
+        x, single = self._as_in(theta)
+        n = x.shape[0]
+        ll = np.empty(n)
+        g = np.empty((n, self.n_in), order="F")
+        self._check(self._lib.octo_logp_grad(self._h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data))
+        return (ll[0], g[0]) if single else (ll, g)
+
+    # LogDensityProblems-style names (src/logdensitymodel.jl:252-256)
+    logdensity = ln_like
+    logdensity_and_gradient = ln_like_and_gradient
+
+    def dimension(self):
+        return self.n_in
+
+    def __call__(self, theta):           # Pigeons calls the model (ext/OctofitterPigeonsExt:10-12)
+        return self.ln_like(theta)
+
+    def enqueue_device(self, d_in, n_chains, ld, d_ll, d_g, stream=0):
+        """Asynchronous launch on device-resident buffers (raw pointers, cudaStream_t handle)."""
+        self._check(self._lib.octo_logp_grad_device(self._h, int(d_in), int(n_chains), int(ld), int(d_ll),
+                                                    int(d_g) if d_g else None, int(stream) if stream else None))

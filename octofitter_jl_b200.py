@@ -1,0 +1,15 @@
+"""Loader: makes the package directory `octofitter.jl_b200/` importable as `octofitter_jl_b200`.
+
+`import octofitter_jl_b200 as octo` returns the package itself (this stub replaces its own
+entry in sys.modules with it).
+"""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "octofitter.jl_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,149 @@
+"""Independent 40+-digit restatement of the hot path in mpmath.  TEST INFRASTRUCTURE ONLY.
+
+Deliberately written along a different route from oracle/octo_oracle.hpp so the two can pin
+each other: Kepler's equation by Newton iteration at working precision (not Markley), positions
+through Thiele-Innes constants and (cosE - e, sqrt(1-e^2) sinE) (the algebra of
+src/parameterizations.jl:34-37, 337-353), radial velocity through cos/sin of the true anomaly
+from E, gradients by mpmath's high-order numerical differentiation at 60 digits.
+
+Used only by tests/golden/make_golden.py to produce the committed golden vectors.
+"""
+from __future__ import annotations
+
+import mpmath as mp
+
+mp.mp.dps = 60
+
+
+def _consts(c):
+    return {k: mp.mpf(v) for k, v in c.items()}
+
+
+def kepler_E(M, e):
+    M = M - 2 * mp.pi * mp.nint(M / (2 * mp.pi))
+    E = M + e * mp.sin(M) if e < mp.mpf("0.8") else mp.pi * mp.sign(M) if M != 0 else mp.mpf(0)
+    for _ in range(200):
+        dE = (E - e * mp.sin(E) - M) / (1 - e * mp.cos(E))
+        E -= dE
+        if abs(dE) < mp.mpf(10) ** (-mp.mp.dps + 5):
+            break
+    return E
+
+
+def planet_state(c, el, t):
+    """(ra [mas], dec [mas], rv [m/s]) of the planet relative to the star at epoch t."""
+    a, e, i, w, W, tp, M, plx = (el[k] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx"))
+    P_days = mp.sqrt(a ** 3 / M) * c["kepler_year_days"]
+    E = kepler_E(2 * mp.pi * (t - tp) / P_days, e)
+    s = mp.sqrt(1 - e * e)
+    X, Y = mp.cos(E) - e, s * mp.sin(E)
+    A = mp.cos(W) * mp.cos(w) - mp.sin(W) * mp.sin(w) * mp.cos(i)
+    B = mp.sin(W) * mp.cos(w) + mp.cos(W) * mp.sin(w) * mp.cos(i)
+    F = -mp.cos(W) * mp.sin(w) - mp.sin(W) * mp.cos(w) * mp.cos(i)
+    G = -mp.sin(W) * mp.sin(w) + mp.cos(W) * mp.cos(w) * mp.cos(i)
+    dist = 1000 / plx * c["pc2au"]
+    c2a = c["rad2as"] * 1000 / dist
+    ra = a * c2a * (X * B + Y * G)
+    dec = a * c2a * (X * A + Y * F)
+    D = 1 - e * mp.cos(E)
+    cosnu, sinnu = X / D, Y / D
+    P_yr = P_days / c["year2day"]
+    K = (2 * mp.pi * a / P_yr) / s * c["au2m"] * c["sec2year"] * mp.sin(i)
+    rv = K * (cosnu * mp.cos(w) - sinnu * mp.sin(w) + e * mp.cos(w))
+    return ra, dec, rv
+
+
+def _mvn2(s1, s2, cor, r1, r2):
+    det = s1 ** 2 * s2 ** 2 * (1 - cor ** 2)
+    maha = (r1 ** 2 / s1 ** 2 - 2 * cor * r1 * r2 / (s1 * s2) + r2 ** 2 / s2 ** 2) / (1 - cor ** 2)
+    return -mp.log(2 * mp.pi) - mp.log(det) / 2 - maha / 2
+
+
+def ln_like(consts, layout, blocks, x):
+    """Scalar log-likelihood for one chain.  layout/blocks are the dictionaries of
+    octofitter.jl_b200._abi.pack; x is a sequence of mp numbers (natural-space inputs)."""
+    c = _consts(consts)
+    x = [mp.mpf(v) for v in x]
+    els = []
+    for p in layout["planets"]:
+        el = {k: x[p[k]] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx")}
+        el["mu"] = x[p["mass"]] * c["mjup2msol"] / el["M"] if p.get("mass", -1) >= 0 else None
+        els.append(el)
+    ll = mp.mpf(0)
+    two_pi = 2 * mp.pi
+    for b in blocks:
+        kind = b["kind"]
+        jit = x[b["idx_jitter"]] if b.get("idx_jitter", -1) >= 0 else mp.mpf(0)
+        off = x[b["idx_offset"]] if b.get("idx_offset", -1) >= 0 else mp.mpf(0)
+        n = len(b["epoch"])
+        if kind in (0, 1):
+            ps = x[b["idx_platescale"]] if b.get("idx_platescale", -1) >= 0 else mp.mpf(1)
+            na = x[b["idx_northangle"]] if b.get("idx_northangle", -1) >= 0 else mp.mpf(0)
+            ip = b["planet"]
+            for k in range(n):
+                t = mp.mpf(float(b["epoch"][k]))
+                ra, dec, _ = planet_state(c, els[ip], t)
+                for j, el in enumerate(els):
+                    if j != ip and el["a"] < els[ip]["a"] and el["mu"] is not None:
+                        rj, dj, _ = planet_state(c, el, t)
+                        ra += el["mu"] * rj          # minus (star reflex = -mu * planet offset)
+                        dec += el["mu"] * dj
+                y1, y2 = mp.mpf(float(b["y1"][k])), mp.mpf(float(b["y2"][k]))
+                s1, s2 = mp.mpf(float(b["s1"][k])), mp.mpf(float(b["s2"][k]))
+                cor = mp.mpf(float(b["cor"][k])) if b.get("cor") is not None else mp.mpf(0)
+                if kind == 1:
+                    rho = mp.hypot(ra, dec)
+                    pa = mp.atan2(ra, dec)
+                    d = (y1 + na) - pa
+                    d = d - two_pi * mp.nint(d / two_pi)        # wrapped to [-pi, pi]
+                    r1, r2 = d, y2 * ps - rho
+                else:
+                    # data rotated by -northangle (East through North) and scaled by platescale
+                    ra_d = ps * (y1 * mp.cos(na) + y2 * mp.sin(na))
+                    dec_d = ps * (y2 * mp.cos(na) - y1 * mp.sin(na))
+                    r1, r2 = ra_d - ra, dec_d - dec
+                s1, s2 = mp.sqrt(s1 ** 2 + jit ** 2), mp.sqrt(s2 ** 2 + jit ** 2)
+                ll += _mvn2(s1, s2, cor, r1, r2)
+        elif kind in (2, 3):
+            A = Bq = Cq = mp.mpf(0)
+            for k in range(n):
+                t = mp.mpf(float(b["epoch"][k]))
+                m = mp.mpf(0) if kind == 3 else off
+                for el in els:
+                    m += -el["mu"] * planet_state(c, el, t)[2]
+                r = mp.mpf(float(b["y1"][k])) - m
+                var = mp.mpf(float(b["s1"][k])) ** 2 + jit ** 2
+                if kind == 3:
+                    A += 1 / var; Bq -= 2 * r / var; Cq += r * r / var
+                    ll -= mp.log(two_pi * var)
+                else:
+                    ll += -(mp.log(two_pi) + mp.log(var) + r * r / var) / 2
+            if kind == 3:
+                ll -= -Bq ** 2 / (4 * A) + Cq + mp.log(A)
+        elif kind == 4:
+            ip = b["planet"]
+            for k in range(n):
+                t = mp.mpf(float(b["epoch"][k]))
+                m = off + planet_state(c, els[ip], t)[2]
+                for j, el in enumerate(els):
+                    if j != ip and el["a"] < els[ip]["a"] and el["mu"] is not None:
+                        m += -el["mu"] * planet_state(c, el, t)[2]
+                r = mp.mpf(float(b["y1"][k])) - m
+                var = mp.mpf(float(b["s1"][k])) ** 2 + jit ** 2
+                ll += -(mp.log(two_pi) + mp.log(var) + r * r / var) / 2
+        else:
+            raise ValueError(kind)
+    return ll
+
+
+def ln_like_grad(consts, layout, blocks, x):
+    x = [mp.mpf(v) for v in x]
+    f0 = ln_like(consts, layout, blocks, x)
+    g = []
+    for k in range(len(x)):
+        def f(v, k=k):
+            y = list(x); y[k] = v
+            return ln_like(consts, layout, blocks, y)
+        h = max(abs(x[k]), mp.mpf(1)) * mp.mpf(10) ** (-18)
+        g.append((f(x[k] + h) - f(x[k] - h)) / (2 * h))      # central difference, error O(h^2) ~ 1e-36
+    return f0, g
