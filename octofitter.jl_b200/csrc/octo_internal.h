@@ -1,0 +1,74 @@
+// octo_internal.h — structures shared by the C-ABI shim (octo_shim.cu) and the kernels
+// (octo_kernels.cu).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/octo_b200.h"
+
+#define OCTO_MAX_BLOCKS 24        // observation tables per model
+#define OCTO_WARPS 8              // warps per CTA: each warp owns one contiguous epoch range
+#define OCTO_LANES 32             // lanes = chains of one chain group
+#define OCTO_MIN_SLICE 4          // fewest epochs worth giving a warp
+
+// Per chain*planet constants staged in shared memory by the prologue ([slot][lane] doubles).
+enum PlanetConst {
+    PC_nd = 0,   // mean motion [rad/day]
+    PC_tp, PC_e, PC_ome /*1-e*/, PC_ca1 /*Markley alpha slope*/, PC_s /*sqrt(1-e^2)*/,
+    PC_Bh, PC_Gs, PC_Ah, PC_Fs,       // scaled Thiele-Innes: ra = X*Bh + sinE*Gs, dec = X*Ah + sinE*Fs [mas]
+    PC_Pc, PC_Ps,                     // rv = (Pc cosE - Ps sinE)/(1 - e cosE)  [m/s]
+    PC_mu,                            // mass*mjup2msol/M, 0 when the planet has no mass variable
+    PC_a,
+    // epilogue only
+    PC_sinW, PC_cosW, PC_sinw, PC_cosw, PC_sini, PC_cosi, PC_M, PC_plx, PC_sc /*a*c2a*/, PC_c2a,
+    PC_K /*RV semi-amplitude*/, PC_Kb /*K / sin i*/,
+    PC_A, PC_B, PC_F, PC_G,
+    PC_COUNT
+};
+
+// Raw (pre chain-rule) accumulators per planet: sums over epochs that the epilogue maps to
+// gradients w.r.t. (a, e, i, ω, Ω, tp, M, plx, mass).
+enum PlanetAcc { PA_Bh = 0, PA_Gs, PA_Ah, PA_Fs, PA_Pc, PA_Ps, PA_e, PA_S0, PA_S1, PA_mu, PA_COUNT };
+
+// extra accumulators of one marginalised-RV table (rv-absolute-margin.jl:161-181)
+enum MarginAcc { MA_A = 0, MA_S1, MA_C, MA_LG, MA_R2, MA_R1, MA_Q, MA_COUNT };   // then 5 V-slots per planet
+enum { MV_Pc = 0, MV_Ps, MV_e, MV_S0, MV_S1, MV_mu, MV_COUNT };
+
+struct DevBlock {
+    int32_t kind, planet, start, n;          // epoch range [start, start+n) in the concatenated tables
+    int32_t has_cor, jit;                     // jit: jitter is an input column (per-pair variance path)
+    int32_t idx_jitter, idx_platescale, idx_northangle, idx_offset;
+    int32_t slot_jitter, slot_platescale, slot_northangle, slot_offset;   // accumulator slots (or -1)
+    int32_t slot_margin;                      // first of the margin accumulators (kind 3) or -1
+    int32_t pad;
+};
+
+struct DevModel {
+    OctoConstants c;
+    double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
+    double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
+    int32_t n_planets, n_in, n_blocks, n_acc;
+    int64_t n_epochs;
+    int32_t idx_plx[OCTO_MAX_PLANETS], idx_a[OCTO_MAX_PLANETS], idx_e[OCTO_MAX_PLANETS], idx_i[OCTO_MAX_PLANETS],
+            idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],
+            idx_mass[OCTO_MAX_PLANETS];
+    DevBlock blocks[OCTO_MAX_BLOCKS];
+    // device tables, length n_epochs each (RV tables use t, y1, c1 only)
+    const double* t;
+    const double* y1;
+    const double* y2;
+    const double* c1;     // astrometry: w11 (no jitter) | σ1² (jitter);  RV: 1/σ² | σ²
+    const double* c2;     // astrometry: w12 | σ2²
+    const double* c3;     // astrometry: w22 | cor
+};
+
+// slot 0 = ll; planets follow
+__host__ __device__ inline int slot_planet(int p, int a) { return 1 + p * PA_COUNT + a; }
+
+struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
+
+// kernels (octo_kernels.cu)
+cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
+                        int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
+                        unsigned int* d_tickets, cudaStream_t stream);
+size_t octo_smem_bytes(const DevModel& m);
+cudaError_t octo_kernels_init(size_t smem_bytes);

@@ -1,0 +1,624 @@
+// octo_kernels.cu — the fused sm_100a kernel of the hot path.
+//
+// One launch evaluates, for every (chain, epoch) pair of a batch:
+//   Kepler solve (Markley 1995, branch-uniform, non-iterative)      ref a4/a5: PlanetOrbits orbitsolve + kepler_solver
+//   sky-plane ΔRA/ΔDec [mas] and radial velocity [m/s]              ref a6/a7: raoff/decoff/radvel
+//   Gaussian log-likelihood terms of the five observation kinds     ref a9-a12: relative-astrometry.jl:166-253, rv-*.jl
+//   the analytic adjoint w.r.t. the orbital elements / obs variables ref a13: replaces the ForwardDiff pass
+// and reduces over epochs to one ll and one gradient row per chain.
+//
+// Mapping (all FP64, no tensor cores — the work is transcendental/irregular, not a contraction):
+//   lane      -> chain of a 32-chain group (chain is the fastest index of `in`, so loads/stores coalesce)
+//   warp      -> one contiguous range of the concatenated epoch list; epoch data are warp-uniform
+//                (one broadcast load serves 32 pairs) and the observation kind never diverges in a warp
+//   CTA       -> 8 warps = 8 epoch ranges of the same chain group; per-chain constants are computed once
+//                per CTA by the prologue and staged in shared memory
+//   grid      -> (chain groups) x (epoch splits); partial accumulators of the splits are combined in a fixed
+//                order by the last CTA to finish (ticket per chain group) => run-to-run bit-reproducible
+//   registers -> per-segment raw accumulators; folded into per-warp shared-memory slots at segment end
+//   epilogue  -> one lane per chain maps the raw sums to ∂ll/∂(inputs) by the chain rule, writes coalesced rows
+#include "octo_internal.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int W = OCTO_WARPS;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.283185307179586477;
+constexpr double kInvTwoPi = 0.15915494309189533577;
+// 2π split for a 3-term Cody-Waite reduction (33 + 33 + 53 bits): MA - k*2π is exact to < 1e-30*|k|
+constexpr double kTwoPi1 = 0x1.921fb54400000p+2;
+constexpr double kTwoPi2 = 0x1.0b4611a600000p-32;
+constexpr double kTwoPi3 = 0x1.3198a2e037073p-67;
+constexpr double kLog2Pi = 1.8378770664093454836;
+// Markley eq. 20: alpha = kA0 + ca1 * (pi - |M|),  ca1 = 1.6 pi / ((pi^2 - 6)(1 + e))
+constexpr double kA0 = 3.0 * kPi * kPi / (kPi * kPi - 6.0);
+constexpr double kA1 = 1.6 * kPi / (kPi * kPi - 6.0);
+
+struct Orb { double nd, tp, e, ome, ca1; };
+
+// ---------------------------------------------------------------------------------------------
+// rem2pi (round to nearest) + Markley's starter + one fifth-order correction; returns sinE, cosE.
+// sin/cos of E = E1 + d5 come from rotating sincos(E1) by d5 (|d5| < 4.4e-4 over the whole
+// domain, so three Taylor terms are exact to 1e-19): one sincos per solve instead of two.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt, double& sE, double& cE) {
+    dt = t - o.tp;
+    const double MA = o.nd * dt;
+    const double k = rint(MA * kInvTwoPi);
+    double M = fma(-k, kTwoPi1, MA);
+    M = fma(-k, kTwoPi2, M);
+    M = fma(-k, kTwoPi3, M);
+    const double alpha = fma(o.ca1, kPi - fabs(M), kA0);          // eq 20
+    const double d = fma(alpha, o.e, 3.0 * o.ome);                 // eq 5
+    const double M2 = M * M;
+    const double ad = alpha * d;
+    const double q = fma(2.0 * ad, o.ome, -M2);                    // eq 9
+    const double r = M * fma(3.0 * ad, d - o.ome, M2);             // eq 10  (d - 1 + e = d - (1 - e))
+    const double q2 = q * q;
+    const double tt = fabs(r) + sqrt(fma(q2, q, r * r));
+    const double w = cbrt(tt * tt);                                // eq 14
+    const double den = fma(w, w + q, q2);
+    const double E1 = fma(M, den, 2.0 * r * w) / (den * d);        // eq 15
+    double s1, c1;
+    sincos(E1, &s1, &c1);
+    const double f2 = o.e * s1, f3 = o.e * c1;                     // eqs 26, 27
+    const double f0 = (E1 - M) - f2;                               // eq 21
+    const double f1 = 1.0 - f3;                                    // eq 25
+    const double d3 = -f0 / (f1 - f0 * f2 / (2.0 * f1));           // eq 22
+    const double d4 = -f0 / fma(d3 * d3, f3 * (1.0 / 6.0), fma(0.5 * f2, d3, f1));                       // eq 23
+    const double d42 = d4 * d4;
+    const double d5 = -f0 / (fma(d42, f3 * (1.0 / 6.0), fma(0.5 * f2, d4, f1)) - d42 * d4 * f2 * (1.0 / 24.0));  // eqs 24, 28
+    const double x2 = d5 * d5;
+    const double sd = d5 * fma(x2, -1.0 / 6.0, 1.0);
+    const double cd = fma(x2, fma(x2, 1.0 / 24.0, -0.5), 1.0);
+    sE = fma(s1, cd, c1 * sd);
+    cE = fma(c1, cd, -s1 * sd);
+}
+
+__device__ __forceinline__ Orb load_orb(const double* sc, int lane) {
+    Orb o;
+    o.nd = sc[PC_nd * 32 + lane]; o.tp = sc[PC_tp * 32 + lane]; o.e = sc[PC_e * 32 + lane];
+    o.ome = sc[PC_ome * 32 + lane]; o.ca1 = sc[PC_ca1 * 32 + lane];
+    return o;
+}
+
+__device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double v) { acc[slot * 32 + lane] += v; }
+
+// ---------------------------------------------------------------------------------------------
+// Astrometry segment (kinds 0, 1): epochs [k0, k1) of table B for this warp's 32 chains.
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD, int NPT>
+__device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+                                        double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
+    const int ip = B.planet;
+    const bool pasep = (B.kind == OCTO_KIND_ASTROM_PASEP);
+    // involved planets: the observed one, then interior companions with a mass (relative-astrometry.jl:117-133)
+    int pj[NPT]; double f[NPT]; Orb orb[NPT]; double Bh[NPT], Gs[NPT], Ah[NPT], Fs[NPT];
+    int ni = 1;
+    pj[0] = ip; f[0] = 1.0;
+    const double a_ip = s_const[(ip * PC_COUNT + PC_a) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        if (NPT > 1 && j < m.n_planets && j != ip && m.idx_mass[j] >= 0) {
+            const double* sc = s_const + j * PC_COUNT * 32;
+            const bool inner = sc[PC_a * 32 + lane] < a_ip;
+            if (__any_sync(0xffffffffu, inner)) {          // warp-uniform: skip the solve if no chain needs it
+#pragma unroll
+                for (int u = 1; u < NPT; ++u) if (u == ni) { pj[u] = j; f[u] = inner ? sc[PC_mu * 32 + lane] : 0.0; }
+                ++ni;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) if (u < ni) {
+        const double* sc = s_const + pj[u] * PC_COUNT * 32;
+        orb[u] = load_orb(sc, lane);
+        Bh[u] = sc[PC_Bh * 32 + lane]; Gs[u] = sc[PC_Gs * 32 + lane];
+        Ah[u] = sc[PC_Ah * 32 + lane]; Fs[u] = sc[PC_Fs * 32 + lane];
+    }
+    const double jit = B.idx_jitter >= 0 ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
+    const double ps = B.idx_platescale >= 0 ? in[c + (int64_t)B.idx_platescale * ld] : 1.0;
+    const double na = B.idx_northangle >= 0 ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
+    const bool rot = (B.idx_platescale >= 0) || (B.idx_northangle >= 0);
+    double sna = 0.0, cna = 1.0;
+    if (rot && !pasep) sincos(na, &sna, &cna);
+    const double j2 = jit * jit;
+
+    double ll = 0.0, g_jit = 0.0, g_ps = 0.0, g_na = 0.0;
+    double L[NPT][7];
+#pragma unroll
+    for (int u = 0; u < NPT; ++u)
+#pragma unroll
+        for (int a = 0; a < 7; ++a) L[u][a] = 0.0;
+
+    for (int k = k0; k < k1; ++k) {
+        const double t = m.t[k], y1 = m.y1[k], y2 = m.y2[k];
+        const double e1 = m.c1[k], e2 = m.c2[k], e3 = m.c3[k];
+        double sE[NPT], cE[NPT], dt[NPT];
+        double ra = 0.0, dec = 0.0;
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) if (u < ni) {
+            kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
+            const double X = cE[u] - orb[u].e;
+            const double ra_u = fma(X, Bh[u], sE[u] * Gs[u]);
+            const double dec_u = fma(X, Ah[u], sE[u] * Fs[u]);
+            if (u == 0) { ra = ra_u; dec = dec_u; } else { ra = fma(f[u], ra_u, ra); dec = fma(f[u], dec_u, dec); }
+        }
+        double r1, r2, rho = 0.0, irho = 0.0, ra_d = y1, dec_d = y2;
+        if (pasep) {
+            rho = sqrt(fma(ra, ra, dec * dec));
+            irho = 1.0 / rho;
+            const double pa = atan2(ra, dec);
+            double pd = fmod((y1 + na) - pa + kPi, kTwoPi) - kPi;      // Julia `%` == fmod
+            if (pd < -kPi) pd += kTwoPi;
+            r1 = pd;
+            r2 = fma(y2, ps, -rho);
+        } else {
+            if (rot) {   // data rotated by -northangle and scaled (relative-astrometry.jl:209-213)
+                ra_d = ps * fma(y1, cna, y2 * sna);
+                dec_d = ps * fma(y2, cna, -y1 * sna);
+            }
+            r1 = ra_d - ra;
+            r2 = dec_d - dec;
+        }
+        double w11, w12, w22, iv1 = 0.0, iv2 = 0.0;
+        if (!B.jit) { w11 = e1; w12 = e2; w22 = e3; }
+        else {
+            const double v1 = e1 + j2, v2 = e2 + j2;
+            iv1 = 1.0 / v1; iv2 = 1.0 / v2;
+            double iom = 1.0, lom = 0.0;
+            w12 = 0.0;
+            if (B.has_cor) {
+                const double om = fma(-e3, e3, 1.0);
+                iom = 1.0 / om; lom = log(om);
+                w12 = -e3 * sqrt(iv1 * iv2) * iom;
+            }
+            w11 = iv1 * iom; w22 = iv2 * iom;
+            ll -= kLog2Pi + 0.5 * (log(v1 * v2) + lom);
+        }
+        const double q1 = fma(w11, r1, w12 * r2), q2 = fma(w12, r1, w22 * r2);
+        ll -= 0.5 * fma(r1, q1, r2 * q2);
+        if (GRAD) {
+            double gr, gd;
+            if (pasep) {
+                const double a1 = q1 * irho * irho, a2 = q2 * irho;
+                gr = fma(a1, dec, a2 * ra);
+                gd = fma(-a1, ra, a2 * dec);
+                g_na -= q1;
+                g_ps -= q2 * y2;
+            } else {
+                gr = q1; gd = q2;
+                if (rot) {
+                    g_ps -= fma(q1, ra_d, q2 * dec_d);
+                    g_na += fma(q2, ra_d, -q1 * dec_d);
+                }
+            }
+            if (B.jit) g_jit += fma(fma(r1, q1, -1.0), iv1, fma(r2, q2, -1.0) * iv2);
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) if (u < ni) {
+                const double X = cE[u] - orb[u].e;
+                const double rD = 1.0 / fma(-orb[u].e, cE[u], 1.0);
+                L[u][0] = fma(gr, X, L[u][0]);
+                L[u][1] = fma(gr, sE[u], L[u][1]);
+                L[u][2] = fma(gd, X, L[u][2]);
+                L[u][3] = fma(gd, sE[u], L[u][3]);
+                const double gX = fma(gr, Bh[u], gd * Ah[u]);
+                const double gS = fma(gr, Gs[u], gd * Fs[u]);
+                const double gM = fma(cE[u], gS, -sE[u] * gX) * rD;
+                L[u][4] += fma(gM, sE[u], -gX);
+                L[u][5] += gM;
+                L[u][6] = fma(gM, dt[u], L[u][6]);
+            }
+        }
+    }
+    acc_add(acc, 0, lane, ll);
+    if (GRAD) {
+        if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
+        if (B.slot_platescale >= 0) acc_add(acc, B.slot_platescale, lane, pasep ? g_ps : g_ps / ps);
+        if (B.slot_northangle >= 0) acc_add(acc, B.slot_northangle, lane, g_na);
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) if (u < ni) {
+            const int p = pj[u];
+            const double fu = f[u];
+            acc_add(acc, slot_planet(p, PA_Bh), lane, fu * L[u][0]);
+            acc_add(acc, slot_planet(p, PA_Gs), lane, fu * L[u][1]);
+            acc_add(acc, slot_planet(p, PA_Ah), lane, fu * L[u][2]);
+            acc_add(acc, slot_planet(p, PA_Fs), lane, fu * L[u][3]);
+            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][4]);
+            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][5]);
+            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][6]);
+            if (u > 0) {   // d f / d mu = [a_j < a_i]
+                const double ind = (s_const[(p * PC_COUNT + PC_a) * 32 + lane] < a_ip) ? 1.0 : 0.0;
+                const double gf = fma(Bh[u], L[u][0], fma(Gs[u], L[u][1], fma(Ah[u], L[u][2], Fs[u] * L[u][3])));
+                acc_add(acc, slot_planet(p, PA_mu), lane, ind * gf);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radial-velocity segment (kinds 2, 3, 4).
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD, int NPT>
+__device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+                                    double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
+    const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
+    const bool margin = (B.kind == OCTO_KIND_RV_STAR_MARGIN);
+    int pj[NPT]; double f[NPT], dmu[NPT]; Orb orb[NPT]; double Pc[NPT], Ps[NPT];
+    int ni = 0;
+    if (star) {   // every planet, reflex of the star: -mu * radvel (rv-absolute.jl:145-154)
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) if (j < m.n_planets) {
+            pj[j] = j; f[j] = -s_const[(j * PC_COUNT + PC_mu) * 32 + lane]; dmu[j] = -1.0; ni = j + 1;
+        }
+    } else {      // the planet itself, plus interior companions with a mass (rv-relative.jl:143-160)
+        const int ip = B.planet;
+        pj[0] = ip; f[0] = 1.0; dmu[0] = 0.0; ni = 1;
+        const double a_ip = s_const[(ip * PC_COUNT + PC_a) * 32 + lane];
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            if (NPT > 1 && j < m.n_planets && j != ip && m.idx_mass[j] >= 0) {
+                const double* sc = s_const + j * PC_COUNT * 32;
+                const bool inner = sc[PC_a * 32 + lane] < a_ip;
+                if (__any_sync(0xffffffffu, inner)) {
+#pragma unroll
+                    for (int u = 1; u < NPT; ++u) if (u == ni) {
+                        pj[u] = j; f[u] = inner ? -sc[PC_mu * 32 + lane] : 0.0; dmu[u] = inner ? -1.0 : 0.0;
+                    }
+                    ++ni;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) if (u < ni) {
+        const double* sc = s_const + pj[u] * PC_COUNT * 32;
+        orb[u] = load_orb(sc, lane);
+        Pc[u] = sc[PC_Pc * 32 + lane]; Ps[u] = sc[PC_Ps * 32 + lane];
+    }
+    const double jit = B.idx_jitter >= 0 ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
+    const double off = (B.idx_offset >= 0 && !margin) ? in[c + (int64_t)B.idx_offset * ld] : 0.0;
+    const double j2 = jit * jit;
+
+    double ll = 0.0, g_jit = 0.0, g_off = 0.0;
+    double mA = 0.0, mS1 = 0.0, mC = 0.0, mLG = 0.0, mR2 = 0.0, mR1 = 0.0, mQ = 0.0;
+    double L[NPT][5], V[NPT][5];
+#pragma unroll
+    for (int u = 0; u < NPT; ++u)
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; V[u][a] = 0.0; }
+
+    for (int k = k0; k < k1; ++k) {
+        const double t = m.t[k], y = m.y1[k], e1 = m.c1[k];
+        double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
+        double model = off;
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) if (u < ni) {
+            kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
+            rD[u] = 1.0 / fma(-orb[u].e, cE[u], 1.0);
+            rv[u] = fma(Pc[u], cE[u], -Ps[u] * sE[u]) * rD[u];
+            model = fma(f[u], rv[u], model);
+        }
+        const double r = y - model;
+        double iv;
+        if (!B.jit) iv = e1;                     // 1/σ² precomputed; normalisation is in const_ll
+        else {
+            const double var = e1 + j2;
+            iv = 1.0 / var;
+            if (margin) mLG += log(kTwoPi * var);
+            else ll -= 0.5 * (kLog2Pi + log(var));
+        }
+        const double riv = r * iv;
+        double g;                                 // d ll / d model
+        if (margin) {
+            mA += iv; mS1 += riv; mC = fma(r, riv, mC);
+            mR2 = fma(riv, riv, mR2); mR1 = fma(riv, iv, mR1); mQ = fma(iv, iv, mQ);
+            g = 2.0 * riv;
+        } else {
+            ll -= 0.5 * r * riv;
+            g = riv;
+            if (GRAD) { g_off += g; if (B.jit) g_jit += fma(r, riv, -1.0) * iv; }
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) if (u < ni) {
+                // d rv / d(Pc, Ps, e|E, E)
+                const double dPc = cE[u] * rD[u], dPs = -sE[u] * rD[u];
+                const double dE = -fma(Pc[u], sE[u], Ps[u] * cE[u]) * rD[u] - rv[u] * orb[u].e * sE[u] * rD[u];
+                const double dM = dE * rD[u];
+                const double de = fma(rv[u], dPc, dM * sE[u]);
+                L[u][0] = fma(g, dPc, L[u][0]); L[u][1] = fma(g, dPs, L[u][1]);
+                L[u][2] = fma(g, de, L[u][2]);  L[u][3] = fma(g, dM, L[u][3]);
+                L[u][4] = fma(g * dM, dt[u], L[u][4]);
+                if (margin) {
+                    V[u][0] = fma(iv, dPc, V[u][0]); V[u][1] = fma(iv, dPs, V[u][1]);
+                    V[u][2] = fma(iv, de, V[u][2]);  V[u][3] = fma(iv, dM, V[u][3]);
+                    V[u][4] = fma(iv * dM, dt[u], V[u][4]);
+                }
+            }
+        }
+    }
+    if (margin) {
+        const int s0 = B.slot_margin;
+        acc_add(acc, s0 + MA_A, lane, mA);   acc_add(acc, s0 + MA_S1, lane, mS1); acc_add(acc, s0 + MA_C, lane, mC);
+        acc_add(acc, s0 + MA_LG, lane, mLG); acc_add(acc, s0 + MA_R2, lane, mR2); acc_add(acc, s0 + MA_R1, lane, mR1);
+        acc_add(acc, s0 + MA_Q, lane, mQ);
+    } else {
+        acc_add(acc, 0, lane, ll);
+    }
+    if (GRAD) {
+        if (!margin) {
+            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
+            if (B.slot_offset >= 0) acc_add(acc, B.slot_offset, lane, g_off);
+        }
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) if (u < ni) {
+            const int p = pj[u];
+            const double fu = f[u];
+            acc_add(acc, slot_planet(p, PA_Pc), lane, fu * L[u][0]);
+            acc_add(acc, slot_planet(p, PA_Ps), lane, fu * L[u][1]);
+            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][2]);
+            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][3]);
+            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][4]);
+            if (dmu[u] != 0.0) acc_add(acc, slot_planet(p, PA_mu), lane, dmu[u] * fma(Pc[u], L[u][0], Ps[u] * L[u][1]));
+            if (margin) {
+                const int v0 = B.slot_margin + MA_COUNT + p * MV_COUNT;
+                acc_add(acc, v0 + MV_Pc, lane, fu * V[u][0]); acc_add(acc, v0 + MV_Ps, lane, fu * V[u][1]);
+                acc_add(acc, v0 + MV_e, lane, fu * V[u][2]);  acc_add(acc, v0 + MV_S0, lane, fu * V[u][3]);
+                acc_add(acc, v0 + MV_S1, lane, fu * V[u][4]);
+                acc_add(acc, v0 + MV_mu, lane, dmu[u] * fma(Pc[u], V[u][0], Ps[u] * V[u][1]));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prologue: per chain*planet constants (ref a3: KepOrbit / Visual ctor caches) -> shared memory.
+// Returns whether the planet's elements are valid for this chain.
+// ---------------------------------------------------------------------------------------------
+__device__ bool planet_prologue(const DevModel& m, int p, const double* __restrict__ in, int64_t c, int64_t ld,
+                                double* sc, int lane) {
+    double a = in[c + (int64_t)m.idx_a[p] * ld], e = in[c + (int64_t)m.idx_e[p] * ld];
+    double inc = in[c + (int64_t)m.idx_i[p] * ld], w = in[c + (int64_t)m.idx_w[p] * ld];
+    double Wn = in[c + (int64_t)m.idx_W[p] * ld], tp = in[c + (int64_t)m.idx_tp[p] * ld];
+    double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
+    double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
+    const bool fin = isfinite(a) && isfinite(e) && isfinite(inc) && isfinite(w) && isfinite(Wn) && isfinite(tp) &&
+                     isfinite(M) && isfinite(plx) && isfinite(mass);
+    const bool ok = fin && (e >= 0.0) && (e < 1.0) && (a > 0.0) && (M > 0.0) && (plx > 0.0);
+    if (!ok) { a = 1.0; e = 0.1; inc = 0.5; w = 0.0; Wn = 0.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
+    const double s2 = fma(-e, e, 1.0), s = sqrt(s2);
+    const double period_days = sqrt(a * a * a / M) * m.c.kepler_year_days;
+    const double nd = kTwoPi / period_days;
+    const double dist = 1000.0 / plx * m.c.pc2au;
+    const double c2a = m.c.rad2as * 1e3 / dist;
+    const double scl = a * c2a;
+    double si, ci, sw, cw, sW, cW;
+    sincos(inc, &si, &ci); sincos(w, &sw, &cw); sincos(Wn, &sW, &cW);
+    const double A = cW * cw - sW * sw * ci, Bc = sW * cw + cW * sw * ci;
+    const double F = -cW * sw - sW * cw * ci, G = -sW * sw + cW * cw * ci;
+    const double Kb = m.kappa * sqrt(M / a) / s;      // K / sin i
+    const double K = Kb * si;
+    sc[PC_nd * 32 + lane] = nd;       sc[PC_tp * 32 + lane] = tp;   sc[PC_e * 32 + lane] = e;
+    sc[PC_ome * 32 + lane] = 1.0 - e; sc[PC_ca1 * 32 + lane] = kA1 / (1.0 + e); sc[PC_s * 32 + lane] = s;
+    sc[PC_Bh * 32 + lane] = scl * Bc; sc[PC_Gs * 32 + lane] = scl * s * G;
+    sc[PC_Ah * 32 + lane] = scl * A;  sc[PC_Fs * 32 + lane] = scl * s * F;
+    sc[PC_Pc * 32 + lane] = K * cw * s2; sc[PC_Ps * 32 + lane] = K * sw * s;
+    sc[PC_mu * 32 + lane] = mass * m.c.mjup2msol / M;
+    sc[PC_a * 32 + lane] = a;
+    sc[PC_sinW * 32 + lane] = sW; sc[PC_cosW * 32 + lane] = cW; sc[PC_sinw * 32 + lane] = sw; sc[PC_cosw * 32 + lane] = cw;
+    sc[PC_sini * 32 + lane] = si; sc[PC_cosi * 32 + lane] = ci; sc[PC_M * 32 + lane] = M; sc[PC_plx * 32 + lane] = plx;
+    sc[PC_sc * 32 + lane] = scl;  sc[PC_c2a * 32 + lane] = c2a; sc[PC_K * 32 + lane] = K; sc[PC_Kb * 32 + lane] = Kb;
+    sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = Bc; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue: raw epoch sums R[slot] -> ll and d ll / d inputs for one chain (one lane).
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__device__ void chain_epilogue(const DevModel& m, const double* s_const, double* R, double* s_g,
+                               const double* __restrict__ in, int64_t c, int64_t ld, int lane, double& ll_out) {
+    double ll = R[0 * 32 + lane] + m.const_ll;
+    if (GRAD) for (int k = 0; k < m.n_in; ++k) s_g[k * 32 + lane] = 0.0;
+    // marginalised RV tables first: they fold their V-sums into the planet sums
+    for (int b = 0; b < m.n_blocks; ++b) {
+        const DevBlock& B = m.blocks[b];
+        if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
+            const int s0 = B.slot_margin;
+            const double A = R[(s0 + MA_A) * 32 + lane], S1 = R[(s0 + MA_S1) * 32 + lane];
+            const double C = R[(s0 + MA_C) * 32 + lane], LG = R[(s0 + MA_LG) * 32 + lane];
+            const double rbar = S1 / A;
+            ll += -LG - C + S1 * rbar - log(A);            // rv-absolute-margin.jl:171-181 with B = -2 S1
+            if (GRAD) {
+                const double R2 = R[(s0 + MA_R2) * 32 + lane], R1 = R[(s0 + MA_R1) * 32 + lane], Q = R[(s0 + MA_Q) * 32 + lane];
+                const double jit = in[c + (int64_t)B.idx_jitter * ld];
+                s_g[B.idx_jitter * 32 + lane] += 2.0 * jit * (-A + R2 - 2.0 * rbar * R1 + rbar * rbar * Q + Q / A);
+                for (int p = 0; p < m.n_planets; ++p) {
+                    const int v0 = s0 + MA_COUNT + p * MV_COUNT;
+                    const double k2 = -2.0 * rbar;
+                    R[slot_planet(p, PA_Pc) * 32 + lane] += k2 * R[(v0 + MV_Pc) * 32 + lane];
+                    R[slot_planet(p, PA_Ps) * 32 + lane] += k2 * R[(v0 + MV_Ps) * 32 + lane];
+                    R[slot_planet(p, PA_e) * 32 + lane] += k2 * R[(v0 + MV_e) * 32 + lane];
+                    R[slot_planet(p, PA_S0) * 32 + lane] += k2 * R[(v0 + MV_S0) * 32 + lane];
+                    R[slot_planet(p, PA_S1) * 32 + lane] += k2 * R[(v0 + MV_S1) * 32 + lane];
+                    R[slot_planet(p, PA_mu) * 32 + lane] += k2 * R[(v0 + MV_mu) * 32 + lane];
+                }
+            }
+        } else if (GRAD) {
+            if (B.slot_jitter >= 0) s_g[B.idx_jitter * 32 + lane] += R[B.slot_jitter * 32 + lane];
+            if (B.slot_platescale >= 0) s_g[B.idx_platescale * 32 + lane] += R[B.slot_platescale * 32 + lane];
+            if (B.slot_northangle >= 0) s_g[B.idx_northangle * 32 + lane] += R[B.slot_northangle * 32 + lane];
+            if (B.slot_offset >= 0) s_g[B.idx_offset * 32 + lane] += R[B.slot_offset * 32 + lane];
+        }
+    }
+    if (GRAD) {
+        for (int p = 0; p < m.n_planets; ++p) {
+            const double* sc = s_const + p * PC_COUNT * 32;
+            auto C = [&](int k) { return sc[k * 32 + lane]; };
+            auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
+            const double a = C(PC_a), e = C(PC_e), s = C(PC_s), M = C(PC_M), plx = C(PC_plx), nd = C(PC_nd);
+            const double sW = C(PC_sinW), cW = C(PC_cosW), sw = C(PC_sinw), cw = C(PC_cosw), si = C(PC_sini), ci = C(PC_cosi);
+            const double A = C(PC_A), Bc = C(PC_B), F = C(PC_F), G = C(PC_G), scl = C(PC_sc), c2a = C(PC_c2a);
+            const double K = C(PC_K), Kb = C(PC_Kb), mu = C(PC_mu);
+            const double gBh = Rp(PA_Bh), gGs = Rp(PA_Gs), gAh = Rp(PA_Ah), gFs = Rp(PA_Fs);
+            const double gPc = Rp(PA_Pc), gPs = Rp(PA_Ps), S0 = Rp(PA_S0), S1 = Rp(PA_S1), gmu = Rp(PA_mu);
+            double g_e = Rp(PA_e);
+            // mean motion: M_k = nd (t_k - tp)
+            double g_tp = -nd * S0;
+            double g_a = S1 * (-1.5 * nd / a);
+            double g_M = S1 * (0.5 * nd / M);
+            // astrometry: Bh = sc*B, Gs = sc*s*G, Ah = sc*A, Fs = sc*s*F with sc = a*c2a
+            const double g_sc = gBh * Bc + gGs * s * G + gAh * A + gFs * s * F;
+            g_a += g_sc * c2a;
+            double g_plx = g_sc * scl / plx;
+            const double gB = gBh * scl, gG = gGs * scl * s, gA = gAh * scl, gF = gFs * scl * s;
+            g_e += -(e / s) * scl * (gGs * G + gFs * F);
+            double g_w = gA * F + gB * G - gF * A - gG * Bc;
+            double g_W = -gA * Bc + gB * A - gF * G + gG * F;
+            double g_i = si * (gA * sW * sw - gB * cW * sw + gF * sW * cw - gG * cW * cw);
+            // radial velocity: Pc = K cosω s², Ps = K sinω s, K = kappa sqrt(M/a) sin i / s
+            const double s2 = s * s;
+            const double gK = gPc * cw * s2 + gPs * sw * s;
+            g_w += -gPc * K * sw * s2 + gPs * K * cw * s;
+            g_e += gPc * K * cw * (-2.0 * e) + gPs * K * sw * (-e / s) + gK * K * e / s2;
+            g_a += gK * (-0.5 * K / a);
+            g_M += gK * (0.5 * K / M);
+            g_i += gK * Kb * ci;
+            // reflex factor mu = mass * mjup2msol / M
+            g_M += -gmu * mu / M;
+            s_g[m.idx_a[p] * 32 + lane] += g_a;   s_g[m.idx_e[p] * 32 + lane] += g_e;
+            s_g[m.idx_i[p] * 32 + lane] += g_i;   s_g[m.idx_w[p] * 32 + lane] += g_w;
+            s_g[m.idx_W[p] * 32 + lane] += g_W;   s_g[m.idx_tp[p] * 32 + lane] += g_tp;
+            s_g[m.idx_M[p] * 32 + lane] += g_M;   s_g[m.idx_plx[p] * 32 + lane] += g_plx;
+            if (m.idx_mass[p] >= 0) s_g[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol / M;
+        }
+    }
+    ll_out = ll;
+}
+
+template <bool GRAD, int NPT>
+__global__ void __launch_bounds__(W * 32, 2)
+k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
+              double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
+              unsigned int* __restrict__ tickets) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_acc = m.n_acc;
+    double* s_const = smem;                                   // [P][PC_COUNT][32]
+    double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
+    double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
+    double* s_g = s_red + n_acc * 32;                         // [n_in][32]
+    int* s_ok = reinterpret_cast<int*>(s_g + m.n_in * 32);    // [W][32]
+    __shared__ int s_last;
+
+    const int64_t c_raw = (int64_t)blockIdx.x * 32 + lane;
+    const bool active = c_raw < n_chains;
+    const int64_t c = active ? c_raw : n_chains - 1;
+
+    // ---- prologue: finiteness of every input (logdensitymodel.jl:120-124), planet constants
+    int ok = 1;
+    for (int k = w; k < m.n_in; k += W) ok &= isfinite(in[c + (int64_t)k * ld]) ? 1 : 0;
+    for (int p = w; p < m.n_planets; p += W) ok &= planet_prologue(m, p, in, c, ld, s_const + p * PC_COUNT * 32, lane) ? 1 : 0;
+    s_ok[w * 32 + lane] = ok;
+    double* acc = s_acc + w * n_acc * 32;
+    for (int s = 0; s < n_acc; ++s) acc[s * 32 + lane] = 0.0;
+    __syncthreads();
+
+    // ---- this warp's contiguous range of the concatenated epoch list
+    const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
+    const int k_lo = (int)(m.n_epochs * u / U), k_hi = (int)(m.n_epochs * (u + 1) / U);
+    for (int b = 0; b < m.n_blocks; ++b) {
+        const DevBlock& B = m.blocks[b];
+        const int k0 = max(k_lo, B.start), k1 = min(k_hi, B.start + B.n);
+        if (k0 >= k1) continue;
+        if (B.kind <= OCTO_KIND_ASTROM_PASEP) seg_astrom<GRAD, NPT>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+        else seg_rv<GRAD, NPT>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+    }
+    __syncthreads();
+
+    // ---- CTA reduction over the 8 warps, fixed order
+    for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
+        double v = s_acc[idx];
+#pragma unroll
+        for (int ww = 1; ww < W; ++ww) v += s_acc[ww * n_acc * 32 + idx];
+        s_red[idx] = v;
+    }
+    __syncthreads();
+
+    // ---- K2: combine the epoch splits of this chain group; the last CTA to arrive sums in split order
+    if (gridDim.y > 1) {
+        double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
+        for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(&tickets[blockIdx.x], 1u);
+            s_last = (prev == gridDim.y - 1);
+            if (s_last) tickets[blockIdx.x] = 0;      // ready for the next launch on this workspace
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const double* base = partial + (int64_t)blockIdx.x * gridDim.y * n_acc * 32;
+        for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
+            double v = 0.0;
+            for (int y = 0; y < (int)gridDim.y; ++y) v += __ldcg(base + (int64_t)y * n_acc * 32 + idx);
+            s_red[idx] = v;
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: warp 0, one lane per chain
+    if (w == 0) {
+        int valid = 1;
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) valid &= s_ok[ww * 32 + lane];
+        double ll;
+        chain_epilogue<GRAD>(m, s_const, s_red, s_g, in, c, ld, lane, ll);
+        if (active) {
+            ll_out[c] = valid ? ll : -CUDART_INF;
+            if (GRAD) for (int k = 0; k < m.n_in; ++k) g_out[c + (int64_t)k * ldg] = valid ? s_g[k * 32 + lane] : 0.0;
+        }
+    }
+}
+
+}  // namespace
+
+size_t octo_smem_bytes(const DevModel& m) {
+    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (size_t)W * m.n_acc * 32 + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
+    return d * sizeof(double) + (size_t)W * 32 * sizeof(int);
+}
+
+template <bool GRAD, int NPT>
+static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
+                            double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
+                            cudaStream_t st) {
+    k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
+                                                                        d_tickets);
+    return cudaGetLastError();
+}
+
+// opt every instantiation in to `smem_bytes` of dynamic shared memory (once per context)
+cudaError_t octo_kernels_init(size_t smem_bytes) {
+    cudaError_t e;
+#define OCTO_ATTR(G, N)                                                                                            \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);   \
+    if (e != cudaSuccess) return e
+    OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
+#undef OCTO_ATTR
+    return cudaSuccess;
+}
+
+cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
+                        int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
+                        unsigned int* d_tickets, cudaStream_t st) {
+#define OCTO_DISPATCH(NPT)                                                                                        \
+    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, st)         \
+                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, st)
+    if (m.n_planets == 1) { OCTO_DISPATCH(1); }
+    if (m.n_planets == 2) { OCTO_DISPATCH(2); }
+    OCTO_DISPATCH(4);
+#undef OCTO_DISPATCH
+}

@@ -1,0 +1,481 @@
+// octo_shim.cu — the C ABI of libocto_b200.so (include/octo_b200.h): context creation
+// (table upload, per-epoch weight precomputation, accumulator slot map), the workspace/stream pool that
+// makes the entry points re-entrant, host-buffer and device-buffer entry points, and the NCCL
+// parallel-tempering swap round.  No CPU evaluation path exists here: without a CUDA device
+// octo_create fails.
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "octo_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return OCTO_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(e_, #call); } while (0)
+
+// One lease = everything a call needs so that concurrent callers never share mutable state.
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    double *d_in = nullptr, *d_ll = nullptr, *d_g = nullptr, *d_partial = nullptr;
+    unsigned int* d_tickets = nullptr;
+    double *h_in = nullptr, *h_out = nullptr;          // pinned staging
+    size_t cap_in = 0, cap_ll = 0, cap_g = 0, cap_partial = 0, cap_tickets = 0, cap_hin = 0, cap_hout = 0;
+    bool busy = false;
+};
+
+// minimal NCCL surface, resolved with dlopen so the library has no link-time NCCL dependency
+struct Id128 { char b[128]; };   // ncclUniqueId, passed by value
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct OctoCtx {
+    DevModel m;
+    int device = 0;
+    int n_sm = 148;
+    size_t smem = 0;
+    double* d_tables = nullptr;
+    std::mutex mu;
+    std::vector<Workspace*> pool;                                  // host-buffer calls: leased per call
+    std::vector<std::pair<cudaStream_t, Workspace*>> stream_ws;    // device-buffer calls: one per caller stream
+    std::atomic<int64_t> launches{0};
+    int ctas_per_sm = 2;
+    int slice_override = 0;
+    // parallel tempering
+    void* nccl_comm = nullptr;
+    int pt_rank = 0, pt_world = 1, pt_local = 0;
+    uint64_t pt_seed = 0;
+    double* d_gather = nullptr;
+    double* h_gather = nullptr;
+    cudaStream_t pt_stream = nullptr;
+};
+
+namespace {
+
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.h) return OCTO_OK;
+    const char* names[] = {getenv("OCTO_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { if (n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!h) return fail(OCTO_ERR_NCCL, "cannot dlopen libnccl.so.2 (set OCTO_B200_NCCL)");
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+        return fail(OCTO_ERR_NCCL, "libnccl is missing required symbols");
+    g_nccl.h = h;
+    return OCTO_OK;
+}
+int fail_nccl(int rc, const char* what) {
+    g_err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error");
+    return OCTO_ERR_NCCL;
+}
+
+template <class T>
+int ensure(T** p, size_t* cap, size_t need, bool pinned = false) {
+    if (need <= *cap) return OCTO_OK;
+    size_t n = need + need / 2;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (pinned) CU(cudaMallocHost((void**)p, n * sizeof(T)));
+    else CU(cudaMalloc((void**)p, n * sizeof(T)));
+    *cap = n;
+    return OCTO_OK;
+}
+
+Workspace* lease(OctoCtx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (Workspace* w : ctx->pool) if (!w->busy) { w->busy = true; return w; }
+    Workspace* w = new Workspace();
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return nullptr; }
+    w->busy = true;
+    ctx->pool.push_back(w);
+    return w;
+}
+void release(OctoCtx* ctx, Workspace* w) { std::lock_guard<std::mutex> lk(ctx->mu); w->busy = false; }
+
+// device-buffer entry point: the partial buffer/tickets are tied to the caller's stream, on which the
+// launches that use them are ordered
+Workspace* stream_workspace(OctoCtx* ctx, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& kv : ctx->stream_ws) if (kv.first == st) return kv.second;
+    Workspace* w = new Workspace();
+    ctx->stream_ws.emplace_back(st, w);
+    return w;
+}
+
+void free_ws(Workspace* w) {
+    if (w->d_in) cudaFree(w->d_in);
+    if (w->d_ll) cudaFree(w->d_ll);
+    if (w->d_g) cudaFree(w->d_g);
+    if (w->d_partial) cudaFree(w->d_partial);
+    if (w->d_tickets) cudaFree(w->d_tickets);
+    if (w->h_in) cudaFreeHost(w->h_in);
+    if (w->h_out) cudaFreeHost(w->h_out);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+// grid: chain groups x epoch splits.  Splits are added only while the chain groups alone cannot fill the
+// SMs, and never below OCTO_MIN_SLICE epochs per warp.
+LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
+    LaunchGeom g;
+    g.block = OCTO_WARPS * 32;
+    g.gx = (int)((n_chains + 31) / 32);
+    const int64_t E = ctx->m.n_epochs;
+    const int min_slice = ctx->slice_override > 0 ? ctx->slice_override : OCTO_MIN_SLICE;
+    int64_t max_gy = E / ((int64_t)min_slice * OCTO_WARPS);
+    if (max_gy < 1) max_gy = 1;
+    if (max_gy > 65535) max_gy = 65535;
+    const int64_t target = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
+    int64_t gy = (target + g.gx - 1) / g.gx;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    g.gy = (int)gy;
+    g.slice = (int)((E + gy * OCTO_WARPS - 1) / (gy * OCTO_WARPS));
+    g.smem = ctx->smem;
+    return g;
+}
+
+int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
+            int64_t ldg, cudaStream_t st) {
+    LaunchGeom g = geometry(ctx, n);
+    if (g.gy > 1) {
+        size_t need = (size_t)g.gx * g.gy * ctx->m.n_acc * 32;
+        if (int rc = ensure(&w->d_partial, &w->cap_partial, need)) return rc;
+        if ((size_t)g.gx > w->cap_tickets) {
+            if (int rc = ensure(&w->d_tickets, &w->cap_tickets, (size_t)g.gx)) return rc;
+            CU(cudaMemsetAsync(w->d_tickets, 0, w->cap_tickets * sizeof(unsigned int), st));
+        }
+    }
+    cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, st);
+    if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return OCTO_OK;
+}
+
+int run_host(OctoCtx* ctx, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (n == 0) return OCTO_OK;
+    if (!in || !ll || (grad && !g) || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = lease(ctx);
+    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
+    const int n_in = ctx->m.n_in;
+    int rc = OCTO_OK;
+    do {
+        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * n_in))) break;
+        if ((rc = ensure(&w->d_ll, &w->cap_ll, (size_t)n))) break;
+        if (grad && (rc = ensure(&w->d_g, &w->cap_g, (size_t)n * n_in))) break;
+        if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * n_in, true))) break;
+        if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (grad ? n_in + 1 : 1), true))) break;
+        // pack to a dense [n x n_in] column-major block in pinned memory, one async copy each way
+        for (int k = 0; k < n_in; ++k) memcpy(w->h_in + (size_t)k * n, in + (size_t)k * ld, (size_t)n * sizeof(double));
+        cudaError_t e = cudaMemcpyAsync(w->d_in, w->h_in, (size_t)n * n_in * sizeof(double), cudaMemcpyHostToDevice, w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
+        if ((rc = enqueue(ctx, w, grad, w->d_in, n, n, w->d_ll, grad ? w->d_g : nullptr, n, w->stream))) break;
+        e = cudaMemcpyAsync(w->h_out, w->d_ll, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess && grad)
+            e = cudaMemcpyAsync(w->h_out + n, w->d_g, (size_t)n * n_in * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
+        e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
+        memcpy(ll, w->h_out, (size_t)n * sizeof(double));
+        if (grad) for (int k = 0; k < n_in; ++k)
+            memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, (size_t)n * sizeof(double));
+    } while (0);
+    release(ctx, w);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* octo_last_error(void) { return g_err.c_str(); }
+int octo_abi_version(void) { return OCTO_ABI_VERSION; }
+
+void octo_default_constants(OctoConstants* c) {
+    if (!c) return;
+    c->kepler_year_days = 365.2568983840419; c->year2day = 365.25; c->rad2as = 206265.0; c->pc2au = 206265.0;
+    c->au2m = 1.495978707e11; c->sec2year = 1.0 / 31557600.0; c->mjup2msol = 0.0009545942339693249;
+}
+
+int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsBlock* blocks, int32_t n_blocks,
+                int32_t device, OctoCtx** out) {
+    if (!out) return fail(OCTO_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!consts || !L || (n_blocks > 0 && !blocks)) return fail(OCTO_ERR_ARG, "null argument");
+    if (L->n_planets < 1 || L->n_planets > OCTO_MAX_PLANETS) return fail(OCTO_ERR_ARG, "n_planets must be 1..4");
+    if (L->n_in < 1 || L->n_in > 4096) return fail(OCTO_ERR_ARG, "n_in out of range");
+    if (n_blocks < 0 || n_blocks > OCTO_MAX_BLOCKS) return fail(OCTO_ERR_ARG, "too many observation tables");
+    auto col_ok = [&](int k, bool optional) { return (optional && k == -1) || (k >= 0 && k < L->n_in); };
+    for (int p = 0; p < L->n_planets; ++p) {
+        if (!col_ok(L->idx_plx[p], false) || !col_ok(L->idx_a[p], false) || !col_ok(L->idx_e[p], false) ||
+            !col_ok(L->idx_i[p], false) || !col_ok(L->idx_w[p], false) || !col_ok(L->idx_W[p], false) ||
+            !col_ok(L->idx_tp[p], false) || !col_ok(L->idx_M[p], false) || !col_ok(L->idx_mass[p], true))
+            return fail(OCTO_ERR_ARG, "layout column index out of range");
+    }
+    int dev_count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&dev_count);
+    if (ce != cudaSuccess || dev_count == 0)
+        return fail(OCTO_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (this library has no CPU path)");
+    if (device < 0 || device >= dev_count) return fail(OCTO_ERR_ARG, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+
+    OctoCtx* ctx = new OctoCtx();
+    DevModel& m = ctx->m;
+    memset(&m, 0, sizeof(m));
+    m.c = *consts;
+    m.kappa = 6.283185307179586 * consts->year2day / consts->kepler_year_days * consts->au2m * consts->sec2year;
+    m.n_planets = L->n_planets; m.n_in = L->n_in; m.n_blocks = n_blocks;
+    for (int p = 0; p < OCTO_MAX_PLANETS; ++p) {
+        m.idx_plx[p] = L->idx_plx[p]; m.idx_a[p] = L->idx_a[p]; m.idx_e[p] = L->idx_e[p]; m.idx_i[p] = L->idx_i[p];
+        m.idx_w[p] = L->idx_w[p]; m.idx_W[p] = L->idx_W[p]; m.idx_tp[p] = L->idx_tp[p]; m.idx_M[p] = L->idx_M[p];
+        m.idx_mass[p] = p < L->n_planets ? L->idx_mass[p] : -1;
+    }
+    // validate tables, assign accumulator slots
+    int64_t E = 0;
+    int n_acc = 1 + PA_COUNT * L->n_planets;
+    for (int b = 0; b < n_blocks; ++b) {
+        const OctoObsBlock& B = blocks[b];
+        DevBlock& D = m.blocks[b];
+        const bool astrom = (B.kind == OCTO_KIND_ASTROM_RADEC || B.kind == OCTO_KIND_ASTROM_PASEP);
+        const bool sys = (B.kind == OCTO_KIND_RV_STAR_ABS || B.kind == OCTO_KIND_RV_STAR_MARGIN);
+        auto bad = [&](const char* msg) { delete ctx; return fail(OCTO_ERR_ARG, std::string("table ") + std::to_string(b) + ": " + msg); };
+        if (B.kind < 0 || B.kind > OCTO_KIND_RV_PLANET_REL) return bad("unknown kind");
+        if (B.n_epochs < 0 || (B.n_epochs > 0 && (!B.epoch || !B.y1 || !B.s1))) return bad("missing columns");
+        if (astrom && B.n_epochs > 0 && (!B.y2 || !B.s2)) return bad("astrometry needs y2 and s2");
+        if (astrom && B.has_cor && B.n_epochs > 0 && !B.cor) return bad("has_cor set but cor is null");
+        if (!sys && (B.planet < 0 || B.planet >= L->n_planets)) return bad("planet index out of range");
+        if (sys) for (int p = 0; p < L->n_planets; ++p)
+            if (L->idx_mass[p] < 0) return bad("star RV needs a mass variable on every planet (rv-absolute.jl:147)");
+        if (!col_ok(B.idx_jitter, true) || !col_ok(B.idx_platescale, true) || !col_ok(B.idx_northangle, true) ||
+            !col_ok(B.idx_offset, true)) return bad("observation variable column out of range");
+        if (B.kind == OCTO_KIND_RV_STAR_MARGIN && B.idx_jitter < 0) return bad("marginalised RV requires jitter (rv-absolute-margin.jl:149)");
+        D.kind = B.kind; D.planet = sys ? -1 : B.planet; D.start = (int32_t)E; D.n = B.n_epochs;
+        D.has_cor = (astrom && B.has_cor) ? 1 : 0;
+        D.jit = B.idx_jitter >= 0 ? 1 : 0;
+        D.idx_jitter = B.idx_jitter; D.idx_offset = (B.kind == OCTO_KIND_RV_STAR_MARGIN || astrom) ? -1 : B.idx_offset;
+        D.idx_platescale = astrom ? B.idx_platescale : -1; D.idx_northangle = astrom ? B.idx_northangle : -1;
+        D.slot_jitter = D.slot_platescale = D.slot_northangle = D.slot_offset = D.slot_margin = -1;
+        if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
+            D.slot_margin = n_acc; n_acc += MA_COUNT + MV_COUNT * L->n_planets;
+        } else {
+            if (D.idx_jitter >= 0) D.slot_jitter = n_acc++;
+            if (D.idx_offset >= 0) D.slot_offset = n_acc++;
+        }
+        if (D.idx_platescale >= 0) D.slot_platescale = n_acc++;
+        if (D.idx_northangle >= 0) D.slot_northangle = n_acc++;
+        E += B.n_epochs;
+        if (E > 0x7fffffff) return bad("too many epochs");
+    }
+    m.n_epochs = E; m.n_acc = n_acc;
+
+    // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
+    std::vector<double> T((size_t)6 * (E > 0 ? E : 1), 0.0);
+    double *t = T.data(), *y1 = t + E, *y2 = y1 + E, *c1 = y2 + E, *c2 = c1 + E, *c3 = c2 + E;
+    long double cll = 0.0L;
+    const long double log2pi = 1.8378770664093454835606594728112353L;
+    for (int b = 0; b < n_blocks; ++b) {
+        const OctoObsBlock& B = blocks[b];
+        const DevBlock& D = m.blocks[b];
+        const bool astrom = (B.kind <= OCTO_KIND_ASTROM_PASEP);
+        for (int k = 0; k < B.n_epochs; ++k) {
+            const size_t o = (size_t)D.start + k;
+            t[o] = B.epoch[k]; y1[o] = B.y1[k];
+            if (astrom) {
+                y2[o] = B.y2[k];
+                const double s1 = B.s1[k], s2 = B.s2[k], cor = D.has_cor ? B.cor[k] : 0.0;
+                if (std::fabs(cor) >= 1.0) { delete ctx; return fail(OCTO_ERR_ARG, "|cor| >= 1 (relative-astrometry.jl:69-71)"); }
+                if (B.kind == OCTO_KIND_ASTROM_RADEC && D.idx_platescale < 0 && D.idx_northangle < 0) {
+                    // the reference pushes the data through atan/hypot/cos/sin even with platescale = 1,
+                    // northangle = 0 (relative-astrometry.jl:209-213): reproduce that <= 2 ulp perturbation here
+                    const double pa = std::atan2(B.y2[k], B.y1[k]) - 0.0, sep = std::hypot(B.y2[k], B.y1[k]) * 1.0;
+                    y1[o] = sep * std::cos(pa); y2[o] = sep * std::sin(pa);
+                }
+                if (!D.jit) {
+                    const double om = 1.0 - cor * cor;
+                    c1[o] = 1.0 / (s1 * s1 * om); c3[o] = 1.0 / (s2 * s2 * om); c2[o] = -cor / (s1 * s2 * om);
+                    cll += -log2pi - 0.5L * std::log((long double)s1 * s1 * s2 * s2 * om);
+                } else { c1[o] = s1 * s1; c2[o] = s2 * s2; c3[o] = cor; }
+            } else {
+                const double s = B.s1[k];
+                if (!D.jit) { c1[o] = 1.0 / (s * s); cll += -0.5L * (log2pi + std::log((long double)s * s)); }
+                else c1[o] = s * s;
+            }
+        }
+    }
+    m.const_ll = (double)cll;
+
+    cudaDeviceProp prop;
+    ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaGetDeviceProperties"); }
+    if (prop.major < 10) { delete ctx; return fail(OCTO_ERR_CUDA, "libocto_b200 is built for sm_100a only"); }
+    ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
+    ctx->smem = octo_smem_bytes(m);
+    if (ctx->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete ctx; return fail(OCTO_ERR_ARG, "model too large: accumulator slots exceed shared memory");
+    }
+    if (const char* s = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, atoi(s));
+    if (const char* s = getenv("OCTO_B200_SLICE")) ctx->slice_override = std::max(1, atoi(s));
+    ce = cudaMalloc((void**)&ctx->d_tables, T.size() * sizeof(double));
+    if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaMalloc tables"); }
+    ce = cudaMemcpy(ctx->d_tables, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
+    m.t = ctx->d_tables; m.y1 = m.t + E; m.y2 = m.y1 + E; m.c1 = m.y2 + E; m.c2 = m.c1 + E; m.c3 = m.c2 + E;
+    ce = octo_kernels_init(ctx->smem);
+    if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
+    *out = ctx;
+    return OCTO_OK;
+}
+
+void octo_destroy(OctoCtx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    octo_pt_finalize(ctx);
+    cudaDeviceSynchronize();
+    for (Workspace* w : ctx->pool) free_ws(w);
+    for (auto& kv : ctx->stream_ws) free_ws(kv.second);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    delete ctx;
+}
+
+int octo_logp(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll) { return run_host(ctx, false, in, n, ld, ll, nullptr); }
+int octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll, double* g) { return run_host(ctx, true, in, n, ld, ll, g); }
+
+int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g, void* stream) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (n == 0) return OCTO_OK;
+    if (!d_in || !d_ll || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);   // partial buffer + tickets of this stream
+    return enqueue(ctx, w, d_g != nullptr, d_in, n, ld, d_ll, d_g, ld, (cudaStream_t)stream);
+}
+
+int32_t octo_n_in(const OctoCtx* ctx) { return ctx ? ctx->m.n_in : -1; }
+int32_t octo_n_planets(const OctoCtx* ctx) { return ctx ? ctx->m.n_planets : -1; }
+int64_t octo_total_epochs(const OctoCtx* ctx) { return ctx ? ctx->m.n_epochs : -1; }
+int32_t octo_device(const OctoCtx* ctx) { return ctx ? ctx->device : -1; }
+int64_t octo_kernel_launches(const OctoCtx* ctx) { return ctx ? ctx->launches.load() : -1; }
+int octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]) {
+    if (!ctx || !out || n_chains < 1) return fail(OCTO_ERR_ARG, "bad argument");
+    LaunchGeom g = geometry(ctx, n_chains);
+    out[0] = g.gx; out[1] = g.gy; out[2] = g.block; out[3] = g.slice;
+    return OCTO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parallel tempering swap round
+// ------------------------------------------------------------------------------------------------
+int octo_pt_unique_id(void* out128) {
+    if (!out128) return fail(OCTO_ERR_ARG, "null id buffer");
+    if (int rc = load_nccl()) return rc;
+    int r = g_nccl.GetUniqueId(out128);
+    return r ? fail_nccl(r, "ncclGetUniqueId") : OCTO_OK;
+}
+
+int octo_pt_init(OctoCtx* ctx, const void* id, int32_t rank, int32_t world, int32_t n_local, uint64_t seed) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world || n_local < 1) return fail(OCTO_ERR_ARG, "bad pt arguments");
+    CU(cudaSetDevice(ctx->device));
+    octo_pt_finalize(ctx);
+    ctx->pt_rank = rank; ctx->pt_world = world; ctx->pt_local = n_local; ctx->pt_seed = seed;
+    CU(cudaStreamCreateWithFlags(&ctx->pt_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void**)&ctx->d_gather, (size_t)world * n_local * 2 * sizeof(double)));
+    CU(cudaMallocHost((void**)&ctx->h_gather, (size_t)world * n_local * 2 * sizeof(double)));
+    if (world > 1) {
+        if (!id) return fail(OCTO_ERR_ARG, "nccl unique id required for world > 1");
+        if (int rc = load_nccl()) return rc;
+        Id128 uid; memcpy(uid.b, id, 128);
+        int r = g_nccl.CommInitRank(&ctx->nccl_comm, world, uid, rank);
+        if (r) return fail_nccl(r, "ncclCommInitRank");
+    }
+    return OCTO_OK;
+}
+
+// counter-based uniform in (0,1): splitmix64 of (seed, round, pair) — identical on every rank
+static double pt_uniform(uint64_t seed, uint64_t round, uint64_t pair) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (round * 0x100000001B3ULL + pair + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+int octo_pt_swap_round(OctoCtx* ctx, const double* d_ll_pair, const double* beta, int32_t* chain_of_replica,
+                       int64_t round, int32_t* accepted) {
+    if (!ctx || !ctx->pt_stream) return fail(OCTO_ERR_STATE, "octo_pt_init has not been called");
+    if (!d_ll_pair || !beta || !chain_of_replica) return fail(OCTO_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const int nl = ctx->pt_local, R = nl * ctx->pt_world;
+    if (ctx->pt_world > 1) {
+        int r = g_nccl.AllGather(d_ll_pair, ctx->d_gather, (size_t)nl * 2, /*ncclFloat64*/ 8, ctx->nccl_comm, ctx->pt_stream);
+        if (r) return fail_nccl(r, "ncclAllGather");
+        CU(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, (size_t)R * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->pt_stream));
+    } else {
+        CU(cudaMemcpyAsync(ctx->h_gather, d_ll_pair, (size_t)R * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->pt_stream));
+    }
+    CU(cudaStreamSynchronize(ctx->pt_stream));
+    // replica_of_chain: inverse permutation
+    std::vector<int> rep_of(R, -1);
+    for (int r = 0; r < R; ++r) {
+        const int ch = chain_of_replica[r];
+        if (ch < 0 || ch >= R || rep_of[ch] != -1) return fail(OCTO_ERR_ARG, "chain_of_replica is not a permutation");
+        rep_of[ch] = r;
+    }
+    if (accepted) for (int i = 0; i < R - 1; ++i) accepted[i] = 0;
+    // even rounds pair ladder rungs (0,1),(2,3)...; odd rounds (1,2),(3,4)... (deterministic even-odd scheme)
+    for (int i = (int)(round & 1); i + 1 < R; i += 2) {
+        const int ra = rep_of[i], rb = rep_of[i + 1];
+        const double* A = ctx->h_gather + 2 * (size_t)ra;   // (l_ref, l_target) of the replica on rung i
+        const double* B = ctx->h_gather + 2 * (size_t)rb;
+        // tempered log-density at beta: (1-b) l_ref + b l_target
+        const double bi = beta[i], bj = beta[i + 1];
+        auto V = [](const double* x, double b) { return (1.0 - b) * x[0] + b * x[1]; };
+        const double log_ratio = (V(A, bj) + V(B, bi)) - (V(A, bi) + V(B, bj));
+        const double u = pt_uniform(ctx->pt_seed, (uint64_t)round, (uint64_t)i);
+        const bool acc = std::isfinite(log_ratio) ? (std::log(u) < log_ratio) : (log_ratio > 0);
+        if (acc) {
+            chain_of_replica[ra] = i + 1; chain_of_replica[rb] = i;
+            rep_of[i] = rb; rep_of[i + 1] = ra;
+            if (accepted) accepted[i] = 1;
+        }
+    }
+    return OCTO_OK;
+}
+
+void octo_pt_finalize(OctoCtx* ctx) {
+    if (!ctx) return;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    if (ctx->d_gather) { cudaFree(ctx->d_gather); ctx->d_gather = nullptr; }
+    if (ctx->h_gather) { cudaFreeHost(ctx->h_gather); ctx->h_gather = nullptr; }
+    if (ctx->pt_stream) { cudaStreamDestroy(ctx->pt_stream); ctx->pt_stream = nullptr; }
+}
+
+}  // extern "C"

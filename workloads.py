@@ -1,0 +1,130 @@
+"""Seeded synthetic workloads for BASELINE.json's configs.
+
+Data synthesis only (numpy Newton solve for the noise-free model values); no likelihood is
+evaluated here.  Used by tests/ and bench.py; nothing reads /root/reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import octofitter_jl_b200 as octo
+
+KYJ = 365.2568983840419
+MJUP2MSOL = 0.0009545942339693249
+TRUTH_B = dict(a=10.0, e=0.3, i=1.0, w=0.5, W=2.0, tp=50000.0, M=1.2, plx=50.0, mass=10.0)
+TRUTH_C = dict(a=4.0, e=0.1, i=1.0, w=1.3, W=2.0, tp=50400.0, M=1.2, plx=50.0, mass=5.0)
+
+
+def _state(el, t):
+    a, e, i, w, W, tp, M, plx = (el[k] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx"))
+    P = np.sqrt(a ** 3 / M) * KYJ
+    MA = 2 * np.pi * (np.asarray(t, float) - tp) / P
+    MA = MA - 2 * np.pi * np.round(MA / (2 * np.pi))
+    E = MA + e * np.sin(MA)
+    for _ in range(50):
+        E = E - (E - e * np.sin(E) - MA) / (1 - e * np.cos(E))
+    s = np.sqrt(1 - e * e)
+    X, Y = np.cos(E) - e, s * np.sin(E)
+    A = np.cos(W) * np.cos(w) - np.sin(W) * np.sin(w) * np.cos(i)
+    B = np.sin(W) * np.cos(w) + np.cos(W) * np.sin(w) * np.cos(i)
+    F = -np.cos(W) * np.sin(w) - np.sin(W) * np.cos(w) * np.cos(i)
+    G = -np.sin(W) * np.sin(w) + np.cos(W) * np.cos(w) * np.cos(i)
+    ra, dec = a * plx * (X * B + Y * G), a * plx * (X * A + Y * F)
+    D = 1 - e * np.cos(E)
+    K = (2 * np.pi * a / (P / 365.25)) / s * 1.495978707e11 / 31557600.0 * np.sin(i)
+    rv = K * ((X / D) * np.cos(w) - (Y / D) * np.sin(w) + e * np.cos(w))
+    return ra, dec, rv, P
+
+
+def _astrom_table(el, epochs, rng, sigma=10.0, cor_frac=0.0, others=()):
+    ra, dec, _, _ = _state(el, epochs)
+    for o in others:        # interior companions pull the star
+        r2, d2, _, _ = _state(o, epochs)
+        mu = o["mass"] * MJUP2MSOL / o["M"]
+        ra, dec = ra + mu * r2, dec + mu * d2
+    n = len(epochs)
+    tab = dict(epoch=epochs, ra=ra + sigma * rng.standard_normal(n), dec=dec + sigma * rng.standard_normal(n),
+               σ_ra=np.full(n, sigma), σ_dec=np.full(n, sigma))
+    if cor_frac > 0:
+        cor = np.zeros(n)
+        pick = rng.random(n) < cor_frac
+        cor[pick] = rng.uniform(-0.9, 0.9, pick.sum())
+        tab["cor"] = cor
+    return octo.Table(**tab)
+
+
+def _chains(spec, truth_by_name, n_chains, rng, rel=0.02):
+    x0 = np.array([truth_by_name[n] for n in spec.input_names])
+    x = x0[None, :] * (1.0 + rel * rng.standard_normal((n_chains, len(x0))))
+    x[0] = x0
+    for k, n in enumerate(spec.input_names):
+        if n.endswith(".e"):
+            x[:, k] = np.clip(x[:, k], 0.0, 0.95)
+        if n.endswith("jitter"):
+            x[:, k] = np.abs(x[:, k])
+    return np.asfortranarray(x)
+
+
+def one_planet(n_astrom, n_rv, n_chains, seed, span=0.9, with_mass=None):
+    """1 planet; n_astrom RA/Dec epochs (+ n_rv star-RV epochs with offset & jitter, interleaved)."""
+    rng = np.random.default_rng(seed)
+    P = _state(TRUTH_B, [0.0])[3]
+    obs, sysobs = [], []
+    truth = {"M": 1.2, "plx": 50.0, "b.a": 10.0, "b.e": 0.3, "b.i": 1.0, "b.ω": 0.5, "b.Ω": 2.0, "b.tp": 50000.0}
+    pvars = ["a", "e", "i", "ω", "Ω", "tp"]
+    n_tot = n_astrom + n_rv
+    grid = np.linspace(50000.0, 50000.0 + span * P, max(n_tot, 1))
+    if n_astrom:
+        ep = grid[::2][:n_astrom] if n_rv else grid
+        ep = np.linspace(50000.0, 50000.0 + span * P, n_astrom) if len(ep) != n_astrom else ep
+        obs.append(octo.PlanetRelAstromObs(_astrom_table(TRUTH_B, ep, rng), name="astrom"))
+    if n_rv or with_mass:
+        pvars.append("mass"); truth["b.mass"] = 10.0
+    if n_rv:
+        ep = grid[1::2][:n_rv]
+        ep = np.linspace(50010.0, 50000.0 + span * P, n_rv) if len(ep) != n_rv else ep
+        _, _, rv, _ = _state(TRUTH_B, ep)
+        mu = TRUTH_B["mass"] * MJUP2MSOL / TRUTH_B["M"]
+        rvd = 150.0 - mu * rv + np.hypot(5.0, 3.0) * rng.standard_normal(n_rv)
+        sysobs.append(octo.StarAbsoluteRVObs(octo.Table(epoch=ep, rv=rvd, σ_rv=np.full(n_rv, 5.0)), name="rv"))
+        truth["rv.offset"] = 150.0; truth["rv.jitter"] = 3.0
+    b = octo.Planet(name="b", variables=pvars, observations=obs)
+    system = octo.System(name="synthetic", variables=["M", "plx"], companions=[b], observations=sysobs)
+    spec = octo.ModelSpec(system)
+    return spec, _chains(spec, truth, n_chains, rng)
+
+
+def two_planet(n_chains, seed, n_b=200, n_c=150, n_rv=150):
+    """C3: hierarchical 2-planet system, 500 epochs: astrometry on both (cor on 20% of b), star RV."""
+    rng = np.random.default_rng(seed)
+    Pb = _state(TRUTH_B, [0.0])[3]
+    ep_b = np.linspace(50000.0, 50000.0 + 0.9 * Pb, n_b)
+    ep_c = np.linspace(50020.0, 50000.0 + 0.5 * Pb, n_c)
+    ep_r = np.linspace(50005.0, 50000.0 + 0.4 * Pb, n_rv)
+    ab = octo.PlanetRelAstromObs(_astrom_table(TRUTH_B, ep_b, rng, cor_frac=0.2, others=[TRUTH_C]), name="astrom_b")
+    ac = octo.PlanetRelAstromObs(_astrom_table(TRUTH_C, ep_c, rng), name="astrom_c", variables=["jitter"])
+    rv = sum(-el["mass"] * MJUP2MSOL / el["M"] * _state(el, ep_r)[2] for el in (TRUTH_B, TRUTH_C))
+    rvo = octo.StarAbsoluteRVObs(octo.Table(epoch=ep_r, rv=150.0 + rv + np.hypot(5, 3) * rng.standard_normal(n_rv),
+                                            σ_rv=np.full(n_rv, 5.0)), name="rv")
+    pb = octo.Planet(name="b", variables=["M", "a", "e", "i", "ω", "Ω", "tp", "mass"], observations=[ab])
+    pc = octo.Planet(name="c", variables=["M", "a", "e", "i", "ω", "Ω", "tp", "mass"], observations=[ac])
+    system = octo.System(name="two", variables=["plx"], companions=[pb, pc], observations=[rvo])
+    spec = octo.ModelSpec(system)
+    truth = {"plx": 50.0, "rv.offset": 150.0, "rv.jitter": 3.0, "c.astrom_c.jitter": 2.0}
+    for nm, el in (("b", TRUTH_B), ("c", TRUTH_C)):
+        truth.update({f"{nm}.M": el["M"], f"{nm}.a": el["a"], f"{nm}.e": el["e"], f"{nm}.i": el["i"],
+                      f"{nm}.ω": el["w"], f"{nm}.Ω": el["W"], f"{nm}.tp": el["tp"], f"{nm}.mass": el["mass"]})
+    return spec, _chains(spec, truth, n_chains, rng)
+
+
+def config(name):
+    """BASELINE.json configs by name: C1..C4; C5 via one_planet(E, 0, 4096, 5 + k)."""
+    if name == "C1":
+        return one_planet(50, 0, 1, seed=1)
+    if name == "C2":
+        return one_planet(100, 100, 1024, seed=2)
+    if name == "C3":
+        return two_planet(256, seed=3)
+    if name == "C4":
+        return one_planet(100, 0, 64, seed=4)
+    raise KeyError(name)
