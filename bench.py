@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — epoch·logp-grad evaluations per second of the hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+    python bench.py --sweep                                   # extra: C5 epoch sweep lines (not the contract line)
+
+Workload at N=1: BASELINE.json configs[1] ("C2": 1 planet, 200 astrometry+RV epochs — 100 RA/Dec + 100
+star-RV with offset and jitter — x 1024 chains).  A "step" is one value+gradient evaluation of the whole batch
+(one leapfrog's worth of work for 1024 chains).  N>1: every rank runs its own 1024 chains (chains are
+independent, no data-path collective) => weak scaling; value = all ranks' pairs / max-over-ranks time.
+
+`value`: inputs resident in HBM, one kernel per step, device time by CUDA events on the launching stream, L2
+flushed between timed steps.  `e2e`: the same metric through the public host API (`LogDensityModel.
+ln_like_and_gradient` -> C ABI `octo_logp_grad`) with HOST buffers: pack + H2D + kernel + D2H inside the
+timed region, wall clock around K synchronous calls.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# FP64 flop per (epoch x chain) pair of the gradient kernel: DFMA = 2, DADD/DMUL = 1, counted from the SASS the
+# kernel executes (ncu smsp__sass_thread_inst_executed_op_d{fma,add,mul}_pred_on, profiles/r01_*); see DESIGN.md
+F_ALG = {"astrom": 404.0, "rv": 452.0}
+FP64_PEAK_FALLBACK_TFLOPS = 37.2     # nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz, used only if the probe fails
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak(device):
+    """Measured FP64 FMA peak (TFLOP/s) — MEASURED_PEAKS.json has no FP64 entry."""
+    so = os.path.join(ROOT, "profiles", "tools", "libfp64_peak.so")
+    try:
+        lib = C.CDLL(so)
+        lib.fp64_peak_tflops.restype = C.c_double
+        lib.fp64_peak_tflops.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        ms = C.c_double()
+        v = lib.fp64_peak_tflops(device, 2000, 5, C.byref(ms))
+        if v > 0:
+            return v, "measured (profiles/tools/fp64_peak.cu, DFMA chains, best of 5)"
+    except OSError:
+        pass
+    return FP64_PEAK_FALLBACK_TFLOPS, "fallback (nominal)"
+
+
+def measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def flops_per_launch(spec, n_chains):
+    fl = 0.0
+    for b in spec.block_dicts:
+        n_pl = len(spec.layout_dict["planets"]) if b["kind"] in (2, 3) else 1
+        fl += len(b["epoch"]) * n_pl * F_ALG["astrom" if b["kind"] <= 1 else "rv"]
+    return fl * n_chains
+
+
+def cpu_baseline(spec, x, threads, budget_s=12.0):
+    """The oracle port (value + dual-number gradient) on the host cores, bounded sample of the same workload."""
+    import octofitter_jl_b200 as octo
+    from oracle import oracle_py
+    orc = oracle_py.Oracle(spec.packed, octo.default_constants())
+    n = x.shape[0]
+    orc.logp_grad(x[: max(1, n // 8)], threads=threads)
+    best, reps, t_all = 1e30, 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t_all < budget_s and reps < 50):
+        t0 = time.perf_counter()
+        orc.logp_grad(x, threads=threads)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    return {"value": n * spec.total_epochs / best, "unit": "epoch*chain logp-grad evals/s", "cores": threads,
+            "kind": "port", "sample": f"full batch ({n} chains x {spec.total_epochs} epochs), best of {reps} passes"}
+
+
+def run_reference(args):
+    """CPU arm: the reference's algorithm as restated by oracle/ (kind 'port' — no Julia in this image), all host
+    threads, same workload/metric.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import workloads
+    from oracle import oracle_py
+    import octofitter_jl_b200 as octo
+    spec, x = workloads.config("C2")
+    threads = oracle_py.max_threads()
+    orc = oracle_py.Oracle(spec.packed, octo.default_constants())
+    for _ in range(max(1, min(args.warmup, 3))):
+        orc.logp_grad(x, threads=threads)
+    steps = max(1, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.logp_grad(x, threads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    pairs = x.shape[0] * spec.total_epochs
+    v = pairs / dt
+    line = {"impl": "reference", "metric": "epoch*chain logp-grad evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 1 planet, 100 astrometry + 100 star-RV epochs x 1024 chains (rank 0 only)"},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} passes over the full batch ({x.shape[0]} chains x {spec.total_epochs} epochs)"},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def time_device(model, d_in, d_ll, d_g, n, steps, warmup, torch, flush):
+    st = torch.cuda.current_stream()
+    for _ in range(warmup):
+        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), d_g.data_ptr(), st.cuda_stream)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        if flush is not None:
+            flush.zero_()                      # > L2 (126 MB): the next step starts from a cold L2
+        a.record(st)
+        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), d_g.data_ptr(), st.cuda_stream)
+        b.record(st)
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in ev])      # ms
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import octofitter_jl_b200 as octo
+    import workloads
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    spec, x = workloads.config("C2")          # every rank: its own 1024 chains (seed offset by rank)
+    if rank > 0:
+        spec, x = workloads.one_planet(100, 100, 1024, seed=2 + 1000 * rank)
+    n, n_in, E = x.shape[0], spec.n_in, spec.total_epochs
+    model = octo.LogDensityModel(spec, device=local)
+    d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()          # [n_in, n] row-major == [n x n_in] column-major
+    d_ll = torch.empty(n, dtype=torch.float64, device="cuda")
+    d_g = torch.empty((n_in, n), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    sampler = ClockSampler(local)
+    launches0 = model.kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ms = time_device(model, d_in, d_ll, d_g, n, args.steps, max(3, args.warmup), torch, flush)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = model.kernel_launches - launches0 - max(3, args.warmup)
+    t_dev = float(ms.sum()) * 1e-3
+
+    # end-to-end through the public host API
+    for _ in range(max(3, min(args.warmup, 10))):
+        model.ln_like_and_gradient(x)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ll_h, g_h = model.ln_like_and_gradient(x)
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    # sanity: device path and host path agree
+    assert np.array_equal(d_ll.cpu().numpy(), ll_h), "device-resident and host-API results differ"
+
+    if rank == 0:
+        pairs_step = n * E * world
+        value = pairs_step * args.steps / t_dev
+        kern_ms = float(np.mean(ms))
+        peak, peak_how = fp64_peak(local)
+        fl = flops_per_launch(spec, n)
+        achieved = fl / (kern_ms * 1e-3) / 1e12
+        hbm_peak, hbm_how = measured_hbm()
+        alg_bytes = 8.0 * (n * n_in * 2 + n) + 8.0 * 6 * E
+        line = {
+            "metric": "epoch*chain logp-grad evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 1 planet, 100 RA/Dec astrometry + 100 star-RV (offset, jitter) epochs x 1024 chains per GPU",
+                       "chains_per_gpu": n, "epochs": E, "n_in": n_in, "launch_geometry": list(model.launch_geometry(n)),
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                       "timing": "CUDA events around each step's single kernel on the launching stream; value = pairs / sum of event times"},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_how, "flop_per_pair": F_ALG,
+                         "kernel_ms": kern_ms, "kernel_ms_min": float(ms.min()),
+                         "hbm": {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "peak_source": hbm_how, "algorithmic_bytes": alg_bytes}},
+            "e2e": {"value": pairs_step * args.steps / t_e2e, "unit": "evals/s",
+                    "h2d_bytes_per_step": n * n_in * 8, "d2h_bytes_per_step": n * (n_in + 1) * 8,
+                    "ms_per_step": t_e2e / args.steps * 1e3,
+                    "api": "LogDensityModel.ln_like_and_gradient(host ndarray) -> octo_logp_grad (pinned staging inside)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import oracle_py
+            line["cpu_baseline"] = cpu_baseline(spec, x, oracle_py.max_threads())
+        print(json.dumps(line))
+        if args.sweep:
+            sweep(octo, workloads, torch, peak, local)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep(octo, workloads, torch, peak, device):
+    """C5: epoch sweep x 4096 chains, device-resident, written to gpurun_out/sweep.jsonl."""
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    out = open(os.path.join(ROOT, "gpurun_out", "sweep.jsonl"), "w")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for k, E in enumerate([10, 32, 100, 316, 1000, 3162, 10000, 31623, 100000]):
+        spec, x = workloads.one_planet(E, 0, 4096, seed=5 + k)
+        model = octo.LogDensityModel(spec, device=device)
+        n, n_in = x.shape
+        d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+        d_ll = torch.empty(n, dtype=torch.float64, device="cuda")
+        d_g = torch.empty((n_in, n), dtype=torch.float64, device="cuda")
+        steps = 20 if E <= 10000 else 5
+        ms = time_device(model, d_in, d_ll, d_g, n, steps, 3, torch, flush)
+        kms = float(np.mean(ms))
+        fl = flops_per_launch(spec, n)
+        rec = {"epochs": E, "chains": n, "kernel_ms": kms, "evals_per_s": n * E / (kms * 1e-3),
+               "fp64_tflops": fl / (kms * 1e-3) / 1e12, "frac_fp64_peak": fl / (kms * 1e-3) / 1e12 / peak,
+               "geometry": list(model.launch_geometry(n))}
+        out.write(json.dumps(rec) + "\n"); out.flush()
+        print("sweep", json.dumps(rec), file=sys.stderr)
+        model.close()
+    out.close()
+
+
+if __name__ == "__main__":
+    main()
