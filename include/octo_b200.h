@@ -161,6 +161,11 @@ int  octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld
 int  octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n_chains, int64_t ld,
                            double* d_ll, double* d_g_in, void* stream);
 
+/* Diagnostic: run only the device Kepler solve (rem2pi + Markley) on n (mean anomaly, e) pairs
+ * and return sin E, cos E.  HOST buffers.  Used by the test-suite to probe e -> 1, M -> 0, |M| = pi. */
+int  octo_selftest_kepler(int32_t device, const double* MA, const double* e, int64_t n,
+                          double* sinE, double* cosE);
+
 /* introspection */
 int32_t octo_n_in(const OctoCtx* ctx);
 int32_t octo_n_planets(const OctoCtx* ctx);

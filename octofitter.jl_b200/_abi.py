@@ -123,6 +123,7 @@ def load_library(path: str | None = None):
     lib.octo_logp.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_logp_grad.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.octo_logp_grad_device.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    lib.octo_selftest_kepler.argtypes = [i32, vp, vp, i64, vp, vp]
     lib.octo_n_in.argtypes = [vp]
     lib.octo_n_in.restype = i32
     lib.octo_n_planets.argtypes = [vp]
@@ -147,6 +148,6 @@ def load_library(path: str | None = None):
 
 EXPORTED_SYMBOLS = (
     "octo_default_constants", "octo_abi_version", "octo_create", "octo_destroy", "octo_logp", "octo_logp_grad",
-    "octo_logp_grad_device", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
+    "octo_logp_grad_device", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
     "octo_pt_finalize", "octo_last_error")

@@ -8,7 +8,7 @@
 #define OCTO_MAX_BLOCKS 24        // observation tables per model
 #define OCTO_WARPS 8              // warps per CTA: each warp owns one contiguous epoch range
 #define OCTO_LANES 32             // lanes = chains of one chain group
-#define OCTO_MIN_SLICE 4          // fewest epochs worth giving a warp
+#define OCTO_MIN_SLICE 2          // fewest epochs worth giving a warp
 
 // Per chain*planet constants staged in shared memory by the prologue ([slot][lane] doubles).
 enum PlanetConst {
@@ -71,4 +71,5 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, cudaStream_t stream);
 size_t octo_smem_bytes(const DevModel& m);
-cudaError_t octo_kernels_init(size_t smem_bytes);
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int* ctas_per_sm);
+cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);

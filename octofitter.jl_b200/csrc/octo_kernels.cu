@@ -35,40 +35,94 @@ constexpr double kLog2Pi = 1.8378770664093454836;
 constexpr double kA0 = 3.0 * kPi * kPi / (kPi * kPi - 6.0);
 constexpr double kA1 = 1.6 * kPi / (kPi * kPi - 6.0);
 
-struct Orb { double nd, tp, e, ome, ca1; };
+struct Orb { double nd, tp, e; float ef, omef, ca1f; };
 
 // ---------------------------------------------------------------------------------------------
-// rem2pi (round to nearest) + Markley's starter + one fifth-order correction; returns sinE, cosE.
-// sin/cos of E = E1 + d5 come from rotating sincos(E1) by d5 (|d5| < 4.4e-4 over the whole
-// domain, so three Taylor terms are exact to 1e-19): one sincos per solve instead of two.
+// Branch-free FP64 building blocks with known input ranges (no libm slow paths, no divergence).
+// ---------------------------------------------------------------------------------------------
+// 1/x: MUFU.RCP64H seed (~2^-20) + two Newton steps -> ~1 ulp.  x finite, normal, non-zero.
+__device__ __forceinline__ double rcp_nr(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+constexpr double kMagic = 6755399441055744.0;      // 1.5 * 2^52: (x + kMagic) - kMagic == rint(x) for |x| < 2^51
+constexpr double kTwoOverPi = 0.63661977236758138243;
+constexpr double kPio2Hi = 1.57079632679489655800e+00;
+constexpr double kPio2Lo = 6.12323399573676603587e-17;
+
+// sin and cos for |x| <= ~4 (here x = E1 in [-pi, pi]): one quadrant reduction, fdlibm kernel polynomials on
+// [-pi/4, pi/4] (< 1 ulp), quadrant fix-up by selects.
+__device__ __forceinline__ void sincos_pi(double x, double& s, double& c) {
+    const double tq = fma(x, kTwoOverPi, kMagic);
+    const int q = __double2loint(tq);
+    const double kq = tq - kMagic;
+    double r = fma(-kq, kPio2Hi, x);
+    r = fma(-kq, kPio2Lo, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double s0 = (q & 1) ? cr : sr;
+    const double c0 = (q & 1) ? sr : cr;
+    s = (q & 2) ? -s0 : s0;
+    c = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kepler solve: rem2pi (round to nearest) + Markley's starter + one fifth-order correction; returns sinE, cosE.
+//  * The starter E1 (Markley eqs 5-15, |E1 - E| < 4.4e-4 rad everywhere) only seeds the correction, whose
+//    result is accurate to O(|E1-E|^6); it is therefore evaluated in FP32 with MUFU rsqrt/lg2/ex2/rcp —
+//    validated over e in [0, 1-1e-12], |M| down to 1e-30: identical max |d5| and residual <= 7e-16.
+//  * f0 = E1 - e sinE1 - M and the correction (eqs 21-28) are FP64; divisions are rcp_nr multiplies.
+//  * sin/cos of E = E1 + d5 come from rotating sincos(E1) by d5 (three Taylor terms, exact to 1e-19):
+//    one sincos per solve instead of two.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt, double& sE, double& cE) {
     dt = t - o.tp;
     const double MA = o.nd * dt;
-    const double k = rint(MA * kInvTwoPi);
+    const double k = fma(MA, kInvTwoPi, kMagic) - kMagic;         // rint(MA / 2pi)
     double M = fma(-k, kTwoPi1, MA);
     M = fma(-k, kTwoPi2, M);
     M = fma(-k, kTwoPi3, M);
-    const double alpha = fma(o.ca1, kPi - fabs(M), kA0);          // eq 20
-    const double d = fma(alpha, o.e, 3.0 * o.ome);                 // eq 5
-    const double M2 = M * M;
-    const double ad = alpha * d;
-    const double q = fma(2.0 * ad, o.ome, -M2);                    // eq 9
-    const double r = M * fma(3.0 * ad, d - o.ome, M2);             // eq 10  (d - 1 + e = d - (1 - e))
-    const double q2 = q * q;
-    const double tt = fabs(r) + sqrt(fma(q2, q, r * r));
-    const double w = cbrt(tt * tt);                                // eq 14
-    const double den = fma(w, w + q, q2);
-    const double E1 = fma(M, den, 2.0 * r * w) / (den * d);        // eq 15
+    // ---- starter, FP32
+    const float Mf = (float)M, ef = o.ef, omef = o.omef;
+    const float alpha = fmaf(o.ca1f, (float)kPi - fabsf(Mf), (float)kA0);      // eq 20
+    const float d = fmaf(alpha, ef, 3.0f * omef);                              // eq 5
+    const float M2 = Mf * Mf;
+    const float ad = alpha * d;
+    const float q = fmaf(2.0f * ad, omef, -M2);                                // eq 9
+    const float r = Mf * fmaf(3.0f * ad, d - omef, M2);                        // eq 10
+    const float q2 = q * q;
+    const float disc = fmaxf(fmaf(q2, q, r * r), 0.0f);
+    const float tt = fabsf(r) + disc * rsqrtf(fmaxf(disc, 1e-37f));            // |r| + sqrt(q^3 + r^2)
+    const float w = exp2f(__log2f(tt) * (2.0f / 3.0f));                        // eq 14: cbrt(tt^2)
+    const float den = fmaf(w, w + q, q2);
+    const double E1 = (double)__fdividef(fmaf(Mf, den, 2.0f * r * w), den * d);   // eq 15
+    // ---- correction, FP64
     double s1, c1;
-    sincos(E1, &s1, &c1);
+    sincos_pi(E1, s1, c1);
     const double f2 = o.e * s1, f3 = o.e * c1;                     // eqs 26, 27
     const double f0 = (E1 - M) - f2;                               // eq 21
     const double f1 = 1.0 - f3;                                    // eq 25
-    const double d3 = -f0 / (f1 - f0 * f2 / (2.0 * f1));           // eq 22
-    const double d4 = -f0 / fma(d3 * d3, f3 * (1.0 / 6.0), fma(0.5 * f2, d3, f1));                       // eq 23
+    const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
+    const double d3 = -2.0 * f0 * f1 * rcp_nr(fma(2.0 * f1, f1, -f0 * f2));             // eq 22
+    const double d4 = -f0 * rcp_nr(fma(d3 * d3, f36, fma(hf2, d3, f1)));                 // eq 23
     const double d42 = d4 * d4;
-    const double d5 = -f0 / (fma(d42, f3 * (1.0 / 6.0), fma(0.5 * f2, d4, f1)) - d42 * d4 * f2 * (1.0 / 24.0));  // eqs 24, 28
+    const double d5 = -f0 * rcp_nr(fma(d42 * d4, f2 * (-1.0 / 24.0), fma(d42, f36, fma(hf2, d4, f1))));  // eqs 24, 28
     const double x2 = d5 * d5;
     const double sd = d5 * fma(x2, -1.0 / 6.0, 1.0);
     const double cd = fma(x2, fma(x2, 1.0 / 24.0, -0.5), 1.0);
@@ -79,7 +133,7 @@ __device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt
 __device__ __forceinline__ Orb load_orb(const double* sc, int lane) {
     Orb o;
     o.nd = sc[PC_nd * 32 + lane]; o.tp = sc[PC_tp * 32 + lane]; o.e = sc[PC_e * 32 + lane];
-    o.ome = sc[PC_ome * 32 + lane]; o.ca1 = sc[PC_ca1 * 32 + lane];
+    o.ef = (float)o.e; o.omef = (float)sc[PC_ome * 32 + lane]; o.ca1f = (float)sc[PC_ca1 * 32 + lane];
     return o;
 }
 
@@ -88,11 +142,13 @@ __device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double 
 // ---------------------------------------------------------------------------------------------
 // Astrometry segment (kinds 0, 1): epochs [k0, k1) of table B for this warp's 32 chains.
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT>
+template <bool GRAD, int NPT, bool LEAN>
 __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                         double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
     const int ip = B.planet;
-    const bool pasep = (B.kind == OCTO_KIND_ASTROM_PASEP);
+    // LEAN: RA/Dec table with fixed weights (no jitter / platescale / northangle) — the common case
+    const bool pasep = !LEAN && (B.kind == OCTO_KIND_ASTROM_PASEP);
+    const bool jitm = !LEAN && B.jit;
     // involved planets: the observed one, then interior companions with a mass (relative-astrometry.jl:117-133)
     int pj[NPT]; double f[NPT]; Orb orb[NPT]; double Bh[NPT], Gs[NPT], Ah[NPT], Fs[NPT];
     int ni = 1;
@@ -117,10 +173,10 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
         Bh[u] = sc[PC_Bh * 32 + lane]; Gs[u] = sc[PC_Gs * 32 + lane];
         Ah[u] = sc[PC_Ah * 32 + lane]; Fs[u] = sc[PC_Fs * 32 + lane];
     }
-    const double jit = B.idx_jitter >= 0 ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
-    const double ps = B.idx_platescale >= 0 ? in[c + (int64_t)B.idx_platescale * ld] : 1.0;
-    const double na = B.idx_northangle >= 0 ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
-    const bool rot = (B.idx_platescale >= 0) || (B.idx_northangle >= 0);
+    const double jit = (!LEAN && B.idx_jitter >= 0) ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
+    const double ps = (!LEAN && B.idx_platescale >= 0) ? in[c + (int64_t)B.idx_platescale * ld] : 1.0;
+    const double na = (!LEAN && B.idx_northangle >= 0) ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
+    const bool rot = !LEAN && ((B.idx_platescale >= 0) || (B.idx_northangle >= 0));
     double sna = 0.0, cna = 1.0;
     if (rot && !pasep) sincos(na, &sna, &cna);
     const double j2 = jit * jit;
@@ -148,7 +204,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
         double r1, r2, rho = 0.0, irho = 0.0, ra_d = y1, dec_d = y2;
         if (pasep) {
             rho = sqrt(fma(ra, ra, dec * dec));
-            irho = 1.0 / rho;
+            irho = rcp_nr(rho);
             const double pa = atan2(ra, dec);
             double pd = fmod((y1 + na) - pa + kPi, kTwoPi) - kPi;      // Julia `%` == fmod
             if (pd < -kPi) pd += kTwoPi;
@@ -163,15 +219,15 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
             r2 = dec_d - dec;
         }
         double w11, w12, w22, iv1 = 0.0, iv2 = 0.0;
-        if (!B.jit) { w11 = e1; w12 = e2; w22 = e3; }
+        if (!jitm) { w11 = e1; w12 = e2; w22 = e3; }
         else {
             const double v1 = e1 + j2, v2 = e2 + j2;
-            iv1 = 1.0 / v1; iv2 = 1.0 / v2;
+            iv1 = rcp_nr(v1); iv2 = rcp_nr(v2);
             double iom = 1.0, lom = 0.0;
             w12 = 0.0;
             if (B.has_cor) {
                 const double om = fma(-e3, e3, 1.0);
-                iom = 1.0 / om; lom = log(om);
+                iom = rcp_nr(om); lom = log(om);
                 w12 = -e3 * sqrt(iv1 * iv2) * iom;
             }
             w11 = iv1 * iom; w22 = iv2 * iom;
@@ -194,11 +250,11 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
                     g_na += fma(q2, ra_d, -q1 * dec_d);
                 }
             }
-            if (B.jit) g_jit += fma(fma(r1, q1, -1.0), iv1, fma(r2, q2, -1.0) * iv2);
+            if (jitm) g_jit += fma(fma(r1, q1, -1.0), iv1, fma(r2, q2, -1.0) * iv2);
 #pragma unroll
             for (int u = 0; u < NPT; ++u) if (u < ni) {
                 const double X = cE[u] - orb[u].e;
-                const double rD = 1.0 / fma(-orb[u].e, cE[u], 1.0);
+                const double rD = rcp_nr(fma(-orb[u].e, cE[u], 1.0));
                 L[u][0] = fma(gr, X, L[u][0]);
                 L[u][1] = fma(gr, sE[u], L[u][1]);
                 L[u][2] = fma(gd, X, L[u][2]);
@@ -214,9 +270,11 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
     }
     acc_add(acc, 0, lane, ll);
     if (GRAD) {
-        if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
-        if (B.slot_platescale >= 0) acc_add(acc, B.slot_platescale, lane, pasep ? g_ps : g_ps / ps);
-        if (B.slot_northangle >= 0) acc_add(acc, B.slot_northangle, lane, g_na);
+        if (!LEAN) {
+            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
+            if (B.slot_platescale >= 0) acc_add(acc, B.slot_platescale, lane, pasep ? g_ps : g_ps / ps);
+            if (B.slot_northangle >= 0) acc_add(acc, B.slot_northangle, lane, g_na);
+        }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             const int p = pj[u];
@@ -240,11 +298,11 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 // Radial-velocity segment (kinds 2, 3, 4).
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT>
+template <bool GRAD, int NPT, bool MARGIN>
 __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                     double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
     const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
-    const bool margin = (B.kind == OCTO_KIND_RV_STAR_MARGIN);
+    constexpr bool margin = MARGIN;
     int pj[NPT]; double f[NPT], dmu[NPT]; Orb orb[NPT]; double Pc[NPT], Ps[NPT];
     int ni = 0;
     if (star) {   // every planet, reflex of the star: -mu * radvel (rv-absolute.jl:145-154)
@@ -283,11 +341,11 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 
     double ll = 0.0, g_jit = 0.0, g_off = 0.0;
     double mA = 0.0, mS1 = 0.0, mC = 0.0, mLG = 0.0, mR2 = 0.0, mR1 = 0.0, mQ = 0.0;
-    double L[NPT][5], V[NPT][5];
+    double L[NPT][5], V[MARGIN ? NPT : 1][5];
 #pragma unroll
     for (int u = 0; u < NPT; ++u)
 #pragma unroll
-        for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; V[u][a] = 0.0; }
+        for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; if constexpr (MARGIN) V[u][a] = 0.0; }
 
     for (int k = k0; k < k1; ++k) {
         const double t = m.t[k], y = m.y1[k], e1 = m.c1[k];
@@ -296,7 +354,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
-            rD[u] = 1.0 / fma(-orb[u].e, cE[u], 1.0);
+            rD[u] = rcp_nr(fma(-orb[u].e, cE[u], 1.0));
             rv[u] = fma(Pc[u], cE[u], -Ps[u] * sE[u]) * rD[u];
             model = fma(f[u], rv[u], model);
         }
@@ -305,13 +363,13 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         if (!B.jit) iv = e1;                     // 1/σ² precomputed; normalisation is in const_ll
         else {
             const double var = e1 + j2;
-            iv = 1.0 / var;
-            if (margin) mLG += log(kTwoPi * var);
+            iv = rcp_nr(var);
+            if constexpr (MARGIN) mLG += log(kTwoPi * var);
             else ll -= 0.5 * (kLog2Pi + log(var));
         }
         const double riv = r * iv;
         double g;                                 // d ll / d model
-        if (margin) {
+        if constexpr (MARGIN) {
             mA += iv; mS1 += riv; mC = fma(r, riv, mC);
             mR2 = fma(riv, riv, mR2); mR1 = fma(riv, iv, mR1); mQ = fma(iv, iv, mQ);
             g = 2.0 * riv;
@@ -331,7 +389,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
                 L[u][0] = fma(g, dPc, L[u][0]); L[u][1] = fma(g, dPs, L[u][1]);
                 L[u][2] = fma(g, de, L[u][2]);  L[u][3] = fma(g, dM, L[u][3]);
                 L[u][4] = fma(g * dM, dt[u], L[u][4]);
-                if (margin) {
+                if constexpr (MARGIN) {
                     V[u][0] = fma(iv, dPc, V[u][0]); V[u][1] = fma(iv, dPs, V[u][1]);
                     V[u][2] = fma(iv, de, V[u][2]);  V[u][3] = fma(iv, dM, V[u][3]);
                     V[u][4] = fma(iv * dM, dt[u], V[u][4]);
@@ -339,7 +397,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             }
         }
     }
-    if (margin) {
+    if constexpr (MARGIN) {
         const int s0 = B.slot_margin;
         acc_add(acc, s0 + MA_A, lane, mA);   acc_add(acc, s0 + MA_S1, lane, mS1); acc_add(acc, s0 + MA_C, lane, mC);
         acc_add(acc, s0 + MA_LG, lane, mLG); acc_add(acc, s0 + MA_R2, lane, mR2); acc_add(acc, s0 + MA_R1, lane, mR1);
@@ -362,7 +420,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][3]);
             acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][4]);
             if (dmu[u] != 0.0) acc_add(acc, slot_planet(p, PA_mu), lane, dmu[u] * fma(Pc[u], L[u][0], Ps[u] * L[u][1]));
-            if (margin) {
+            if constexpr (MARGIN) {
                 const int v0 = B.slot_margin + MA_COUNT + p * MV_COUNT;
                 acc_add(acc, v0 + MV_Pc, lane, fu * V[u][0]); acc_add(acc, v0 + MV_Ps, lane, fu * V[u][1]);
                 acc_add(acc, v0 + MV_e, lane, fu * V[u][2]);  acc_add(acc, v0 + MV_S0, lane, fu * V[u][3]);
@@ -533,8 +591,12 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         const DevBlock& B = m.blocks[b];
         const int k0 = max(k_lo, B.start), k1 = min(k_hi, B.start + B.n);
         if (k0 >= k1) continue;
-        if (B.kind <= OCTO_KIND_ASTROM_PASEP) seg_astrom<GRAD, NPT>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
-        else seg_rv<GRAD, NPT>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+        if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
+            const bool lean = B.kind == OCTO_KIND_ASTROM_RADEC && !B.jit && B.idx_platescale < 0 && B.idx_northangle < 0;
+            if (lean) seg_astrom<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+            else seg_astrom<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+        } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) seg_rv<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
+        else seg_rv<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
     }
     __syncthreads();
 
@@ -584,7 +646,24 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
 }
 
+__global__ void k_selftest_kepler(const double* __restrict__ MA, const double* __restrict__ e, int64_t n,
+                                  double* __restrict__ sE, double* __restrict__ cE) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Orb o;
+    o.nd = 1.0; o.tp = 0.0; o.e = e[i];
+    o.ef = (float)o.e; o.omef = (float)(1.0 - o.e); o.ca1f = (float)(kA1 / (1.0 + o.e));
+    double dt, s, c;
+    kepler_sincos(o, MA[i], dt, s, c);
+    sE[i] = s; cE[i] = c;
+}
+
 }  // namespace
+
+cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c) {
+    k_selftest_kepler<<<(unsigned)((n + 255) / 256), 256>>>(d_MA, d_e, n, d_s, d_c);
+    return cudaGetLastError();
+}
 
 size_t octo_smem_bytes(const DevModel& m) {
     size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (size_t)W * m.n_acc * 32 + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
@@ -601,14 +680,18 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 }
 
 // opt every instantiation in to `smem_bytes` of dynamic shared memory (once per context)
-cudaError_t octo_kernels_init(size_t smem_bytes) {
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int* ctas_per_sm) {
     cudaError_t e;
 #define OCTO_ATTR(G, N)                                                                                            \
     e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);   \
     if (e != cudaSuccess) return e
     OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
 #undef OCTO_ATTR
-    return cudaSuccess;
+    // resident CTAs per SM of the gradient kernel this model dispatches to (drives the launch geometry)
+    if (m.n_planets == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 1>, W * 32, smem_bytes);
+    else if (m.n_planets == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 2>, W * 32, smem_bytes);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 4>, W * 32, smem_bytes);
+    return e;
 }
 
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,

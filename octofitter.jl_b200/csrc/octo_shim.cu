@@ -142,8 +142,9 @@ void free_ws(Workspace* w) {
     delete w;
 }
 
-// grid: chain groups x epoch splits.  Splits are added only while the chain groups alone cannot fill the
-// SMs, and never below OCTO_MIN_SLICE epochs per warp.
+// grid: chain groups x epoch splits.  Small problems: as many splits as fill the resident CTA slots exactly once
+// (an integral number of waves, never below min_slice epochs per warp).  Large problems (>= 4 waves): ~32 epochs
+// per warp so the per-CTA prologue/epilogue is amortised and the hardware CTA scheduler balances the tail.
 LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     LaunchGeom g;
     g.block = OCTO_WARPS * 32;
@@ -153,9 +154,24 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     int64_t max_gy = E / ((int64_t)min_slice * OCTO_WARPS);
     if (max_gy < 1) max_gy = 1;
     if (max_gy > 65535) max_gy = 65535;
-    const int64_t target = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
-    int64_t gy = (target + g.gx - 1) / g.gx;
-    if (gy > max_gy) gy = max_gy;
+    const int64_t resident = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
+    int64_t gy_fill = (resident + g.gx - 1) / g.gx;
+    if (gy_fill > max_gy) gy_fill = max_gy;
+    int64_t gy = gy_fill;
+    if ((int64_t)g.gx * gy_fill >= 4 * resident) {
+        const int64_t gy_big = E / (32 * OCTO_WARPS);
+        gy = gy_big > gy_fill ? (gy_big < max_gy ? gy_big : max_gy) : gy_fill;
+    } else if ((int64_t)g.gx * max_gy > resident) {
+        // pick the split count whose CTA total is closest below an integral number of waves
+        double best_eff = -1.0;
+        const int64_t hi = max_gy < gy_fill * 4 + 8 ? max_gy : gy_fill * 4 + 8;
+        for (int64_t c = gy_fill > 2 ? gy_fill - 2 : 1; c <= hi; ++c) {
+            const double waves = (double)(g.gx * c) / (double)resident;
+            if (waves < 0.9) continue;
+            const double eff = waves / std::ceil(waves);
+            if (eff > best_eff + 1e-9) { best_eff = eff; gy = c; if (eff >= 0.95) break; }
+        }
+    }
     if (gy < 1) gy = 1;
     g.gy = (int)gy;
     g.slice = (int)((E + gy * OCTO_WARPS - 1) / (gy * OCTO_WARPS));
@@ -343,15 +359,17 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ctx->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete ctx; return fail(OCTO_ERR_ARG, "model too large: accumulator slots exceed shared memory");
     }
-    if (const char* s = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, atoi(s));
     if (const char* s = getenv("OCTO_B200_SLICE")) ctx->slice_override = std::max(1, atoi(s));
     ce = cudaMalloc((void**)&ctx->d_tables, T.size() * sizeof(double));
     if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaMalloc tables"); }
     ce = cudaMemcpy(ctx->d_tables, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
     m.t = ctx->d_tables; m.y1 = m.t + E; m.y2 = m.y1 + E; m.c1 = m.y2 + E; m.c2 = m.c1 + E; m.c3 = m.c2 + E;
-    ce = octo_kernels_init(ctx->smem);
+    int occ = 0;
+    ce = octo_kernels_init(m, ctx->smem, &occ);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
+    ctx->ctas_per_sm = occ > 0 ? occ : 1;
+    if (const char* s = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, atoi(s));
     *out = ctx;
     return OCTO_OK;
 }
@@ -377,6 +395,24 @@ int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t l
     CU(cudaSetDevice(ctx->device));
     Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);   // partial buffer + tickets of this stream
     return enqueue(ctx, w, d_g != nullptr, d_in, n, ld, d_ll, d_g, ld, (cudaStream_t)stream);
+}
+
+// diagnostic: the device Kepler solve on its own (mean anomaly MA, eccentricity e) -> sin E, cos E
+int octo_selftest_kepler(int32_t device, const double* MA, const double* e, int64_t n, double* sinE, double* cosE) {
+    if (!MA || !e || !sinE || !cosE || n < 0) return fail(OCTO_ERR_ARG, "null argument");
+    if (n == 0) return OCTO_OK;
+    CU(cudaSetDevice(device));
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, (size_t)4 * n * sizeof(double)));
+    int rc = OCTO_OK;
+    cudaError_t ce = cudaMemcpy(d, MA, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d + n, e, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = octo_selftest_kepler_launch(d, d + n, n, d + 2 * n, d + 3 * n);
+    if (ce == cudaSuccess) ce = cudaMemcpy(sinE, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(cosE, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (ce != cudaSuccess) rc = fail_cuda(ce, "selftest");
+    cudaFree(d);
+    return rc;
 }
 
 int32_t octo_n_in(const OctoCtx* ctx) { return ctx ? ctx->m.n_in : -1; }

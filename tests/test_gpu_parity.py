@@ -167,3 +167,35 @@ def test_concurrent_calls_threads(oracle_lib):
     for o in out:
         assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1])
     model.close()
+
+
+def test_device_kepler_edge_cases(oracle_lib):
+    """The device solve (FP32 Markley starter + FP64 fifth-order correction) against the oracle's Markley
+    solve and Kepler's equation itself, including e -> 1, M -> 0, |M| = pi and many revolutions."""
+    rng = np.random.default_rng(17)
+    n = 200_000
+    MA = np.concatenate([rng.uniform(-np.pi, np.pi, n), rng.uniform(-300, 300, n // 4),
+                         10.0 ** rng.uniform(-30, -2, n // 4) * rng.choice([-1, 1], n // 4),
+                         [0.0, np.pi, -np.pi, np.nextafter(np.pi, 4), 1e-300, 2 * np.pi, 12345.678]])
+    e = np.concatenate([rng.uniform(0, 1, n) ** 0.3, rng.uniform(0, 0.99, n // 4),
+                        1 - 10.0 ** rng.uniform(-9, -1, n // 4), [0.0, 0.5, 0.5, 0.5, 0.999, 0.3, 0.3]])
+    e = np.clip(e, 0, 1 - 1e-9)
+    s, c = np.empty_like(MA), np.empty_like(MA)
+    lib = octo.load_library()
+    rc = lib.octo_selftest_kepler(0, MA.ctypes.data, e.ctypes.data, len(MA), s.ctypes.data, c.ctypes.data)
+    assert rc == 0, lib.octo_last_error()
+    assert np.all(np.isfinite(s)) and np.all(np.isfinite(c))
+    assert np.abs(s * s + c * c - 1).max() < 1e-15
+    E = np.arctan2(s, c)
+    M = np.array([oracle_lib.lib().octo_oracle_rem2pi(float(x)) for x in MA[-(n // 2 + 7):]])
+    # Kepler's equation residual, modulo 2 pi (|M| = pi may come back as the other branch)
+    res = E - e * s - np.concatenate([np.zeros(len(MA) - len(M)), M])
+    res[: len(MA) - len(M)] -= MA[: len(MA) - len(M)]
+    res = res - 2 * np.pi * np.round(res / (2 * np.pi))
+    assert np.abs(res).max() < 3e-15
+    # against the oracle's Markley solve where the problem is well conditioned
+    idx = rng.choice(len(MA), 5000, replace=False)
+    Eo = np.array([oracle_lib.kepler(float(MA[i]), float(e[i])) for i in idx])
+    ok = e[idx] < 0.99
+    assert np.abs(np.sin(Eo[ok]) - s[idx][ok]).max() < 2e-14
+    assert np.abs(np.cos(Eo[ok]) - c[idx][ok]).max() < 2e-14
