@@ -221,15 +221,22 @@ def main():
     launches = model.kernel_launches - launches0 - max(3, args.warmup)
     t_dev = float(ms.sum()) * 1e-3
 
-    # end-to-end through the public host API
+    # end-to-end through the public host API: inputs in pinned host memory, outputs read back every step
+    x_pin = model.pinned_empty(x.shape); x_pin[...] = x
+    out = (model.pinned_empty(n), model.pinned_empty((n, n_in)))
     for _ in range(max(3, min(args.warmup, 10))):
-        model.ln_like_and_gradient(x)
+        model.ln_like_and_gradient(x_pin, out=out)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ll_h, g_h = model.ln_like_and_gradient(x)
+        ll_h, g_h = model.ln_like_and_gradient(x_pin, out=out)
     t_e2e = time.perf_counter() - t0
+    # the same call with ordinary (pageable) numpy arrays, staged through the library's pinned buffers
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.ln_like_and_gradient(x)
+    t_e2e_pageable = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if world > 1:
@@ -264,7 +271,9 @@ def main():
             "e2e": {"value": pairs_step * args.steps / t_e2e, "unit": "evals/s",
                     "h2d_bytes_per_step": n * n_in * 8, "d2h_bytes_per_step": n * (n_in + 1) * 8,
                     "ms_per_step": t_e2e / args.steps * 1e3,
-                    "api": "LogDensityModel.ln_like_and_gradient(host ndarray) -> octo_logp_grad (pinned staging inside)"},
+                    "ms_per_step_pageable_host_arrays": t_e2e_pageable / args.steps * 1e3,
+                    "api": "LogDensityModel.ln_like_and_gradient(pinned host ndarray, out=pinned) -> C ABI octo_logp_grad: "
+                           "H2D + kernel + D2H + stream sync per step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -39,6 +39,7 @@
 #ifndef OCTO_B200_H
 #define OCTO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -155,6 +156,12 @@ int  octo_logp(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, dou
 int  octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld,
                     double* ll, double* g_in);
 
+/* Page-locked host memory for the HOST-buffer entry points.  Buffers that come from octo_alloc_pinned
+ * are copied to/from the device directly (no staging copy); any other host pointer works too and is
+ * staged through the context's own pinned buffers.  Returns NULL on failure (see octo_last_error). */
+void* octo_alloc_pinned(size_t bytes);
+void  octo_free_pinned(void* p);
+
 /* Same, DEVICE buffers on the context's device, enqueued on `stream`
  * (a cudaStream_t; NULL = the legacy default stream). Asynchronous: the caller
  * synchronises. g_in may be NULL for value only. */
@@ -188,14 +195,19 @@ int  octo_pt_unique_id(void* out128);
 int  octo_pt_init(OctoCtx* ctx, const void* nccl_unique_id, int32_t rank, int32_t world,
                   int32_t n_replicas_local, uint64_t seed);
 /*
- * d_ll_pair: DEVICE [n_replicas_local x 2] (ℓ_ref, ℓ_target) row-major for the local replicas.
- * beta: HOST [n_replicas_total] ladder (β by chain index, ascending).
- * chain_of_replica: HOST in/out [n_replicas_total] — which ladder index each replica holds.
- * round: swap round counter (even rounds pair (0,1),(2,3).., odd rounds (1,2),(3,4)..).
+ * ll_pair: HOST [n_replicas_local x 2] row-major (l_ref, l_target) of this rank's replicas (l_target from
+ *          octo_logp, l_ref from the caller's prior-only model, ext/OctofitterPigeonsExt:61-67).
+ * beta: HOST [n_replicas_total] ladder, ascending.
+ * chain_of_replica: HOST in/out [n_replicas_total] — which ladder rung each replica holds (a permutation).
+ * round: swap round counter (even rounds pair rungs (0,1),(2,3).., odd rounds (1,2),(3,4)..).
  * accepted: HOST out [n_replicas_total-1] 0/1 per adjacent pair (may be NULL).
+ * Collective: every rank calls it with the same beta / chain_of_replica / round.
  */
-int  octo_pt_swap_round(OctoCtx* ctx, const double* d_ll_pair, const double* beta,
+int  octo_pt_swap_round(OctoCtx* ctx, const double* ll_pair, const double* beta,
                         int32_t* chain_of_replica, int64_t round, int32_t* accepted);
+/* The decision step alone (pure host code, no CUDA/NCCL): ll_pair_all is [n_replicas_total x 2]. */
+int  octo_pt_decide(const double* ll_pair_all, const double* beta, int32_t* chain_of_replica,
+                    int32_t n_replicas_total, int64_t round, uint64_t seed, int32_t* accepted);
 void octo_pt_finalize(OctoCtx* ctx);
 
 const char* octo_last_error(void);

@@ -11,5 +11,6 @@ from ._abi import (OctoConstants, OctoLayout, OctoObsBlock, default_constants, l
 from .model import (Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, StarAbsoluteRVObs,
                     StarAbsoluteRVLikelihood, MarginalizedStarAbsoluteRVObs, MarginalizedStarAbsoluteRVLikelihood,
                     PlanetRelativeRVObs, PlanetRelativeRVLikelihood, Planet, System, ModelSpec, LogDensityModel, OctoError)
+from .pt import ParallelTempering
 
 __all__ = [n for n in dir() if not n.startswith("_")]

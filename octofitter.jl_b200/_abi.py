@@ -123,6 +123,10 @@ def load_library(path: str | None = None):
     lib.octo_logp.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_logp_grad.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.octo_logp_grad_device.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    lib.octo_alloc_pinned.argtypes = [C.c_size_t]
+    lib.octo_alloc_pinned.restype = vp
+    lib.octo_free_pinned.argtypes = [vp]
+    lib.octo_free_pinned.restype = None
     lib.octo_selftest_kepler.argtypes = [i32, vp, vp, i64, vp, vp]
     lib.octo_n_in.argtypes = [vp]
     lib.octo_n_in.restype = i32
@@ -138,6 +142,7 @@ def load_library(path: str | None = None):
     lib.octo_pt_unique_id.argtypes = [vp]
     lib.octo_pt_init.argtypes = [vp, vp, i32, i32, i32, C.c_uint64]
     lib.octo_pt_swap_round.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.octo_pt_decide.argtypes = [vp, vp, vp, i32, i64, C.c_uint64, vp]
     lib.octo_pt_finalize.argtypes = [vp]
     lib.octo_pt_finalize.restype = None
     lib.octo_last_error.restype = C.c_char_p
@@ -148,6 +153,6 @@ def load_library(path: str | None = None):
 
 EXPORTED_SYMBOLS = (
     "octo_default_constants", "octo_abi_version", "octo_create", "octo_destroy", "octo_logp", "octo_logp_grad",
-    "octo_logp_grad_device", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
+    "octo_logp_grad_device", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
-    "octo_pt_finalize", "octo_last_error")
+    "octo_pt_decide", "octo_pt_finalize", "octo_last_error")

@@ -12,6 +12,17 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
 
+def build_variant(out, defines):
+    """Tuning builds (e.g. -DOCTO_MIN_CTAS=3 -DOCTO_UNROLL=2) into another path; select with OCTO_B200_LIB."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out, "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    return r.stdout + r.stderr
+
+
 def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)

@@ -19,9 +19,10 @@ enum PlanetConst {
     PC_mu,                            // mass*mjup2msol/M, 0 when the planet has no mass variable
     PC_a,
     // epilogue only
-    PC_sinW, PC_cosW, PC_sinw, PC_cosw, PC_sini, PC_cosi, PC_M, PC_plx, PC_sc /*a*c2a*/, PC_c2a,
+    PC_sinW, PC_cosW /* = PC_sinW + 1 */, PC_sinw, PC_cosw, PC_sini, PC_cosi, PC_M, PC_plx, PC_sc /*a*c2a*/, PC_c2a,
     PC_K /*RV semi-amplitude*/, PC_Kb /*K / sin i*/,
     PC_A, PC_B, PC_F, PC_G,
+    PC_inv_s, PC_inv_a, PC_inv_M,
     PC_COUNT
 };
 
@@ -45,6 +46,8 @@ struct DevBlock {
 struct DevModel {
     OctoConstants c;
     double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
+    double two_pi_over_kyd;  // 2π / kepler_year_days: mean motion [rad/day] = this * sqrt(M/a) / a
+    double c2a_per_plx;      // rad2as*1e3 / (1000*pc2au): mas per AU per mas of parallax
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
     int64_t n_epochs;

@@ -19,17 +19,21 @@
 //   epilogue  -> one lane per chain maps the raw sums to ∂ll/∂(inputs) by the chain rule, writes coalesced rows
 #include "octo_internal.h"
 #include <math_constants.h>
+#include <cstdio>
 
 namespace {
 
 constexpr int W = OCTO_WARPS;
+#ifndef OCTO_MIN_CTAS
+#define OCTO_MIN_CTAS 2          // resident CTAs/SM the register allocator targets
+#endif
+#ifndef OCTO_UNROLL
+#define OCTO_UNROLL 1            // epochs in flight per warp in the lean loops
+#endif
+#define OCTO_PRAGMA(x) _Pragma(#x)
+#define OCTO_UNROLL_LOOP(n) OCTO_PRAGMA(unroll n)
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kTwoPi = 6.283185307179586477;
-constexpr double kInvTwoPi = 0.15915494309189533577;
-// 2π split for a 3-term Cody-Waite reduction (33 + 33 + 53 bits): MA - k*2π is exact to < 1e-30*|k|
-constexpr double kTwoPi1 = 0x1.921fb54400000p+2;
-constexpr double kTwoPi2 = 0x1.0b4611a600000p-32;
-constexpr double kTwoPi3 = 0x1.3198a2e037073p-67;
 constexpr double kLog2Pi = 1.8378770664093454836;
 // Markley eq. 20: alpha = kA0 + ca1 * (pi - |M|),  ca1 = 1.6 pi / ((pi^2 - 6)(1 + e))
 constexpr double kA0 = 3.0 * kPi * kPi / (kPi * kPi - 6.0);
@@ -39,43 +43,71 @@ struct Orb { double nd, tp, e; float ef, omef, ca1f; };
 
 // ---------------------------------------------------------------------------------------------
 // Branch-free FP64 building blocks with known input ranges (no libm slow paths, no divergence).
+// FP64 literals live in the constant bank: DFMA/DMUL/DADD read them as c[3][..] operands, so the hot loop
+// spends no issue slots (MOV/UMOV pairs) or registers on materialising 64-bit immediates.
 // ---------------------------------------------------------------------------------------------
+struct KConst {
+    double magic, inv_two_pi, two_pi1, two_pi2, two_pi3, two_over_pi, pio2_hi, pio2_lo;
+    double s[6], c[6];
+    double one, half, mhalf, sixth, msixth, r24, mr24, two, mtwo;
+};
+__constant__ KConst kc = {
+    6755399441055744.0,            // 1.5 * 2^52: (x + magic) - magic == rint(x) for |x| < 2^51
+    // 1/2pi, then 2pi split 33 + 33 + 53 bits for a 3-term Cody-Waite reduction (exact to < 1e-30 |k|)
+    0.15915494309189533577, 0x1.921fb54400000p+2, 0x1.0b4611a600000p-32, 0x1.3198a2e037073p-67,
+    0.63661977236758138243, 1.57079632679489655800e+00, 6.12323399573676603587e-17,
+    // fdlibm __kernel_sin S1..S6 (highest degree first), __kernel_cos C1..C6 (highest first)
+    {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+     -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01},
+    {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02},
+    1.0, 0.5, -0.5, 1.0 / 6.0, -1.0 / 6.0, 1.0 / 24.0, -1.0 / 24.0, 2.0, -2.0};
+
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 1/x with one Newton step (~2^-40): enough for Markley's d3/d4, whose relative error reaches the final
+// d5 multiplied by (f2 d / 2 f1)^2 ~ 1e-7.
+__device__ __forceinline__ double rcp_nr1(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, kc.one);
+    return fma(y, e, y);
+}
+
 // 1/x: MUFU.RCP64H seed (~2^-20) + two Newton steps -> ~1 ulp.  x finite, normal, non-zero.
 __device__ __forceinline__ double rcp_nr(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
+    double e = fma(-x, y, kc.one);
     y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
+    e = fma(-x, y, kc.one);
     return fma(y, e, y);
 }
-
-constexpr double kMagic = 6755399441055744.0;      // 1.5 * 2^52: (x + kMagic) - kMagic == rint(x) for |x| < 2^51
-constexpr double kTwoOverPi = 0.63661977236758138243;
-constexpr double kPio2Hi = 1.57079632679489655800e+00;
-constexpr double kPio2Lo = 6.12323399573676603587e-17;
 
 // sin and cos for |x| <= ~4 (here x = E1 in [-pi, pi]): one quadrant reduction, fdlibm kernel polynomials on
 // [-pi/4, pi/4] (< 1 ulp), quadrant fix-up by selects.
 __device__ __forceinline__ void sincos_pi(double x, double& s, double& c) {
-    const double tq = fma(x, kTwoOverPi, kMagic);
+    const double tq = fma(x, kc.two_over_pi, kc.magic);
     const int q = __double2loint(tq);
-    const double kq = tq - kMagic;
-    double r = fma(-kq, kPio2Hi, x);
-    r = fma(-kq, kPio2Lo, r);
+    const double kq = tq - kc.magic;
+    double r = fma(-kq, kc.pio2_hi, x);
+    r = fma(-kq, kc.pio2_lo, r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kc.s[0], kc.s[1]);
+    ps = fma(z, ps, kc.s[2]);
+    ps = fma(z, ps, kc.s[3]);
+    ps = fma(z, ps, kc.s[4]);
+    ps = fma(z, ps, kc.s[5]);
     const double sr = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    double pc = fma(z, kc.c[0], kc.c[1]);
+    pc = fma(z, pc, kc.c[2]);
+    pc = fma(z, pc, kc.c[3]);
+    pc = fma(z, pc, kc.c[4]);
+    pc = fma(z, pc, kc.c[5]);
+    const double cr = fma(z * z, pc, fma(z, kc.mhalf, kc.one));
     const double s0 = (q & 1) ? cr : sr;
     const double c0 = (q & 1) ? sr : cr;
     s = (q & 2) ? -s0 : s0;
@@ -94,10 +126,10 @@ __device__ __forceinline__ void sincos_pi(double x, double& s, double& c) {
 __device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt, double& sE, double& cE) {
     dt = t - o.tp;
     const double MA = o.nd * dt;
-    const double k = fma(MA, kInvTwoPi, kMagic) - kMagic;         // rint(MA / 2pi)
-    double M = fma(-k, kTwoPi1, MA);
-    M = fma(-k, kTwoPi2, M);
-    M = fma(-k, kTwoPi3, M);
+    const double k = fma(MA, kc.inv_two_pi, kc.magic) - kc.magic;     // rint(MA / 2pi)
+    double M = fma(-k, kc.two_pi1, MA);
+    M = fma(-k, kc.two_pi2, M);
+    M = fma(-k, kc.two_pi3, M);
     // ---- starter, FP32
     const float Mf = (float)M, ef = o.ef, omef = o.omef;
     const float alpha = fmaf(o.ca1f, (float)kPi - fabsf(Mf), (float)kA0);      // eq 20
@@ -107,25 +139,25 @@ __device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt
     const float q = fmaf(2.0f * ad, omef, -M2);                                // eq 9
     const float r = Mf * fmaf(3.0f * ad, d - omef, M2);                        // eq 10
     const float q2 = q * q;
-    const float disc = fmaxf(fmaf(q2, q, r * r), 0.0f);
-    const float tt = fabsf(r) + disc * rsqrtf(fmaxf(disc, 1e-37f));            // |r| + sqrt(q^3 + r^2)
-    const float w = exp2f(__log2f(tt) * (2.0f / 3.0f));                        // eq 14: cbrt(tt^2)
+    const float disc = fmaxf(fmaf(q2, q, r * r), 1e-30f);
+    const float tt = fmaf(disc, mufu_rsqrt(disc), fabsf(r));                   // |r| + sqrt(q^3 + r^2)
+    const float w = mufu_ex2(mufu_lg2(tt) * (2.0f / 3.0f));                    // eq 14: cbrt(tt^2)
     const float den = fmaf(w, w + q, q2);
-    const double E1 = (double)__fdividef(fmaf(Mf, den, 2.0f * r * w), den * d);   // eq 15
+    const double E1 = (double)(fmaf(Mf, den, 2.0f * r * w) * mufu_rcp(den * d));   // eq 15
     // ---- correction, FP64
     double s1, c1;
     sincos_pi(E1, s1, c1);
     const double f2 = o.e * s1, f3 = o.e * c1;                     // eqs 26, 27
     const double f0 = (E1 - M) - f2;                               // eq 21
-    const double f1 = 1.0 - f3;                                    // eq 25
-    const double hf2 = 0.5 * f2, f36 = f3 * (1.0 / 6.0);
-    const double d3 = -2.0 * f0 * f1 * rcp_nr(fma(2.0 * f1, f1, -f0 * f2));             // eq 22
-    const double d4 = -f0 * rcp_nr(fma(d3 * d3, f36, fma(hf2, d3, f1)));                 // eq 23
+    const double f1 = kc.one - f3;                                 // eq 25
+    const double hf2 = kc.half * f2, f36 = f3 * kc.sixth;
+    const double d3 = kc.mtwo * f0 * f1 * rcp_nr1(fma(kc.two * f1, f1, -f0 * f2));      // eq 22
+    const double d4 = -f0 * rcp_nr1(fma(d3 * d3, f36, fma(hf2, d3, f1)));                // eq 23
     const double d42 = d4 * d4;
-    const double d5 = -f0 * rcp_nr(fma(d42 * d4, f2 * (-1.0 / 24.0), fma(d42, f36, fma(hf2, d4, f1))));  // eqs 24, 28
+    const double d5 = -f0 * rcp_nr(fma(d42 * d4, f2 * kc.mr24, fma(d42, f36, fma(hf2, d4, f1))));  // eqs 24, 28
     const double x2 = d5 * d5;
-    const double sd = d5 * fma(x2, -1.0 / 6.0, 1.0);
-    const double cd = fma(x2, fma(x2, 1.0 / 24.0, -0.5), 1.0);
+    const double sd = d5 * fma(x2, kc.msixth, kc.one);
+    const double cd = fma(x2, fma(x2, kc.r24, kc.mhalf), kc.one);
     sE = fma(s1, cd, c1 * sd);
     cE = fma(c1, cd, -s1 * sd);
 }
@@ -188,6 +220,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 #pragma unroll
         for (int a = 0; a < 7; ++a) L[u][a] = 0.0;
 
+    OCTO_UNROLL_LOOP(OCTO_UNROLL)
     for (int k = k0; k < k1; ++k) {
         const double t = m.t[k], y1 = m.y1[k], y2 = m.y2[k];
         const double e1 = m.c1[k], e2 = m.c2[k], e3 = m.c3[k];
@@ -347,6 +380,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 #pragma unroll
         for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; if constexpr (MARGIN) V[u][a] = 0.0; }
 
+    OCTO_UNROLL_LOOP(OCTO_UNROLL)
     for (int k = k0; k < k1; ++k) {
         const double t = m.t[k], y = m.y1[k], e1 = m.c1[k];
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
@@ -433,54 +467,88 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 
 // ---------------------------------------------------------------------------------------------
 // Prologue: per chain*planet constants (ref a3: KepOrbit / Visual ctor caches) -> shared memory.
-// Returns whether the planet's elements are valid for this chain.
+// Two phases so that the 8 warps of a CTA share the latency: phase 1 = four independent tasks per planet
+// (sincos i | sincos ω | sincos Ω | scalar chain: validity, s, mean motion, K/sin i, mas/AU, mu), phase 2 =
+// the Thiele-Innes / RV products.  All branch-free (rcp/rsqrt Newton, quadrant-reduced sincos).
 // ---------------------------------------------------------------------------------------------
-__device__ bool planet_prologue(const DevModel& m, int p, const double* __restrict__ in, int64_t c, int64_t ld,
-                                double* sc, int lane) {
+__device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 normal: seed + 3 Newton steps
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = kc.half * x;
+#pragma unroll
+    for (int it = 0; it < 3; ++it) y = fma(y, fma(-hx * y, y, kc.half), y);
+    return y;
+}
+
+__device__ __forceinline__ void sincos_any(double x, double& s, double& c) {   // any finite angle of sane size
+    const double k = fma(x, kc.inv_two_pi, kc.magic) - kc.magic;
+    double r = fma(-k, kc.two_pi1, x);
+    r = fma(-k, kc.two_pi2, r);
+    r = fma(-k, kc.two_pi3, r);
+    sincos_pi(r, s, c);
+}
+
+// returns validity of what the task looked at
+__device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
+                              double* sc, int lane) {
+    if (kind < 3) {
+        const int idx = kind == 0 ? m.idx_i[p] : (kind == 1 ? m.idx_w[p] : m.idx_W[p]);
+        const double x = in[c + (int64_t)idx * ld];
+        const bool ok = isfinite(x) && fabs(x) < 1e9;
+        double sn, cs;
+        sincos_any(ok ? x : 0.0, sn, cs);
+        const int ks = kind == 0 ? PC_sini : (kind == 1 ? PC_sinw : PC_sinW);
+        sc[ks * 32 + lane] = sn; sc[(ks + 1) * 32 + lane] = cs;
+        return ok;
+    }
     double a = in[c + (int64_t)m.idx_a[p] * ld], e = in[c + (int64_t)m.idx_e[p] * ld];
-    double inc = in[c + (int64_t)m.idx_i[p] * ld], w = in[c + (int64_t)m.idx_w[p] * ld];
-    double Wn = in[c + (int64_t)m.idx_W[p] * ld], tp = in[c + (int64_t)m.idx_tp[p] * ld];
+    double tp = in[c + (int64_t)m.idx_tp[p] * ld];
     double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
     double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
-    const bool fin = isfinite(a) && isfinite(e) && isfinite(inc) && isfinite(w) && isfinite(Wn) && isfinite(tp) &&
-                     isfinite(M) && isfinite(plx) && isfinite(mass);
+    const bool fin = isfinite(a) && isfinite(e) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
     const bool ok = fin && (e >= 0.0) && (e < 1.0) && (a > 0.0) && (M > 0.0) && (plx > 0.0);
-    if (!ok) { a = 1.0; e = 0.1; inc = 0.5; w = 0.0; Wn = 0.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
-    const double s2 = fma(-e, e, 1.0), s = sqrt(s2);
-    const double period_days = sqrt(a * a * a / M) * m.c.kepler_year_days;
-    const double nd = kTwoPi / period_days;
-    const double dist = 1000.0 / plx * m.c.pc2au;
-    const double c2a = m.c.rad2as * 1e3 / dist;
-    const double scl = a * c2a;
-    double si, ci, sw, cw, sW, cW;
-    sincos(inc, &si, &ci); sincos(w, &sw, &cw); sincos(Wn, &sW, &cW);
+    if (!ok) { a = 1.0; e = 0.1; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
+    const double s2 = fma(-e, e, 1.0);
+    const double inv_s = rsqrt_nr(s2), s = s2 * inv_s;
+    const double inv_a = rcp_nr(a), inv_M = rcp_nr(M);
+    const double Moa = M * inv_a;                               // M / a
+    const double rt = Moa * rsqrt_nr(Moa);                      // sqrt(M / a)
+    const double nd = m.two_pi_over_kyd * rt * inv_a;           // 2π / (sqrt(a³/M) * kepler_year_days)
+    const double c2a = plx * m.c2a_per_plx;                     // rad2as*1e3 / (1000/plx * pc2au)  [mas/AU]
+    sc[PC_nd * 32 + lane] = nd;        sc[PC_tp * 32 + lane] = tp;  sc[PC_e * 32 + lane] = e;
+    sc[PC_ome * 32 + lane] = 1.0 - e;  sc[PC_ca1 * 32 + lane] = kA1 * rcp_nr(1.0 + e);
+    sc[PC_s * 32 + lane] = s;          sc[PC_inv_s * 32 + lane] = inv_s;
+    sc[PC_a * 32 + lane] = a;          sc[PC_inv_a * 32 + lane] = inv_a;
+    sc[PC_M * 32 + lane] = M;          sc[PC_inv_M * 32 + lane] = inv_M;
+    sc[PC_plx * 32 + lane] = plx;      sc[PC_c2a * 32 + lane] = c2a; sc[PC_sc * 32 + lane] = a * c2a;
+    sc[PC_Kb * 32 + lane] = m.kappa * rt * inv_s;               // K / sin i
+    sc[PC_mu * 32 + lane] = mass * m.c.mjup2msol * inv_M;
+    return ok;
+}
+
+__device__ __noinline__ void prologue_products(double* sc, int lane) {
+    const double sW = sc[PC_sinW * 32 + lane], cW = sc[PC_cosW * 32 + lane], sw = sc[PC_sinw * 32 + lane];
+    const double cw = sc[PC_cosw * 32 + lane], si = sc[PC_sini * 32 + lane], ci = sc[PC_cosi * 32 + lane];
+    const double s = sc[PC_s * 32 + lane], scl = sc[PC_sc * 32 + lane];
     const double A = cW * cw - sW * sw * ci, Bc = sW * cw + cW * sw * ci;
     const double F = -cW * sw - sW * cw * ci, G = -sW * sw + cW * cw * ci;
-    const double Kb = m.kappa * sqrt(M / a) / s;      // K / sin i
-    const double K = Kb * si;
-    sc[PC_nd * 32 + lane] = nd;       sc[PC_tp * 32 + lane] = tp;   sc[PC_e * 32 + lane] = e;
-    sc[PC_ome * 32 + lane] = 1.0 - e; sc[PC_ca1 * 32 + lane] = kA1 / (1.0 + e); sc[PC_s * 32 + lane] = s;
+    const double K = sc[PC_Kb * 32 + lane] * si;
+    sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = Bc; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
     sc[PC_Bh * 32 + lane] = scl * Bc; sc[PC_Gs * 32 + lane] = scl * s * G;
     sc[PC_Ah * 32 + lane] = scl * A;  sc[PC_Fs * 32 + lane] = scl * s * F;
-    sc[PC_Pc * 32 + lane] = K * cw * s2; sc[PC_Ps * 32 + lane] = K * sw * s;
-    sc[PC_mu * 32 + lane] = mass * m.c.mjup2msol / M;
-    sc[PC_a * 32 + lane] = a;
-    sc[PC_sinW * 32 + lane] = sW; sc[PC_cosW * 32 + lane] = cW; sc[PC_sinw * 32 + lane] = sw; sc[PC_cosw * 32 + lane] = cw;
-    sc[PC_sini * 32 + lane] = si; sc[PC_cosi * 32 + lane] = ci; sc[PC_M * 32 + lane] = M; sc[PC_plx * 32 + lane] = plx;
-    sc[PC_sc * 32 + lane] = scl;  sc[PC_c2a * 32 + lane] = c2a; sc[PC_K * 32 + lane] = K; sc[PC_Kb * 32 + lane] = Kb;
-    sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = Bc; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
-    return ok;
+    sc[PC_K * 32 + lane] = K;
+    sc[PC_Pc * 32 + lane] = K * cw * s * s; sc[PC_Ps * 32 + lane] = K * sw * s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Epilogue: raw epoch sums R[slot] -> ll and d ll / d inputs for one chain (one lane).
 // ---------------------------------------------------------------------------------------------
 template <bool GRAD>
-__device__ void chain_epilogue(const DevModel& m, const double* s_const, double* R, double* s_g,
+__device__ __noinline__ void chain_epilogue(const DevModel& m, const double* s_const, double* R, double* s_g,
                                const double* __restrict__ in, int64_t c, int64_t ld, int lane, double& ll_out) {
     double ll = R[0 * 32 + lane] + m.const_ll;
-    if (GRAD) for (int k = 0; k < m.n_in; ++k) s_g[k * 32 + lane] = 0.0;
-    // marginalised RV tables first: they fold their V-sums into the planet sums
+    // s_g was zeroed in the prologue.  marginalised RV tables first: they fold their V-sums into the planet sums
+#pragma unroll 1
     for (int b = 0; b < m.n_blocks; ++b) {
         const DevBlock& B = m.blocks[b];
         if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
@@ -493,6 +561,7 @@ __device__ void chain_epilogue(const DevModel& m, const double* s_const, double*
                 const double R2 = R[(s0 + MA_R2) * 32 + lane], R1 = R[(s0 + MA_R1) * 32 + lane], Q = R[(s0 + MA_Q) * 32 + lane];
                 const double jit = in[c + (int64_t)B.idx_jitter * ld];
                 s_g[B.idx_jitter * 32 + lane] += 2.0 * jit * (-A + R2 - 2.0 * rbar * R1 + rbar * rbar * Q + Q / A);
+#pragma unroll 1
                 for (int p = 0; p < m.n_planets; ++p) {
                     const int v0 = s0 + MA_COUNT + p * MV_COUNT;
                     const double k2 = -2.0 * rbar;
@@ -512,11 +581,13 @@ __device__ void chain_epilogue(const DevModel& m, const double* s_const, double*
         }
     }
     if (GRAD) {
+#pragma unroll 1
         for (int p = 0; p < m.n_planets; ++p) {
             const double* sc = s_const + p * PC_COUNT * 32;
             auto C = [&](int k) { return sc[k * 32 + lane]; };
             auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
-            const double a = C(PC_a), e = C(PC_e), s = C(PC_s), M = C(PC_M), plx = C(PC_plx), nd = C(PC_nd);
+            const double e = C(PC_e), s = C(PC_s), nd = C(PC_nd);
+            const double inv_a = C(PC_inv_a), inv_M = C(PC_inv_M), inv_s = C(PC_inv_s);
             const double sW = C(PC_sinW), cW = C(PC_cosW), sw = C(PC_sinw), cw = C(PC_cosw), si = C(PC_sini), ci = C(PC_cosi);
             const double A = C(PC_A), Bc = C(PC_B), F = C(PC_F), G = C(PC_G), scl = C(PC_sc), c2a = C(PC_c2a);
             const double K = C(PC_K), Kb = C(PC_Kb), mu = C(PC_mu);
@@ -525,14 +596,14 @@ __device__ void chain_epilogue(const DevModel& m, const double* s_const, double*
             double g_e = Rp(PA_e);
             // mean motion: M_k = nd (t_k - tp)
             double g_tp = -nd * S0;
-            double g_a = S1 * (-1.5 * nd / a);
-            double g_M = S1 * (0.5 * nd / M);
+            double g_a = S1 * (-1.5 * nd * inv_a);
+            double g_M = S1 * (0.5 * nd * inv_M);
             // astrometry: Bh = sc*B, Gs = sc*s*G, Ah = sc*A, Fs = sc*s*F with sc = a*c2a
             const double g_sc = gBh * Bc + gGs * s * G + gAh * A + gFs * s * F;
             g_a += g_sc * c2a;
-            double g_plx = g_sc * scl / plx;
+            double g_plx = g_sc * C(PC_a) * m.c2a_per_plx;      // d(a*c2a)/d plx
             const double gB = gBh * scl, gG = gGs * scl * s, gA = gAh * scl, gF = gFs * scl * s;
-            g_e += -(e / s) * scl * (gGs * G + gFs * F);
+            g_e += -(e * inv_s) * scl * (gGs * G + gFs * F);
             double g_w = gA * F + gB * G - gF * A - gG * Bc;
             double g_W = -gA * Bc + gB * A - gF * G + gG * F;
             double g_i = si * (gA * sW * sw - gB * cW * sw + gF * sW * cw - gG * cW * cw);
@@ -540,24 +611,24 @@ __device__ void chain_epilogue(const DevModel& m, const double* s_const, double*
             const double s2 = s * s;
             const double gK = gPc * cw * s2 + gPs * sw * s;
             g_w += -gPc * K * sw * s2 + gPs * K * cw * s;
-            g_e += gPc * K * cw * (-2.0 * e) + gPs * K * sw * (-e / s) + gK * K * e / s2;
-            g_a += gK * (-0.5 * K / a);
-            g_M += gK * (0.5 * K / M);
+            g_e += gPc * K * cw * (-2.0 * e) + gPs * K * sw * (-e * inv_s) + gK * K * e * inv_s * inv_s;
+            g_a += gK * (-0.5 * K * inv_a);
+            g_M += gK * (0.5 * K * inv_M);
             g_i += gK * Kb * ci;
             // reflex factor mu = mass * mjup2msol / M
-            g_M += -gmu * mu / M;
+            g_M += -gmu * mu * inv_M;
             s_g[m.idx_a[p] * 32 + lane] += g_a;   s_g[m.idx_e[p] * 32 + lane] += g_e;
             s_g[m.idx_i[p] * 32 + lane] += g_i;   s_g[m.idx_w[p] * 32 + lane] += g_w;
             s_g[m.idx_W[p] * 32 + lane] += g_W;   s_g[m.idx_tp[p] * 32 + lane] += g_tp;
             s_g[m.idx_M[p] * 32 + lane] += g_M;   s_g[m.idx_plx[p] * 32 + lane] += g_plx;
-            if (m.idx_mass[p] >= 0) s_g[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol / M;
+            if (m.idx_mass[p] >= 0) s_g[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol * inv_M;
         }
     }
     ll_out = ll;
 }
 
 template <bool GRAD, int NPT>
-__global__ void __launch_bounds__(W * 32, 2)
+__global__ void __launch_bounds__(W * 32, OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets) {
@@ -571,22 +642,42 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     int* s_ok = reinterpret_cast<int*>(s_g + m.n_in * 32);    // [W][32]
     __shared__ int s_last;
 
+#ifdef OCTO_TIMING
+    long long tm[6]; int tmi = 0;
+#define OCTO_TICK() do { if (threadIdx.x == 0) tm[tmi++] = clock64(); } while (0)
+#else
+#define OCTO_TICK() do {} while (0)
+#endif
+    OCTO_TICK();
     const int64_t c_raw = (int64_t)blockIdx.x * 32 + lane;
     const bool active = c_raw < n_chains;
     const int64_t c = active ? c_raw : n_chains - 1;
 
     // ---- prologue: finiteness of every input (logdensitymodel.jl:120-124), planet constants
     int ok = 1;
+#pragma unroll 1
     for (int k = w; k < m.n_in; k += W) ok &= isfinite(in[c + (int64_t)k * ld]) ? 1 : 0;
-    for (int p = w; p < m.n_planets; p += W) ok &= planet_prologue(m, p, in, c, ld, s_const + p * PC_COUNT * 32, lane) ? 1 : 0;
+#pragma unroll 1
+    for (int task = w; task < 4 * m.n_planets; task += W)
+        ok &= prologue_task(m, task >> 2, task & 3, in, c, ld, s_const + (task >> 2) * PC_COUNT * 32, lane) ? 1 : 0;
     s_ok[w * 32 + lane] = ok;
     double* acc = s_acc + w * n_acc * 32;
+#pragma unroll 4
     for (int s = 0; s < n_acc; ++s) acc[s * 32 + lane] = 0.0;
+    if (GRAD) {
+#pragma unroll 1
+        for (int k = w; k < m.n_in; k += W) s_g[k * 32 + lane] = 0.0;
+    }
     __syncthreads();
+#pragma unroll 1
+    for (int p = w; p < m.n_planets; p += W) prologue_products(s_const + p * PC_COUNT * 32, lane);
+    __syncthreads();
+    OCTO_TICK();
 
     // ---- this warp's contiguous range of the concatenated epoch list
     const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
     const int k_lo = (int)(m.n_epochs * u / U), k_hi = (int)(m.n_epochs * (u + 1) / U);
+#pragma unroll 1
     for (int b = 0; b < m.n_blocks; ++b) {
         const DevBlock& B = m.blocks[b];
         const int k0 = max(k_lo, B.start), k1 = min(k_hi, B.start + B.n);
@@ -599,8 +690,10 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         else seg_rv<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, lane);
     }
     __syncthreads();
+    OCTO_TICK();
 
     // ---- CTA reduction over the 8 warps, fixed order
+#pragma unroll 1
     for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
         double v = s_acc[idx];
 #pragma unroll
@@ -608,10 +701,12 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         s_red[idx] = v;
     }
     __syncthreads();
+    OCTO_TICK();
 
     // ---- K2: combine the epoch splits of this chain group; the last CTA to arrive sums in split order
     if (gridDim.y > 1) {
         double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
+#pragma unroll 2
         for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
         __threadfence();
         __syncthreads();
@@ -624,14 +719,29 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         if (!s_last) return;
         __threadfence();
         const double* base = partial + (int64_t)blockIdx.x * gridDim.y * n_acc * 32;
+#pragma unroll 1
         for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
+            // loads batched 8 deep (latency overlapped); additions in split order => same bits every run
+            const int64_t stride = (int64_t)n_acc * 32;
+            const double* q = base + idx;
             double v = 0.0;
-            for (int y = 0; y < (int)gridDim.y; ++y) v += __ldcg(base + (int64_t)y * n_acc * 32 + idx);
+            int y = 0;
+#pragma unroll 1
+            for (; y + 8 <= (int)gridDim.y; y += 8) {
+                double t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = __ldcg(q + (y + j) * stride);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v += t[j];
+            }
+#pragma unroll 1
+            for (; y < (int)gridDim.y; ++y) v += __ldcg(q + y * stride);
             s_red[idx] = v;
         }
         __syncthreads();
     }
 
+    OCTO_TICK();
     // ---- epilogue: warp 0, one lane per chain
     if (w == 0) {
         int valid = 1;
@@ -641,9 +751,19 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         chain_epilogue<GRAD>(m, s_const, s_red, s_g, in, c, ld, lane, ll);
         if (active) {
             ll_out[c] = valid ? ll : -CUDART_INF;
-            if (GRAD) for (int k = 0; k < m.n_in; ++k) g_out[c + (int64_t)k * ldg] = valid ? s_g[k * 32 + lane] : 0.0;
+            if (GRAD) {
+#pragma unroll 4
+                for (int k = 0; k < m.n_in; ++k) g_out[c + (int64_t)k * ldg] = valid ? s_g[k * 32 + lane] : 0.0;
+            }
         }
     }
+#ifdef OCTO_TIMING
+    if (threadIdx.x == 0 && blockIdx.x < 2) {
+        tm[tmi++] = clock64();
+        printf("cta(%d,%d) sm-clk: prologue %lld  segments %lld  cta-reduce %lld  splits %lld  epilogue %lld  total %lld\n",
+               blockIdx.x, blockIdx.y, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[5] - tm[0]);
+    }
+#endif
 }
 
 __global__ void k_selftest_kepler(const double* __restrict__ MA, const double* __restrict__ e, int64_t n,

@@ -76,6 +76,15 @@ namespace {
 NcclApi g_nccl;
 std::mutex g_nccl_mu;
 
+// host buffers handed out by octo_alloc_pinned: copies to/from them need no staging
+std::mutex g_pin_mu;
+std::vector<std::pair<const char*, size_t>> g_pinned;
+bool is_pinned(const void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto& r : g_pinned) if ((const char*)p >= r.first && (const char*)p + bytes <= r.first + r.second) return true;
+    return false;
+}
+
 int load_nccl() {
     std::lock_guard<std::mutex> lk(g_nccl_mu);
     if (g_nccl.h) return OCTO_OK;
@@ -204,27 +213,41 @@ int run_host(OctoCtx* ctx, bool grad, const double* in, int64_t n, int64_t ld, d
     Workspace* w = lease(ctx);
     if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
     const int n_in = ctx->m.n_in;
+    const size_t col = (size_t)n * sizeof(double), pitch = (size_t)ld * sizeof(double);
+    // buffers from octo_alloc_pinned are copied directly; anything else is staged through pinned memory
+    const bool pin_in = is_pinned(in, pitch * (n_in - 1) + col);
+    const bool pin_out = is_pinned(ll, col) && (!grad || is_pinned(g, pitch * (n_in - 1) + col));
     int rc = OCTO_OK;
     do {
         if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * n_in))) break;
-        if ((rc = ensure(&w->d_ll, &w->cap_ll, (size_t)n))) break;
-        if (grad && (rc = ensure(&w->d_g, &w->cap_g, (size_t)n * n_in))) break;
-        if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * n_in, true))) break;
-        if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (grad ? n_in + 1 : 1), true))) break;
-        // pack to a dense [n x n_in] column-major block in pinned memory, one async copy each way
-        for (int k = 0; k < n_in; ++k) memcpy(w->h_in + (size_t)k * n, in + (size_t)k * ld, (size_t)n * sizeof(double));
-        cudaError_t e = cudaMemcpyAsync(w->d_in, w->h_in, (size_t)n * n_in * sizeof(double), cudaMemcpyHostToDevice, w->stream);
+        if ((rc = ensure(&w->d_ll, &w->cap_ll, (size_t)n * (n_in + 1)))) break;      // [ll | g] contiguous
+        double* d_ll = w->d_ll;
+        double* d_g = w->d_ll + n;
+        cudaError_t e;
+        if (pin_in) {
+            e = cudaMemcpy2DAsync(w->d_in, col, in, pitch, col, n_in, cudaMemcpyHostToDevice, w->stream);
+        } else {
+            if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * n_in, true))) break;
+            for (int k = 0; k < n_in; ++k) memcpy(w->h_in + (size_t)k * n, in + (size_t)k * ld, col);
+            e = cudaMemcpyAsync(w->d_in, w->h_in, col * n_in, cudaMemcpyHostToDevice, w->stream);
+        }
         if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if ((rc = enqueue(ctx, w, grad, w->d_in, n, n, w->d_ll, grad ? w->d_g : nullptr, n, w->stream))) break;
-        e = cudaMemcpyAsync(w->h_out, w->d_ll, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
-        if (e == cudaSuccess && grad)
-            e = cudaMemcpyAsync(w->h_out + n, w->d_g, (size_t)n * n_in * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+        if ((rc = enqueue(ctx, w, grad, w->d_in, n, n, d_ll, grad ? d_g : nullptr, n, w->stream))) break;
+        if (pin_out) {
+            e = cudaMemcpyAsync(ll, d_ll, col, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && grad)
+                e = cudaMemcpy2DAsync(g, pitch, d_g, col, col, n_in, cudaMemcpyDeviceToHost, w->stream);
+        } else {
+            if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (n_in + 1), true))) break;
+            e = cudaMemcpyAsync(w->h_out, d_ll, col * (grad ? n_in + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
+        }
         if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
         e = cudaStreamSynchronize(w->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
-        memcpy(ll, w->h_out, (size_t)n * sizeof(double));
-        if (grad) for (int k = 0; k < n_in; ++k)
-            memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, (size_t)n * sizeof(double));
+        if (!pin_out) {
+            memcpy(ll, w->h_out, col);
+            if (grad) for (int k = 0; k < n_in; ++k) memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
+        }
     } while (0);
     release(ctx, w);
     return rc;
@@ -270,6 +293,8 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     memset(&m, 0, sizeof(m));
     m.c = *consts;
     m.kappa = 6.283185307179586 * consts->year2day / consts->kepler_year_days * consts->au2m * consts->sec2year;
+    m.two_pi_over_kyd = 6.283185307179586 / consts->kepler_year_days;
+    m.c2a_per_plx = consts->rad2as * 1e3 / (1000.0 * consts->pc2au);
     m.n_planets = L->n_planets; m.n_in = L->n_in; m.n_blocks = n_blocks;
     for (int p = 0; p < OCTO_MAX_PLANETS; ++p) {
         m.idx_plx[p] = L->idx_plx[p]; m.idx_a[p] = L->idx_a[p]; m.idx_e[p] = L->idx_e[p]; m.idx_i[p] = L->idx_i[p];
@@ -397,6 +422,26 @@ int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t l
     return enqueue(ctx, w, d_g != nullptr, d_in, n, ld, d_ll, d_g, ld, (cudaStream_t)stream);
 }
 
+// page-locked host memory for `in` / `ll` / `g_in`: octo_logp[_grad] then copies without staging
+void* octo_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaMallocHost"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pinned.emplace_back((const char*)p, bytes);
+    return p;
+}
+void octo_free_pinned(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (size_t i = 0; i < g_pinned.size(); ++i)
+            if (g_pinned[i].first == (const char*)p) { g_pinned.erase(g_pinned.begin() + i); break; }
+    }
+    cudaFreeHost(p);
+}
+
 // diagnostic: the device Kepler solve on its own (mean anomaly MA, eccentricity e) -> sin E, cos E
 int octo_selftest_kepler(int32_t device, const double* MA, const double* e, int64_t n, double* sinE, double* cosE) {
     if (!MA || !e || !sinE || !cosE || n < 0) return fail(OCTO_ERR_ARG, "null argument");
@@ -443,8 +488,8 @@ int octo_pt_init(OctoCtx* ctx, const void* id, int32_t rank, int32_t world, int3
     octo_pt_finalize(ctx);
     ctx->pt_rank = rank; ctx->pt_world = world; ctx->pt_local = n_local; ctx->pt_seed = seed;
     CU(cudaStreamCreateWithFlags(&ctx->pt_stream, cudaStreamNonBlocking));
-    CU(cudaMalloc((void**)&ctx->d_gather, (size_t)world * n_local * 2 * sizeof(double)));
-    CU(cudaMallocHost((void**)&ctx->h_gather, (size_t)world * n_local * 2 * sizeof(double)));
+    CU(cudaMalloc((void**)&ctx->d_gather, (size_t)(world + 1) * n_local * 2 * sizeof(double)));
+    CU(cudaMallocHost((void**)&ctx->h_gather, (size_t)(world + 1) * n_local * 2 * sizeof(double)));
     if (world > 1) {
         if (!id) return fail(OCTO_ERR_ARG, "nccl unique id required for world > 1");
         if (int rc = load_nccl()) return rc;
@@ -464,38 +509,27 @@ static double pt_uniform(uint64_t seed, uint64_t round, uint64_t pair) {
     return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-int octo_pt_swap_round(OctoCtx* ctx, const double* d_ll_pair, const double* beta, int32_t* chain_of_replica,
-                       int64_t round, int32_t* accepted) {
-    if (!ctx || !ctx->pt_stream) return fail(OCTO_ERR_STATE, "octo_pt_init has not been called");
-    if (!d_ll_pair || !beta || !chain_of_replica) return fail(OCTO_ERR_ARG, "null argument");
-    CU(cudaSetDevice(ctx->device));
-    const int nl = ctx->pt_local, R = nl * ctx->pt_world;
-    if (ctx->pt_world > 1) {
-        int r = g_nccl.AllGather(d_ll_pair, ctx->d_gather, (size_t)nl * 2, /*ncclFloat64*/ 8, ctx->nccl_comm, ctx->pt_stream);
-        if (r) return fail_nccl(r, "ncclAllGather");
-        CU(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, (size_t)R * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->pt_stream));
-    } else {
-        CU(cudaMemcpyAsync(ctx->h_gather, d_ll_pair, (size_t)R * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->pt_stream));
-    }
-    CU(cudaStreamSynchronize(ctx->pt_stream));
-    // replica_of_chain: inverse permutation
-    std::vector<int> rep_of(R, -1);
+// Pure host part of a swap round (no CUDA, no NCCL): given every replica's (l_ref, l_target), decide the
+// deterministic even-odd swaps.  Identical inputs give identical decisions on every rank.
+int octo_pt_decide(const double* ll_pair_all, const double* beta, int32_t* chain_of_replica, int32_t R,
+                   int64_t round, uint64_t seed, int32_t* accepted) {
+    if (!ll_pair_all || !beta || !chain_of_replica || R < 1) return fail(OCTO_ERR_ARG, "null argument");
+    std::vector<int> rep_of(R, -1);                 // inverse permutation: which replica sits on ladder rung i
     for (int r = 0; r < R; ++r) {
         const int ch = chain_of_replica[r];
         if (ch < 0 || ch >= R || rep_of[ch] != -1) return fail(OCTO_ERR_ARG, "chain_of_replica is not a permutation");
         rep_of[ch] = r;
     }
     if (accepted) for (int i = 0; i < R - 1; ++i) accepted[i] = 0;
-    // even rounds pair ladder rungs (0,1),(2,3)...; odd rounds (1,2),(3,4)... (deterministic even-odd scheme)
+    // even rounds pair rungs (0,1),(2,3)...; odd rounds (1,2),(3,4)...
     for (int i = (int)(round & 1); i + 1 < R; i += 2) {
         const int ra = rep_of[i], rb = rep_of[i + 1];
-        const double* A = ctx->h_gather + 2 * (size_t)ra;   // (l_ref, l_target) of the replica on rung i
-        const double* B = ctx->h_gather + 2 * (size_t)rb;
-        // tempered log-density at beta: (1-b) l_ref + b l_target
+        const double* A = ll_pair_all + 2 * (size_t)ra;   // (l_ref, l_target) of the replica on rung i
+        const double* B = ll_pair_all + 2 * (size_t)rb;
         const double bi = beta[i], bj = beta[i + 1];
-        auto V = [](const double* x, double b) { return (1.0 - b) * x[0] + b * x[1]; };
+        auto V = [](const double* x, double b) { return (1.0 - b) * x[0] + b * x[1]; };   // tempered log-density
         const double log_ratio = (V(A, bj) + V(B, bi)) - (V(A, bi) + V(B, bj));
-        const double u = pt_uniform(ctx->pt_seed, (uint64_t)round, (uint64_t)i);
+        const double u = pt_uniform(seed, (uint64_t)round, (uint64_t)i);
         const bool acc = std::isfinite(log_ratio) ? (std::log(u) < log_ratio) : (log_ratio > 0);
         if (acc) {
             chain_of_replica[ra] = i + 1; chain_of_replica[rb] = i;
@@ -504,6 +538,26 @@ int octo_pt_swap_round(OctoCtx* ctx, const double* d_ll_pair, const double* beta
         }
     }
     return OCTO_OK;
+}
+
+int octo_pt_swap_round(OctoCtx* ctx, const double* ll_pair, const double* beta, int32_t* chain_of_replica,
+                       int64_t round, int32_t* accepted) {
+    if (!ctx || !ctx->pt_stream) return fail(OCTO_ERR_STATE, "octo_pt_init has not been called");
+    if (!ll_pair || !beta || !chain_of_replica) return fail(OCTO_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const int nl = ctx->pt_local, R = nl * ctx->pt_world;
+    if (ctx->pt_world > 1) {
+        // local pairs -> device slot of this rank; one all-gather over NVLink; back to pinned host memory
+        double* mine = ctx->d_gather + (size_t)R * 2;       // send buffer lives after the receive buffer
+        memcpy(ctx->h_gather + (size_t)R * 2, ll_pair, (size_t)nl * 2 * sizeof(double));
+        CU(cudaMemcpyAsync(mine, ctx->h_gather + (size_t)R * 2, (size_t)nl * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->pt_stream));
+        int r = g_nccl.AllGather(mine, ctx->d_gather, (size_t)nl * 2, /*ncclFloat64*/ 8, ctx->nccl_comm, ctx->pt_stream);
+        if (r) return fail_nccl(r, "ncclAllGather");
+        CU(cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, (size_t)R * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->pt_stream));
+        CU(cudaStreamSynchronize(ctx->pt_stream));
+        return octo_pt_decide(ctx->h_gather, beta, chain_of_replica, R, round, ctx->pt_seed, accepted);
+    }
+    return octo_pt_decide(ll_pair, beta, chain_of_replica, R, round, ctx->pt_seed, accepted);
 }
 
 void octo_pt_finalize(OctoCtx* ctx) {

@@ -285,6 +285,7 @@ class LogDensityModel:
         if rc != 0:
             raise OctoError(f"octo_create failed ({rc}): {self._lib.octo_last_error().decode()}")
         self._h = h
+        self._pinned = []
         self.device = int(device)
 
     # -- lifetime ---------------------------------------------------------------------
@@ -292,6 +293,9 @@ class LogDensityModel:
         if getattr(self, "_h", None):
             self._lib.octo_destroy(self._h)
             self._h = None
+            for p in self._pinned:
+                self._lib.octo_free_pinned(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -326,20 +330,36 @@ class LogDensityModel:
         if rc != 0:
             raise OctoError(f"libocto_b200 error {rc}: {self._lib.octo_last_error().decode()}")
 
-    def ln_like(self, theta):
+    def pinned_empty(self, shape):
+        """Column-major float64 array in page-locked host memory (octo_alloc_pinned): inputs/outputs placed
+        here are copied to/from the device without a staging copy.  Freed with the model."""
+        shape = (shape,) if np.isscalar(shape) else tuple(shape)
+        nbytes = int(np.prod(shape)) * 8
+        p = self._lib.octo_alloc_pinned(nbytes)
+        if not p:
+            raise OctoError(f"octo_alloc_pinned failed: {self._lib.octo_last_error().decode()}")
+        self._pinned.append(p)
+        buf = (C.c_double * (nbytes // 8)).from_address(p)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape, order="F")
+
+    def ln_like(self, theta, out=None):
         """Epoch-summed log-likelihood per chain (value-only kernel K1v)."""
         x, single = self._as_in(theta)
         n = x.shape[0]
-        ll = np.empty(n)
+        ll = np.empty(n) if out is None else out
         self._check(self._lib.octo_logp(self._h, x.ctypes.data, n, n, ll.ctypes.data))
         return ll[0] if single else ll
 
-    def ln_like_and_gradient(self, theta):
-        """(ll, ∂ll/∂inputs) per chain (fused kernel K1)."""
+    def ln_like_and_gradient(self, theta, out=None):
+        """(ll, ∂ll/∂inputs) per chain (fused kernel K1).  out=(ll[n], g[n, n_in] column-major) reuses buffers."""
         x, single = self._as_in(theta)
         n = x.shape[0]
-        ll = np.empty(n)
-        g = np.empty((n, self.n_in), order="F")
+        if out is None:
+            ll, g = np.empty(n), np.empty((n, self.n_in), order="F")
+        else:
+            ll, g = out
+            if ll.shape != (n,) or g.shape != (n, self.n_in) or not g.flags.f_contiguous:
+                raise ValueError("out must be (ll[n], g[n, n_in]) with g column-major")
         self._check(self._lib.octo_logp_grad(self._h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data))
         return (ll[0], g[0]) if single else (ll, g)
 
