@@ -313,11 +313,15 @@ class LogDensityModel:
         return int(self._lib.octo_kernel_launches(self._h))
 
     def launch_geometry(self, n_chains):
-        out = (C.c_int32 * 4)()
+        """(grid.x, grid.y, block, epochs-or-strides per warp, cluster, G) — see octo_launch_geometry."""
+        out = (C.c_int32 * 6)()
         self._lib.octo_launch_geometry(self._h, int(n_chains), C.byref(out))
         return tuple(out)
 
     def _as_in(self, theta):
+        if (type(theta) is np.ndarray and theta.ndim == 2 and theta.dtype == np.float64
+                and theta.flags.f_contiguous and theta.shape[1] == self.n_in):
+            return theta, False                                  # fast path: already column-major float64
         th = np.asarray(theta, dtype=np.float64)
         single = th.ndim == 1
         if single:

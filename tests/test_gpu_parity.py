@@ -143,13 +143,36 @@ def test_epoch_split_geometry_consistent(oracle_lib):
     """Many epochs, few chains: the grid splits epochs across CTAs (K2 path) and still matches."""
     spec, x = workloads.one_planet(3000, 0, 40, seed=9)
     model = octo.LogDensityModel(spec)
-    gx, gy, block, slice_ = model.launch_geometry(40)
-    assert gy > 1
+    gx, gy, block, slice_, cluster, G = model.launch_geometry(40)
+    assert gy > 1 and G == 0
     ll, g = model.ln_like_and_gradient(x)
     orc = oracle_lib.Oracle(spec.packed, octo.default_constants())
     ll_o, g_o = orc.logp_grad(x, threads=8)
     assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
     model.close()
+
+
+@pytest.mark.parametrize("env", [{"OCTO_B200_EPOCH_LANES": "0"}, {"OCTO_B200_EPOCH_LANES": "1"},
+                                 {"OCTO_B200_EPOCH_LANES": "4"}, {"OCTO_B200_EPOCH_LANES": "8"},
+                                 {"OCTO_B200_EPOCH_LANES": "0", "OCTO_B200_CLUSTERS": "1"}])
+def test_every_lane_mapping_matches_oracle(oracle_lib, env, monkeypatch):
+    """Force each launch strategy (chain-lane with L2 ticket combine, with DSMEM cluster combine, epoch-lane with
+    1/4/8 warps per chain) on the 2-planet C3 model and on C2; all must agree with the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for cfg in ("C2", "C3"):
+        spec, x = workloads.config(cfg)
+        x = x[:70]
+        model = octo.LogDensityModel(spec)
+        geo = model.launch_geometry(x.shape[0])
+        assert geo[5] == int(env["OCTO_B200_EPOCH_LANES"])
+        ll, g = model.ln_like_and_gradient(x)
+        llv = model.ln_like(x)
+        model.close()
+        orc = oracle_lib.Oracle(spec.packed, octo.default_constants())
+        ll_o, g_o = orc.logp_grad(x, threads=8)
+        assert rel_err(ll, ll_o).max() < LOGP_RTOL and rel_err(llv, ll_o).max() < LOGP_RTOL
+        assert grad_err(g, g_o).max() < GRAD_RTOL
 
 
 def test_concurrent_calls_threads(oracle_lib):
