@@ -55,13 +55,9 @@ struct DevModel {
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],
             idx_mass[OCTO_MAX_PLANETS];
     DevBlock blocks[OCTO_MAX_BLOCKS];
-    // device tables, length n_epochs each (RV tables use t, y1, c1 only)
-    const double* t;
-    const double* y1;
-    const double* y2;
-    const double* c1;     // astrometry: w11 (no jitter) | σ1² (jitter);  RV: 1/σ² | σ²
-    const double* c2;     // astrometry: w12 | σ2²
-    const double* c3;     // astrometry: w22 | cor
+    // device table, one 48-byte record per epoch of the concatenated list: [t, y1, c1, y2, c2, c3]
+    //   astrometry: c1,c2,c3 = w11,w12,w22 (no jitter) | σ1², σ2², cor (jitter);   RV: c1 = 1/σ² | σ² (y2,c2,c3 unused)
+    const double* tab;
 };
 
 // slot 0 = ll; planets follow

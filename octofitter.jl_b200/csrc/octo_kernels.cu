@@ -51,7 +51,7 @@ struct Orb { double nd, tp, e; float ef, omef, ca1f; };
 struct KConst {
     double magic, inv_two_pi, two_pi1, two_pi2, two_pi3, two_over_pi, pio2_hi, pio2_lo;
     double s[6], c[6];
-    double one, half, mhalf, sixth, msixth, r24, mr24, two, mtwo;
+    double one, half, mhalf, sixth, msixth, r24, mr24, two, mtwo, five, two_pi, log2pi;
 };
 __constant__ KConst kc = {
     6755399441055744.0,            // 1.5 * 2^52: (x + magic) - magic == rint(x) for |x| < 2^51
@@ -63,21 +63,13 @@ __constant__ KConst kc = {
      -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01},
     {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
      2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02},
-    1.0, 0.5, -0.5, 1.0 / 6.0, -1.0 / 6.0, 1.0 / 24.0, -1.0 / 24.0, 2.0, -2.0};
+    1.0, 0.5, -0.5, 1.0 / 6.0, -1.0 / 6.0, 1.0 / 24.0, -1.0 / 24.0, 2.0, -2.0, 5.0,
+    6.283185307179586477, 1.8378770664093454836};
 
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// 1/x with one Newton step (~2^-40): enough for Markley's d3/d4, whose relative error reaches the final
-// d5 multiplied by (f2 d / 2 f1)^2 ~ 1e-7.
-__device__ __forceinline__ double rcp_nr1(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, kc.one);
-    return fma(y, e, y);
-}
 
 // 1/x: MUFU.RCP64H seed (~2^-20) + two Newton steps -> ~1 ulp.  x finite, normal, non-zero.
 __device__ __forceinline__ double rcp_nr(double x) {
@@ -116,12 +108,20 @@ __device__ __forceinline__ void sincos_pi(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -c0 : c0;
 }
 
+__device__ __forceinline__ void sincos_any(double x, double& s, double& c) {   // any finite angle of sane size
+    const double k = fma(x, kc.inv_two_pi, kc.magic) - kc.magic;
+    double r = fma(-k, kc.two_pi1, x);
+    r = fma(-k, kc.two_pi2, r);
+    r = fma(-k, kc.two_pi3, r);
+    sincos_pi(r, s, c);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kepler solve: rem2pi (round to nearest) + Markley's starter + one fifth-order correction; returns sinE, cosE.
 //  * The starter E1 (Markley eqs 5-15, |E1 - E| < 4.4e-4 rad everywhere) only seeds the correction, whose
 //    result is accurate to O(|E1-E|^6); it is therefore evaluated in FP32 with MUFU rsqrt/lg2/ex2/rcp —
 //    validated over e in [0, 1-1e-12], |M| down to 1e-30: identical max |d5| and residual <= 7e-16.
-//  * f0 = E1 - e sinE1 - M and the correction (eqs 21-28) are FP64; divisions are rcp_nr multiplies.
+//  * f0 = E1 - e sinE1 - M and the fifth-order correction (eqs 21-28) are FP64, with ONE reciprocal (rcp_nr).
 //  * sin/cos of E = E1 + d5 come from rotating sincos(E1) by d5 (three Taylor terms, exact to 1e-19):
 //    one sincos per solve instead of two.
 // ---------------------------------------------------------------------------------------------
@@ -152,11 +152,17 @@ __device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt
     const double f2 = o.e * s1, f3 = o.e * c1;                     // eqs 26, 27
     const double f0 = (E1 - M) - f2;                               // eq 21
     const double f1 = kc.one - f3;                                 // eq 25
-    const double hf2 = kc.half * f2, f36 = f3 * kc.sixth;
-    const double d3 = kc.mtwo * f0 * f1 * rcp_nr1(fma(kc.two * f1, f1, -f0 * f2));      // eq 22
-    const double d4 = -f0 * rcp_nr1(fma(d3 * d3, f36, fma(hf2, d3, f1)));                // eq 23
-    const double d42 = d4 * d4;
-    const double d5 = -f0 * rcp_nr(fma(d42 * d4, f2 * kc.mr24, fma(d42, f36, fma(hf2, d4, f1))));  // eqs 24, 28
+    // eqs 22-24, 28: Markley's d5 is the root of f0 + f1 d + f2 d^2/2 + f3 d^3/6 - f2 d^4/24 = 0 reached by three
+    // nested divisions.  The same root by series reversion in the Newton step u = -f0/f1 (|u| < 4.4e-4, and
+    // |a2 u| < 2.5e-4 over the whole domain): d = u (1 - u (a2 - u (c3 - u c4))), one reciprocal, a third
+    // of the dependent chain.  Agrees with the nested form to 1.1e-17 rad (validated e <= 1 - 1e-9, |M| >= 1e-30).
+    const double h = rcp_nr(f1);
+    const double u = -f0 * h;
+    const double g2 = f2 * h, g3 = f3 * h;
+    const double a2 = kc.half * g2, a3 = kc.sixth * g3, a4 = kc.mr24 * g2;
+    const double c3 = fma(a2, g2, -a3);                            // 2 a2^2 - a3
+    const double c4 = fma(kc.five * a2, fma(a2, a2, -a3), a4);     // 5 a2^3 - 5 a2 a3 + a4
+    const double d5 = u * fma(-u, fma(-u, fma(-u, c4, c3), a2), kc.one);
     const double x2 = d5 * d5;
     const double sd = d5 * fma(x2, kc.msixth, kc.one);
     const double cd = fma(x2, fma(x2, kc.r24, kc.mhalf), kc.one);
@@ -227,7 +233,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
     const double na = (!LEAN && B.idx_northangle >= 0) ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
     const bool rot = !LEAN && ((B.idx_platescale >= 0) || (B.idx_northangle >= 0));
     double sna = 0.0, cna = 1.0;
-    if (rot && !pasep) sincos(na, &sna, &cna);
+    if (rot && !pasep) sincos_any(na, sna, cna);
     const double j2 = jit * jit;
 
     double ll = 0.0, g_jit = 0.0, g_ps = 0.0, g_na = 0.0;
@@ -237,10 +243,17 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 #pragma unroll
         for (int a = 0; a < 7; ++a) L[u][a] = 0.0;
 
+    // epoch record [t, y1 | c1, y2 | c2, c3] as three 16-byte read-only loads, fetched one iteration ahead
+    const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
+    double2 ra0, ra1, ra2;
+    if (k0 < k1) { ra0 = __ldg(tab + 3 * (int64_t)k0); ra1 = __ldg(tab + 3 * (int64_t)k0 + 1); ra2 = __ldg(tab + 3 * (int64_t)k0 + 2); }
     OCTO_UNROLL_LOOP(OCTO_UNROLL)
     for (int k = k0; k < k1; k += kstep) {
-        const double t = m.t[k], y1 = m.y1[k], y2 = m.y2[k];
-        const double e1 = m.c1[k], e2 = m.c2[k], e3 = m.c3[k];
+        const double t = ra0.x, y1 = ra0.y, e1 = ra1.x, y2 = ra1.y, e2 = ra2.x, e3 = ra2.y;
+        {
+            const int64_t kn = min(k + kstep, k1 - 1);
+            ra0 = __ldg(tab + 3 * kn); ra1 = __ldg(tab + 3 * kn + 1); ra2 = __ldg(tab + 3 * kn + 2);
+        }
         double sE[NPT], cE[NPT], dt[NPT];
         double ra = 0.0, dec = 0.0;
 #pragma unroll
@@ -284,7 +297,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
             ll -= kLog2Pi + 0.5 * (log(v1 * v2) + lom);
         }
         const double q1 = fma(w11, r1, w12 * r2), q2 = fma(w12, r1, w22 * r2);
-        ll -= 0.5 * fma(r1, q1, r2 * q2);
+        ll = fma(kc.mhalf, fma(r1, q1, r2 * q2), ll);
         if (GRAD) {
             double gr, gd;
             if (pasep) {
@@ -304,7 +317,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 #pragma unroll
             for (int u = 0; u < NPT; ++u) if (u < ni) {
                 const double X = cE[u] - orb[u].e;
-                const double rD = rcp_nr(fma(-orb[u].e, cE[u], 1.0));
+                const double rD = rcp_nr(fma(-orb[u].e, cE[u], kc.one));
                 L[u][0] = fma(gr, X, L[u][0]);
                 L[u][1] = fma(gr, sE[u], L[u][1]);
                 L[u][2] = fma(gd, X, L[u][2]);
@@ -349,7 +362,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 // Radial-velocity segment (kinds 2, 3, 4).
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT, bool MARGIN>
+template <bool GRAD, int NPT, bool MARGIN, bool JIT>
 __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                     double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane,
                                     int kstep, bool red) {
@@ -387,7 +400,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         orb[u] = load_orb(sc, lane);
         Pc[u] = sc[PC_Pc * 32 + lane]; Ps[u] = sc[PC_Ps * 32 + lane];
     }
-    const double jit = B.idx_jitter >= 0 ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
+    const double jit = JIT ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
     const double off = (B.idx_offset >= 0 && !margin) ? in[c + (int64_t)B.idx_offset * ld] : 0.0;
     const double j2 = jit * jit;
 
@@ -399,37 +412,44 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 #pragma unroll
         for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; if constexpr (MARGIN) V[u][a] = 0.0; }
 
+    const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
+    double2 ra0, ra1;
+    if (k0 < k1) { ra0 = __ldg(tab + 3 * (int64_t)k0); ra1 = __ldg(tab + 3 * (int64_t)k0 + 1); }
     OCTO_UNROLL_LOOP(OCTO_UNROLL)
     for (int k = k0; k < k1; k += kstep) {
-        const double t = m.t[k], y = m.y1[k], e1 = m.c1[k];
+        const double t = ra0.x, y = ra0.y, e1 = ra1.x;
+        {
+            const int64_t kn = min(k + kstep, k1 - 1);
+            ra0 = __ldg(tab + 3 * kn); ra1 = __ldg(tab + 3 * kn + 1);
+        }
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
         double model = off;
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
-            rD[u] = rcp_nr(fma(-orb[u].e, cE[u], 1.0));
+            rD[u] = rcp_nr(fma(-orb[u].e, cE[u], kc.one));
             rv[u] = fma(Pc[u], cE[u], -Ps[u] * sE[u]) * rD[u];
             model = fma(f[u], rv[u], model);
         }
         const double r = y - model;
         double iv;
-        if (!B.jit) iv = e1;                     // 1/σ² precomputed; normalisation is in const_ll
+        if constexpr (!JIT) iv = e1;             // 1/σ² precomputed; normalisation is in const_ll
         else {
             const double var = e1 + j2;
             iv = rcp_nr(var);
-            if constexpr (MARGIN) mLG += log(kTwoPi * var);
-            else ll -= 0.5 * (kLog2Pi + log(var));
+            if constexpr (MARGIN) mLG += log(kc.two_pi * var);
+            else ll = fma(kc.mhalf, kc.log2pi + log(var), ll);
         }
         const double riv = r * iv;
         double g;                                 // d ll / d model
         if constexpr (MARGIN) {
             mA += iv; mS1 += riv; mC = fma(r, riv, mC);
             mR2 = fma(riv, riv, mR2); mR1 = fma(riv, iv, mR1); mQ = fma(iv, iv, mQ);
-            g = 2.0 * riv;
+            g = kc.two * riv;
         } else {
-            ll -= 0.5 * r * riv;
+            ll = fma(kc.mhalf * r, riv, ll);
             g = riv;
-            if (GRAD) { g_off += g; if (B.jit) g_jit += fma(r, riv, -1.0) * iv; }
+            if (GRAD) { g_off += g; if constexpr (JIT) g_jit = fma(fma(r, riv, -kc.one), iv, g_jit); }
         }
         if (GRAD) {
 #pragma unroll
@@ -498,14 +518,6 @@ __device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 
 #pragma unroll
     for (int it = 0; it < 3; ++it) y = fma(y, fma(-hx * y, y, kc.half), y);
     return y;
-}
-
-__device__ __forceinline__ void sincos_any(double x, double& s, double& c) {   // any finite angle of sane size
-    const double k = fma(x, kc.inv_two_pi, kc.magic) - kc.magic;
-    double r = fma(-k, kc.two_pi1, x);
-    r = fma(-k, kc.two_pi2, r);
-    r = fma(-k, kc.two_pi3, r);
-    sincos_pi(r, s, c);
 }
 
 // returns validity of what the task looked at
@@ -656,9 +668,11 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
         if (lean) seg_astrom<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
         else seg_astrom<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
     } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-        seg_rv<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        seg_rv<GRAD, NPT, true, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+    } else if (B.jit) {
+        seg_rv<GRAD, NPT, false, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
     } else {
-        seg_rv<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        seg_rv<GRAD, NPT, false, false>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
     }
 }
 

@@ -376,7 +376,8 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
     std::vector<double> T((size_t)6 * (E > 0 ? E : 1), 0.0);
-    double *t = T.data(), *y1 = t + E, *y2 = y1 + E, *c1 = y2 + E, *c2 = c1 + E, *c3 = c2 + E;
+    struct Col { double* b; double& operator[](size_t o) const { return b[6 * o]; } };   // AoS record field view
+    const Col t{T.data()}, y1{T.data() + 1}, c1{T.data() + 2}, y2{T.data() + 3}, c2{T.data() + 4}, c3{T.data() + 5};
     long double cll = 0.0L;
     const long double log2pi = 1.8378770664093454835606594728112353L;
     for (int b = 0; b < n_blocks; ++b) {
@@ -427,7 +428,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaMalloc tables"); }
     ce = cudaMemcpy(ctx->d_tables, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
-    m.t = ctx->d_tables; m.y1 = m.t + E; m.y2 = m.y1 + E; m.c1 = m.y2 + E; m.c2 = m.c1 + E; m.c3 = m.c2 + E;
+    m.tab = ctx->d_tables;
     int occ = 0;
     ce = octo_kernels_init(m, ctx->smem, &occ);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
