@@ -375,7 +375,8 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     m.n_epochs = E; m.n_acc = n_acc;
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
-    std::vector<double> T((size_t)6 * (E > 0 ? E : 1), 0.0);
+    // + padding: the kernels prefetch one lane-stride (<= 32*8 records) past the record they read
+    std::vector<double> T((size_t)6 * ((E > 0 ? E : 1) + 32 * OCTO_WARPS + 1), 0.0);
     struct Col { double* b; double& operator[](size_t o) const { return b[6 * o]; } };   // AoS record field view
     const Col t{T.data()}, y1{T.data() + 1}, c1{T.data() + 2}, y2{T.data() + 3}, c2{T.data() + 4}, c3{T.data() + 5};
     long double cll = 0.0L;
