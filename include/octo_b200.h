@@ -179,10 +179,8 @@ int32_t octo_n_planets(const OctoCtx* ctx);
 int64_t octo_total_epochs(const OctoCtx* ctx);   /* E: length of the concatenated epoch list      */
 int32_t octo_device(const OctoCtx* ctx);
 int64_t octo_kernel_launches(const OctoCtx* ctx); /* kernels launched so far through this context */
-/* launch geometry chosen for a batch of n_chains: {grid.x, grid.y, block, epochs (or lane-strides) per warp,
- * cluster (1: epoch splits combined over DSMEM), G (0: chain-lane mapping; >0: epoch-lane mapping with G warps
- * per chain)} */
-int  octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[6]);
+/* launch geometry chosen for a batch of n_chains: {grid.x = chain groups, grid.y = epoch splits, block, epochs per warp} */
+int  octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]);
 
 /*
  * Parallel-tempering swap round (replaces the replica exchange Pigeons does over

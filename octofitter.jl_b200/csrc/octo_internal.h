@@ -63,7 +63,7 @@ struct DevModel {
 // slot 0 = ll; planets follow
 __host__ __device__ inline int slot_planet(int p, int a) { return 1 + p * PA_COUNT + a; }
 
-struct LaunchGeom { int gx, gy, block, slice, cluster, G; size_t smem; };   // G > 0: epoch-lane mapping, G warps per chain
+struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
 
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,

@@ -19,9 +19,7 @@
 //   epilogue  -> one lane per chain maps the raw sums to ∂ll/∂(inputs) by the chain rule, writes coalesced rows
 #include "octo_internal.h"
 #include <math_constants.h>
-#include <cooperative_groups.h>
 #include <cstdio>
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -177,29 +175,14 @@ __device__ __forceinline__ Orb load_orb(const double* sc, int lane) {
     return o;
 }
 
-__device__ __forceinline__ double warp_sum(double v) {      // xor butterfly: same total, same bits, in every lane
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// add a segment's local sum into this warp's slot array.  red: lanes hold different epochs of ONE chain
-// (epoch-lane mapping) -> reduce over the warp first, lane 0 stores.
-__device__ __forceinline__ void acc_add(double* acc, int slot, int col, double v, bool red) {
-    if (red) {
-        v = warp_sum(v);
-        if ((threadIdx.x & 31) == 0) acc[slot * 32 + col] += v;
-    } else {
-        acc[slot * 32 + col] += v;
-    }
-}
+__device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double v) { acc[slot * 32 + lane] += v; }
 
 // ---------------------------------------------------------------------------------------------
 // Astrometry segment (kinds 0, 1): epochs [k0, k1) of table B for this warp's 32 chains.
 // ---------------------------------------------------------------------------------------------
 template <bool GRAD, int NPT, bool LEAN>
 __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
-                                        double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane,
-                                        int kstep, bool red) {
+                                        double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
     const int ip = B.planet;
     // LEAN: RA/Dec table with fixed weights (no jitter / platescale / northangle) — the common case
     const bool pasep = !LEAN && (B.kind == OCTO_KIND_ASTROM_PASEP);
@@ -243,17 +226,23 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 #pragma unroll
         for (int a = 0; a < 7; ++a) L[u][a] = 0.0;
 
-    // epoch record [t, y1 | c1, y2 | c2, c3] as three 16-byte read-only loads, fetched one iteration ahead
+    // Epoch records [t, y1 | c1, y2 | c2, c3] are staged through shared memory 32 at a time: one coalesced
+    // read-only load per lane (three 16-byte words), then every iteration reads its record as a broadcast LDS —
+    // no global-load latency inside the dependent chain.
     const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
-    double2 ra0, ra1, ra2;
-    if (k0 < k1) { ra0 = __ldg(tab + 3 * (int64_t)k0); ra1 = __ldg(tab + 3 * (int64_t)k0 + 1); ra2 = __ldg(tab + 3 * (int64_t)k0 + 2); }
+    for (int kb = k0; kb < k1; kb += 32) {
+    const int nrec = min(32, k1 - kb);
+    __syncwarp();
+    if (lane < nrec) {
+        const double2* src = tab + 3 * (int64_t)(kb + lane);
+        const double2 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+        stage[3 * lane] = a0; stage[3 * lane + 1] = a1; stage[3 * lane + 2] = a2;
+    }
+    __syncwarp();
     OCTO_UNROLL_LOOP(OCTO_UNROLL)
-    for (int k = k0; k < k1; k += kstep) {
+    for (int j = 0; j < nrec; ++j) {
+        const double2 ra0 = stage[3 * j], ra1 = stage[3 * j + 1], ra2 = stage[3 * j + 2];
         const double t = ra0.x, y1 = ra0.y, e1 = ra1.x, y2 = ra1.y, e2 = ra2.x, e3 = ra2.y;
-        {
-            const int64_t kn = min(k + kstep, k1 - 1);
-            ra0 = __ldg(tab + 3 * kn); ra1 = __ldg(tab + 3 * kn + 1); ra2 = __ldg(tab + 3 * kn + 2);
-        }
         double sE[NPT], cE[NPT], dt[NPT];
         double ra = 0.0, dec = 0.0;
 #pragma unroll
@@ -331,29 +320,29 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
             }
         }
     }
-    __syncwarp();
-    acc_add(acc, 0, lane, ll, red);
+    }
+    acc_add(acc, 0, lane, ll);
     if (GRAD) {
         if (!LEAN) {
-            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit, red);
-            if (B.slot_platescale >= 0) acc_add(acc, B.slot_platescale, lane, pasep ? g_ps : g_ps / ps, red);
-            if (B.slot_northangle >= 0) acc_add(acc, B.slot_northangle, lane, g_na, red);
+            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
+            if (B.slot_platescale >= 0) acc_add(acc, B.slot_platescale, lane, pasep ? g_ps : g_ps / ps);
+            if (B.slot_northangle >= 0) acc_add(acc, B.slot_northangle, lane, g_na);
         }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             const int p = pj[u];
             const double fu = f[u];
-            acc_add(acc, slot_planet(p, PA_Bh), lane, fu * L[u][0], red);
-            acc_add(acc, slot_planet(p, PA_Gs), lane, fu * L[u][1], red);
-            acc_add(acc, slot_planet(p, PA_Ah), lane, fu * L[u][2], red);
-            acc_add(acc, slot_planet(p, PA_Fs), lane, fu * L[u][3], red);
-            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][4], red);
-            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][5], red);
-            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][6], red);
+            acc_add(acc, slot_planet(p, PA_Bh), lane, fu * L[u][0]);
+            acc_add(acc, slot_planet(p, PA_Gs), lane, fu * L[u][1]);
+            acc_add(acc, slot_planet(p, PA_Ah), lane, fu * L[u][2]);
+            acc_add(acc, slot_planet(p, PA_Fs), lane, fu * L[u][3]);
+            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][4]);
+            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][5]);
+            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][6]);
             if (u > 0) {   // d f / d mu = [a_j < a_i]
                 const double ind = (s_const[(p * PC_COUNT + PC_a) * 32 + lane] < a_ip) ? 1.0 : 0.0;
                 const double gf = fma(Bh[u], L[u][0], fma(Gs[u], L[u][1], fma(Ah[u], L[u][2], Fs[u] * L[u][3])));
-                acc_add(acc, slot_planet(p, PA_mu), lane, ind * gf, red);
+                acc_add(acc, slot_planet(p, PA_mu), lane, ind * gf);
             }
         }
     }
@@ -364,8 +353,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 template <bool GRAD, int NPT, bool MARGIN, bool JIT>
 __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
-                                    double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int lane,
-                                    int kstep, bool red) {
+                                    double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
     const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
     constexpr bool margin = MARGIN;
     int pj[NPT]; double f[NPT], dmu[NPT]; Orb orb[NPT]; double Pc[NPT], Ps[NPT];
@@ -413,15 +401,19 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; if constexpr (MARGIN) V[u][a] = 0.0; }
 
     const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
-    double2 ra0, ra1;
-    if (k0 < k1) { ra0 = __ldg(tab + 3 * (int64_t)k0); ra1 = __ldg(tab + 3 * (int64_t)k0 + 1); }
+    for (int kb = k0; kb < k1; kb += 32) {
+    const int nrec = min(32, k1 - kb);
+    __syncwarp();
+    if (lane < nrec) {
+        const double2* src = tab + 3 * (int64_t)(kb + lane);
+        const double2 a0 = __ldg(src), a1 = __ldg(src + 1);
+        stage[3 * lane] = a0; stage[3 * lane + 1] = a1;
+    }
+    __syncwarp();
     OCTO_UNROLL_LOOP(OCTO_UNROLL)
-    for (int k = k0; k < k1; k += kstep) {
+    for (int j = 0; j < nrec; ++j) {
+        const double2 ra0 = stage[3 * j], ra1 = stage[3 * j + 1];
         const double t = ra0.x, y = ra0.y, e1 = ra1.x;
-        {
-            const int64_t kn = min(k + kstep, k1 - 1);
-            ra0 = __ldg(tab + 3 * kn); ra1 = __ldg(tab + 3 * kn + 1);
-        }
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
         double model = off;
 #pragma unroll
@@ -470,36 +462,36 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             }
         }
     }
-    __syncwarp();
+    }
     if constexpr (MARGIN) {
         const int s0 = B.slot_margin;
-        acc_add(acc, s0 + MA_A, lane, mA, red);   acc_add(acc, s0 + MA_S1, lane, mS1, red); acc_add(acc, s0 + MA_C, lane, mC, red);
-        acc_add(acc, s0 + MA_LG, lane, mLG, red); acc_add(acc, s0 + MA_R2, lane, mR2, red); acc_add(acc, s0 + MA_R1, lane, mR1, red);
-        acc_add(acc, s0 + MA_Q, lane, mQ, red);
+        acc_add(acc, s0 + MA_A, lane, mA);   acc_add(acc, s0 + MA_S1, lane, mS1); acc_add(acc, s0 + MA_C, lane, mC);
+        acc_add(acc, s0 + MA_LG, lane, mLG); acc_add(acc, s0 + MA_R2, lane, mR2); acc_add(acc, s0 + MA_R1, lane, mR1);
+        acc_add(acc, s0 + MA_Q, lane, mQ);
     } else {
-        acc_add(acc, 0, lane, ll, red);
+        acc_add(acc, 0, lane, ll);
     }
     if (GRAD) {
         if (!margin) {
-            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit, red);
-            if (B.slot_offset >= 0) acc_add(acc, B.slot_offset, lane, g_off, red);
+            if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
+            if (B.slot_offset >= 0) acc_add(acc, B.slot_offset, lane, g_off);
         }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             const int p = pj[u];
             const double fu = f[u];
-            acc_add(acc, slot_planet(p, PA_Pc), lane, fu * L[u][0], red);
-            acc_add(acc, slot_planet(p, PA_Ps), lane, fu * L[u][1], red);
-            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][2], red);
-            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][3], red);
-            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][4], red);
-            if (dmu[u] != 0.0) acc_add(acc, slot_planet(p, PA_mu), lane, dmu[u] * fma(Pc[u], L[u][0], Ps[u] * L[u][1]), red);
+            acc_add(acc, slot_planet(p, PA_Pc), lane, fu * L[u][0]);
+            acc_add(acc, slot_planet(p, PA_Ps), lane, fu * L[u][1]);
+            acc_add(acc, slot_planet(p, PA_e), lane, fu * L[u][2]);
+            acc_add(acc, slot_planet(p, PA_S0), lane, fu * L[u][3]);
+            acc_add(acc, slot_planet(p, PA_S1), lane, fu * L[u][4]);
+            if (dmu[u] != 0.0) acc_add(acc, slot_planet(p, PA_mu), lane, dmu[u] * fma(Pc[u], L[u][0], Ps[u] * L[u][1]));
             if constexpr (MARGIN) {
                 const int v0 = B.slot_margin + MA_COUNT + p * MV_COUNT;
-                acc_add(acc, v0 + MV_Pc, lane, fu * V[u][0], red); acc_add(acc, v0 + MV_Ps, lane, fu * V[u][1], red);
-                acc_add(acc, v0 + MV_e, lane, fu * V[u][2], red);  acc_add(acc, v0 + MV_S0, lane, fu * V[u][3], red);
-                acc_add(acc, v0 + MV_S1, lane, fu * V[u][4], red);
-                acc_add(acc, v0 + MV_mu, lane, dmu[u] * fma(Pc[u], V[u][0], Ps[u] * V[u][1]), red);
+                acc_add(acc, v0 + MV_Pc, lane, fu * V[u][0]); acc_add(acc, v0 + MV_Ps, lane, fu * V[u][1]);
+                acc_add(acc, v0 + MV_e, lane, fu * V[u][2]);  acc_add(acc, v0 + MV_S0, lane, fu * V[u][3]);
+                acc_add(acc, v0 + MV_S1, lane, fu * V[u][4]);
+                acc_add(acc, v0 + MV_mu, lane, dmu[u] * fma(Pc[u], V[u][0], Ps[u] * V[u][1]));
             }
         }
     }
@@ -661,32 +653,26 @@ __device__ __noinline__ void chain_epilogue(const DevModel& m, const double* s_c
 
 template <bool GRAD, int NPT>
 __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
-                                            double* acc, const double* __restrict__ in, int64_t c, int64_t ld, int col,
-                                            int kstep, bool red) {
+                                            double* acc, double2* stage, const double* __restrict__ in, int64_t c,
+                                            int64_t ld, int lane) {
     if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
         const bool lean = B.kind == OCTO_KIND_ASTROM_RADEC && !B.jit && B.idx_platescale < 0 && B.idx_northangle < 0;
-        if (lean) seg_astrom<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
-        else seg_astrom<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        if (lean) seg_astrom<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        else seg_astrom<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-        seg_rv<GRAD, NPT, true, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        seg_rv<GRAD, NPT, true, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     } else if (B.jit) {
-        seg_rv<GRAD, NPT, false, true>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        seg_rv<GRAD, NPT, false, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     } else {
-        seg_rv<GRAD, NPT, false, false>(m, B, k0, k1, s_const, acc, in, c, ld, col, kstep, red);
+        seg_rv<GRAD, NPT, false, false>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     }
 }
 
-// Two lane mappings share all the code below:
-//  * chain-lane (G == 0): lane = chain of a 32-chain group, warp = contiguous epoch range, grid.y = epoch splits.
-//    Epoch data are warp-uniform; best when there is enough work per chain group (throughput regime).
-//  * epoch-lane (G > 0): a chain is owned by G warps whose lanes stride over the epochs of each table; the
-//    epoch sum is a warp shuffle + the CTA reduction, so no cross-CTA combine exists at all.  A CTA holds
-//    W/G chains.  Best when chains x epochs is small (latency regime, e.g. 1024 chains x 200 epochs).
 template <bool GRAD, int NPT>
 __global__ void __launch_bounds__(W * 32, OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
-              unsigned int* __restrict__ tickets, int G) {
+              unsigned int* __restrict__ tickets) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_acc = m.n_acc;
@@ -694,7 +680,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
     double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
     double* s_g = s_red + n_acc * 32;                         // [n_in][32]
-    int* s_ok = reinterpret_cast<int*>(s_g + m.n_in * 32);    // [32]
+    double2* s_stage = reinterpret_cast<double2*>(s_g + m.n_in * 32);   // [W][32 records][3]
+    int* s_ok = reinterpret_cast<int*>(s_stage + W * 96);     // [32]
     __shared__ int s_last;
 
 #ifdef OCTO_TIMING
@@ -708,7 +695,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     if (n_chains > 0) { if (threadIdx.x == 0 && blockIdx.y == 0) ll_out[blockIdx.x] = 0.0; return; }   // launch-floor probe
 #endif
     // columns of the shared-memory arrays = chains of this CTA
-    const int ncol = G > 0 ? W / G : 32;
+    constexpr int ncol = 32;
     const int64_t chain0 = (int64_t)blockIdx.x * ncol;
     auto chain_of = [&](int col) { const int64_t cc = chain0 + col; return cc < n_chains ? cc : n_chains - 1; };
 
@@ -743,8 +730,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     __syncthreads();
     OCTO_TICK();
 
-    if (G == 0) {
-        // ---- chain-lane: this warp's contiguous range of the concatenated epoch list
+    {
+        // ---- this warp's contiguous range of the concatenated epoch list
         const int64_t c = chain_of(lane);
         const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
         const int k_lo = (int)(m.n_epochs * u / U), k_hi = (int)(m.n_epochs * (u + 1) / U);
@@ -753,20 +740,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             const DevBlock& B = m.blocks[b];
             const int k0 = max(k_lo, B.start), k1 = min(k_hi, B.start + B.n);
             if (k0 >= k1) continue;
-            run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, in, c, ld, lane, 1, false);
-        }
-    } else {
-        // ---- epoch-lane: warp (w / G) of chain column w / G; lanes stride over every table's epochs
-        const int col = w / G, g = w % G;
-        if (chain0 + col < n_chains) {
-            const int64_t c = chain0 + col;
-#pragma unroll 1
-            for (int b = 0; b < m.n_blocks; ++b) {
-                const DevBlock& B = m.blocks[b];
-                if (B.n == 0) continue;
-                run_segment<GRAD, NPT>(m, B, B.start + g * 32 + lane, B.start + B.n, s_const, acc, in, c, ld, col,
-                                       32 * G, true);
-            }
+            run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, in, c, ld, lane);
         }
     }
     __syncthreads();
@@ -783,31 +757,9 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     __syncthreads();
     OCTO_TICK();
 
-    // ---- K2: combine the epoch splits of this chain group.
-    // (a) cluster launch (the splits of a chain group are one thread-block cluster, <= 8 CTAs): every CTA sums,
-    //     over distributed shared memory, the slots of ITS share of the 32 chains (lane % n_cta == rank) in split
-    //     order, then runs the epilogue for those chains — no global round trip, no atomics.
-    // (b) otherwise: partials through L2 + a ticket; the last CTA to arrive sums them in split order.
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned int nc = cluster.num_blocks();
-    int lane_mod = 1, lane_rem = 0;             // which lanes this CTA finishes: lane % lane_mod == lane_rem
-    if (nc > 1) {
-        cluster.sync();                          // every CTA's s_red is complete and visible cluster-wide
-        const unsigned int rank = cluster.block_rank();
-        lane_mod = (int)nc; lane_rem = (int)rank;
-        const int lanes_mine = 32 / (int)nc;     // nc is 2, 4 or 8
-        double* s_tot = s_acc;                   // scratch: this CTA's warp partials are no longer needed
-#pragma unroll 1
-        for (int it = threadIdx.x; it < n_acc * lanes_mine; it += W * 32) {
-            const int slot = it / lanes_mine, l = (it % lanes_mine) * (int)nc + (int)rank;
-            double v = 0.0;
-#pragma unroll 1
-            for (unsigned int y = 0; y < nc; ++y) v += cluster.map_shared_rank(s_red, y)[slot * 32 + l];
-            s_tot[slot * 32 + l] = v;
-        }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading the peers' smem
-        __syncthreads();
-    } else if (gridDim.y > 1) {
+    // ---- K2: combine the epoch splits of this chain group: partials through L2 + a ticket; the last CTA to
+    //      arrive sums them in split order (run-to-run bit-reproducible)
+    if (gridDim.y > 1) {
         double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
 #pragma unroll 2
         for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
@@ -851,8 +803,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         const bool active = lane < ncol && chain0 + lane < n_chains;
         const int valid = s_ok[lane];
         double ll;
-        chain_epilogue<GRAD>(m, s_const, nc > 1 ? s_acc : s_red, s_g, in, c, ld, lane, ll);
-        if (active && (lane % lane_mod) == lane_rem) {
+        chain_epilogue<GRAD>(m, s_const, s_red, s_g, in, c, ld, lane, ll);
+        if (active) {
             ll_out[c] = valid ? ll : -CUDART_INF;
             if (GRAD) {
 #pragma unroll 4
@@ -860,7 +812,6 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             }
         }
     }
-    if (nc > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // peers finished reading ours
 #ifdef OCTO_TIMING
     if (threadIdx.x == 0 && blockIdx.x < 2) {
         tm[tmi++] = clock64();
@@ -891,26 +842,16 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
 
 size_t octo_smem_bytes(const DevModel& m) {
     size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (size_t)W * m.n_acc * 32 + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
-    return d * sizeof(double) + (size_t)32 * sizeof(int);
+    return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 
 template <bool GRAD, int NPT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             cudaStream_t st) {
-    if (!g.cluster) {
-        k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
-                                                                            d_tickets, g.G);
-        return cudaGetLastError();
-    }
-    // the epoch splits of one chain group form a thread-block cluster (1 x gy x 1)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g.gx, g.gy); cfg.blockDim = dim3(g.block); cfg.dynamicSmemBytes = g.smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = g.gy; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, g.G);
+    k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
+                                                                        d_tickets);
+    return cudaGetLastError();
 }
 
 // opt every instantiation in to `smem_bytes` of dynamic shared memory (once per context)

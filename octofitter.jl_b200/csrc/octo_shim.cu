@@ -62,9 +62,6 @@ struct OctoCtx {
     std::atomic<int64_t> launches{0};
     int ctas_per_sm = 2;
     int slice_override = 0;
-    int use_clusters = 0;          // DSMEM combine of epoch splits: measured no faster than the L2 ticket path
-    int epoch_lanes = 0;           // 0: chain-lane mapping (default; measured fastest on C2), -1: auto, G > 0: force G warps per chain
-    int64_t max_block_epochs = 0;
     // parallel tempering
     void* nccl_comm = nullptr;
     int pt_rank = 0, pt_world = 1, pt_local = 0;
@@ -160,26 +157,8 @@ void free_ws(Workspace* w) {
 LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     LaunchGeom g;
     g.block = OCTO_WARPS * 32;
-    g.cluster = 0; g.G = 0; g.smem = ctx->smem;
+    g.smem = ctx->smem;
     const int64_t E = ctx->m.n_epochs;
-    // latency regime (few pair evaluations per resident lane): epoch-lane mapping, G warps per chain, no epoch
-    // splits across CTAs.  Otherwise the chain-lane mapping below.
-    {
-        const int64_t resident_warps = (int64_t)ctx->n_sm * ctx->ctas_per_sm * OCTO_WARPS;
-        int G = 0;
-        if (ctx->epoch_lanes > 0) G = ctx->epoch_lanes;
-        else if (ctx->epoch_lanes < 0 && ctx->max_block_epochs >= 16 && n_chains * E < 12 * 32 * resident_warps) {
-            G = 1;
-            while (G < 8 && 2 * G * n_chains <= resident_warps && 32 * G < ctx->max_block_epochs) G *= 2;
-        }
-        if (G > 0) {
-            if (G > OCTO_WARPS) G = OCTO_WARPS;
-            const int cpc = OCTO_WARPS / G;
-            g.G = G; g.gx = (int)((n_chains + cpc - 1) / cpc); g.gy = 1;
-            g.slice = (int)((ctx->max_block_epochs + 32 * G - 1) / (32 * G));
-            return g;
-        }
-    }
     g.gx = (int)((n_chains + 31) / 32);
     const int min_slice = ctx->slice_override > 0 ? ctx->slice_override : OCTO_MIN_SLICE;
     int64_t max_gy = E / ((int64_t)min_slice * OCTO_WARPS);
@@ -204,19 +183,6 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
         }
     }
     if (gy < 1) gy = 1;
-    // latency-bound regime (few epochs per warp): make the splits of a chain group one thread-block cluster
-    // (2, 4 or 8 CTAs) so that they combine over distributed shared memory instead of through L2 + a ticket
-    g.cluster = 0;
-    if (ctx->use_clusters && gy > 1 && E / (gy * OCTO_WARPS) <= 8) {
-        auto util = [&](int64_t c) {
-            const double waves = (double)(g.gx * c) / (double)resident;
-            return waves >= 1.0 ? waves / std::ceil(waves) : waves;
-        };
-        int64_t best = 0; double bu = -1.0;
-        for (int64_t c = 2; c <= 8 && c <= max_gy; c *= 2)
-            if (util(c) >= bu - 0.02) { bu = util(c); best = c; }
-        if (best && bu >= 0.8 * util(gy)) { gy = best; g.cluster = 1; }
-    }
     g.gy = (int)gy;
     g.slice = (int)((E + gy * OCTO_WARPS - 1) / (gy * OCTO_WARPS));
     return g;
@@ -225,7 +191,7 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
             int64_t ldg, cudaStream_t st) {
     LaunchGeom g = geometry(ctx, n);
-    if (g.gy > 1 && !g.cluster) {
+    if (g.gy > 1) {
         size_t need = (size_t)g.gx * g.gy * ctx->m.n_acc * 32;
         if (int rc = ensure(&w->d_partial, &w->cap_partial, need)) return rc;
         if ((size_t)g.gx > w->cap_tickets) {
@@ -421,9 +387,6 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ctx->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete ctx; return fail(OCTO_ERR_ARG, "model too large: accumulator slots exceed shared memory");
     }
-    if (const char* s = getenv("OCTO_B200_CLUSTERS")) ctx->use_clusters = atoi(s);
-    if (const char* s = getenv("OCTO_B200_EPOCH_LANES")) ctx->epoch_lanes = atoi(s);
-    for (int b = 0; b < n_blocks; ++b) if (blocks[b].n_epochs > ctx->max_block_epochs) ctx->max_block_epochs = blocks[b].n_epochs;
     if (const char* s = getenv("OCTO_B200_SLICE")) ctx->slice_override = std::max(1, atoi(s));
     ce = cudaMalloc((void**)&ctx->d_tables, T.size() * sizeof(double));
     if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaMalloc tables"); }
@@ -505,10 +468,10 @@ int32_t octo_n_planets(const OctoCtx* ctx) { return ctx ? ctx->m.n_planets : -1;
 int64_t octo_total_epochs(const OctoCtx* ctx) { return ctx ? ctx->m.n_epochs : -1; }
 int32_t octo_device(const OctoCtx* ctx) { return ctx ? ctx->device : -1; }
 int64_t octo_kernel_launches(const OctoCtx* ctx) { return ctx ? ctx->launches.load() : -1; }
-int octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[6]) {
+int octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]) {
     if (!ctx || !out || n_chains < 1) return fail(OCTO_ERR_ARG, "bad argument");
     LaunchGeom g = geometry(ctx, n_chains);
-    out[0] = g.gx; out[1] = g.gy; out[2] = g.block; out[3] = g.slice; out[4] = g.cluster; out[5] = g.G;
+    out[0] = g.gx; out[1] = g.gy; out[2] = g.block; out[3] = g.slice;
     return OCTO_OK;
 }
 

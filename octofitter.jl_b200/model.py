@@ -313,8 +313,8 @@ class LogDensityModel:
         return int(self._lib.octo_kernel_launches(self._h))
 
     def launch_geometry(self, n_chains):
-        """(grid.x, grid.y, block, epochs-or-strides per warp, cluster, G) — see octo_launch_geometry."""
-        out = (C.c_int32 * 6)()
+        """(grid.x = chain groups, grid.y = epoch splits, block, epochs per warp) — see octo_launch_geometry."""
+        out = (C.c_int32 * 4)()
         self._lib.octo_launch_geometry(self._h, int(n_chains), C.byref(out))
         return tuple(out)
 

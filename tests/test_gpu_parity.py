@@ -143,8 +143,8 @@ def test_epoch_split_geometry_consistent(oracle_lib):
     """Many epochs, few chains: the grid splits epochs across CTAs (K2 path) and still matches."""
     spec, x = workloads.one_planet(3000, 0, 40, seed=9)
     model = octo.LogDensityModel(spec)
-    gx, gy, block, slice_, cluster, G = model.launch_geometry(40)
-    assert gy > 1 and G == 0
+    gx, gy, block, slice_ = model.launch_geometry(40)
+    assert gy > 1
     ll, g = model.ln_like_and_gradient(x)
     orc = oracle_lib.Oracle(spec.packed, octo.default_constants())
     ll_o, g_o = orc.logp_grad(x, threads=8)
@@ -152,20 +152,15 @@ def test_epoch_split_geometry_consistent(oracle_lib):
     model.close()
 
 
-@pytest.mark.parametrize("env", [{"OCTO_B200_EPOCH_LANES": "0"}, {"OCTO_B200_EPOCH_LANES": "1"},
-                                 {"OCTO_B200_EPOCH_LANES": "4"}, {"OCTO_B200_EPOCH_LANES": "8"},
-                                 {"OCTO_B200_EPOCH_LANES": "0", "OCTO_B200_CLUSTERS": "1"}])
-def test_every_lane_mapping_matches_oracle(oracle_lib, env, monkeypatch):
-    """Force each launch strategy (chain-lane with L2 ticket combine, with DSMEM cluster combine, epoch-lane with
-    1/4/8 warps per chain) on the 2-planet C3 model and on C2; all must agree with the oracle."""
+@pytest.mark.parametrize("env", [{}, {"OCTO_B200_SLICE": "1"}, {"OCTO_B200_SLICE": "40"}, {"OCTO_B200_CTAS_PER_SM": "1"}])
+def test_launch_geometry_knobs_do_not_change_results(oracle_lib, env, monkeypatch):
+    """Different epoch-split geometries (slice length, resident-CTA target) on C2 and the 2-planet C3."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for cfg in ("C2", "C3"):
         spec, x = workloads.config(cfg)
         x = x[:70]
         model = octo.LogDensityModel(spec)
-        geo = model.launch_geometry(x.shape[0])
-        assert geo[5] == int(env["OCTO_B200_EPOCH_LANES"])
         ll, g = model.ln_like_and_gradient(x)
         llv = model.ln_like(x)
         model.close()
