@@ -69,6 +69,6 @@ struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, cudaStream_t stream);
-size_t octo_smem_bytes(const DevModel& m);
-cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int* ctas_per_sm);
+size_t octo_smem_bytes(const DevModel& m, int warps);
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);

@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int W = OCTO_WARPS;
+constexpr int WMAX = OCTO_WARPS;   // warps per CTA (models whose accumulator slots would not fit launch with fewer)
 #ifndef OCTO_MIN_CTAS
 #define OCTO_MIN_CTAS 2          // resident CTAs/SM the register allocator targets
 #endif
@@ -669,12 +669,13 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
 }
 
 template <bool GRAD, int NPT>
-__global__ void __launch_bounds__(W * 32, OCTO_MIN_CTAS)
+__global__ void __launch_bounds__(WMAX * 32, OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
     const int n_acc = m.n_acc;
     double* s_const = smem;                                   // [P][PC_COUNT][32]
     double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
@@ -750,7 +751,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #pragma unroll 1
     for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
         double v = s_acc[idx];
-#pragma unroll
+#pragma unroll 8
         for (int ww = 1; ww < W; ++ww) v += s_acc[ww * n_acc * 32 + idx];
         s_red[idx] = v;
     }
@@ -840,7 +841,7 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
     return cudaGetLastError();
 }
 
-size_t octo_smem_bytes(const DevModel& m) {
+size_t octo_smem_bytes(const DevModel& m, int W) {
     size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (size_t)W * m.n_acc * 32 + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
@@ -855,7 +856,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 }
 
 // opt every instantiation in to `smem_bytes` of dynamic shared memory (once per context)
-cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int* ctas_per_sm) {
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int W, int* ctas_per_sm) {
     cudaError_t e;
 #define OCTO_ATTR(G, N)                                                                                            \
     e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);   \

@@ -61,6 +61,7 @@ struct OctoCtx {
     std::vector<std::pair<cudaStream_t, Workspace*>> stream_ws;    // device-buffer calls: one per caller stream
     std::atomic<int64_t> launches{0};
     int ctas_per_sm = 2;
+    int warps = OCTO_WARPS;        // warps per CTA; halved until the model's accumulator slots fit in shared memory
     int slice_override = 0;
     // parallel tempering
     void* nccl_comm = nullptr;
@@ -156,12 +157,13 @@ void free_ws(Workspace* w) {
 // per warp so the per-CTA prologue/epilogue is amortised and the hardware CTA scheduler balances the tail.
 LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     LaunchGeom g;
-    g.block = OCTO_WARPS * 32;
+    const int W = ctx->warps;
+    g.block = W * 32;
     g.smem = ctx->smem;
     const int64_t E = ctx->m.n_epochs;
     g.gx = (int)((n_chains + 31) / 32);
     const int min_slice = ctx->slice_override > 0 ? ctx->slice_override : OCTO_MIN_SLICE;
-    int64_t max_gy = E / ((int64_t)min_slice * OCTO_WARPS);
+    int64_t max_gy = E / ((int64_t)min_slice * W);
     if (max_gy < 1) max_gy = 1;
     if (max_gy > 65535) max_gy = 65535;
     const int64_t resident = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
@@ -169,7 +171,7 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     if (gy_fill > max_gy) gy_fill = max_gy;
     int64_t gy = gy_fill;
     if ((int64_t)g.gx * gy_fill >= 4 * resident) {
-        const int64_t gy_big = E / (32 * OCTO_WARPS);
+        const int64_t gy_big = E / (32 * W);
         gy = gy_big > gy_fill ? (gy_big < max_gy ? gy_big : max_gy) : gy_fill;
     } else if ((int64_t)g.gx * max_gy > resident) {
         // pick the split count whose CTA total is closest below an integral number of waves
@@ -184,7 +186,7 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     }
     if (gy < 1) gy = 1;
     g.gy = (int)gy;
-    g.slice = (int)((E + gy * OCTO_WARPS - 1) / (gy * OCTO_WARPS));
+    g.slice = (int)((E + gy * W - 1) / (gy * W));
     return g;
 }
 
@@ -342,7 +344,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
     // + padding: the kernels prefetch one lane-stride (<= 32*8 records) past the record they read
-    std::vector<double> T((size_t)6 * ((E > 0 ? E : 1) + 32 * OCTO_WARPS + 1), 0.0);
+    std::vector<double> T((size_t)6 * (E > 0 ? E : 1), 0.0);
     struct Col { double* b; double& operator[](size_t o) const { return b[6 * o]; } };   // AoS record field view
     const Col t{T.data()}, y1{T.data() + 1}, c1{T.data() + 2}, y2{T.data() + 3}, c2{T.data() + 4}, c3{T.data() + 5};
     long double cll = 0.0L;
@@ -383,7 +385,9 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaGetDeviceProperties"); }
     if (prop.major < 10) { delete ctx; return fail(OCTO_ERR_CUDA, "libocto_b200 is built for sm_100a only"); }
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
-    ctx->smem = octo_smem_bytes(m);
+    ctx->warps = OCTO_WARPS;
+    while (ctx->warps > 1 && octo_smem_bytes(m, ctx->warps) > (size_t)prop.sharedMemPerBlockOptin) ctx->warps /= 2;
+    ctx->smem = octo_smem_bytes(m, ctx->warps);
     if (ctx->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete ctx; return fail(OCTO_ERR_ARG, "model too large: accumulator slots exceed shared memory");
     }
@@ -394,7 +398,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
     m.tab = ctx->d_tables;
     int occ = 0;
-    ce = octo_kernels_init(m, ctx->smem, &occ);
+    ce = octo_kernels_init(m, ctx->smem, ctx->warps, &occ);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
     ctx->ctas_per_sm = occ > 0 ? occ : 1;
     if (const char* s = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, atoi(s));

@@ -100,6 +100,45 @@ def test_baseline_configs_match_oracle(oracle_lib, cfg):
     model.close()
 
 
+@pytest.mark.parametrize("n_planets", [3, 4])
+def test_many_planets_every_kind(oracle_lib, n_planets):
+    """3 and 4 planets (the NPT=4 kernel instantiation): reflex astrometry from several interior companions in
+    RA/Dec and PA/sep tables, relative RV with interior companions, star RV, marginalised RV."""
+    spec, x = workloads.many_planets(n_planets, 45, seed=21)
+    model = octo.LogDensityModel(spec)
+    ll, g = model.ln_like_and_gradient(x)
+    llv = model.ln_like(x)
+    model.close()
+    orc = oracle_lib.Oracle(spec.packed, octo.default_constants())
+    ll_o, g_o = orc.logp_grad(x, threads=8)
+    assert np.all(np.isfinite(ll_o))
+    assert rel_err(ll, ll_o).max() < LOGP_RTOL and rel_err(llv, ll_o).max() < LOGP_RTOL
+    assert grad_err(g, g_o).max() < GRAD_RTOL
+
+
+def test_degenerate_shapes(oracle_lib):
+    """Empty table next to a populated one, a single epoch, a model with no tables at all, zero chains."""
+    import ctypes as C
+    t1 = octo.Table(epoch=[50000.0], ra=[100.0], dec=[-50.0], σ_ra=[2.0], σ_dec=[3.0])
+    t0 = octo.Table(epoch=[], ra=[], dec=[], σ_ra=[], σ_dec=[])
+    for tabs in ([t1], [t0, t1], [t0], []):
+        obs = [octo.PlanetRelAstromObs(t, name=f"o{k}") for k, t in enumerate(tabs)]
+        b = octo.Planet(name="b", variables=["a", "e", "i", "ω", "Ω", "tp"], observations=obs)
+        spec = octo.ModelSpec(octo.System(name="s", variables=["M", "plx"], companions=[b]))
+        x = np.array([[1.2, 50.0, 10.0, 0.3, 1.0, 0.5, 2.0, 50000.0], [1.1, 49.0, 9.0, 0.2, 0.9, 0.4, 1.9, 50100.0]])
+        model = octo.LogDensityModel(spec)
+        ll, g = model.ln_like_and_gradient(x)
+        orc = oracle_lib.Oracle(spec.packed, octo.default_constants())
+        ll_o, g_o = orc.logp_grad(x)
+        if spec.total_epochs == 0:
+            assert np.all(ll == 0.0) and np.all(g == 0.0) and np.all(ll_o == 0.0)
+        else:
+            assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+        # zero chains: a no-op that succeeds
+        assert model._lib.octo_logp_grad(model._h, None, 0, 0, None, None) == 0
+        model.close()
+
+
 def test_invalid_chains():
     spec, x = workloads.config("C2")
     x = np.array(x[:40])

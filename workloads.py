@@ -128,3 +128,50 @@ def config(name):
     if name == "C4":
         return one_planet(100, 0, 64, seed=4)
     raise KeyError(name)
+
+
+def many_planets(n_planets, n_chains, seed, n_ep=40):
+    """3-4 planet system touching every observation kind: RA/Dec (+cor, +jitter), PA/sep (+platescale,
+    northangle), relative RV, star RV and marginalised star RV; masses on all but the outermost planet."""
+    rng = np.random.default_rng(seed)
+    els = [dict(a=3.0 * 1.9 ** k, e=0.05 + 0.07 * k, i=0.9 + 0.05 * k, w=0.4 + 0.9 * k, W=1.8 + 0.1 * k,
+                tp=50000.0 + 300.0 * k, M=1.2, plx=40.0, mass=(3.0 + 2 * k)) for k in range(n_planets)]
+    truth = {"M": 1.2, "plx": 40.0}
+    planets, names = [], "bcde"
+    for k, el in enumerate(els):
+        P = _state(el, [0.0])[3]
+        ep = np.linspace(50000.0 + 7 * k, 50000.0 + min(0.8 * P, 9000.0), n_ep + 3 * k)
+        inner = [o for o in els if o["a"] < el["a"]]
+        obs = []
+        if k % 2 == 0:
+            tab = _astrom_table(el, ep, rng, sigma=3.0, cor_frac=0.3, others=inner)
+            obs.append(octo.PlanetRelAstromObs(tab, name=f"cam{k}", variables=["jitter"] if k == 2 else []))
+            if k == 2:
+                truth[f"{names[k]}.cam{k}.jitter"] = 1.5
+        else:
+            ra, dec, _, _ = _state(el, ep)
+            for o in inner:
+                r2, d2, _, _ = _state(o, ep); mu = o["mass"] * MJUP2MSOL / o["M"]; ra, dec = ra + mu * r2, dec + mu * d2
+            sep, pa = np.hypot(ra, dec), np.arctan2(ra, dec)
+            tab = octo.Table(epoch=ep, sep=sep + 2.0 * rng.standard_normal(len(ep)), pa=pa + 0.002 * rng.standard_normal(len(ep)),
+                             σ_sep=np.full(len(ep), 2.0), σ_pa=np.full(len(ep), 0.002), cor=rng.uniform(-0.5, 0.5, len(ep)))
+            obs.append(octo.PlanetRelAstromObs(tab, name=f"ifs{k}", variables=["platescale", "northangle"]))
+            truth[f"{names[k]}.ifs{k}.platescale"] = 1.002; truth[f"{names[k]}.ifs{k}.northangle"] = 0.003
+            epr = np.linspace(50100.0, 50900.0, 11)
+            obs.append(octo.PlanetRelativeRVObs(octo.Table(epoch=epr, rv=_state(el, epr)[2] + 200 * rng.standard_normal(11),
+                                                           σ_rv=np.full(11, 200.0)), name=f"crires{k}", variables=["jitter"]))
+            truth[f"{names[k]}.crires{k}.jitter"] = 80.0
+        pv = ["a", "e", "i", "ω", "Ω", "tp"] + ([] if k == n_planets - 1 and False else ["mass"])
+        planets.append(octo.Planet(name=names[k], variables=pv, observations=obs))
+        truth.update({f"{names[k]}.a": el["a"], f"{names[k]}.e": el["e"], f"{names[k]}.i": el["i"], f"{names[k]}.ω": el["w"],
+                      f"{names[k]}.Ω": el["W"], f"{names[k]}.tp": el["tp"], f"{names[k]}.mass": el["mass"]})
+    eps = np.linspace(50020.0, 53000.0, 25)
+    rv = sum(-el["mass"] * MJUP2MSOL / el["M"] * _state(el, eps)[2] for el in els)
+    s1 = octo.StarAbsoluteRVObs(octo.Table(epoch=eps[:13], rv=30 + rv[:13] + 4 * rng.standard_normal(13), σ_rv=np.full(13, 4.0)),
+                                name="harps", variables=["offset"])
+    s2 = octo.MarginalizedStarAbsoluteRVObs(octo.Table(epoch=eps[13:], rv=-12 + rv[13:] + 4 * rng.standard_normal(12),
+                                                       σ_rv=np.full(12, 4.0)), name="hires")
+    truth.update({"harps.offset": 30.0, "hires.jitter": 2.0})
+    system = octo.System(name="many", variables=["M", "plx"], companions=planets, observations=[s1, s2])
+    spec = octo.ModelSpec(system)
+    return spec, _chains(spec, truth, n_chains, rng, rel=0.01)
