@@ -156,6 +156,54 @@ int  octo_logp(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, dou
 int  octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld,
                     double* ll, double* g_in);
 
+/*
+ * ---- Standard parameterisation on the device ------------------------------------------------
+ * Optional: describe how the sampler's unconstrained vector θ_t (length D) maps to natural-space parameters, their
+ * priors, and the kernel inputs, and the library evaluates the whole log-posterior of the standard model families
+ *     ℓπ(θ_t) = Σ_j logpdf_with_trans(prior_j, invlink_j(θ_t[j]))      src/variables.jl:1205-1369, 1449-1493
+ *             + Σ UnitLengthPrior terms of UniformCircular variables    src/variables.jl:267-323
+ *             + ln_like(inputs(θ))                                      the path above
+ * and its gradient w.r.t. θ_t on the device, with no per-chain host work.  Prior families and bijectors follow
+ * Distributions.jl / Bijectors.jl (third-party, not in the reference tree; formulas in SURVEY.md Appendix B).
+ */
+#define OCTO_PRIOR_NORMAL      0   /* p = {mu, sigma}                     support R        : identity          */
+#define OCTO_PRIOR_UNIFORM     1   /* p = {a, b}                          [a, b]           : scaled logit      */
+#define OCTO_PRIOR_LOGUNIFORM  2   /* p = {a, b}                          [a, b]           : scaled logit      */
+#define OCTO_PRIOR_SINE        3   /* src/distributions.jl:15-40          [eps, pi - eps]  : scaled logit      */
+#define OCTO_PRIOR_TRUNCNORMAL 4   /* p = {mu, sigma, lower, upper} (+-Inf allowed): log-shift / scaled logit    */
+typedef struct OctoPrior {
+    int32_t family;
+    int32_t reserved;
+    double  p[4];
+} OctoPrior;
+
+#define OCTO_IN_PARAM 0   /* input = theta[a[0]]                                                                  */
+#define OCTO_IN_CONST 1   /* input = value                                                                        */
+#define OCTO_IN_CIRC  2   /* UniformCircular: input = atan(theta[a[1]], theta[a[0]]) / 2pi * value, and the
+                           * UnitLengthPrior LogNormal(0, 0.1) on hypot(theta[a[0]], theta[a[1]]) is added         */
+#define OCTO_IN_TPERI 3   /* tp = θ_at_epoch_to_tperi(in[a[0]], value; M=in[a[1]], e=in[a[2]], a=in[a[3]],
+                           * i=in[a[4]], ω=in[a[5]], Ω=in[a[6]])  (src/parameterizations.jl:6-69); the arguments
+                           * are EARLIER kernel inputs (their own definitions may be PARAM / CONST / CIRC)         */
+typedef struct OctoInputDef {
+    int32_t op;
+    int32_t a[7];
+    double  value;
+} OctoInputDef;
+
+/* Attach the parameterisation: D priors (one per entry of θ_t, in the reference's parameter order) and one
+ * definition per kernel input (n_in of them, evaluated in index order).  Copied; may be called again to replace. */
+int  octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, const OctoInputDef* defs);
+/* θ_t: HOST column-major [n_chains x D] (leading dimension ld); lp[n_chains]; g_t [n_chains x D] or NULL.
+ * What `ℓπcallback` / `∇ℓπcallback` return (src/logdensitymodel.jl:110-146, 169-177) for such a model. */
+int  octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* lp, double* g_t);
+/* Same on DEVICE buffers, enqueued on `stream`; d_work is caller-provided scratch of
+ * octo_logpost_workspace(ctx, n_chains) bytes. */
+int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n_chains);
+int  octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta_t, int64_t n_chains, int64_t ld, double* d_lp,
+                              double* d_g_t, void* d_work, void* stream);
+/* invlink only: natural-space parameters [n_chains x D] for a batch of θ_t (HOST buffers). */
+int  octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* theta_nat);
+
 /* Page-locked host memory for the HOST-buffer entry points.  Buffers that come from octo_alloc_pinned
  * are copied to/from the device directly (no staging copy); any other host pointer works too and is
  * staged through the context's own pinned buffers.  Returns NULL on failure (see octo_last_error). */

@@ -5,10 +5,11 @@ Only what the path needs lives here: `csrc/` (CUDA kernels + the C-ABI shim, bui
 The directory name is not a Python identifier; import it through the repo-root loader
 `octofitter_jl_b200` (see octofitter_jl_b200.py).
 """
-from ._abi import (OctoConstants, OctoLayout, OctoObsBlock, default_constants, load_library, pack,
+from ._abi import (OctoConstants, OctoLayout, OctoObsBlock, OctoPrior, OctoInputDef, default_constants, load_library, pack,
                    EXPORTED_SYMBOLS, LIB_PATH,
                    KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL)
-from .model import (Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, StarAbsoluteRVObs,
+from .model import (Normal, Uniform, LogUniform, Sine, truncated, UniformCircular, θ_at_epoch_to_tperi,
+                    theta_at_epoch_to_tperi, Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, StarAbsoluteRVObs,
                     StarAbsoluteRVLikelihood, MarginalizedStarAbsoluteRVObs, MarginalizedStarAbsoluteRVLikelihood,
                     PlanetRelativeRVObs, PlanetRelativeRVLikelihood, Planet, System, ModelSpec, LogDensityModel, OctoError)
 from .pt import ParallelTempering

@@ -47,6 +47,18 @@ class OctoLayout(C.Structure):
                 ("idx_W", _i4), ("idx_tp", _i4), ("idx_M", _i4), ("idx_mass", _i4)]
 
 
+PRIOR_NORMAL, PRIOR_UNIFORM, PRIOR_LOGUNIFORM, PRIOR_SINE, PRIOR_TRUNCNORMAL = range(5)
+IN_PARAM, IN_CONST, IN_CIRC, IN_TPERI = range(4)
+
+
+class OctoPrior(C.Structure):
+    _fields_ = [("family", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 4)]
+
+
+class OctoInputDef(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32 * 7), ("value", C.c_double)]
+
+
 def _dptr(a):
     return a.ctypes.data_as(_pd) if a is not None else _pd()
 
@@ -123,6 +135,12 @@ def load_library(path: str | None = None):
     lib.octo_logp.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_logp_grad.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.octo_logp_grad_device.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    lib.octo_set_parameterization.argtypes = [vp, C.POINTER(OctoPrior), i32, C.POINTER(OctoInputDef)]
+    lib.octo_logpost_grad.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.octo_logpost_workspace.argtypes = [vp, i64]
+    lib.octo_logpost_workspace.restype = i64
+    lib.octo_logpost_grad_device.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
+    lib.octo_invlink.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_alloc_pinned.argtypes = [C.c_size_t]
     lib.octo_alloc_pinned.restype = vp
     lib.octo_free_pinned.argtypes = [vp]
@@ -153,6 +171,7 @@ def load_library(path: str | None = None):
 
 EXPORTED_SYMBOLS = (
     "octo_default_constants", "octo_abi_version", "octo_create", "octo_destroy", "octo_logp", "octo_logp_grad",
-    "octo_logp_grad_device", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
+    "octo_logp_grad_device", "octo_set_parameterization", "octo_logpost_grad", "octo_logpost_workspace",
+    "octo_logpost_grad_device", "octo_invlink", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
     "octo_pt_decide", "octo_pt_finalize", "octo_last_error")

@@ -63,6 +63,15 @@ struct DevModel {
 // slot 0 = ll; planets follow
 __host__ __device__ inline int slot_planet(int p, int a) { return 1 + p * PA_COUNT + a; }
 
+// ---- device-side standard parameterisation (octo_param.cu)
+#define OCTO_PARAM_MAX 64         // max D and max n_in of a parameterised model
+struct DevParam {
+    int32_t D, n_in;
+    OctoPrior priors[OCTO_PARAM_MAX];
+    double lognorm[OCTO_PARAM_MAX];      // log(Φ(β) - Φ(α)) of truncated normals, 0 otherwise
+    OctoInputDef defs[OCTO_PARAM_MAX];
+};
+
 struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
 
 // kernels (octo_kernels.cu)
@@ -72,3 +81,10 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
 size_t octo_smem_bytes(const DevModel& m, int warps);
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);
+cudaError_t octo_param_forward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
+                               double* d_in, cudaStream_t st);
+cudaError_t octo_param_backward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
+                                const double* d_ll, const double* d_g_in, double* d_lp, double* d_g_t, int64_t ldg,
+                                cudaStream_t st);
+cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,
+                               cudaStream_t st);

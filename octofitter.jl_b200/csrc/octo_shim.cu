@@ -33,6 +33,8 @@ struct Workspace {
     double *d_in = nullptr, *d_ll = nullptr, *d_g = nullptr, *d_partial = nullptr;
     unsigned int* d_tickets = nullptr;
     double *h_in = nullptr, *h_out = nullptr;          // pinned staging
+    double *d_theta = nullptr, *d_post = nullptr;      // parameterised entry points: θ_t and [lp | g_t]
+    size_t cap_theta = 0, cap_post = 0;
     size_t cap_in = 0, cap_ll = 0, cap_g = 0, cap_partial = 0, cap_tickets = 0, cap_hin = 0, cap_hout = 0;
     bool busy = false;
 };
@@ -63,6 +65,9 @@ struct OctoCtx {
     int ctas_per_sm = 2;
     int warps = OCTO_WARPS;        // warps per CTA; halved until the model's accumulator slots fit in shared memory
     int slice_override = 0;
+    // device-side parameterisation (N1)
+    DevParam* d_param = nullptr;
+    int param_D = 0;
     // parallel tempering
     void* nccl_comm = nullptr;
     int pt_rank = 0, pt_world = 1, pt_local = 0;
@@ -146,6 +151,8 @@ void free_ws(Workspace* w) {
     if (w->d_g) cudaFree(w->d_g);
     if (w->d_partial) cudaFree(w->d_partial);
     if (w->d_tickets) cudaFree(w->d_tickets);
+    if (w->d_theta) cudaFree(w->d_theta);
+    if (w->d_post) cudaFree(w->d_post);
     if (w->h_in) cudaFreeHost(w->h_in);
     if (w->h_out) cudaFreeHost(w->h_out);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -414,6 +421,7 @@ void octo_destroy(OctoCtx* ctx) {
     for (Workspace* w : ctx->pool) free_ws(w);
     for (auto& kv : ctx->stream_ws) free_ws(kv.second);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_param) cudaFree(ctx->d_param);
     delete ctx;
 }
 
@@ -427,6 +435,149 @@ int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t l
     CU(cudaSetDevice(ctx->device));
     Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);   // partial buffer + tickets of this stream
     return enqueue(ctx, w, d_g != nullptr, d_in, n, ld, d_ll, d_g, ld, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standard parameterisation on the device
+// ------------------------------------------------------------------------------------------------
+int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, const OctoInputDef* defs) {
+    if (!ctx || !priors || !defs) return fail(OCTO_ERR_ARG, "null argument");
+    const int n_in = ctx->m.n_in;
+    if (D < 1 || D > OCTO_PARAM_MAX || n_in > OCTO_PARAM_MAX)
+        return fail(OCTO_ERR_ARG, "parameterised models support D, n_in <= " + std::to_string(OCTO_PARAM_MAX));
+    DevParam P;
+    memset(&P, 0, sizeof(P));
+    P.D = D; P.n_in = n_in;
+    for (int j = 0; j < D; ++j) {
+        const OctoPrior& pr = priors[j];
+        P.priors[j] = pr;
+        P.lognorm[j] = 0.0;
+        switch (pr.family) {
+            case OCTO_PRIOR_NORMAL: if (!(pr.p[1] > 0)) return fail(OCTO_ERR_ARG, "Normal: sigma must be > 0"); break;
+            case OCTO_PRIOR_UNIFORM: if (!(pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "Uniform: a < b required"); break;
+            case OCTO_PRIOR_LOGUNIFORM: if (!(0 < pr.p[0] && pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "LogUniform: 0 < a < b required"); break;
+            case OCTO_PRIOR_SINE: break;
+            case OCTO_PRIOR_TRUNCNORMAL: {
+                if (!(pr.p[1] > 0) || !(pr.p[2] < pr.p[3])) return fail(OCTO_ERR_ARG, "truncated Normal: sigma > 0, lower < upper required");
+                // log(Φ(β) - Φ(α)), on the side of the distribution that avoids cancellation
+                const double is2 = 0.7071067811865476, mu = pr.p[0], sg = pr.p[1];
+                const double a = std::isfinite(pr.p[2]) ? (pr.p[2] - mu) / sg : -INFINITY;
+                const double b = std::isfinite(pr.p[3]) ? (pr.p[3] - mu) / sg : INFINITY;
+                const double tp = a > 0 ? 0.5 * (std::erfc(a * is2) - std::erfc(b * is2))
+                                        : 0.5 * (std::erfc(-b * is2) - std::erfc(-a * is2));
+                P.lognorm[j] = std::log(tp);
+                break;
+            }
+            default: return fail(OCTO_ERR_ARG, "unknown prior family");
+        }
+    }
+    for (int k = 0; k < n_in; ++k) {
+        const OctoInputDef& d = defs[k];
+        P.defs[k] = d;
+        auto th_ok = [&](int j) { return j >= 0 && j < D; };
+        switch (d.op) {
+            case OCTO_IN_PARAM: if (!th_ok(d.a[0])) return fail(OCTO_ERR_ARG, "input definition: parameter index out of range"); break;
+            case OCTO_IN_CONST: break;
+            case OCTO_IN_CIRC: if (!th_ok(d.a[0]) || !th_ok(d.a[1])) return fail(OCTO_ERR_ARG, "UniformCircular: parameter index out of range"); break;
+            case OCTO_IN_TPERI:
+                for (int q = 0; q < 7; ++q)
+                    if (d.a[q] < 0 || d.a[q] >= k) return fail(OCTO_ERR_ARG, "θ_at_epoch_to_tperi: arguments must be earlier kernel inputs");
+                break;
+            default: return fail(OCTO_ERR_ARG, "unknown input definition");
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_param) CU(cudaMalloc((void**)&ctx->d_param, sizeof(DevParam)));
+    CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
+    ctx->param_D = D;
+    return OCTO_OK;
+}
+
+int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n) {
+    if (!ctx || n < 0) return -1;
+    return (int64_t)sizeof(double) * n * (2 * (int64_t)ctx->m.n_in + 1);
+}
+
+static int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
+                           double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st) {
+    const int n_in = ctx->m.n_in;
+    double* d_in = d_work;                      // [n x n_in]
+    double* d_ll = d_work + (size_t)n * n_in;   // [n]
+    double* d_gin = d_ll + n;                   // [n x n_in]
+    cudaError_t e = octo_param_forward(ctx->d_param, ctx->m, d_theta, n, ld, d_in, st);
+    if (e != cudaSuccess) return fail_cuda(e, "k_param_forward");
+    if (int rc = enqueue(ctx, w, d_g_t != nullptr, d_in, n, n, d_ll, d_g_t ? d_gin : nullptr, n, st)) return rc;
+    e = octo_param_backward(ctx->d_param, ctx->m, d_theta, n, ld, d_ll, d_gin, d_lp, d_g_t, ldg, st);
+    if (e != cudaSuccess) return fail_cuda(e, "k_param_backward");
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    return OCTO_OK;
+}
+
+int octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta, int64_t n, int64_t ld, double* d_lp, double* d_g_t,
+                             void* d_work, void* stream) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
+    if (n == 0) return OCTO_OK;
+    if (!d_theta || !d_lp || !d_work || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);
+    return logpost_enqueue(ctx, w, d_theta, n, ld, d_lp, d_g_t, ld, (double*)d_work, (cudaStream_t)stream);
+}
+
+int octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* lp, double* g_t) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
+    if (n == 0) return OCTO_OK;
+    if (!theta_t || !lp || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = lease(ctx);
+    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
+    const int D = ctx->param_D, n_in = ctx->m.n_in;
+    const size_t col = (size_t)n * sizeof(double);
+    int rc = OCTO_OK;
+    do {
+        if ((rc = ensure(&w->d_theta, &w->cap_theta, (size_t)n * D))) break;
+        if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * (D + 1)))) break;
+        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1)))) break;
+        if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * D, true))) break;
+        if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (D + 1), true))) break;
+        for (int k = 0; k < D; ++k) memcpy(w->h_in + (size_t)k * n, theta_t + (size_t)k * ld, col);
+        cudaError_t e = cudaMemcpyAsync(w->d_theta, w->h_in, col * D, cudaMemcpyHostToDevice, w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
+        if ((rc = logpost_enqueue(ctx, w, w->d_theta, n, n, w->d_post, g_t ? w->d_post + n : nullptr, n, w->d_in, w->stream))) break;
+        e = cudaMemcpyAsync(w->h_out, w->d_post, col * (g_t ? D + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
+        e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
+        memcpy(lp, w->h_out, col);
+        if (g_t) for (int k = 0; k < D; ++k) memcpy(g_t + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
+    } while (0);
+    release(ctx, w);
+    return rc;
+}
+
+int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
+    if (n == 0) return OCTO_OK;
+    if (!theta_t || !theta_nat || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = lease(ctx);
+    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
+    const int D = ctx->param_D;
+    int rc = OCTO_OK;
+    do {
+        const size_t col = (size_t)n * sizeof(double), pitch = (size_t)ld * sizeof(double);
+        if ((rc = ensure(&w->d_theta, &w->cap_theta, (size_t)n * D))) break;
+        if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * (D + 1)))) break;
+        cudaError_t e = cudaMemcpy2DAsync(w->d_theta, col, theta_t, pitch, col, D, cudaMemcpyHostToDevice, w->stream);
+        if (e == cudaSuccess) e = octo_param_invlink(ctx->d_param, w->d_theta, n, n, w->d_post, w->stream);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(theta_nat, pitch, w->d_post, col, col, D, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "invlink");
+    } while (0);
+    release(ctx, w);
+    return rc;
 }
 
 // page-locked host memory for `in` / `ll` / `g_in`: octo_logp[_grad] then copies without staging

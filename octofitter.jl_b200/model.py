@@ -58,12 +58,85 @@ def _check_table(table, name):
     return table
 
 
+# ---------------------------------------------------------------------------------------------------------
+# The `@variables` vocabulary of the reference that the device-side parameterisation understands:
+# priors (Distributions.jl families used by the reference's docs/tests), UniformCircular, constants, and the
+# derived variable tp = θ_at_epoch_to_tperi(θ, t_ref; M, e, a, i, ω, Ω).
+# ---------------------------------------------------------------------------------------------------------
+class Prior:
+    family, p = -1, (0.0, 0.0, 0.0, 0.0)
+
+
+class Normal(Prior):
+    def __init__(self, mu, sigma):
+        if not sigma > 0:
+            raise ValueError("Normal: the condition σ > 0 is not satisfied")
+        self.family, self.p = _abi.PRIOR_NORMAL, (float(mu), float(sigma), 0.0, 0.0)
+
+
+class Uniform(Prior):
+    def __init__(self, a, b):
+        if not a < b:
+            raise ValueError("Uniform: the condition a < b is not satisfied")
+        self.family, self.p = _abi.PRIOR_UNIFORM, (float(a), float(b), 0.0, 0.0)
+
+
+class LogUniform(Prior):
+    def __init__(self, a, b):
+        if not 0 < a < b:
+            raise ValueError("LogUniform: the condition 0 < a < b is not satisfied")
+        self.family, self.p = _abi.PRIOR_LOGUNIFORM, (float(a), float(b), 0.0, 0.0)
+
+
+class Sine(Prior):
+    """src/distributions.jl:15-40: pdf sin(x)/2 on (0, π)."""
+    def __init__(self):
+        self.family, self.p = _abi.PRIOR_SINE, (0.0, 0.0, 0.0, 0.0)
+
+
+def truncated(d, lower=None, upper=None):
+    """truncated(Normal(μ, σ), lower=, upper=) as used throughout the reference's docs."""
+    if not isinstance(d, Normal):
+        raise ValueError("only truncated(Normal(...)) is offloaded")
+    out = Prior()
+    out.family = _abi.PRIOR_TRUNCNORMAL
+    out.p = (d.p[0], d.p[1], -np.inf if lower is None else float(lower), np.inf if upper is None else float(upper))
+    if not out.p[2] < out.p[3]:
+        raise ValueError("truncated: lower must be below upper")
+    return out
+
+
+class UniformCircular:
+    """src/variables.jl:260-299: expands to `<v>x, <v>y ~ Normal(0, 1)`, `<v> = atan(<v>y, <v>x)/2π*domain` and a
+    UnitLengthPrior on the vector length."""
+    def __init__(self, domain=2 * np.pi):
+        self.domain = float(domain)
+
+
+class θ_at_epoch_to_tperi:
+    """Derived `tp = θ_at_epoch_to_tperi(θ, t_ref; M, e, a, i, ω, Ω)` (src/parameterizations.jl:6-69); `theta` names
+    the position-angle variable of the same planet, the orbital elements are taken from merge(system, planet)."""
+    def __init__(self, theta, theta_epoch):
+        self.theta, self.theta_epoch = _ALIASES.get(theta, theta), float(theta_epoch)
+
+
+theta_at_epoch_to_tperi = θ_at_epoch_to_tperi
+
+
+def _norm_variables(variables):
+    """list of names (raw natural-space inputs) or {name: prior | UniformCircular | number | θ_at_epoch_to_tperi}"""
+    if isinstance(variables, dict):
+        return tuple((_ALIASES.get(k, k), v) for k, v in variables.items())
+    return tuple((_ALIASES.get(v, v), None) for v in variables)
+
+
 class AbstractObs:
     kind = -1
     allowed_variables = ()
 
     def _set_variables(self, variables):
-        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        self.var_specs = _norm_variables(variables)
+        self.variables = tuple(n for n, _ in self.var_specs)
         for v in self.variables:
             if v not in self.allowed_variables:
                 raise ValueError(f"{type(self).__name__} '{self.name}': variable '{v}' is not offloadable "
@@ -174,7 +247,8 @@ class Planet:
             raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}}")
         self.name = str(name)
         self.basis = "Visual{KepOrbit}"
-        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        self.var_specs = _norm_variables(variables)
+        self.variables = tuple(n for n, _ in self.var_specs)
         self.observations = list(observations)
         for o in self.observations:
             if o.kind in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN):
@@ -186,7 +260,8 @@ class System:
 
     def __init__(self, *, name, variables, companions, observations=()):
         self.name = str(name)
-        self.variables = tuple(_ALIASES.get(v, v) for v in variables)
+        self.var_specs = _norm_variables(variables)
+        self.variables = tuple(n for n, _ in self.var_specs)
         self.planets = list(companions)
         self.observations = list(observations)
         names = [p.name for p in self.planets]
@@ -244,6 +319,7 @@ class ModelSpec:
                                    "mass": pcol.get("mass", -1)})
         self.input_names = tuple(names)
         self.n_in = len(names)
+        self._build_parameterization(system, col)
         blocks = []
         for ip, p in enumerate(system.planets):
             for o in p.observations:
@@ -257,6 +333,54 @@ class ModelSpec:
 
     def column(self, name):
         return self.input_names.index(name)
+
+    def _build_parameterization(self, system, syscol):
+        """θ_t layout (priors in the reference's order, UniformCircular expanded to x, y) and one OctoInputDef per
+        kernel input.  `self.priors is None` when the variables were given as bare names (raw-input mode)."""
+        scopes = [("", system.var_specs, None)]
+        for o in system.observations:
+            scopes.append((f"{_normalizename(o.name)}.", o.var_specs, None))
+        for p in system.planets:
+            scopes.append((f"{p.name}.", p.var_specs, p))
+            for o in p.observations:
+                scopes.append((f"{p.name}.{_normalizename(o.name)}.", o.var_specs, None))
+        if any(spec is None for _, specs, _ in scopes for _, spec in specs):
+            self.priors = self.defs = self.theta_names = None
+            self.D = None
+            return
+        priors, tnames, defs = [], [], [None] * self.n_in
+        incol = {n: k for k, n in enumerate(self.input_names)}
+        for prefix, specs, planet in scopes:
+            for name, spec in specs:
+                k = incol[prefix + name]
+                d = _abi.OctoInputDef()
+                if isinstance(spec, Prior):
+                    d.op, d.a[0] = _abi.IN_PARAM, len(priors)
+                    priors.append(spec); tnames.append(prefix + name)
+                elif isinstance(spec, UniformCircular):
+                    d.op, d.a[0], d.a[1], d.value = _abi.IN_CIRC, len(priors), len(priors) + 1, spec.domain
+                    priors += [Normal(0, 1), Normal(0, 1)]; tnames += [prefix + name + "x", prefix + name + "y"]
+                elif isinstance(spec, θ_at_epoch_to_tperi):
+                    if planet is None:
+                        raise OctoError("θ_at_epoch_to_tperi belongs in a planet's variables")
+                    look = lambda v: incol.get(prefix + v, incol.get(v))
+                    args = [look(spec.theta)] + [look(v) for v in ("M", "e", "a", "i", "ω", "Ω")]
+                    if any(a is None for a in args):
+                        raise OctoError(f"{prefix}{name}: θ_at_epoch_to_tperi needs θ, M, e, a, i, ω, Ω")
+                    if any(a >= k for a in args):
+                        raise OctoError(f"{prefix}{name}: define it after the variables it depends on")
+                    d.op, d.value = _abi.IN_TPERI, spec.theta_epoch
+                    for q, a in enumerate(args):
+                        d.a[q] = a
+                elif np.isscalar(spec):
+                    d.op, d.value = _abi.IN_CONST, float(spec)
+                else:
+                    raise OctoError(f"{prefix}{name}: unsupported variable definition {spec!r}")
+                defs[k] = d
+        self.priors = (_abi.OctoPrior * len(priors))(*[_abi.OctoPrior(p.family, 0, (C.c_double * 4)(*p.p)) for p in priors])
+        self.defs = (_abi.OctoInputDef * self.n_in)(*defs)
+        self.theta_names = tuple(tnames)
+        self.D = len(priors)
 
     @staticmethod
     def _block(o, ip, obs_cols):
@@ -287,6 +411,10 @@ class LogDensityModel:
         self._h = h
         self._pinned = []
         self.device = int(device)
+        if self.spec.priors is not None:        # device-side standard parameterisation (N1)
+            self.D = self.spec.D
+            self.theta_names = self.spec.theta_names
+            self._check(self._lib.octo_set_parameterization(self._h, self.spec.priors, self.spec.D, self.spec.defs))
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
@@ -367,15 +495,56 @@ class LogDensityModel:
         self._check(self._lib.octo_logp_grad(self._h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data))
         return (ll[0], g[0]) if single else (ll, g)
 
+    # -- sampler-facing surface when the model was given priors (src/logdensitymodel.jl:110-146, 169-177, 252-256)
+    def _as_theta(self, theta_t):
+        if self.spec.priors is None:
+            raise OctoError("this model was built from bare variable names: no priors/bijectors to evaluate "
+                            "(pass natural-space inputs to ln_like / ln_like_and_gradient)")
+        th = np.asarray(theta_t, dtype=np.float64)
+        single = th.ndim == 1
+        if single:
+            th = th[None, :]
+        if th.ndim != 2 or th.shape[1] != self.D:
+            raise ValueError(f"expected (n_chains, {self.D}) unconstrained parameters, got {th.shape}")
+        return np.asfortranarray(th), single
+
+    def ℓπcallback(self, theta_t):
+        """log-posterior of the unconstrained vector(s) θ_t: priors + bijector Jacobians + likelihood, on device."""
+        th, single = self._as_theta(theta_t)
+        n = th.shape[0]
+        lp = np.empty(n)
+        self._check(self._lib.octo_logpost_grad(self._h, th.ctypes.data, n, n, lp.ctypes.data, None))
+        return lp[0] if single else lp
+
+    def ℓπcallback_grad(self, theta_t):
+        th, single = self._as_theta(theta_t)
+        n = th.shape[0]
+        lp, g = np.empty(n), np.empty((n, self.D), order="F")
+        self._check(self._lib.octo_logpost_grad(self._h, th.ctypes.data, n, n, lp.ctypes.data, g.ctypes.data))
+        return (lp[0], g[0]) if single else (lp, g)
+
+    def invlink(self, theta_t):
+        th, single = self._as_theta(theta_t)
+        n = th.shape[0]
+        out = np.empty((n, self.D), order="F")
+        self._check(self._lib.octo_invlink(self._h, th.ctypes.data, n, n, out.ctypes.data))
+        return out[0] if single else out
+
+    logpost = ℓπcallback
+    logpost_and_gradient = ℓπcallback_grad
+
     # LogDensityProblems-style names (src/logdensitymodel.jl:252-256)
-    logdensity = ln_like
-    logdensity_and_gradient = ln_like_and_gradient
+    def logdensity(self, theta):
+        return self.ℓπcallback(theta) if self.spec.priors is not None else self.ln_like(theta)
+
+    def logdensity_and_gradient(self, theta):
+        return self.ℓπcallback_grad(theta) if self.spec.priors is not None else self.ln_like_and_gradient(theta)
 
     def dimension(self):
-        return self.n_in
+        return self.D
 
     def __call__(self, theta):           # Pigeons calls the model (ext/OctofitterPigeonsExt:10-12)
-        return self.ln_like(theta)
+        return self.logdensity(theta)
 
     def enqueue_device(self, d_in, n_chains, ld, d_ll, d_g, stream=0):
         """Asynchronous launch on device-resident buffers (raw pointers, cudaStream_t handle)."""

@@ -147,3 +147,105 @@ def ln_like_grad(consts, layout, blocks, x):
         h = max(abs(x[k]), mp.mpf(1)) * mp.mpf(10) ** (-18)
         g.append((f(x[k] + h) - f(x[k] - h)) / (2 * h))      # central difference, error O(h^2) ~ 1e-36
     return f0, g
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Standard parameterisation (priors + bijectors + derived inputs): independent high-precision restatement
+# of ℓπcallback for the prior families of octofitter.jl_b200.model.
+# priors: list of (family, p0, p1, p2, p3); defs: list of (op, [a0..a6], value) as in include/octo_b200.h
+# ---------------------------------------------------------------------------------------------------------
+def _bounds(fam, p):
+    if fam in (1, 2):
+        return mp.mpf(p[0]), mp.mpf(p[1])
+    if fam == 3:
+        eps = mp.mpf(2) ** -52
+        return eps, mp.mpf(float(mp.pi)) - eps       # π as the Float64 the reference uses
+    if fam == 4:
+        return (mp.mpf(p[2]) if p[2] != float("-inf") else None), (mp.mpf(p[3]) if p[3] != float("inf") else None)
+    return None, None
+
+
+def _invlink(fam, p, y):
+    lo, hi = _bounds(fam, p)
+    if lo is not None and hi is not None:
+        return lo + (hi - lo) / (1 + mp.e ** (-y))
+    if lo is not None:
+        return lo + mp.e ** y
+    if hi is not None:
+        return hi - mp.e ** y
+    return y
+
+
+def _logpdf_with_trans(fam, p, x):
+    lo, hi = _bounds(fam, p)
+    if fam == 0:
+        lp = mp.log(mp.npdf(x, p[0], p[1]))
+    elif fam == 1:
+        lp = -mp.log(mp.mpf(p[1]) - mp.mpf(p[0]))
+    elif fam == 2:
+        lp = -mp.log(x) - mp.log(mp.log(mp.mpf(p[1]) / mp.mpf(p[0])))
+    elif fam == 3:
+        lp = mp.log(mp.sin(x) / 2)
+    elif fam == 4:
+        a = mp.ncdf(lo, p[0], p[1]) if lo is not None else mp.mpf(0)
+        b = mp.ncdf(hi, p[0], p[1]) if hi is not None else mp.mpf(1)
+        lp = mp.log(mp.npdf(x, p[0], p[1])) - mp.log(b - a)
+    if lo is not None and hi is not None:
+        lp += mp.log((x - lo) * (hi - x) / (hi - lo))
+    elif lo is not None:
+        lp += mp.log(x - lo)
+    elif hi is not None:
+        lp += mp.log(hi - x)
+    return lp
+
+
+def _tperi(c, theta, t_ref, M, e, a, i, w, W):
+    """tp such that the position angle at t_ref is theta: solve the geometry independently of the reference's
+    matrix route — rotate the sky-plane direction back into the orbital plane."""
+    # sky-plane unit direction: (x, y) = (cosθ, sinθ) in the reference's (dec-like, ra-like) convention of
+    # [A F; B G] (x/r, y/r) = (cosθ, sinθ)
+    A = mp.cos(W) * mp.cos(w) - mp.sin(W) * mp.sin(w) * mp.cos(i)
+    B = mp.sin(W) * mp.cos(w) + mp.cos(W) * mp.sin(w) * mp.cos(i)
+    F = -mp.cos(W) * mp.sin(w) - mp.sin(W) * mp.cos(w) * mp.cos(i)
+    G = -mp.sin(W) * mp.sin(w) + mp.cos(W) * mp.cos(w) * mp.cos(i)
+    sol = mp.lu_solve(mp.matrix([[A, F], [B, G]]), mp.matrix([mp.cos(theta), mp.sin(theta)]))
+    nu = mp.atan2(sol[1], sol[0])
+    # eccentric anomaly from the true anomaly, then Kepler's equation forwards
+    E = 2 * mp.atan(mp.sqrt((1 - e) / (1 + e)) * mp.tan(nu / 2))
+    MA = E - e * mp.sin(E)
+    MA = MA % (2 * mp.pi)                      # the reference's atan(...)+π form lands in [0, 2π)
+    P_days = mp.sqrt(a ** 3 / M) * c["kepler_year_days"]
+    return t_ref - MA * P_days / (2 * mp.pi)
+
+
+def logpost(consts, layout, blocks, priors, defs, theta_t):
+    c = _consts(consts)
+    y = [mp.mpf(v) for v in theta_t]
+    th = [_invlink(f, p, yy) for (f, *p), yy in zip(priors, y)]
+    lp = sum(_logpdf_with_trans(f, p, x) for (f, *p), x in zip(priors, th))
+    inp, extra = [], mp.mpf(0)
+    for op, a, val in defs:
+        if op == 0:
+            inp.append(th[a[0]])
+        elif op == 1:
+            inp.append(mp.mpf(val))
+        elif op == 2:
+            x, yv = th[a[0]], th[a[1]]
+            inp.append(mp.atan2(yv, x) / (2 * mp.pi) * mp.mpf(val))
+            r = mp.sqrt(x * x + yv * yv)
+            extra += mp.log(mp.npdf(mp.log(r), 0, mp.mpf("0.1")) / r)          # LogNormal(0, 0.1) density at r
+        elif op == 3:
+            inp.append(_tperi(c, inp[a[0]], mp.mpf(val), *[inp[k] for k in a[1:7]]))
+    return lp + extra + ln_like(consts, layout, blocks, inp)
+
+
+def logpost_grad(consts, layout, blocks, priors, defs, theta_t):
+    x = [mp.mpf(v) for v in theta_t]
+    f0 = logpost(consts, layout, blocks, priors, defs, x)
+    g = []
+    for k in range(len(x)):
+        h = mp.mpf(10) ** (-18)
+        xp = list(x); xp[k] += h
+        xm = list(x); xm[k] -= h
+        g.append((logpost(consts, layout, blocks, priors, defs, xp) - logpost(consts, layout, blocks, priors, defs, xm)) / (2 * h))
+    return f0, g

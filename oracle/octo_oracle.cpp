@@ -1,6 +1,7 @@
 // octo_oracle.cpp — C entry points of the CPU oracle (see octo_oracle.hpp for scope and
 // parity status).  TEST INFRASTRUCTURE ONLY: never linked into libocto_b200.so.
 #include "octo_oracle.hpp"
+#include "octo_oracle_param.hpp"
 #include <cstring>
 #include <string>
 #include <algorithm>
@@ -101,6 +102,55 @@ int octo_oracle_logp_grad(const OctoConstants* c, const OctoLayout* L, const Oct
         else               eval_grad_chain<48>(*c, *L, blocks, n_blocks, in, ld, ch, ll, g, ld);
     });
     return OCTO_OK;
+}
+
+}  // extern "C"
+
+template <int N>
+static void eval_post_chain(const OctoConstants& c, const OctoLayout& L, const OctoObsBlock* blocks, int n_blocks,
+                            const OctoPrior* priors, int D, const OctoInputDef* defs, const double* th, int64_t ld,
+                            int64_t ch, double* lp, double* g) {
+    Dual<N> X[N];
+    for (int k = 0; k < D; ++k) X[k] = seed<N>(th[ch + k * ld], k);
+    Dual<N> r = logpost_chain<Dual<N>>(c, L, blocks, n_blocks, priors, D, defs, X);
+    lp[ch] = r.v;
+    for (int k = 0; k < D; ++k) g[ch + k * ld] = std::isfinite(r.v) ? r.d[k] : 0.0;
+}
+
+extern "C" {
+
+// ℓπcallback / ∇ℓπcallback of the standard parameterisation (theta_t: column-major [n x D])
+int octo_oracle_logpost(const OctoConstants* c, const OctoLayout* L, const OctoObsBlock* blocks, int n_blocks,
+                        const OctoPrior* priors, int D, const OctoInputDef* defs, const double* theta_t, int64_t n,
+                        int64_t ld, double* lp, double* g, int n_threads) {
+    if (int rc = validate(L, blocks, n_blocks)) return rc;
+    if (D < 1 || D > 48) { g_err = "oracle logpost supports 1 <= D <= 48"; return OCTO_ERR_ARG; }
+    parallel_chains(n, n_threads, [&](int64_t ch) {
+        if (!g) {
+            double X[48];
+            for (int k = 0; k < D; ++k) X[k] = theta_t[ch + k * ld];
+            lp[ch] = logpost_chain<double>(*c, *L, blocks, n_blocks, priors, D, defs, X);
+            return;
+        }
+        if (D <= 8)       eval_post_chain<8>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+        else if (D <= 12) eval_post_chain<12>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+        else if (D <= 16) eval_post_chain<16>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+        else if (D <= 24) eval_post_chain<24>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+        else if (D <= 32) eval_post_chain<32>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+        else              eval_post_chain<48>(*c, *L, blocks, n_blocks, priors, D, defs, theta_t, ld, ch, lp, g);
+    });
+    return OCTO_OK;
+}
+
+int octo_oracle_invlink(const OctoPrior* priors, int D, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {
+    for (int64_t ch = 0; ch < n; ++ch)
+        for (int k = 0; k < D; ++k) theta_nat[ch + k * ld] = prior_invlink<double>(priors[k], theta_t[ch + k * ld]);
+    return OCTO_OK;
+}
+
+double octo_oracle_tperi(const OctoConstants* c, double theta, double t_ref, double M, double e, double a, double i,
+                         double w, double W) {
+    return theta_at_epoch_to_tperi<double>(*c, theta, t_ref, M, e, a, i, w, W);
 }
 
 int octo_oracle_max_threads(void) {

@@ -17,7 +17,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("octo_oracle.cpp", "octo_oracle.hpp")] + \
+    srcs = [os.path.join(HERE, f) for f in ("octo_oracle.cpp", "octo_oracle.hpp", "octo_oracle_param.hpp")] + \
            [os.path.join(HERE, "..", "include", "octo_b200.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
@@ -58,6 +58,33 @@ def orbit_radecrv(consts, a, e, i, w, W, tp, M, plx, t):
     lib().octo_oracle_orbit_radecrv(C.addressof(consts), a, e, i, w, W, tp, M, plx, t.ctypes.data, len(t),
                                     ra.ctypes.data, dec.ctypes.data, rv.ctypes.data)
     return ra, dec, rv
+
+
+def logpost(spec, consts, theta_t, grad=True, threads=1):
+    """ℓπ(θ_t) (and ∇) of a parameterised ModelSpec on the CPU oracle."""
+    L = lib()
+    L.octo_oracle_logpost.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    th = np.asfortranarray(np.atleast_2d(np.asarray(theta_t, dtype=np.float64)))
+    n, D = th.shape
+    assert D == spec.D
+    lp = np.empty(n)
+    g = np.empty((n, D), order="F") if grad else None
+    rc = L.octo_oracle_logpost(C.addressof(consts), C.addressof(spec.packed.layout), spec.packed.blocks, spec.packed.n_blocks,
+                               spec.priors, D, spec.defs, th.ctypes.data, n, n, lp.ctypes.data,
+                               g.ctypes.data if grad else None, threads)
+    if rc:
+        raise RuntimeError(L.octo_oracle_last_error().decode())
+    return (lp, g) if grad else lp
+
+
+def invlink(spec, theta_t):
+    L = lib()
+    L.octo_oracle_invlink.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    th = np.asfortranarray(np.atleast_2d(np.asarray(theta_t, dtype=np.float64)))
+    out = np.empty_like(th, order="F")
+    L.octo_oracle_invlink(spec.priors, spec.D, th.ctypes.data, th.shape[0], th.shape[0], out.ctypes.data)
+    return out
 
 
 class Oracle:

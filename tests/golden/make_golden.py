@@ -162,8 +162,56 @@ def build_cases():
     return cases
 
 
+def build_post_cases():
+    """Parameterised models (priors + UniformCircular + θ_at_epoch_to_tperi): the reference's 11-D test model
+    (test/integration/sampling.jl:29-71, test/integration-tests.jl:17-40) and an RV+astrometry model."""
+    cases = {}
+    astrom = octo.PlanetRelAstromObs(octo.Table(epoch=FIX_EPOCH, ra=FIX_RA, dec=FIX_DEC, σ_ra=[10.] * 8,
+                                                σ_dec=[10.] * 8, cor=[0.] * 8), name="relastrom")
+    b = octo.Planet(name="b", observations=[astrom], variables={
+        "a": octo.Uniform(0, 100), "e": octo.Uniform(0.0, 0.99), "i": octo.Sine(), "ω": octo.UniformCircular(),
+        "Ω": octo.UniformCircular(), "θ": octo.UniformCircular(), "tp": octo.θ_at_epoch_to_tperi("θ", 50000)})
+    sy = octo.System(name="TestSys", companions=[b], variables={
+        "M": octo.truncated(octo.Normal(1.2, 0.1), lower=0.1), "plx": octo.truncated(octo.Normal(50.0, 0.02), lower=0.1)})
+    # θ_t chosen so that the natural parameters sit near the fixture's generating orbit
+    cases["post_fixture8"] = (sy, [np.log(1.2 - 0.1) + 0.01, np.log(50.0 - 0.1) + 1e-4, -1.99, -2.0, -0.5,
+                                   0.8, 0.6, 0.95, 0.28, -0.99, -0.13])
+    rng = np.random.default_rng(99)
+    el = dict(a=1.0, e=0.7, i=np.pi / 4, W=0.1, w=np.pi / 4, M=1.0, plx=100.0, tp=58829.0 - 40)
+    ep_a = [58849., 58852., 58858., 58890.]
+    st = mp_states(el, ep_a)
+    astrom = octo.PlanetRelAstromObs(octo.Table(epoch=ep_a, ra=noisy([s[0] for s in st], 1.0, rng),
+                                                dec=noisy([s[1] for s in st], 1.0, rng), σ_ra=[1.0] * 4, σ_dec=[1.0] * 4),
+                                     name="sim", variables={"jitter": octo.LogUniform(0.01, 10.0)})
+    ep_rv = list(58849.0 + np.sort(rng.uniform(0, 365, 10)))
+    mu = 30.0 * CONSTS["mjup2msol"] / el["M"]
+    rv_true = [-mu * float(s[2]) for s in mp_states(el, ep_rv)]
+    rv = octo.StarAbsoluteRVObs(octo.Table(epoch=ep_rv, rv=noisy(np.array(rv_true) + 150.0, 5.0, rng), σ_rv=[5.0] * 10),
+                                name="HARPS", variables={"offset": octo.Normal(150, 100), "jitter": octo.LogUniform(0.1, 100.0)})
+    pl = octo.Planet(name="b", observations=[astrom], variables={
+        "a": octo.LogUniform(0.1, 10), "e": octo.Uniform(0, 0.999), "i": octo.Sine(), "ω": octo.UniformCircular(),
+        "Ω": octo.UniformCircular(np.pi), "tp": octo.Uniform(58000, 59000), "mass": octo.truncated(octo.Normal(30, 20), lower=0, upper=200)})
+    sy2 = octo.System(name="rvastrom", companions=[pl], observations=[rv],
+                      variables={"M": octo.truncated(octo.Normal(1.0, 0.05), lower=0.1), "plx": 100.0})
+    cases["post_rv_astrom"] = (sy2, [0.02 + np.log(0.9), 148.0, 0.1, -0.1, 0.8, -0.5, 0.7, 0.72, 0.99, 0.2, 1.32, -1.73, 0.05])
+    return cases
+
+
 def main():
     fixture_pin()
+    for name, (system, th) in build_post_cases().items():
+        spec = octo.ModelSpec(system)
+        assert len(th) == spec.D, (name, len(th), spec.D, spec.theta_names)
+        blocks = [{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in b.items()} for b in spec.block_dicts]
+        priors = [[int(p.family)] + [float(v) for v in p.p] for p in spec.priors]
+        defs = [[int(d.op), [int(v) for v in d.a], float(d.value)] for d in spec.defs]
+        lp, g = mpr.logpost_grad(CONSTS, spec.layout_dict, blocks, priors, defs, th)
+        out = {"constants": CONSTS, "input_names": list(spec.input_names), "theta_names": list(spec.theta_names),
+               "layout": spec.layout_dict, "blocks": blocks, "priors": priors, "defs": defs, "theta_t": [float(v) for v in th],
+               "lp": float(lp), "grad": [float(v) for v in g], "lp_str": mp.nstr(lp, 30),
+               "how": "oracle/mp_reference.py logpost_grad, mp.dps=60, central differences h=1e-18"}
+        json.dump(out, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
+        print(name, "lp =", mp.nstr(lp, 20), "D =", spec.D)
     for name, (system, xd) in build_cases().items():
         spec = octo.ModelSpec(system)
         x = [xd[n] for n in spec.input_names]

@@ -1,0 +1,92 @@
+"""GPU tests of the device-side standard parameterisation (K0 forward/backward around K1): libocto_b200's
+octo_logpost_grad against the oracle and the mpmath goldens."""
+import numpy as np
+import pytest
+
+import octofitter_jl_b200 as octo
+from helpers import grad_err, load_post, post_cases, reference_test_system, rel_err
+
+pytestmark = pytest.mark.gpu
+LOGP_RTOL, GRAD_RTOL = 1e-10, 1e-8
+
+
+def _model_from_golden(d, spec, consts):
+    import ctypes as C
+    lib = octo.load_library()
+    h = C.c_void_p()
+    assert lib.octo_create(C.byref(consts), C.byref(spec.packed.layout), spec.packed.blocks, spec.packed.n_blocks, 0,
+                           C.byref(h)) == 0, lib.octo_last_error()
+    assert lib.octo_set_parameterization(h, spec.priors, spec.D, spec.defs) == 0, lib.octo_last_error()
+    return lib, h
+
+
+def _logpost(lib, h, D, th, grad=True):
+    th = np.asfortranarray(np.atleast_2d(np.asarray(th, dtype=np.float64)))
+    n = th.shape[0]
+    lp = np.empty(n); g = np.empty((n, D), order="F") if grad else None
+    rc = lib.octo_logpost_grad(h, th.ctypes.data, n, n, lp.ctypes.data, g.ctypes.data if grad else None)
+    assert rc == 0, lib.octo_last_error()
+    return lp, g
+
+
+@pytest.mark.parametrize("name", post_cases())
+def test_cuda_logpost_matches_golden_and_oracle(oracle_lib, name):
+    d, spec, consts = load_post(name)
+    lib, h = _model_from_golden(d, spec, consts)
+    lp, g = _logpost(lib, h, spec.D, d["theta_t"])
+    assert rel_err(lp[0], d["lp"]) < LOGP_RTOL and grad_err(g, d["grad"]).max() < GRAD_RTOL
+    rng = np.random.default_rng(8)
+    th = np.array(d["theta_t"])[None, :] + 0.05 * rng.standard_normal((67, spec.D))
+    lp, g = _logpost(lib, h, spec.D, th)
+    lpv, _ = _logpost(lib, h, spec.D, th, grad=False)
+    lp_o, g_o = oracle_lib.logpost(spec, consts, th, threads=4)
+    assert rel_err(lp, lp_o).max() < LOGP_RTOL and rel_err(lpv, lp_o).max() < LOGP_RTOL
+    assert grad_err(g, g_o).max() < GRAD_RTOL
+    lib.octo_destroy(h)
+
+
+def test_reference_test_model_on_device(oracle_lib):
+    """The reference's 11-D test model through the host mirror: ℓπcallback / ∇ℓπcallback / invlink."""
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    assert model.D == 11 and model.dimension() == 11
+    rng = np.random.default_rng(2)
+    th = rng.normal(0, 0.8, (129, 11))
+    th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(129)       # keep plx near its tight prior
+    lp, g = model.ℓπcallback_grad(th)
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    assert rel_err(lp, lp_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+    assert rel_err(model.ℓπcallback(th), lp_o).max() < LOGP_RTOL
+    assert np.allclose(model.invlink(th), oracle_lib.invlink(spec, th), rtol=1e-14, atol=0)
+    lp1, g1 = model.logdensity_and_gradient(th[0])
+    assert rel_err(lp1, lp_o[0]) < LOGP_RTOL and model(th[0]) == pytest.approx(lp1, rel=1e-12)
+    # `@test model.ℓπcallback(start) > -1000` style sanity at a sensible point (test/integration/sampling.jl:76)
+    good = np.array([np.log(1.1), np.log(49.9), -1.99, -2.0, -0.5, 0.8, 0.6, 0.95, 0.28, -0.99, -0.13])
+    assert np.isfinite(model.ℓπcallback(good))
+    model.close()
+
+
+def test_device_logpost_invalid_and_healed(oracle_lib):
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    th = np.zeros((4, spec.D)); th[:, 5:] = 0.7; th[:, 4] = -0.5      # (i = π/2 exactly makes tp ill-conditioned)
+    th[1, 3] = np.nan
+    th[2, 3] = 800.0                       # e clamps to its bound: healed prior, finite but hugely negative
+    th[3, 9] = np.inf
+    lp, g = model.ℓπcallback_grad(th)
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th)
+    assert np.isfinite(lp[0]) and lp[1] == -np.inf and lp[3] == -np.inf and np.all(g[1] == 0) and np.all(g[3] == 0)
+    assert lp[2] == lp_o[2] and lp[2] < -1e300
+    assert rel_err(lp[0], lp_o[0]) < LOGP_RTOL and grad_err(g[:1], g_o[:1]).max() < GRAD_RTOL
+    model.close()
+
+
+def test_parameterisation_required():
+    import workloads
+    spec, x = workloads.config("C1")
+    model = octo.LogDensityModel(spec)
+    with pytest.raises(octo.OctoError, match="bare variable names"):
+        model.ℓπcallback(np.zeros(3))
+    lp = np.empty(1)
+    assert model._lib.octo_logpost_grad(model._h, x.ctypes.data, 1, 1, lp.ctypes.data, None) == 4   # OCTO_ERR_STATE
+    model.close()
