@@ -249,6 +249,16 @@ def main():
     for _ in range(args.steps):
         model.ln_like_and_gradient(x)
     t_e2e_pageable = time.perf_counter() - t0
+    # the same tables with the reference's standard priors attached: full ℓπ(θ_t), ∇ℓπ(θ_t) on the device
+    # (K0 forward + K1 + K0 backward), host θ_t in, host (lp, ∇) out
+    spec_p, th_p = workloads.one_planet_with_priors(100, 100, n, seed=2 + 1000 * rank)
+    model_p = octo.LogDensityModel(spec_p, device=local)
+    for _ in range(5):
+        model_p.ℓπcallback_grad(th_p)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model_p.ℓπcallback_grad(th_p)
+    t_post = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if world > 1:
@@ -289,7 +299,10 @@ def main():
                     "ms_per_step_pageable_host_arrays": t_e2e_pageable / args.steps * 1e3,
                     "api": "LogDensityModel.ln_like_and_gradient(pinned host ndarray, out=pinned) -> C ABI octo_logp_grad: "
                            "H2D + kernel + D2H + stream sync per step"},
-            "gpu_launches": int(launches),
+            "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "
+                                "θ_at_epoch_to_tperi on device), same tables, D = %d; 3 launches per step" % spec_p.D,
+                        "value": pairs_step * args.steps / t_post, "unit": "evals/s", "ms_per_step": t_post / args.steps * 1e3},
+        "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
@@ -299,6 +312,7 @@ def main():
         if args.sweep:
             sweep(octo, workloads, torch, peak, local)
     model.close()
+    model_p.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -533,6 +533,66 @@ class LogDensityModel:
     logpost = ℓπcallback
     logpost_and_gradient = ℓπcallback_grad
 
+    # -- batched value-only consumers -------------------------------------------------
+    def sample_priors(self, rng, n=1):
+        """n draws from the priors, natural space, shape (n, D) (model.sample_priors, src/variables.jl:1385-1440)."""
+        if self.spec.priors is None:
+            raise OctoError("sample_priors needs a model built with priors")
+        out = np.empty((n, self.D))
+        for j, pr in enumerate(self.spec.priors):
+            p = pr.p
+            if pr.family == _abi.PRIOR_NORMAL:
+                out[:, j] = rng.normal(p[0], p[1], n)
+            elif pr.family == _abi.PRIOR_UNIFORM:
+                out[:, j] = rng.uniform(p[0], p[1], n)
+            elif pr.family == _abi.PRIOR_LOGUNIFORM:
+                out[:, j] = np.exp(rng.uniform(np.log(p[0]), np.log(p[1]), n))
+            elif pr.family == _abi.PRIOR_SINE:
+                out[:, j] = np.arccos(1.0 - 2.0 * rng.uniform(0, 1, n))          # quantile, src/distributions.jl:40
+            else:                                                                # truncated normal: inverse-cdf
+                from scipy.stats import truncnorm
+                a, b = (p[2] - p[0]) / p[1], (p[3] - p[0]) / p[1]
+                out[:, j] = truncnorm.rvs(a, b, loc=p[0], scale=p[1], size=n, random_state=rng)
+        return out
+
+    def link(self, theta_nat):
+        """Natural -> unconstrained parameters (Bijectors.link per prior; inverse of `invlink`)."""
+        x = np.atleast_2d(np.asarray(theta_nat, dtype=np.float64))
+        y = np.empty_like(x)
+        for j, pr in enumerate(self.spec.priors):
+            lo, hi = -np.inf, np.inf
+            if pr.family in (_abi.PRIOR_UNIFORM, _abi.PRIOR_LOGUNIFORM):
+                lo, hi = pr.p[0], pr.p[1]
+            elif pr.family == _abi.PRIOR_SINE:
+                lo, hi = np.finfo(float).eps, np.pi - np.finfo(float).eps
+            elif pr.family == _abi.PRIOR_TRUNCNORMAL:
+                lo, hi = pr.p[2], pr.p[3]
+            if np.isfinite(lo) and np.isfinite(hi):
+                u = (x[:, j] - lo) / (hi - lo)
+                y[:, j] = np.log(u) - np.log1p(-u)
+            elif np.isfinite(lo):
+                y[:, j] = np.log(x[:, j] - lo)
+            elif np.isfinite(hi):
+                y[:, j] = np.log(hi - x[:, j])
+            else:
+                y[:, j] = x[:, j]
+        return y if np.ndim(theta_nat) == 2 else y[0]
+
+    def guess_starting_position(self, rng, N=500_000, batch=65536):
+        """Sample IID from the prior N times and return the highest-posterior draw and its log-posterior
+        (src/initialization.jl:14-66) — the N ℓπ evaluations run as value-only device batches (K1v)."""
+        best, best_lp = None, -np.inf
+        done = 0
+        while done < N:
+            m = min(batch, N - done)
+            params = self.sample_priors(rng, m)
+            lp = self.ℓπcallback(self.link(params))
+            k = int(np.argmax(lp))
+            if lp[k] > best_lp:
+                best, best_lp = params[k].copy(), float(lp[k])
+            done += m
+        return best, best_lp
+
     # LogDensityProblems-style names (src/logdensitymodel.jl:252-256)
     def logdensity(self, theta):
         return self.ℓπcallback(theta) if self.spec.priors is not None else self.ln_like(theta)

@@ -175,3 +175,51 @@ def many_planets(n_planets, n_chains, seed, n_ep=40):
     system = octo.System(name="many", variables=["M", "plx"], companions=planets, observations=[s1, s2])
     spec = octo.ModelSpec(system)
     return spec, _chains(spec, truth, n_chains, rng, rel=0.01)
+
+
+def one_planet_with_priors(n_astrom, n_rv, n_chains, seed):
+    """The C2 tables with the reference's standard priors attached (device-side parameterisation, N1):
+    returns (spec, θ_t [n_chains x D]) with θ_t scattered around the truth in unconstrained space."""
+    raw_spec, _ = one_planet(n_astrom, n_rv, 1, seed)
+    sys0 = raw_spec.system
+    planet0 = sys0.planets[0]
+    astrom = [octo.PlanetRelAstromObs(o.table, name=o.name) for o in planet0.observations]
+    rvs = [octo.StarAbsoluteRVObs({"epoch": o.table["epoch"], "rv": o.table["rv"], "σ_rv": o.table["σ_rv"]}, name=o.name,
+                                  variables={"offset": octo.Normal(150, 100), "jitter": octo.LogUniform(0.1, 100.0)})
+           for o in sys0.observations]
+    pv = {"a": octo.LogUniform(1, 100), "e": octo.Uniform(0, 0.99), "i": octo.Sine(), "ω": octo.UniformCircular(),
+          "Ω": octo.UniformCircular(), "θ": octo.UniformCircular(), "tp": octo.θ_at_epoch_to_tperi("θ", 50000.0)}
+    if rvs:
+        pv["mass"] = octo.LogUniform(0.1, 100)
+    b = octo.Planet(name="b", variables=pv, observations=astrom)
+    system = octo.System(name="synthetic", companions=[b], observations=rvs, variables={
+        "M": octo.truncated(octo.Normal(1.2, 0.1), lower=0.1), "plx": octo.truncated(octo.Normal(50.0, 0.02), lower=0.1)})
+    spec = octo.ModelSpec(system)
+    rng = np.random.default_rng(seed + 77)
+    # truth in natural space -> θ_t by hand (logit / log-shift / identity), then scatter
+    ra, dec, _, _ = _state(TRUTH_B, [50000.0])
+    theta_pa = float(np.arctan2(ra[0], dec[0]))
+    nat = {"M": 1.2, "plx": 50.0, "rv.offset": 150.0, "rv.jitter": 3.0, "b.a": 10.0, "b.e": 0.3, "b.i": 1.0, "b.mass": 10.0}
+    ang = {"b.ω": 0.5, "b.Ω": 2.0, "b.θ": theta_pa}
+    th0 = np.zeros(spec.D)
+    for j, (name, pr) in enumerate(zip(spec.theta_names, spec.priors)):
+        if name[:-1] in ang and name[-1] in "xy":
+            th0[j] = np.cos(ang[name[:-1]]) if name[-1] == "x" else np.sin(ang[name[:-1]])
+            continue
+        x = nat[name]
+        lo, hi = -np.inf, np.inf
+        if pr.family in (1, 2):
+            lo, hi = pr.p[0], pr.p[1]
+        elif pr.family == 3:
+            lo, hi = 0.0, np.pi
+        elif pr.family == 4:
+            lo, hi = pr.p[2], pr.p[3]
+        if np.isfinite(lo) and np.isfinite(hi):
+            u = (x - lo) / (hi - lo); th0[j] = np.log(u / (1 - u))
+        elif np.isfinite(lo):
+            th0[j] = np.log(x - lo)
+        else:
+            th0[j] = x
+    th = th0[None, :] + 0.01 * rng.standard_normal((n_chains, spec.D)) * np.maximum(1.0, 0.0)
+    th[0] = th0
+    return spec, np.asfortranarray(th)
