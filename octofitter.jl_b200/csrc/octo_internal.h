@@ -81,10 +81,11 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
 size_t octo_smem_bytes(const DevModel& m, int warps);
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);
-cudaError_t octo_param_forward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
-                               double* d_in, cudaStream_t st);
-cudaError_t octo_param_backward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
-                                const double* d_ll, const double* d_g_in, double* d_lp, double* d_g_t, int64_t ldg,
-                                cudaStream_t st);
+cudaError_t octo_param_init(int D, int n_in);
+cudaError_t octo_param_forward(const DevParam* d_param, int D, const DevModel& m, const double* d_theta, int64_t n,
+                               int64_t ld, double* d_in, double* d_save, cudaStream_t st);
+cudaError_t octo_param_backward(const DevParam* d_param, int D, const DevModel& m, int64_t n, const double* d_in,
+                                const double* d_save, const double* d_ll, const double* d_g_in, double* d_lp,
+                                double* d_g_t, int64_t ldg, cudaStream_t st);
 cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,
                                cudaStream_t st);

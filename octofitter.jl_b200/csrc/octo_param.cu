@@ -1,7 +1,7 @@
 // octo_param.cu — K0: the standard parameterisation around the hot path, on the device.
 //
 //   forward  (k_param_forward):  θ_t -> invlink -> natural parameters -> derived kernel inputs `in`
-//                                + Σ logpdf_with_trans + UnitLengthPrior terms            (one thread per chain)
+//                                + Σ logpdf_with_trans + UnitLengthPrior terms            (8 lanes per chain)
 //   K1 / K1v (octo_kernels.cu):  ll(in), ∂ll/∂in
 //   backward (k_param_backward): ∂ll/∂in -> ∂/∂θ (reverse through the input definitions; θ_at_epoch_to_tperi by
 //                                forward-mode duals) -> + prior gradients -> × d invlink/dθ_t; lp = prior + ll
@@ -11,7 +11,7 @@
 // θ_at_epoch_to_tperi src/parameterizations.jl:6-69); ln_prior_transformed with the "healing" of a non-finite
 // term (src/variables.jl:1205-1369); then ln_like (which contains the UnitLengthPrior terms, :301-323).
 // Bijectors/Distributions formulas: SURVEY.md Appendix B.  All per-chain work; performance is irrelevant next
-// to K1 (two tiny launches), correctness is checked against oracle/octo_oracle_param.hpp.
+// to K1 (two small launches, 8 lanes per chain), correctness is checked against oracle/octo_oracle_param.hpp.
 #include <cfloat>
 #include <math_constants.h>
 
@@ -19,7 +19,6 @@
 
 namespace {
 
-constexpr int MAXD = OCTO_PARAM_MAX, MAXIN = OCTO_PARAM_MAX;
 constexpr double kTwoPi = 6.283185307179586477, kPi = 3.14159265358979323846, kHalfLog2Pi = 0.91893853320467274178;
 
 struct PriorEval { double x, dxdy, L, dLdx; };
@@ -73,36 +72,30 @@ __device__ PriorEval prior_eval(const OctoPrior& pr, double lognorm, double y) {
     return r;
 }
 
-// minimal forward-mode dual with 7 partials, for θ_at_epoch_to_tperi only
-struct D7 { double v, d[7]; };
-__device__ D7 mk(double v, int k) { D7 r; r.v = v; for (int q = 0; q < 7; ++q) r.d[q] = (q == k) ? 1.0 : 0.0; return r; }
-__device__ D7 un(const D7& a, double f, double df) { D7 r; r.v = f; for (int q = 0; q < 7; ++q) r.d[q] = df * a.d[q]; return r; }
-__device__ D7 operator+(const D7& a, const D7& b) { D7 r; r.v = a.v + b.v; for (int q = 0; q < 7; ++q) r.d[q] = a.d[q] + b.d[q]; return r; }
-__device__ D7 operator-(const D7& a, const D7& b) { D7 r; r.v = a.v - b.v; for (int q = 0; q < 7; ++q) r.d[q] = a.d[q] - b.d[q]; return r; }
-__device__ D7 operator-(const D7& a) { D7 r; r.v = -a.v; for (int q = 0; q < 7; ++q) r.d[q] = -a.d[q]; return r; }
-__device__ D7 operator*(const D7& a, const D7& b) { D7 r; r.v = a.v * b.v; for (int q = 0; q < 7; ++q) r.d[q] = a.d[q] * b.v + a.v * b.d[q]; return r; }
-__device__ D7 operator/(const D7& a, const D7& b) { D7 r; r.v = a.v / b.v; for (int q = 0; q < 7; ++q) r.d[q] = (a.d[q] - r.v * b.d[q]) / b.v; return r; }
-__device__ D7 operator+(const D7& a, double b) { D7 r = a; r.v += b; return r; }
-__device__ D7 operator-(double a, const D7& b) { D7 r = -b; r.v += a; return r; }
-__device__ D7 operator*(const D7& a, double b) { D7 r; r.v = a.v * b; for (int q = 0; q < 7; ++q) r.d[q] = a.d[q] * b; return r; }
-__device__ D7 dsin(const D7& a) { return un(a, sin(a.v), cos(a.v)); }
-__device__ D7 dcos(const D7& a) { return un(a, cos(a.v), -sin(a.v)); }
-__device__ D7 dsqrt(const D7& a) { const double s = sqrt(a.v); return un(a, s, 0.5 / s); }
-__device__ D7 datan2(const D7& y, const D7& x) {
-    D7 r; r.v = atan2(y.v, x.v); const double h = x.v * x.v + y.v * y.v;
-    for (int q = 0; q < 7; ++q) r.d[q] = (x.v * y.d[q] - y.v * x.d[q]) / h;
-    return r;
+// minimal forward-mode dual with ONE partial: θ_at_epoch_to_tperi's 7 partial derivatives are computed by 7
+// lanes, each seeding a different argument
+struct D1 { double v, d; };
+__device__ __forceinline__ D1 mk(double v, bool seed) { return D1{v, seed ? 1.0 : 0.0}; }
+__device__ __forceinline__ D1 operator+(const D1& a, const D1& b) { return D1{a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ D1 operator-(const D1& a, const D1& b) { return D1{a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ D1 operator-(const D1& a) { return D1{-a.v, -a.d}; }
+__device__ __forceinline__ D1 operator*(const D1& a, const D1& b) { return D1{a.v * b.v, a.d * b.v + a.v * b.d}; }
+__device__ __forceinline__ D1 operator/(const D1& a, const D1& b) { const double q = a.v / b.v; return D1{q, (a.d - q * b.d) / b.v}; }
+__device__ __forceinline__ D1 operator+(const D1& a, double b) { return D1{a.v + b, a.d}; }
+__device__ __forceinline__ D1 operator-(double a, const D1& b) { return D1{a - b.v, -b.d}; }
+__device__ __forceinline__ D1 operator*(const D1& a, double b) { return D1{a.v * b, a.d * b}; }
+__device__ __forceinline__ double psin(double a) { return sin(a); }
+__device__ __forceinline__ double pcos(double a) { return cos(a); }
+__device__ __forceinline__ double psqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double patan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ D1 psin(const D1& a) { double s, c; sincos(a.v, &s, &c); return D1{s, c * a.d}; }
+__device__ __forceinline__ D1 pcos(const D1& a) { double s, c; sincos(a.v, &s, &c); return D1{c, -s * a.d}; }
+__device__ __forceinline__ D1 psqrt(const D1& a) { const double s = sqrt(a.v); return D1{s, 0.5 / s * a.d}; }
+__device__ __forceinline__ D1 patan2(const D1& y, const D1& x) {
+    return D1{atan2(y.v, x.v), (x.v * y.d - y.v * x.d) / (x.v * x.v + y.v * y.v)};
 }
-__device__ double psin(double a) { return sin(a); }
-__device__ double pcos(double a) { return cos(a); }
-__device__ double psqrt(double a) { return sqrt(a); }
-__device__ double patan2(double y, double x) { return atan2(y, x); }
-__device__ D7 psin(const D7& a) { return dsin(a); }
-__device__ D7 pcos(const D7& a) { return dcos(a); }
-__device__ D7 psqrt(const D7& a) { return dsqrt(a); }
-__device__ D7 patan2(const D7& y, const D7& x) { return datan2(y, x); }
 
-// src/parameterizations.jl:6-69, Campbell branch.  T = double (forward) or D7 (backward).
+// src/parameterizations.jl:6-69, Campbell branch.  T = double (forward) or D1 (backward, one partial per lane).
 template <class T>
 __device__ T tperi(const OctoConstants& c, const T& theta, double t_ref, const T& M, const T& e, const T& a, const T& i,
                    const T& w, const T& W) {
@@ -121,102 +114,150 @@ __device__ T tperi(const OctoConstants& c, const T& theta, double t_ref, const T
     return t_ref - MA * period_yrs * (c.year2day / kTwoPi);
 }
 
-struct ChainState {
-    double th[MAXD], dxdy[MAXD], dLdx[MAXD], in[MAXIN];
-    double lp_prior, extra;
-    bool finite_in, healed, valid;
-};
+// ---------------------------------------------------------------------------------------------
+// SUB lanes cooperate on one chain: prior evaluations and the 7 tperi partials run lane-parallel, the few
+// order-dependent steps (sums, reverse pass) run on the chain's lane 0 in a fixed order.  Per-chain scratch
+// lives in shared memory.  What backward needs from forward is saved in the caller's workspace.
+// ---------------------------------------------------------------------------------------------
+constexpr int SUB = 8, CHAINS = 16;                  // 128 threads per CTA
+struct ChainSmem { double *th, *dxdy, *dLdx, *L, *in, *aux, *gth; };
+__device__ __forceinline__ ChainSmem chain_smem(double* base, int local_chain, int D, int n_in) {
+    const int Dp = D < SUB ? SUB : D;                  // every array has at least SUB slots (scratch use)
+    double* p = base + (size_t)local_chain * (5 * Dp + 2 * n_in);
+    ChainSmem s; s.th = p; s.dxdy = p + Dp; s.dLdx = p + 2 * Dp; s.L = p + 3 * Dp; s.gth = p + 4 * Dp;
+    s.in = p + 5 * Dp; s.aux = p + 5 * Dp + n_in;
+    return s;
+}
 
-// shared by forward and backward: everything up to the kernel inputs
-__device__ void chain_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c, int64_t ld,
-                              ChainState& S) {
-    S.finite_in = true; S.healed = false; S.lp_prior = 0.0; S.extra = 0.0;
-    for (int j = 0; j < P.D; ++j) {
+// save layout per chain: [th(D) | dxdy(D) | dLdx(D) | lp_prior | extra | flags], column-major over chains
+__global__ void __launch_bounds__(SUB * CHAINS)
+k_param_forward(const DevParam* __restrict__ Pp, const __grid_constant__ DevModel m, const double* __restrict__ theta_t,
+                int64_t n, int64_t ld, double* __restrict__ in_out, double* __restrict__ save) {
+    extern __shared__ double sm[];
+    const DevParam& P = *Pp;
+    const int D = P.D, n_in = P.n_in;
+    const int lc = threadIdx.x / SUB, s = threadIdx.x % SUB;
+    const int64_t c_raw = (int64_t)blockIdx.x * CHAINS + lc;
+    const bool active = c_raw < n;
+    const int64_t c = active ? c_raw : n - 1;
+    ChainSmem S = chain_smem(sm, lc, D, n_in);
+    // phase 1: invlink + logpdf_with_trans, lane-parallel over parameters
+    for (int j = s; j < D; j += SUB) {
         const double y = theta_t[c + (int64_t)j * ld];
-        if (!isfinite(y)) S.finite_in = false;
-        const PriorEval r = prior_eval(P.priors[j], P.lognorm[j], isfinite(y) ? y : 0.0);
+        const bool fin = isfinite(y);
+        const PriorEval r = prior_eval(P.priors[j], P.lognorm[j], fin ? y : 0.0);
         S.th[j] = r.x; S.dxdy[j] = r.dxdy; S.dLdx[j] = r.dLdx;
-        if (!S.healed) {
-            if (!isfinite(r.L)) { S.healed = true; S.lp_prior = -DBL_MAX; }   // nextfloat(typemin(Float64)), then return
-            else S.lp_prior += r.L;
-        }
+        S.L[j] = fin ? r.L : CUDART_NAN;                         // NaN marks a non-finite θ_t entry
     }
-    for (int k = 0; k < P.n_in; ++k) {
+    __syncthreads();
+    // phase 2a: derived inputs that depend on parameters only (arr2nt), lane-parallel
+    for (int k = s; k < n_in; k += SUB) {
         const OctoInputDef& d = P.defs[k];
-        double v = 0.0;
-        switch (d.op) {
-            case OCTO_IN_PARAM: v = S.th[d.a[0]]; break;
-            case OCTO_IN_CONST: v = d.value; break;
-            case OCTO_IN_CIRC: {
-                const double x = S.th[d.a[0]], y = S.th[d.a[1]];
-                v = atan2(y, x) / kTwoPi * d.value;
-                const double lr = log(sqrt(x * x + y * y));
-                S.extra += -lr - log(0.1) - kHalfLog2Pi - lr * lr / (2.0 * 0.1 * 0.1);
-                break;
-            }
-            case OCTO_IN_TPERI:
-                v = tperi<double>(m.c, S.in[d.a[0]], d.value, S.in[d.a[1]], S.in[d.a[2]], S.in[d.a[3]], S.in[d.a[4]],
-                                  S.in[d.a[5]], S.in[d.a[6]]);
-                break;
+        double v = 0.0, ext = 0.0;
+        if (d.op == OCTO_IN_PARAM) v = S.th[d.a[0]];
+        else if (d.op == OCTO_IN_CONST) v = d.value;
+        else if (d.op == OCTO_IN_CIRC) {
+            const double x = S.th[d.a[0]], y = S.th[d.a[1]];
+            v = atan2(y, x) / kTwoPi * d.value;
+            const double lr = log(sqrt(x * x + y * y));
+            ext = -lr - log(0.1) - kHalfLog2Pi - lr * lr / (2.0 * 0.1 * 0.1);      // UnitLengthPrior
         }
-        S.in[k] = v;
+        S.in[k] = v; S.aux[k] = ext;
     }
-    S.valid = S.finite_in;
-    for (int k = 0; k < P.n_in; ++k) if (!isfinite(S.in[k])) S.valid = false;
+    __syncthreads();
+    // phase 2b + 3: the chain's lane 0 — θ_at_epoch_to_tperi in definition order, ordered sums, validity
+    if (s == 0) {
+        for (int k = 0; k < n_in; ++k) {
+            const OctoInputDef& d = P.defs[k];
+            if (d.op == OCTO_IN_TPERI)
+                S.in[k] = tperi<double>(m.c, S.in[d.a[0]], d.value, S.in[d.a[1]], S.in[d.a[2]], S.in[d.a[3]], S.in[d.a[4]],
+                                        S.in[d.a[5]], S.in[d.a[6]]);
+        }
+        bool finite_in = true, healed = false, valid = true;
+        double lp = 0.0, extra = 0.0;
+        for (int j = 0; j < D; ++j) {
+            const double L = S.L[j];
+            if (isnan(L) && !isfinite(theta_t[c + (int64_t)j * ld])) { finite_in = false; continue; }
+            if (!healed) { if (!isfinite(L)) { healed = true; lp = -DBL_MAX; } else lp += L; }   // variables.jl:1229-1236
+        }
+        for (int k = 0; k < n_in; ++k) { extra += S.aux[k]; if (!isfinite(S.in[k])) valid = false; }
+        valid = valid && finite_in;
+        if (active) {
+            double* sv = save + c;
+            sv[(int64_t)(3 * D) * n] = lp; sv[(int64_t)(3 * D + 1) * n] = extra;
+            sv[(int64_t)(3 * D + 2) * n] = (double)((finite_in ? 1 : 0) | (healed ? 2 : 0) | (valid ? 4 : 0));
+        }
+        S.aux[0] = valid ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (active) {
+        const bool valid = S.aux[0] != 0.0;
+        // an invalid chain gets NaN inputs: K1 then returns -Inf / zero gradient for it
+        for (int k = s; k < n_in; k += SUB) in_out[c + (int64_t)k * n] = valid ? S.in[k] : CUDART_NAN;
+        for (int j = s; j < D; j += SUB) {
+            save[c + (int64_t)j * n] = S.th[j]; save[c + (int64_t)(D + j) * n] = S.dxdy[j];
+            save[c + (int64_t)(2 * D + j) * n] = S.dLdx[j];
+        }
+    }
 }
 
-__global__ void k_param_forward(const DevParam* __restrict__ Pp, const __grid_constant__ DevModel m,
-                                const double* __restrict__ theta_t, int64_t n, int64_t ld, double* __restrict__ in_out) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+__global__ void __launch_bounds__(SUB * CHAINS)
+k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevModel m, int64_t n,
+                 const double* __restrict__ in_vals, const double* __restrict__ save, const double* __restrict__ ll,
+                 const double* __restrict__ g_in, double* __restrict__ lp_out, double* __restrict__ g_t, int64_t ldg) {
+    extern __shared__ double sm[];
     const DevParam& P = *Pp;
-    ChainState S;
-    chain_forward(P, m, theta_t, c, ld, S);
-    // an invalid chain gets NaN inputs: K1 then returns -Inf / zero gradient for it
-    for (int k = 0; k < P.n_in; ++k) in_out[c + (int64_t)k * n] = S.valid ? S.in[k] : CUDART_NAN;
-}
-
-__global__ void k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevModel m,
-                                 const double* __restrict__ theta_t, int64_t n, int64_t ld, const double* __restrict__ ll,
-                                 const double* __restrict__ g_in, double* __restrict__ lp_out, double* __restrict__ g_t,
-                                 int64_t ldg) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    const DevParam& P = *Pp;
-    ChainState S;
-    chain_forward(P, m, theta_t, c, ld, S);
+    const int D = P.D, n_in = P.n_in;
+    const int lc = threadIdx.x / SUB, s = threadIdx.x % SUB;
+    const int64_t c_raw = (int64_t)blockIdx.x * CHAINS + lc;
+    const bool active = c_raw < n;
+    const int64_t c = active ? c_raw : n - 1;
+    ChainSmem S = chain_smem(sm, lc, D, n_in);
+    const double lp_prior = save[c + (int64_t)(3 * D) * n], extra = save[c + (int64_t)(3 * D + 1) * n];
+    const int flags = (int)save[c + (int64_t)(3 * D + 2) * n];
+    const bool finite_in = flags & 1, healed = flags & 2, valid = flags & 4;
     const double llc = ll[c];
-    const bool ok = S.finite_in && S.valid && isfinite(llc);
-    lp_out[c] = !S.finite_in ? -CUDART_INF : ((S.valid && isfinite(llc)) ? S.lp_prior + (S.extra + llc) : -CUDART_INF);
+    const bool ok = valid && isfinite(llc);
+    if (active && s == 0) lp_out[c] = !finite_in ? -CUDART_INF : (ok ? lp_prior + (extra + llc) : -CUDART_INF);
     if (!g_t) return;
-    if (!ok) { for (int j = 0; j < P.D; ++j) g_t[c + (int64_t)j * ldg] = 0.0; return; }
-    double gin[MAXIN], gth[MAXD];
-    for (int k = 0; k < P.n_in; ++k) gin[k] = g_in[c + (int64_t)k * n];
-    for (int j = 0; j < P.D; ++j) gth[j] = S.healed ? 0.0 : S.dLdx[j];        // a healed prior is a constant
-    for (int k = P.n_in - 1; k >= 0; --k) {
+    for (int j = s; j < D; j += SUB) {
+        S.th[j] = save[c + (int64_t)j * n]; S.dxdy[j] = save[c + (int64_t)(D + j) * n];
+        S.gth[j] = healed ? 0.0 : save[c + (int64_t)(2 * D + j) * n];          // a healed prior is a constant
+    }
+    for (int k = s; k < n_in; k += SUB) { S.in[k] = ok ? in_vals[c + (int64_t)k * n] : 1.0; S.aux[k] = ok ? g_in[c + (int64_t)k * n] : 0.0; }
+    __syncthreads();
+    // θ_at_epoch_to_tperi inputs, last definition first: lanes 0..6 each produce one partial derivative
+    for (int k = n_in - 1; k >= 0; --k) {
         const OctoInputDef& d = P.defs[k];
-        const double gk = gin[k];
-        switch (d.op) {
-            case OCTO_IN_PARAM: gth[d.a[0]] += gk; break;
-            case OCTO_IN_CIRC: {
+        if (d.op != OCTO_IN_TPERI) continue;
+        double part = 0.0;
+        if (s < 7) {
+            D1 a[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) a[q] = mk(S.in[d.a[q]], q == s);
+            part = tperi<D1>(m.c, a[0], d.value, a[1], a[2], a[3], a[4], a[5], a[6]).d;
+        }
+        S.L[s] = part;                                      // L is free scratch here (D >= 1; SUB slots needed)
+        __syncthreads();
+        if (s == 0) { const double gk = S.aux[k]; for (int q = 0; q < 7; ++q) S.aux[d.a[q]] += gk * S.L[q]; }
+        __syncthreads();
+    }
+    // parameters and UniformCircular inputs: ordered accumulation on lane 0
+    if (s == 0) {
+        for (int k = n_in - 1; k >= 0; --k) {
+            const OctoInputDef& d = P.defs[k];
+            const double gk = S.aux[k];
+            if (d.op == OCTO_IN_PARAM) S.gth[d.a[0]] += gk;
+            else if (d.op == OCTO_IN_CIRC) {
                 const double x = S.th[d.a[0]], y = S.th[d.a[1]], r2 = x * x + y * y, sc = d.value / kTwoPi;
-                // angle, plus the UnitLengthPrior term  f(lr) = -lr - lr^2/(2*0.01), lr = ½ log r2
-                const double lr = 0.5 * log(r2), dfdlr = -1.0 - lr / (0.1 * 0.1);
-                gth[d.a[0]] += gk * sc * (-y / r2) + dfdlr * x / r2;
-                gth[d.a[1]] += gk * sc * (x / r2) + dfdlr * y / r2;
-                break;
+                const double lr = 0.5 * log(r2), dfdlr = -1.0 - lr / (0.1 * 0.1);   // angle + UnitLengthPrior
+                S.gth[d.a[0]] += gk * sc * (-y / r2) + dfdlr * x / r2;
+                S.gth[d.a[1]] += gk * sc * (x / r2) + dfdlr * y / r2;
             }
-            case OCTO_IN_TPERI: {
-                D7 a[7];
-                for (int q = 0; q < 7; ++q) a[q] = mk(S.in[d.a[q]], q);
-                const D7 t = tperi<D7>(m.c, a[0], d.value, a[1], a[2], a[3], a[4], a[5], a[6]);
-                for (int q = 0; q < 7; ++q) gin[d.a[q]] += gk * t.d[q];
-                break;
-            }
-            default: break;
         }
     }
-    for (int j = 0; j < P.D; ++j) g_t[c + (int64_t)j * ldg] = gth[j] * S.dxdy[j];
+    __syncthreads();
+    if (active) for (int j = s; j < D; j += SUB) g_t[c + (int64_t)j * ldg] = ok ? S.gth[j] * S.dxdy[j] : 0.0;
 }
 
 __global__ void k_invlink(const DevParam* __restrict__ Pp, const double* __restrict__ theta_t, int64_t n, int64_t ld,
@@ -229,15 +270,26 @@ __global__ void k_invlink(const DevParam* __restrict__ Pp, const double* __restr
 
 }  // namespace
 
-cudaError_t octo_param_forward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
-                               double* d_in, cudaStream_t st) {
-    k_param_forward<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_param, m, d_theta, n, ld, d_in);
+static size_t param_smem(int D, int n_in) { return (size_t)CHAINS * (5 * (size_t)(D < SUB ? SUB : D) + 2 * n_in) * sizeof(double); }
+
+// opt both kernels in to the dynamic shared memory a (D, n_in) model needs (57 KB at the 64/64 limit)
+cudaError_t octo_param_init(int D, int n_in) {
+    cudaError_t e = cudaFuncSetAttribute(k_param_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)param_smem(D, n_in));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_param_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)param_smem(D, n_in));
+}
+
+cudaError_t octo_param_forward(const DevParam* d_param, int D, const DevModel& m, const double* d_theta, int64_t n,
+                               int64_t ld, double* d_in, double* d_save, cudaStream_t st) {
+    k_param_forward<<<(unsigned)((n + CHAINS - 1) / CHAINS), SUB * CHAINS, param_smem(D, m.n_in), st>>>(
+        d_param, m, d_theta, n, ld, d_in, d_save);
     return cudaGetLastError();
 }
-cudaError_t octo_param_backward(const DevParam* d_param, const DevModel& m, const double* d_theta, int64_t n, int64_t ld,
-                                const double* d_ll, const double* d_g_in, double* d_lp, double* d_g_t, int64_t ldg,
-                                cudaStream_t st) {
-    k_param_backward<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_param, m, d_theta, n, ld, d_ll, d_g_in, d_lp, d_g_t, ldg);
+cudaError_t octo_param_backward(const DevParam* d_param, int D, const DevModel& m, int64_t n, const double* d_in,
+                                const double* d_save, const double* d_ll, const double* d_g_in, double* d_lp,
+                                double* d_g_t, int64_t ldg, cudaStream_t st) {
+    k_param_backward<<<(unsigned)((n + CHAINS - 1) / CHAINS), SUB * CHAINS, param_smem(D, m.n_in), st>>>(
+        d_param, m, n, d_in, d_save, d_ll, d_g_in, d_lp, d_g_t, ldg);
     return cudaGetLastError();
 }
 cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,

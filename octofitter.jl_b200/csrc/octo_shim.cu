@@ -487,6 +487,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
         }
     }
     CU(cudaSetDevice(ctx->device));
+    CU(octo_param_init(D, n_in));
     if (!ctx->d_param) CU(cudaMalloc((void**)&ctx->d_param, sizeof(DevParam)));
     CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
     ctx->param_D = D;
@@ -495,7 +496,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
 
 int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n) {
     if (!ctx || n < 0) return -1;
-    return (int64_t)sizeof(double) * n * (2 * (int64_t)ctx->m.n_in + 1);
+    return (int64_t)sizeof(double) * n * (2 * (int64_t)ctx->m.n_in + 1 + 3 * (int64_t)ctx->param_D + 3);
 }
 
 static int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
@@ -504,10 +505,11 @@ static int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, in
     double* d_in = d_work;                      // [n x n_in]
     double* d_ll = d_work + (size_t)n * n_in;   // [n]
     double* d_gin = d_ll + n;                   // [n x n_in]
-    cudaError_t e = octo_param_forward(ctx->d_param, ctx->m, d_theta, n, ld, d_in, st);
+    double* d_save = d_gin + (size_t)n * n_in;  // [n x (3D + 3)]
+    cudaError_t e = octo_param_forward(ctx->d_param, ctx->param_D, ctx->m, d_theta, n, ld, d_in, d_save, st);
     if (e != cudaSuccess) return fail_cuda(e, "k_param_forward");
     if (int rc = enqueue(ctx, w, d_g_t != nullptr, d_in, n, n, d_ll, d_g_t ? d_gin : nullptr, n, st)) return rc;
-    e = octo_param_backward(ctx->d_param, ctx->m, d_theta, n, ld, d_ll, d_gin, d_lp, d_g_t, ldg, st);
+    e = octo_param_backward(ctx->d_param, ctx->param_D, ctx->m, n, d_in, d_save, d_ll, d_gin, d_lp, d_g_t, ldg, st);
     if (e != cudaSuccess) return fail_cuda(e, "k_param_backward");
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     return OCTO_OK;
@@ -538,7 +540,7 @@ int octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld
     do {
         if ((rc = ensure(&w->d_theta, &w->cap_theta, (size_t)n * D))) break;
         if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * (D + 1)))) break;
-        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1)))) break;
+        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * D + 3)))) break;
         if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * D, true))) break;
         if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (D + 1), true))) break;
         for (int k = 0; k < D; ++k) memcpy(w->h_in + (size_t)k * n, theta_t + (size_t)k * ld, col);
