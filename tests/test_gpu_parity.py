@@ -256,3 +256,45 @@ def test_device_kepler_edge_cases(oracle_lib):
     ok = e[idx] < 0.99
     assert np.abs(np.sin(Eo[ok]) - s[idx][ok]).max() < 2e-14
     assert np.abs(np.cos(Eo[ok]) - c[idx][ok]).max() < 2e-14
+
+
+def test_create_destroy_cycles_and_workspace_growth():
+    """Contexts are independent and reclaim everything; a workspace grows with the batch and shrinking is a no-op."""
+    import torch
+    spec, x = workloads.config("C2")
+    free0 = torch.cuda.mem_get_info()[0]
+    ref = None
+    for it in range(30):
+        model = octo.LogDensityModel(spec)
+        for n in (1, 700, 33, 1024):
+            ll, g = model.ln_like_and_gradient(x[:n])
+            if n == 1024:
+                if ref is None:
+                    ref = (ll.copy(), g.copy())
+                assert np.array_equal(ll, ref[0]) and np.array_equal(g, ref[1])
+        model.close()
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20        # nothing substantial left behind
+
+
+def test_device_buffer_entry_point_matches_host_entry_point():
+    import torch
+    spec, x = workloads.config("C3")
+    model = octo.LogDensityModel(spec)
+    n, n_in = x.shape
+    ll_h, g_h = model.ln_like_and_gradient(x)
+    d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    d_ll = torch.empty(n, dtype=torch.float64, device="cuda")
+    d_g = torch.empty((n_in, n), dtype=torch.float64, device="cuda")
+    for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(stream):
+            d_ll.zero_(); d_g.zero_()
+            model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), d_g.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        assert np.array_equal(d_ll.cpu().numpy(), ll_h) and np.array_equal(d_g.cpu().numpy().T, g_h)
+    # value-only through the device entry point
+    d_ll.zero_()
+    model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.max(np.abs(d_ll.cpu().numpy() - ll_h) / np.abs(ll_h)) < 1e-13
+    model.close()
