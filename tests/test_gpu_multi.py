@@ -48,7 +48,7 @@ def test_sharded_chains_and_nccl_swap_round():
     import torch.multiprocessing as mp
     import octofitter_jl_b200 as octo
     import workloads
-    world = 2
+    world = 8 if _ngpu() >= 8 else (4 if _ngpu() >= 4 else 2)     # C4 proper on an 8-GPU box: 64 replicas, 8 per GPU
     spec, x = workloads.config("C4")
     R = x.shape[0]
     model = octo.LogDensityModel(spec, device=0)
