@@ -41,6 +41,7 @@ struct DevBlock {
     int32_t slot_jitter, slot_platescale, slot_northangle, slot_offset;   // accumulator slots (or -1)
     int32_t slot_margin;                      // first of the margin accumulators (kind 3) or -1
     int32_t pad;
+    double wgt, cum;                          // relative cost of one epoch of this table; Σ n*wgt of the tables before it
 };
 
 struct DevModel {
@@ -48,6 +49,7 @@ struct DevModel {
     double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
     double two_pi_over_kyd;  // 2π / kepler_year_days: mean motion [rad/day] = this * sqrt(M/a) / a
     double c2a_per_plx;      // rad2as*1e3 / (1000*pc2au): mas per AU per mas of parallax
+    double wtot;             // Σ n*wgt over all tables: warps split this, not the raw epoch count
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
     int64_t n_epochs;

@@ -686,8 +686,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     __shared__ int s_last;
 
 #ifdef OCTO_TIMING
-    long long tm[6]; int tmi = 0;
-#define OCTO_TICK() do { if (threadIdx.x == 0) tm[tmi++] = clock64(); } while (0)
+    long long tm[10]; int tmi = 0;
+#define OCTO_TICK() do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tm[tmi++] = (long long)t_; } } while (0)
 #else
 #define OCTO_TICK() do {} while (0)
 #endif
@@ -735,11 +735,13 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         // ---- this warp's contiguous range of the concatenated epoch list
         const int64_t c = chain_of(lane);
         const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
-        const int k_lo = (int)(m.n_epochs * u / U), k_hi = (int)(m.n_epochs * (u + 1) / U);
+        // contiguous range of the COST-weighted epoch list (an RV+jitter epoch costs ~1.8 lean astrometry epochs)
+        const double w_lo = m.wtot * (double)u / (double)U, w_hi = (u + 1 == U) ? 2.0 * m.wtot + 1.0 : m.wtot * (double)(u + 1) / (double)U;
 #pragma unroll 1
         for (int b = 0; b < m.n_blocks; ++b) {
             const DevBlock& B = m.blocks[b];
-            const int k0 = max(k_lo, B.start), k1 = min(k_hi, B.start + B.n);
+            const int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
+            const int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
             if (k0 >= k1) continue;
             run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, in, c, ld, lane);
         }
@@ -766,12 +768,19 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
         __threadfence();
         __syncthreads();
+        OCTO_TICK();
         if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(&tickets[blockIdx.x], 1u);
             s_last = (prev == gridDim.y - 1);
             if (s_last) tickets[blockIdx.x] = 0;      // ready for the next launch on this workspace
         }
         __syncthreads();
+        OCTO_TICK();
+#ifdef OCTO_TIMING
+        if (!s_last && threadIdx.x == 0 && blockIdx.x == 0)
+            printf("cta(0,%d) ns: start %lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld\n", blockIdx.y,
+                   tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4]);
+#endif
         if (!s_last) return;
         __threadfence();
         const double* base = partial + (int64_t)blockIdx.x * gridDim.y * n_acc * 32;
@@ -814,10 +823,11 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         }
     }
 #ifdef OCTO_TIMING
-    if (threadIdx.x == 0 && blockIdx.x < 2) {
-        tm[tmi++] = clock64();
-        printf("cta(%d,%d) sm-clk: prologue %lld  segments %lld  cta-reduce %lld  splits %lld  epilogue %lld  total %lld\n",
-               blockIdx.x, blockIdx.y, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[5] - tm[0]);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        OCTO_TICK();
+        printf("cta(0,%d) LAST ns: start %lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld reads +%lld epilogue +%lld end %lld\n",
+               blockIdx.y, tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4],
+               tm[6] - tm[5], tm[7] - tm[6], tm[7] % 100000000);
     }
 #endif
 }

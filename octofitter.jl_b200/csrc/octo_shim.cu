@@ -348,6 +348,21 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         if (E > 0x7fffffff) return bad("too many epochs");
     }
     m.n_epochs = E; m.n_acc = n_acc;
+    // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
+    double cum = 0.0;
+    for (int b = 0; b < n_blocks; ++b) {
+        DevBlock& D = m.blocks[b];
+        const bool astrom = D.kind <= OCTO_KIND_ASTROM_PASEP;
+        const bool lean = D.kind == OCTO_KIND_ASTROM_RADEC && !D.jit && D.idx_platescale < 0 && D.idx_northangle < 0;
+        double w = astrom ? (lean ? 1.0 : 2.5) : (D.kind == OCTO_KIND_RV_STAR_MARGIN ? 1.9 : (D.jit ? 1.8 : 1.1));
+        int solves = 1;
+        if (D.kind == OCTO_KIND_RV_STAR_ABS || D.kind == OCTO_KIND_RV_STAR_MARGIN) solves = L->n_planets;
+        else for (int p = 0; p < L->n_planets; ++p) if (p != D.planet && L->idx_mass[p] >= 0) ++solves;   // upper bound
+        D.wgt = w + 0.8 * (solves - 1);
+        D.cum = cum;
+        cum += D.wgt * D.n;
+    }
+    m.wtot = cum;
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
     // + padding: the kernels prefetch one lane-stride (<= 32*8 records) past the record they read

@@ -1,4 +1,4 @@
-"""Phase timing of the C2 launch (needs a library built with -DOCTO_TIMING; prints SM-clock deltas per phase)."""
+"""Phase timeline of the C2 launch (needs a library built with -DOCTO_TIMING; prints %globaltimer stamps [ns])."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,11 @@ import octofitter_jl_b200 as octo
 import workloads
 spec, x = workloads.config("C2")
 model = octo.LogDensityModel(spec)
-for _ in range(2):
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for it in range(4):
+    if it < 2:
+        flush.zero_()
+    print('flushed' if it < 2 else 'warm L2')
     model.ln_like_and_gradient(x)
     torch.cuda.synchronize()
     print("----")
