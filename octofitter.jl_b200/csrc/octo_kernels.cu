@@ -784,24 +784,30 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         if (!s_last) return;
         __threadfence();
         const double* base = partial + (int64_t)blockIdx.x * gridDim.y * n_acc * 32;
+        // every load of this thread (two accumulator cells x up to 16 splits) is issued before the first add: one
+        // L2 round trip instead of four; additions stay in split order => same bits every run
+        const int64_t stride = (int64_t)n_acc * 32;
+        const int ncell = n_acc * 32, gy = (int)gridDim.y;
 #pragma unroll 1
-        for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
-            // loads batched 8 deep (latency overlapped); additions in split order => same bits every run
-            const int64_t stride = (int64_t)n_acc * 32;
-            const double* q = base + idx;
-            double v = 0.0;
-            int y = 0;
+        for (int idx0 = threadIdx.x; idx0 < ncell; idx0 += 2 * W * 32) {
+            const int idx1 = idx0 + W * 32;
+            const bool has1 = idx1 < ncell;
+            const double* q0 = base + idx0;
+            const double* q1 = base + (has1 ? idx1 : idx0);
+            double v0 = 0.0, v1 = 0.0;
 #pragma unroll 1
-            for (; y + 8 <= (int)gridDim.y; y += 8) {
-                double t[8];
+            for (int y0 = 0; y0 < gy; y0 += 16) {
+                double t0[16], t1[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = __ldcg(q + (y + j) * stride);
+                for (int j = 0; j < 16; ++j) {
+                    const int y = min(y0 + j, gy - 1);
+                    t0[j] = __ldcg(q0 + y * stride); t1[j] = __ldcg(q1 + y * stride);
+                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v += t[j];
+                for (int j = 0; j < 16; ++j) if (y0 + j < gy) { v0 += t0[j]; v1 += t1[j]; }
             }
-#pragma unroll 1
-            for (; y < (int)gridDim.y; ++y) v += __ldcg(q + y * stride);
-            s_red[idx] = v;
+            s_red[idx0] = v0;
+            if (has1) s_red[idx1] = v1;
         }
         __syncthreads();
     }
