@@ -52,6 +52,7 @@ struct DevModel {
     double wtot;             // Σ n*wgt over all tables: warps split this, not the raw epoch count
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
+    int32_t has_margin, pad0;    // any marginalised-RV table (its epilogue fold needs an extra barrier)
     int64_t n_epochs;
     int32_t idx_plx[OCTO_MAX_PLANETS], idx_a[OCTO_MAX_PLANETS], idx_e[OCTO_MAX_PLANETS], idx_i[OCTO_MAX_PLANETS],
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],

@@ -565,90 +565,106 @@ __device__ __noinline__ void prologue_products(double* sc, int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue: raw epoch sums R[slot] -> ll and d ll / d inputs for one chain (one lane).
+// Epilogue: raw epoch sums R[slot] -> ll and d ll / d inputs, one lane per chain, FOUR WARPS IN PARALLEL.
+// This code runs once per chain group (in the last CTA to arrive) and is instruction-fetch bound when cold
+// (measured 5.3k cycles cold vs 2.5k warm as a single function); splitting it into independent parts on
+// different warps overlaps the fetches and the dependency chains.  Every part adds into its own gradient
+// array gp[part][n_in][32]; the parts are summed in a fixed order afterwards (bit-reproducible).
+//   part 0: table terms — ll, observation-variable slots
+//   part 1: astrometry chain rule (scaled Thiele-Innes -> a, plx, e, i, ω, Ω)
+//   part 2: radial-velocity chain rule (Pc, Ps -> K, ω, e, a, M, i)
+//   part 3: mean motion / tp / reflex factor (S0, S1, e, mu -> tp, a, M, e, mass)
+// Marginalised-RV tables fold their V-sums into the planet sums first (epilogue_margin, own barrier).
 // ---------------------------------------------------------------------------------------------
+constexpr int EPI_PARTS = 4;
+
 template <bool GRAD>
-__device__ __noinline__ void chain_epilogue(const DevModel& m, const double* s_const, double* R, double* s_g,
-                               const double* __restrict__ in, int64_t c, int64_t ld, int lane, double& ll_out) {
-    double ll = R[0 * 32 + lane] + m.const_ll;
-    // s_g was zeroed in the prologue.  marginalised RV tables first: they fold their V-sums into the planet sums
+__device__ __noinline__ void epilogue_margin(const DevModel& m, double* R, double* gp0, const double* __restrict__ in,
+                                             int64_t c, int64_t ld, int lane) {
+    double ll = 0.0;
 #pragma unroll 1
     for (int b = 0; b < m.n_blocks; ++b) {
         const DevBlock& B = m.blocks[b];
-        if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-            const int s0 = B.slot_margin;
-            const double A = R[(s0 + MA_A) * 32 + lane], S1 = R[(s0 + MA_S1) * 32 + lane];
-            const double C = R[(s0 + MA_C) * 32 + lane], LG = R[(s0 + MA_LG) * 32 + lane];
-            const double rbar = S1 / A;
-            ll += -LG - C + S1 * rbar - log(A);            // rv-absolute-margin.jl:171-181 with B = -2 S1
-            if (GRAD) {
-                const double R2 = R[(s0 + MA_R2) * 32 + lane], R1 = R[(s0 + MA_R1) * 32 + lane], Q = R[(s0 + MA_Q) * 32 + lane];
-                const double jit = in[c + (int64_t)B.idx_jitter * ld];
-                s_g[B.idx_jitter * 32 + lane] += 2.0 * jit * (-A + R2 - 2.0 * rbar * R1 + rbar * rbar * Q + Q / A);
+        if (B.kind != OCTO_KIND_RV_STAR_MARGIN) continue;
+        const int s0 = B.slot_margin;
+        const double A = R[(s0 + MA_A) * 32 + lane], S1 = R[(s0 + MA_S1) * 32 + lane];
+        const double C = R[(s0 + MA_C) * 32 + lane], LG = R[(s0 + MA_LG) * 32 + lane];
+        const double rbar = S1 / A;
+        ll += -LG - C + S1 * rbar - log(A);            // rv-absolute-margin.jl:171-181 with B = -2 S1
+        if (GRAD) {
+            const double R2 = R[(s0 + MA_R2) * 32 + lane], R1 = R[(s0 + MA_R1) * 32 + lane], Q = R[(s0 + MA_Q) * 32 + lane];
+            const double jit = in[c + (int64_t)B.idx_jitter * ld];
+            gp0[B.idx_jitter * 32 + lane] += 2.0 * jit * (-A + R2 - 2.0 * rbar * R1 + rbar * rbar * Q + Q / A);
 #pragma unroll 1
-                for (int p = 0; p < m.n_planets; ++p) {
-                    const int v0 = s0 + MA_COUNT + p * MV_COUNT;
-                    const double k2 = -2.0 * rbar;
-                    R[slot_planet(p, PA_Pc) * 32 + lane] += k2 * R[(v0 + MV_Pc) * 32 + lane];
-                    R[slot_planet(p, PA_Ps) * 32 + lane] += k2 * R[(v0 + MV_Ps) * 32 + lane];
-                    R[slot_planet(p, PA_e) * 32 + lane] += k2 * R[(v0 + MV_e) * 32 + lane];
-                    R[slot_planet(p, PA_S0) * 32 + lane] += k2 * R[(v0 + MV_S0) * 32 + lane];
-                    R[slot_planet(p, PA_S1) * 32 + lane] += k2 * R[(v0 + MV_S1) * 32 + lane];
-                    R[slot_planet(p, PA_mu) * 32 + lane] += k2 * R[(v0 + MV_mu) * 32 + lane];
-                }
+            for (int p = 0; p < m.n_planets; ++p) {
+                const int v0 = s0 + MA_COUNT + p * MV_COUNT;
+                const double k2 = -2.0 * rbar;
+                R[slot_planet(p, PA_Pc) * 32 + lane] += k2 * R[(v0 + MV_Pc) * 32 + lane];
+                R[slot_planet(p, PA_Ps) * 32 + lane] += k2 * R[(v0 + MV_Ps) * 32 + lane];
+                R[slot_planet(p, PA_e) * 32 + lane] += k2 * R[(v0 + MV_e) * 32 + lane];
+                R[slot_planet(p, PA_S0) * 32 + lane] += k2 * R[(v0 + MV_S0) * 32 + lane];
+                R[slot_planet(p, PA_S1) * 32 + lane] += k2 * R[(v0 + MV_S1) * 32 + lane];
+                R[slot_planet(p, PA_mu) * 32 + lane] += k2 * R[(v0 + MV_mu) * 32 + lane];
             }
-        } else if (GRAD) {
-            if (B.slot_jitter >= 0) s_g[B.idx_jitter * 32 + lane] += R[B.slot_jitter * 32 + lane];
-            if (B.slot_platescale >= 0) s_g[B.idx_platescale * 32 + lane] += R[B.slot_platescale * 32 + lane];
-            if (B.slot_northangle >= 0) s_g[B.idx_northangle * 32 + lane] += R[B.slot_northangle * 32 + lane];
-            if (B.slot_offset >= 0) s_g[B.idx_offset * 32 + lane] += R[B.slot_offset * 32 + lane];
         }
     }
-    if (GRAD) {
+    R[0 * 32 + lane] += ll;
+}
+
+__device__ __noinline__ void epilogue_part(int part, const DevModel& m, const double* s_const, const double* R, double* gp,
+                                           int lane) {
+    if (part == 0) {
 #pragma unroll 1
-        for (int p = 0; p < m.n_planets; ++p) {
-            const double* sc = s_const + p * PC_COUNT * 32;
-            auto C = [&](int k) { return sc[k * 32 + lane]; };
-            auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
-            const double e = C(PC_e), s = C(PC_s), nd = C(PC_nd);
-            const double inv_a = C(PC_inv_a), inv_M = C(PC_inv_M), inv_s = C(PC_inv_s);
-            const double sW = C(PC_sinW), cW = C(PC_cosW), sw = C(PC_sinw), cw = C(PC_cosw), si = C(PC_sini), ci = C(PC_cosi);
-            const double A = C(PC_A), Bc = C(PC_B), F = C(PC_F), G = C(PC_G), scl = C(PC_sc), c2a = C(PC_c2a);
-            const double K = C(PC_K), Kb = C(PC_Kb), mu = C(PC_mu);
-            const double gBh = Rp(PA_Bh), gGs = Rp(PA_Gs), gAh = Rp(PA_Ah), gFs = Rp(PA_Fs);
-            const double gPc = Rp(PA_Pc), gPs = Rp(PA_Ps), S0 = Rp(PA_S0), S1 = Rp(PA_S1), gmu = Rp(PA_mu);
-            double g_e = Rp(PA_e);
-            // mean motion: M_k = nd (t_k - tp)
-            double g_tp = -nd * S0;
-            double g_a = S1 * (-1.5 * nd * inv_a);
-            double g_M = S1 * (0.5 * nd * inv_M);
+        for (int b = 0; b < m.n_blocks; ++b) {
+            const DevBlock& B = m.blocks[b];
+            if (B.kind == OCTO_KIND_RV_STAR_MARGIN) continue;
+            if (B.slot_jitter >= 0) gp[B.idx_jitter * 32 + lane] += R[B.slot_jitter * 32 + lane];
+            if (B.slot_platescale >= 0) gp[B.idx_platescale * 32 + lane] += R[B.slot_platescale * 32 + lane];
+            if (B.slot_northangle >= 0) gp[B.idx_northangle * 32 + lane] += R[B.slot_northangle * 32 + lane];
+            if (B.slot_offset >= 0) gp[B.idx_offset * 32 + lane] += R[B.slot_offset * 32 + lane];
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int p = 0; p < m.n_planets; ++p) {
+        const double* sc = s_const + p * PC_COUNT * 32;
+        auto C = [&](int k) { return sc[k * 32 + lane]; };
+        auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
+        const double e = C(PC_e), s = C(PC_s), inv_s = C(PC_inv_s), inv_a = C(PC_inv_a), inv_M = C(PC_inv_M);
+        if (part == 1) {
             // astrometry: Bh = sc*B, Gs = sc*s*G, Ah = sc*A, Fs = sc*s*F with sc = a*c2a
+            const double sW = C(PC_sinW), cW = C(PC_cosW), sw = C(PC_sinw), cw = C(PC_cosw), si = C(PC_sini);
+            const double A = C(PC_A), Bc = C(PC_B), F = C(PC_F), G = C(PC_G), scl = C(PC_sc);
+            const double gBh = Rp(PA_Bh), gGs = Rp(PA_Gs), gAh = Rp(PA_Ah), gFs = Rp(PA_Fs);
             const double g_sc = gBh * Bc + gGs * s * G + gAh * A + gFs * s * F;
-            g_a += g_sc * c2a;
-            double g_plx = g_sc * C(PC_a) * m.c2a_per_plx;      // d(a*c2a)/d plx
             const double gB = gBh * scl, gG = gGs * scl * s, gA = gAh * scl, gF = gFs * scl * s;
-            g_e += -(e * inv_s) * scl * (gGs * G + gFs * F);
-            double g_w = gA * F + gB * G - gF * A - gG * Bc;
-            double g_W = -gA * Bc + gB * A - gF * G + gG * F;
-            double g_i = si * (gA * sW * sw - gB * cW * sw + gF * sW * cw - gG * cW * cw);
+            gp[m.idx_a[p] * 32 + lane] += g_sc * C(PC_c2a);
+            gp[m.idx_plx[p] * 32 + lane] += g_sc * C(PC_a) * m.c2a_per_plx;      // d(a*c2a)/d plx
+            gp[m.idx_e[p] * 32 + lane] += -(e * inv_s) * scl * (gGs * G + gFs * F);
+            gp[m.idx_w[p] * 32 + lane] += gA * F + gB * G - gF * A - gG * Bc;
+            gp[m.idx_W[p] * 32 + lane] += -gA * Bc + gB * A - gF * G + gG * F;
+            gp[m.idx_i[p] * 32 + lane] += si * (gA * sW * sw - gB * cW * sw + gF * sW * cw - gG * cW * cw);
+        } else if (part == 2) {
             // radial velocity: Pc = K cosω s², Ps = K sinω s, K = kappa sqrt(M/a) sin i / s
+            const double sw = C(PC_sinw), cw = C(PC_cosw), K = C(PC_K);
+            const double gPc = Rp(PA_Pc), gPs = Rp(PA_Ps);
             const double s2 = s * s;
             const double gK = gPc * cw * s2 + gPs * sw * s;
-            g_w += -gPc * K * sw * s2 + gPs * K * cw * s;
-            g_e += gPc * K * cw * (-2.0 * e) + gPs * K * sw * (-e * inv_s) + gK * K * e * inv_s * inv_s;
-            g_a += gK * (-0.5 * K * inv_a);
-            g_M += gK * (0.5 * K * inv_M);
-            g_i += gK * Kb * ci;
-            // reflex factor mu = mass * mjup2msol / M
-            g_M += -gmu * mu * inv_M;
-            s_g[m.idx_a[p] * 32 + lane] += g_a;   s_g[m.idx_e[p] * 32 + lane] += g_e;
-            s_g[m.idx_i[p] * 32 + lane] += g_i;   s_g[m.idx_w[p] * 32 + lane] += g_w;
-            s_g[m.idx_W[p] * 32 + lane] += g_W;   s_g[m.idx_tp[p] * 32 + lane] += g_tp;
-            s_g[m.idx_M[p] * 32 + lane] += g_M;   s_g[m.idx_plx[p] * 32 + lane] += g_plx;
-            if (m.idx_mass[p] >= 0) s_g[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol * inv_M;
+            gp[m.idx_w[p] * 32 + lane] += -gPc * K * sw * s2 + gPs * K * cw * s;
+            gp[m.idx_e[p] * 32 + lane] += gPc * K * cw * (-2.0 * e) + gPs * K * sw * (-e * inv_s) + gK * K * e * inv_s * inv_s;
+            gp[m.idx_a[p] * 32 + lane] += gK * (-0.5 * K * inv_a);
+            gp[m.idx_M[p] * 32 + lane] += gK * (0.5 * K * inv_M);
+            gp[m.idx_i[p] * 32 + lane] += gK * C(PC_Kb) * C(PC_cosi);
+        } else {
+            // mean motion M_k = nd (t_k - tp); direct e terms; reflex factor mu = mass * mjup2msol / M
+            const double nd = C(PC_nd), S0 = Rp(PA_S0), S1 = Rp(PA_S1), gmu = Rp(PA_mu);
+            gp[m.idx_tp[p] * 32 + lane] += -nd * S0;
+            gp[m.idx_a[p] * 32 + lane] += S1 * (-1.5 * nd * inv_a);
+            gp[m.idx_M[p] * 32 + lane] += S1 * (0.5 * nd * inv_M) - gmu * C(PC_mu) * inv_M;
+            gp[m.idx_e[p] * 32 + lane] += Rp(PA_e);
+            if (m.idx_mass[p] >= 0) gp[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol * inv_M;
         }
     }
-    ll_out = ll;
 }
 
 template <bool GRAD, int NPT>
@@ -680,8 +696,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     double* s_const = smem;                                   // [P][PC_COUNT][32]
     double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
     double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
-    double* s_g = s_red + n_acc * 32;                         // [n_in][32]
-    double2* s_stage = reinterpret_cast<double2*>(s_g + m.n_in * 32);   // [W][32 records][3]
+    double2* s_stage = reinterpret_cast<double2*>(s_red + n_acc * 32);   // [W][32 records][3]
     int* s_ok = reinterpret_cast<int*>(s_stage + W * 96);     // [32]
     __shared__ int s_last;
 
@@ -704,10 +719,6 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     double* acc = s_acc + w * n_acc * 32;
 #pragma unroll 4
     for (int s = 0; s < n_acc; ++s) acc[s * 32 + lane] = 0.0;
-    if (GRAD) {
-#pragma unroll 1
-        for (int k = w; k < m.n_in; k += W) s_g[k * 32 + lane] = 0.0;
-    }
     __syncthreads();
 
     // ---- prologue phase 1: finiteness of every input (logdensitymodel.jl:120-124) and the per-planet tasks,
@@ -813,18 +824,34 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
 
     OCTO_TICK();
-    // ---- epilogue: warp 0, one lane per chain column
-    if (w == 0) {
-        const int64_t c = chain_of(lane);
-        const bool active = lane < ncol && chain0 + lane < n_chains;
-        const int valid = s_ok[lane];
-        double ll;
-        chain_epilogue<GRAD>(m, s_const, s_red, s_g, in, c, ld, lane, ll);
-        if (active) {
-            ll_out[c] = valid ? ll : -CUDART_INF;
-            if (GRAD) {
-#pragma unroll 4
-                for (int k = 0; k < m.n_in; ++k) g_out[c + (int64_t)k * ldg] = valid ? s_g[k * 32 + lane] : 0.0;
+    // ---- epilogue (see epilogue_part): gradient parts live in the now free per-warp accumulator area
+    double* s_gp = s_acc;                                     // [EPI_PARTS][n_in][32]
+    if (GRAD) {
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < EPI_PARTS * m.n_in * 32; idx += W * 32) s_gp[idx] = 0.0;
+    }
+    __syncthreads();
+    if (m.has_margin) {
+        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, in, chain_of(lane), ld, lane);
+        __syncthreads();
+    }
+    if (GRAD) {
+#pragma unroll 1
+        for (int part = w; part < EPI_PARTS; part += W) epilogue_part(part, m, s_const, s_red, s_gp + part * m.n_in * 32, lane);
+    }
+    if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
+        const bool active = chain0 + lane < n_chains;
+        if (active) ll_out[chain0 + lane] = s_ok[lane] ? s_red[lane] + m.const_ll : -CUDART_INF;
+    }
+    if (GRAD) {
+        __syncthreads();
+        const int ng = m.n_in * 32;
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < ng; idx += W * 32) {
+            const int l = idx & 31;
+            if (chain0 + l < n_chains) {
+                const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
+                g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
             }
         }
     }
@@ -858,7 +885,8 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
 }
 
 size_t octo_smem_bytes(const DevModel& m, int W) {
-    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (size_t)W * m.n_acc * 32 + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
+    size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * m.n_in * 32;      // the epilogue's gradient parts reuse the accumulator area
+    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32;
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 

@@ -348,6 +348,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         if (E > 0x7fffffff) return bad("too many epochs");
     }
     m.n_epochs = E; m.n_acc = n_acc;
+    for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN) m.has_margin = 1;
     // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
     double cum = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
