@@ -36,7 +36,7 @@ F_ALG = {"astrom": 308.0, "rv": 336.0, "extra_solve": 259.0}
 # EXECUTED FP64 flop per pair of THIS kernel, from ncu SASS counts (DFMA = 2, DMUL/DADD = 1; profiles/r01_*):
 # the FP32 Markley starter, the branch-free sincos/rcp and the single sincos per solve make it ~1.8x leaner than
 # the algorithmic figure.  Reported next to the roofline as `executed`.
-F_EXEC = {"astrom": 171.0, "rv": 228.0}
+F_EXEC = {"astrom": 150.0, "rv": 207.0}      # astrometry: 55 DFMA + 27 DMUL + 13 DADD; RV+jitter: 76 + 36 + 19 (+ libm log)
 FP64_PEAK_FALLBACK_TFLOPS = 37.2     # nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz, used only if the probe fails
 
 
@@ -287,7 +287,8 @@ def main():
                        "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
                        "timing": "CUDA events around each step's single kernel on the launching stream; value = pairs / sum of event times"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_how, "flop_per_pair": F_ALG,
+                         # dram__bytes_read + write of this launch from the committed ncu capture (profiles/r01_ncu_summary.txt)
+                         "traffic": 491520, "peak_source": peak_how, "flop_per_pair": F_ALG,
                          "executed": {"tflops": flops_per_launch(spec, n, F_EXEC) / (kern_ms * 1e-3) / 1e12,
                                       "flop_per_pair": F_EXEC, "how": "ncu SASS op counts, see profiles/"},
                          "kernel_ms": kern_ms, "kernel_ms_min": float(ms.min()),
