@@ -177,17 +177,18 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def time_device(model, d_in, d_ll, d_g, n, steps, warmup, torch, flush):
+def time_device(model, d_in, d_ll, d_g, n, steps, warmup, torch, flush, grad=True):
     st = torch.cuda.current_stream()
+    gp = d_g.data_ptr() if grad else 0
     for _ in range(warmup):
-        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), d_g.data_ptr(), st.cuda_stream)
+        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), gp, st.cuda_stream)
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
         if flush is not None:
             flush.zero_()                      # > L2 (126 MB): the next step starts from a cold L2
         a.record(st)
-        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), d_g.data_ptr(), st.cuda_stream)
+        model.enqueue_device(d_in.data_ptr(), n, n, d_ll.data_ptr(), gp, st.cuda_stream)
         b.record(st)
     torch.cuda.synchronize()
     return np.array([a.elapsed_time(b) for a, b in ev])      # ms
@@ -232,6 +233,7 @@ def main():
         dist.barrier()
     launches = model.kernel_launches - launches0 - max(3, args.warmup)
     t_dev = float(ms.sum()) * 1e-3
+    ms_val = time_device(model, d_in, d_ll, d_g, n, max(20, args.steps // 4), 3, torch, None if args.no_flush else flush, grad=False)
 
     # end-to-end through the public host API: inputs in pinned host memory, outputs read back every step
     x_pin = model.pinned_empty(x.shape); x_pin[...] = x
@@ -300,7 +302,9 @@ def main():
                     "ms_per_step_pageable_host_arrays": t_e2e_pageable / args.steps * 1e3,
                     "api": "LogDensityModel.ln_like_and_gradient(pinned host ndarray, out=pinned) -> C ABI octo_logp_grad: "
                            "H2D + kernel + D2H + stream sync per step"},
-            "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "
+            "value_only": {"what": "K1v, logp without gradient (Pigeons slice sampler / prior search), same workload, device-resident",
+                       "value": n * E * world / (float(np.mean(ms_val)) * 1e-3), "unit": "evals/s", "ms_per_step": float(np.mean(ms_val))},
+        "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "
                                 "θ_at_epoch_to_tperi on device), same tables, D = %d; 3 launches per step" % spec_p.D,
                         "value": pairs_step * args.steps / t_post, "unit": "evals/s", "ms_per_step": t_post / args.steps * 1e3},
         "gpu_launches": int(launches),
@@ -338,6 +342,25 @@ def sweep(octo, workloads, torch, peak, device):
                "fp64_tflops": fl / (kms * 1e-3) / 1e12, "frac_fp64_peak": fl / (kms * 1e-3) / 1e12 / peak,
                "geometry": list(model.launch_geometry(n))}
         out.write(json.dumps(rec) + "\n"); out.flush()
+        print("sweep", json.dumps(rec), file=sys.stderr)
+        model.close()
+    # the other BASELINE.json configs (parity-test cases; timed here for the record, not bench lines)
+    for name in ("C1", "C3", "C4"):
+        spec, x = workloads.config(name)
+        model = octo.LogDensityModel(spec, device=device)
+        n, n_in = x.shape
+        d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+        d_ll = torch.empty(n, dtype=torch.float64, device="cuda")
+        d_g = torch.empty((n_in, n), dtype=torch.float64, device="cuda")
+        ms = time_device(model, d_in, d_ll, d_g, n, 50, 5, torch, flush)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            model.ln_like_and_gradient(x)
+        t_e2e = (time.perf_counter() - t0) / 50
+        rec = {"config": name, "chains": n, "epochs": spec.total_epochs, "planets": len(spec.layout_dict["planets"]),
+               "kernel_ms": float(np.mean(ms)), "evals_per_s": n * spec.total_epochs / (float(np.mean(ms)) * 1e-3),
+               "e2e_ms_pageable": t_e2e * 1e3, "geometry": list(model.launch_geometry(n))}
+        out.write(json.dumps(rec) + "\n")
         print("sweep", json.dumps(rec), file=sys.stderr)
         model.close()
     out.close()

@@ -192,6 +192,13 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
         }
     }
     if (gy < 1) gy = 1;
+    // tiny problems: the cross-CTA combine (write + fence + ticket + reads, ~3.5 us) costs more than the epochs it
+    // takes off each warp (~0.6 us per lean-astrometry-equivalent epoch, measured on C2's timeline)
+    if (gy > 1) {
+        const double t_iter = 0.6, t_k2 = 3.5, ew = ctx->m.wtot;
+        const double split = std::ceil(ew / (double)(W * gy)) * t_iter + t_k2, single = std::ceil(ew / (double)W) * t_iter;
+        if (single <= split) gy = 1;
+    }
     g.gy = (int)gy;
     g.slice = (int)((E + gy * W - 1) / (gy * W));
     return g;
