@@ -1,0 +1,100 @@
+"""Replica-batched explorers over the device log-posterior.
+
+The reference samples ONE chain at a time (AdvancedHMC NUTS, src/sampling.jl:412-423; Pigeons SliceSampler per
+replica, ext/OctofitterPigeonsExt:70-72).  On the GPU the natural unit is a batch of chains advanced in lockstep:
+every leapfrog step is one `ℓπcallback_grad` call for all chains.  These drivers are deliberately small — the
+samplers stay the caller's business; they exist so the path can be exercised end to end.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def diagonal_metric(model, theta, h=1e-5):
+    """Diagonal inverse mass from the curvature at `theta` (D,): 1 / |∂²ℓπ/∂θ_j²| by central differences of the
+    device gradient — all 2D probes are one batched call.  (The reference adapts a dense metric with Stan's windowed
+    adaptation, src/sampling.jl:335-345; this is the minimal stand-in for tests and examples.)"""
+    th = np.asarray(theta, dtype=np.float64)
+    D = th.shape[0]
+    probes = np.repeat(th[None, :], 2 * D, axis=0)
+    for j in range(D):
+        probes[2 * j, j] += h; probes[2 * j + 1, j] -= h
+    _, g = model.ℓπcallback_grad(np.asfortranarray(probes))
+    hjj = np.array([-(g[2 * j, j] - g[2 * j + 1, j]) / (2 * h) for j in range(D)])
+    return 1.0 / np.maximum(np.abs(hjj), 1e-8)
+
+
+def batched_hmc(model, theta0, n_iter, *, step_size=0.02, n_leapfrog=16, rng=None, inv_mass=None):
+    """Static-trajectory HMC on `model.ℓπcallback_grad` for all chains at once.
+
+    theta0: (n_chains, D) unconstrained start.  Returns dict(theta [n_iter, n_chains, D], logpost [n_iter, n_chains],
+    accept_rate, n_gradient_calls).  inv_mass: optional diagonal inverse mass (D,).
+    """
+    rng = np.random.default_rng() if rng is None else rng
+    th = np.array(theta0, dtype=np.float64, order="F")
+    n, D = th.shape
+    im = np.ones(D) if inv_mass is None else np.asarray(inv_mass, dtype=np.float64)
+    lp, g = model.ℓπcallback_grad(th)
+    lp, g = lp.copy(), g.copy()
+    out_th = np.empty((n_iter, n, D)); out_lp = np.empty((n_iter, n))
+    acc_total, calls = 0.0, 1
+    for it in range(n_iter):
+        p = rng.standard_normal((n, D)) / np.sqrt(im)
+        h0 = -lp + 0.5 * np.sum(p * p * im, axis=1)
+        q, gq, lq = th.copy(), g.copy(), lp.copy()
+        p = p + 0.5 * step_size * gq
+        for k in range(n_leapfrog):
+            q = q + step_size * p * im
+            lq, gq = model.ℓπcallback_grad(np.asfortranarray(q))
+            calls += 1
+            gq = np.where(np.isfinite(lq)[:, None], gq, 0.0)
+            p = p + (step_size if k < n_leapfrog - 1 else 0.5 * step_size) * gq
+        with np.errstate(over="ignore", invalid="ignore"):
+            h1 = -lq + 0.5 * np.sum(p * p * im, axis=1)
+        dh = h0 - h1
+        accept = np.isfinite(lq) & (np.log(rng.uniform(size=n)) < dh)
+        th[accept] = q[accept]; g[accept] = gq[accept]; lp[accept] = lq[accept]
+        acc_total += accept.mean()
+        out_th[it] = th; out_lp[it] = lp
+    return {"theta": out_th, "logpost": out_lp, "accept_rate": acc_total / n_iter, "n_gradient_calls": calls}
+
+
+def batched_parallel_tempering(model, model_ref_logp, pt, theta0, n_rounds, *, step_size=0.02, n_leapfrog=8, rng=None,
+                               inv_mass=None):
+    """Tempered HMC explorer + deterministic even-odd swaps (octo.ParallelTempering) for the LOCAL replicas of a rank.
+
+    model: parameterised LogDensityModel (target ℓπ, prior included); model_ref_logp(θ_t) -> (ℓ_ref, ∇ℓ_ref) of the
+    tempering reference (the prior-only model, ext/OctofitterPigeonsExt:61-67).  Replica r explores
+    (1-β) ℓ_ref + β ℓ_target with the β it currently holds; swaps exchange β indices, not states.
+    """
+    rng = np.random.default_rng() if rng is None else rng
+    th = np.array(theta0, dtype=np.float64, order="F")
+    n, D = th.shape
+    assert n == pt.n_local
+    im = np.ones(D) if inv_mass is None else np.asarray(inv_mass, dtype=np.float64)
+    swaps = []
+    for rnd in range(n_rounds):
+        beta = pt.local_betas()[:, None]
+
+        def tempered(q):
+            lt, gt = model.ℓπcallback_grad(np.asfortranarray(q))
+            lr, gr = model_ref_logp(q)
+            ok = np.isfinite(lt)
+            lt = np.where(ok, lt, -np.inf); gt = np.where(ok[:, None], gt, 0.0)
+            return (1 - beta[:, 0]) * lr + beta[:, 0] * lt, (1 - beta) * gr + beta * gt, lr, lt
+        lp, g, lr, lt = tempered(th)
+        p = rng.standard_normal((n, D)) / np.sqrt(im)
+        h0 = -lp + 0.5 * np.sum(p * p * im, axis=1)
+        q, gq = th.copy(), g.copy()
+        p = p + 0.5 * step_size * gq
+        for k in range(n_leapfrog):
+            q = q + step_size * p * im
+            lq, gq, lrq, ltq = tempered(q)
+            gq = np.where(np.isfinite(lq)[:, None], gq, 0.0)
+            p = p + (step_size if k < n_leapfrog - 1 else 0.5 * step_size) * gq
+        with np.errstate(over="ignore", invalid="ignore"):
+            h1 = -lq + 0.5 * np.sum(p * p * im, axis=1)
+        accept = np.isfinite(lq) & (np.log(rng.uniform(size=n)) < h0 - h1)
+        th[accept] = q[accept]; lr = np.where(accept, lrq, lr); lt = np.where(accept, ltq, lt)
+        swaps.append(pt.swap_round(lr, lt))
+    return {"theta": th, "swap_accept": np.array(swaps)}

@@ -106,3 +106,54 @@ def test_guess_starting_position_batched(oracle_lib):
     # a uniform draw from the prior is (much) worse than the best of 40k
     assert lp > np.median(model.ℓπcallback(model.link(model.sample_priors(rng, 2000))))
     model.close()
+
+
+def test_batched_hmc_end_to_end():
+    """The whole stack as a sampler sees it (reference: "Test fitting a chain", test/integration-tests.jl:52-58):
+    256 chains of static HMC on the reference's 11-D test model, every leapfrog one device call.  Chains must move,
+    accept, stay at plausible log-posterior, and the posterior must cover the orbit that generated the fixture."""
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(4)
+    params, lp0 = model.guess_starting_position(rng, N=60_000, batch=20_000)
+    start = model.link(params)
+    inv_mass = octo.diagonal_metric(model, start)            # diagonal preconditioner from the local curvature
+    th0 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((256, spec.D))
+    res = octo.batched_hmc(model, th0, 150, step_size=0.15, n_leapfrog=12, rng=rng, inv_mass=inv_mass)
+    assert 0.4 < res["accept_rate"] <= 1.0
+    lp_end = res["logpost"][-1]
+    assert np.all(np.isfinite(lp_end)) and np.median(lp_end) > -1000            # `@test all(chain[:logpost] .> -1000)`
+    assert np.median(lp_end) >= lp0 - 30
+    nat = model.invlink(res["theta"][-1])
+    names = list(spec.theta_names)
+    a, e = nat[:, names.index("b.a")], nat[:, names.index("b.e")]
+    assert 5.0 < np.median(a) < 40.0 and 0.0 <= np.median(e) < 0.9            # generating orbit: a = 12, e = 0.11
+    assert res["n_gradient_calls"] == 1 + 150 * 12
+    model.close()
+
+
+def test_batched_parallel_tempering_single_rank():
+    """N2: tempered replicas advanced in lockstep on the device + deterministic even-odd swaps.  The tempering
+    reference is the prior-only model, built as the reference does (observations blanked, same parameters:
+    src/cross-validation.jl:60-99, ext/OctofitterPigeonsExt:61-67)."""
+    system = reference_test_system()
+    spec = octo.ModelSpec(system)
+    model = octo.LogDensityModel(spec)
+    # prior-only twin: same variables, no tables
+    b0 = system.planets[0]
+    b_ref = octo.Planet(name=b0.name, variables=dict(b0.var_specs), observations=[])
+    ref_model = octo.LogDensityModel(octo.ModelSpec(octo.System(name="ref", variables=dict(system.var_specs), companions=[b_ref])))
+    assert ref_model.D == model.D and ref_model.spec.total_epochs == 0
+    rng = np.random.default_rng(6)
+    params, _ = model.guess_starting_position(rng, N=30_000, batch=30_000)
+    start = model.link(params)
+    inv_mass = octo.diagonal_metric(model, start)
+    R = 16
+    pt = octo.ParallelTempering(R, seed=3, backend="local")
+    th0 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((R, spec.D))
+    res = octo.batched_parallel_tempering(model, ref_model.ℓπcallback_grad, pt, th0, 40, step_size=0.15, n_leapfrog=6, rng=rng,
+                                          inv_mass=inv_mass)
+    assert sorted(pt.chain_of_replica) == list(range(R)) and pt.round == 40
+    assert res["swap_accept"].shape == (40, R - 1) and res["swap_accept"].sum() > 0
+    assert np.all(np.isfinite(model.ℓπcallback(np.asfortranarray(res["theta"]))))
+    model.close(); ref_model.close()
