@@ -180,13 +180,16 @@ __device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double 
 // ---------------------------------------------------------------------------------------------
 // Astrometry segment (kinds 0, 1): epochs [k0, k1) of table B for this warp's 32 chains.
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT, bool LEAN>
+// MODE 0: RA/Dec table with fixed weights (no jitter / platescale / northangle) — the common case
+// MODE 1: RA/Dec table with a sampled jitter (per-pair covariance), no platescale / northangle
+// MODE 2: everything else (PA/sep tables, platescale, northangle), decided at run time
+template <bool GRAD, int NPT, int MODE>
 __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                         double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
     const int ip = B.planet;
-    // LEAN: RA/Dec table with fixed weights (no jitter / platescale / northangle) — the common case
-    const bool pasep = !LEAN && (B.kind == OCTO_KIND_ASTROM_PASEP);
-    const bool jitm = !LEAN && B.jit;
+    constexpr bool LEAN = (MODE == 0);
+    const bool pasep = (MODE == 2) && (B.kind == OCTO_KIND_ASTROM_PASEP);
+    const bool jitm = (MODE == 1) || (MODE == 2 && B.jit);
     // involved planets: the observed one, then interior companions with a mass (relative-astrometry.jl:117-133)
     int pj[NPT]; double f[NPT]; Orb orb[NPT]; double Bh[NPT], Gs[NPT], Ah[NPT], Fs[NPT];
     int ni = 1;
@@ -212,9 +215,9 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
         Ah[u] = sc[PC_Ah * 32 + lane]; Fs[u] = sc[PC_Fs * 32 + lane];
     }
     const double jit = (!LEAN && B.idx_jitter >= 0) ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
-    const double ps = (!LEAN && B.idx_platescale >= 0) ? in[c + (int64_t)B.idx_platescale * ld] : 1.0;
-    const double na = (!LEAN && B.idx_northangle >= 0) ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
-    const bool rot = !LEAN && ((B.idx_platescale >= 0) || (B.idx_northangle >= 0));
+    const double ps = (MODE == 2 && B.idx_platescale >= 0) ? in[c + (int64_t)B.idx_platescale * ld] : 1.0;
+    const double na = (MODE == 2 && B.idx_northangle >= 0) ? in[c + (int64_t)B.idx_northangle * ld] : 0.0;
+    const bool rot = (MODE == 2) && ((B.idx_platescale >= 0) || (B.idx_northangle >= 0));
     double sna = 0.0, cna = 1.0;
     if (rot && !pasep) sincos_any(na, sna, cna);
     const double j2 = jit * jit;
@@ -672,9 +675,10 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
                                             int64_t ld, int lane) {
     if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
-        const bool lean = B.kind == OCTO_KIND_ASTROM_RADEC && !B.jit && B.idx_platescale < 0 && B.idx_northangle < 0;
-        if (lean) seg_astrom<GRAD, NPT, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
-        else seg_astrom<GRAD, NPT, false>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0;
+        if (plain && !B.jit) seg_astrom<GRAD, NPT, 0>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        else if (plain) seg_astrom<GRAD, NPT, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        else seg_astrom<GRAD, NPT, 2>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
         seg_rv<GRAD, NPT, true, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
     } else if (B.jit) {
