@@ -362,7 +362,8 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         DevBlock& D = m.blocks[b];
         const bool astrom = D.kind <= OCTO_KIND_ASTROM_PASEP;
         const bool lean = D.kind == OCTO_KIND_ASTROM_RADEC && !D.jit && D.idx_platescale < 0 && D.idx_northangle < 0;
-        double w = astrom ? (lean ? 1.0 : 2.5) : (D.kind == OCTO_KIND_RV_STAR_MARGIN ? 1.9 : (D.jit ? 1.8 : 1.1));
+        const bool plain = D.kind == OCTO_KIND_ASTROM_RADEC && D.idx_platescale < 0 && D.idx_northangle < 0;
+        double w = astrom ? (lean ? 1.0 : (plain ? 1.6 : 2.5)) : (D.kind == OCTO_KIND_RV_STAR_MARGIN ? 1.9 : (D.jit ? 1.8 : 1.1));
         int solves = 1;
         if (D.kind == OCTO_KIND_RV_STAR_ABS || D.kind == OCTO_KIND_RV_STAR_MARGIN) solves = L->n_planets;
         else for (int p = 0; p < L->n_planets; ++p) if (p != D.planet && L->idx_mass[p] >= 0) ++solves;   // upper bound
