@@ -47,7 +47,6 @@ struct DevBlock {
 struct DevModel {
     OctoConstants c;
     double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
-    double two_pi_over_kyd;  // 2π / kepler_year_days: mean motion [rad/day] = this * sqrt(M/a) / a
     double c2a_per_plx;      // rad2as*1e3 / (1000*pc2au): mas per AU per mas of parallax
     double wtot;             // Σ n*wgt over all tables: warps split this, not the raw epoch count
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter

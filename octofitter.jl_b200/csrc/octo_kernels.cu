@@ -502,8 +502,8 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
 
 // ---------------------------------------------------------------------------------------------
 // Prologue: per chain*planet constants (ref a3: KepOrbit / Visual ctor caches) -> shared memory.
-// Two phases so that the 8 warps of a CTA share the latency: phase 1 = four independent tasks per planet
-// (sincos i | sincos ω | sincos Ω | scalar chain: validity, s, mean motion, K/sin i, mas/AU, mu), phase 2 =
+// Two phases so that the 8 warps of a CTA share the latency: phase 1 = five independent tasks per planet
+// (sincos i | sincos ω | sincos Ω | eccentricity chain | size/mass/time chain: mean motion, mas/AU, mu), phase 2 =
 // the Thiele-Innes / RV products.  All branch-free (rcp/rsqrt Newton, quadrant-reduced sincos).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 normal: seed + 3 Newton steps
@@ -528,27 +528,38 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
         sc[ks * 32 + lane] = sn; sc[(ks + 1) * 32 + lane] = cs;
         return ok;
     }
-    double a = in[c + (int64_t)m.idx_a[p] * ld], e = in[c + (int64_t)m.idx_e[p] * ld];
-    double tp = in[c + (int64_t)m.idx_tp[p] * ld];
+    if (kind == 3) {          // eccentricity chain
+        double e = in[c + (int64_t)m.idx_e[p] * ld];
+        const bool ok = isfinite(e) && (e >= 0.0) && (e < 1.0);
+        if (!ok) e = 0.1;
+        const double s2 = fma(-e, e, 1.0);
+        const double inv_s = rsqrt_nr(s2);
+        sc[PC_e * 32 + lane] = e;          sc[PC_ome * 32 + lane] = 1.0 - e;  sc[PC_ca1 * 32 + lane] = kA1 * rcp_nr(1.0 + e);
+        sc[PC_s * 32 + lane] = s2 * inv_s; sc[PC_inv_s * 32 + lane] = inv_s;
+        return ok;
+    }
+    // kind 4: size / mass / time chain.  The mean motion follows the reference's operation order with IEEE
+    // division and square root (KepOrbit ctor + orbitsolve: n = 2π / (√(a³/M)·kyd / y2d), MA = n / y2d · (t - tp)):
+    // its last bit is multiplied by |MA| (thousands of radians for short periods), so anything else would cost
+    // parity digits in exactly the regime where the problem is already ill-conditioned.
+    double a = in[c + (int64_t)m.idx_a[p] * ld], tp = in[c + (int64_t)m.idx_tp[p] * ld];
     double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
     double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
-    const bool fin = isfinite(a) && isfinite(e) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
-    const bool ok = fin && (e >= 0.0) && (e < 1.0) && (a > 0.0) && (M > 0.0) && (plx > 0.0);
-    if (!ok) { a = 1.0; e = 0.1; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
-    const double s2 = fma(-e, e, 1.0);
-    const double inv_s = rsqrt_nr(s2), s = s2 * inv_s;
+    const bool fin = isfinite(a) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
+    const bool ok = fin && (a > 0.0) && (M > 0.0) && (plx > 0.0);
+    if (!ok) { a = 1.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
+    const double period_days = __dmul_rn(__dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(a, a), a), M)), m.c.kepler_year_days);
+    const double period_yrs = __ddiv_rn(period_days, m.c.year2day);
+    const double n_yr = __ddiv_rn(kTwoPi, period_yrs);
     const double inv_a = rcp_nr(a), inv_M = rcp_nr(M);
-    const double Moa = M * inv_a;                               // M / a
-    const double rt = Moa * rsqrt_nr(Moa);                      // sqrt(M / a)
-    const double nd = m.two_pi_over_kyd * rt * inv_a;           // 2π / (sqrt(a³/M) * kepler_year_days)
+    const double Moa = M * inv_a;
     const double c2a = plx * m.c2a_per_plx;                     // rad2as*1e3 / (1000/plx * pc2au)  [mas/AU]
-    sc[PC_nd * 32 + lane] = nd;        sc[PC_tp * 32 + lane] = tp;  sc[PC_e * 32 + lane] = e;
-    sc[PC_ome * 32 + lane] = 1.0 - e;  sc[PC_ca1 * 32 + lane] = kA1 * rcp_nr(1.0 + e);
-    sc[PC_s * 32 + lane] = s;          sc[PC_inv_s * 32 + lane] = inv_s;
+    sc[PC_nd * 32 + lane] = __ddiv_rn(n_yr, m.c.year2day);      // [rad/day]
+    sc[PC_tp * 32 + lane] = tp;
     sc[PC_a * 32 + lane] = a;          sc[PC_inv_a * 32 + lane] = inv_a;
     sc[PC_M * 32 + lane] = M;          sc[PC_inv_M * 32 + lane] = inv_M;
     sc[PC_plx * 32 + lane] = plx;      sc[PC_c2a * 32 + lane] = c2a; sc[PC_sc * 32 + lane] = a * c2a;
-    sc[PC_Kb * 32 + lane] = m.kappa * rt * inv_s;               // K / sin i
+    sc[PC_Kb * 32 + lane] = m.kappa * Moa * rsqrt_nr(Moa);      // K s / sin i  (finished in prologue_products)
     sc[PC_mu * 32 + lane] = mass * m.c.mjup2msol * inv_M;
     return ok;
 }
@@ -559,7 +570,9 @@ __device__ __noinline__ void prologue_products(double* sc, int lane) {
     const double s = sc[PC_s * 32 + lane], scl = sc[PC_sc * 32 + lane];
     const double A = cW * cw - sW * sw * ci, Bc = sW * cw + cW * sw * ci;
     const double F = -cW * sw - sW * cw * ci, G = -sW * sw + cW * cw * ci;
-    const double K = sc[PC_Kb * 32 + lane] * si;
+    const double Kb = sc[PC_Kb * 32 + lane] * sc[PC_inv_s * 32 + lane];        // K / sin i
+    const double K = Kb * si;
+    sc[PC_Kb * 32 + lane] = Kb;
     sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = Bc; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
     sc[PC_Bh * 32 + lane] = scl * Bc; sc[PC_Gs * 32 + lane] = scl * s * G;
     sc[PC_Ah * 32 + lane] = scl * A;  sc[PC_Fs * 32 + lane] = scl * s * F;
@@ -733,9 +746,9 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         if (!isfinite(in[chain_of(col) + (int64_t)k * ld])) s_ok[col] = 0;
     }
 #pragma unroll 1
-    for (int it = threadIdx.x; it < ncol * 4 * m.n_planets; it += W * 32) {
+    for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
         const int col = it % ncol, task = it / ncol;
-        if (!prologue_task(m, task >> 2, task & 3, in, chain_of(col), ld, s_const + (task >> 2) * PC_COUNT * 32, col))
+        if (!prologue_task(m, task / 5, task % 5, in, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col))
             s_ok[col] = 0;
     }
     __syncthreads();

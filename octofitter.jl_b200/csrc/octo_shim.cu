@@ -310,7 +310,6 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     memset(&m, 0, sizeof(m));
     m.c = *consts;
     m.kappa = 6.283185307179586 * consts->year2day / consts->kepler_year_days * consts->au2m * consts->sec2year;
-    m.two_pi_over_kyd = 6.283185307179586 / consts->kepler_year_days;
     m.c2a_per_plx = consts->rad2as * 1e3 / (1000.0 * consts->pc2au);
     m.n_planets = L->n_planets; m.n_in = L->n_in; m.n_blocks = n_blocks;
     for (int p = 0; p < OCTO_MAX_PLANETS; ++p) {
