@@ -327,3 +327,19 @@ def test_extreme_orbits_stress(oracle_lib):
     # bound is the north star's 1e-8 away from the singular corner and scaled by 1/(1-e) inside it
     cond = 1.0 / (1.0 - x[:, names.index("b.e")])
     assert (grad_err(g, g_o).max(axis=1) / np.maximum(1.0, cond / 10)).max() < GRAD_RTOL
+
+
+def test_plain_c_consumer(oracle_lib, tmp_path):
+    """The boundary is a C ABI: a plain C program (gcc, dlopen — what Julia's ccall amounts to) builds the model from
+    the structs of include/octo_b200.h and gets the same numbers as the oracle and the mpmath golden vector."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "c_abi_smoke"
+    subprocess.run(["gcc", "-O1", "-o", str(exe), os.path.join(root, "tests", "c_abi_smoke.c"), "-ldl"], check=True)
+    out = subprocess.run([str(exe), octo.LIB_PATH], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    vals = np.array([[float.fromhex(t) for t in ln.split()] for ln in out])
+    d, packed, consts = load_golden("case_fixture8")
+    assert rel_err(vals[0, 0], d["ll"]) < LOGP_RTOL and grad_err(vals[0, 1:], d["grad"]).max() < GRAD_RTOL
+    x = np.array([d["x"], [v * (1.0 if k == 7 else 1.01) for k, v in enumerate(d["x"])]])
+    ll_o, g_o = oracle_lib.Oracle(packed, consts).logp_grad(x)
+    assert rel_err(vals[:, 0], ll_o).max() < LOGP_RTOL and grad_err(vals[:, 1:], g_o).max() < GRAD_RTOL
