@@ -197,7 +197,10 @@ int  octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D,
  * What `ℓπcallback` / `∇ℓπcallback` return (src/logdensitymodel.jl:110-146, 169-177) for such a model. */
 int  octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* lp, double* g_t);
 /* Same on DEVICE buffers, enqueued on `stream`; d_work is caller-provided scratch of
- * octo_logpost_workspace(ctx, n_chains) bytes. */
+ * octo_logpost_workspace(ctx, n_chains) bytes.  Normally the parameterisation runs inside the likelihood kernel
+ * (one launch; the workspace size is 0 and d_work may be NULL); models the fused stage cannot hold (more than 8
+ * θ_at_epoch_to_tperi definitions, a tperi that depends on another one, shared memory) use three launches that
+ * hand their intermediates through d_work. */
 int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n_chains);
 int  octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta_t, int64_t n_chains, int64_t ld, double* d_lp,
                               double* d_g_t, void* d_work, void* stream);

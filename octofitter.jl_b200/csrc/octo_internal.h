@@ -67,11 +67,18 @@ __host__ __device__ inline int slot_planet(int p, int a) { return 1 + p * PA_COU
 
 // ---- device-side standard parameterisation (octo_param.cu)
 #define OCTO_PARAM_MAX 64         // max D and max n_in of a parameterised model
+#define OCTO_PARAM_TPERI_MAX 8    // more θ_at_epoch_to_tperi definitions than this: stand-alone K0 kernels instead of the fused stage
 struct DevParam {
     int32_t D, n_in;
     OctoPrior priors[OCTO_PARAM_MAX];
-    double lognorm[OCTO_PARAM_MAX];      // log(Φ(β) - Φ(α)) of truncated normals, 0 otherwise
+    double pc[OCTO_PARAM_MAX][5];        // per-prior constants: lo, hi, constant part of the log density, 1/(hi-lo), 1/σ
     OctoInputDef defs[OCTO_PARAM_MAX];
+    int32_t n_tperi, pad;                // θ_at_epoch_to_tperi definitions, ascending input index
+    int32_t tperi_k[OCTO_PARAM_TPERI_MAX];
+    // reverse map for the gradient: parameter j gathers entries gat[gat_start[j] .. gat_start[j+1]), last input first;
+    // entry = input index | role << 8 (role 0: the parameter itself, 1: x of a UniformCircular pair, 2: y, 3: both)
+    int16_t gat_start[OCTO_PARAM_MAX + 1];
+    int16_t gat[2 * OCTO_PARAM_MAX];
 };
 
 struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
@@ -79,9 +86,9 @@ struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
-                        unsigned int* d_tickets, cudaStream_t stream);
-size_t octo_smem_bytes(const DevModel& m, int warps);
-cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int warps, int* ctas_per_sm);
+                        unsigned int* d_tickets, const DevParam* d_param, cudaStream_t stream);
+size_t octo_smem_bytes(const DevModel& m, int warps, int D = 0, int n_tperi = 0);
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);
 cudaError_t octo_param_init(int D, int n_in);
 cudaError_t octo_param_forward(const DevParam* d_param, int D, const DevModel& m, const double* d_theta, int64_t n,

@@ -18,6 +18,7 @@
 //   registers -> per-segment raw accumulators; folded into per-warp shared-memory slots at segment end
 //   epilogue  -> one lane per chain maps the raw sums to ∂ll/∂(inputs) by the chain rule, writes coalesced rows
 #include "octo_internal.h"
+#include "octo_param_dev.cuh"
 #include <math_constants.h>
 #include <cstdio>
 
@@ -683,6 +684,157 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused standard parameterisation: with a DevParam the kernel's input is θ_t.  Every CTA runs the
+// forward stage for its 32 chains (lane = chain; WARPS stride over parameters / inputs / tperi items, so a prior
+// family or input definition is warp-uniform), the last CTA of a chain group runs the reverse stage after the
+// epilogue.  Same device functions and the same summation orders as the stand-alone K0 kernels (octo_param.cu):
+// both paths give the same bits.  All arrays are [index][32 lanes].
+// ---------------------------------------------------------------------------------------------
+#ifdef OCTO_TIMING
+#define PTICK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ptk[i] = (long long)t_; } } while (0)
+__device__ long long g_ptk[2][8];
+#else
+#define PTICK(i) do {} while (0)
+#endif
+struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *trig, *part, *lp, *extra; int* flags; };
+__device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
+    ParamSmem S;
+    S.th = base; S.dxdy = S.th + D * 32; S.gth = S.dxdy + D * 32; S.L = S.gth + D * 32; S.aux = S.L + D * 32;
+    S.trig = S.aux + n_in * 32; S.part = S.trig + T * 9 * 32; S.lp = S.part + T * 7 * 32; S.extra = S.lp + 32;
+    S.flags = reinterpret_cast<int*>(S.extra + 32);
+    return S;
+}
+__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 16 * T + 3) * 32; }
+
+__device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
+                                           int64_t ld, double* s_in, const ParamSmem& S, int* s_ok, int w, int W, int lane) {
+    using namespace octo_param_dev;
+    const int D = P.D, n_in = P.n_in, T = P.n_tperi;
+#ifdef OCTO_TIMING
+    long long* ptk = g_ptk[0];
+#endif
+    PTICK(0);
+    // invlink + logpdf_with_trans
+#pragma unroll 1
+    for (int j = w; j < D; j += W) {
+        const double y = theta_t[c + (int64_t)j * ld];
+        const bool fin = isfinite(y);
+        const PriorEval r = prior_eval(P.priors[j].family, P.priors[j].p[0], P.pc[j], fin ? y : 0.0);
+        S.th[j * 32 + lane] = r.x; S.dxdy[j * 32 + lane] = r.dxdy; S.gth[j * 32 + lane] = r.dLdx;
+        S.L[j * 32 + lane] = fin ? r.L : CUDART_NAN;
+        if (!fin) S.flags[lane] = 16;                                // non-finite θ_t entry (flags start at 0)
+    }
+    __syncthreads();
+    PTICK(1);
+    // derived inputs that depend on parameters only (arr2nt)
+#pragma unroll 1
+    for (int k = w; k < n_in; k += W) {
+        const OctoInputDef& d = P.defs[k];
+        double v = 0.0, ext = 0.0;
+        if (d.op == OCTO_IN_PARAM) v = S.th[d.a[0] * 32 + lane];
+        else if (d.op == OCTO_IN_CONST) v = d.value;
+        else if (d.op == OCTO_IN_CIRC) circ_forward(S.th[d.a[0] * 32 + lane], S.th[d.a[1] * 32 + lane], d.value, v, ext);
+        s_in[k * 32 + lane] = v; S.aux[k * 32 + lane] = ext;
+    }
+    __syncthreads();
+    PTICK(2);
+    // θ_at_epoch_to_tperi: trigonometry of (θ, i, ω, Ω) as (definition, angle) items, then one warp per definition
+    if (T > 0) {
+#pragma unroll 1
+        for (int it = w; it < 4 * T; it += W) {
+            const int t = it >> 2, q = it & 3;
+            const OctoInputDef& d = P.defs[P.tperi_k[t]];
+            double sn, cs;
+            sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
+            S.trig[(t * 9 + 2 * q) * 32 + lane] = sn; S.trig[(t * 9 + 2 * q + 1) * 32 + lane] = cs;
+        }
+        __syncthreads();
+        PTICK(3);
+#pragma unroll 1
+        for (int t = w; t < T; t += W) {
+            const int k = P.tperi_k[t];
+            const OctoInputDef& d = P.defs[k];
+            double arg[7], trig[8];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) arg[q] = s_in[d.a[q] * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
+            double MA;
+            s_in[k * 32 + lane] = tperi_value(m.c, d.value, arg, trig, &MA);
+            S.trig[(t * 9 + 8) * 32 + lane] = MA;
+        }
+        __syncthreads();
+    }
+    PTICK(4);
+    // ordered sums, "healing" of a non-finite prior term (variables.jl:1229-1236), validity
+    if (w == W - 1) {                                                // the last warp has no prologue task on small models
+        double lp, extra;
+        const int fl = prior_sums(S.L + lane, S.aux + lane, s_in + lane, D, n_in, 32, !(S.flags[lane] & 16), lp, extra);
+        S.lp[lane] = lp; S.extra[lane] = extra; S.flags[lane] = fl;
+        if (!(fl & 4)) s_ok[lane] = 0;                               // K1 then returns -Inf / zero gradient
+    }
+    PTICK(5);
+#ifdef OCTO_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("  forward ns: priors +%lld inputs +%lld trig +%lld tperi +%lld sums +%lld\n", ptk[1] - ptk[0], ptk[2] - ptk[1], ptk[3] - ptk[2], ptk[4] - ptk[3], ptk[5] - ptk[4]);
+#endif
+}
+
+// reverse stage: S.aux holds d ll / d inputs of the 32 chains; S.flags bit 3 = chain is ok (valid and ll finite)
+__device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
+                                            double* __restrict__ g_t, int64_t chain0, int64_t n_chains, int64_t ldg, int w,
+                                            int W, int lane) {
+    using namespace octo_param_dev;
+    const int D = P.D, n_in = P.n_in, T = P.n_tperi;
+#ifdef OCTO_TIMING
+    long long* ptk = g_ptk[1];
+#endif
+    PTICK(0);
+    // the 7 partial derivatives of every θ_at_epoch_to_tperi: one warp per definition (hand-derived reverse pass)
+#pragma unroll 1
+    for (int t = w; t < T; t += W) {
+        const OctoInputDef& d = P.defs[P.tperi_k[t]];
+        double arg[7], trig[8], part[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) arg[q] = s_in[d.a[q] * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
+        tperi_reverse(m.c, arg, trig, S.trig[(t * 9 + 8) * 32 + lane], part);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) S.part[(t * 7 + q) * 32 + lane] = part[q];
+    }
+    __syncthreads();
+    PTICK(1);
+    if (w == 0) {                                                    // fold the tperi partials into ∂ll/∂inputs, last definition first
+#pragma unroll 1
+        for (int t = T - 1; t >= 0; --t) {
+            const int k = P.tperi_k[t];
+            const OctoInputDef& d = P.defs[k];
+            const double gk = S.aux[k * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) S.aux[d.a[q] * 32 + lane] += gk * S.part[(t * 7 + q) * 32 + lane];
+        }
+    }
+    PTICK(2);
+    if (T > 0) __syncthreads();
+    PTICK(3);
+    {                                                                // every parameter gathers its inputs: one warp per parameter
+        const int fl = S.flags[lane];
+        const bool ok = fl & 8, healed = fl & 2, active = chain0 + lane < n_chains;
+#pragma unroll 1
+        for (int j = w; j < D; j += W) {
+            const double g = param_gather(P, j, healed ? 0.0 : S.gth[j * 32 + lane], S.th + lane, S.aux + lane, 32);
+            if (active) g_t[chain0 + lane + (int64_t)j * ldg] = ok ? g * S.dxdy[j * 32 + lane] : 0.0;
+        }
+    }
+    PTICK(4);
+#ifdef OCTO_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("  backward ns: tperi +%lld accumulate +%lld barrier +%lld stores +%lld\n", ptk[1] - ptk[0], ptk[2] - ptk[1], ptk[3] - ptk[2], ptk[4] - ptk[3]);
+#endif
+}
+
 template <bool GRAD, int NPT>
 __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
@@ -705,7 +857,7 @@ template <bool GRAD, int NPT>
 __global__ void __launch_bounds__(WMAX * 32, OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
-              unsigned int* __restrict__ tickets) {
+              unsigned int* __restrict__ tickets, const DevParam* __restrict__ P) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -715,10 +867,11 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
     double2* s_stage = reinterpret_cast<double2*>(s_red + n_acc * 32);   // [W][32 records][3]
     int* s_ok = reinterpret_cast<int*>(s_stage + W * 96);     // [32]
+    double* s_in = reinterpret_cast<double*>(s_ok + 32);       // [n_in][32]: the kernel inputs of this CTA's chains
     __shared__ int s_last;
 
 #ifdef OCTO_TIMING
-    long long tm[10]; int tmi = 0;
+    long long tm[12]; int tmi = 0;
 #define OCTO_TICK() do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tm[tmi++] = (long long)t_; } } while (0)
 #else
 #define OCTO_TICK() do {} while (0)
@@ -732,24 +885,40 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     const int64_t chain0 = (int64_t)blockIdx.x * ncol;
     auto chain_of = [&](int col) { const int64_t cc = chain0 + col; return cc < n_chains ? cc : n_chains - 1; };
 
-    if (threadIdx.x < 32) s_ok[threadIdx.x] = 1;
+    if (threadIdx.x < 32) {
+        s_ok[threadIdx.x] = 1;
+        if (P) param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi).flags[threadIdx.x] = 0;
+    }
     double* acc = s_acc + w * n_acc * 32;
 #pragma unroll 4
     for (int s = 0; s < n_acc; ++s) acc[s * 32 + lane] = 0.0;
     __syncthreads();
 
-    // ---- prologue phase 1: finiteness of every input (logdensitymodel.jl:120-124) and the per-planet tasks,
-    //      spread over all threads as (column, task) items
+    // ---- inputs of this CTA's chains into shared memory, with the finiteness check of logdensitymodel.jl:120-124;
+    //      with a parameterisation `in` is θ_t and the inputs are derived here (param_forward)
+    ParamSmem PS;
+    if (P) {
+        PS = param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi);
+        param_forward(*P, m, in, chain_of(lane), ld, s_in, PS, s_ok, w, W, lane);
+    } else {
 #pragma unroll 1
-    for (int it = threadIdx.x; it < ncol * m.n_in; it += W * 32) {
-        const int col = it % ncol, k = it / ncol;
-        if (!isfinite(in[chain_of(col) + (int64_t)k * ld])) s_ok[col] = 0;
+        for (int it = threadIdx.x; it < ncol * m.n_in; it += W * 32) {
+            const int col = it % ncol, k = it / ncol;
+            const double v = in[chain_of(col) + (int64_t)k * ld];
+            s_in[it] = v;
+            if (!isfinite(v)) s_ok[col] = 0;
+        }
     }
+    OCTO_TICK();
+    // ---- prologue phase 1: the per-planet tasks, spread over all threads as (column, task) items.  Without a
+    //      parameterisation they read global memory themselves (no barrier between the staging loop and this one:
+    //      the load latency overlaps the first, cold pass through the task code)
 #pragma unroll 1
     for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
         const int col = it % ncol, task = it / ncol;
-        if (!prologue_task(m, task / 5, task % 5, in, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col))
-            s_ok[col] = 0;
+        const bool ok = P ? prologue_task(m, task / 5, task % 5, s_in, col, 32, s_const + (task / 5) * PC_COUNT * 32, col)
+                          : prologue_task(m, task / 5, task % 5, in, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col);
+        if (!ok) s_ok[col] = 0;
     }
     __syncthreads();
     // ---- phase 2: Thiele-Innes / RV products
@@ -761,7 +930,6 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 
     {
         // ---- this warp's contiguous range of the concatenated epoch list
-        const int64_t c = chain_of(lane);
         const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
         // contiguous range of the COST-weighted epoch list (an RV+jitter epoch costs ~1.8 lean astrometry epochs)
         const double w_lo = m.wtot * (double)u / (double)U, w_hi = (u + 1 == U) ? 2.0 * m.wtot + 1.0 : m.wtot * (double)(u + 1) / (double)U;
@@ -771,7 +939,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             const int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
             const int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
             if (k0 >= k1) continue;
-            run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, in, c, ld, lane);
+            run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane);
         }
     }
     __syncthreads();
@@ -806,8 +974,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         OCTO_TICK();
 #ifdef OCTO_TIMING
         if (!s_last && threadIdx.x == 0 && blockIdx.x == 0)
-            printf("cta(0,%d) ns: start %lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld\n", blockIdx.y,
-                   tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4]);
+            printf("cta(0,%d) ns: start %lld inputs +%lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld\n", blockIdx.y,
+                   tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[6] - tm[5]);
 #endif
         if (!s_last) return;
         __threadfence();
@@ -849,7 +1017,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     __syncthreads();
     if (m.has_margin) {
-        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, in, chain_of(lane), ld, lane);
+        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, s_in, lane, 32, lane);
         __syncthreads();
     }
     if (GRAD) {
@@ -858,7 +1026,15 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
         const bool active = chain0 + lane < n_chains;
-        if (active) ll_out[chain0 + lane] = s_ok[lane] ? s_red[lane] + m.const_ll : -CUDART_INF;
+        const double llv = s_ok[lane] ? s_red[lane] + m.const_ll : -CUDART_INF;
+        if (!P) {
+            if (active) ll_out[chain0 + lane] = llv;
+        } else {                                               // log posterior (logdensitymodel.jl:110-146)
+            const int fl = PS.flags[lane];
+            const bool ok = (fl & 4) && isfinite(llv);
+            if (active) ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? PS.lp[lane] + (PS.extra[lane] + llv) : -CUDART_INF);
+            PS.flags[lane] = fl | (ok ? 8 : 0);
+        }
     }
     if (GRAD) {
         __syncthreads();
@@ -866,18 +1042,22 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #pragma unroll 1
         for (int idx = threadIdx.x; idx < ng; idx += W * 32) {
             const int l = idx & 31;
-            if (chain0 + l < n_chains) {
-                const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
-                g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
-            }
+            const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
+            if (P) PS.aux[idx] = (PS.flags[l] & 8) ? v : 0.0;
+            else if (chain0 + l < n_chains) g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
+        }
+        if (P) {
+            __syncthreads();
+            OCTO_TICK();
+            param_backward(*P, m, s_in, PS, g_out, chain0, n_chains, ldg, w, W, lane);
         }
     }
 #ifdef OCTO_TIMING
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         OCTO_TICK();
-        printf("cta(0,%d) LAST ns: start %lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld reads +%lld epilogue +%lld end %lld\n",
+        printf("cta(0,%d) LAST ns: start %lld inputs +%lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld reads +%lld epilogue +%lld (+%lld) end %lld\n",
                blockIdx.y, tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4],
-               tm[6] - tm[5], tm[7] - tm[6], tm[7] % 100000000);
+               tm[6] - tm[5], tm[7] - tm[6], tm[8] - tm[7], P && GRAD ? tm[9] - tm[8] : 0LL, tm[tmi - 1] % 100000000);
     }
 #endif
 }
@@ -901,42 +1081,46 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
     return cudaGetLastError();
 }
 
-size_t octo_smem_bytes(const DevModel& m, int W) {
+// D > 0: with the fused parameterisation stage (D parameters, T θ_at_epoch_to_tperi definitions)
+size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
     size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * m.n_in * 32;      // the epilogue's gradient parts reuse the accumulator area
-    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32;
+    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
+    if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32;
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 
 template <bool GRAD, int NPT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
-                            cudaStream_t st) {
+                            const DevParam* d_param, cudaStream_t st) {
     k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
-                                                                        d_tickets);
+                                                                        d_tickets, d_param);
     return cudaGetLastError();
 }
 
-// opt every instantiation in to `smem_bytes` of dynamic shared memory (once per context)
-cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, int W, int* ctas_per_sm) {
+// opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
+// contexts of different sizes must not shrink it for each other), and report the resident CTAs per SM of the
+// gradient kernel this model dispatches to (drives the launch geometry)
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
     cudaError_t e;
 #define OCTO_ATTR(G, N)                                                                                            \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);   \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);   \
     if (e != cudaSuccess) return e
     OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
 #undef OCTO_ATTR
-    // resident CTAs per SM of the gradient kernel this model dispatches to (drives the launch geometry)
     if (m.n_planets == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 1>, W * 32, smem_bytes);
     else if (m.n_planets == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 2>, W * 32, smem_bytes);
     else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 4>, W * 32, smem_bytes);
     return e;
 }
 
+// d_param != nullptr: d_in is θ_t [n x D], d_ll receives the log posterior and d_g its gradient [n x D]
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
-                        unsigned int* d_tickets, cudaStream_t st) {
+                        unsigned int* d_tickets, const DevParam* d_param, cudaStream_t st) {
 #define OCTO_DISPATCH(NPT)                                                                                        \
-    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, st)         \
-                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, st)
+    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, st)         \
+                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, st)
     if (m.n_planets == 1) { OCTO_DISPATCH(1); }
     if (m.n_planets == 2) { OCTO_DISPATCH(2); }
     OCTO_DISPATCH(4);

@@ -1,0 +1,186 @@
+// octo_param_dev.cuh — device functions of the standard parameterisation, shared by the fused
+// path inside K1 (octo_kernels.cu) and the stand-alone K0 kernels (octo_param.cu) so that both produce the same bits.
+//
+// Reference semantics: invlink (src/variables.jl:1449-1493), logpdf_with_trans / ln_prior_transformed
+// (src/variables.jl:1205-1369), UniformCircular + UnitLengthPrior (src/variables.jl:279-323),
+// θ_at_epoch_to_tperi (src/parameterizations.jl:6-69).  Bijectors/Distributions formulas: SURVEY.md Appendix B.
+#pragma once
+#include <cfloat>
+#include <math_constants.h>
+
+#include "octo_internal.h"
+
+namespace octo_param_dev {
+
+constexpr double kTwoPi = 6.283185307179586477, kPi = 3.14159265358979323846, kHalfLog2Pi = 0.91893853320467274178;
+
+struct PriorEval { double x, dxdy, L, dLdx; };
+
+// x = invlink(y); L = logpdf_with_trans(prior, x); derivatives for the chain rule.
+// pc = per-prior constants prepared by octo_set_parameterization (DevParam::pc):
+//   [0] lower bound, [1] upper bound (±Inf when open), [2] the constant part of the log density
+//   (Normal: -log σ - ½log 2π - log(Φ(β)-Φ(α)); Uniform: -log(b-a); LogUniform: -log(log(b/a))), [3] 1/(hi-lo), [4] 1/σ
+static __device__ __noinline__ PriorEval prior_eval(int family, double mu, const double* __restrict__ pc, double y) {
+    PriorEval r;
+    const double lo = pc[0], hi = pc[1];
+    const bool lb = isfinite(lo), ub = isfinite(hi);
+    double J = 0.0, dJ = 0.0;
+    if (lb && ub) {                                   // scaled logit, clamped (Bijectors TruncatedBijector)
+        const double s = 1.0 / (1.0 + exp(-y));
+        double x = (hi - lo) * s + lo;
+        r.dxdy = (hi - lo) * s * (1.0 - s);
+        if (x < lo) { x = lo; r.dxdy = 0.0; }
+        if (x > hi) { x = hi; r.dxdy = 0.0; }
+        r.x = x;
+        const double a = x - lo, b = hi - x, ab = a * b;
+        J = log(ab * pc[3]); dJ = (b - a) / ab;
+    } else if (lb) {
+        const double ex = exp(y);
+        r.x = ex + lo; r.dxdy = ex;
+        const double a = r.x - lo;
+        J = log(a); dJ = 1.0 / a;
+    } else if (ub) {
+        const double ex = exp(y);
+        r.x = hi - ex; r.dxdy = -ex;
+        const double b = hi - r.x;
+        J = log(b); dJ = -1.0 / b;
+    } else { r.x = y; r.dxdy = 1.0; }
+    const double x = r.x;
+    double lp = pc[2], dlp = 0.0;
+    switch (family) {
+        case OCTO_PRIOR_NORMAL: case OCTO_PRIOR_TRUNCNORMAL: {
+            const double z = (x - mu) * pc[4];
+            lp = -0.5 * z * z + pc[2]; dlp = -z * pc[4]; break;
+        }
+        case OCTO_PRIOR_LOGUNIFORM: lp = -log(x) + pc[2]; dlp = -1.0 / x; break;
+        case OCTO_PRIOR_SINE: { double sn, cs; sincos(x, &sn, &cs); lp = log(sn * 0.5); dlp = cs / sn; break; }
+        default: break;                               // Uniform: the constant
+    }
+    r.L = lp + J; r.dLdx = dlp + dJ;
+    return r;
+}
+
+// UniformCircular (src/variables.jl:279-299): angle = atan(y, x) / 2π · domain, plus the UnitLengthPrior term
+// LogNormal(0, 0.1) on √(x² + y²) (src/variables.jl:301-323)
+__device__ __forceinline__ void circ_forward(double x, double y, double domain, double& v, double& ext) {
+    v = atan2(y, x) * (domain / kTwoPi);
+    const double lr = 0.5 * log(x * x + y * y);
+    ext = -lr - (-2.302585092994045684 /* log 0.1 */) - kHalfLog2Pi - lr * lr * 50.0;
+}
+// gk = ∂/∂angle; returns the contributions to ∂/∂x and ∂/∂y (angle and UnitLengthPrior)
+__device__ __forceinline__ void circ_backward(double x, double y, double domain, double gk, double& gx, double& gy) {
+    const double r2 = x * x + y * y, ir2 = 1.0 / r2, sc = gk * (domain / kTwoPi);
+    const double dfdlr = -1.0 - 0.5 * log(r2) * 100.0;
+    gx = (dfdlr * x - sc * y) * ir2;
+    gy = (dfdlr * y + sc * x) * ir2;
+}
+
+// ordered sum of the prior terms with the reference's "healing" of a non-finite term (variables.jl:1229-1236: the
+// sum stops at the first non-finite term and becomes -floatmax), the UnitLengthPrior terms, validity of the inputs.
+// flags: 1 = every θ_t finite, 2 = healed, 4 = valid.  `stride` = distance between consecutive entries.
+__device__ __forceinline__ int prior_sums(const double* L, const double* aux, const double* in, int D, int n_in, int stride,
+                                          bool finite_in, double& lp, double& extra) {
+    double sum = 0.0, ex = 0.0;
+    bool bad = false, valid = true;
+#pragma unroll 4
+    for (int j = 0; j < D; ++j) { const double v = L[j * stride]; bad = bad || !isfinite(v); sum += v; }
+#pragma unroll 4
+    for (int k = 0; k < n_in; ++k) { ex += aux[k * stride]; valid = valid && isfinite(in[k * stride]); }
+    lp = bad ? -DBL_MAX : sum; extra = ex;
+    return (finite_in ? 1 : 0) | (bad ? 2 : 0) | ((valid && finite_in) ? 4 : 0);
+}
+
+// d lp / dθ_j before the invlink factor: the prior term (0 when healed) plus, last input first, every input that
+// reads parameter j (DevParam::gat).  aux = ∂ll/∂inputs after the θ_at_epoch_to_tperi contributions were folded in.
+__device__ __forceinline__ double param_gather(const DevParam& P, int j, double g0, const double* th, const double* aux,
+                                               int stride) {
+    double g = g0;
+#pragma unroll 1
+    for (int it = P.gat_start[j]; it < P.gat_start[j + 1]; ++it) {
+        const int k = P.gat[it] & 255, role = P.gat[it] >> 8;
+        if (role == 0) g += aux[k * stride];
+        else {
+            const OctoInputDef& d = P.defs[k];
+            double gx, gy;
+            circ_backward(th[d.a[0] * stride], th[d.a[1] * stride], d.value, aux[k * stride], gx, gy);
+            if (role & 1) g += gx;
+            if (role & 2) g += gy;
+        }
+    }
+    return g;
+}
+
+// θ_at_epoch_to_tperi, src/parameterizations.jl:6-69, Campbell branch.
+//   arguments in definition order arg[0..6] = (θ, M, e, a, i, ω, Ω); trig[0..7] = sin, cos of θ, i, ω, Ω (computed by
+//   the caller, possibly on other warps).  sin/cos of the true anomaly come from (xr, yr) / r instead of
+//   sincos(atan2(yr, xr)).  Returns tp and the mean anomaly MA (the one transcendental the reverse pass needs).
+struct TperiMid { double A, B, F, G, idet, xr, yr, ir, snu, cnu, s, u, v, iw2, q, p; };
+__device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const double* arg, const double* trig) {
+    const double st = trig[0], ct = trig[1], ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
+    const double M = arg[1], e = arg[2], a = arg[3];
+    TperiMid m;
+    m.A = cW * cw - sW * sw * ci; m.B = sW * cw + cW * sw * ci;
+    m.F = -(cW * sw) - sW * cw * ci; m.G = -(sW * sw) + cW * cw * ci;
+    m.idet = 1.0 / (m.A * m.G - m.F * m.B);
+    m.xr = (m.G * ct - m.F * st) * m.idet; m.yr = (m.A * st - m.B * ct) * m.idet;
+    m.ir = rsqrt(m.xr * m.xr + m.yr * m.yr);
+    m.snu = m.yr * m.ir; m.cnu = m.xr * m.ir;
+    m.s = sqrt(1.0 - e * e);
+    m.u = -(m.s * m.snu); m.v = -e - m.cnu;
+    m.iw2 = 1.0 / (e * m.cnu + 1.0);
+    m.q = e * m.s * m.snu * m.iw2;
+    m.p = sqrt(a * a * a / M) * (c.kepler_year_days / c.year2day);      // period [yr]
+    return m;
+}
+static __device__ __noinline__ double tperi_value(const OctoConstants& c, double t_ref, const double* arg, const double* trig,
+                                              double* MA_out) {
+    const TperiMid m = tperi_mid(c, arg, trig);
+    const double MA = atan2(m.u, m.v) + kPi - m.q;
+    *MA_out = MA;
+    // n = 2π / period_yrs;  tp = t_ref - MA / n * year2day
+    return t_ref - MA * m.p * (c.year2day / kTwoPi);
+}
+// hand-derived reverse pass: grad[q] = ∂tp/∂arg[q].  Cheap arithmetic only (the forward intermediates are
+// recomputed, MA comes from the forward pass); this replaced 7 forward-mode dual evaluations whose code size made
+// the once-per-CTA reverse stage instruction-fetch bound.
+static __device__ __noinline__ void tperi_reverse(const OctoConstants& c, const double* arg, const double* trig, double MA,
+                                              double* grad) {
+    const double st = trig[0], ct = trig[1], si = trig[2], ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
+    const double M = arg[1], e = arg[2], a = arg[3];
+    const TperiMid m = tperi_mid(c, arg, trig);
+    const double cc = c.year2day / kTwoPi;
+    const double MAb = -m.p * cc, pb = -MA * cc;                 // tp = t_ref - MA p cc
+    const double g_a = pb * 1.5 * m.p / a, g_M = -pb * 0.5 * m.p / M;
+    // MA = atan2(u, v) + π - q
+    const double qb = -MAb;
+    const double w2b = -qb * m.q * m.iw2;                        // q = e s snu / w2, w2 = e cnu + 1
+    const double ih = 1.0 / (m.u * m.u + m.v * m.v);
+    const double ub = MAb * m.v * ih, vb = -MAb * m.u * ih;
+    double eb = qb * m.s * m.snu * m.iw2 + w2b * m.cnu - vb;
+    double sb = qb * e * m.snu * m.iw2 - ub * m.snu;
+    const double snub = qb * e * m.s * m.iw2 - ub * m.s;
+    const double cnub = w2b * e - vb;
+    eb += sb * (-e / m.s);                                       // s = sqrt(1 - e²)
+    // snu = yr / r, cnu = xr / r
+    const double dot = (snub * m.yr + cnub * m.xr) * m.ir * m.ir * m.ir;
+    const double xrb = cnub * m.ir - dot * m.xr, yrb = snub * m.ir - dot * m.yr;
+    // xr = (G ct - F st) / det, yr = (A st - B ct) / det, det = A G - F B
+    const double xd = xrb * m.idet, yd = yrb * m.idet;
+    const double detb = -(xd * m.xr + yd * m.yr);
+    const double Ab = yd * st + detb * m.G, Bb = -yd * ct - detb * m.F;
+    const double Fb = -xd * st - detb * m.B, Gb = xd * ct + detb * m.A;
+    const double stb = -xd * m.F + yd * m.A, ctb = xd * m.G - yd * m.B;
+    // A = cW cw - sW sw ci, B = sW cw + cW sw ci, F = -cW sw - sW cw ci, G = -sW sw + cW cw ci
+    const double cWb = Ab * cw + Bb * sw * ci - Fb * sw + Gb * cw * ci;
+    const double sWb = -Ab * sw * ci + Bb * cw - Fb * cw * ci - Gb * sw;
+    const double cwb = Ab * cW + Bb * sW - Fb * sW * ci + Gb * cW * ci;
+    const double swb = -Ab * sW * ci + Bb * cW * ci - Fb * cW - Gb * sW;
+    const double cib = -Ab * sW * sw + Bb * cW * sw - Fb * sW * cw + Gb * cW * cw;
+    grad[0] = stb * ct - ctb * st;                               // θ
+    grad[1] = g_M; grad[2] = eb; grad[3] = g_a;
+    grad[4] = -cib * si;                                         // i
+    grad[5] = swb * cw - cwb * sw;                               // ω
+    grad[6] = sWb * cW - cWb * sW;                               // Ω
+}
+
+}  // namespace octo_param_dev

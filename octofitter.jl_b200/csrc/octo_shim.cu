@@ -68,6 +68,10 @@ struct OctoCtx {
     // device-side parameterisation (N1)
     DevParam* d_param = nullptr;
     int param_D = 0;
+    bool param_fused = false;      // the parameterisation runs inside K1 (one launch) instead of K0f + K1 + K0b
+    size_t smem_fused = 0;
+    int ctas_per_sm_fused = 1;
+    size_t smem_optin = 0;
     // parallel tempering
     void* nccl_comm = nullptr;
     int pt_rank = 0, pt_world = 1, pt_local = 0;
@@ -162,18 +166,18 @@ void free_ws(Workspace* w) {
 // grid: chain groups x epoch splits.  Small problems: as many splits as fill the resident CTA slots exactly once
 // (an integral number of waves, never below min_slice epochs per warp).  Large problems (>= 4 waves): ~32 epochs
 // per warp so the per-CTA prologue/epilogue is amortised and the hardware CTA scheduler balances the tail.
-LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
+LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
     LaunchGeom g;
     const int W = ctx->warps;
     g.block = W * 32;
-    g.smem = ctx->smem;
+    g.smem = fused ? ctx->smem_fused : ctx->smem;
     const int64_t E = ctx->m.n_epochs;
     g.gx = (int)((n_chains + 31) / 32);
     const int min_slice = ctx->slice_override > 0 ? ctx->slice_override : OCTO_MIN_SLICE;
     int64_t max_gy = E / ((int64_t)min_slice * W);
     if (max_gy < 1) max_gy = 1;
     if (max_gy > 65535) max_gy = 65535;
-    const int64_t resident = (int64_t)ctx->n_sm * ctx->ctas_per_sm;
+    const int64_t resident = (int64_t)ctx->n_sm * (fused ? ctx->ctas_per_sm_fused : ctx->ctas_per_sm);
     int64_t gy_fill = (resident + g.gx - 1) / g.gx;
     if (gy_fill > max_gy) gy_fill = max_gy;
     int64_t gy = gy_fill;
@@ -204,9 +208,10 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains) {
     return g;
 }
 
+// d_param != nullptr: fused parameterisation — d_in is θ_t, d_ll / d_g receive the log posterior and its gradient
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
-            int64_t ldg, cudaStream_t st) {
-    LaunchGeom g = geometry(ctx, n);
+            int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr) {
+    LaunchGeom g = geometry(ctx, n, d_param != nullptr);
     if (g.gy > 1) {
         size_t need = (size_t)g.gx * g.gy * ctx->m.n_acc * 32;
         if (int rc = ensure(&w->d_partial, &w->cap_partial, need)) return rc;
@@ -215,55 +220,83 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
             CU(cudaMemsetAsync(w->d_tickets, 0, w->cap_tickets * sizeof(unsigned int), st));
         }
     }
-    cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, st);
+    cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return OCTO_OK;
 }
 
-int run_host(OctoCtx* ctx, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g) {
+int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
+                    double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st) {
+    if (ctx->param_fused)     // one launch: θ_t -> inputs in K1's prologue, ∂/∂θ_t in its epilogue; no workspace
+        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param);
+    const int n_in = ctx->m.n_in;
+    double* d_in = d_work;                      // [n x n_in]
+    double* d_ll = d_work + (size_t)n * n_in;   // [n]
+    double* d_gin = d_ll + n;                   // [n x n_in]
+    double* d_save = d_gin + (size_t)n * n_in;  // [n x (3D + 3)]
+    cudaError_t e = octo_param_forward(ctx->d_param, ctx->param_D, ctx->m, d_theta, n, ld, d_in, d_save, st);
+    if (e != cudaSuccess) return fail_cuda(e, "k_param_forward");
+    if (int rc = enqueue(ctx, w, d_g_t != nullptr, d_in, n, n, d_ll, d_g_t ? d_gin : nullptr, n, st)) return rc;
+    e = octo_param_backward(ctx->d_param, ctx->param_D, ctx->m, n, d_in, d_save, d_ll, d_gin, d_lp, d_g_t, ldg, st);
+    if (e != cudaSuccess) return fail_cuda(e, "k_param_backward");
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    return OCTO_OK;
+}
+
+// One synchronous evaluation with host buffers.  post = false: `in` are the kernel inputs [n x n_in] (octo_logp[_grad]);
+// post = true: θ_t [n x D] -> log posterior (octo_logpost_grad).  Gradient columns = input columns in both cases.
+int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (post && !ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
     if (n == 0) return OCTO_OK;
     if (!in || !ll || (grad && !g) || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = lease(ctx);
     if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
-    const int n_in = ctx->m.n_in;
+    const int n_in = ctx->m.n_in, nc = post ? ctx->param_D : n_in;
     const size_t col = (size_t)n * sizeof(double), pitch = (size_t)ld * sizeof(double);
     // buffers from octo_alloc_pinned are copied directly; anything else is staged through pinned memory
-    const bool pin_in = is_pinned(in, pitch * (n_in - 1) + col);
-    const bool pin_out = is_pinned(ll, col) && (!grad || is_pinned(g, pitch * (n_in - 1) + col));
+    const bool pin_in = is_pinned(in, pitch * (nc - 1) + col);
+    const bool pin_out = is_pinned(ll, col) && (!grad || is_pinned(g, pitch * (nc - 1) + col));
     int rc = OCTO_OK;
     do {
-        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * n_in))) break;
-        if ((rc = ensure(&w->d_ll, &w->cap_ll, (size_t)n * (n_in + 1)))) break;      // [ll | g] contiguous
-        // pinned outputs: the kernel's epilogue stores ll / g rows straight into the caller's page-locked
+        double*& d_x = post ? w->d_theta : w->d_in;
+        size_t& cap_x = post ? w->cap_theta : w->cap_in;
+        double*& d_y = post ? w->d_post : w->d_ll;
+        size_t& cap_y = post ? w->cap_post : w->cap_ll;
+        if ((rc = ensure(&d_x, &cap_x, (size_t)n * nc))) break;
+        if ((rc = ensure(&d_y, &cap_y, (size_t)n * (nc + 1)))) break;                // [ll | g] contiguous
+        if (post && !ctx->param_fused && (rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * nc + 3)))) break;
+        // pinned outputs: the last kernel stores ll / g rows straight into the caller's page-locked
         // buffers over PCIe (UVA: host pointer == device pointer) — no D2H copy launches at all
         const bool direct_out = pin_out;
-        double* d_ll = direct_out ? ll : w->d_ll;
-        double* d_g = direct_out ? g : w->d_ll + n;
+        double* d_ll = direct_out ? ll : d_y;
+        double* d_g = direct_out ? g : d_y + n;
         const int64_t ldg = direct_out ? ld : n;
         cudaError_t e;
         if (pin_in) {
-            e = (ld == n) ? cudaMemcpyAsync(w->d_in, in, col * n_in, cudaMemcpyHostToDevice, w->stream)
-                          : cudaMemcpy2DAsync(w->d_in, col, in, pitch, col, n_in, cudaMemcpyHostToDevice, w->stream);
+            e = (ld == n) ? cudaMemcpyAsync(d_x, in, col * nc, cudaMemcpyHostToDevice, w->stream)
+                          : cudaMemcpy2DAsync(d_x, col, in, pitch, col, nc, cudaMemcpyHostToDevice, w->stream);
         } else {
-            if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * n_in, true))) break;
-            for (int k = 0; k < n_in; ++k) memcpy(w->h_in + (size_t)k * n, in + (size_t)k * ld, col);
-            e = cudaMemcpyAsync(w->d_in, w->h_in, col * n_in, cudaMemcpyHostToDevice, w->stream);
+            if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * nc, true))) break;
+            for (int k = 0; k < nc; ++k) memcpy(w->h_in + (size_t)k * n, in + (size_t)k * ld, col);
+            e = cudaMemcpyAsync(d_x, w->h_in, col * nc, cudaMemcpyHostToDevice, w->stream);
         }
         if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if ((rc = enqueue(ctx, w, grad, w->d_in, n, n, d_ll, grad ? d_g : nullptr, ldg, w->stream))) break;
+        if (post) rc = logpost_enqueue(ctx, w, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->d_in, w->stream);
+        else rc = enqueue(ctx, w, grad, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->stream);
+        if (rc) break;
         if (!direct_out) {
-            if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (n_in + 1), true))) break;
-            e = cudaMemcpyAsync(w->h_out, d_ll, col * (grad ? n_in + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
+            if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (nc + 1), true))) break;
+            e = cudaMemcpyAsync(w->h_out, d_ll, col * (grad ? nc + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
             if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
         }
         e = cudaStreamSynchronize(w->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
         if (!direct_out) {
             memcpy(ll, w->h_out, col);
-            if (grad) for (int k = 0; k < n_in; ++k) memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
+            if (grad) for (int k = 0; k < nc; ++k) memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
         }
     } while (0);
     release(ctx, w);
@@ -416,7 +449,8 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (prop.major < 10) { delete ctx; return fail(OCTO_ERR_CUDA, "libocto_b200 is built for sm_100a only"); }
     ctx->device = device; ctx->n_sm = prop.multiProcessorCount;
     ctx->warps = OCTO_WARPS;
-    while (ctx->warps > 1 && octo_smem_bytes(m, ctx->warps) > (size_t)prop.sharedMemPerBlockOptin) ctx->warps /= 2;
+    ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin - 1024;      // room for the kernels' static shared memory
+    while (ctx->warps > 1 && octo_smem_bytes(m, ctx->warps) > ctx->smem_optin) ctx->warps /= 2;
     ctx->smem = octo_smem_bytes(m, ctx->warps);
     if (ctx->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete ctx; return fail(OCTO_ERR_ARG, "model too large: accumulator slots exceed shared memory");
@@ -428,7 +462,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
     m.tab = ctx->d_tables;
     int occ = 0;
-    ce = octo_kernels_init(m, ctx->smem, ctx->warps, &occ);
+    ce = octo_kernels_init(m, ctx->smem, ctx->smem_optin, ctx->warps, &occ);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
     ctx->ctas_per_sm = occ > 0 ? occ : 1;
     if (const char* s = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, atoi(s));
@@ -448,8 +482,8 @@ void octo_destroy(OctoCtx* ctx) {
     delete ctx;
 }
 
-int octo_logp(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll) { return run_host(ctx, false, in, n, ld, ll, nullptr); }
-int octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll, double* g) { return run_host(ctx, true, in, n, ld, ll, g); }
+int octo_logp(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll) { return run_host(ctx, false, false, in, n, ld, ll, nullptr); }
+int octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll, double* g) { return run_host(ctx, false, true, in, n, ld, ll, g); }
 
 int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g, void* stream) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
@@ -474,12 +508,23 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
     for (int j = 0; j < D; ++j) {
         const OctoPrior& pr = priors[j];
         P.priors[j] = pr;
-        P.lognorm[j] = 0.0;
+        double* pc = P.pc[j];                      // lo, hi, constant part of the log density, 1/(hi-lo), 1/σ
+        const double kHalfLog2Pi = 0.91893853320467274178, kPi = 3.14159265358979323846;
+        pc[0] = -INFINITY; pc[1] = INFINITY; pc[2] = 0.0; pc[3] = 0.0; pc[4] = 0.0;
         switch (pr.family) {
-            case OCTO_PRIOR_NORMAL: if (!(pr.p[1] > 0)) return fail(OCTO_ERR_ARG, "Normal: sigma must be > 0"); break;
-            case OCTO_PRIOR_UNIFORM: if (!(pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "Uniform: a < b required"); break;
-            case OCTO_PRIOR_LOGUNIFORM: if (!(0 < pr.p[0] && pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "LogUniform: 0 < a < b required"); break;
-            case OCTO_PRIOR_SINE: break;
+            case OCTO_PRIOR_NORMAL:
+                if (!(pr.p[1] > 0)) return fail(OCTO_ERR_ARG, "Normal: sigma must be > 0");
+                pc[2] = -std::log(pr.p[1]) - kHalfLog2Pi; pc[4] = 1.0 / pr.p[1];
+                break;
+            case OCTO_PRIOR_UNIFORM:
+                if (!(pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "Uniform: a < b required");
+                pc[0] = pr.p[0]; pc[1] = pr.p[1]; pc[2] = -std::log(pr.p[1] - pr.p[0]);
+                break;
+            case OCTO_PRIOR_LOGUNIFORM:
+                if (!(0 < pr.p[0] && pr.p[0] < pr.p[1])) return fail(OCTO_ERR_ARG, "LogUniform: 0 < a < b required");
+                pc[0] = pr.p[0]; pc[1] = pr.p[1]; pc[2] = -std::log(std::log(pr.p[1] / pr.p[0]));
+                break;
+            case OCTO_PRIOR_SINE: pc[0] = 2.220446049250313e-16; pc[1] = kPi - 2.220446049250313e-16; break;
             case OCTO_PRIOR_TRUNCNORMAL: {
                 if (!(pr.p[1] > 0) || !(pr.p[2] < pr.p[3])) return fail(OCTO_ERR_ARG, "truncated Normal: sigma > 0, lower < upper required");
                 // log(Φ(β) - Φ(α)), on the side of the distribution that avoids cancellation
@@ -488,11 +533,13 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
                 const double b = std::isfinite(pr.p[3]) ? (pr.p[3] - mu) / sg : INFINITY;
                 const double tp = a > 0 ? 0.5 * (std::erfc(a * is2) - std::erfc(b * is2))
                                         : 0.5 * (std::erfc(-b * is2) - std::erfc(-a * is2));
-                P.lognorm[j] = std::log(tp);
+                pc[0] = pr.p[2]; pc[1] = pr.p[3];
+                pc[2] = -std::log(sg) - kHalfLog2Pi - std::log(tp); pc[4] = 1.0 / sg;
                 break;
             }
             default: return fail(OCTO_ERR_ARG, "unknown prior family");
         }
+        if (std::isfinite(pc[0]) && std::isfinite(pc[1])) pc[3] = 1.0 / (pc[1] - pc[0]);
     }
     for (int k = 0; k < n_in; ++k) {
         const OctoInputDef& d = defs[k];
@@ -509,76 +556,71 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
             default: return fail(OCTO_ERR_ARG, "unknown input definition");
         }
     }
+    // reverse map parameter -> inputs that read it, last input first (the order of the reference's reverse pass)
+    {
+        int n = 0;
+        for (int j = 0; j < D; ++j) {
+            P.gat_start[j] = (int16_t)n;
+            for (int k = n_in - 1; k >= 0; --k) {
+                const OctoInputDef& d = P.defs[k];
+                int role = -1;
+                if (d.op == OCTO_IN_PARAM && d.a[0] == j) role = 0;
+                else if (d.op == OCTO_IN_CIRC && (d.a[0] == j || d.a[1] == j)) role = (d.a[0] == j ? 1 : 0) | (d.a[1] == j ? 2 : 0);
+                if (role >= 0) P.gat[n++] = (int16_t)(k | (role << 8));
+            }
+        }
+        P.gat_start[D] = (int16_t)n;
+    }
+    // fused stage inside K1: needs every θ_at_epoch_to_tperi to depend on non-tperi inputs only (they are evaluated
+    // together), at most OCTO_PARAM_TPERI_MAX of them, and the extra shared memory; otherwise K0f + K1 + K0b
+    bool fusable = true;
+    P.n_tperi = 0;
+    for (int k = 0; k < n_in; ++k) {
+        if (P.defs[k].op != OCTO_IN_TPERI) continue;
+        for (int q = 0; q < 7; ++q) if (P.defs[P.defs[k].a[q]].op == OCTO_IN_TPERI) fusable = false;
+        if (P.n_tperi < OCTO_PARAM_TPERI_MAX) P.tperi_k[P.n_tperi] = k;
+        if (++P.n_tperi > OCTO_PARAM_TPERI_MAX) { fusable = false; P.n_tperi = OCTO_PARAM_TPERI_MAX; }
+    }
+    if (const char* e = getenv("OCTO_B200_FUSE_PARAM")) if (atoi(e) == 0) fusable = false;
     CU(cudaSetDevice(ctx->device));
+    const size_t smem_f = octo_smem_bytes(ctx->m, ctx->warps, D, P.n_tperi);
+    if (smem_f > ctx->smem_optin) fusable = false;
+    if (fusable) {
+        int occ = 0;
+        CU(octo_kernels_init(ctx->m, smem_f, ctx->smem_optin, ctx->warps, &occ));
+        if (occ < 1) fusable = false;
+        ctx->smem_fused = smem_f; ctx->ctas_per_sm_fused = occ > 0 ? occ : 1;
+        if (const char* e = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm_fused = std::max(1, atoi(e));
+    }
     CU(octo_param_init(D, n_in));
     if (!ctx->d_param) CU(cudaMalloc((void**)&ctx->d_param, sizeof(DevParam)));
     CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
     ctx->param_D = D;
+    ctx->param_fused = fusable;
     return OCTO_OK;
 }
 
 int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n) {
     if (!ctx || n < 0) return -1;
+    if (ctx->param_fused) return 0;            // one fused launch: nothing to hand from kernel to kernel
     return (int64_t)sizeof(double) * n * (2 * (int64_t)ctx->m.n_in + 1 + 3 * (int64_t)ctx->param_D + 3);
 }
 
-static int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
-                           double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st) {
-    const int n_in = ctx->m.n_in;
-    double* d_in = d_work;                      // [n x n_in]
-    double* d_ll = d_work + (size_t)n * n_in;   // [n]
-    double* d_gin = d_ll + n;                   // [n x n_in]
-    double* d_save = d_gin + (size_t)n * n_in;  // [n x (3D + 3)]
-    cudaError_t e = octo_param_forward(ctx->d_param, ctx->param_D, ctx->m, d_theta, n, ld, d_in, d_save, st);
-    if (e != cudaSuccess) return fail_cuda(e, "k_param_forward");
-    if (int rc = enqueue(ctx, w, d_g_t != nullptr, d_in, n, n, d_ll, d_g_t ? d_gin : nullptr, n, st)) return rc;
-    e = octo_param_backward(ctx->d_param, ctx->param_D, ctx->m, n, d_in, d_save, d_ll, d_gin, d_lp, d_g_t, ldg, st);
-    if (e != cudaSuccess) return fail_cuda(e, "k_param_backward");
-    ctx->launches.fetch_add(2, std::memory_order_relaxed);
-    return OCTO_OK;
-}
 
 int octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta, int64_t n, int64_t ld, double* d_lp, double* d_g_t,
                              void* d_work, void* stream) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
     if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
     if (n == 0) return OCTO_OK;
-    if (!d_theta || !d_lp || !d_work || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    if (!d_theta || !d_lp || (!d_work && !ctx->param_fused) || n < 0 || ld < n)
+        return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);
     return logpost_enqueue(ctx, w, d_theta, n, ld, d_lp, d_g_t, ld, (double*)d_work, (cudaStream_t)stream);
 }
 
 int octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* lp, double* g_t) {
-    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
-    if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
-    if (n == 0) return OCTO_OK;
-    if (!theta_t || !lp || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
-    CU(cudaSetDevice(ctx->device));
-    Workspace* w = lease(ctx);
-    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
-    const int D = ctx->param_D, n_in = ctx->m.n_in;
-    const size_t col = (size_t)n * sizeof(double);
-    int rc = OCTO_OK;
-    do {
-        if ((rc = ensure(&w->d_theta, &w->cap_theta, (size_t)n * D))) break;
-        if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * (D + 1)))) break;
-        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * D + 3)))) break;
-        if ((rc = ensure(&w->h_in, &w->cap_hin, (size_t)n * D, true))) break;
-        if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (D + 1), true))) break;
-        for (int k = 0; k < D; ++k) memcpy(w->h_in + (size_t)k * n, theta_t + (size_t)k * ld, col);
-        cudaError_t e = cudaMemcpyAsync(w->d_theta, w->h_in, col * D, cudaMemcpyHostToDevice, w->stream);
-        if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if ((rc = logpost_enqueue(ctx, w, w->d_theta, n, n, w->d_post, g_t ? w->d_post + n : nullptr, n, w->d_in, w->stream))) break;
-        e = cudaMemcpyAsync(w->h_out, w->d_post, col * (g_t ? D + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
-        if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
-        e = cudaStreamSynchronize(w->stream);
-        if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
-        memcpy(lp, w->h_out, col);
-        if (g_t) for (int k = 0; k < D; ++k) memcpy(g_t + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
-    } while (0);
-    release(ctx, w);
-    return rc;
+    return run_host(ctx, true, g_t != nullptr, theta_t, n, ld, lp, g_t);
 }
 
 int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {

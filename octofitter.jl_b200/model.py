@@ -516,10 +516,17 @@ class LogDensityModel:
         self._check(self._lib.octo_logpost_grad(self._h, th.ctypes.data, n, n, lp.ctypes.data, None))
         return lp[0] if single else lp
 
-    def ℓπcallback_grad(self, theta_t):
+    def ℓπcallback_grad(self, theta_t, out=None):
+        """(ℓπ, ∇ℓπ) of the unconstrained vector(s) θ_t, one fused launch.  out=(lp[n], g[n, D] column-major) reuses
+        buffers; with buffers from pinned_empty() the copies need no staging."""
         th, single = self._as_theta(theta_t)
         n = th.shape[0]
-        lp, g = np.empty(n), np.empty((n, self.D), order="F")
+        if out is None:
+            lp, g = np.empty(n), np.empty((n, self.D), order="F")
+        else:
+            lp, g = out
+            if lp.shape != (n,) or g.shape != (n, self.D) or not g.flags.f_contiguous:
+                raise ValueError("out must be (lp[n], g[n, D]) with g column-major")
         self._check(self._lib.octo_logpost_grad(self._h, th.ctypes.data, n, n, lp.ctypes.data, g.ctypes.data))
         return (lp[0], g[0]) if single else (lp, g)
 
@@ -610,3 +617,14 @@ class LogDensityModel:
         """Asynchronous launch on device-resident buffers (raw pointers, cudaStream_t handle)."""
         self._check(self._lib.octo_logp_grad_device(self._h, int(d_in), int(n_chains), int(ld), int(d_ll),
                                                     int(d_g) if d_g else None, int(stream) if stream else None))
+
+    def logpost_workspace_bytes(self, n_chains):
+        """Scratch the device entry point needs for n_chains (0 when the parameterisation is fused into the kernel)."""
+        return int(self._lib.octo_logpost_workspace(self._h, int(n_chains)))
+
+    def enqueue_logpost_device(self, d_theta_t, n_chains, ld, d_lp, d_g_t, d_work=0, stream=0):
+        """Asynchronous ℓπ(θ_t), ∇ℓπ(θ_t) on device-resident buffers (raw pointers, cudaStream_t handle)."""
+        self._check(self._lib.octo_logpost_grad_device(self._h, int(d_theta_t), int(n_chains), int(ld), int(d_lp),
+                                                       int(d_g_t) if d_g_t else None, int(d_work) if d_work else None,
+                                                       int(stream) if stream else None))
+

@@ -157,3 +157,89 @@ def test_batched_parallel_tempering_single_rank():
     assert res["swap_accept"].shape == (40, R - 1) and res["swap_accept"].sum() > 0
     assert np.all(np.isfinite(model.ℓπcallback(np.asfortranarray(res["theta"]))))
     model.close(); ref_model.close()
+
+
+@pytest.mark.parametrize("name", post_cases())
+def test_fused_parameterisation_equals_standalone_kernels(name, monkeypatch):
+    """The parameterisation fused into K1 (one launch) and the stand-alone K0 forward / backward kernels share their
+    device functions and summation orders: identical bits, for valid, invalid and "healed" chains alike."""
+    d, spec, consts = load_post(name)
+    rng = np.random.default_rng(21)
+    th = np.array(d["theta_t"])[None, :] + 0.1 * rng.standard_normal((131, spec.D))
+    th[5, 0] = np.nan; th[9, 1] = np.inf; th[11, :] = 40.0; th[12, :] = -745.0
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("OCTO_B200_FUSE_PARAM", mode)
+        lib, h = _model_from_golden(d, spec, consts)
+        n0 = lib.octo_kernel_launches(h)
+        lp, g = _logpost(lib, h, spec.D, th)
+        launches = lib.octo_kernel_launches(h) - n0
+        lpv, _ = _logpost(lib, h, spec.D, th, grad=False)
+        out[mode] = (lp, g, lpv, launches)
+        lib.octo_destroy(h)
+    assert out["1"][3] == 1 and out["0"][3] == 3
+    for a, b in zip(out["1"][:3], out["0"][:3]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(out["1"][0], out["1"][2], equal_nan=True)
+    assert np.isneginf(out["1"][0][[5, 9]]).all() and (out["1"][1][[5, 9]] == 0).all()
+
+
+def test_logpost_pinned_buffers_and_leading_dimension():
+    """octo_logpost_grad with octo_alloc_pinned buffers (direct copies, results written straight to host) and a
+    leading dimension larger than the batch gives the same bits as pageable arrays."""
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(4)
+    n, ld, D = 77, 96, spec.D
+    th = rng.normal(0, 0.8, (n, D))
+    th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(n)
+    lp0, g0 = model.ℓπcallback_grad(th)
+    thp = model.pinned_empty((ld, D)); thp[...] = 0.0; thp[:n] = th
+    lpp = model.pinned_empty(ld); gp = model.pinned_empty((ld, D)); gp[...] = 7.0
+    rc = model._lib.octo_logpost_grad(model._h, thp.ctypes.data, n, ld, lpp.ctypes.data, gp.ctypes.data)
+    assert rc == 0, model._lib.octo_last_error()
+    assert np.array_equal(lpp[:n], lp0) and np.array_equal(gp[:n], g0) and (gp[n:] == 7.0).all()
+
+
+def test_two_models_alive_with_different_shared_memory_sizes(oracle_lib):
+    """The dynamic shared-memory opt-in is a per-function attribute: a small model created after a large one must
+    not shrink it for the large one."""
+    import workloads
+    big, xb = workloads.many_planets(4, 64, seed=3)
+    small, xs = workloads.one_planet(20, 0, 64, seed=4)
+    mb = octo.LogDensityModel(big)
+    ms = octo.LogDensityModel(small)
+    for model, spec, x in ((mb, big, xb), (ms, small, xs), (mb, big, xb)):
+        ll, g = model.ln_like_and_gradient(x)
+        ll_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(x)
+        assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_logpost_device_entry_point(oracle_lib, monkeypatch, fuse):
+    """octo_logpost_grad_device on device-resident buffers and the caller's stream (torch tensors), both as the
+    fused single launch (no workspace) and as the three-launch fallback with a caller-provided workspace."""
+    import torch
+    monkeypatch.setenv("OCTO_B200_FUSE_PARAM", fuse)
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(12)
+    n, ld, D = 200, 256, spec.D
+    th = rng.normal(0, 0.8, (n, D))
+    th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(n)
+    d_th = torch.zeros((D, ld), dtype=torch.float64, device="cuda"); d_th[:, :n] = torch.from_numpy(th.T.copy()).cuda()
+    d_lp = torch.zeros(ld, dtype=torch.float64, device="cuda")
+    d_g = torch.full((D, ld), 7.0, dtype=torch.float64, device="cuda")
+    nbytes = model.logpost_workspace_bytes(n)
+    assert (nbytes == 0) == (fuse == "1")
+    d_work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(2):        # twice: tickets / partial buffers of the stream's workspace are reused
+            model.enqueue_logpost_device(d_th.data_ptr(), n, ld, d_lp.data_ptr(), d_g.data_ptr(),
+                                         d_work.data_ptr() if nbytes else 0, st.cuda_stream)
+    st.synchronize()
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    assert rel_err(d_lp[:n].cpu().numpy(), lp_o).max() < LOGP_RTOL
+    assert grad_err(d_g[:, :n].cpu().numpy().T, g_o).max() < GRAD_RTOL
+    assert (d_g[:, n:] == 7.0).all()
