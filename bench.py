@@ -301,7 +301,7 @@ def main():
                        "timing": "CUDA events around each step's single kernel on the launching stream; value = pairs / sum of event times"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read + write of this launch from the committed ncu capture (profiles/r01_ncu_summary.txt)
-                         "traffic": 491520, "peak_source": peak_how, "flop_per_pair": F_ALG,
+                         "traffic": 227072, "peak_source": peak_how, "flop_per_pair": F_ALG,
                          "executed": {"tflops": flops_per_launch(spec, n, F_EXEC) / (kern_ms * 1e-3) / 1e12,
                                       "flop_per_pair": F_EXEC, "how": "ncu SASS op counts, see profiles/"},
                          "kernel_ms": kern_ms, "kernel_ms_min": float(ms.min()),
