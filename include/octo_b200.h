@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define OCTO_ABI_VERSION 1
+#define OCTO_ABI_VERSION 2
 #define OCTO_MAX_PLANETS 4
 
 /* error codes */
@@ -204,6 +204,15 @@ int  octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n_chains, in
 int64_t octo_logpost_workspace(const OctoCtx* ctx, int64_t n_chains);
 int  octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta_t, int64_t n_chains, int64_t ld, double* d_lp,
                               double* d_g_t, void* d_work, void* stream);
+/* The likelihood part alone for a batch of θ_t: ln_like(system, arr2nt(invlink(θ_t))), UnitLengthPrior terms
+ * included, -Inf where it is not finite.  What `octofit_rejection` evaluates per prior draw
+ * (src/sampling.jl:168-279, _rejection_evaluate_likelihoods :261-270).  HOST buffers, value only. */
+int  octo_loglike_theta(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* ll);
+/* Per-epoch log-likelihoods of natural-space kernel inputs: out[chain + e * ldo] (e = 0 .. octo_total_epochs - 1, in
+ * the order the tables were passed to octo_create) is ln_like of the model reduced to that single epoch, i.e. one
+ * column per system of `generate_system_per_epoch` — the matrix `pointwise_like` builds
+ * (src/cross-validation.jl:6-49, 453-497).  HOST buffers; n_chains * epochs <= 2e9 and epochs <= 65535 per call. */
+int  octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, double* out, int64_t ldo);
 /* invlink only: natural-space parameters [n_chains x D] for a batch of θ_t (HOST buffers). */
 int  octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* theta_nat);
 

@@ -86,7 +86,8 @@ struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
-                        unsigned int* d_tickets, const DevParam* d_param, cudaStream_t stream);
+                        unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
+                        cudaStream_t stream);
 size_t octo_smem_bytes(const DevModel& m, int warps, int D = 0, int n_tperi = 0);
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);
@@ -95,6 +96,6 @@ cudaError_t octo_param_forward(const DevParam* d_param, int D, const DevModel& m
                                int64_t ld, double* d_in, double* d_save, cudaStream_t st);
 cudaError_t octo_param_backward(const DevParam* d_param, int D, const DevModel& m, int64_t n, const double* d_in,
                                 const double* d_save, const double* d_ll, const double* d_g_in, double* d_lp,
-                                double* d_g_t, int64_t ldg, cudaStream_t st);
+                                double* d_g_t, int64_t ldg, int post_mode, cudaStream_t st);
 cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,
                                cudaStream_t st);

@@ -597,7 +597,7 @@ constexpr int EPI_PARTS = 4;
 
 template <bool GRAD>
 __device__ __noinline__ void epilogue_margin(const DevModel& m, double* R, double* gp0, const double* __restrict__ in,
-                                             int64_t c, int64_t ld, int lane) {
+                                             int64_t c, int64_t ld, int lane, bool skip_empty) {
     double ll = 0.0;
 #pragma unroll 1
     for (int b = 0; b < m.n_blocks; ++b) {
@@ -606,6 +606,7 @@ __device__ __noinline__ void epilogue_margin(const DevModel& m, double* R, doubl
         const int s0 = B.slot_margin;
         const double A = R[(s0 + MA_A) * 32 + lane], S1 = R[(s0 + MA_S1) * 32 + lane];
         const double C = R[(s0 + MA_C) * 32 + lane], LG = R[(s0 + MA_LG) * 32 + lane];
+        if (skip_empty && A == 0.0) continue;          // pointwise mode: the epoch of this CTA is not in this table
         const double rbar = S1 / A;
         ll += -LG - C + S1 * rbar - log(A);            // rv-absolute-margin.jl:171-181 with B = -2 S1
         if (GRAD) {
@@ -857,7 +858,8 @@ template <bool GRAD, int NPT>
 __global__ void __launch_bounds__(WMAX * 32, OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
-              unsigned int* __restrict__ tickets, const DevParam* __restrict__ P) {
+              unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
+              const double* __restrict__ pw_const) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -936,8 +938,13 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #pragma unroll 1
         for (int b = 0; b < m.n_blocks; ++b) {
             const DevBlock& B = m.blocks[b];
-            const int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
-            const int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
+            int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
+            int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
+            if (pw_const) {      // pointwise mode: this CTA evaluates the single epoch blockIdx.y (warp 0)
+                const int ep = (int)blockIdx.y;
+                const bool mine = w == 0 && ep >= B.start && ep < B.start + B.n;
+                k0 = mine ? ep : 0; k1 = mine ? ep + 1 : 0;
+            }
             if (k0 >= k1) continue;
             run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane);
         }
@@ -958,7 +965,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 
     // ---- K2: combine the epoch splits of this chain group: partials through L2 + a ticket; the last CTA to
     //      arrive sums them in split order (run-to-run bit-reproducible)
-    if (gridDim.y > 1) {
+    if (gridDim.y > 1 && !pw_const) {
         double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
 #pragma unroll 2
         for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
@@ -1017,7 +1024,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     __syncthreads();
     if (m.has_margin) {
-        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, s_in, lane, 32, lane);
+        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, s_in, lane, 32, lane, pw_const != nullptr);
         __syncthreads();
     }
     if (GRAD) {
@@ -1026,13 +1033,17 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
         const bool active = chain0 + lane < n_chains;
-        const double llv = s_ok[lane] ? s_red[lane] + m.const_ll : -CUDART_INF;
+        const double cll = pw_const ? pw_const[blockIdx.y] : m.const_ll;
+        const double llv = s_ok[lane] ? s_red[lane] + cll : -CUDART_INF;
         if (!P) {
-            if (active) ll_out[chain0 + lane] = llv;
+            // pointwise mode: out[chain + epoch * ldg] = ln_like of the model reduced to that one epoch
+            if (active) ll_out[chain0 + lane + (pw_const ? (int64_t)blockIdx.y * ldg : 0)] = llv;
         } else {                                               // log posterior (logdensitymodel.jl:110-146)
             const int fl = PS.flags[lane];
             const bool ok = (fl & 4) && isfinite(llv);
-            if (active) ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? PS.lp[lane] + (PS.extra[lane] + llv) : -CUDART_INF);
+            // post_mode 1: the likelihood part alone, ln_like(system, arr2nt(θ)) incl. the UnitLengthPrior terms
+            const double like = PS.extra[lane] + llv;
+            if (active) ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? (post_mode == 1 ? like : PS.lp[lane] + like) : -CUDART_INF);
             PS.flags[lane] = fl | (ok ? 8 : 0);
         }
     }
@@ -1092,9 +1103,9 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
 template <bool GRAD, int NPT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
-                            const DevParam* d_param, cudaStream_t st) {
+                            const DevParam* d_param, int post_mode, const double* d_pw_const, cudaStream_t st) {
     k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
-                                                                        d_tickets, d_param);
+                                                                        d_tickets, d_param, post_mode, d_pw_const);
     return cudaGetLastError();
 }
 
@@ -1114,13 +1125,16 @@ cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_
     return e;
 }
 
-// d_param != nullptr: d_in is θ_t [n x D], d_ll receives the log posterior and d_g its gradient [n x D]
+// d_param != nullptr: d_in is θ_t [n x D], d_ll receives the log posterior (post_mode 1: its likelihood part) and d_g
+// its gradient [n x D].  d_pw_const != nullptr (value-only): pointwise mode, grid.y = epochs, d_ll is [n x E] with
+// leading dimension ldg.
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
-                        unsigned int* d_tickets, const DevParam* d_param, cudaStream_t st) {
+                        unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
+                        cudaStream_t st) {
 #define OCTO_DISPATCH(NPT)                                                                                        \
-    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, st)         \
-                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, st)
+    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st)         \
+                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st)
     if (m.n_planets == 1) { OCTO_DISPATCH(1); }
     if (m.n_planets == 2) { OCTO_DISPATCH(2); }
     OCTO_DISPATCH(4);

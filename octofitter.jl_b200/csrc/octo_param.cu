@@ -104,7 +104,8 @@ k_param_forward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMode
 __global__ void __launch_bounds__(SUB * CHAINS)
 k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevModel m, int64_t n,
                  const double* __restrict__ in_vals, const double* __restrict__ save, const double* __restrict__ ll,
-                 const double* __restrict__ g_in, double* __restrict__ lp_out, double* __restrict__ g_t, int64_t ldg) {
+                 const double* __restrict__ g_in, double* __restrict__ lp_out, double* __restrict__ g_t, int64_t ldg,
+                 int post_mode) {
     extern __shared__ double sm[];
     const DevParam& P = *Pp;
     const int D = P.D, n_in = P.n_in;
@@ -118,7 +119,10 @@ k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMod
     const bool finite_in = flags & 1, healed = flags & 2, valid = flags & 4;
     const double llc = ll[c];
     const bool ok = valid && isfinite(llc);
-    if (active && s == 0) lp_out[c] = !finite_in ? -CUDART_INF : (ok ? lp_prior + (extra + llc) : -CUDART_INF);
+    if (active && s == 0) {
+        const double like = extra + llc;               // post_mode 1: the likelihood part alone
+        lp_out[c] = !finite_in ? -CUDART_INF : (ok ? (post_mode == 1 ? like : lp_prior + like) : -CUDART_INF);
+    }
     if (!g_t) return;
     for (int j = s; j < D; j += SUB) {
         S.th[j] = save[c + (int64_t)j * n]; S.dxdy[j] = save[c + (int64_t)(D + j) * n];
@@ -173,9 +177,9 @@ cudaError_t octo_param_forward(const DevParam* d_param, int D, const DevModel& m
 }
 cudaError_t octo_param_backward(const DevParam* d_param, int D, const DevModel& m, int64_t n, const double* d_in,
                                 const double* d_save, const double* d_ll, const double* d_g_in, double* d_lp,
-                                double* d_g_t, int64_t ldg, cudaStream_t st) {
+                                double* d_g_t, int64_t ldg, int post_mode, cudaStream_t st) {
     k_param_backward<<<(unsigned)((n + CHAINS - 1) / CHAINS), SUB * CHAINS, param_smem(D, m.n_in), st>>>(
-        d_param, m, n, d_in, d_save, d_ll, d_g_in, d_lp, d_g_t, ldg);
+        d_param, m, n, d_in, d_save, d_ll, d_g_in, d_lp, d_g_t, ldg, post_mode);
     return cudaGetLastError();
 }
 cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,

@@ -58,6 +58,7 @@ struct OctoCtx {
     int n_sm = 148;
     size_t smem = 0;
     double* d_tables = nullptr;
+    double* d_pw_const = nullptr;   // per-epoch normalisation constants (pointwise mode)
     std::mutex mu;
     std::vector<Workspace*> pool;                                  // host-buffer calls: leased per call
     std::vector<std::pair<cudaStream_t, Workspace*>> stream_ws;    // device-buffer calls: one per caller stream
@@ -209,10 +210,16 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
 }
 
 // d_param != nullptr: fused parameterisation — d_in is θ_t, d_ll / d_g receive the log posterior and its gradient
+// post_mode 1 (with d_param): likelihood part only.  pointwise: value-only, one CTA row per epoch, d_ll is [n x E] (ld ldg).
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
-            int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr) {
+            int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false) {
     LaunchGeom g = geometry(ctx, n, d_param != nullptr);
-    if (g.gy > 1) {
+    if (pointwise) {
+        if (ctx->m.n_epochs > 65535) return fail(OCTO_ERR_ARG, "pointwise evaluation supports at most 65535 epochs per call");
+        const int W = ctx->warps > 4 ? 4 : ctx->warps;        // one warp does the epoch; the others only help the prologue
+        g.block = W * 32; g.gy = (int)ctx->m.n_epochs; g.smem = octo_smem_bytes(ctx->m, W);
+    }
+    if (g.gy > 1 && !pointwise) {
         size_t need = (size_t)g.gx * g.gy * ctx->m.n_acc * 32;
         if (int rc = ensure(&w->d_partial, &w->cap_partial, need)) return rc;
         if ((size_t)g.gx > w->cap_tickets) {
@@ -220,16 +227,17 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
             CU(cudaMemsetAsync(w->d_tickets, 0, w->cap_tickets * sizeof(unsigned int), st));
         }
     }
-    cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, st);
+    cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, post_mode,
+                                pointwise ? ctx->d_pw_const : nullptr, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return OCTO_OK;
 }
 
 int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
-                    double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st) {
+                    double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st, int post_mode = 0) {
     if (ctx->param_fused)     // one launch: θ_t -> inputs in K1's prologue, ∂/∂θ_t in its epilogue; no workspace
-        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param);
+        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param, post_mode);
     const int n_in = ctx->m.n_in;
     double* d_in = d_work;                      // [n x n_in]
     double* d_ll = d_work + (size_t)n * n_in;   // [n]
@@ -238,7 +246,7 @@ int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n
     cudaError_t e = octo_param_forward(ctx->d_param, ctx->param_D, ctx->m, d_theta, n, ld, d_in, d_save, st);
     if (e != cudaSuccess) return fail_cuda(e, "k_param_forward");
     if (int rc = enqueue(ctx, w, d_g_t != nullptr, d_in, n, n, d_ll, d_g_t ? d_gin : nullptr, n, st)) return rc;
-    e = octo_param_backward(ctx->d_param, ctx->param_D, ctx->m, n, d_in, d_save, d_ll, d_gin, d_lp, d_g_t, ldg, st);
+    e = octo_param_backward(ctx->d_param, ctx->param_D, ctx->m, n, d_in, d_save, d_ll, d_gin, d_lp, d_g_t, ldg, post_mode, st);
     if (e != cudaSuccess) return fail_cuda(e, "k_param_backward");
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     return OCTO_OK;
@@ -246,7 +254,9 @@ int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n
 
 // One synchronous evaluation with host buffers.  post = false: `in` are the kernel inputs [n x n_in] (octo_logp[_grad]);
 // post = true: θ_t [n x D] -> log posterior (octo_logpost_grad).  Gradient columns = input columns in both cases.
-int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g) {
+// post_mode 1 (post only, value-only): the likelihood part, ln_like(system, arr2nt(invlink(θ_t))).
+int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g,
+             int post_mode = 0) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
     if (post && !ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
     if (n == 0) return OCTO_OK;
@@ -284,7 +294,7 @@ int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, in
             e = cudaMemcpyAsync(d_x, w->h_in, col * nc, cudaMemcpyHostToDevice, w->stream);
         }
         if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if (post) rc = logpost_enqueue(ctx, w, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->d_in, w->stream);
+        if (post) rc = logpost_enqueue(ctx, w, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->d_in, w->stream, post_mode);
         else rc = enqueue(ctx, w, grad, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->stream);
         if (rc) break;
         if (!direct_out) {
@@ -411,6 +421,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     struct Col { double* b; double& operator[](size_t o) const { return b[6 * o]; } };   // AoS record field view
     const Col t{T.data()}, y1{T.data() + 1}, c1{T.data() + 2}, y2{T.data() + 3}, c2{T.data() + 4}, c3{T.data() + 5};
     long double cll = 0.0L;
+    std::vector<double> pwc((size_t)(E > 0 ? E : 1), 0.0);        // the same normalisation terms, per epoch (pointwise mode)
     const long double log2pi = 1.8378770664093454835606594728112353L;
     for (int b = 0; b < n_blocks; ++b) {
         const OctoObsBlock& B = blocks[b];
@@ -432,11 +443,15 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
                 if (!D.jit) {
                     const double om = 1.0 - cor * cor;
                     c1[o] = 1.0 / (s1 * s1 * om); c3[o] = 1.0 / (s2 * s2 * om); c2[o] = -cor / (s1 * s2 * om);
-                    cll += -log2pi - 0.5L * std::log((long double)s1 * s1 * s2 * s2 * om);
+                    const long double term = -log2pi - 0.5L * std::log((long double)s1 * s1 * s2 * s2 * om);
+                    cll += term; pwc[o] = (double)term;
                 } else { c1[o] = s1 * s1; c2[o] = s2 * s2; c3[o] = cor; }
             } else {
                 const double s = B.s1[k];
-                if (!D.jit) { c1[o] = 1.0 / (s * s); cll += -0.5L * (log2pi + std::log((long double)s * s)); }
+                if (!D.jit) {
+                    const long double term = -0.5L * (log2pi + std::log((long double)s * s));
+                    c1[o] = 1.0 / (s * s); cll += term; pwc[o] = (double)term;
+                }
                 else c1[o] = s * s;
             }
         }
@@ -461,6 +476,9 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     ce = cudaMemcpy(ctx->d_tables, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "upload tables"); }
     m.tab = ctx->d_tables;
+    ce = cudaMalloc((void**)&ctx->d_pw_const, pwc.size() * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMemcpy(ctx->d_pw_const, pwc.data(), pwc.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(ctx->d_tables); if (ctx->d_pw_const) cudaFree(ctx->d_pw_const); delete ctx; return fail_cuda(ce, "upload per-epoch constants"); }
     int occ = 0;
     ce = octo_kernels_init(m, ctx->smem, ctx->smem_optin, ctx->warps, &occ);
     if (ce != cudaSuccess) { cudaFree(ctx->d_tables); delete ctx; return fail_cuda(ce, "cudaFuncSetAttribute"); }
@@ -478,6 +496,7 @@ void octo_destroy(OctoCtx* ctx) {
     for (Workspace* w : ctx->pool) free_ws(w);
     for (auto& kv : ctx->stream_ws) free_ws(kv.second);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_pw_const) cudaFree(ctx->d_pw_const);
     if (ctx->d_param) cudaFree(ctx->d_param);
     delete ctx;
 }
@@ -621,6 +640,38 @@ int octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta, int64_t n, int
 
 int octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* lp, double* g_t) {
     return run_host(ctx, true, g_t != nullptr, theta_t, n, ld, lp, g_t);
+}
+
+int octo_loglike_theta(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* ll) {
+    return run_host(ctx, true, false, theta_t, n, ld, ll, nullptr, 1);
+}
+
+// per-epoch log-likelihoods: out[chain + e * ldo] = ln_like of the model reduced to epoch e alone (e in the order of
+// the concatenated tables).  What `pointwise_like` (src/cross-validation.jl:6-49) evaluates per posterior sample.
+int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* out, int64_t ldo) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    const int64_t E = ctx->m.n_epochs;
+    if (n == 0 || E == 0) return OCTO_OK;
+    if (!in || !out || n < 0 || ld < n || ldo < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
+    if ((double)n * (double)E > 2.0e9) return fail(OCTO_ERR_ARG, "pointwise output too large: split the batch of chains");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = lease(ctx);
+    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
+    const int n_in = ctx->m.n_in;
+    const size_t col = (size_t)n * sizeof(double);
+    int rc = OCTO_OK;
+    do {
+        if ((rc = ensure(&w->d_in, &w->cap_in, (size_t)n * n_in))) break;
+        if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * E))) break;
+        cudaError_t e = cudaMemcpy2DAsync(w->d_in, col, in, (size_t)ld * sizeof(double), col, n_in, cudaMemcpyHostToDevice, w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
+        if ((rc = enqueue(ctx, w, false, w->d_in, n, n, w->d_post, nullptr, n, w->stream, nullptr, 0, true))) break;
+        e = cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), w->d_post, col, col, (size_t)E, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "pointwise evaluation"); break; }
+    } while (0);
+    release(ctx, w);
+    return rc;
 }
 
 int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {

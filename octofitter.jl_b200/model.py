@@ -618,6 +618,41 @@ class LogDensityModel:
         self._check(self._lib.octo_logp_grad_device(self._h, int(d_in), int(n_chains), int(ld), int(d_ll),
                                                     int(d_g) if d_g else None, int(stream) if stream else None))
 
+    def ln_like_of_theta(self, theta_t):
+        """ln_like(system, arr2nt(invlink(θ_t))) alone (UnitLengthPrior terms included), -Inf where not finite: what
+        `octofit_rejection` evaluates per prior draw (src/sampling.jl:261-270).  One fused launch, value only."""
+        th, single = self._as_theta(theta_t)
+        n = th.shape[0]
+        ll = np.empty(n)
+        self._check(self._lib.octo_loglike_theta(self._h, th.ctypes.data, n, n, ll.ctypes.data))
+        return ll[0] if single else ll
+
+    def pointwise_like(self, theta, batch=4096):
+        """(LL_out[n_samples, n_epochs], epochs) as `pointwise_like(model, chain)` builds them
+        (src/cross-validation.jl:6-49): column e is ln_like of the system reduced to its e-th epoch alone, epochs
+        ordered like `generate_system_per_epoch` (:453-497) — system-level tables first, then the planets' tables.
+        `theta` are natural-space kernel inputs, one row per posterior sample."""
+        x, single = self._as_in(theta)
+        n, E = x.shape[0], self.total_epochs
+        out = np.empty((n, E), order="F")
+        for lo in range(0, n, batch):
+            xb = np.asfortranarray(x[lo:lo + batch])
+            ob = np.empty((xb.shape[0], E), order="F")
+            self._check(self._lib.octo_logp_pointwise(self._h, xb.ctypes.data, xb.shape[0], xb.shape[0], ob.ctypes.data, xb.shape[0]))
+            out[lo:lo + batch] = ob
+        # kernel order = planet tables then system tables (the order ln_like sums them); reference order = system first
+        blocks, start, order, epochs = self.spec.block_dicts, 0, [], []
+        spans = []
+        for b in blocks:
+            spans.append((b["planet"] < 0, start, len(b["epoch"]), b["epoch"]))
+            start += len(b["epoch"])
+        for system_level in (True, False):
+            for is_sys, s0, cnt, ep in spans:
+                if is_sys == system_level:
+                    order.extend(range(s0, s0 + cnt)); epochs.extend(ep)
+        out = out[:, order]
+        return (out[0] if single else out), np.asarray(epochs, dtype=np.float64)
+
     def logpost_workspace_bytes(self, n_chains):
         """Scratch the device entry point needs for n_chains (0 when the parameterisation is fused into the kernel)."""
         return int(self._lib.octo_logpost_workspace(self._h, int(n_chains)))

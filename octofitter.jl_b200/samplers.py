@@ -98,3 +98,35 @@ def batched_parallel_tempering(model, model_ref_logp, pt, theta0, n_rounds, *, s
         th[accept] = q[accept]; lr = np.where(accept, lrq, lr); lt = np.where(accept, ltq, lt)
         swaps.append(pt.swap_round(lr, lt))
     return {"theta": th, "swap_accept": np.array(swaps)}
+
+
+def octofit_rejection(model, rng=None, *, draws=100_000, batch=65536, verbosity=0):
+    """Rejection sampling from the prior, batched on the device (octofit_rejection, src/sampling.jl:168-258).
+
+    Draw `draws` samples from the priors, evaluate ln_like for all of them (`octo_loglike_theta`, one fused launch per
+    batch instead of one CPU call per draw), accept draw i with probability exp(ll_i - max ll).  Returns a dict with
+    the accepted natural-space samples (`theta`, [n_accepted, D]), their `loglike` and `logpost`, and the run
+    statistics the reference stores in the chain info (`draws`, `n_accepted`, `acceptance_rate`)."""
+    rng = np.random.default_rng() if rng is None else rng
+    theta = model.sample_priors(rng, draws)
+    theta_t = model.link(theta)
+    ll = np.empty(draws)
+    for lo in range(0, draws, batch):
+        ll[lo:lo + batch] = model.ln_like_of_theta(theta_t[lo:lo + batch])
+    ll[~np.isfinite(ll)] = -np.inf
+    max_ll = ll.max()
+    if not np.isfinite(max_ll):
+        raise RuntimeError(f"All {draws} prior samples produced non-finite log-likelihoods. Check your model and priors.")
+    u = rng.random(draws)
+    accepted = np.flatnonzero((ll > -np.inf) & (u < np.exp(ll - max_ll)))
+    if accepted.size == 0:
+        raise RuntimeError(f"No samples were accepted out of {draws} draws. The posterior may be extremely concentrated "
+                           "relative to the prior. Consider increasing `draws` or using a different sampler.")
+    rate = accepted.size / draws
+    if verbosity >= 1 and rate < 0.001:
+        import warnings
+        warnings.warn(f"Very low acceptance rate ({100 * rate:.2g}%). Consider HMC for more efficient sampling.")
+    return {"theta": theta[accepted], "theta_t": theta_t[accepted], "loglike": ll[accepted],
+            "logpost": model.ℓπcallback(theta_t[accepted]), "names": model.spec.theta_names,
+            "info": {"sampler": "rejection", "draws": draws, "n_accepted": int(accepted.size), "acceptance_rate": rate}}
+

@@ -142,6 +142,21 @@ int octo_oracle_logpost(const OctoConstants* c, const OctoLayout* L, const OctoO
     return OCTO_OK;
 }
 
+// ln_like(system, arr2nt(invlink(θ_t))) alone, -Inf where not finite (octofit_rejection, src/sampling.jl:261-270)
+int octo_oracle_loglike_theta(const OctoConstants* c, const OctoLayout* L, const OctoObsBlock* blocks, int n_blocks,
+                              const OctoPrior* priors, int D, const OctoInputDef* defs, const double* theta_t, int64_t n,
+                              int64_t ld, double* ll, int n_threads) {
+    if (int rc = validate(L, blocks, n_blocks)) return rc;
+    if (D < 1 || D > 48) { g_err = "oracle logpost supports 1 <= D <= 48"; return OCTO_ERR_ARG; }
+    parallel_chains(n, n_threads, [&](int64_t ch) {
+        double X[48];
+        for (int k = 0; k < D; ++k) X[k] = theta_t[ch + k * ld];
+        const double v = logpost_chain<double>(*c, *L, blocks, n_blocks, priors, D, defs, X, true);
+        ll[ch] = std::isfinite(v) ? v : -std::numeric_limits<double>::infinity();
+    });
+    return OCTO_OK;
+}
+
 int octo_oracle_invlink(const OctoPrior* priors, int D, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {
     for (int64_t ch = 0; ch < n; ++ch)
         for (int k = 0; k < D; ++k) theta_nat[ch + k * ld] = prior_invlink<double>(priors[k], theta_t[ch + k * ld]);

@@ -105,7 +105,7 @@ inline T theta_at_epoch_to_tperi(const OctoConstants& c, const T& theta, double 
 // ℓπcallback(θ_t) for the standard model families (src/logdensitymodel.jl:110-146)
 template <class T>
 inline T logpost_chain(const OctoConstants& c, const OctoLayout& L, const OctoObsBlock* blocks, int n_blocks,
-                       const OctoPrior* priors, int D, const OctoInputDef* defs, const T* theta_t) {
+                       const OctoPrior* priors, int D, const OctoInputDef* defs, const T* theta_t, bool like_only = false) {
     const double ninf = -std::numeric_limits<double>::infinity();
     for (int j = 0; j < D; ++j) if (!std::isfinite(value(theta_t[j]))) return T(ninf);      // :120-124
     std::vector<T> th(D), in(L.n_in);
@@ -133,8 +133,10 @@ inline T logpost_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
         }
     }
     // ln_prior_transformed (:128), with the reference's "healing" of a non-finite term (variables.jl:1229-1236)
+    // like_only: what octofit_rejection evaluates per prior draw — ln_like(system, arr2nt(θ)) alone
+    // (src/sampling.jl:261-270); the UnitLengthPrior terms are part of ln_like in the reference
     T lp(0.0);
-    for (int j = 0; j < D; ++j) {
+    for (int j = 0; j < D && !like_only; ++j) {
         T p = logpdf_with_trans(priors[j], th[j]);
         if (!std::isfinite(value(p))) { lp = T(-std::numeric_limits<double>::max()); goto like; }
         lp += p;

@@ -78,6 +78,22 @@ def logpost(spec, consts, theta_t, grad=True, threads=1):
     return (lp, g) if grad else lp
 
 
+def loglike_theta(spec, consts, theta_t, threads=1):
+    """ln_like(system, arr2nt(invlink(θ_t))) of a parameterised ModelSpec on the CPU oracle (rejection sampler)."""
+    L = lib()
+    L.octo_oracle_loglike_theta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+    th = np.asfortranarray(np.atleast_2d(np.asarray(theta_t, dtype=np.float64)))
+    n, D = th.shape
+    assert D == spec.D
+    ll = np.empty(n)
+    rc = L.octo_oracle_loglike_theta(C.addressof(consts), C.addressof(spec.packed.layout), spec.packed.blocks,
+                                     spec.packed.n_blocks, spec.priors, D, spec.defs, th.ctypes.data, n, n, ll.ctypes.data, threads)
+    if rc:
+        raise RuntimeError(L.octo_oracle_last_error().decode())
+    return ll
+
+
 def invlink(spec, theta_t):
     L = lib()
     L.octo_oracle_invlink.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]

@@ -243,3 +243,36 @@ def test_logpost_device_entry_point(oracle_lib, monkeypatch, fuse):
     assert rel_err(d_lp[:n].cpu().numpy(), lp_o).max() < LOGP_RTOL
     assert grad_err(d_g[:, :n].cpu().numpy().T, g_o).max() < GRAD_RTOL
     assert (d_g[:, n:] == 7.0).all()
+
+
+def test_loglike_of_theta_and_rejection_sampler(oracle_lib, monkeypatch):
+    """octo_loglike_theta (the likelihood part of the fused launch) against the oracle, fused and stand-alone, and
+    the batched rejection sampler built on it (octofit_rejection, src/sampling.jl:168-258)."""
+    spec = octo.ModelSpec(reference_test_system())
+    rng = np.random.default_rng(31)
+    th = rng.normal(0, 0.8, (150, spec.D))
+    th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(150)
+    th[3, 2] = np.nan
+    ll_o = oracle_lib.loglike_theta(spec, octo.default_constants(), th, threads=4)
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("OCTO_B200_FUSE_PARAM", fuse)
+        model = octo.LogDensityModel(spec)
+        res[fuse] = model.ln_like_of_theta(th)
+        assert np.isneginf(res[fuse][3]) and np.isneginf(ll_o[3])
+        fin = np.isfinite(ll_o)
+        assert rel_err(res[fuse][fin], ll_o[fin]).max() < LOGP_RTOL
+        # lp = prior part + likelihood part
+        lp = model.ℓπcallback(th)
+        assert np.all(lp[fin] <= res[fuse][fin] + 200.0)
+    assert np.array_equal(res["1"], res["0"], equal_nan=True)
+    monkeypatch.setenv("OCTO_B200_FUSE_PARAM", "1")
+    model = octo.LogDensityModel(spec)
+    out = octo.octofit_rejection(model, np.random.default_rng(5), draws=200_000, batch=50_000)
+    info = out["info"]
+    assert info["draws"] == 200_000 and info["n_accepted"] == len(out["loglike"]) >= 1
+    assert out["theta"].shape == (info["n_accepted"], spec.D)
+    # accepted draws: the oracle agrees on their likelihood, and logpost is what ℓπcallback returns for them
+    ll_acc = oracle_lib.loglike_theta(spec, octo.default_constants(), out["theta_t"], threads=4)
+    assert rel_err(out["loglike"], ll_acc).max() < 1e-9
+    assert np.array_equal(out["logpost"], model.ℓπcallback(out["theta_t"]))

@@ -343,3 +343,51 @@ def test_plain_c_consumer(oracle_lib, tmp_path):
     x = np.array([d["x"], [v * (1.0 if k == 7 else 1.01) for k, v in enumerate(d["x"])]])
     ll_o, g_o = oracle_lib.Oracle(packed, consts).logp_grad(x)
     assert rel_err(vals[:, 0], ll_o).max() < LOGP_RTOL and grad_err(vals[:, 1:], g_o).max() < GRAD_RTOL
+
+
+def _single_epoch_model(spec, e):
+    """The packed model reduced to epoch e of the concatenated tables (other tables empty), as
+    generate_system_per_epoch (src/cross-validation.jl:453-497) does with likeobj_from_epoch_subset."""
+    blocks, start = [], 0
+    for b in spec.block_dicts:
+        n = len(b["epoch"])
+        sel = [e - start] if start <= e < start + n else []
+        nb = dict(b)
+        for k in ("epoch", "y1", "y2", "s1", "s2", "cor"):
+            nb[k] = None if b.get(k) is None else np.asarray(b[k])[sel]
+        blocks.append(nb)
+        start += n
+    blocks = [b for b in blocks if len(b["epoch"])]
+    return octo.pack(spec.layout_dict, blocks)
+
+
+@pytest.mark.parametrize("which", ["two_planet", "many_planets"])
+def test_pointwise_like_matches_single_epoch_models(oracle_lib, which):
+    """octo_logp_pointwise: column e equals the oracle's ln_like of the model reduced to epoch e alone, for every
+    observation kind (incl. the marginalised RV formula on one epoch); the columns of additive kinds sum to ln_like."""
+    import workloads
+    if which == "two_planet":
+        spec, x = workloads.two_planet(24, seed=3, n_b=9, n_c=7, n_rv=8)
+    else:
+        spec, x = workloads.many_planets(3, 24, seed=5, n_ep=4)
+    model = octo.LogDensityModel(spec)
+    x[2, spec.layout_dict["planets"][0]["e"]] = 1.5          # invalid chain: -Inf in every column
+    E = model.total_epochs
+    out = np.empty((x.shape[0], E), order="F")
+    xf = np.asfortranarray(x)
+    rc = model._lib.octo_logp_pointwise(model._h, xf.ctypes.data, x.shape[0], x.shape[0], out.ctypes.data, x.shape[0])
+    assert rc == 0, model._lib.octo_last_error()
+    consts = octo.default_constants()
+    for e in range(E):
+        ll_o = oracle_lib.Oracle(_single_epoch_model(spec, e), consts).logp(x)
+        assert np.isneginf(out[2, e]) and np.isneginf(ll_o[2])
+        ok = np.arange(x.shape[0]) != 2
+        assert rel_err(out[ok, e], ll_o[ok]).max() < LOGP_RTOL, (which, e)
+    has_margin = any(b["kind"] == octo.KIND_RV_STAR_MARGIN for b in spec.block_dicts)
+    if not has_margin:
+        assert rel_err(out[ok].sum(axis=1), model.ln_like(x)[ok]).max() < 1e-12
+    # host mirror: reference column order (system-level tables first) and the matching epoch vector
+    LL, epochs = model.pointwise_like(x)
+    assert LL.shape == (x.shape[0], E) and epochs.shape == (E,)
+    n_sys = sum(len(b["epoch"]) for b in spec.block_dicts if b["planet"] < 0)
+    assert np.array_equal(LL[:, :n_sys], out[:, E - n_sys:]) and np.array_equal(LL[:, n_sys:], out[:, :E - n_sys])
