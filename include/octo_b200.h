@@ -109,6 +109,10 @@ typedef struct OctoObsBlock {
     int32_t idx_platescale;
     int32_t idx_northangle;
     int32_t idx_offset;
+    int32_t obs_prior;     /* 1 (astrometry kinds only): the table is wrapped in ObsPriorAstromONeil2019 — on top of
+                            * the table's ln_like add 2 log( Σ_epochs |3M(e+cosE) + 2(-2+e²+e cosE) sinE| · cbrt(P)/√(1-e²) )
+                            * for the observed planet (src/likelihoods/prior-observable.jl:78-137) */
+    int32_t reserved;
 } OctoObsBlock;
 
 /*

@@ -9,7 +9,7 @@ from ._abi import (OctoConstants, OctoLayout, OctoObsBlock, OctoPrior, OctoInput
                    EXPORTED_SYMBOLS, LIB_PATH,
                    KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL)
 from .model import (Normal, Uniform, LogUniform, Sine, truncated, UniformCircular, θ_at_epoch_to_tperi,
-                    theta_at_epoch_to_tperi, Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, StarAbsoluteRVObs,
+                    theta_at_epoch_to_tperi, Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, ObsPriorAstromONeil2019, StarAbsoluteRVObs,
                     StarAbsoluteRVLikelihood, MarginalizedStarAbsoluteRVObs, MarginalizedStarAbsoluteRVLikelihood,
                     PlanetRelativeRVObs, PlanetRelativeRVLikelihood, Planet, System, ModelSpec, LogDensityModel, OctoError)
 from .pt import ParallelTempering

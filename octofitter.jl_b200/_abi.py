@@ -35,7 +35,7 @@ class OctoObsBlock(C.Structure):
     _fields_ = [("kind", C.c_int32), ("planet", C.c_int32), ("n_epochs", C.c_int32), ("has_cor", C.c_int32),
                 ("epoch", _pd), ("y1", _pd), ("y2", _pd), ("s1", _pd), ("s2", _pd), ("cor", _pd),
                 ("idx_jitter", C.c_int32), ("idx_platescale", C.c_int32),
-                ("idx_northangle", C.c_int32), ("idx_offset", C.c_int32)]
+                ("idx_northangle", C.c_int32), ("idx_offset", C.c_int32), ("obs_prior", C.c_int32), ("reserved", C.c_int32)]
 
 
 _i4 = C.c_int32 * OCTO_MAX_PLANETS
@@ -106,7 +106,7 @@ def pack(layout_dict: dict, block_dicts: list) -> PackedModel:
             _dptr(cols["epoch"]), _dptr(cols["y1"]), _dptr(cols["y2"]), _dptr(cols["s1"]), _dptr(cols["s2"]),
             _dptr(cols["cor"]),
             int(bd.get("idx_jitter", -1)), int(bd.get("idx_platescale", -1)),
-            int(bd.get("idx_northangle", -1)), int(bd.get("idx_offset", -1))))
+            int(bd.get("idx_northangle", -1)), int(bd.get("idx_offset", -1)), int(bd.get("obs_prior", 0)), 0))
     return PackedModel(L, blocks, keep)
 
 

@@ -33,6 +33,8 @@ enum PlanetAcc { PA_Bh = 0, PA_Gs, PA_Ah, PA_Fs, PA_Pc, PA_Ps, PA_e, PA_S0, PA_S
 // extra accumulators of one marginalised-RV table (rv-absolute-margin.jl:161-181)
 enum MarginAcc { MA_A = 0, MA_S1, MA_C, MA_LG, MA_R2, MA_R1, MA_Q, MA_COUNT };   // then 5 V-slots per planet
 enum { MV_Pc = 0, MV_Ps, MV_e, MV_S0, MV_S1, MV_mu, MV_COUNT };
+// accumulators of an astrometry table wrapped in ObsPriorAstromONeil2019: S = Σ|f|, then Σ sign(f) ∂f/∂(MA, MA·dt, e)
+enum ObsPriorAcc { OP_S = 0, OP_Q0, OP_Q1, OP_Qe, OP_COUNT };
 
 struct DevBlock {
     int32_t kind, planet, start, n;          // epoch range [start, start+n) in the concatenated tables
@@ -40,7 +42,7 @@ struct DevBlock {
     int32_t idx_jitter, idx_platescale, idx_northangle, idx_offset;
     int32_t slot_jitter, slot_platescale, slot_northangle, slot_offset;   // accumulator slots (or -1)
     int32_t slot_margin;                      // first of the margin accumulators (kind 3) or -1
-    int32_t pad;
+    int32_t slot_obsprior;                    // first of the 4 observable-prior accumulators (OP_*) or -1
     double wgt, cum;                          // relative cost of one epoch of this table; Σ n*wgt of the tables before it
 };
 
@@ -51,7 +53,7 @@ struct DevModel {
     double wtot;             // Σ n*wgt over all tables: warps split this, not the raw epoch count
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
-    int32_t has_margin, pad0;    // any marginalised-RV table (its epilogue fold needs an extra barrier)
+    int32_t has_margin, pad0;    // any marginalised-RV or observable-prior table (their epilogue fold needs an extra barrier)
     int64_t n_epochs;
     int32_t idx_plx[OCTO_MAX_PLANETS], idx_a[OCTO_MAX_PLANETS], idx_e[OCTO_MAX_PLANETS], idx_i[OCTO_MAX_PLANETS],
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],

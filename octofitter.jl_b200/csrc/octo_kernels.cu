@@ -124,13 +124,14 @@ __device__ __forceinline__ void sincos_any(double x, double& s, double& c) {   /
 //  * sin/cos of E = E1 + d5 come from rotating sincos(E1) by d5 (three Taylor terms, exact to 1e-19):
 //    one sincos per solve instead of two.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt, double& sE, double& cE) {
+__device__ __forceinline__ void kepler_sincos(const Orb& o, double t, double& dt, double& sE, double& cE, double* M_out = nullptr) {
     dt = t - o.tp;
     const double MA = o.nd * dt;
     const double k = fma(MA, kc.inv_two_pi, kc.magic) - kc.magic;     // rint(MA / 2pi)
     double M = fma(-k, kc.two_pi1, MA);
     M = fma(-k, kc.two_pi2, M);
     M = fma(-k, kc.two_pi3, M);
+    if (M_out) *M_out = M;                                            // reduced mean anomaly = E - e sin E
     // ---- starter, FP32
     const float Mf = (float)M, ef = o.ef, omef = o.omef;
     const float alpha = fmaf(o.ca1f, (float)kPi - fabsf(Mf), (float)kA0);      // eq 20
@@ -224,6 +225,9 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
     const double j2 = jit * jit;
 
     double ll = 0.0, g_jit = 0.0, g_ps = 0.0, g_na = 0.0;
+    // ObsPriorAstromONeil2019 wrapper (generic path only): Σ|f| and Σ sign(f) ∂f/∂(MA, MA·dt, e) of the observed planet
+    const bool obsprior = (MODE == 2) && B.slot_obsprior >= 0;
+    double op_S = 0.0, op_Q0 = 0.0, op_Q1 = 0.0, op_Qe = 0.0;
     double L[NPT][7];
 #pragma unroll
     for (int u = 0; u < NPT; ++u)
@@ -248,10 +252,11 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
         const double2 ra0 = stage[3 * j], ra1 = stage[3 * j + 1], ra2 = stage[3 * j + 2];
         const double t = ra0.x, y1 = ra0.y, e1 = ra1.x, y2 = ra1.y, e2 = ra2.x, e3 = ra2.y;
         double sE[NPT], cE[NPT], dt[NPT];
-        double ra = 0.0, dec = 0.0;
+        double ra = 0.0, dec = 0.0, Mred = 0.0;
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
-            kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
+            if (MODE == 2 && u == 0) kepler_sincos(orb[u], t, dt[u], sE[u], cE[u], &Mred);
+            else kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
             const double X = cE[u] - orb[u].e;
             const double ra_u = fma(X, Bh[u], sE[u] * Gs[u]);
             const double dec_u = fma(X, Ah[u], sE[u] * Fs[u]);
@@ -291,6 +296,23 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
         }
         const double q1 = fma(w11, r1, w12 * r2), q2 = fma(w12, r1, w22 * r2);
         ll = fma(kc.mhalf, fma(r1, q1, r2 * q2), ll);
+        if (obsprior) {       // f = 3M(e + cos E) + 2(-2 + e² + e cos E) sin E,  M = meananom = E - e sin E
+            const double e = orb[0].e, sn = sE[0], cs = cE[0];
+            const double t2 = fma(e, cs, fma(e, e, -2.0));
+            const double fo = fma(3.0 * Mred, e + cs, 2.0 * t2 * sn);
+            op_S += fabs(fo);
+            if (GRAD) {
+                const double sg = fo < 0.0 ? -1.0 : 1.0;
+                const double D1m = fma(-e, cs, kc.one), rD = rcp_nr(D1m);
+                // ∂f/∂E at fixed e (dM/dE = 1 - e cos E) and ∂f/∂e at fixed E (∂M/∂e = -sin E)
+                const double dfdE = 3.0 * D1m * (e + cs) - 3.0 * Mred * sn - 2.0 * e * sn * sn + 2.0 * t2 * cs;
+                const double dfde = -3.0 * sn * (e + cs) + 3.0 * Mred + 2.0 * fma(2.0, e, cs) * sn;
+                const double gM = sg * dfdE * rD;              // dE/dMA = 1 / (1 - e cos E)
+                op_Q0 += gM;
+                op_Q1 = fma(gM, dt[0], op_Q1);
+                op_Qe += fma(gM, sn, sg * dfde);               // dE/de = sin E / (1 - e cos E)
+            }
+        }
         if (GRAD) {
             double gr, gd;
             if (pasep) {
@@ -326,6 +348,13 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
     }
     }
     acc_add(acc, 0, lane, ll);
+    if (obsprior) {
+        acc_add(acc, B.slot_obsprior + OP_S, lane, op_S);
+        if (GRAD) {
+            acc_add(acc, B.slot_obsprior + OP_Q0, lane, op_Q0); acc_add(acc, B.slot_obsprior + OP_Q1, lane, op_Q1);
+            acc_add(acc, B.slot_obsprior + OP_Qe, lane, op_Qe);
+        }
+    }
     if (GRAD) {
         if (!LEAN) {
             if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
@@ -596,12 +625,32 @@ __device__ __noinline__ void prologue_products(double* sc, int lane) {
 constexpr int EPI_PARTS = 4;
 
 template <bool GRAD>
-__device__ __noinline__ void epilogue_margin(const DevModel& m, double* R, double* gp0, const double* __restrict__ in,
-                                             int64_t c, int64_t ld, int lane, bool skip_empty) {
+__device__ __noinline__ void epilogue_margin(const DevModel& m, const double* s_const, double* R, double* gp0,
+                                             const double* __restrict__ in, int64_t c, int64_t ld, int lane, bool skip_empty) {
     double ll = 0.0;
 #pragma unroll 1
     for (int b = 0; b < m.n_blocks; ++b) {
         const DevBlock& B = m.blocks[b];
+        if (B.slot_obsprior >= 0) {
+            // ln_prior = 2 log(S cbrt(P) / sqrt(1 - e²)), P = period [days] / 365.25 (prior-observable.jl:96-134)
+            const int p = B.planet;
+            const double* sc = s_const + p * PC_COUNT * 32;
+            const double S = R[(B.slot_obsprior + OP_S) * 32 + lane];
+            if (skip_empty && S == 0.0) continue;       // pointwise mode: the epoch of this CTA is not in this table
+            const double a = sc[PC_a * 32 + lane], Ms = sc[PC_M * 32 + lane], e = sc[PC_e * 32 + lane];
+            const double inv_s = sc[PC_inv_s * 32 + lane], s = sc[PC_s * 32 + lane];
+            const double P = sqrt(a * a * a / Ms) * m.c.kepler_year_days / 365.25;
+            ll += 2.0 * log(S * cbrt(P) / s);
+            if (GRAD) {
+                const double fac = 2.0 / S;
+                R[slot_planet(p, PA_S0) * 32 + lane] += fac * R[(B.slot_obsprior + OP_Q0) * 32 + lane];
+                R[slot_planet(p, PA_S1) * 32 + lane] += fac * R[(B.slot_obsprior + OP_Q1) * 32 + lane];
+                R[slot_planet(p, PA_e) * 32 + lane] += fac * R[(B.slot_obsprior + OP_Qe) * 32 + lane] + 2.0 * e * inv_s * inv_s;
+                gp0[m.idx_a[p] * 32 + lane] += sc[PC_inv_a * 32 + lane];                  // (2/3) d log P / da
+                gp0[m.idx_M[p] * 32 + lane] -= sc[PC_inv_M * 32 + lane] * (1.0 / 3.0);
+            }
+            continue;
+        }
         if (B.kind != OCTO_KIND_RV_STAR_MARGIN) continue;
         const int s0 = B.slot_margin;
         const double A = R[(s0 + MA_A) * 32 + lane], S1 = R[(s0 + MA_S1) * 32 + lane];
@@ -841,7 +890,7 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
                                             int64_t ld, int lane) {
     if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
-        const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0;
+        const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0 && B.slot_obsprior < 0;
         if (plain && !B.jit) seg_astrom<GRAD, NPT, 0>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
         else if (plain) seg_astrom<GRAD, NPT, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
         else seg_astrom<GRAD, NPT, 2>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
@@ -1024,7 +1073,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     __syncthreads();
     if (m.has_margin) {
-        if (w == 0) epilogue_margin<GRAD>(m, s_red, s_gp, s_in, lane, 32, lane, pw_const != nullptr);
+        if (w == 0) epilogue_margin<GRAD>(m, s_const, s_red, s_gp, s_in, lane, 32, lane, pw_const != nullptr);
         __syncthreads();
     }
     if (GRAD) {

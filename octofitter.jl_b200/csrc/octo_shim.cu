@@ -384,7 +384,11 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         D.jit = B.idx_jitter >= 0 ? 1 : 0;
         D.idx_jitter = B.idx_jitter; D.idx_offset = (B.kind == OCTO_KIND_RV_STAR_MARGIN || astrom) ? -1 : B.idx_offset;
         D.idx_platescale = astrom ? B.idx_platescale : -1; D.idx_northangle = astrom ? B.idx_northangle : -1;
-        D.slot_jitter = D.slot_platescale = D.slot_northangle = D.slot_offset = D.slot_margin = -1;
+        D.slot_jitter = D.slot_platescale = D.slot_northangle = D.slot_offset = D.slot_margin = D.slot_obsprior = -1;
+        if (B.obs_prior) {
+            if (!astrom) return bad("the observable-based prior is offloaded for relative astrometry only (prior-observable.jl:78-137)");
+            D.slot_obsprior = n_acc; n_acc += OP_COUNT;
+        }
         if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
             D.slot_margin = n_acc; n_acc += MA_COUNT + MV_COUNT * L->n_planets;
         } else {
@@ -397,14 +401,14 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         if (E > 0x7fffffff) return bad("too many epochs");
     }
     m.n_epochs = E; m.n_acc = n_acc;
-    for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN) m.has_margin = 1;
+    for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN || m.blocks[b].slot_obsprior >= 0) m.has_margin = 1;
     // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
     double cum = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
         DevBlock& D = m.blocks[b];
         const bool astrom = D.kind <= OCTO_KIND_ASTROM_PASEP;
-        const bool lean = D.kind == OCTO_KIND_ASTROM_RADEC && !D.jit && D.idx_platescale < 0 && D.idx_northangle < 0;
-        const bool plain = D.kind == OCTO_KIND_ASTROM_RADEC && D.idx_platescale < 0 && D.idx_northangle < 0;
+        const bool lean = D.kind == OCTO_KIND_ASTROM_RADEC && !D.jit && D.idx_platescale < 0 && D.idx_northangle < 0 && D.slot_obsprior < 0;
+        const bool plain = D.kind == OCTO_KIND_ASTROM_RADEC && D.idx_platescale < 0 && D.idx_northangle < 0 && D.slot_obsprior < 0;
         double w = astrom ? (lean ? 1.0 : (plain ? 1.6 : 2.5)) : (D.kind == OCTO_KIND_RV_STAR_MARGIN ? 1.9 : (D.jit ? 1.8 : 1.1));
         int solves = 1;
         if (D.kind == OCTO_KIND_RV_STAR_ABS || D.kind == OCTO_KIND_RV_STAR_MARGIN) solves = L->n_planets;

@@ -183,6 +183,26 @@ class PlanetRelAstromObs(AbstractObs):
 PlanetRelAstromLikelihood = PlanetRelAstromObs
 
 
+class ObsPriorAstromONeil2019(AbstractObs):
+    """`ObsPriorAstromONeil2019(astrometry_likelihood)` (src/likelihoods/prior-observable.jl:12-137): the observable-based
+    prior of O'Neil (2019) for relative astrometry.  Like the reference object it wraps the table (its ln_like is the
+    wrapped likelihood's plus 2 log of the summed Jacobian term over the table's epochs) and carries its own copy of
+    the wrapped likelihood's variables, under the name "obspri_<name>"."""
+
+    def __init__(self, obs):
+        if not isinstance(obs, PlanetRelAstromObs):
+            raise ValueError("the observable-based prior is offloaded for PlanetRelAstromObs only")
+        self.wrapped_like = obs
+        self.name = "obspri_" + obs.name
+        self.kind, self.table = obs.kind, obs.table
+        self.allowed_variables = obs.allowed_variables
+        self.var_specs, self.variables = obs.var_specs, obs.variables
+        self.obs_prior = 1
+
+    def _columns(self):
+        return self.wrapped_like._columns()
+
+
 class _RVObs(AbstractObs):
     def __init__(self, observations, *, name, variables=None, trend_function=None, gaussian_process=None):
         self.name = str(name)
@@ -388,7 +408,8 @@ class ModelSpec:
         g = lambda v: obs_cols.get((id(o), v), -1)
         return {"kind": o.kind, "planet": ip, "epoch": ep, "y1": y1, "y2": y2, "s1": s1, "s2": s2, "cor": cor,
                 "idx_jitter": g("jitter"), "idx_platescale": g("platescale"),
-                "idx_northangle": g("northangle"), "idx_offset": g("offset"), "name": o.name}
+                "idx_northangle": g("northangle"), "idx_offset": g("offset"), "name": o.name,
+                "obs_prior": int(getattr(o, "obs_prior", 0))}
 
 
 class LogDensityModel:

@@ -104,6 +104,18 @@ def ln_like(consts, layout, blocks, x):
                     r1, r2 = ra_d - ra, dec_d - dec
                 s1, s2 = mp.sqrt(s1 ** 2 + jit ** 2), mp.sqrt(s2 ** 2 + jit ** 2)
                 ll += _mvn2(s1, s2, cor, r1, r2)
+            if b.get("obs_prior", 0):
+                # ObsPriorAstromONeil2019 (src/likelihoods/prior-observable.jl:78-137)
+                el = els[ip]
+                P_days = mp.sqrt(el["a"] ** 3 / el["M"]) * c["kepler_year_days"]
+                jac = mp.mpf(0)
+                for k in range(n):
+                    t = mp.mpf(float(b["epoch"][k]))
+                    E = kepler_E(2 * mp.pi * (t - el["tp"]) / P_days, el["e"])
+                    Mm = E - el["e"] * mp.sin(E)
+                    jac += abs(3 * Mm * (el["e"] + mp.cos(E)) + 2 * (-2 + el["e"] ** 2 + el["e"] * mp.cos(E)) * mp.sin(E))
+                jac *= mp.cbrt(P_days / mp.mpf("365.25")) / mp.sqrt(1 - el["e"] ** 2)
+                ll += 2 * mp.log(jac)
         elif kind in (2, 3):
             A = Bq = Cq = mp.mpf(0)
             for k in range(n):

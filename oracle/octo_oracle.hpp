@@ -83,13 +83,14 @@ inline double value(double x) { return x; }
 template <int N> inline double value(const Dual<N>& x) { return x.v; }
 
 using std::sin; using std::cos; using std::tan; using std::atan; using std::atan2; using std::sqrt;
-using std::log; using std::hypot; using std::fabs;
+using std::log; using std::hypot; using std::fabs; using std::cbrt;
 template <int N> inline Dual<N> sin(const Dual<N>& a) { return unary(a, std::sin(a.v), std::cos(a.v)); }
 template <int N> inline Dual<N> cos(const Dual<N>& a) { return unary(a, std::cos(a.v), -std::sin(a.v)); }
 template <int N> inline Dual<N> tan(const Dual<N>& a) { double t = std::tan(a.v); return unary(a, t, 1.0 + t * t); }
 template <int N> inline Dual<N> atan(const Dual<N>& a) { return unary(a, std::atan(a.v), 1.0 / (1.0 + a.v * a.v)); }
 template <int N> inline Dual<N> sqrt(const Dual<N>& a) { double s = std::sqrt(a.v); return unary(a, s, 0.5 / s); }
 template <int N> inline Dual<N> log(const Dual<N>& a) { return unary(a, std::log(a.v), 1.0 / a.v); }
+template <int N> inline Dual<N> cbrt(const Dual<N>& a) { double r = std::cbrt(a.v); return unary(a, r, r / (3.0 * a.v)); }
 template <int N> inline Dual<N> atan2(const Dual<N>& y, const Dual<N>& x) {
     Dual<N> r; r.v = std::atan2(y.v, x.v); const double h = x.v * x.v + y.v * y.v;
     for (int k = 0; k < N; ++k) { r.d[k] = (x.v * y.d[k] - y.v * x.d[k]) / h; } return r;
@@ -312,6 +313,24 @@ inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
                     T s1 = hypot(B.s1[k], jitter), s2 = hypot(B.s2[k], jitter);
                     ll += logpdf_mvnormal2(s1, s2, cor, resid1, resid2);
                 }
+            }
+            if (B.obs_prior) {
+                // ObsPriorAstromONeil2019 (src/likelihoods/prior-observable.jl:78-137): on top of the wrapped table's
+                // ln_like.  meananom(sol) / eccanom(sol) are PlanetOrbits accessors (third-party, absent):
+                // eccanom = the solver's E, meananom = E - e sin E.
+                const Orbit<T>& o = orb[ip];
+                T P = sqrt(o.a * o.a * o.a / o.M) * c.kepler_year_days / 365.25;     // period(orbit) / 365.25
+                T jac(0.0);
+                for (int k = 0; k < n; ++k) {
+                    const Solution<T>& sol = sols[(size_t)ip * E + start[b] + k];
+                    T EA = sol.EA;
+                    T Mm = EA - o.e * sin(EA);
+                    T f = 3.0 * Mm * (o.e + cos(EA)) + 2.0 * (-2.0 + o.e * o.e + o.e * cos(EA)) * sin(EA);
+                    jac += value(f) < 0.0 ? -f : f;
+                }
+                T sqrt_eccen = sqrt(1.0 - o.e * o.e);
+                jac = jac * cbrt(P) / sqrt_eccen;
+                ll += 2.0 * log(jac);
             }
         } else if (B.kind == OCTO_KIND_RV_STAR_ABS || B.kind == OCTO_KIND_RV_STAR_MARGIN) {
             const bool margin = (B.kind == OCTO_KIND_RV_STAR_MARGIN);

@@ -159,6 +159,22 @@ def build_cases():
                                      "b.tp": 50030.0, "b.mass": 9.0, "b.CRIRES.jitter": 100.0,
                                      "c.M": 1.2, "c.a": 4.1, "c.e": 0.12, "c.i": 0.98, "c.ω": 1.28, "c.Ω": 2.03,
                                      "c.tp": 50390.0, "c.mass": 25.0, "c.SPHERE.jitter": 1.5})
+
+    # --- case 6: the observable-based prior of O'Neil (2019) exactly as the reference's docstring attaches it
+    #     (src/likelihoods/prior-observable.jl:26-52: `end astrom_like obs_prior`), on the 8-epoch fixture, plus a
+    #     wrapped sep/PA table with sampled jitter / northangle on a second, outer planet (reflex of the inner, massive one)
+    astrom = octo.PlanetRelAstromObs(octo.Table(epoch=FIX_EPOCH, ra=FIX_RA, dec=FIX_DEC, σ_ra=[10.] * 8,
+                                                σ_dec=[10.] * 8, cor=[0.] * 8), name="relastrom")
+    obs_seppa = octo.PlanetRelAstromObs(tab_seppa, name="inst", variables=["jitter", "northangle"])
+    pb = octo.Planet(name="b", variables=["a", "e", "i", "ω", "Ω", "tp", "mass"],
+                     observations=[astrom, octo.ObsPriorAstromONeil2019(astrom)])
+    pc = octo.Planet(name="c", variables=["a", "e", "i", "ω", "Ω", "tp"],
+                     observations=[octo.ObsPriorAstromONeil2019(obs_seppa)])
+    sy = octo.System(name="obsprior", variables=["M", "plx"], companions=[pb, pc])
+    cases["case_obsprior"] = (sy, {"M": 1.21, "plx": 50.01, "b.a": 12.1, "b.e": 0.12, "b.i": 0.72, "b.ω": 0.65,
+                                   "b.Ω": 0.29, "b.tp": 41500.0, "b.mass": 20.0, "c.a": 15.1, "c.e": 0.21, "c.i": 0.61, "c.ω": 0.31,
+                                   "c.Ω": 1.09, "c.tp": 50010.0, "c.obspri_inst.jitter": 0.0007,
+                                   "c.obspri_inst.northangle": -0.045})
     return cases
 
 
@@ -198,8 +214,12 @@ def build_post_cases():
 
 
 def main():
-    fixture_pin()
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases
+    if not only:
+        fixture_pin()
     for name, (system, th) in build_post_cases().items():
+        if only and name not in only:
+            continue
         spec = octo.ModelSpec(system)
         assert len(th) == spec.D, (name, len(th), spec.D, spec.theta_names)
         blocks = [{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in b.items()} for b in spec.block_dicts]
@@ -213,6 +233,8 @@ def main():
         json.dump(out, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
         print(name, "lp =", mp.nstr(lp, 20), "D =", spec.D)
     for name, (system, xd) in build_cases().items():
+        if only and name not in only:
+            continue
         spec = octo.ModelSpec(system)
         x = [xd[n] for n in spec.input_names]
         blocks = [{k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in b.items()} for b in spec.block_dicts]

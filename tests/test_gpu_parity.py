@@ -391,3 +391,30 @@ def test_pointwise_like_matches_single_epoch_models(oracle_lib, which):
     assert LL.shape == (x.shape[0], E) and epochs.shape == (E,)
     n_sys = sum(len(b["epoch"]) for b in spec.block_dicts if b["planet"] < 0)
     assert np.array_equal(LL[:, :n_sys], out[:, E - n_sys:]) and np.array_equal(LL[:, n_sys:], out[:, :E - n_sys])
+
+
+def test_observable_prior_many_chains(oracle_lib):
+    """ObsPriorAstromONeil2019-wrapped tables (RA/Dec next to its own wrapped copy as in the reference's docstring,
+    and a wrapped sep/PA table with jitter / northangle and the reflex of an inner massive planet): value, gradient
+    and the per-epoch pointwise values against the oracle over a cloud of chains."""
+    d, packed, consts = load_golden("case_obsprior")
+    import ctypes as C
+    lib = octo.load_library()
+    h = C.c_void_p()
+    assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 0, lib.octo_last_error()
+    rng = np.random.default_rng(77)
+    x0 = np.array(d["x"])
+    n, n_in = 300, len(x0)
+    x = np.asfortranarray(x0[None, :] * (1.0 + 0.01 * rng.standard_normal((n, n_in))))
+    x[:, d["input_names"].index("b.e")] = rng.uniform(0.0, 0.9, n)
+    x[1, d["input_names"].index("b.e")] = 0.0
+    x[0] = x0
+    ll = np.empty(n); g = np.empty((n, n_in), order="F"); llv = np.empty(n)
+    assert lib.octo_logp_grad(h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data) == 0, lib.octo_last_error()
+    assert lib.octo_logp(h, x.ctypes.data, n, n, llv.ctypes.data) == 0
+    assert rel_err(ll[0], d["ll"]) < LOGP_RTOL and grad_err(g[0], d["grad"]).max() < GRAD_RTOL
+    ora = oracle_lib.Oracle(packed, consts)
+    ll_o, g_o = ora.logp_grad(x, threads=4)
+    assert rel_err(ll, ll_o).max() < LOGP_RTOL and rel_err(llv, ll_o).max() < LOGP_RTOL
+    assert grad_err(g, g_o).max() < GRAD_RTOL
+    lib.octo_destroy(h)
