@@ -1,14 +1,34 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): C2- and C3-shaped models,
-ragged batch sizes, value and gradient kernels, epoch-split path."""
+ragged batch sizes, value and gradient kernels, epoch-split path; the fused parameterisation stage (and its
+three-launch fallback), the likelihood-of-theta mode, pointwise mode and an observable-prior table."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import octofitter_jl_b200 as octo
 import workloads
 for cfg, n in (("C2", 37), ("C3", 33), ("C1", 1)):
     spec, x = workloads.config(cfg)
     m = octo.LogDensityModel(spec)
     ll, g = m.ln_like_and_gradient(x[:n]); v = m.ln_like(x[:n])
-    print(cfg, n, m.launch_geometry(n), float(ll[0]) if n > 1 else float(ll), np.isfinite(g).all())
+    pw, _ = m.pointwise_like(x[:min(n, 5)])
+    print(cfg, n, m.launch_geometry(n), float(np.ravel(ll)[0]), np.isfinite(g).all(), np.isfinite(pw).all())
     m.close()
+for fuse in ("1", "0"):
+    os.environ["OCTO_B200_FUSE_PARAM"] = fuse
+    spec, th = workloads.one_planet_with_priors(40, 30, 45, seed=2)
+    m = octo.LogDensityModel(spec)
+    lp, g = m.ℓπcallback_grad(th); v = m.ℓπcallback(th); l = m.ln_like_of_theta(th)
+    print("logpost fuse=" + fuse, float(lp[0]), np.isfinite(g).all(), float(l[0]))
+    m.close()
+from helpers import load_golden
+import ctypes as C
+d, packed, consts = load_golden("case_obsprior")
+lib = octo.load_library(); h = C.c_void_p()
+assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 0
+x = np.asfortranarray(np.tile(np.array(d["x"]), (35, 1)))
+ll = np.empty(35); g = np.empty((35, x.shape[1]), order="F")
+assert lib.octo_logp_grad(h, x.ctypes.data, 35, 35, ll.ctypes.data, g.ctypes.data) == 0
+print("obsprior", ll[0], d["ll"])
+lib.octo_destroy(h)
