@@ -10,8 +10,10 @@ star-RV with offset and jitter — x 1024 chains).  A "step" is one value+gradie
 (one leapfrog's worth of work for 1024 chains).  N>1: every rank runs its own 1024 chains (chains are
 independent, no data-path collective) => weak scaling; value = all ranks' pairs / max-over-ranks time.
 
-`value`: inputs resident in HBM, one kernel per step, device time by CUDA events on the launching stream, L2
-flushed between timed steps.  `e2e`: the same metric through the public host API (`LogDensityModel.
+`value`: inputs resident in HBM, one kernel per step, K steps launched back to back between one pair of CUDA
+events on the launching stream (barrier + synchronize on both sides); every step reads its own input set from a
+pool larger than L2, so no step finds its inputs cached.  `roofline.kernel_ms_isolated` is the latency of one cold
+launch (own event pair, whole L2 flushed before it).  `e2e`: the same metric through the public host API (`LogDensityModel.
 ln_like_and_gradient` -> C ABI `octo_logp_grad`) with HOST buffers: pack + H2D + kernel + D2H inside the
 timed region, wall clock around K synchronous calls.
 """
@@ -32,6 +34,7 @@ sys.path.insert(0, ROOT)
 # ALGORITHMIC FP64 flop per (epoch x chain) pair — SURVEY.md §8(d)'s per-unit figure (libm-style cost model:
 # add/mul = 1, div = 8, sqrt = 8, cbrt = 24, sincos = 48, log = 24): one Kepler solve = 75 + 7*8 + 8 + 24 + 2*48 =
 # 259; astrometry projection + chi^2 + adjoint = 49; RV = 45 + div + log = 77.  The roofline's `achieved` uses this.
+L2_BYTES = 126 * 1024 * 1024       # B200 L2
 F_ALG = {"astrom": 308.0, "rv": 336.0, "extra_solve": 259.0}
 # EXECUTED FP64 flop per pair of THIS kernel, from ncu SASS counts (DFMA = 2, DMUL/DADD = 1; profiles/r01_*):
 # the FP32 Markley starter, the branch-free sincos/rcp and the single sincos per solve make it ~1.8x leaner than
@@ -200,6 +203,28 @@ def time_device(model, d_in, d_ll, d_g, n, steps, warmup, torch, flush, grad=Tru
     return np.array([a.elapsed_time(b) for a, b in ev])      # ms
 
 
+def time_stream(model, d_in_all, d_ll_all, d_g_all, n, steps, warmup, torch, flush):
+    """The timed region of the contract: `steps` launches back to back on the launching stream between ONE pair of
+    CUDA events.  Every launch reads its own input set and writes its own output set; the pool of sets is larger than
+    L2 and L2 is flushed once before the region, so no step finds its inputs cached (observation tables and code
+    stay resident, as they do across a sampler's evaluations)."""
+    st = torch.cuda.current_stream()
+    n_sets = d_in_all.shape[0]
+    ptr = lambda t, k: t[k % n_sets].data_ptr()
+    for k in range(warmup):
+        model.enqueue_device(ptr(d_in_all, k), n, n, ptr(d_ll_all, k), ptr(d_g_all, k), st.cuda_stream)
+    torch.cuda.synchronize()
+    flush.zero_()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for k in range(warmup, warmup + steps):
+        model.enqueue_device(ptr(d_in_all, k), n, n, ptr(d_ll_all, k), ptr(d_g_all, k), st.cuda_stream)
+    b.record(st)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b)            # ms for all steps
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -226,6 +251,16 @@ def main():
     d_ll = torch.empty(n, dtype=torch.float64, device="cuda")
     d_g = torch.empty((n_in, n), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    # pool of input/output sets for the timed region: > 1.5 x L2 in total, one set per step (reused only after the
+    # whole pool went by); set 0 is the workload itself, the others are 1e-7-relative rescalings of it
+    warm = max(3, args.warmup)
+    set_bytes = 8 * n * (2 * n_in + 1)
+    n_sets = max(warm + args.steps, int(1.5 * L2_BYTES / set_bytes) + 1) if not args.no_flush else 1
+    n_sets = min(n_sets, 8192)
+    scale = 1.0 + 1e-7 * torch.arange(n_sets, dtype=torch.float64, device="cuda")
+    d_in_all = d_in.unsqueeze(0) * scale[:, None, None]
+    d_ll_all = torch.empty((n_sets, n), dtype=torch.float64, device="cuda")
+    d_g_all = torch.empty((n_sets, n_in, n), dtype=torch.float64, device="cuda")
 
     sampler = ClockSampler(local)
     launches0 = model.kernel_launches
@@ -233,12 +268,14 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    ms = time_device(model, d_in, d_ll, d_g, n, args.steps, max(3, args.warmup), torch, None if args.no_flush else flush)
+    t_region_ms = time_stream(model, d_in_all, d_ll_all, d_g_all, n, args.steps, warm, torch, flush)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = model.kernel_launches - launches0 - max(3, args.warmup)
-    t_dev = float(ms.sum()) * 1e-3
+    launches = model.kernel_launches - launches0 - warm
+    t_dev = t_region_ms * 1e-3
+    # secondary: every launch alone between its own event pair, L2 flushed before each (latency of one cold call)
+    ms = time_device(model, d_in, d_ll, d_g, n, max(20, args.steps // 4), 3, torch, None if args.no_flush else flush)
     ms_val = time_device(model, d_in, d_ll, d_g, n, max(20, args.steps // 4), 3, torch, None if args.no_flush else flush, grad=False)
 
     # end-to-end through the public host API: inputs in pinned host memory, outputs read back every step
@@ -278,14 +315,16 @@ def main():
         tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(tt[0]), float(tt[1])
-    # sanity: device path and host path agree
+    # sanity: device path and host path agree (set 0 of the pool is the workload itself)
     if not os.environ.get("OCTO_B200_LIB"):
         assert np.array_equal(d_ll.cpu().numpy(), ll_h), "device-resident and host-API results differ"
+        if warm + args.steps <= n_sets or n_sets == 1:
+            assert np.array_equal(d_ll_all[0].cpu().numpy(), ll_h), "timed-region results differ from the host API's"
 
     if rank == 0:
         pairs_step = n * E * world
         value = pairs_step * args.steps / t_dev
-        kern_ms = float(np.mean(ms))
+        kern_ms = t_dev / args.steps * 1e3          # average launch duration over the timed region
         peak, peak_how = fp64_peak(local)
         fl = flops_per_launch(spec, n)
         achieved = fl / (kern_ms * 1e-3) / 1e12
@@ -297,14 +336,20 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2: 1 planet, 100 RA/Dec astrometry + 100 star-RV (offset, jitter) epochs x 1024 chains per GPU",
                        "chains_per_gpu": n, "epochs": E, "n_in": n_in, "launch_geometry": list(model.launch_geometry(n)),
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                       "timing": "CUDA events around each step's single kernel on the launching stream; value = pairs / sum of event times"},
+                       "l2": "inputs larger than L2: every timed step reads its own input set and writes its own output set "
+                             "(pool of %d sets, %.0f MB > 126 MB L2; one 256 MiB flush before the timed region); the 9.6 KB "
+                             "observation tables and the code stay cached, as across a sampler's evaluations" % (n_sets, n_sets * set_bytes / 1e6),
+                       "timing": "one CUDA event pair on the launching stream around the K back-to-back launches, barrier + "
+                                 "synchronize on both sides, max over ranks; value = pairs x K / region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read + write of this launch from the committed ncu capture (profiles/r01_ncu_summary.txt)
                          "traffic": 227072, "peak_source": peak_how, "flop_per_pair": F_ALG,
                          "executed": {"tflops": flops_per_launch(spec, n, F_EXEC) / (kern_ms * 1e-3) / 1e12,
                                       "flop_per_pair": F_EXEC, "how": "ncu SASS op counts, see profiles/"},
-                         "kernel_ms": kern_ms, "kernel_ms_min": float(ms.min()),
+                         "kernel_ms": kern_ms,
+                         "kernel_ms_isolated": {"mean": float(np.mean(ms)), "min": float(ms.min()),
+                                                "what": "each launch alone between its own event pair, L2 (code and tables "
+                                                        "included) flushed before it; an empty kernel measures 6.1 us this way"},
                          "hbm": {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "peak_source": hbm_how, "algorithmic_bytes": alg_bytes}},
             "e2e": {"value": pairs_step * args.steps / t_e2e, "unit": "evals/s",
