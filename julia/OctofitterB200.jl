@@ -33,6 +33,7 @@ struct OctoObsBlock
     kind::Int32; planet::Int32; n_epochs::Int32; has_cor::Int32
     epoch::Ptr{Cdouble}; y1::Ptr{Cdouble}; y2::Ptr{Cdouble}; s1::Ptr{Cdouble}; s2::Ptr{Cdouble}; cor::Ptr{Cdouble}
     idx_jitter::Int32; idx_platescale::Int32; idx_northangle::Int32; idx_offset::Int32
+    obs_prior::Int32; reserved::Int32      # 1: astrometry table wrapped in ObsPriorAstromONeil2019
 end
 
 struct OctoLayout
@@ -48,6 +49,8 @@ check(rc) = rc == 0 ? nothing : error("libocto_b200: $(octo_error())")
 "Can this observation be offloaded?  (a9-a12 of SURVEY.md; GP and custom trends stay in Julia.)"
 function kind_of(obs)
     T = nameof(typeof(obs))
+    # the observable-based prior wraps an astrometry table (src/likelihoods/prior-observable.jl:57-67)
+    T === :ObsPriorAstromONeil2019 && nameof(typeof(obs.wrapped_like)) === :PlanetRelAstromObs && return kind_of(obs.wrapped_like)
     if T === :PlanetRelAstromObs
         return hasproperty(obs.table, :pa) && hasproperty(obs.table, :sep) ? Int32(1) : Int32(0)
     elseif T === :StarAbsoluteRVObs && isnothing(obs.gaussian_process)
@@ -106,7 +109,8 @@ function B200Model(model::LogDensityModel; device::Integer=0)
         v(sym) = hasproperty(θobs, sym) ? Int32(col((path..., sym))) : Int32(-1)
         ptr(x) = isnothing(x) ? Ptr{Cdouble}(0) : pointer(x)
         push!(blocks, OctoObsBlock(k, Int32(ip - 1), length(ep), isnothing(cor) ? 0 : 1, ptr(ep), ptr(y1), ptr(y2), ptr(s1),
-                                   ptr(s2), ptr(cor), v(:jitter), v(:platescale), v(:northangle), v(:offset)))
+                                   ptr(s2), ptr(cor), v(:jitter), v(:platescale), v(:northangle), v(:offset),
+                                   Int32(nameof(typeof(obs)) === :ObsPriorAstromONeil2019), Int32(0)))
         push!(offloaded, obs)
     end
     # reference summation order: planet observations first, then system observations (system.jl:223-236)
