@@ -80,12 +80,19 @@ typedef struct OctoConstants {
 #define OCTO_KIND_RV_STAR_ABS    2  /* StarAbsoluteRVObs, gaussian_process = nothing      */
 #define OCTO_KIND_RV_STAR_MARGIN 3  /* MarginalizedStarAbsoluteRVObs                      */
 #define OCTO_KIND_RV_PLANET_REL  4  /* PlanetRelativeRVObs, gaussian_process = nothing    */
+#define OCTO_KIND_HGCA_INSTANT   5  /* HGCAInstantaneousObs (src/likelihoods/hgca.jl:29-417), Visual{KepOrbit} planets */
 
 /*
  * One observation table (SoA, host pointers; copied at octo_create, not retained).
  *   kind 0: y1=ra  y2=dec  s1=σ_ra s2=σ_dec  cor optional       [mas]
  *   kind 1: y1=pa  y2=sep  s1=σ_pa s2=σ_sep  cor optional       [rad, mas]
  *   kind 2,3,4: y1=rv s1=σ_rv; y2,s2,cor must be NULL            [m/s]
+ *   kind 5 (system-level, planet = -1): one row per simulated position measurement, as the reference ctor lays them
+ *           out (hgca.jl:94-110): epoch [MJD], y1 = 0 Hipparcos-RA | 1 Hipparcos-Dec | 2 Gaia-RA | 3 Gaia-Dec; every
+ *           other column NULL.  aux[15] = for Hipparcos, Hipparcos-Gaia, Gaia in turn:
+ *           { pmra, pmdec, pmra_error * factor, pmdec_error * factor, pmra_pmdec correlation }   [mas/yr].
+ *           Every planet needs a mass variable (hgca.jl:271, 275).  The rows are not part of octo_total_epochs and
+ *           octo_logp_pointwise ignores them (a one-row subset of this likelihood is 0/0 in the reference as well).
  * Rows must already be in the order the reference holds them (the astrometry
  * ctor sorts by epoch, relative-astrometry.jl:46-47).
  * idx_*: column of the per-observation variable in the input matrix, or -1 for
@@ -112,7 +119,10 @@ typedef struct OctoObsBlock {
     int32_t obs_prior;     /* 1 (astrometry kinds only): the table is wrapped in ObsPriorAstromONeil2019 — on top of
                             * the table's ln_like add 2 log( Σ_epochs |3M(e+cosE) + 2(-2+e²+e cosE) sinE| · cbrt(P)/√(1-e²) )
                             * for the observed planet (src/likelihoods/prior-observable.jl:78-137) */
+    int32_t idx_pmra;      /* kind 5 only: columns of the system proper motion (θ_system.pmra, .pmdec) [mas/yr] */
+    int32_t idx_pmdec;
     int32_t reserved;
+    const double* aux;     /* kind 5 only: the 15 catalogue numbers, see OCTO_KIND_HGCA_INSTANT */
 } OctoObsBlock;
 
 /*

@@ -33,7 +33,9 @@ struct OctoObsBlock
     kind::Int32; planet::Int32; n_epochs::Int32; has_cor::Int32
     epoch::Ptr{Cdouble}; y1::Ptr{Cdouble}; y2::Ptr{Cdouble}; s1::Ptr{Cdouble}; s2::Ptr{Cdouble}; cor::Ptr{Cdouble}
     idx_jitter::Int32; idx_platescale::Int32; idx_northangle::Int32; idx_offset::Int32
-    obs_prior::Int32; reserved::Int32      # 1: astrometry table wrapped in ObsPriorAstromONeil2019
+    obs_prior::Int32                       # 1: astrometry table wrapped in ObsPriorAstromONeil2019
+    idx_pmra::Int32; idx_pmdec::Int32; reserved::Int32   # kind 5 (HGCAInstantaneousObs): system proper-motion columns
+    aux::Ptr{Cdouble}                      # kind 5: the 15 catalogue numbers (see include/octo_b200.h)
 end
 
 struct OctoLayout
@@ -49,6 +51,8 @@ check(rc) = rc == 0 ? nothing : error("libocto_b200: $(octo_error())")
 "Can this observation be offloaded?  (a9-a12 of SURVEY.md; GP and custom trends stay in Julia.)"
 function kind_of(obs)
     T = nameof(typeof(obs))
+    # HGCAInstantaneousObs (kind 5) is supported by the library; this glue does not offload it yet (it would build the
+    # rows from obs.table.epoch / .meas / .inst and aux from obs.hgca, see octofitter.jl_b200/model.py)
     # the observable-based prior wraps an astrometry table (src/likelihoods/prior-observable.jl:57-67)
     T === :ObsPriorAstromONeil2019 && nameof(typeof(obs.wrapped_like)) === :PlanetRelAstromObs && return kind_of(obs.wrapped_like)
     if T === :PlanetRelAstromObs
@@ -110,7 +114,8 @@ function B200Model(model::LogDensityModel; device::Integer=0)
         ptr(x) = isnothing(x) ? Ptr{Cdouble}(0) : pointer(x)
         push!(blocks, OctoObsBlock(k, Int32(ip - 1), length(ep), isnothing(cor) ? 0 : 1, ptr(ep), ptr(y1), ptr(y2), ptr(s1),
                                    ptr(s2), ptr(cor), v(:jitter), v(:platescale), v(:northangle), v(:offset),
-                                   Int32(nameof(typeof(obs)) === :ObsPriorAstromONeil2019), Int32(0)))
+                                   Int32(nameof(typeof(obs)) === :ObsPriorAstromONeil2019), Int32(-1), Int32(-1), Int32(0),
+                                   Ptr{Cdouble}(0)))
         push!(offloaded, obs)
     end
     # reference summation order: planet observations first, then system observations (system.jl:223-236)

@@ -7,9 +7,10 @@ The directory name is not a Python identifier; import it through the repo-root l
 """
 from ._abi import (OctoConstants, OctoLayout, OctoObsBlock, OctoPrior, OctoInputDef, default_constants, load_library, pack,
                    EXPORTED_SYMBOLS, LIB_PATH,
-                   KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL)
+                   KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL,
+                   KIND_HGCA_INSTANT)
 from .model import (Normal, Uniform, LogUniform, Sine, truncated, UniformCircular, θ_at_epoch_to_tperi,
-                    theta_at_epoch_to_tperi, Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, ObsPriorAstromONeil2019, StarAbsoluteRVObs,
+                    theta_at_epoch_to_tperi, Table, PlanetRelAstromObs, PlanetRelAstromLikelihood, ObsPriorAstromONeil2019, HGCAInstantaneousObs, StarAbsoluteRVObs,
                     StarAbsoluteRVLikelihood, MarginalizedStarAbsoluteRVObs, MarginalizedStarAbsoluteRVLikelihood,
                     PlanetRelativeRVObs, PlanetRelativeRVLikelihood, Planet, System, ModelSpec, LogDensityModel, OctoError)
 from .pt import ParallelTempering

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 OCTO_MAX_PLANETS = 4
-KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL = range(5)
+KIND_ASTROM_RADEC, KIND_ASTROM_PASEP, KIND_RV_STAR_ABS, KIND_RV_STAR_MARGIN, KIND_RV_PLANET_REL, KIND_HGCA_INSTANT = range(6)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libocto_b200.so")
@@ -35,7 +35,8 @@ class OctoObsBlock(C.Structure):
     _fields_ = [("kind", C.c_int32), ("planet", C.c_int32), ("n_epochs", C.c_int32), ("has_cor", C.c_int32),
                 ("epoch", _pd), ("y1", _pd), ("y2", _pd), ("s1", _pd), ("s2", _pd), ("cor", _pd),
                 ("idx_jitter", C.c_int32), ("idx_platescale", C.c_int32),
-                ("idx_northangle", C.c_int32), ("idx_offset", C.c_int32), ("obs_prior", C.c_int32), ("reserved", C.c_int32)]
+                ("idx_northangle", C.c_int32), ("idx_offset", C.c_int32), ("obs_prior", C.c_int32), ("idx_pmra", C.c_int32),
+                ("idx_pmdec", C.c_int32), ("reserved", C.c_int32), ("aux", _pd)]
 
 
 _i4 = C.c_int32 * OCTO_MAX_PLANETS
@@ -93,20 +94,21 @@ def pack(layout_dict: dict, block_dicts: list) -> PackedModel:
     keep, blocks = [], []
     for bd in block_dicts:
         cols = {}
-        for k in ("epoch", "y1", "y2", "s1", "s2", "cor"):
+        for k in ("epoch", "y1", "y2", "s1", "s2", "cor", "aux"):
             v = bd.get(k)
             cols[k] = None if v is None else np.ascontiguousarray(np.asarray(v, dtype=np.float64))
         keep.append(cols)
         n = len(cols["epoch"])
         for k, v in cols.items():
-            if v is not None and len(v) != n:
+            if k != "aux" and v is not None and len(v) != n:
                 raise ValueError("The columns in the input data do not all have the same length")
         blocks.append(OctoObsBlock(
             int(bd["kind"]), int(bd.get("planet", -1)), n, 0 if cols["cor"] is None else 1,
             _dptr(cols["epoch"]), _dptr(cols["y1"]), _dptr(cols["y2"]), _dptr(cols["s1"]), _dptr(cols["s2"]),
             _dptr(cols["cor"]),
             int(bd.get("idx_jitter", -1)), int(bd.get("idx_platescale", -1)),
-            int(bd.get("idx_northangle", -1)), int(bd.get("idx_offset", -1)), int(bd.get("obs_prior", 0)), 0))
+            int(bd.get("idx_northangle", -1)), int(bd.get("idx_offset", -1)), int(bd.get("obs_prior", 0)),
+            int(bd.get("idx_pmra", -1)), int(bd.get("idx_pmdec", -1)), 0, _dptr(cols["aux"])))
     return PackedModel(L, blocks, keep)
 
 

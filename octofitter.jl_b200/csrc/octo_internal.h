@@ -46,6 +46,18 @@ struct DevBlock {
     double wgt, cum;                          // relative cost of one epoch of this table; Σ n*wgt of the tables before it
 };
 
+// HGCAInstantaneousObs (kind 5): a handful of rows evaluated by the last CTA of a chain group (octo_kernels.cu, hgca_tail)
+#define OCTO_MAX_HGCA 2
+struct DevHg {
+    int32_t n_rows, row_off;          // rows [t, code] at tab + row_off (doubles); code 0 hip-ra, 1 hip-dec, 2 gaia-ra, 3 gaia-dec
+    int32_t idx_pmra, idx_pmdec;
+    int32_t slot_pmra, slot_pmdec;    // accumulator slots that carry d ll / d pmra, d ll / d pmdec to the epilogue
+    double inv_N[4];                  // 1 / (planets x rows of that code): the reference's averaging (hgca.jl:247-290)
+    double k_ra, k_dec;               // 365.25 / (mean Gaia epoch - mean Hipparcos epoch) of the RA / Dec rows
+    double cat[3][2];                 // catalogue pmra, pmdec: Hipparcos, Hipparcos-Gaia, Gaia
+    double w[3][3];                   // precision matrices w11, w12, w22
+};
+
 struct DevModel {
     OctoConstants c;
     double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
@@ -59,6 +71,8 @@ struct DevModel {
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],
             idx_mass[OCTO_MAX_PLANETS];
     DevBlock blocks[OCTO_MAX_BLOCKS];
+    int32_t n_hg, pad1;
+    DevHg hg[OCTO_MAX_HGCA];
     // device table, one 48-byte record per epoch of the concatenated list: [t, y1, c1, y2, c2, c3]
     //   astrometry: c1,c2,c3 = w11,w12,w22 (no jitter) | σ1², σ2², cor (jitter);   RV: c1 = 1/σ² | σ² (y2,c2,c3 unused)
     const double* tab;

@@ -690,6 +690,11 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
             if (B.slot_northangle >= 0) gp[B.idx_northangle * 32 + lane] += R[B.slot_northangle * 32 + lane];
             if (B.slot_offset >= 0) gp[B.idx_offset * 32 + lane] += R[B.slot_offset * 32 + lane];
         }
+#pragma unroll 1
+        for (int h = 0; h < m.n_hg; ++h) {
+            gp[m.hg[h].idx_pmra * 32 + lane] += R[m.hg[h].slot_pmra * 32 + lane];
+            gp[m.hg[h].idx_pmdec * 32 + lane] += R[m.hg[h].slot_pmdec * 32 + lane];
+        }
         return;
     }
 #pragma unroll 1
@@ -732,6 +737,129 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
             if (m.idx_mass[p] >= 0) gp[m.idx_mass[p] * 32 + lane] += gmu * m.c.mjup2msol * inv_M;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// HGCAInstantaneousObs (kind 5; src/likelihoods/hgca.jl:155-417, Visual{KepOrbit}, absolute_orbits = false).
+// A handful of rows whose likelihood is a non-linear function of eight sums (star position and proper motion at the
+// Hipparcos / Gaia epochs, RA and Dec), so it is evaluated by the last CTA of a chain group once the epoch sums are
+// complete: pass 1 (rows over warps) builds the eight sums, every lane then knows ll and its derivative w.r.t. each
+// sum, pass 2 revisits the rows with those seeds and adds the adjoints into the per-planet sums R that the ordinary
+// epilogue turns into gradients.  scratch = the per-warp accumulator area (free at this point).
+//   position  = X B1 + sinE G1        (B1, G1) = (Bh, Gs) for RA rows, (Ah, Fs) for Dec rows      [mas]
+//   velocity  = (-sinE B1 + cosE G1) nd year2day / (1 - e cosE)                                   [mas/yr]
+//   star      = -mu x planet, summed over planets; the reference divides by planets x rows
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__device__ __noinline__ void hgca_tail(const DevModel& m, const DevHg& H, const double* s_const, double* R, double* scratch,
+                                       const double* s_in, int n_acc, int w, int W, int lane) {
+    const double* __restrict__ rows = m.tab + H.row_off;
+    double* mine = scratch + w * n_acc * 32;
+    double S[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) S[q] = 0.0;
+#pragma unroll 1
+    for (int r = w; r < H.n_rows; r += W) {
+        const double t = rows[2 * r];
+        const int code = (int)rows[2 * r + 1];
+        double pos = 0.0, vel = 0.0;
+#pragma unroll 1
+        for (int p = 0; p < m.n_planets; ++p) {
+            const double* sc = s_const + p * PC_COUNT * 32;
+            const Orb o = load_orb(sc, lane);
+            double dt, sE, cE;
+            kepler_sincos(o, t, dt, sE, cE);
+            const double B1 = sc[((code & 1) ? PC_Ah : PC_Bh) * 32 + lane], G1 = sc[((code & 1) ? PC_Fs : PC_Gs) * 32 + lane];
+            const double mu = sc[PC_mu * 32 + lane];
+            const double rD = rcp_nr(fma(-o.e, cE, kc.one));
+            const double u = fma(cE, G1, -sE * B1);
+            pos = fma(-mu, fma(cE - o.e, B1, sE * G1), pos);
+            vel = fma(-mu, u * (o.nd * m.c.year2day * rD), vel);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (code == q) { S[2 * q] += pos; S[2 * q + 1] += vel; }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mine[q * 32 + lane] = S[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        double v = scratch[q * 32 + lane];
+        for (int ww = 1; ww < W; ++ww) v += scratch[(ww * n_acc + q) * 32 + lane];
+        S[q] = v;
+    }
+    const double pmra = s_in[H.idx_pmra * 32 + lane], pmdec = s_in[H.idx_pmdec * 32 + lane];
+    // model proper motions: Hipparcos, Hipparcos-Gaia (position difference), Gaia
+    const double mod[3][2] = {
+        {fma(S[1], H.inv_N[0], pmra), fma(S[3], H.inv_N[1], pmdec)},
+        {fma(S[4] * H.inv_N[2] - S[0] * H.inv_N[0], H.k_ra, pmra), fma(S[6] * H.inv_N[3] - S[2] * H.inv_N[1], H.k_dec, pmdec)},
+        {fma(S[5], H.inv_N[2], pmra), fma(S[7], H.inv_N[3], pmdec)}};
+    double ll = 0.0, q1[3], q2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double r1 = mod[d][0] - H.cat[d][0], r2 = mod[d][1] - H.cat[d][1];
+        q1[d] = fma(H.w[d][0], r1, H.w[d][1] * r2); q2[d] = fma(H.w[d][1], r1, H.w[d][2] * r2);
+        ll = fma(kc.mhalf, fma(r1, q1[d], r2 * q2[d]), ll);
+    }
+    __syncthreads();                                   // everyone has read the partial sums
+    if (w == 0) {
+        R[0 * 32 + lane] += ll;
+        if (GRAD) {
+            R[H.slot_pmra * 32 + lane] = -(q1[0] + q1[1] + q1[2]);
+            R[H.slot_pmdec * 32 + lane] = -(q2[0] + q2[1] + q2[2]);
+        }
+    }
+    if (!GRAD) return;
+    // seeds d ll / d S[q]
+    double g[8];
+    g[0] = q1[1] * H.k_ra * H.inv_N[0];  g[1] = -q1[0] * H.inv_N[0];
+    g[2] = q2[1] * H.k_dec * H.inv_N[1]; g[3] = -q2[0] * H.inv_N[1];
+    g[4] = -q1[1] * H.k_ra * H.inv_N[2]; g[5] = -q1[2] * H.inv_N[2];
+    g[6] = -q2[1] * H.k_dec * H.inv_N[3]; g[7] = -q2[2] * H.inv_N[3];
+    const int np = m.n_planets * PA_COUNT;
+#pragma unroll 1
+    for (int a = 0; a < np; ++a) mine[a * 32 + lane] = 0.0;
+#pragma unroll 1
+    for (int r = w; r < H.n_rows; r += W) {
+        const double t = rows[2 * r];
+        const int code = (int)rows[2 * r + 1];
+        double gp = 0.0, gv = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (code == q) { gp = g[2 * q]; gv = g[2 * q + 1]; }
+#pragma unroll 1
+        for (int p = 0; p < m.n_planets; ++p) {
+            const double* sc = s_const + p * PC_COUNT * 32;
+            const Orb o = load_orb(sc, lane);
+            double dt, sE, cE;
+            kepler_sincos(o, t, dt, sE, cE);
+            const double B1 = sc[((code & 1) ? PC_Ah : PC_Bh) * 32 + lane], G1 = sc[((code & 1) ? PC_Fs : PC_Gs) * 32 + lane];
+            const double mu = sc[PC_mu * 32 + lane];
+            const double rD = rcp_nr(fma(-o.e, cE, kc.one));
+            const double kv = o.nd * m.c.year2day * rD;
+            const double X = cE - o.e, u = fma(cE, G1, -sE * B1);
+            const double pos = fma(X, B1, sE * G1), vel = u * kv;
+            const double cp = -mu * gp, cv = -mu * gv;
+            double* acc = mine + p * PA_COUNT * 32;
+            // d/dB1, d/dG1
+            acc[((code & 1) ? PA_Ah : PA_Bh) * 32 + lane] += fma(cp, X, -cv * sE * kv);
+            acc[((code & 1) ? PA_Fs : PA_Gs) * 32 + lane] += fma(cp, sE, cv * cE * kv);
+            // through E: d pos/dE = u, d vel/dE = (-(cosE B1 + sinE G1) - u e sinE rD) kv;  dE/dMA = rD, dE/de = sinE rD
+            const double dvel = (-fma(cE, B1, sE * G1) - u * o.e * sE * rD) * kv;
+            const double gM = fma(cp, u, cv * dvel) * rD;
+            acc[PA_S0 * 32 + lane] += gM;
+            acc[PA_S1 * 32 + lane] += fma(gM, dt, cv * u * (m.c.year2day * rD));      // + explicit mean-motion factor of the velocity
+            acc[PA_e * 32 + lane] += fma(gM, sE, fma(cv * vel, cE * rD, -cp * B1)); // + explicit e in 1/(1 - e cosE) and in X
+            acc[PA_mu * 32 + lane] -= fma(gp, pos, gv * vel);
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int idx = threadIdx.x; idx < np * 32; idx += W * 32) {
+        double v = scratch[idx];
+        for (int ww = 1; ww < W; ++ww) v += scratch[ww * n_acc * 32 + idx];
+        R[32 + idx] += v;                              // planet slots start at slot 1 (slot_planet)
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1065,6 +1193,11 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
 
     OCTO_TICK();
+    // ---- HGCA tables: evaluated here, on the complete sums (not in pointwise mode: they are not part of the epoch list)
+    if (m.n_hg > 0 && !pw_const) {
+#pragma unroll 1
+        for (int h = 0; h < m.n_hg; ++h) hgca_tail<GRAD>(m, m.hg[h], s_const, s_red, s_acc, s_in, n_acc, w, W, lane);
+    }
     // ---- epilogue (see epilogue_part): gradient parts live in the now free per-warp accumulator area
     double* s_gp = s_acc;                                     // [EPI_PARTS][n_in][32]
     if (GRAD) {

@@ -341,6 +341,12 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
             !col_ok(L->idx_tp[p], false) || !col_ok(L->idx_M[p], false) || !col_ok(L->idx_mass[p], true))
             return fail(OCTO_ERR_ARG, "layout column index out of range");
     }
+    // HGCAInstantaneousObs tables (kind 5) are not part of the epoch list: set them aside
+    std::vector<OctoObsBlock> regular;
+    std::vector<OctoObsBlock> hgs;
+    for (int b = 0; b < n_blocks; ++b) (blocks[b].kind == OCTO_KIND_HGCA_INSTANT ? hgs : regular).push_back(blocks[b]);
+    if ((int)hgs.size() > OCTO_MAX_HGCA) return fail(OCTO_ERR_ARG, "too many HGCA tables");
+    blocks = regular.data(); n_blocks = (int32_t)regular.size();
     int dev_count = 0;
     cudaError_t ce = cudaGetDeviceCount(&dev_count);
     if (ce != cudaSuccess || dev_count == 0)
@@ -400,6 +406,45 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         E += B.n_epochs;
         if (E > 0x7fffffff) return bad("too many epochs");
     }
+    // HGCA tables: validation, averaging constants, precision matrices; two accumulator slots each (pmra, pmdec)
+    long double cll_hg = 0.0L;
+    size_t hg_rows_total = 0;
+    m.n_hg = (int32_t)hgs.size();
+    for (size_t h = 0; h < hgs.size(); ++h) {
+        const OctoObsBlock& B = hgs[h];
+        DevHg& H = m.hg[h];
+        auto bad = [&](const char* msg) { delete ctx; return fail(OCTO_ERR_ARG, std::string("HGCA table: ") + msg); };
+        if (B.n_epochs < 4 || !B.epoch || !B.y1 || !B.aux) return bad("needs rows (epoch, code) and the 15 catalogue numbers");
+        if (!col_ok(B.idx_pmra, false) || !col_ok(B.idx_pmdec, false)) return bad("pmra / pmdec column out of range");
+        for (int p = 0; p < L->n_planets; ++p)
+            if (L->idx_mass[p] < 0) return bad("needs a mass variable on every planet (hgca.jl:271)");
+        int cnt[4] = {0, 0, 0, 0};
+        double ep[4] = {0, 0, 0, 0};
+        for (int k = 0; k < B.n_epochs; ++k) {
+            const int code = (int)B.y1[k];
+            if (code < 0 || code > 3 || (double)code != B.y1[k]) return bad("row code must be 0..3");
+            cnt[code]++; ep[code] += B.epoch[k];
+        }
+        for (int q = 0; q < 4; ++q) {
+            if (cnt[q] == 0) return bad("needs at least one row of every kind (Hipparcos/Gaia x RA/Dec)");
+            ep[q] /= cnt[q];
+            H.inv_N[q] = 1.0 / ((double)cnt[q] * L->n_planets);
+        }
+        if (ep[2] == ep[0] || ep[3] == ep[1]) return bad("Hipparcos and Gaia epochs coincide");
+        H.k_ra = 365.25 / (ep[2] - ep[0]); H.k_dec = 365.25 / (ep[3] - ep[1]);
+        for (int d = 0; d < 3; ++d) {
+            const double* q = B.aux + 5 * d;
+            const double s1 = q[2], s2 = q[3], cor = q[4];
+            if (!(s1 > 0) || !(s2 > 0) || !(std::fabs(cor) < 1.0)) return bad("catalogue errors must be > 0 and |correlation| < 1");
+            const double om = 1.0 - cor * cor;
+            H.cat[d][0] = q[0]; H.cat[d][1] = q[1];
+            H.w[d][0] = 1.0 / (s1 * s1 * om); H.w[d][1] = -cor / (s1 * s2 * om); H.w[d][2] = 1.0 / (s2 * s2 * om);
+            cll_hg += -1.8378770664093454835606594728112353L - 0.5L * std::log((long double)s1 * s1 * s2 * s2 * om);
+        }
+        H.n_rows = B.n_epochs; H.idx_pmra = B.idx_pmra; H.idx_pmdec = B.idx_pmdec;
+        H.slot_pmra = n_acc++; H.slot_pmdec = n_acc++;
+        hg_rows_total += (size_t)B.n_epochs;
+    }
     m.n_epochs = E; m.n_acc = n_acc;
     for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN || m.blocks[b].slot_obsprior >= 0) m.has_margin = 1;
     // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
@@ -421,7 +466,15 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
     // + padding: the kernels prefetch one lane-stride (<= 32*8 records) past the record they read
-    std::vector<double> T((size_t)6 * (E > 0 ? E : 1), 0.0);
+    const size_t hg_off0 = (size_t)6 * (E > 0 ? E : 1) + 6 * 32;        // HGCA rows live behind the (padded) epoch records
+    std::vector<double> T(hg_off0 + 2 * hg_rows_total + 2, 0.0);
+    {
+        size_t off = hg_off0;
+        for (size_t h = 0; h < hgs.size(); ++h) {
+            m.hg[h].row_off = (int32_t)off;
+            for (int k = 0; k < hgs[h].n_epochs; ++k) { T[off++] = hgs[h].epoch[k]; T[off++] = hgs[h].y1[k]; }
+        }
+    }
     struct Col { double* b; double& operator[](size_t o) const { return b[6 * o]; } };   // AoS record field view
     const Col t{T.data()}, y1{T.data() + 1}, c1{T.data() + 2}, y2{T.data() + 3}, c2{T.data() + 4}, c3{T.data() + 5};
     long double cll = 0.0L;
@@ -460,7 +513,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
             }
         }
     }
-    m.const_ll = (double)cll;
+    m.const_ll = (double)(cll + cll_hg);
 
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);

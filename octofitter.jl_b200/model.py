@@ -203,6 +203,44 @@ class ObsPriorAstromONeil2019(AbstractObs):
         return self.wrapped_like._columns()
 
 
+class HGCAInstantaneousObs(AbstractObs):
+    """`HGCAInstantaneousObs(; gaia_id, N_ave=1, factor=1)` (src/likelihoods/hgca.jl:29-153): Hipparcos-Gaia Catalog of
+    Accelerations proper-motion anomaly, instantaneous approximation.  The reference reads the star's row from the
+    HGCA FITS file; here the caller passes that row as `hgca` (a mapping with the catalogue's column names:
+    pmra_hip, pmdec_hip, pmra_hip_error, pmdec_hip_error, pmra_pmdec_hip, the same for _hg and _gaia, and
+    epoch_ra_hip, epoch_dec_hip, epoch_ra_gaia, epoch_dec_gaia in Julian years).  System-level; the system needs
+    `pmra` and `pmdec` variables and every planet a `mass`."""
+    kind = _abi.KIND_HGCA_INSTANT
+    allowed_variables = ()
+
+    def __init__(self, hgca, *, N_ave=1, factor=1.0, name="hgca", variables=()):
+        self.name = str(name)
+        self.hgca = dict(hgca)
+        h = self.hgca
+        julian_year, J2000_mjd = 365.25, 51544.5
+        mjd = lambda key: (float(h[key]) - 2000.0) * julian_year + J2000_mjd          # hgca.jl:78-84
+        e_ra_hip, e_dec_hip, e_ra_gaia, e_dec_gaia = (mjd(k) for k in ("epoch_ra_hip", "epoch_dec_hip", "epoch_ra_gaia", "epoch_dec_gaia"))
+        dt_gaia, dt_hip = 1038.0, 4 * 365.25                                            # hgca.jl:86-88
+        if N_ave == 1:
+            d_hip = d_gaia = [0.0]
+        else:
+            d_hip = np.linspace(-dt_hip / 2, dt_hip / 2, N_ave); d_gaia = np.linspace(-dt_gaia / 2, dt_gaia / 2, N_ave)
+        epoch, code = [], []
+        for d in d_hip:
+            epoch += [e_ra_hip + d, e_dec_hip + d]; code += [0.0, 1.0]
+        for d in d_gaia:
+            epoch += [e_ra_gaia + d, e_dec_gaia + d]; code += [2.0, 3.0]
+        self.table = {"epoch": np.asarray(epoch), "code": np.asarray(code)}
+        f = float(factor)
+        self.aux = np.asarray([v for tag in ("hip", "hg", "gaia") for v in (
+            float(h[f"pmra_{tag}"]), float(h[f"pmdec_{tag}"]), float(h[f"pmra_{tag}_error"]) * f,
+            float(h[f"pmdec_{tag}_error"]) * f, float(h[f"pmra_pmdec_{tag}"]))], dtype=np.float64)
+        self._set_variables(variables)
+
+    def _columns(self):
+        return self.table["epoch"], self.table["code"], None, None, None, None
+
+
 class _RVObs(AbstractObs):
     def __init__(self, observations, *, name, variables=None, trend_function=None, gaussian_process=None):
         self.name = str(name)
@@ -288,7 +326,7 @@ class System:
         if len(set(names)) != len(names):
             raise ValueError("planet names must be unique")
         for o in self.observations:
-            if o.kind not in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN):
+            if o.kind not in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN, _abi.KIND_HGCA_INSTANT):
                 raise ValueError(f"{type(o).__name__} must be attached to a planet")
 
 
@@ -345,11 +383,16 @@ class ModelSpec:
             for o in p.observations:
                 blocks.append(self._block(o, ip, obs_cols))
         for o in system.observations:
-            blocks.append(self._block(o, -1, obs_cols))
+            blk = self._block(o, -1, obs_cols)
+            if o.kind == _abi.KIND_HGCA_INSTANT:
+                if "pmra" not in col or "pmdec" not in col:
+                    raise OctoError("HGCAInstantaneousObs needs system variables pmra and pmdec (hgca.jl:298-299)")
+                blk.update(idx_pmra=col["pmra"], idx_pmdec=col["pmdec"], aux=o.aux)
+            blocks.append(blk)
         self.layout_dict = {"n_in": self.n_in, "planets": planets_layout}
         self.block_dicts = blocks
         self.packed = _abi.pack(self.layout_dict, blocks)
-        self.total_epochs = sum(len(b["epoch"]) for b in blocks)
+        self.total_epochs = sum(len(b["epoch"]) for b in blocks if b["kind"] != _abi.KIND_HGCA_INSTANT)
 
     def column(self, name):
         return self.input_names.index(name)
@@ -665,6 +708,8 @@ class LogDensityModel:
         blocks, start, order, epochs = self.spec.block_dicts, 0, [], []
         spans = []
         for b in blocks:
+            if b["kind"] == _abi.KIND_HGCA_INSTANT:
+                continue            # not part of the epoch list (a one-row subset is 0/0 in the reference as well)
             spans.append((b["planet"] < 0, start, len(b["epoch"]), b["epoch"]))
             start += len(b["epoch"])
         for system_level in (True, False):

@@ -132,6 +132,30 @@ def ln_like(consts, layout, blocks, x):
                     ll += -(mp.log(two_pi) + mp.log(var) + r * r / var) / 2
             if kind == 3:
                 ll -= -Bq ** 2 / (4 * A) + Cq + mp.log(A)
+        elif kind == 5:
+            # HGCAInstantaneousObs (src/likelihoods/hgca.jl:155-417): proper motions as numerical time derivatives
+            # of the star's reflex position (independent of the closed-form velocity formula the oracle uses)
+            pm_sys = (x[b["idx_pmra"]], x[b["idx_pmdec"]])
+            P = len(els)
+            def star_pos(t, axis):
+                tot = mp.mpf(0)
+                for el in els:
+                    st = planet_state(c, el, t)
+                    tot += -el["mu"] * st[axis]
+                return tot
+            pos, pm, ep = {}, {}, {}
+            for inst in (0, 1):
+                for axis in (0, 1):
+                    ts = [mp.mpf(float(b["epoch"][k])) for k in range(n) if int(b["y1"][k]) == 2 * inst + axis]
+                    # the reference divides the sum over planets AND rows by (planets x rows) (hgca.jl:247-290)
+                    pos[inst, axis] = sum(star_pos(t, axis) for t in ts) / (P * len(ts))
+                    pm[inst, axis] = sum(mp.diff(lambda tt: star_pos(tt, axis), t) * mp.mpf("365.25") for t in ts) / (P * len(ts)) + pm_sys[axis]
+                    ep[inst, axis] = sum(ts) / len(ts)
+            hg = [(pos[1, ax] - pos[0, ax]) / (ep[1, ax] - ep[0, ax]) * mp.mpf("365.25") + pm_sys[ax] for ax in (0, 1)]
+            q = [mp.mpf(float(v)) for v in b["aux"]]
+            ll += _mvn2(q[2], q[3], q[4], pm[0, 0] - q[0], pm[0, 1] - q[1])
+            ll += _mvn2(q[7], q[8], q[9], hg[0] - q[5], hg[1] - q[6])
+            ll += _mvn2(q[12], q[13], q[14], pm[1, 0] - q[10], pm[1, 1] - q[11])
         elif kind == 4:
             ip = b["planet"]
             for k in range(n):

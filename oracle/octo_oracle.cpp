@@ -28,8 +28,9 @@ static int validate(const OctoLayout* L, const OctoObsBlock* blocks, int n_block
     if (!L || L->n_planets < 1 || L->n_planets > OCTO_MAX_PLANETS || L->n_in < 1) { g_err = "bad layout"; return OCTO_ERR_ARG; }
     for (int b = 0; b < n_blocks; ++b) {
         const OctoObsBlock& B = blocks[b];
-        if (B.kind < 0 || B.kind > 4) { g_err = "bad kind"; return OCTO_ERR_ARG; }
-        const bool sys = (B.kind == OCTO_KIND_RV_STAR_ABS || B.kind == OCTO_KIND_RV_STAR_MARGIN);
+        if (B.kind < 0 || B.kind > 5) { g_err = "bad kind"; return OCTO_ERR_ARG; }
+        const bool sys = (B.kind == OCTO_KIND_RV_STAR_ABS || B.kind == OCTO_KIND_RV_STAR_MARGIN || B.kind == OCTO_KIND_HGCA_INSTANT);
+        if (B.kind == OCTO_KIND_HGCA_INSTANT && (!B.aux || B.idx_pmra < 0 || B.idx_pmdec < 0)) { g_err = "HGCA needs aux, pmra, pmdec"; return OCTO_ERR_ARG; }
         if (!sys && (B.planet < 0 || B.planet >= L->n_planets)) { g_err = "bad planet index"; return OCTO_ERR_ARG; }
         if (sys) for (int p = 0; p < L->n_planets; ++p)
             if (L->idx_mass[p] < 0) { g_err = "star RV needs a mass variable on every planet"; return OCTO_ERR_ARG; }

@@ -211,6 +211,18 @@ template <class T> inline T radvel(const Orbit<T>& o, const Solution<T>& s) { re
 template <class T> inline T raoff(const Orbit<T>& o, const Solution<T>& s, const T& m) { return -m / o.M * raoff(o, s); }
 template <class T> inline T decoff(const Orbit<T>& o, const Solution<T>& s, const T& m) { return -m / o.M * decoff(o, s); }
 template <class T> inline T radvel(const Orbit<T>& o, const Solution<T>& s, const T& m) { return -m / o.M * radvel(o, s); }
+// proper motion of the relative orbit [mas/yr] (PlanetOrbits pmra/pmdec: d(raoff)/dt, d(decoff)/dt):
+// with u = ν + ω:  d(r cos u)/dt = -J (sin u + e sin ω),  d(r sin u)/dt = J (cos u + e cos ω),  J = n a / sqrt(1 - e²) [AU/yr]
+template <class T> inline T pmra(const Orbit<T>& o, const Solution<T>& s) {
+    T xdot = o.J * (o.cosi_cosW * (s.cosnu_w + o.ecosw) - o.sinW * (s.sinnu_w + o.esinw));
+    return xdot * s.cart2angle;
+}
+template <class T> inline T pmdec(const Orbit<T>& o, const Solution<T>& s) {
+    T ydot = -o.J * (o.cosi_sinW * (s.cosnu_w + o.ecosw) + o.cosW * (s.sinnu_w + o.esinw));
+    return ydot * s.cart2angle;
+}
+template <class T> inline T pmra(const Orbit<T>& o, const Solution<T>& s, const T& m) { return -m / o.M * pmra(o, s); }
+template <class T> inline T pmdec(const Orbit<T>& o, const Solution<T>& s, const T& m) { return -m / o.M * pmdec(o, s); }
 
 // 2-D zero-mean normal logpdf, Σ = [v1 c√(v1v2); c√(v1v2) v2]  (Distributions.MvNormal)
 template <class T>
@@ -370,6 +382,41 @@ inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
                 acc += -0.5 * (log2pi + log(var) + resid * resid / var);
             }
             ll += acc;
+        } else if (B.kind == OCTO_KIND_HGCA_INSTANT) {
+            // HGCAInstantaneousObs: simulate (hgca.jl:219-417, absolute_orbits = false) + ln_like (:155-216).
+            // The averaging counters and epoch sums advance inside the planet loop, exactly as written there.
+            T pmra_sys = X[B.idx_pmra], pmdec_sys = X[B.idx_pmdec];
+            T ra_m[2] = {T(0.0), T(0.0)}, dec_m[2] = {T(0.0), T(0.0)}, pmra_m[2] = {T(0.0), T(0.0)}, pmdec_m[2] = {T(0.0), T(0.0)};
+            double ep_ra[2] = {0, 0}, ep_dec[2] = {0, 0};
+            int N_ra[2] = {0, 0}, N_dec[2] = {0, 0};
+            for (int inst = 0; inst < 2; ++inst)
+                for (int p = 0; p < P; ++p)
+                    for (int k = 0; k < n; ++k) {
+                        const int code = (int)B.y1[k];
+                        if (code / 2 != inst) continue;
+                        const Solution<T>& sol = sols[(size_t)p * E + start[b] + k];
+                        T m = X[L.idx_mass[p]] * c.mjup2msol;
+                        if (code % 2 == 0) {
+                            N_ra[inst] += 1; ep_ra[inst] += B.epoch[k];
+                            ra_m[inst] += raoff(orb[p], sol, m); pmra_m[inst] += pmra(orb[p], sol, m);
+                        } else {
+                            N_dec[inst] += 1; ep_dec[inst] += B.epoch[k];
+                            dec_m[inst] += decoff(orb[p], sol, m); pmdec_m[inst] += pmdec(orb[p], sol, m);
+                        }
+                    }
+            for (int inst = 0; inst < 2; ++inst) {
+                ra_m[inst] = ra_m[inst] / (double)N_ra[inst]; dec_m[inst] = dec_m[inst] / (double)N_dec[inst];
+                pmra_m[inst] = pmra_m[inst] / (double)N_ra[inst] + pmra_sys;
+                pmdec_m[inst] = pmdec_m[inst] / (double)N_dec[inst] + pmdec_sys;
+                ep_ra[inst] /= N_ra[inst]; ep_dec[inst] /= N_dec[inst];
+            }
+            const double julian_year = 365.25;
+            T pmra_hg = (ra_m[1] - ra_m[0]) / (ep_ra[1] - ep_ra[0]) * julian_year + pmra_sys;
+            T pmdec_hg = (dec_m[1] - dec_m[0]) / (ep_dec[1] - ep_dec[0]) * julian_year + pmdec_sys;
+            const double* q = B.aux;       // hip, hg, gaia: pmra, pmdec, σ_pmra, σ_pmdec, correlation
+            ll += logpdf_mvnormal2(T(q[2]), T(q[3]), q[4], pmra_m[0] - q[0], pmdec_m[0] - q[1]);
+            ll += logpdf_mvnormal2(T(q[7]), T(q[8]), q[9], pmra_hg - q[5], pmdec_hg - q[6]);
+            ll += logpdf_mvnormal2(T(q[12]), T(q[13]), q[14], pmra_m[1] - q[10], pmdec_m[1] - q[11]);
         }
     }
     return ll;

@@ -175,6 +175,22 @@ def build_cases():
                                    "b.Ω": 0.29, "b.tp": 41500.0, "b.mass": 20.0, "c.a": 15.1, "c.e": 0.21, "c.i": 0.61, "c.ω": 0.31,
                                    "c.Ω": 1.09, "c.tp": 50010.0, "c.obspri_inst.jitter": 0.0007,
                                    "c.obspri_inst.northangle": -0.045})
+
+    # --- case 7: Hipparcos-Gaia proper-motion anomaly (HGCAInstantaneousObs, src/likelihoods/hgca.jl), N_ave = 3, two
+    #     massive planets (the reference's planets-times-rows averaging shows with more than one), next to
+    #     relative astrometry of the outer planet
+    hgca_row = dict(pmra_hip=10.1, pmdec_hip=-5.2, pmra_hip_error=0.9, pmdec_hip_error=0.8, pmra_pmdec_hip=0.2,
+                    pmra_hg=10.5, pmdec_hg=-5.0, pmra_hg_error=0.05, pmdec_hg_error=0.04, pmra_pmdec_hg=-0.1,
+                    pmra_gaia=11.2, pmdec_gaia=-4.6, pmra_gaia_error=0.12, pmdec_gaia_error=0.1, pmra_pmdec_gaia=0.35,
+                    epoch_ra_hip=1991.1, epoch_dec_hip=1991.3, epoch_ra_gaia=2016.0, epoch_dec_gaia=2016.2)
+    hg = octo.HGCAInstantaneousObs(hgca_row, N_ave=3, factor=1.2)
+    pb = octo.Planet(name="b", variables=["a", "e", "i", "ω", "Ω", "tp", "mass"])
+    pc = octo.Planet(name="c", variables=["a", "e", "i", "ω", "Ω", "tp", "mass"], observations=[ac])
+    sy = octo.System(name="pma", variables=["M", "plx", "pmra", "pmdec"], companions=[pb, pc], observations=[hg])
+    cases["case_hgca"] = (sy, {"M": 1.2, "plx": 50.1, "pmra": 10.6, "pmdec": -4.9,
+                               "b.a": 4.1, "b.e": 0.12, "b.i": 0.98, "b.ω": 1.28, "b.Ω": 2.03, "b.tp": 50390.0, "b.mass": 25.0,
+                               "c.a": 10.2, "c.e": 0.31, "c.i": 1.02, "c.ω": 0.52, "c.Ω": 1.97, "c.tp": 50030.0, "c.mass": 9.0,
+                               "c.SPHERE.jitter": 1.5})
     return cases
 
 

@@ -276,3 +276,31 @@ def test_loglike_of_theta_and_rejection_sampler(oracle_lib, monkeypatch):
     ll_acc = oracle_lib.loglike_theta(spec, octo.default_constants(), out["theta_t"], threads=4)
     assert rel_err(out["loglike"], ll_acc).max() < 1e-9
     assert np.array_equal(out["logpost"], model.ℓπcallback(out["theta_t"]))
+
+
+def test_hgca_model_with_priors_on_device(oracle_lib):
+    """A proper-motion-anomaly model as the docs build it (docs/src/pma.md: HGCAInstantaneousObs, pmra/pmdec priors,
+    mass prior, θ_at_epoch_to_tperi): full ℓπ and ∇ℓπ through the host mirror against the oracle."""
+    row = dict(pmra_hip=10.1, pmdec_hip=-5.2, pmra_hip_error=0.9, pmdec_hip_error=0.8, pmra_pmdec_hip=0.2,
+               pmra_hg=10.5, pmdec_hg=-5.0, pmra_hg_error=0.05, pmdec_hg_error=0.04, pmra_pmdec_hg=-0.1,
+               pmra_gaia=11.2, pmdec_gaia=-4.6, pmra_gaia_error=0.12, pmdec_gaia_error=0.1, pmra_pmdec_gaia=0.35,
+               epoch_ra_hip=1991.1, epoch_dec_hip=1991.3, epoch_ra_gaia=2016.0, epoch_dec_gaia=2016.2)
+    hg = octo.HGCAInstantaneousObs(row, N_ave=5)
+    b = octo.Planet(name="b", variables={
+        "a": octo.LogUniform(1, 30), "e": octo.Uniform(0, 0.9), "i": octo.Sine(), "ω": octo.UniformCircular(),
+        "Ω": octo.UniformCircular(), "θ": octo.UniformCircular(), "tp": octo.θ_at_epoch_to_tperi("θ", 57000.0),
+        "mass": octo.LogUniform(1, 100)})
+    system = octo.System(name="pma", companions=[b], observations=[hg], variables={
+        "M": octo.truncated(octo.Normal(1.2, 0.1), lower=0.1), "plx": octo.truncated(octo.Normal(50.0, 0.02), lower=0.1),
+        "pmra": octo.Normal(10.5, 5.0), "pmdec": octo.Normal(-5.0, 5.0)})
+    spec = octo.ModelSpec(system)
+    model = octo.LogDensityModel(spec)
+    assert model.total_epochs == 0
+    rng = np.random.default_rng(41)
+    th = rng.normal(0, 0.7, (97, spec.D))
+    th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(97)
+    lp, g = model.ℓπcallback_grad(th)
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    assert np.isfinite(lp_o).all()
+    assert rel_err(lp, lp_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+    assert rel_err(model.ℓπcallback(th), lp_o).max() < LOGP_RTOL

@@ -2,6 +2,8 @@
 
 Tolerances are the north_star's: 1e-10 relative on logp, 1e-8 on ∇logp (relative to the largest
 component of each gradient row)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -417,4 +419,47 @@ def test_observable_prior_many_chains(oracle_lib):
     ll_o, g_o = ora.logp_grad(x, threads=4)
     assert rel_err(ll, ll_o).max() < LOGP_RTOL and rel_err(llv, ll_o).max() < LOGP_RTOL
     assert grad_err(g, g_o).max() < GRAD_RTOL
+    lib.octo_destroy(h)
+
+
+def test_hgca_many_chains_and_split_geometry(oracle_lib):
+    """HGCAInstantaneousObs (evaluated by the last CTA of a chain group after the epoch sums are complete) next to an
+    astrometry table: value and gradient against the oracle over a cloud of chains, with and without epoch splits,
+    through the host mirror's class; HGCA alone (no epoch table at all) as well."""
+    d, packed, consts = load_golden("case_hgca")
+    import ctypes as C
+    lib = octo.load_library()
+    rng = np.random.default_rng(78)
+    x0 = np.array(d["x"])
+    n, n_in = 150, len(x0)
+    x = np.asfortranarray(x0[None, :] * (1.0 + 0.02 * rng.standard_normal((n, n_in))))
+    x[3, d["input_names"].index("b.e")] = -0.1                  # invalid chain
+    ora = oracle_lib.Oracle(packed, consts)
+    ll_o, g_o = ora.logp_grad(x, threads=4)
+    for slice_env in (None, "2"):
+        if slice_env:
+            os.environ["OCTO_B200_SLICE"] = slice_env
+        try:
+            h = C.c_void_p()
+            assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 0, lib.octo_last_error()
+        finally:
+            os.environ.pop("OCTO_B200_SLICE", None)
+        assert lib.octo_total_epochs(h) == 6                        # the astrometry table only
+        ll = np.empty(n); g = np.empty((n, n_in), order="F"); llv = np.empty(n)
+        assert lib.octo_logp_grad(h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data) == 0, lib.octo_last_error()
+        assert lib.octo_logp(h, x.ctypes.data, n, n, llv.ctypes.data) == 0
+        ok = np.arange(n) != 3
+        assert np.isneginf(ll[3]) and (g[3] == 0).all()
+        assert rel_err(ll[ok], ll_o[ok]).max() < LOGP_RTOL and rel_err(llv[ok], ll_o[ok]).max() < LOGP_RTOL
+        assert grad_err(g[ok], g_o[ok]).max() < GRAD_RTOL
+        lib.octo_destroy(h)
+    # HGCA only
+    blocks = [b for b in d["blocks"] if b["kind"] == octo.KIND_HGCA_INSTANT]
+    packed2 = octo.pack(d["layout"], blocks)
+    h = C.c_void_p()
+    assert lib.octo_create(C.byref(consts), C.byref(packed2.layout), packed2.blocks, packed2.n_blocks, 0, C.byref(h)) == 0, lib.octo_last_error()
+    ll = np.empty(n); g = np.empty((n, n_in), order="F")
+    assert lib.octo_logp_grad(h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data) == 0, lib.octo_last_error()
+    ll_o2, g_o2 = oracle_lib.Oracle(packed2, consts).logp_grad(x, threads=4)
+    assert rel_err(ll[ok], ll_o2[ok]).max() < LOGP_RTOL and grad_err(g[ok], g_o2[ok]).max() < GRAD_RTOL
     lib.octo_destroy(h)
