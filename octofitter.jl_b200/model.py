@@ -297,14 +297,26 @@ class Planet:
     """Planet(name=, basis=, variables=, observations=) — src/variables.jl:468-508.
 
     variables: names of this planet's natural-space variables (e.g. "a","e","i","ω","Ω","tp","mass").
-    Only the Visual{KepOrbit} basis is offloaded.
+    Bases: Visual{KepOrbit}, and RadialVelocityOrbit (PlanetOrbits: a, e, ω, tp, M only — the orbit as radial
+    velocities see it, K without the sin i factor).  The latter is the same kernel with i = π/2 (sin i = 1 exactly),
+    Ω = 0 and an arbitrary parallax injected as constants, so it needs the dict form of `variables`; astrometry
+    cannot be attached to it.
     """
 
     def __init__(self, *, name, basis="Visual{KepOrbit}", variables, observations=()):
-        if basis not in ("Visual{KepOrbit}", "VisualKepOrbit"):
-            raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}}")
+        if basis not in ("Visual{KepOrbit}", "VisualKepOrbit", "RadialVelocityOrbit"):
+            raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}} and RadialVelocityOrbit")
         self.name = str(name)
-        self.basis = "Visual{KepOrbit}"
+        self.basis = "RadialVelocityOrbit" if basis == "RadialVelocityOrbit" else "Visual{KepOrbit}"
+        if self.basis == "RadialVelocityOrbit":
+            if not isinstance(variables, dict):
+                raise ValueError("RadialVelocityOrbit needs variables as a dict (i, Ω and plx are injected as constants)")
+            if any(o.kind in (_abi.KIND_ASTROM_RADEC, _abi.KIND_ASTROM_PASEP) for o in observations):
+                raise ValueError("a RadialVelocityOrbit has no sky-plane projection: astrometry cannot be attached to it")
+            variables = dict(variables)
+            for k, v in (("i", np.pi / 2), ("Ω", 0.0), ("plx", 1.0)):
+                if _ALIASES.get(k, k) not in {_ALIASES.get(n, n) for n in variables}:
+                    variables[k] = v
         self.var_specs = _norm_variables(variables)
         self.variables = tuple(n for n, _ in self.var_specs)
         self.observations = list(observations)

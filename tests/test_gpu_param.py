@@ -304,3 +304,27 @@ def test_hgca_model_with_priors_on_device(oracle_lib):
     assert np.isfinite(lp_o).all()
     assert rel_err(lp, lp_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
     assert rel_err(model.ℓπcallback(th), lp_o).max() < LOGP_RTOL
+
+
+def test_radial_velocity_orbit_basis(oracle_lib):
+    """Planet(basis="RadialVelocityOrbit"): the RV-only orbit (no i, Ω, plx) is the same kernel with i = π/2, Ω = 0
+    injected as constants; K carries no sin i factor (sin(π/2) == 1.0 exactly)."""
+    rng = np.random.default_rng(52)
+    ep = np.sort(rng.uniform(58000, 59500, 40))
+    rv = octo.StarAbsoluteRVObs(octo.Table(epoch=ep, rv=30 * np.sin(ep / 60.0) + rng.normal(0, 5, 40), σ_rv=np.full(40, 5.0)),
+                                name="HARPS", variables={"offset": octo.Normal(0, 100), "jitter": octo.LogUniform(0.1, 100.0)})
+    b = octo.Planet(name="b", basis="RadialVelocityOrbit", variables={
+        "a": octo.LogUniform(0.1, 10), "e": octo.Uniform(0, 0.9), "ω": octo.UniformCircular(),
+        "tp": octo.Uniform(57500, 59000), "mass": octo.LogUniform(0.1, 100)})
+    system = octo.System(name="rvonly", companions=[b], observations=[rv],
+                         variables={"M": octo.truncated(octo.Normal(1.0, 0.05), lower=0.1)})
+    spec = octo.ModelSpec(system)
+    assert float(np.sin(np.pi / 2)) == 1.0
+    model = octo.LogDensityModel(spec)
+    th = rng.normal(0, 0.8, (64, spec.D))
+    lp, g = model.ℓπcallback_grad(th)
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    assert np.isfinite(lp_o).all() and rel_err(lp, lp_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+    with pytest.raises(ValueError):
+        octo.Planet(name="c", basis="RadialVelocityOrbit", variables={"a": 1.0},
+                    observations=[octo.PlanetRelAstromObs(octo.Table(epoch=[5e4], ra=[1.], dec=[1.], σ_ra=[1.], σ_dec=[1.]), name="x")])
