@@ -145,7 +145,20 @@ typedef struct OctoLayout {
     int32_t idx_tp  [OCTO_MAX_PLANETS];
     int32_t idx_M   [OCTO_MAX_PLANETS];
     int32_t idx_mass[OCTO_MAX_PLANETS];   /* Mjup, or -1 */
+    /* Orbit basis per planet: 0 = Visual{KepOrbit} (Campbell elements above), 1 = ThieleInnesOrbit
+     * (docs/src/thiele-innes.md; PlanetOrbits): the planet's inputs are e, tp, M, plx and the Thiele-Innes
+     * constants A, B, F, G in mas (columns idx_A.. below; idx_a, idx_i, idx_w, idx_W are ignored).  The semi-major
+     * axis that sets the period is a = sqrt(u + sqrt((u+v)(u-v))) / plx, u = (A²+B²+F²+G²)/2, v = AG - BF
+     * (src/parameterizations.jl:14-18); ra = xB + yG, dec = xA + yF with x = cos E - e, y = sqrt(1-e²) sin E
+     * (:346-353).  Radial-velocity tables cannot be combined with a Thiele-Innes planet (not offloaded). */
+    int32_t basis   [OCTO_MAX_PLANETS];
+    int32_t idx_A   [OCTO_MAX_PLANETS];
+    int32_t idx_B   [OCTO_MAX_PLANETS];
+    int32_t idx_F   [OCTO_MAX_PLANETS];
+    int32_t idx_G   [OCTO_MAX_PLANETS];
 } OctoLayout;
+#define OCTO_BASIS_CAMPBELL     0
+#define OCTO_BASIS_THIELE_INNES 1
 
 typedef struct OctoCtx OctoCtx;
 
@@ -198,9 +211,12 @@ typedef struct OctoPrior {
 #define OCTO_IN_TPERI 3   /* tp = θ_at_epoch_to_tperi(in[a[0]], value; M=in[a[1]], e=in[a[2]], a=in[a[3]],
                            * i=in[a[4]], ω=in[a[5]], Ω=in[a[6]])  (src/parameterizations.jl:6-69); the arguments
                            * are EARLIER kernel inputs (their own definitions may be PARAM / CONST / CIRC)         */
+#define OCTO_IN_TPERI_TI 4 /* the same for a ThieleInnesOrbit planet: tp = θ_at_epoch_to_tperi(in[a[0]], value; M=in[a[1]],
+                           * e=in[a[2]], plx=in[a[3]], A=in[a[4]], B=in[a[5]], F=in[a[6]], G=in[a[7]])
+                           * (src/parameterizations.jl:9-19)                                                      */
 typedef struct OctoInputDef {
     int32_t op;
-    int32_t a[7];
+    int32_t a[8];
     double  value;
 } OctoInputDef;
 

@@ -43,6 +43,8 @@ struct OctoLayout
     idx_plx::NTuple{MAXP,Int32}; idx_a::NTuple{MAXP,Int32}; idx_e::NTuple{MAXP,Int32}; idx_i::NTuple{MAXP,Int32}
     idx_w::NTuple{MAXP,Int32}; idx_W::NTuple{MAXP,Int32}; idx_tp::NTuple{MAXP,Int32}; idx_M::NTuple{MAXP,Int32}
     idx_mass::NTuple{MAXP,Int32}
+    basis::NTuple{MAXP,Int32}              # 0 Visual{KepOrbit}, 1 ThieleInnesOrbit (then idx_A.. are used instead of idx_a, idx_i, idx_w, idx_W)
+    idx_A::NTuple{MAXP,Int32}; idx_B::NTuple{MAXP,Int32}; idx_F::NTuple{MAXP,Int32}; idx_G::NTuple{MAXP,Int32}
 end
 
 octo_error() = unsafe_string(ccall((:octo_last_error, LIB), Cstring, ()))
@@ -128,7 +130,10 @@ function B200Model(model::LogDensityModel; device::Integer=0)
     layout = OctoLayout(P, length(names), ntuple(i -> idx[:plx][i], MAXP), ntuple(i -> idx[:a][i], MAXP),
         ntuple(i -> idx[:e][i], MAXP), ntuple(i -> idx[:i][i], MAXP), ntuple(i -> idx[:ω][i], MAXP),
         ntuple(i -> idx[:Ω][i], MAXP), ntuple(i -> idx[:tp][i], MAXP), ntuple(i -> idx[:M][i], MAXP),
-        ntuple(i -> idx[:mass][i], MAXP))
+        ntuple(i -> idx[:mass][i], MAXP),
+        # this glue offloads Visual{KepOrbit} planets; ThieleInnesOrbit planets would set basis = 1 and idx_A..idx_G
+        ntuple(_ -> Int32(0), MAXP), ntuple(_ -> Int32(-1), MAXP), ntuple(_ -> Int32(-1), MAXP),
+        ntuple(_ -> Int32(-1), MAXP), ntuple(_ -> Int32(-1), MAXP))
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         check(ccall((:octo_create, LIB), Cint,

@@ -45,11 +45,12 @@ _i4 = C.c_int32 * OCTO_MAX_PLANETS
 class OctoLayout(C.Structure):
     _fields_ = [("n_planets", C.c_int32), ("n_in", C.c_int32),
                 ("idx_plx", _i4), ("idx_a", _i4), ("idx_e", _i4), ("idx_i", _i4), ("idx_w", _i4),
-                ("idx_W", _i4), ("idx_tp", _i4), ("idx_M", _i4), ("idx_mass", _i4)]
+                ("idx_W", _i4), ("idx_tp", _i4), ("idx_M", _i4), ("idx_mass", _i4),
+                ("basis", _i4), ("idx_A", _i4), ("idx_B", _i4), ("idx_F", _i4), ("idx_G", _i4)]
 
 
 PRIOR_NORMAL, PRIOR_UNIFORM, PRIOR_LOGUNIFORM, PRIOR_SINE, PRIOR_TRUNCNORMAL = range(5)
-IN_PARAM, IN_CONST, IN_CIRC, IN_TPERI = range(4)
+IN_PARAM, IN_CONST, IN_CIRC, IN_TPERI, IN_TPERI_TI = range(5)
 
 
 class OctoPrior(C.Structure):
@@ -57,7 +58,7 @@ class OctoPrior(C.Structure):
 
 
 class OctoInputDef(C.Structure):
-    _fields_ = [("op", C.c_int32), ("a", C.c_int32 * 7), ("value", C.c_double)]
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32 * 8), ("value", C.c_double)]
 
 
 def _dptr(a):
@@ -87,10 +88,12 @@ def pack(layout_dict: dict, block_dicts: list) -> PackedModel:
         raise ValueError(f"1..{OCTO_MAX_PLANETS} planets supported, got {len(planets)}")
     L.n_planets = len(planets)
     L.n_in = int(layout_dict["n_in"])
-    for f in ("plx", "a", "e", "i", "w", "W", "tp", "M", "mass"):
+    for f in ("plx", "a", "e", "i", "w", "W", "tp", "M", "mass", "A", "B", "F", "G"):
         arr = getattr(L, "idx_" + f)
         for p in range(OCTO_MAX_PLANETS):
             arr[p] = int(planets[p].get(f, -1)) if p < len(planets) else -1
+    for p in range(OCTO_MAX_PLANETS):
+        L.basis[p] = int(planets[p].get("basis", 0)) if p < len(planets) else 0
     keep, blocks = [], []
     for bd in block_dicts:
         cols = {}

@@ -70,6 +70,10 @@ struct DevModel {
     int32_t idx_plx[OCTO_MAX_PLANETS], idx_a[OCTO_MAX_PLANETS], idx_e[OCTO_MAX_PLANETS], idx_i[OCTO_MAX_PLANETS],
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],
             idx_mass[OCTO_MAX_PLANETS];
+    // Thiele-Innes planets (basis 1): columns of A, B, F, G; their idx_a is the VIRTUAL gradient column n_in + p (the
+    // semi-major axis is an intermediate there: a = alpha(A,B,F,G) / plx), idx_i / idx_w / idx_W are -1
+    int32_t basis[OCTO_MAX_PLANETS], idx_A[OCTO_MAX_PLANETS], idx_B[OCTO_MAX_PLANETS], idx_F[OCTO_MAX_PLANETS],
+            idx_G[OCTO_MAX_PLANETS];
     DevBlock blocks[OCTO_MAX_BLOCKS];
     int32_t n_hg, pad1;
     DevHg hg[OCTO_MAX_HGCA];

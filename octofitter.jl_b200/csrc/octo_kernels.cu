@@ -548,7 +548,13 @@ __device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 
 // returns validity of what the task looked at
 __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
                               double* sc, int lane) {
+    const bool ti = m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
+        if (ti) {            // no angles: neutral values for the slots the Campbell code reads
+            const int ks = kind == 0 ? PC_sini : (kind == 1 ? PC_sinw : PC_sinW);
+            sc[ks * 32 + lane] = 0.0; sc[(ks + 1) * 32 + lane] = 1.0;
+            return true;
+        }
         const int idx = kind == 0 ? m.idx_i[p] : (kind == 1 ? m.idx_w[p] : m.idx_W[p]);
         const double x = in[c + (int64_t)idx * ld];
         const bool ok = isfinite(x) && fabs(x) < 1e9;
@@ -572,9 +578,21 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     // division and square root (KepOrbit ctor + orbitsolve: n = 2π / (√(a³/M)·kyd / y2d), MA = n / y2d · (t - tp)):
     // its last bit is multiplied by |MA| (thousands of radians for short periods), so anything else would cost
     // parity digits in exactly the regime where the problem is already ill-conditioned.
-    double a = in[c + (int64_t)m.idx_a[p] * ld], tp = in[c + (int64_t)m.idx_tp[p] * ld];
+    double tp = in[c + (int64_t)m.idx_tp[p] * ld];
     double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
     double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
+    double a;
+    if (ti) {
+        // ThieleInnesOrbit: a = sqrt(u + sqrt((u+v)(u-v))) / plx (src/parameterizations.jl:14-18); the constants and
+        // the pieces of that formula are kept for the projection and the chain rule (slots unused by this basis)
+        const double A = in[c + (int64_t)m.idx_A[p] * ld], B = in[c + (int64_t)m.idx_B[p] * ld];
+        const double F = in[c + (int64_t)m.idx_F[p] * ld], G = in[c + (int64_t)m.idx_G[p] * ld];
+        const double u = 0.5 * (A * A + B * B + F * F + G * G), v = A * G - B * F;
+        const double wq = sqrt((u + v) * (u - v)), alpha = sqrt(u + wq);
+        a = (isfinite(plx) && plx > 0.0) ? alpha / plx : -1.0;
+        sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = B; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
+        sc[PC_K * 32 + lane] = u; sc[PC_Kb * 32 + lane] = v; sc[PC_Pc * 32 + lane] = wq; sc[PC_Ps * 32 + lane] = alpha;
+    } else a = in[c + (int64_t)m.idx_a[p] * ld];
     const bool fin = isfinite(a) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
     const bool ok = fin && (a > 0.0) && (M > 0.0) && (plx > 0.0);
     if (!ok) { a = 1.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
@@ -589,12 +607,18 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     sc[PC_a * 32 + lane] = a;          sc[PC_inv_a * 32 + lane] = inv_a;
     sc[PC_M * 32 + lane] = M;          sc[PC_inv_M * 32 + lane] = inv_M;
     sc[PC_plx * 32 + lane] = plx;      sc[PC_c2a * 32 + lane] = c2a; sc[PC_sc * 32 + lane] = a * c2a;
-    sc[PC_Kb * 32 + lane] = m.kappa * Moa * rsqrt_nr(Moa);      // K s / sin i  (finished in prologue_products)
+    if (!ti) sc[PC_Kb * 32 + lane] = m.kappa * Moa * rsqrt_nr(Moa);      // K s / sin i  (finished in prologue_products)
     sc[PC_mu * 32 + lane] = mass * m.c.mjup2msol * inv_M;
     return ok;
 }
 
-__device__ __noinline__ void prologue_products(double* sc, int lane) {
+__device__ __noinline__ void prologue_products(double* sc, int lane, bool ti) {
+    if (ti) {      // ra = X B + sinE s G, dec = X A + sinE s F [mas]; no radial velocity for this basis
+        const double s = sc[PC_s * 32 + lane];
+        sc[PC_Bh * 32 + lane] = sc[PC_B * 32 + lane]; sc[PC_Gs * 32 + lane] = s * sc[PC_G * 32 + lane];
+        sc[PC_Ah * 32 + lane] = sc[PC_A * 32 + lane]; sc[PC_Fs * 32 + lane] = s * sc[PC_F * 32 + lane];
+        return;
+    }
     const double sW = sc[PC_sinW * 32 + lane], cW = sc[PC_cosW * 32 + lane], sw = sc[PC_sinw * 32 + lane];
     const double cw = sc[PC_cosw * 32 + lane], si = sc[PC_sini * 32 + lane], ci = sc[PC_cosi * 32 + lane];
     const double s = sc[PC_s * 32 + lane], scl = sc[PC_sc * 32 + lane];
@@ -703,6 +727,16 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
         auto C = [&](int k) { return sc[k * 32 + lane]; };
         auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
         const double e = C(PC_e), s = C(PC_s), inv_s = C(PC_inv_s), inv_a = C(PC_inv_a), inv_M = C(PC_inv_M);
+        const bool ti = m.basis[p] == OCTO_BASIS_THIELE_INNES;
+        if (ti && part < 3) {
+            if (part == 1) {      // Bh = B, Gs = s G, Ah = A, Fs = s F
+                const double gGs = Rp(PA_Gs), gFs = Rp(PA_Fs);
+                gp[m.idx_B[p] * 32 + lane] += Rp(PA_Bh); gp[m.idx_G[p] * 32 + lane] += gGs * s;
+                gp[m.idx_A[p] * 32 + lane] += Rp(PA_Ah); gp[m.idx_F[p] * 32 + lane] += gFs * s;
+                gp[m.idx_e[p] * 32 + lane] += -(e * inv_s) * (gGs * C(PC_G) + gFs * C(PC_F));
+            }
+            continue;
+        }
         if (part == 1) {
             // astrometry: Bh = sc*B, Gs = sc*s*G, Ah = sc*A, Fs = sc*s*F with sc = a*c2a
             const double sW = C(PC_sinW), cW = C(PC_cosW), sw = C(PC_sinw), cw = C(PC_cosw), si = C(PC_sini);
@@ -879,11 +913,11 @@ struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *trig, *part, *lp, *extra;
 __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
     ParamSmem S;
     S.th = base; S.dxdy = S.th + D * 32; S.gth = S.dxdy + D * 32; S.L = S.gth + D * 32; S.aux = S.L + D * 32;
-    S.trig = S.aux + n_in * 32; S.part = S.trig + T * 9 * 32; S.lp = S.part + T * 7 * 32; S.extra = S.lp + 32;
+    S.trig = S.aux + n_in * 32; S.part = S.trig + T * 9 * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
     S.flags = reinterpret_cast<int*>(S.extra + 32);
     return S;
 }
-__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 16 * T + 3) * 32; }
+__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 17 * T + 3) * 32; }
 
 __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
                                            int64_t ld, double* s_in, const ParamSmem& S, int* s_ok, int w, int W, int lane) {
@@ -923,6 +957,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
         for (int it = w; it < 4 * T; it += W) {
             const int t = it >> 2, q = it & 3;
             const OctoInputDef& d = P.defs[P.tperi_k[t]];
+            if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
             double sn, cs;
             sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
             S.trig[(t * 9 + 2 * q) * 32 + lane] = sn; S.trig[(t * 9 + 2 * q + 1) * 32 + lane] = cs;
@@ -933,13 +968,14 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
         for (int t = w; t < T; t += W) {
             const int k = P.tperi_k[t];
             const OctoInputDef& d = P.defs[k];
-            double arg[7], trig[8];
+            const bool ti = d.op == OCTO_IN_TPERI_TI;
+            double arg[8], trig[8];
 #pragma unroll
-            for (int q = 0; q < 7; ++q) arg[q] = s_in[d.a[q] * 32 + lane];
+            for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
             double MA;
-            s_in[k * 32 + lane] = tperi_value(m.c, d.value, arg, trig, &MA);
+            s_in[k * 32 + lane] = tperi_value(m.c, d.value, arg, trig, &MA, ti);
             S.trig[(t * 9 + 8) * 32 + lane] = MA;
         }
         __syncthreads();
@@ -973,14 +1009,16 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
 #pragma unroll 1
     for (int t = w; t < T; t += W) {
         const OctoInputDef& d = P.defs[P.tperi_k[t]];
-        double arg[7], trig[8], part[7];
+        const bool ti = d.op == OCTO_IN_TPERI_TI;
+        double arg[8], trig[8], part[8];
 #pragma unroll
-        for (int q = 0; q < 7; ++q) arg[q] = s_in[d.a[q] * 32 + lane];
+        for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
-        tperi_reverse(m.c, arg, trig, S.trig[(t * 9 + 8) * 32 + lane], part);
+        part[7] = 0.0;
+        tperi_reverse(m.c, arg, trig, S.trig[(t * 9 + 8) * 32 + lane], part, ti);
 #pragma unroll
-        for (int q = 0; q < 7; ++q) S.part[(t * 7 + q) * 32 + lane] = part[q];
+        for (int q = 0; q < 8; ++q) S.part[(t * 8 + q) * 32 + lane] = part[q];
     }
     __syncthreads();
     PTICK(1);
@@ -990,8 +1028,9 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
             const int k = P.tperi_k[t];
             const OctoInputDef& d = P.defs[k];
             const double gk = S.aux[k * 32 + lane];
+            const int na = d.op == OCTO_IN_TPERI_TI ? 8 : 7;
 #pragma unroll
-            for (int q = 0; q < 7; ++q) S.aux[d.a[q] * 32 + lane] += gk * S.part[(t * 7 + q) * 32 + lane];
+            for (int q = 0; q < 8; ++q) if (q < na) S.aux[d.a[q] * 32 + lane] += gk * S.part[(t * 8 + q) * 32 + lane];
         }
     }
     PTICK(2);
@@ -1103,7 +1142,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     // ---- phase 2: Thiele-Innes / RV products
 #pragma unroll 1
     for (int it = threadIdx.x; it < ncol * m.n_planets; it += W * 32)
-        prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol);
+        prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
     __syncthreads();
     OCTO_TICK();
 
@@ -1199,10 +1238,11 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         for (int h = 0; h < m.n_hg; ++h) hgca_tail<GRAD>(m, m.hg[h], s_const, s_red, s_acc, s_in, n_acc, w, W, lane);
     }
     // ---- epilogue (see epilogue_part): gradient parts live in the now free per-warp accumulator area
-    double* s_gp = s_acc;                                     // [EPI_PARTS][n_in][32]
+    double* s_gp = s_acc;                                     // [EPI_PARTS][n_g][32]
+    const int n_g = m.n_in + m.n_planets;                     // + one virtual column per planet (Thiele-Innes: d/da)
     if (GRAD) {
 #pragma unroll 1
-        for (int idx = threadIdx.x; idx < EPI_PARTS * m.n_in * 32; idx += W * 32) s_gp[idx] = 0.0;
+        for (int idx = threadIdx.x; idx < EPI_PARTS * n_g * 32; idx += W * 32) s_gp[idx] = 0.0;
     }
     __syncthreads();
     if (m.has_margin) {
@@ -1211,7 +1251,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     if (GRAD) {
 #pragma unroll 1
-        for (int part = w; part < EPI_PARTS; part += W) epilogue_part(part, m, s_const, s_red, s_gp + part * m.n_in * 32, lane);
+        for (int part = w; part < EPI_PARTS; part += W) epilogue_part(part, m, s_const, s_red, s_gp + part * n_g * 32, lane);
     }
     if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
         const bool active = chain0 + lane < n_chains;
@@ -1231,9 +1271,31 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     if (GRAD) {
         __syncthreads();
-        const int ng = m.n_in * 32;
+        const int ng = n_g * 32;
+        // Thiele-Innes planets: hand d ll / da (virtual column) on to A, B, F, G and plx:  a = alpha / plx,
+        // alpha² = u + w, w² = (u+v)(u-v)  =>  d alpha/dX = (du/dX + (u du/dX - v dv/dX) / w) / (2 alpha)
+        bool any_ti = false;
 #pragma unroll 1
-        for (int idx = threadIdx.x; idx < ng; idx += W * 32) {
+        for (int p = 0; p < m.n_planets && w == 0; ++p) {       // one warp: planets may share the plx column
+            if (m.basis[p] != OCTO_BASIS_THIELE_INNES) continue;
+            const double* sc = s_const + p * PC_COUNT * 32;
+            const int va = (m.n_in + p) * 32 + lane;
+            const double ga = ((s_gp[va] + s_gp[ng + va]) + s_gp[2 * ng + va]) + s_gp[3 * ng + va];
+            const double A = sc[PC_A * 32 + lane], B = sc[PC_B * 32 + lane], F = sc[PC_F * 32 + lane], G = sc[PC_G * 32 + lane];
+            const double u = sc[PC_K * 32 + lane], v = sc[PC_Kb * 32 + lane], wq = sc[PC_Pc * 32 + lane], alpha = sc[PC_Ps * 32 + lane];
+            const double a = sc[PC_a * 32 + lane], plx = sc[PC_plx * 32 + lane];
+            const double k = ga / (2.0 * alpha * plx), iw = 1.0 / wq;
+            s_gp[m.idx_A[p] * 32 + lane] += k * (A + (u * A - v * G) * iw);
+            s_gp[m.idx_B[p] * 32 + lane] += k * (B + (u * B + v * F) * iw);
+            s_gp[m.idx_F[p] * 32 + lane] += k * (F + (u * F + v * B) * iw);
+            s_gp[m.idx_G[p] * 32 + lane] += k * (G + (u * G - v * A) * iw);
+            s_gp[m.idx_plx[p] * 32 + lane] -= ga * a / plx;
+        }
+#pragma unroll 1
+        for (int p = 0; p < m.n_planets; ++p) any_ti = any_ti || m.basis[p] == OCTO_BASIS_THIELE_INNES;
+        if (any_ti) __syncthreads();
+#pragma unroll 1
+        for (int idx = threadIdx.x; idx < m.n_in * 32; idx += W * 32) {
             const int l = idx & 31;
             const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
             if (P) PS.aux[idx] = (PS.flags[l] & 8) ? v : 0.0;
@@ -1276,7 +1338,7 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
 
 // D > 0: with the fused parameterisation stage (D parameters, T θ_at_epoch_to_tperi definitions)
 size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
-    size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * m.n_in * 32;      // the epilogue's gradient parts reuse the accumulator area
+    size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * (m.n_in + m.n_planets) * 32;      // the epilogue's gradient parts reuse the accumulator area
     size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
     if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32;
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);

@@ -68,13 +68,14 @@ k_param_forward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMode
     if (s == 0) {
         for (int k = 0; k < n_in; ++k) {
             const OctoInputDef& d = P.defs[k];
-            if (d.op == OCTO_IN_TPERI) {
-                double arg[7], trig[8];
-                for (int q = 0; q < 7; ++q) arg[q] = S.in[d.a[q]];
-                sincos(arg[0], &trig[0], &trig[1]); sincos(arg[4], &trig[2], &trig[3]);
-                sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]);
+            if (d.op == OCTO_IN_TPERI || d.op == OCTO_IN_TPERI_TI) {
+                const bool ti = d.op == OCTO_IN_TPERI_TI;
+                double arg[8], trig[8];
+                for (int q = 0; q < (ti ? 8 : 7); ++q) arg[q] = S.in[d.a[q]];
+                sincos(arg[0], &trig[0], &trig[1]);
+                if (!ti) { sincos(arg[4], &trig[2], &trig[3]); sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]); }
                 double MA;
-                S.in[k] = tperi_value(m.c, d.value, arg, trig, &MA);
+                S.in[k] = tperi_value(m.c, d.value, arg, trig, &MA, ti);
             }
         }
         bool finite_in = true;
@@ -134,15 +135,17 @@ k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMod
     if (s == 0) {
         for (int k = n_in - 1; k >= 0; --k) {
             const OctoInputDef& d = P.defs[k];
-            if (d.op != OCTO_IN_TPERI) continue;
-            double arg[7], trig[8], part[7], MA;
-            for (int q = 0; q < 7; ++q) arg[q] = S.in[d.a[q]];
-            sincos(arg[0], &trig[0], &trig[1]); sincos(arg[4], &trig[2], &trig[3]);
-            sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]);
-            tperi_value(m.c, d.value, arg, trig, &MA);
-            tperi_reverse(m.c, arg, trig, MA, part);
+            if (d.op != OCTO_IN_TPERI && d.op != OCTO_IN_TPERI_TI) continue;
+            const bool ti = d.op == OCTO_IN_TPERI_TI;
+            const int na = ti ? 8 : 7;
+            double arg[8], trig[8], part[8], MA;
+            for (int q = 0; q < na; ++q) arg[q] = S.in[d.a[q]];
+            sincos(arg[0], &trig[0], &trig[1]);
+            if (!ti) { sincos(arg[4], &trig[2], &trig[3]); sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]); }
+            tperi_value(m.c, d.value, arg, trig, &MA, ti);
+            tperi_reverse(m.c, arg, trig, MA, part, ti);
             const double gk = S.aux[k];
-            for (int q = 0; q < 7; ++q) S.aux[d.a[q]] += gk * part[q];
+            for (int q = 0; q < na; ++q) S.aux[d.a[q]] += gk * part[q];
         }
     }
     __syncthreads();

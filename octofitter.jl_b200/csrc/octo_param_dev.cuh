@@ -110,17 +110,28 @@ __device__ __forceinline__ double param_gather(const DevParam& P, int j, double 
     return g;
 }
 
-// θ_at_epoch_to_tperi, src/parameterizations.jl:6-69, Campbell branch.
-//   arguments in definition order arg[0..6] = (θ, M, e, a, i, ω, Ω); trig[0..7] = sin, cos of θ, i, ω, Ω (computed by
-//   the caller, possibly on other warps).  sin/cos of the true anomaly come from (xr, yr) / r instead of
-//   sincos(atan2(yr, xr)).  Returns tp and the mean anomaly MA (the one transcendental the reverse pass needs).
-struct TperiMid { double A, B, F, G, idet, xr, yr, ir, snu, cnu, s, u, v, iw2, q, p; };
-__device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const double* arg, const double* trig) {
-    const double st = trig[0], ct = trig[1], ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
-    const double M = arg[1], e = arg[2], a = arg[3];
+// θ_at_epoch_to_tperi, src/parameterizations.jl:6-69.
+//   Campbell branch: arguments in definition order arg[0..6] = (θ, M, e, a, i, ω, Ω); trig[0..7] = sin, cos of θ, i, ω, Ω
+//   (computed by the caller, possibly on other warps).  Thiele-Innes branch (`ti`, :9-19): arg[0..7] = (θ, M, e, plx, A,
+//   B, F, G), a = sqrt(u + sqrt((u+v)(u-v))) / plx; only trig[0..1] is used.
+//   sin/cos of the true anomaly come from (xr, yr) / r instead of sincos(atan2(yr, xr)).  Returns tp and the mean
+//   anomaly MA (the one transcendental the reverse pass needs).
+struct TperiMid { double A, B, F, G, idet, xr, yr, ir, snu, cnu, s, u, v, iw2, q, p, a, tu, tv, tw, alpha; };
+__device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const double* arg, const double* trig, bool ti) {
+    const double st = trig[0], ct = trig[1];
+    const double M = arg[1], e = arg[2];
     TperiMid m;
-    m.A = cW * cw - sW * sw * ci; m.B = sW * cw + cW * sw * ci;
-    m.F = -(cW * sw) - sW * cw * ci; m.G = -(sW * sw) + cW * cw * ci;
+    if (ti) {
+        m.A = arg[4]; m.B = arg[5]; m.F = arg[6]; m.G = arg[7];
+        m.tu = 0.5 * (m.A * m.A + m.B * m.B + m.F * m.F + m.G * m.G); m.tv = m.A * m.G - m.B * m.F;
+        m.tw = sqrt((m.tu + m.tv) * (m.tu - m.tv)); m.alpha = sqrt(m.tu + m.tw);
+        m.a = m.alpha / arg[3];
+    } else {
+        const double ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
+        m.A = cW * cw - sW * sw * ci; m.B = sW * cw + cW * sw * ci;
+        m.F = -(cW * sw) - sW * cw * ci; m.G = -(sW * sw) + cW * cw * ci;
+        m.a = arg[3]; m.tu = m.tv = m.tw = m.alpha = 0.0;
+    }
     m.idet = 1.0 / (m.A * m.G - m.F * m.B);
     m.xr = (m.G * ct - m.F * st) * m.idet; m.yr = (m.A * st - m.B * ct) * m.idet;
     m.ir = rsqrt(m.xr * m.xr + m.yr * m.yr);
@@ -129,28 +140,28 @@ __device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const doub
     m.u = -(m.s * m.snu); m.v = -e - m.cnu;
     m.iw2 = 1.0 / (e * m.cnu + 1.0);
     m.q = e * m.s * m.snu * m.iw2;
-    m.p = sqrt(a * a * a / M) * (c.kepler_year_days / c.year2day);      // period [yr]
+    m.p = sqrt(m.a * m.a * m.a / M) * (c.kepler_year_days / c.year2day);      // period [yr]
     return m;
 }
 static __device__ __noinline__ double tperi_value(const OctoConstants& c, double t_ref, const double* arg, const double* trig,
-                                              double* MA_out) {
-    const TperiMid m = tperi_mid(c, arg, trig);
+                                              double* MA_out, bool ti) {
+    const TperiMid m = tperi_mid(c, arg, trig, ti);
     const double MA = atan2(m.u, m.v) + kPi - m.q;
     *MA_out = MA;
     // n = 2π / period_yrs;  tp = t_ref - MA / n * year2day
     return t_ref - MA * m.p * (c.year2day / kTwoPi);
 }
-// hand-derived reverse pass: grad[q] = ∂tp/∂arg[q].  Cheap arithmetic only (the forward intermediates are
-// recomputed, MA comes from the forward pass); this replaced 7 forward-mode dual evaluations whose code size made
-// the once-per-CTA reverse stage instruction-fetch bound.
+// hand-derived reverse pass: grad[q] = ∂tp/∂arg[q] (7 entries, or 8 for the Thiele-Innes branch).  Cheap arithmetic only
+// (the forward intermediates are recomputed, MA comes from the forward pass); this replaced forward-mode dual
+// evaluations whose code size made the once-per-CTA reverse stage instruction-fetch bound.
 static __device__ __noinline__ void tperi_reverse(const OctoConstants& c, const double* arg, const double* trig, double MA,
-                                              double* grad) {
-    const double st = trig[0], ct = trig[1], si = trig[2], ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
-    const double M = arg[1], e = arg[2], a = arg[3];
-    const TperiMid m = tperi_mid(c, arg, trig);
+                                              double* grad, bool ti) {
+    const double st = trig[0], ct = trig[1];
+    const double M = arg[1], e = arg[2];
+    const TperiMid m = tperi_mid(c, arg, trig, ti);
     const double cc = c.year2day / kTwoPi;
     const double MAb = -m.p * cc, pb = -MA * cc;                 // tp = t_ref - MA p cc
-    const double g_a = pb * 1.5 * m.p / a, g_M = -pb * 0.5 * m.p / M;
+    const double g_a = pb * 1.5 * m.p / m.a, g_M = -pb * 0.5 * m.p / M;
     // MA = atan2(u, v) + π - q
     const double qb = -MAb;
     const double w2b = -qb * m.q * m.iw2;                        // q = e s snu / w2, w2 = e cnu + 1
@@ -170,14 +181,26 @@ static __device__ __noinline__ void tperi_reverse(const OctoConstants& c, const 
     const double Ab = yd * st + detb * m.G, Bb = -yd * ct - detb * m.F;
     const double Fb = -xd * st - detb * m.B, Gb = xd * ct + detb * m.A;
     const double stb = -xd * m.F + yd * m.A, ctb = xd * m.G - yd * m.B;
+    grad[0] = stb * ct - ctb * st;                               // θ
+    grad[1] = g_M; grad[2] = eb;
+    if (ti) {
+        // a = alpha / plx, alpha² = u + w, w² = (u+v)(u-v)
+        const double plx = arg[3], k = g_a / (2.0 * m.alpha * plx), iw = 1.0 / m.tw;
+        grad[3] = -g_a * m.a / plx;
+        grad[4] = Ab + k * (m.A + (m.tu * m.A - m.tv * m.G) * iw);
+        grad[5] = Bb + k * (m.B + (m.tu * m.B + m.tv * m.F) * iw);
+        grad[6] = Fb + k * (m.F + (m.tu * m.F + m.tv * m.B) * iw);
+        grad[7] = Gb + k * (m.G + (m.tu * m.G - m.tv * m.A) * iw);
+        return;
+    }
+    const double si = trig[2], ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
     // A = cW cw - sW sw ci, B = sW cw + cW sw ci, F = -cW sw - sW cw ci, G = -sW sw + cW cw ci
     const double cWb = Ab * cw + Bb * sw * ci - Fb * sw + Gb * cw * ci;
     const double sWb = -Ab * sw * ci + Bb * cw - Fb * cw * ci - Gb * sw;
     const double cwb = Ab * cW + Bb * sW - Fb * sW * ci + Gb * cW * ci;
     const double swb = -Ab * sW * ci + Bb * cW * ci - Fb * cW - Gb * sW;
     const double cib = -Ab * sW * sw + Bb * cW * sw - Fb * sW * cw + Gb * cW * cw;
-    grad[0] = stb * ct - ctb * st;                               // θ
-    grad[1] = g_M; grad[2] = eb; grad[3] = g_a;
+    grad[3] = g_a;
     grad[4] = -cib * si;                                         // i
     grad[5] = swb * cw - cwb * sw;                               // ω
     grad[6] = sWb * cW - cWb * sW;                               // Ω

@@ -335,12 +335,22 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     if (L->n_in < 1 || L->n_in > 4096) return fail(OCTO_ERR_ARG, "n_in out of range");
     if (n_blocks < 0 || n_blocks > OCTO_MAX_BLOCKS) return fail(OCTO_ERR_ARG, "too many observation tables");
     auto col_ok = [&](int k, bool optional) { return (optional && k == -1) || (k >= 0 && k < L->n_in); };
+    bool any_ti = false;
     for (int p = 0; p < L->n_planets; ++p) {
-        if (!col_ok(L->idx_plx[p], false) || !col_ok(L->idx_a[p], false) || !col_ok(L->idx_e[p], false) ||
-            !col_ok(L->idx_i[p], false) || !col_ok(L->idx_w[p], false) || !col_ok(L->idx_W[p], false) ||
-            !col_ok(L->idx_tp[p], false) || !col_ok(L->idx_M[p], false) || !col_ok(L->idx_mass[p], true))
+        if (L->basis[p] != OCTO_BASIS_CAMPBELL && L->basis[p] != OCTO_BASIS_THIELE_INNES) return fail(OCTO_ERR_ARG, "unknown orbit basis");
+        const bool ti = L->basis[p] == OCTO_BASIS_THIELE_INNES;
+        any_ti = any_ti || ti;
+        if (!col_ok(L->idx_plx[p], false) || !col_ok(L->idx_e[p], false) || !col_ok(L->idx_tp[p], false) ||
+            !col_ok(L->idx_M[p], false) || !col_ok(L->idx_mass[p], true))
+            return fail(OCTO_ERR_ARG, "layout column index out of range");
+        if (ti ? (!col_ok(L->idx_A[p], false) || !col_ok(L->idx_B[p], false) || !col_ok(L->idx_F[p], false) || !col_ok(L->idx_G[p], false))
+               : (!col_ok(L->idx_a[p], false) || !col_ok(L->idx_i[p], false) || !col_ok(L->idx_w[p], false) || !col_ok(L->idx_W[p], false)))
             return fail(OCTO_ERR_ARG, "layout column index out of range");
     }
+    if (any_ti)
+        for (int b = 0; b < n_blocks; ++b)
+            if (blocks[b].kind == OCTO_KIND_RV_STAR_ABS || blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN || blocks[b].kind == OCTO_KIND_RV_PLANET_REL)
+                return fail(OCTO_ERR_ARG, "radial-velocity tables cannot be combined with a Thiele-Innes planet (not offloaded)");
     // HGCAInstantaneousObs tables (kind 5) are not part of the epoch list: set them aside
     std::vector<OctoObsBlock> regular;
     std::vector<OctoObsBlock> hgs;
@@ -365,6 +375,12 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         m.idx_plx[p] = L->idx_plx[p]; m.idx_a[p] = L->idx_a[p]; m.idx_e[p] = L->idx_e[p]; m.idx_i[p] = L->idx_i[p];
         m.idx_w[p] = L->idx_w[p]; m.idx_W[p] = L->idx_W[p]; m.idx_tp[p] = L->idx_tp[p]; m.idx_M[p] = L->idx_M[p];
         m.idx_mass[p] = p < L->n_planets ? L->idx_mass[p] : -1;
+        m.basis[p] = p < L->n_planets ? L->basis[p] : 0;
+        m.idx_A[p] = L->idx_A[p]; m.idx_B[p] = L->idx_B[p]; m.idx_F[p] = L->idx_F[p]; m.idx_G[p] = L->idx_G[p];
+        if (p < L->n_planets && m.basis[p] == OCTO_BASIS_THIELE_INNES) {
+            m.idx_a[p] = L->n_in + p;            // virtual gradient column: a is an intermediate of this basis
+            m.idx_i[p] = m.idx_w[p] = m.idx_W[p] = -1;
+        }
     }
     // validate tables, assign accumulator slots
     int64_t E = 0;
@@ -625,8 +641,8 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
             case OCTO_IN_PARAM: if (!th_ok(d.a[0])) return fail(OCTO_ERR_ARG, "input definition: parameter index out of range"); break;
             case OCTO_IN_CONST: break;
             case OCTO_IN_CIRC: if (!th_ok(d.a[0]) || !th_ok(d.a[1])) return fail(OCTO_ERR_ARG, "UniformCircular: parameter index out of range"); break;
-            case OCTO_IN_TPERI:
-                for (int q = 0; q < 7; ++q)
+            case OCTO_IN_TPERI: case OCTO_IN_TPERI_TI:
+                for (int q = 0; q < (d.op == OCTO_IN_TPERI_TI ? 8 : 7); ++q)
                     if (d.a[q] < 0 || d.a[q] >= k) return fail(OCTO_ERR_ARG, "θ_at_epoch_to_tperi: arguments must be earlier kernel inputs");
                 break;
             default: return fail(OCTO_ERR_ARG, "unknown input definition");
@@ -652,8 +668,11 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
     bool fusable = true;
     P.n_tperi = 0;
     for (int k = 0; k < n_in; ++k) {
-        if (P.defs[k].op != OCTO_IN_TPERI) continue;
-        for (int q = 0; q < 7; ++q) if (P.defs[P.defs[k].a[q]].op == OCTO_IN_TPERI) fusable = false;
+        if (P.defs[k].op != OCTO_IN_TPERI && P.defs[k].op != OCTO_IN_TPERI_TI) continue;
+        for (int q = 0; q < (P.defs[k].op == OCTO_IN_TPERI_TI ? 8 : 7); ++q) {
+            const int op = P.defs[P.defs[k].a[q]].op;
+            if (op == OCTO_IN_TPERI || op == OCTO_IN_TPERI_TI) fusable = false;
+        }
         if (P.n_tperi < OCTO_PARAM_TPERI_MAX) P.tperi_k[P.n_tperi] = k;
         if (++P.n_tperi > OCTO_PARAM_TPERI_MAX) { fusable = false; P.n_tperi = OCTO_PARAM_TPERI_MAX; }
     }

@@ -304,10 +304,12 @@ class Planet:
     """
 
     def __init__(self, *, name, basis="Visual{KepOrbit}", variables, observations=()):
-        if basis not in ("Visual{KepOrbit}", "VisualKepOrbit", "RadialVelocityOrbit"):
-            raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}} and RadialVelocityOrbit")
+        if basis not in ("Visual{KepOrbit}", "VisualKepOrbit", "RadialVelocityOrbit", "ThieleInnesOrbit"):
+            raise ValueError(f"basis {basis!r} is not offloaded; only Visual{{KepOrbit}}, ThieleInnesOrbit and RadialVelocityOrbit")
         self.name = str(name)
-        self.basis = "RadialVelocityOrbit" if basis == "RadialVelocityOrbit" else "Visual{KepOrbit}"
+        self.basis = basis if basis in ("RadialVelocityOrbit", "ThieleInnesOrbit") else "Visual{KepOrbit}"
+        if self.basis == "ThieleInnesOrbit" and any(o.kind == _abi.KIND_RV_PLANET_REL for o in observations):
+            raise ValueError("radial velocities of a ThieleInnesOrbit planet are not offloaded")
         if self.basis == "RadialVelocityOrbit":
             if not isinstance(variables, dict):
                 raise ValueError("RadialVelocityOrbit needs variables as a dict (i, Ω and plx are injected as constants)")
@@ -381,6 +383,16 @@ class ModelSpec:
                     names.append(f"{p.name}.{_normalizename(o.name)}.{v}")
             merged = dict(col)
             merged.update(pcol)          # merge(θ_system, θ_planet): planet wins (system.jl:117)
+            if p.basis == "ThieleInnesOrbit":
+                missing = [e for e in ("A", "B", "F", "G", "e", "tp", "M", "plx") if e not in merged]
+                if missing:
+                    raise OctoError(f"planet {p.name}: missing orbital variables {missing} for ThieleInnesOrbit")
+                if any(o.kind in (_abi.KIND_RV_STAR_ABS, _abi.KIND_RV_STAR_MARGIN) for o in system.observations):
+                    raise OctoError("star radial velocities with a ThieleInnesOrbit planet are not offloaded")
+                planets_layout.append({"basis": 1, "A": merged["A"], "B": merged["B"], "F": merged["F"], "G": merged["G"],
+                                       "e": merged["e"], "tp": merged["tp"], "M": merged["M"], "plx": merged["plx"],
+                                       "a": -1, "i": -1, "w": -1, "W": -1, "mass": pcol.get("mass", -1)})
+                continue
             missing = [e for e in _ELEMS if e not in merged]
             if missing:
                 raise OctoError(f"planet {p.name}: missing orbital variables {missing} for Visual{{KepOrbit}}")
@@ -439,12 +451,14 @@ class ModelSpec:
                     if planet is None:
                         raise OctoError("θ_at_epoch_to_tperi belongs in a planet's variables")
                     look = lambda v: incol.get(prefix + v, incol.get(v))
-                    args = [look(spec.theta)] + [look(v) for v in ("M", "e", "a", "i", "ω", "Ω")]
+                    ti = planet.basis == "ThieleInnesOrbit"
+                    needs = ("M", "e", "plx", "A", "B", "F", "G") if ti else ("M", "e", "a", "i", "ω", "Ω")
+                    args = [look(spec.theta)] + [look(v) for v in needs]
                     if any(a is None for a in args):
-                        raise OctoError(f"{prefix}{name}: θ_at_epoch_to_tperi needs θ, M, e, a, i, ω, Ω")
+                        raise OctoError(f"{prefix}{name}: θ_at_epoch_to_tperi needs θ, " + ", ".join(needs))
                     if any(a >= k for a in args):
                         raise OctoError(f"{prefix}{name}: define it after the variables it depends on")
-                    d.op, d.value = _abi.IN_TPERI, spec.theta_epoch
+                    d.op, d.value = (_abi.IN_TPERI_TI if ti else _abi.IN_TPERI), spec.theta_epoch
                     for q, a in enumerate(args):
                         d.a[q] = a
                 elif np.isscalar(spec):

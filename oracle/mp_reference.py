@@ -30,8 +30,22 @@ def kepler_E(M, e):
     return E
 
 
+def ti_semimajor(A, B, F, G, plx):
+    """a [AU] of a Thiele-Innes orbit (src/parameterizations.jl:14-18)."""
+    u = (A * A + B * B + F * F + G * G) / 2
+    v = A * G - B * F
+    return mp.sqrt(u + mp.sqrt((u + v) * (u - v))) / plx
+
+
 def planet_state(c, el, t):
     """(ra [mas], dec [mas], rv [m/s]) of the planet relative to the star at epoch t."""
+    if "A" in el:        # ThieleInnesOrbit: ra = xB + yG, dec = xA + yF [mas] (src/parameterizations.jl:346-353)
+        e, tp, M, plx = el["e"], el["tp"], el["M"], el["plx"]
+        a = ti_semimajor(el["A"], el["B"], el["F"], el["G"], plx)
+        P_days = mp.sqrt(a ** 3 / M) * c["kepler_year_days"]
+        E = kepler_E(2 * mp.pi * (t - tp) / P_days, e)
+        X, Y = mp.cos(E) - e, mp.sqrt(1 - e * e) * mp.sin(E)
+        return X * el["B"] + Y * el["G"], X * el["A"] + Y * el["F"], None
     a, e, i, w, W, tp, M, plx = (el[k] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx"))
     P_days = mp.sqrt(a ** 3 / M) * c["kepler_year_days"]
     E = kepler_E(2 * mp.pi * (t - tp) / P_days, e)
@@ -66,7 +80,11 @@ def ln_like(consts, layout, blocks, x):
     x = [mp.mpf(v) for v in x]
     els = []
     for p in layout["planets"]:
-        el = {k: x[p[k]] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx")}
+        if p.get("basis", 0) == 1:
+            el = {k: x[p[k]] for k in ("A", "B", "F", "G", "e", "tp", "M", "plx")}
+            el["a"] = ti_semimajor(el["A"], el["B"], el["F"], el["G"], el["plx"])
+        else:
+            el = {k: x[p[k]] for k in ("a", "e", "i", "w", "W", "tp", "M", "plx")}
         el["mu"] = x[p["mass"]] * c["mjup2msol"] / el["M"] if p.get("mass", -1) >= 0 else None
         els.append(el)
     ll = mp.mpf(0)
@@ -254,6 +272,17 @@ def _tperi(c, theta, t_ref, M, e, a, i, w, W):
     return t_ref - MA * P_days / (2 * mp.pi)
 
 
+def _tperi_ti(c, theta, t_ref, M, e, plx, A, B, F, G):
+    """The same for a Thiele-Innes orbit (src/parameterizations.jl:9-19): the constants are given, a follows from them."""
+    sol = mp.lu_solve(mp.matrix([[A, F], [B, G]]), mp.matrix([mp.cos(theta), mp.sin(theta)]))
+    nu = mp.atan2(sol[1], sol[0])
+    E = 2 * mp.atan(mp.sqrt((1 - e) / (1 + e)) * mp.tan(nu / 2))
+    MA = (E - e * mp.sin(E)) % (2 * mp.pi)
+    a = ti_semimajor(A, B, F, G, plx)
+    P_days = mp.sqrt(a ** 3 / M) * c["kepler_year_days"]
+    return t_ref - MA * P_days / (2 * mp.pi)
+
+
 def logpost(consts, layout, blocks, priors, defs, theta_t):
     c = _consts(consts)
     y = [mp.mpf(v) for v in theta_t]
@@ -272,6 +301,8 @@ def logpost(consts, layout, blocks, priors, defs, theta_t):
             extra += mp.log(mp.npdf(mp.log(r), 0, mp.mpf("0.1")) / r)          # LogNormal(0, 0.1) density at r
         elif op == 3:
             inp.append(_tperi(c, inp[a[0]], mp.mpf(val), *[inp[k] for k in a[1:7]]))
+        elif op == 4:
+            inp.append(_tperi_ti(c, inp[a[0]], mp.mpf(val), *[inp[k] for k in a[1:8]]))
     return lp + extra + ln_like(consts, layout, blocks, inp)
 
 

@@ -35,6 +35,9 @@ static int validate(const OctoLayout* L, const OctoObsBlock* blocks, int n_block
         if (sys) for (int p = 0; p < L->n_planets; ++p)
             if (L->idx_mass[p] < 0) { g_err = "star RV needs a mass variable on every planet"; return OCTO_ERR_ARG; }
         if (B.kind == OCTO_KIND_RV_STAR_MARGIN && B.idx_jitter < 0) { g_err = "marginalised RV needs jitter"; return OCTO_ERR_ARG; }
+        const bool rv = (B.kind == OCTO_KIND_RV_STAR_ABS || B.kind == OCTO_KIND_RV_STAR_MARGIN || B.kind == OCTO_KIND_RV_PLANET_REL);
+        if (rv) for (int p = 0; p < L->n_planets; ++p)
+            if (L->basis[p] == OCTO_BASIS_THIELE_INNES) { g_err = "radial velocities with a Thiele-Innes planet are not offloaded"; return OCTO_ERR_ARG; }
     }
     return OCTO_OK;
 }

@@ -154,6 +154,8 @@ template <int N> inline Dual<N> kepler_solver(const Dual<N>& MA, const Dual<N>& 
 // ---------------------------------------------------------------------------------------
 template <class T>
 struct Orbit {
+    bool ti = false;              // ThieleInnesOrbit: tiA..tiG [mas] replace the Campbell angles
+    T tiA, tiB, tiF, tiG;
     T a, e, i, w, W, tp, M, plx;
     T n, nu_fact, p, cosi, sini, cosW, sinW, ecosw, esinw, cosi_cosW, cosi_sinW, J, K, dist;
 };
@@ -179,6 +181,29 @@ inline Orbit<T> make_orbit(const OctoConstants& c, T a, T e, T i, T w, T W, T tp
     return o;
 }
 
+// ThieleInnesOrbit(; e, tp, M, plx, A, B, F, G) (PlanetOrbits; the in-repo restatement of its semi-major axis is
+// src/parameterizations.jl:14-18, of its projection :346-353)
+template <class T>
+inline Orbit<T> make_orbit_ti(const OctoConstants& c, T A, T B, T F, T G, T e, T tp, T M, T plx) {
+    Orbit<T> o; o.ti = true; o.tiA = A; o.tiB = B; o.tiF = F; o.tiG = G;
+    o.e = e; o.tp = tp; o.M = M; o.plx = plx;
+    T u = (A * A + B * B + F * F + G * G) / 2.0;
+    T v = A * G - B * F;
+    T alpha = sqrt(u + sqrt((u + v) * (u - v)));
+    o.a = alpha / plx;
+    const double two_pi = 6.283185307179586;
+    T period_days = sqrt(o.a * o.a * o.a / M) * c.kepler_year_days;
+    T period_yrs = period_days / c.year2day;
+    o.n = two_pi / period_yrs;
+    o.nu_fact = sqrt((1.0 + e) / (1.0 - e));
+    o.p = o.a * (1.0 - e * e);
+    o.i = T(0.0); o.w = T(0.0); o.W = T(0.0);
+    o.sini = T(0.0); o.cosi = T(1.0); o.sinW = T(0.0); o.cosW = T(1.0); o.ecosw = e; o.esinw = T(0.0);
+    o.cosi_cosW = T(1.0); o.cosi_sinW = T(0.0); o.J = T(0.0); o.K = T(0.0);
+    o.dist = 1000.0 / plx * c.pc2au;
+    return o;
+}
+
 // a4: solution at one epoch
 template <class T>
 struct Solution { T nu, EA, sinnu_w, cosnu_w, ecosnu, r, cart2angle; double t; };
@@ -198,11 +223,20 @@ inline Solution<T> orbitsolve(const OctoConstants& c, const Orbit<T>& o, double 
 }
 
 // a6, a7
+// Thiele-Innes projection: x = cos E - e, y = sqrt(1 - e²) sin E; ra = xB + yG, dec = xA + yF [mas]
+template <class T> inline void ti_xy(const Orbit<T>& o, const Solution<T>& s, T& x, T& y, T& xdot, T& ydot) {
+    T sE = sin(s.EA), cE = cos(s.EA), rt = sqrt(1.0 - o.e * o.e);
+    x = cE - o.e; y = rt * sE;
+    T Edot = o.n / (1.0 - o.e * cE);          // [rad/yr]
+    xdot = -sE * Edot; ydot = rt * cE * Edot;
+}
 template <class T> inline T raoff(const Orbit<T>& o, const Solution<T>& s) {
+    if (o.ti) { T x, y, xd, yd; ti_xy(o, s, x, y, xd, yd); return x * o.tiB + y * o.tiG; }
     T xcart = s.r * (s.cosnu_w * o.sinW + s.sinnu_w * o.cosi * o.cosW);   // [AU]
     return xcart * s.cart2angle;                                           // [mas]
 }
 template <class T> inline T decoff(const Orbit<T>& o, const Solution<T>& s) {
+    if (o.ti) { T x, y, xd, yd; ti_xy(o, s, x, y, xd, yd); return x * o.tiA + y * o.tiF; }
     T ycart = s.r * (s.cosnu_w * o.cosW - s.sinnu_w * o.cosi * o.sinW);
     return ycart * s.cart2angle;
 }
@@ -214,10 +248,12 @@ template <class T> inline T radvel(const Orbit<T>& o, const Solution<T>& s, cons
 // proper motion of the relative orbit [mas/yr] (PlanetOrbits pmra/pmdec: d(raoff)/dt, d(decoff)/dt):
 // with u = ν + ω:  d(r cos u)/dt = -J (sin u + e sin ω),  d(r sin u)/dt = J (cos u + e cos ω),  J = n a / sqrt(1 - e²) [AU/yr]
 template <class T> inline T pmra(const Orbit<T>& o, const Solution<T>& s) {
+    if (o.ti) { T x, y, xd, yd; ti_xy(o, s, x, y, xd, yd); return xd * o.tiB + yd * o.tiG; }
     T xdot = o.J * (o.cosi_cosW * (s.cosnu_w + o.ecosw) - o.sinW * (s.sinnu_w + o.esinw));
     return xdot * s.cart2angle;
 }
 template <class T> inline T pmdec(const Orbit<T>& o, const Solution<T>& s) {
+    if (o.ti) { T x, y, xd, yd; ti_xy(o, s, x, y, xd, yd); return xd * o.tiA + yd * o.tiF; }
     T ydot = -o.J * (o.cosi_sinW * (s.cosnu_w + o.ecosw) + o.cosW * (s.sinnu_w + o.esinw));
     return ydot * s.cart2angle;
 }
@@ -241,8 +277,12 @@ template <int N> inline Dual<N> rem_trunc(const Dual<N>& x, double m) { Dual<N> 
 inline bool chain_valid(const OctoLayout& L, const double* in, int64_t ld, int64_t c) {
     for (int k = 0; k < L.n_in; ++k) if (!std::isfinite(in[c + k * ld])) return false;
     for (int p = 0; p < L.n_planets; ++p) {
-        double e = in[c + L.idx_e[p] * ld], a = in[c + L.idx_a[p] * ld];
+        double e = in[c + L.idx_e[p] * ld], a;
         double M = in[c + L.idx_M[p] * ld], plx = in[c + L.idx_plx[p] * ld];
+        if (L.basis[p] == OCTO_BASIS_THIELE_INNES) {
+            const double A = in[c + L.idx_A[p] * ld], B = in[c + L.idx_B[p] * ld], F = in[c + L.idx_F[p] * ld], G = in[c + L.idx_G[p] * ld];
+            a = (A * A + B * B + F * F + G * G) > 0.0 ? 1.0 : 0.0;
+        } else a = in[c + L.idx_a[p] * ld];
         if (!(e >= 0.0 && e < 1.0) || !(a > 0.0) || !(M > 0.0) || !(plx > 0.0)) return false;
     }
     return true;
@@ -263,9 +303,14 @@ inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
 
     // orbits (system.jl:116-118)
     Orbit<T> orb[OCTO_MAX_PLANETS];
-    for (int p = 0; p < P; ++p)
-        orb[p] = make_orbit<T>(c, X[L.idx_a[p]], X[L.idx_e[p]], X[L.idx_i[p]], X[L.idx_w[p]], X[L.idx_W[p]],
-                               X[L.idx_tp[p]], X[L.idx_M[p]], X[L.idx_plx[p]]);
+    for (int p = 0; p < P; ++p) {
+        if (L.basis[p] == OCTO_BASIS_THIELE_INNES)
+            orb[p] = make_orbit_ti<T>(c, X[L.idx_A[p]], X[L.idx_B[p]], X[L.idx_F[p]], X[L.idx_G[p]], X[L.idx_e[p]],
+                                      X[L.idx_tp[p]], X[L.idx_M[p]], X[L.idx_plx[p]]);
+        else
+            orb[p] = make_orbit<T>(c, X[L.idx_a[p]], X[L.idx_e[p]], X[L.idx_i[p]], X[L.idx_w[p]], X[L.idx_W[p]],
+                                   X[L.idx_tp[p]], X[L.idx_M[p]], X[L.idx_plx[p]]);
+    }
     // HOT LOOP 1: every planet at every epoch (system.jl:156-170, 257-262)
     std::vector<Solution<T>> sols((size_t)P * (size_t)E);
     for (int p = 0; p < P; ++p)

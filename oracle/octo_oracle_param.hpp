@@ -102,6 +102,28 @@ inline T theta_at_epoch_to_tperi(const OctoConstants& c, const T& theta, double 
     return theta_epoch - MA / n * c.year2day;
 }
 
+// src/parameterizations.jl:6-69, Thiele-Innes branch (:9-19): a from the constants, T = [A F; B G] as given
+template <class T>
+inline T theta_at_epoch_to_tperi_ti(const OctoConstants& c, const T& theta, double theta_epoch, const T& M, const T& e,
+                                    const T& plx, const T& A, const T& B, const T& F, const T& G) {
+    const double pi = 3.141592653589793, two_pi = 6.283185307179586;
+    T u = (A * A + B * B + F * F + G * G) / 2.0;
+    T v = A * G - B * F;
+    T alpha = sqrt(u + sqrt((u + v) * (u - v)));
+    T a = alpha / plx;
+    T ct = cos(theta), st = sin(theta);
+    T det = A * G - F * B;
+    T x_over_r = (G * ct - F * st) / det;
+    T y_over_r = (A * st - B * ct) / det;
+    T nu = atan2(y_over_r, x_over_r);
+    T s = sqrt(1.0 - e * e);
+    T MA = atan2(-s * sin(nu), -e - cos(nu)) + pi - e * s * sin(nu) / (1.0 + e * cos(nu));
+    T period_days = sqrt(a * a * a / M) * c.kepler_year_days;
+    T period_yrs = period_days / c.year2day;
+    T n = two_pi / period_yrs;
+    return theta_epoch - MA / n * c.year2day;
+}
+
 // ℓπcallback(θ_t) for the standard model families (src/logdensitymodel.jl:110-146)
 template <class T>
 inline T logpost_chain(const OctoConstants& c, const OctoLayout& L, const OctoObsBlock* blocks, int n_blocks,
@@ -130,6 +152,10 @@ inline T logpost_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
                 in[k] = theta_at_epoch_to_tperi(c, in[d.a[0]], d.value, in[d.a[1]], in[d.a[2]], in[d.a[3]], in[d.a[4]],
                                                 in[d.a[5]], in[d.a[6]]);
                 break;
+            case OCTO_IN_TPERI_TI:
+                in[k] = theta_at_epoch_to_tperi_ti(c, in[d.a[0]], d.value, in[d.a[1]], in[d.a[2]], in[d.a[3]], in[d.a[4]],
+                                                   in[d.a[5]], in[d.a[6]], in[d.a[7]]);
+                break;
         }
     }
     // ln_prior_transformed (:128), with the reference's "healing" of a non-finite term (variables.jl:1229-1236)
@@ -145,7 +171,12 @@ like:
     if (!std::isfinite(value(lp))) return lp;                                              // :130-133
     // orbit-constructor failure => -Inf (system.jl:214-221); here: elements outside the Keplerian domain
     for (int p = 0; p < L.n_planets; ++p) {
-        const double e = value(in[L.idx_e[p]]), a = value(in[L.idx_a[p]]), M = value(in[L.idx_M[p]]), plx = value(in[L.idx_plx[p]]);
+        const double e = value(in[L.idx_e[p]]), M = value(in[L.idx_M[p]]), plx = value(in[L.idx_plx[p]]);
+        double a;
+        if (L.basis[p] == OCTO_BASIS_THIELE_INNES) {
+            const double A = value(in[L.idx_A[p]]), B = value(in[L.idx_B[p]]), F = value(in[L.idx_F[p]]), G = value(in[L.idx_G[p]]);
+            a = (A * A + B * B + F * F + G * G) > 0.0 ? 1.0 : 0.0;
+        } else a = value(in[L.idx_a[p]]);
         if (!(e >= 0.0 && e < 1.0) || !(a > 0.0) || !(M > 0.0) || !(plx > 0.0)) return T(ninf);
     }
     for (int k = 0; k < L.n_in; ++k) if (!std::isfinite(value(in[k]))) return T(ninf);

@@ -43,7 +43,7 @@ class GoldenSpec:
         self.D = len(d["theta_t"])
         self.n_in = d["layout"]["n_in"]
         self.priors = (octo.OctoPrior * self.D)(*[octo.OctoPrior(p[0], 0, (C.c_double * 4)(*p[1:])) for p in d["priors"]])
-        self.defs = (octo.OctoInputDef * len(d["defs"]))(*[octo.OctoInputDef(q[0], (C.c_int32 * 7)(*q[1]), q[2]) for q in d["defs"]])
+        self.defs = (octo.OctoInputDef * len(d["defs"]))(*[octo.OctoInputDef(q[0], (C.c_int32 * 8)(*(list(q[1]) + [0] * (8 - len(q[1])))), q[2]) for q in d["defs"]])
         self.theta_names = tuple(d["theta_names"])
 
 

@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_struct_sizes_match_header():
     assert C.sizeof(octo.OctoConstants) == 7 * 8
-    assert C.sizeof(octo.OctoLayout) == 4 * (2 + 9 * 4)
+    assert C.sizeof(octo.OctoLayout) == 4 * (2 + 14 * 4)
     assert C.sizeof(octo.OctoObsBlock) == 4 * 4 + 6 * 8 + 8 * 4 + 8
 
 

