@@ -1094,6 +1094,8 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #else
 #define OCTO_TICK() do {} while (0)
 #endif
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     OCTO_TICK();
 #ifdef OCTO_EMPTY
     if (n_chains > 0) { if (threadIdx.x == 0 && blockIdx.y == 0) ll_out[blockIdx.x] = 0.0; return; }   // launch-floor probe
@@ -1348,9 +1350,17 @@ template <bool GRAD, int NPT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             const DevParam* d_param, int post_mode, const double* d_pw_const, cudaStream_t st) {
-    k_kepler_like<GRAD, NPT><<<dim3(g.gx, g.gy), g.block, g.smem, st>>>(m, d_in, n, ld, d_ll, d_g, ldg, d_partial,
-                                                                        d_tickets, d_param, post_mode, d_pw_const);
-    return cudaGetLastError();
+    // programmatic dependent launch: the kernel lets the next launch on the stream be scheduled while it is still
+    // running (griddepcontrol.launch_dependents) and itself waits for everything before it in the stream to complete
+    // and become visible before it touches memory (griddepcontrol.wait) — stream semantics, minus the launch gap
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.gx, g.gy); cfg.blockDim = dim3(g.block); cfg.dynamicSmemBytes = g.smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
+                              post_mode, d_pw_const);
 }
 
 // opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
