@@ -463,3 +463,55 @@ def test_hgca_many_chains_and_split_geometry(oracle_lib):
     ll_o2, g_o2 = oracle_lib.Oracle(packed2, consts).logp_grad(x, threads=4)
     assert rel_err(ll[ok], ll_o2[ok]).max() < LOGP_RTOL and grad_err(g[ok], g_o2[ok]).max() < GRAD_RTOL
     lib.octo_destroy(h)
+
+
+@pytest.mark.parametrize("n_planets", [2, 4])
+def test_every_observation_kind_in_one_model(oracle_lib, n_planets):
+    """All kinds at once — RA/Dec (+cor, +jitter), PA/sep (+platescale, northangle), relative RV, star RV, marginalised
+    RV, observable-prior wrappers and HGCA — with up to 4 planets (the CTA then runs with fewer warps to fit shared
+    memory): value, gradient and value-only launch against the oracle."""
+    import workloads
+    spec, x = workloads.many_planets(n_planets, 70, seed=11, n_ep=12, extras=True)
+    assert spec.n_in <= 48
+    model = octo.LogDensityModel(spec)
+    ll, g = model.ln_like_and_gradient(x)
+    ll_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(x, threads=4)
+    assert np.isfinite(ll_o).all()
+    assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+    assert rel_err(model.ln_like(x), ll_o).max() < LOGP_RTOL
+    geom = model.launch_geometry(70)
+    assert geom[2] in (64, 128, 256)
+
+
+def test_thiele_innes_planets_with_hgca_and_observable_prior(oracle_lib):
+    """Three Thiele-Innes planets (two massive): astrometry with reflex terms, an observable-prior wrapper and HGCA; the
+    gradient w.r.t. A, B, F, G and plx runs through the virtual a-column of each planet."""
+    d, packed, consts = load_golden("case_thiele_innes")
+    import workloads
+    rng = np.random.default_rng(91)
+    base = dict(zip(d["input_names"], d["x"]))
+    astrom_b = octo.PlanetRelAstromObs(octo.Table(epoch=d["blocks"][0]["epoch"], ra=d["blocks"][0]["y1"], dec=d["blocks"][0]["y2"],
+                                                  σ_ra=d["blocks"][0]["s1"], σ_dec=d["blocks"][0]["s2"]), name="relastrom")
+    ti = ["A", "B", "F", "G", "e", "tp"]
+    pb = octo.Planet(name="b", basis="ThieleInnesOrbit", variables=ti + ["mass"], observations=[astrom_b, octo.ObsPriorAstromONeil2019(astrom_b)])
+    pc = octo.Planet(name="c", basis="ThieleInnesOrbit", variables=ti + ["mass"])
+    pd = octo.Planet(name="d", basis="ThieleInnesOrbit", variables=ti + ["mass"])
+    hg = octo.HGCAInstantaneousObs(workloads.HGCA_ROW, N_ave=2)
+    system = octo.System(name="ti3", variables=["M", "plx", "pmra", "pmdec"], companions=[pb, pc, pd], observations=[hg])
+    spec = octo.ModelSpec(system)
+    x0 = {"M": 1.21, "plx": 50.01, "pmra": 10.6, "pmdec": -4.9}
+    for nm in ("b", "c"):
+        x0.update({f"{nm}.{k}": base[f"{nm}.{k}"] for k in ti})
+    x0.update({"b.mass": 3.0, "c.mass": 25.0, "d.mass": 8.0})
+    x0.update({f"d.{k}": 0.4 * base[f"c.{k}"] if k in "ABFG" else base[f"c.{k}"] for k in ti})
+    x0["d.A"], x0["d.e"] = x0["d.A"] + 30.0, 0.3
+    xv = np.array([x0[nm] for nm in spec.input_names])
+    x = xv[None, :] * (1.0 + 0.01 * rng.standard_normal((60, len(xv))))
+    model = octo.LogDensityModel(spec)
+    ll, g = model.ln_like_and_gradient(x)
+    ll_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(x, threads=4)
+    assert np.isfinite(ll_o).all()
+    assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
+    with pytest.raises(octo.OctoError):
+        rv = octo.StarAbsoluteRVObs(octo.Table(epoch=[5e4], rv=[1.0], σ_rv=[1.0]), name="rv", variables=["offset", "jitter"])
+        octo.ModelSpec(octo.System(name="bad", variables=["M", "plx"], companions=[pc], observations=[rv]))

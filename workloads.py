@@ -130,7 +130,13 @@ def config(name):
     raise KeyError(name)
 
 
-def many_planets(n_planets, n_chains, seed, n_ep=40):
+HGCA_ROW = dict(pmra_hip=10.1, pmdec_hip=-5.2, pmra_hip_error=0.9, pmdec_hip_error=0.8, pmra_pmdec_hip=0.2,
+                pmra_hg=10.5, pmdec_hg=-5.0, pmra_hg_error=0.5, pmdec_hg_error=0.4, pmra_pmdec_hg=-0.1,
+                pmra_gaia=11.2, pmdec_gaia=-4.6, pmra_gaia_error=0.3, pmdec_gaia_error=0.25, pmra_pmdec_gaia=0.35,
+                epoch_ra_hip=1991.1, epoch_dec_hip=1991.3, epoch_ra_gaia=2016.0, epoch_dec_gaia=2016.2)
+
+
+def many_planets(n_planets, n_chains, seed, n_ep=40, extras=False):
     """3-4 planet system touching every observation kind: RA/Dec (+cor, +jitter), PA/sep (+platescale,
     northangle), relative RV, star RV and marginalised star RV; masses on all but the outermost planet."""
     rng = np.random.default_rng(seed)
@@ -148,6 +154,10 @@ def many_planets(n_planets, n_chains, seed, n_ep=40):
             obs.append(octo.PlanetRelAstromObs(tab, name=f"cam{k}", variables=["jitter"] if k == 2 else []))
             if k == 2:
                 truth[f"{names[k]}.cam{k}.jitter"] = 1.5
+            if extras:          # the observable-based prior wrapped around the same table (its own copy of the variables)
+                obs.append(octo.ObsPriorAstromONeil2019(obs[-1]))
+                if k == 2:
+                    truth[f"{names[k]}.obspri_cam{k}.jitter"] = 1.2
         else:
             ra, dec, _, _ = _state(el, ep)
             for o in inner:
@@ -172,7 +182,11 @@ def many_planets(n_planets, n_chains, seed, n_ep=40):
     s2 = octo.MarginalizedStarAbsoluteRVObs(octo.Table(epoch=eps[13:], rv=-12 + rv[13:] + 4 * rng.standard_normal(12),
                                                        σ_rv=np.full(12, 4.0)), name="hires")
     truth.update({"harps.offset": 30.0, "hires.jitter": 2.0})
-    system = octo.System(name="many", variables=["M", "plx"], companions=planets, observations=[s1, s2])
+    sysobs, sysvars = [s1, s2], ["M", "plx"]
+    if extras:                  # Hipparcos-Gaia proper-motion anomaly next to everything else
+        sysobs.append(octo.HGCAInstantaneousObs(HGCA_ROW, N_ave=4)); sysvars += ["pmra", "pmdec"]
+        truth.update({"pmra": 10.6, "pmdec": -4.9})
+    system = octo.System(name="many", variables=sysvars, companions=planets, observations=sysobs)
     spec = octo.ModelSpec(system)
     return spec, _chains(spec, truth, n_chains, rng, rel=0.01)
 
