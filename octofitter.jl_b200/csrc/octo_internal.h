@@ -75,7 +75,7 @@ struct DevModel {
     int32_t basis[OCTO_MAX_PLANETS], idx_A[OCTO_MAX_PLANETS], idx_B[OCTO_MAX_PLANETS], idx_F[OCTO_MAX_PLANETS],
             idx_G[OCTO_MAX_PLANETS];
     DevBlock blocks[OCTO_MAX_BLOCKS];
-    int32_t n_hg, pad1;
+    int32_t n_hg, any_ti;         // any_ti: some planet uses the Thiele-Innes basis
     DevHg hg[OCTO_MAX_HGCA];
     // device table, one 48-byte record per epoch of the concatenated list: [t, y1, c1, y2, c2, c3]
     //   astrometry: c1,c2,c3 = w11,w12,w22 (no jitter) | σ1², σ2², cor (jitter);   RV: c1 = 1/σ² | σ² (y2,c2,c3 unused)

@@ -545,10 +545,24 @@ __device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 
     return y;
 }
 
+// ThieleInnesOrbit: a = sqrt(u + sqrt((u+v)(u-v))) / plx (src/parameterizations.jl:14-18); the constants and the pieces
+// of that formula are kept for the projection and the chain rule (in slots this basis does not otherwise use).
+// Out of line: models without such planets never fetch this code.
+__device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const double* __restrict__ in, int64_t c, int64_t ld,
+                                            double plx, double* sc, int lane) {
+    const double A = in[c + (int64_t)m.idx_A[p] * ld], B = in[c + (int64_t)m.idx_B[p] * ld];
+    const double F = in[c + (int64_t)m.idx_F[p] * ld], G = in[c + (int64_t)m.idx_G[p] * ld];
+    const double u = 0.5 * (A * A + B * B + F * F + G * G), v = A * G - B * F;
+    const double wq = sqrt((u + v) * (u - v)), alpha = sqrt(u + wq);
+    sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = B; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
+    sc[PC_K * 32 + lane] = u; sc[PC_Kb * 32 + lane] = v; sc[PC_Pc * 32 + lane] = wq; sc[PC_Ps * 32 + lane] = alpha;
+    return (isfinite(plx) && plx > 0.0) ? alpha / plx : -1.0;
+}
+
 // returns validity of what the task looked at
 __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
                               double* sc, int lane) {
-    const bool ti = m.basis[p] == OCTO_BASIS_THIELE_INNES;
+    const bool ti = m.any_ti && m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
         if (ti) {            // no angles: neutral values for the slots the Campbell code reads
             const int ks = kind == 0 ? PC_sini : (kind == 1 ? PC_sinw : PC_sinW);
@@ -581,18 +595,7 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     double tp = in[c + (int64_t)m.idx_tp[p] * ld];
     double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
     double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
-    double a;
-    if (ti) {
-        // ThieleInnesOrbit: a = sqrt(u + sqrt((u+v)(u-v))) / plx (src/parameterizations.jl:14-18); the constants and
-        // the pieces of that formula are kept for the projection and the chain rule (slots unused by this basis)
-        const double A = in[c + (int64_t)m.idx_A[p] * ld], B = in[c + (int64_t)m.idx_B[p] * ld];
-        const double F = in[c + (int64_t)m.idx_F[p] * ld], G = in[c + (int64_t)m.idx_G[p] * ld];
-        const double u = 0.5 * (A * A + B * B + F * F + G * G), v = A * G - B * F;
-        const double wq = sqrt((u + v) * (u - v)), alpha = sqrt(u + wq);
-        a = (isfinite(plx) && plx > 0.0) ? alpha / plx : -1.0;
-        sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = B; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
-        sc[PC_K * 32 + lane] = u; sc[PC_Kb * 32 + lane] = v; sc[PC_Pc * 32 + lane] = wq; sc[PC_Ps * 32 + lane] = alpha;
-    } else a = in[c + (int64_t)m.idx_a[p] * ld];
+    double a = ti ? ti_semimajor(m, p, in, c, ld, plx, sc, lane) : in[c + (int64_t)m.idx_a[p] * ld];
     const bool fin = isfinite(a) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
     const bool ok = fin && (a > 0.0) && (M > 0.0) && (plx > 0.0);
     if (!ok) { a = 1.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
@@ -702,6 +705,37 @@ __device__ __noinline__ void epilogue_margin(const DevModel& m, const double* s_
     R[0 * 32 + lane] += ll;
 }
 
+// Thiele-Innes planet: Bh = B, Gs = s G, Ah = A, Fs = s F (out of line, see ti_semimajor)
+__device__ __noinline__ void epilogue_ti_astrom(const DevModel& m, int p, const double* sc, const double* R, double* gp, int lane) {
+    const double e = sc[PC_e * 32 + lane], s = sc[PC_s * 32 + lane], inv_s = sc[PC_inv_s * 32 + lane];
+    const double gGs = R[slot_planet(p, PA_Gs) * 32 + lane], gFs = R[slot_planet(p, PA_Fs) * 32 + lane];
+    gp[m.idx_B[p] * 32 + lane] += R[slot_planet(p, PA_Bh) * 32 + lane]; gp[m.idx_G[p] * 32 + lane] += gGs * s;
+    gp[m.idx_A[p] * 32 + lane] += R[slot_planet(p, PA_Ah) * 32 + lane]; gp[m.idx_F[p] * 32 + lane] += gFs * s;
+    gp[m.idx_e[p] * 32 + lane] += -(e * inv_s) * (gGs * sc[PC_G * 32 + lane] + gFs * sc[PC_F * 32 + lane]);
+}
+
+// hands d ll / da of the Thiele-Innes planets (virtual column n_in + p, summed over the gradient parts) on to A, B, F, G
+// and plx:  a = alpha / plx, alpha² = u + w, w² = (u+v)(u-v)  =>  d alpha/dX = (du/dX + (u du/dX - v dv/dX) / w) / (2 alpha).
+// One warp, planets in order: they may share the plx column.
+__device__ __noinline__ void epilogue_ti_distribute(const DevModel& m, const double* s_const, double* s_gp, int ng, int lane) {
+#pragma unroll 1
+    for (int p = 0; p < m.n_planets; ++p) {
+        if (m.basis[p] != OCTO_BASIS_THIELE_INNES) continue;
+        const double* sc = s_const + p * PC_COUNT * 32;
+        const int va = (m.n_in + p) * 32 + lane;
+        const double ga = ((s_gp[va] + s_gp[ng + va]) + s_gp[2 * ng + va]) + s_gp[3 * ng + va];
+        const double A = sc[PC_A * 32 + lane], B = sc[PC_B * 32 + lane], F = sc[PC_F * 32 + lane], G = sc[PC_G * 32 + lane];
+        const double u = sc[PC_K * 32 + lane], v = sc[PC_Kb * 32 + lane], wq = sc[PC_Pc * 32 + lane], alpha = sc[PC_Ps * 32 + lane];
+        const double a = sc[PC_a * 32 + lane], plx = sc[PC_plx * 32 + lane];
+        const double k = ga / (2.0 * alpha * plx), iw = 1.0 / wq;
+        s_gp[m.idx_A[p] * 32 + lane] += k * (A + (u * A - v * G) * iw);
+        s_gp[m.idx_B[p] * 32 + lane] += k * (B + (u * B + v * F) * iw);
+        s_gp[m.idx_F[p] * 32 + lane] += k * (F + (u * F + v * B) * iw);
+        s_gp[m.idx_G[p] * 32 + lane] += k * (G + (u * G - v * A) * iw);
+        s_gp[m.idx_plx[p] * 32 + lane] -= ga * a / plx;
+    }
+}
+
 __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const double* s_const, const double* R, double* gp,
                                            int lane) {
     if (part == 0) {
@@ -727,14 +761,8 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
         auto C = [&](int k) { return sc[k * 32 + lane]; };
         auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
         const double e = C(PC_e), s = C(PC_s), inv_s = C(PC_inv_s), inv_a = C(PC_inv_a), inv_M = C(PC_inv_M);
-        const bool ti = m.basis[p] == OCTO_BASIS_THIELE_INNES;
-        if (ti && part < 3) {
-            if (part == 1) {      // Bh = B, Gs = s G, Ah = A, Fs = s F
-                const double gGs = Rp(PA_Gs), gFs = Rp(PA_Fs);
-                gp[m.idx_B[p] * 32 + lane] += Rp(PA_Bh); gp[m.idx_G[p] * 32 + lane] += gGs * s;
-                gp[m.idx_A[p] * 32 + lane] += Rp(PA_Ah); gp[m.idx_F[p] * 32 + lane] += gFs * s;
-                gp[m.idx_e[p] * 32 + lane] += -(e * inv_s) * (gGs * C(PC_G) + gFs * C(PC_F));
-            }
+        if (m.any_ti && part < 3 && m.basis[p] == OCTO_BASIS_THIELE_INNES) {
+            if (part == 1) epilogue_ti_astrom(m, p, sc, R, gp, lane);
             continue;
         }
         if (part == 1) {
@@ -1094,8 +1122,10 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #else
 #define OCTO_TICK() do {} while (0)
 #endif
+#ifndef OCTO_NO_PDL
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     OCTO_TICK();
 #ifdef OCTO_EMPTY
     if (n_chains > 0) { if (threadIdx.x == 0 && blockIdx.y == 0) ll_out[blockIdx.x] = 0.0; return; }   // launch-floor probe
@@ -1144,7 +1174,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     // ---- phase 2: Thiele-Innes / RV products
 #pragma unroll 1
     for (int it = threadIdx.x; it < ncol * m.n_planets; it += W * 32)
-        prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
+        prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.any_ti && m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
     __syncthreads();
     OCTO_TICK();
 
@@ -1274,28 +1304,10 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     if (GRAD) {
         __syncthreads();
         const int ng = n_g * 32;
-        // Thiele-Innes planets: hand d ll / da (virtual column) on to A, B, F, G and plx:  a = alpha / plx,
-        // alpha² = u + w, w² = (u+v)(u-v)  =>  d alpha/dX = (du/dX + (u du/dX - v dv/dX) / w) / (2 alpha)
-        bool any_ti = false;
-#pragma unroll 1
-        for (int p = 0; p < m.n_planets && w == 0; ++p) {       // one warp: planets may share the plx column
-            if (m.basis[p] != OCTO_BASIS_THIELE_INNES) continue;
-            const double* sc = s_const + p * PC_COUNT * 32;
-            const int va = (m.n_in + p) * 32 + lane;
-            const double ga = ((s_gp[va] + s_gp[ng + va]) + s_gp[2 * ng + va]) + s_gp[3 * ng + va];
-            const double A = sc[PC_A * 32 + lane], B = sc[PC_B * 32 + lane], F = sc[PC_F * 32 + lane], G = sc[PC_G * 32 + lane];
-            const double u = sc[PC_K * 32 + lane], v = sc[PC_Kb * 32 + lane], wq = sc[PC_Pc * 32 + lane], alpha = sc[PC_Ps * 32 + lane];
-            const double a = sc[PC_a * 32 + lane], plx = sc[PC_plx * 32 + lane];
-            const double k = ga / (2.0 * alpha * plx), iw = 1.0 / wq;
-            s_gp[m.idx_A[p] * 32 + lane] += k * (A + (u * A - v * G) * iw);
-            s_gp[m.idx_B[p] * 32 + lane] += k * (B + (u * B + v * F) * iw);
-            s_gp[m.idx_F[p] * 32 + lane] += k * (F + (u * F + v * B) * iw);
-            s_gp[m.idx_G[p] * 32 + lane] += k * (G + (u * G - v * A) * iw);
-            s_gp[m.idx_plx[p] * 32 + lane] -= ga * a / plx;
+        if (m.any_ti) {
+            if (w == 0) epilogue_ti_distribute(m, s_const, s_gp, ng, lane);
+            __syncthreads();
         }
-#pragma unroll 1
-        for (int p = 0; p < m.n_planets; ++p) any_ti = any_ti || m.basis[p] == OCTO_BASIS_THIELE_INNES;
-        if (any_ti) __syncthreads();
 #pragma unroll 1
         for (int idx = threadIdx.x; idx < m.n_in * 32; idx += W * 32) {
             const int l = idx & 31;
@@ -1359,6 +1371,9 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+#ifdef OCTO_NO_PDL
+    cfg.numAttrs = 0;
+#endif
     return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
                               post_mode, d_pw_const);
 }

@@ -378,6 +378,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         m.basis[p] = p < L->n_planets ? L->basis[p] : 0;
         m.idx_A[p] = L->idx_A[p]; m.idx_B[p] = L->idx_B[p]; m.idx_F[p] = L->idx_F[p]; m.idx_G[p] = L->idx_G[p];
         if (p < L->n_planets && m.basis[p] == OCTO_BASIS_THIELE_INNES) {
+            m.any_ti = 1;
             m.idx_a[p] = L->n_in + p;            // virtual gradient column: a is an intermediate of this basis
             m.idx_i[p] = m.idx_w[p] = m.idx_W[p] = -1;
         }
