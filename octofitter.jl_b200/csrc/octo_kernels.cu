@@ -1251,8 +1251,9 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
                 double t0[16], t1[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int y = min(y0 + j, gy - 1);
-                    t0[j] = __ldcg(q0 + y * stride); t1[j] = __ldcg(q1 + y * stride);
+                    const int y = y0 + j;
+                    if (y < gy) { t0[j] = __ldcg(q0 + y * stride); t1[j] = __ldcg(q1 + y * stride); }
+                    else { t0[j] = 0.0; t1[j] = 0.0; }
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) if (y0 + j < gy) { v0 += t0[j]; v1 += t1[j]; }
