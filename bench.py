@@ -309,6 +309,13 @@ def main():
     n0 = model_p._lib.octo_kernel_launches(model_p._h)
     model_p.ℓπcallback_grad(thp, out=out_p)
     post_launches = model_p._lib.octo_kernel_launches(model_p._h) - n0
+    # the same log posterior driven by the device-resident HMC explorer (octo_hmc_run): whole run on one stream
+    hmc_iters, hmc_leap = 20, 10
+    im_p = np.full(spec_p.D, 1e-4)
+    octo.device_hmc(model_p, th_p, 2, step_size=1e-3, n_leapfrog=hmc_leap, inv_mass=im_p, seed=1, keep_samples=False)
+    t0 = time.perf_counter()
+    hres = octo.device_hmc(model_p, th_p, hmc_iters, step_size=1e-3, n_leapfrog=hmc_leap, inv_mass=im_p, seed=2, keep_samples=False)
+    t_hmc = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if world > 1:
@@ -363,6 +370,10 @@ def main():
         "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "
                                 "θ_at_epoch_to_tperi on device), same tables, D = %d, pinned host buffers; %d launch(es) per step" % (spec_p.D, post_launches),
                         "value": pairs_step * args.steps / t_post, "unit": "evals/s", "ms_per_step": t_post / args.steps * 1e3},
+        "hmc_device": {"what": "octo_hmc_run on the same model: %d transitions x %d leapfrogs for %d chains, every launch on one "
+                               "stream, one synchronisation at the end (wall clock of the call, copies included)" % (hmc_iters, hmc_leap, n),
+                       "us_per_leapfrog": t_hmc / (hmc_iters * hmc_leap) * 1e6,
+                       "value": pairs_step / world * hmc_iters * hmc_leap / t_hmc, "unit": "evals/s", "accept_rate": hres["accept_rate"]},
         "gpu_launches": int(launches),
             "clocks": clocks,
         }

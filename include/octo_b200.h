@@ -243,6 +243,20 @@ int  octo_loglike_theta(OctoCtx* ctx, const double* theta_t, int64_t n_chains, i
  * column per system of `generate_system_per_epoch` — the matrix `pointwise_like` builds
  * (src/cross-validation.jl:6-49, 453-497).  HOST buffers; n_chains * epochs <= 2e9 and epochs <= 65535 per call. */
 int  octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, double* out, int64_t ldo);
+/* A device-resident, chain-batched static-trajectory HMC explorer over the log-posterior launch: n_iter transitions of
+ * n_leapfrog leapfrog steps (step_size, diagonal inverse mass inv_mass[D] or NULL = identity) for all n_chains in
+ * lockstep, everything enqueued on one stream (one small update kernel + one log-posterior launch per leapfrog), one
+ * synchronisation at the end.  The reference advances one chain at a time with AdvancedHMC (src/sampling.jl:412-423);
+ * this is the batched counterpart of its leapfrog loop, not a NUTS implementation.  Randomness is counter-based
+ * (octo_hmc_random reproduces it on the host): a run is a pure function of its arguments.
+ * HOST buffers: theta0 / theta_final column-major [n_chains x D] (ld); optional stores theta_samples
+ * [n_iter][D][n_chains], lp_samples [n_iter][n_chains]; lp_final[n_chains]; accept_rate[n_chains]. */
+int  octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n_chains, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
+                  double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
+                  double* theta_final, double* lp_final, double* accept_rate);
+/* the random numbers of transition `it` of chain `chain`: D standard normals (momentum, before the mass scaling) and the
+ * uniform of the accept step */
+void octo_hmc_random(uint64_t seed, int64_t it, int64_t chain, int32_t D, double* z, double* u);
 /* invlink only: natural-space parameters [n_chains x D] for a batch of θ_t (HOST buffers). */
 int  octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* theta_nat);
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libocto_b200.so")
-SOURCES = ["octo_kernels.cu", "octo_param.cu", "octo_shim.cu"]
+SOURCES = ["octo_kernels.cu", "octo_param.cu", "octo_hmc.cu", "octo_shim.cu"]
 DEPS = SOURCES + ["octo_internal.h", "octo_param_dev.cuh", os.path.join("..", "..", "include", "octo_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

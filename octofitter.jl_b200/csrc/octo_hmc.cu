@@ -1,0 +1,142 @@
+// octo_hmc.cu — a device-resident, chain-batched static-trajectory HMC explorer over the fused log-posterior launch
+// (SURVEY.md §8f N2).  The reference advances ONE chain at a time with AdvancedHMC (src/sampling.jl:412-423); here
+// all chains of a batch move in lockstep and nothing returns to the host between the first and the last launch of a
+// run: per leapfrog one small update kernel + one log-posterior launch, chained on one stream with programmatic
+// dependent launch.  Randomness is counter-based (splitmix64 of seed, iteration, chain, coordinate): a run is a pure
+// function of its arguments.  Arrays are column-major [n_chains x D] (chain fastest), one thread per chain.
+#include <math_constants.h>
+
+#include "octo_internal.h"
+
+namespace {
+
+__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline double u01(uint64_t s) { return ((double)(s >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+// stream of (seed, iteration): coordinate j of chain c draws from splitmix64(key ^ (c * K1 + j * K2))
+__host__ __device__ inline uint64_t hmc_key(uint64_t seed, uint64_t it) { return splitmix64(seed ^ splitmix64(it + 1)); }
+__host__ __device__ inline uint64_t hmc_draw(uint64_t key, uint64_t chain, uint64_t j) {
+    return splitmix64(key ^ (chain * 0x9E3779B97F4A7C15ULL + j * 0xD1B54A32D192ED03ULL));
+}
+
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+struct HmcBuf {
+    double *q, *lp, *g;              // current state, its log posterior and gradient
+    double *qp, *lpp, *gp;           // proposal (what the log-posterior launch reads and writes)
+    double *p, *h0;                  // momentum, initial Hamiltonian
+    double *inv_mass;                // [D]
+    double *acc;                     // [n] accepted transitions
+    double *out_theta, *out_lp;      // optional sample store [n_iter][n x D], [n_iter][n]
+};
+
+// accept/reject transition `it - 1` (it > 0), record the sample, then start transition `it` (it < n_iter):
+// fresh momentum, H0, first half kick and drift.
+__global__ void k_hmc_turn(HmcBuf b, int64_t n, int D, int it, int n_iter, double eps, uint64_t seed) {
+    pdl_sync();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (it > 0) {
+        const double lpp = b.lpp[c];
+        double kin = 0.0;
+        for (int j = 0; j < D; ++j) { const double pj = b.p[c + (int64_t)j * n]; kin += pj * pj * b.inv_mass[j]; }
+        const double h1 = -lpp + 0.5 * kin;
+        const double u = u01(hmc_draw(hmc_key(seed, it - 1), (uint64_t)c, (uint64_t)D));
+        const bool accept = isfinite(lpp) && (log(u) < b.h0[c] - h1);
+        if (accept) {
+            for (int j = 0; j < D; ++j) { b.q[c + (int64_t)j * n] = b.qp[c + (int64_t)j * n]; b.g[c + (int64_t)j * n] = b.gp[c + (int64_t)j * n]; }
+            b.lp[c] = lpp; b.acc[c] += 1.0;
+        }
+        if (b.out_lp) b.out_lp[(int64_t)(it - 1) * n + c] = b.lp[c];
+        if (b.out_theta) for (int j = 0; j < D; ++j) b.out_theta[((int64_t)(it - 1) * D + j) * n + c] = b.q[c + (int64_t)j * n];
+    }
+    if (it >= n_iter) return;
+    const uint64_t key = hmc_key(seed, it);
+    double kin = 0.0;
+    for (int j = 0; j < D; ++j) {
+        const uint64_t s = hmc_draw(key, (uint64_t)c, (uint64_t)j);
+        const double z = sqrt(-2.0 * log(u01(s))) * cospi(2.0 * u01(splitmix64(s)));      // Box-Muller
+        const double im = b.inv_mass[j];
+        double pj = z * rsqrt(im);                                                          // p ~ N(0, M), M = 1 / inv_mass
+        kin += pj * pj * im;
+        pj += 0.5 * eps * b.g[c + (int64_t)j * n];
+        b.p[c + (int64_t)j * n] = pj;
+        b.qp[c + (int64_t)j * n] = b.q[c + (int64_t)j * n] + eps * pj * im;
+    }
+    b.h0[c] = -b.lp[c] + 0.5 * kin;
+}
+
+// after a log-posterior launch on the proposal: (half) kick, and drift unless it was the last leapfrog
+__global__ void k_hmc_leap(HmcBuf b, int64_t n, int D, int last, double eps) {
+    pdl_sync();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const bool ok = isfinite(b.lpp[c]);
+    const double k = last ? 0.5 * eps : eps;
+    for (int j = 0; j < D; ++j) {
+        const double pj = b.p[c + (int64_t)j * n] + (ok ? k * b.gp[c + (int64_t)j * n] : 0.0);
+        b.p[c + (int64_t)j * n] = pj;
+        if (!last) b.qp[c + (int64_t)j * n] += eps * pj * b.inv_mass[j];
+    }
+}
+
+template <class... Args>
+cudaError_t launch_pdl(void (*kern)(Args...), int64_t n, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n + 127) / 128)); cfg.blockDim = dim3(128); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+}  // namespace
+
+// d_state: 2 * (2 n D + n) + n D + 3 n + D doubles laid out as HmcBuf expects (see octo_hmc_state_doubles)
+size_t octo_hmc_state_doubles(int64_t n, int D) { return (size_t)(2 * (2 * n * D + n) + n * D + 2 * n + D); }
+
+// logpost(d_theta [n x D], d_lp, d_g) enqueues one log-posterior + gradient evaluation on `st`
+cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
+                             double* d_out_theta, double* d_out_lp, cudaStream_t st,
+                             int (*logpost)(void*, const double*, double*, double*), void* user, int* rc_out) {
+    HmcBuf b;
+    double* p = d_state;
+    const size_t nD = (size_t)n * D;
+    b.q = p; p += nD; b.lp = p; p += n; b.g = p; p += nD;
+    b.qp = p; p += nD; b.lpp = p; p += n; b.gp = p; p += nD;
+    b.p = p; p += nD; b.h0 = p; p += n; b.acc = p; p += n; b.inv_mass = p; p += D;
+    b.out_theta = d_out_theta; b.out_lp = d_out_lp;
+    *rc_out = 0;
+    cudaError_t e;
+    if ((*rc_out = logpost(user, b.q, b.lp, b.g))) return cudaSuccess;            // state of the start
+    for (int it = 0; it <= n_iter; ++it) {
+        e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, seed);
+        if (e != cudaSuccess) return e;
+        if (it == n_iter) break;
+        for (int l = 0; l < n_leapfrog; ++l) {
+            if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp))) return cudaSuccess;
+            e = launch_pdl(k_hmc_leap, n, st, b, n, D, (int)(l == n_leapfrog - 1), eps);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
+}
+
+// host twin of the random stream (tests reproduce a transition with it)
+extern "C" void octo_hmc_random(uint64_t seed, int64_t it, int64_t chain, int32_t D, double* z, double* u) {
+    const uint64_t key = hmc_key(seed, (uint64_t)it);
+    for (int j = 0; j < D; ++j) {
+        const uint64_t s = hmc_draw(key, (uint64_t)chain, (uint64_t)j);
+        const double u1 = u01(s), u2 = u01(splitmix64(s));
+        z[j] = sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2);
+    }
+    *u = u01(hmc_draw(key, (uint64_t)chain, (uint64_t)D));
+}

@@ -119,3 +119,10 @@ cudaError_t octo_param_backward(const DevParam* d_param, int D, const DevModel& 
                                 double* d_g_t, int64_t ldg, int post_mode, cudaStream_t st);
 cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, int64_t n, int64_t ld, double* d_out,
                                cudaStream_t st);
+
+// device-resident HMC explorer (octo_hmc.cu)
+size_t octo_hmc_state_doubles(int64_t n, int D);
+cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
+                             double* d_out_theta, double* d_out_lp, cudaStream_t st,
+                             int (*logpost)(void*, const double*, double*, double*), void* user, int* rc_out);
+

@@ -751,6 +751,66 @@ int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, d
     return rc;
 }
 
+// ---- device-resident HMC explorer (octo_hmc.cu): the whole run is enqueued on one stream, one sync at the end
+namespace {
+struct HmcUser { OctoCtx* ctx; Workspace* w; int64_t n; };
+int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g) {
+    HmcUser* u = (HmcUser*)user;
+    return logpost_enqueue(u->ctx, u->w, d_theta, u->n, u->n, d_lp, d_g, u->n, u->w->d_in, u->w->stream);
+}
+}  // namespace
+
+int octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
+                 double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
+                 double* theta_final, double* lp_final, double* accept_rate) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
+    if (!theta0 || n < 1 || ld < n || n_iter < 1 || n_leapfrog < 1 || !(step_size > 0)) return fail(OCTO_ERR_ARG, "bad arguments");
+    const int D = ctx->param_D, n_in = ctx->m.n_in;
+    if (inv_mass) for (int j = 0; j < D; ++j) if (!(inv_mass[j] > 0) || !std::isfinite(inv_mass[j])) return fail(OCTO_ERR_ARG, "inverse mass must be positive");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = lease(ctx);
+    if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
+    const size_t col = (size_t)n * sizeof(double), nD = (size_t)n * D;
+    double *d_state = nullptr, *d_ot = nullptr, *d_ol = nullptr;
+    int rc = OCTO_OK;
+    do {
+        if (!ctx->param_fused && (rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * D + 3)))) break;
+        cudaError_t e = cudaMalloc((void**)&d_state, octo_hmc_state_doubles(n, D) * sizeof(double));
+        if (e == cudaSuccess && theta_samples) e = cudaMalloc((void**)&d_ot, (size_t)n_iter * nD * sizeof(double));
+        if (e == cudaSuccess && lp_samples) e = cudaMalloc((void**)&d_ol, (size_t)n_iter * col);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc (HMC state)"); break; }
+        double* d_acc = d_state + 5 * nD + 3 * (size_t)n;
+        double* d_im = d_acc + n;
+        std::vector<double> im(D, 1.0);
+        if (inv_mass) im.assign(inv_mass, inv_mass + D);
+        e = cudaMemcpy2DAsync(d_state, col, theta0, (size_t)ld * sizeof(double), col, D, cudaMemcpyHostToDevice, w->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_im, im.data(), D * sizeof(double), cudaMemcpyHostToDevice, w->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, col, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);          // `im` is a local
+        if (e != cudaSuccess) { rc = fail_cuda(e, "HMC setup"); break; }
+        HmcUser user{ctx, w, n};
+        int cb_rc = 0;
+        e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user, &cb_rc);
+        if (cb_rc) { rc = cb_rc; cudaStreamSynchronize(w->stream); break; }
+        if (e != cudaSuccess) { rc = fail_cuda(e, "HMC launch"); cudaStreamSynchronize(w->stream); break; }
+        ctx->launches.fetch_add((int64_t)n_iter * (n_leapfrog + 1) + 1, std::memory_order_relaxed);
+        if (theta_final) e = cudaMemcpy2DAsync(theta_final, (size_t)ld * sizeof(double), d_state, col, col, D, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess && lp_final) e = cudaMemcpyAsync(lp_final, d_state + nD, col, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess && accept_rate) e = cudaMemcpyAsync(accept_rate, d_acc, col, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess && theta_samples) e = cudaMemcpyAsync(theta_samples, d_ot, (size_t)n_iter * nD * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess && lp_samples) e = cudaMemcpyAsync(lp_samples, d_ol, (size_t)n_iter * col, cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "HMC run"); break; }
+        if (accept_rate) for (int64_t c = 0; c < n; ++c) accept_rate[c] /= (double)n_iter;
+    } while (0);
+    if (d_state) cudaFree(d_state);
+    if (d_ot) cudaFree(d_ot);
+    if (d_ol) cudaFree(d_ol);
+    release(ctx, w);
+    return rc;
+}
+
 int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
     if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");

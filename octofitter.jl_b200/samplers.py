@@ -59,6 +59,34 @@ def batched_hmc(model, theta0, n_iter, *, step_size=0.02, n_leapfrog=16, rng=Non
     return {"theta": out_th, "logpost": out_lp, "accept_rate": acc_total / n_iter, "n_gradient_calls": calls}
 
 
+def device_hmc(model, theta0, n_iter, *, step_size=0.02, n_leapfrog=16, inv_mass=None, seed=0, keep_samples=True):
+    """The same explorer as `batched_hmc`, resident on the device (C ABI `octo_hmc_run`): the whole run — n_iter
+    transitions x n_leapfrog leapfrogs for all chains — is enqueued on one stream and synchronised once.  Returns the
+    same dict as `batched_hmc` plus `theta_final`, `logpost_final` and the per-chain `accept` rates.  Counter-based
+    randomness: the result is a pure function of (theta0, step_size, n_leapfrog, inv_mass, seed)."""
+    import ctypes as C
+    th = np.array(theta0, dtype=np.float64, order="F")
+    n, D = th.shape
+    im = None if inv_mass is None else np.ascontiguousarray(inv_mass, dtype=np.float64)
+    samples = np.empty((n_iter, D, n)) if keep_samples else None
+    lps = np.empty((n_iter, n)) if keep_samples else None
+    th_f = np.empty((n, D), order="F"); lp_f = np.empty(n); acc = np.empty(n)
+    p = lambda a: None if a is None else a.ctypes.data
+    model._check(model._lib.octo_hmc_run(model._h, th.ctypes.data, n, n, int(n_iter), int(n_leapfrog), float(step_size), p(im),
+                                         C.c_uint64(int(seed)), p(samples), p(lps), th_f.ctypes.data, lp_f.ctypes.data, acc.ctypes.data))
+    return {"theta": None if samples is None else np.ascontiguousarray(samples.transpose(0, 2, 1)), "logpost": lps,
+            "theta_final": th_f, "logpost_final": lp_f, "accept": acc, "accept_rate": float(acc.mean()),
+            "n_gradient_calls": n_iter * n_leapfrog + 1}
+
+
+def hmc_random(model, seed, it, chain, D):
+    """(z[D], u): the standard normals and the accept-step uniform `octo_hmc_run` uses for transition `it` of `chain`."""
+    import ctypes as C
+    z = np.empty(D); u = C.c_double()
+    model._lib.octo_hmc_random(C.c_uint64(int(seed)), int(it), int(chain), int(D), z.ctypes.data, C.byref(u))
+    return z, u.value
+
+
 def batched_parallel_tempering(model, model_ref_logp, pt, theta0, n_rounds, *, step_size=0.02, n_leapfrog=8, rng=None,
                                inv_mass=None):
     """Tempered HMC explorer + deterministic even-odd swaps (octo.ParallelTempering) for the LOCAL replicas of a rank.

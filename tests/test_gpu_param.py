@@ -328,3 +328,62 @@ def test_radial_velocity_orbit_basis(oracle_lib):
     with pytest.raises(ValueError):
         octo.Planet(name="c", basis="RadialVelocityOrbit", variables={"a": 1.0},
                     observations=[octo.PlanetRelAstromObs(octo.Table(epoch=[5e4], ra=[1.], dec=[1.], σ_ra=[1.], σ_dec=[1.]), name="x")])
+
+
+def test_device_resident_hmc():
+    """octo_hmc_run: the whole HMC run enqueued on one stream.  (1) One transition is reproduced step by step on the
+    host from the same counter-based random numbers and the same device log-posterior; (2) runs are reproducible;
+    (3) a longer run behaves like the host-driven batched_hmc on the reference's 11-D test model."""
+    import time
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(4)
+    params, lp0 = model.guess_starting_position(rng, N=60_000, batch=20_000)
+    start = model.link(params)
+    inv_mass = octo.diagonal_metric(model, start)
+    n, D, eps, L, seed = 64, spec.D, 0.15, 5, 1234
+    th0 = np.asfortranarray(start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((n, D)))
+    res = octo.device_hmc(model, th0, 1, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=seed)
+    # host replica of transition 0
+    lp, g = model.ℓπcallback_grad(th0)
+    zu = [octo.hmc_random(model, seed, 0, c, D) for c in range(n)]
+    z = np.array([t[0] for t in zu]); u = np.array([t[1] for t in zu])
+    p = z / np.sqrt(inv_mass)
+    h0 = -lp + 0.5 * np.sum(p * p * inv_mass, axis=1)
+    p = p + 0.5 * eps * g
+    q = th0 + eps * p * inv_mass
+    for k in range(L):
+        lq, gq = model.ℓπcallback_grad(np.asfortranarray(q))
+        gq = np.where(np.isfinite(lq)[:, None], gq, 0.0)
+        p = p + (eps if k < L - 1 else 0.5 * eps) * gq
+        if k < L - 1:
+            q = q + eps * p * inv_mass
+    h1 = -lq + 0.5 * np.sum(p * p * inv_mass, axis=1)
+    accept = np.isfinite(lq) & (np.log(u) < h0 - h1)
+    expect = np.where(accept[:, None], q, th0)
+    assert 0 < accept.sum() <= n and np.array_equal(res["accept"] == 1.0, accept)
+    assert np.allclose(res["theta_final"], expect, rtol=1e-11, atol=1e-13)
+    assert np.allclose(res["logpost_final"], np.where(accept, lq, lp), rtol=1e-10)
+    assert np.array_equal(res["theta"][0], res["theta_final"]) and np.array_equal(res["logpost"][0], res["logpost_final"])
+    # reproducible
+    r1 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
+    r2 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
+    assert np.array_equal(r1["theta"], r2["theta"]) and np.array_equal(r1["accept"], r2["accept"])
+    r3 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=100)
+    assert not np.array_equal(r1["theta"], r3["theta"])
+    # a real run: 256 chains x 150 transitions x 12 leapfrogs, against the host-driven explorer
+    th256 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((256, D))
+    t0 = time.perf_counter()
+    dev = octo.device_hmc(model, th256, 150, step_size=0.15, n_leapfrog=12, inv_mass=inv_mass, seed=7)
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host = octo.batched_hmc(model, th256, 150, step_size=0.15, n_leapfrog=12, rng=rng, inv_mass=inv_mass)
+    t_host = time.perf_counter() - t0
+    print(f"device-resident HMC {t_dev*1e3:.1f} ms vs host-driven {t_host*1e3:.1f} ms for 256 chains x 150 x 12 leapfrogs")
+    assert abs(dev["accept_rate"] - host["accept_rate"]) < 0.08 and dev["accept_rate"] > 0.4
+    assert abs(np.median(dev["logpost"][-50:]) - np.median(host["logpost"][-50:])) < 2.0
+    names = list(spec.theta_names)
+    for nm in ("b.a", "b.e"):
+        a_d = model.invlink(dev["theta"][-1])[:, names.index(nm)]; a_h = model.invlink(host["theta"][-1])[:, names.index(nm)]
+        assert abs(np.median(a_d) - np.median(a_h)) < 0.35 * (np.std(a_h) + np.std(a_d))
+    model.close()
