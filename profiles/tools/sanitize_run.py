@@ -1,6 +1,7 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): C2- and C3-shaped models,
 ragged batch sizes, value and gradient kernels, epoch-split path; the fused parameterisation stage (and its
-three-launch fallback), the likelihood-of-theta mode, pointwise mode and an observable-prior table."""
+three-launch fallback), the likelihood-of-theta mode, pointwise mode, an observable-prior table, HGCA, Thiele-Innes
+planets and the device-resident HMC explorer."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,3 +33,19 @@ ll = np.empty(35); g = np.empty((35, x.shape[1]), order="F")
 assert lib.octo_logp_grad(h, x.ctypes.data, 35, 35, ll.ctypes.data, g.ctypes.data) == 0
 print("obsprior", ll[0], d["ll"])
 lib.octo_destroy(h)
+
+for name in ("case_hgca", "case_thiele_innes"):
+    d, packed, consts = load_golden(name)
+    h = C.c_void_p()
+    assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 0
+    x = np.asfortranarray(np.tile(np.array(d["x"]), (35, 1)))
+    ll = np.empty(35); g = np.empty((35, x.shape[1]), order="F")
+    assert lib.octo_logp_grad(h, x.ctypes.data, 35, 35, ll.ctypes.data, g.ctypes.data) == 0
+    print(name, ll[0], d["ll"])
+    lib.octo_destroy(h)
+os.environ["OCTO_B200_FUSE_PARAM"] = "1"
+spec, th = workloads.one_planet_with_priors(40, 30, 45, seed=2)
+m = octo.LogDensityModel(spec)
+r = octo.device_hmc(m, th, 3, step_size=1e-3, n_leapfrog=4, inv_mass=np.full(spec.D, 1e-4), seed=3)
+print("hmc", r["accept_rate"], float(r["logpost_final"][0]))
+m.close()
