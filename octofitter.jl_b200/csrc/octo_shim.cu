@@ -72,6 +72,7 @@ struct OctoCtx {
     bool param_fused = false;      // the parameterisation runs inside K1 (one launch) instead of K0f + K1 + K0b
     size_t smem_fused = 0;
     int ctas_per_sm_fused = 1;
+    int warps_fused = OCTO_WARPS;  // the fused stage's arrays may need a smaller CTA than the plain kernel
     size_t smem_optin = 0;
     // parallel tempering
     void* nccl_comm = nullptr;
@@ -169,7 +170,7 @@ void free_ws(Workspace* w) {
 // per warp so the per-CTA prologue/epilogue is amortised and the hardware CTA scheduler balances the tail.
 LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
     LaunchGeom g;
-    const int W = ctx->warps;
+    const int W = fused ? ctx->warps_fused : ctx->warps;
     g.block = W * 32;
     g.smem = fused ? ctx->smem_fused : ctx->smem;
     const int64_t E = ctx->m.n_epochs;
@@ -679,11 +680,14 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
     }
     if (const char* e = getenv("OCTO_B200_FUSE_PARAM")) if (atoi(e) == 0) fusable = false;
     CU(cudaSetDevice(ctx->device));
-    const size_t smem_f = octo_smem_bytes(ctx->m, ctx->warps, D, P.n_tperi);
+    int wf = ctx->warps;
+    while (wf > 1 && octo_smem_bytes(ctx->m, wf, D, P.n_tperi) > ctx->smem_optin) wf /= 2;
+    const size_t smem_f = octo_smem_bytes(ctx->m, wf, D, P.n_tperi);
     if (smem_f > ctx->smem_optin) fusable = false;
     if (fusable) {
         int occ = 0;
-        CU(octo_kernels_init(ctx->m, smem_f, ctx->smem_optin, ctx->warps, &occ));
+        ctx->warps_fused = wf;
+        CU(octo_kernels_init(ctx->m, smem_f, ctx->smem_optin, wf, &occ));
         if (occ < 1) fusable = false;
         ctx->smem_fused = smem_f; ctx->ctas_per_sm_fused = occ > 0 ? occ : 1;
         if (const char* e = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm_fused = std::max(1, atoi(e));

@@ -387,3 +387,48 @@ def test_device_resident_hmc():
         a_d = model.invlink(dev["theta"][-1])[:, names.index(nm)]; a_h = model.invlink(host["theta"][-1])[:, names.index(nm)]
         assert abs(np.median(a_d) - np.median(a_h)) < 0.35 * (np.std(a_h) + np.std(a_d))
     model.close()
+
+
+def test_three_planet_parameterised_model(oracle_lib, monkeypatch):
+    """A larger standard model — three planets, each with UniformCircular ω, Ω, θ and its own θ_at_epoch_to_tperi,
+    astrometry with sampled jitter, star RV and marginalised RV (D = 38, three tperi definitions in one launch) —
+    fused and stand-alone against the oracle."""
+    rng = np.random.default_rng(61)
+    planets = []
+    for k, nm in enumerate("bcd"):
+        a0 = 3.0 * 2.1 ** k
+        ep = np.sort(rng.uniform(50000, 52500, 9 + k))
+        tab = octo.Table(epoch=ep, ra=50 * a0 * np.cos(ep / (200.0 * (k + 1))) + rng.normal(0, 2, len(ep)),
+                         dec=50 * a0 * np.sin(ep / (200.0 * (k + 1))) + rng.normal(0, 2, len(ep)),
+                         σ_ra=np.full(len(ep), 2.0), σ_dec=np.full(len(ep), 2.5), cor=rng.uniform(-0.5, 0.5, len(ep)))
+        obs = octo.PlanetRelAstromObs(tab, name=f"cam{k}", variables={"jitter": octo.LogUniform(0.01, 10.0)})
+        planets.append(octo.Planet(name=nm, observations=[obs], variables={
+            "a": octo.LogUniform(0.5 * a0, 2.0 * a0), "e": octo.Uniform(0, 0.8), "i": octo.Sine(), "ω": octo.UniformCircular(),
+            "Ω": octo.UniformCircular(), "θ": octo.UniformCircular(), "tp": octo.θ_at_epoch_to_tperi("θ", 51000.0),
+            "mass": octo.LogUniform(0.5, 50)}))
+    eps = np.sort(rng.uniform(50000, 52500, 30))
+    rv1 = octo.StarAbsoluteRVObs(octo.Table(epoch=eps[:15], rv=rng.normal(0, 30, 15), σ_rv=np.full(15, 5.0)), name="harps",
+                                 variables={"offset": octo.Normal(0, 100), "jitter": octo.LogUniform(0.1, 100.0)})
+    rv2 = octo.MarginalizedStarAbsoluteRVObs(octo.Table(epoch=eps[15:], rv=rng.normal(0, 30, 15), σ_rv=np.full(15, 5.0)), name="hires",
+                                             variables={"jitter": octo.LogUniform(0.1, 100.0)})
+    system = octo.System(name="three", companions=planets, observations=[rv1, rv2], variables={
+        "M": octo.truncated(octo.Normal(1.2, 0.1), lower=0.1), "plx": octo.truncated(octo.Normal(40.0, 0.5), lower=0.1)})
+    spec = octo.ModelSpec(system)
+    assert spec.D == 38 and sum(1 for d in spec.defs if d.op == 3) == 3
+    th = rng.normal(0, 0.6, (90, spec.D))
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    fin = np.isfinite(lp_o)
+    assert fin.sum() > 60
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("OCTO_B200_FUSE_PARAM", fuse)
+        model = octo.LogDensityModel(spec)
+        n0 = model.kernel_launches
+        lp, g = model.ℓπcallback_grad(th)
+        out[fuse] = (lp, g, model.kernel_launches - n0)
+        assert np.array_equal(np.isfinite(lp), fin)
+        assert rel_err(lp[fin], lp_o[fin]).max() < LOGP_RTOL and grad_err(g[fin], g_o[fin]).max() < GRAD_RTOL
+        model.close()
+    assert out["1"][2] == 1 and out["0"][2] == 3
+    # (not bit-equal here: the fused launch needs a smaller CTA for this model, which changes the summation tree)
+    assert rel_err(out["1"][0][fin], out["0"][0][fin]).max() < 1e-12
