@@ -1139,9 +1139,11 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         s_ok[threadIdx.x] = 1;
         if (P) param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi).flags[threadIdx.x] = 0;
     }
+    // the value-only kernel of a model without non-linear folds (marginalised RV, observable prior) needs one sum: ll
+    const int n_use = (!GRAD && !m.has_margin) ? 1 : n_acc;
     double* acc = s_acc + w * n_acc * 32;
 #pragma unroll 4
-    for (int s = 0; s < n_acc; ++s) acc[s * 32 + lane] = 0.0;
+    for (int s = 0; s < n_use; ++s) acc[s * 32 + lane] = 0.0;
     __syncthreads();
 
     // ---- inputs of this CTA's chains into shared memory, with the finiteness check of logdensitymodel.jl:120-124;
@@ -1202,7 +1204,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 
     // ---- CTA reduction over the 8 warps, fixed order
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) {
+    for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) {
         double v = s_acc[idx];
 #pragma unroll 8
         for (int ww = 1; ww < W; ++ww) v += s_acc[ww * n_acc * 32 + idx];
@@ -1216,7 +1218,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     if (gridDim.y > 1 && !pw_const) {
         double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
 #pragma unroll 2
-        for (int idx = threadIdx.x; idx < n_acc * 32; idx += W * 32) mine[idx] = s_red[idx];
+        for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) mine[idx] = s_red[idx];
         __threadfence();
         __syncthreads();
         OCTO_TICK();
@@ -1238,7 +1240,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         // every load of this thread (two accumulator cells x up to 16 splits) is issued before the first add: one
         // L2 round trip instead of four; additions stay in split order => same bits every run
         const int64_t stride = (int64_t)n_acc * 32;
-        const int ncell = n_acc * 32, gy = (int)gridDim.y;
+        const int ncell = n_use * 32, gy = (int)gridDim.y;
 #pragma unroll 1
         for (int idx0 = threadIdx.x; idx0 < ncell; idx0 += 2 * W * 32) {
             const int idx1 = idx0 + W * 32;
