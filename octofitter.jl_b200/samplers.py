@@ -87,6 +87,55 @@ def hmc_random(model, seed, it, chain, D):
     return z, u.value
 
 
+def octofit(model, rng=None, *, n_chains=256, adaptation=300, iterations=300, target_accept=0.8, n_leapfrog=12,
+            n_init=100_000, windows=6, seed=None, verbosity=0):
+    """`octofit(model; adaptation, iterations)` (src/sampling.jl:300-470) for a batch of chains on the device.
+
+    The reference runs one NUTS chain with Stan-style windowed adaptation (AdvancedHMC `StanHMCAdaptor`: dual-averaging
+    step size + a metric estimated in expanding windows).  Here `n_chains` chains of static-trajectory HMC run in
+    lockstep on the device (`octo_hmc_run`): start = best of `n_init` prior draws (guess_starting_position,
+    src/initialization.jl:14-66) plus a small scatter; adaptation = `windows` expanding windows, after each of which the
+    diagonal inverse mass is set to the pooled per-coordinate variance of the window's draws and the step size is
+    rescaled towards `target_accept`; then `iterations` sampling transitions.  Returns a dict like the reference's chain:
+    `theta_t` / `theta` (natural space) [iterations, n_chains, D], `logpost`, `names`, and an `info` dict with the
+    acceptance rate, the adapted step size / inverse mass and the gradient-call count."""
+    rng = np.random.default_rng() if rng is None else rng
+    seed = int(rng.integers(1 << 62)) if seed is None else int(seed)
+    D = model.D
+    params, _ = model.guess_starting_position(rng, N=n_init)
+    start = model.link(params)
+    inv_mass = diagonal_metric(model, start)
+    th = np.asfortranarray(start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((n_chains, D)))
+    eps, calls = 0.1, 0
+    # expanding windows (Stan: each twice the previous); every window ends with a metric and step-size update
+    sizes = np.maximum(1, (adaptation * 2.0 ** np.arange(windows) / (2.0 ** windows - 1)).astype(int))
+    for k, w in enumerate(sizes):
+        # a few short runs inside the window tune the step size at the current metric
+        for sub in range(3):
+            n_it = max(1, int(w) // 3)
+            r = device_hmc(model, th, n_it, step_size=eps, n_leapfrog=n_leapfrog, inv_mass=inv_mass, seed=seed + 1000 * k + sub)
+            calls += r["n_gradient_calls"]
+            th = r["theta_final"]
+            acc = r["accept_rate"]
+            eps *= float(np.clip(np.exp(1.5 * (acc - target_accept)), 0.5, 2.0))
+            if verbosity >= 2:
+                print(f"adapt window {k}.{sub}: {n_it} it, accept {acc:.2f}, step {eps:.3g}")
+        draws = r["theta"].reshape(-1, D)
+        var = draws.var(axis=0)
+        if np.all(np.isfinite(var)) and np.all(var > 0):
+            # Stan's regularisation of the variance estimate
+            nw = draws.shape[0]
+            inv_mass = (nw / (nw + 5.0)) * var + 1e-3 * (5.0 / (nw + 5.0))
+    r = device_hmc(model, th, iterations, step_size=eps, n_leapfrog=n_leapfrog, inv_mass=inv_mass, seed=seed + 999_983)
+    calls += r["n_gradient_calls"]
+    theta_t = r["theta"]
+    nat = model.invlink(theta_t.reshape(-1, D)).reshape(theta_t.shape)
+    return {"theta_t": theta_t, "theta": nat, "logpost": r["logpost"], "names": model.spec.theta_names,
+            "info": {"sampler": "device_hmc", "n_chains": n_chains, "adaptation": int(sizes.sum()), "iterations": iterations,
+                     "accept_rate": r["accept_rate"], "step_size": eps, "inv_mass": inv_mass, "n_leapfrog": n_leapfrog,
+                     "n_gradient_calls": calls, "seed": seed}}
+
+
 def batched_parallel_tempering(model, model_ref_logp, pt, theta0, n_rounds, *, step_size=0.02, n_leapfrog=8, rng=None,
                                inv_mass=None):
     """Tempered HMC explorer + deterministic even-odd swaps (octo.ParallelTempering) for the LOCAL replicas of a rank.

@@ -432,3 +432,36 @@ def test_three_planet_parameterised_model(oracle_lib, monkeypatch):
     assert out["1"][2] == 1 and out["0"][2] == 3
     # (not bit-equal here: the fused launch needs a smaller CTA for this model, which changes the summation tree)
     assert rel_err(out["1"][0][fin], out["0"][0][fin]).max() < 1e-12
+
+
+def test_octofit_recovers_the_fixture_orbit():
+    """The reference's "fit a chain" smoke test (test/integration-tests.jl:52-58, test/integration/sampling.jl:78-134)
+    through the batched driver: adaptation + sampling on the 11-D test model; the posterior must be plausible
+    (`logpost > -1000`), the chains must agree with each other, and the well-constrained quantity of this data set —
+    the position angle at the reference epoch — must match the data."""
+    import time
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    t0 = time.perf_counter()
+    chain = octo.octofit(model, np.random.default_rng(3), n_chains=256, adaptation=240, iterations=200, n_init=60_000, seed=11)
+    dt = time.perf_counter() - t0
+    info = chain["info"]
+    print(f"octofit: {info['n_gradient_calls']} batched gradient calls for 256 chains in {dt:.2f} s, accept {info['accept_rate']:.2f}, step {info['step_size']:.3g}")
+    assert 0.5 < info["accept_rate"] <= 1.0
+    lp = chain["logpost"]
+    assert np.all(np.isfinite(lp[-1])) and np.all(lp[-1] > -1000)
+    names = list(chain["names"])
+    nat = chain["theta"][-100:].reshape(-1, len(names))
+    th_x, th_y = nat[:, names.index("b.θx")], nat[:, names.index("b.θy")]
+    theta = np.arctan2(th_y, th_x)
+    # the fixture's first epoch is the reference epoch of θ (50000): PA of the data there
+    d = load_post("post_fixture8")[0]
+    ra0, dec0 = d["blocks"][0]["y1"][0], d["blocks"][0]["y2"][0]
+    pa = np.arctan2(ra0, dec0)
+    dpa = np.angle(np.exp(1j * (theta - pa)))
+    assert abs(np.median(dpa)) < 0.05 and np.std(dpa) < 0.2
+    # between-chain agreement (a crude R-hat on the log posterior): chains have mixed
+    lp_tail = lp[-100:]
+    between = lp_tail.mean(axis=0).var(); within = lp_tail.var(axis=0).mean()
+    assert between < 0.5 * within
+    model.close()
