@@ -2,11 +2,15 @@
 
 Same names and argument meaning as the Julia types the path sits behind
 (src/variables.jl:468-594 `Planet`/`System`; src/likelihoods/relative-astrometry.jl:19-93
-`PlanetRelAstromObs`; OctofitterRadialVelocity/src/rv-*.jl; src/logdensitymodel.jl
-`LogDensityModel`), reduced to what the path needs: the observation tables, which natural-space
-variables exist, and where they sit in the kernel's input matrix.  Priors, bijectors, derived
-expressions and samplers stay with the caller (SURVEY.md §8b "split"): the caller passes
-NATURAL-space values of every variable.
+`PlanetRelAstromObs`; OctofitterRadialVelocity/src/rv-*.jl; src/likelihoods/prior-observable.jl;
+src/likelihoods/hgca.jl; src/logdensitymodel.jl `LogDensityModel`), reduced to what the path needs: the
+observation tables, which variables exist, and where they sit in the kernel's input matrix.
+
+Two ways to declare variables.  A list of names: the caller passes NATURAL-space values of every variable
+(`ln_like`, `ln_like_and_gradient`) and keeps priors/bijectors to itself (SURVEY.md §8b "split").  A dict
+name -> prior | UniformCircular | constant | θ_at_epoch_to_tperi: the standard parameterisation then runs on the
+device as well and the model offers the sampler-facing surface of the reference (`ℓπcallback`, `ℓπcallback_grad`,
+`link`/`invlink`, `sample_priors`, ...).
 
 The compute is exclusively libocto_b200.so (hand-written sm_100a kernels).  Nothing here
 evaluates a likelihood on the CPU.
