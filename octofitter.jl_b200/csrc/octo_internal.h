@@ -6,7 +6,9 @@
 #include "../../include/octo_b200.h"
 
 #define OCTO_MAX_BLOCKS 24        // observation tables per model
+#ifndef OCTO_WARPS
 #define OCTO_WARPS 8              // warps per CTA: each warp owns one contiguous epoch range
+#endif
 #define OCTO_LANES 32             // lanes = chains of one chain group
 #define OCTO_MIN_SLICE 2          // fewest epochs worth giving a warp
 
