@@ -350,7 +350,7 @@ def main():
                                  "synchronize on both sides, max over ranks; value = pairs x K / region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read + write of this launch from the committed ncu capture (profiles/r01_ncu_summary.txt)
-                         "traffic": 227072, "peak_source": peak_how, "flop_per_pair": F_ALG,
+                         "traffic": 195840, "peak_source": peak_how, "flop_per_pair": F_ALG,
                          "executed": {"tflops": flops_per_launch(spec, n, F_EXEC) / (kern_ms * 1e-3) / 1e12,
                                       "flop_per_pair": F_EXEC, "how": "ncu SASS op counts, see profiles/"},
                          "kernel_ms": kern_ms,

@@ -103,7 +103,7 @@ struct DevParam {
     int16_t gat[2 * OCTO_PARAM_MAX];
 };
 
-struct LaunchGeom { int gx, gy, block, slice; size_t smem; };
+struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; };   // lat: the latency-tuned instantiation
 
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,

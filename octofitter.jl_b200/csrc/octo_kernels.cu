@@ -1098,8 +1098,10 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
     }
 }
 
-template <bool GRAD, int NPT>
-__global__ void __launch_bounds__(WMAX * 32, OCTO_MIN_CTAS)
+// LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
+// single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
+template <bool GRAD, int NPT, bool LAT>
+__global__ void __launch_bounds__(WMAX * 32, LAT ? 1 : OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
@@ -1361,7 +1363,7 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 
-template <bool GRAD, int NPT>
+template <bool GRAD, int NPT, bool LAT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             const DevParam* d_param, int post_mode, const double* d_pw_const, cudaStream_t st) {
@@ -1377,7 +1379,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 #ifdef OCTO_NO_PDL
     cfg.numAttrs = 0;
 #endif
-    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
+    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
                               post_mode, d_pw_const);
 }
 
@@ -1387,13 +1389,15 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
     cudaError_t e;
 #define OCTO_ATTR(G, N)                                                                                            \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);   \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);   \
+    if (e != cudaSuccess) return e;                                                                                \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);    \
     if (e != cudaSuccess) return e
     OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
 #undef OCTO_ATTR
-    if (m.n_planets == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 1>, W * 32, smem_bytes);
-    else if (m.n_planets == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 2>, W * 32, smem_bytes);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 4>, W * 32, smem_bytes);
+    if (m.n_planets == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 1, false>, W * 32, smem_bytes);
+    else if (m.n_planets == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 2, false>, W * 32, smem_bytes);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 4, false>, W * 32, smem_bytes);
     return e;
 }
 
@@ -1404,11 +1408,13 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
                         cudaStream_t st) {
+#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st
 #define OCTO_DISPATCH(NPT)                                                                                        \
-    return grad ? launch_t<true, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st)         \
-                : launch_t<false, NPT>(m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st)
+    if (g.lat) return grad ? launch_t<true, NPT, true>(OCTO_ARGS) : launch_t<false, NPT, true>(OCTO_ARGS);         \
+    return grad ? launch_t<true, NPT, false>(OCTO_ARGS) : launch_t<false, NPT, false>(OCTO_ARGS)
     if (m.n_planets == 1) { OCTO_DISPATCH(1); }
     if (m.n_planets == 2) { OCTO_DISPATCH(2); }
     OCTO_DISPATCH(4);
 #undef OCTO_DISPATCH
+#undef OCTO_ARGS
 }
