@@ -9,6 +9,9 @@
 #ifndef OCTO_WARPS
 #define OCTO_WARPS 8              // warps per CTA: each warp owns one contiguous epoch range
 #endif
+#ifndef OCTO_LAT_WARPS
+#define OCTO_LAT_WARPS 8          // warps per CTA of the latency-tuned instantiation (one CTA per SM)
+#endif
 #define OCTO_LANES 32             // lanes = chains of one chain group
 #define OCTO_MIN_SLICE 2          // fewest epochs worth giving a warp
 

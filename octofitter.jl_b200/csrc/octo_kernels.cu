@@ -1101,7 +1101,7 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
 // LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
 // single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
 template <bool GRAD, int NPT, bool LAT>
-__global__ void __launch_bounds__(WMAX * 32, LAT ? 1 : OCTO_MIN_CTAS)
+__global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,

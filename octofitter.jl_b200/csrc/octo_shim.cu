@@ -69,7 +69,7 @@ struct OctoCtx {
     int latency_mode = 1;          // OCTO_B200_LATENCY: 0 never, 1 automatic, 2 whenever the chain groups fit one per SM
     // device-side parameterisation (N1)
     DevParam* d_param = nullptr;
-    int param_D = 0;
+    int param_D = 0, param_T = 0;
     bool param_fused = false;      // the parameterisation runs inside K1 (one launch) instead of K0f + K1 + K0b
     size_t smem_fused = 0;
     int ctas_per_sm_fused = 1;
@@ -209,13 +209,23 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
     // Latency-tuned instantiation (no register cap, one CTA per SM): when the grid above is a single wave anyway and
     // the chain groups fit one per SM, run fewer, fatter CTAs of it instead — on C2 128 CTAs x 7 epochs per warp beat
     // 288 x 3 (14.6 vs 15.4 us per step): no spills, a 4- instead of 9-way combine, the SM to itself
+    int Wg = W;
     if (ctx->latency_mode != 0 && g.gx <= ctx->n_sm && ((int64_t)g.gx * gy <= resident || ctx->latency_mode == 2)) {
+        // its CTA may be wider than the throughput one when the model's shared memory allows
+        int Wl = (W == OCTO_WARPS) ? OCTO_LAT_WARPS : W;
+        const int D = fused ? ctx->param_D : 0, T = fused ? ctx->param_T : 0;
+        if (octo_smem_bytes(ctx->m, Wl, D, T) > ctx->smem_optin) Wl = W;
+        int64_t max_gl = E / ((int64_t)min_slice * Wl);
+        if (max_gl < 1) max_gl = 1;
         int64_t gl = ctx->n_sm / g.gx;
-        if (gl > max_gy) gl = max_gy;
-        if (gl >= 1) { if (gy > 1 || ctx->latency_mode == 2) gy = gl; g.lat = true; }
+        if (gl > max_gl) gl = max_gl;
+        if (gl >= 1) {
+            if (gy > 1 || ctx->latency_mode == 2) gy = gl;
+            g.lat = true; Wg = Wl; g.block = Wl * 32; g.smem = octo_smem_bytes(ctx->m, Wl, D, T);
+        }
     }
     g.gy = (int)gy;
-    g.slice = (int)((E + gy * W - 1) / (gy * W));
+    g.slice = (int)((E + gy * Wg - 1) / (gy * Wg));
     return g;
 }
 
@@ -705,7 +715,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
     CU(octo_param_init(D, n_in));
     if (!ctx->d_param) CU(cudaMalloc((void**)&ctx->d_param, sizeof(DevParam)));
     CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
-    ctx->param_D = D;
+    ctx->param_D = D; ctx->param_T = P.n_tperi;
     ctx->param_fused = fusable;
     return OCTO_OK;
 }
