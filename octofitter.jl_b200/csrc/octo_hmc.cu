@@ -81,9 +81,9 @@ __global__ void k_hmc_leap(HmcBuf b, int64_t n, int D, int last, double eps) {
     const bool ok = isfinite(b.lpp[c]);
     const double k = last ? 0.5 * eps : eps;
     for (int j = 0; j < D; ++j) {
-        const double pj = b.p[c + (int64_t)j * n] + (ok ? k * b.gp[c + (int64_t)j * n] : 0.0);
+        const double pj = fma(k, ok ? b.gp[c + (int64_t)j * n] : 0.0, b.p[c + (int64_t)j * n]);    // same roundings as the fused form
         b.p[c + (int64_t)j * n] = pj;
-        if (!last) b.qp[c + (int64_t)j * n] += eps * pj * b.inv_mass[j];
+        if (!last) b.qp[c + (int64_t)j * n] = fma(eps * pj, b.inv_mass[j], b.qp[c + (int64_t)j * n]);
     }
 }
 
@@ -106,7 +106,8 @@ size_t octo_hmc_state_doubles(int64_t n, int D) { return (size_t)(2 * (2 * n * D
 // logpost(d_theta [n x D], d_lp, d_g) enqueues one log-posterior + gradient evaluation on `st`
 cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
-                             int (*logpost)(void*, const double*, double*, double*), void* user, int* rc_out) {
+                             int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
+                             bool fused_leap, int* rc_out) {
     HmcBuf b;
     double* p = d_state;
     const size_t nD = (size_t)n * D;
@@ -116,14 +117,20 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
     b.out_theta = d_out_theta; b.out_lp = d_out_lp;
     *rc_out = 0;
     cudaError_t e;
-    if ((*rc_out = logpost(user, b.q, b.lp, b.g))) return cudaSuccess;            // state of the start
+    if ((*rc_out = logpost(user, b.q, b.lp, b.g, nullptr))) return cudaSuccess;   // state of the start
     for (int it = 0; it <= n_iter; ++it) {
         e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, seed);
         if (e != cudaSuccess) return e;
         if (it == n_iter) break;
         for (int l = 0; l < n_leapfrog; ++l) {
-            if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp))) return cudaSuccess;
-            e = launch_pdl(k_hmc_leap, n, st, b, n, D, (int)(l == n_leapfrog - 1), eps);
+            const int last = (int)(l == n_leapfrog - 1);
+            if (fused_leap) {        // the log-posterior launch applies the kick (and drift) itself: one launch per leapfrog
+                const HmcLeap leap{b.p, b.qp, b.inv_mass, eps, last ? 0.5 * eps : eps, !last, 0};
+                if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, &leap))) return cudaSuccess;
+                continue;
+            }
+            if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, nullptr))) return cudaSuccess;
+            e = launch_pdl(k_hmc_leap, n, st, b, n, D, last, eps);
             if (e != cudaSuccess) return e;
         }
     }

@@ -106,13 +106,16 @@ struct DevParam {
     int16_t gat[2 * OCTO_PARAM_MAX];
 };
 
+// leapfrog update folded into the fused log-posterior launch (octo_hmc.cu): after the gradient of a chain is known,
+// p += kick * g and, unless it was the last leapfrog of the trajectory, q += eps * p * inv_mass.  p == nullptr: off.
+struct HmcLeap { double* p; double* q; const double* inv_mass; double eps, kick; int drift, pad; };
 struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; };   // lat: the latency-tuned instantiation
 
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
-                        cudaStream_t stream);
+                        const HmcLeap& leap, cudaStream_t stream);
 size_t octo_smem_bytes(const DevModel& m, int warps, int D = 0, int n_tperi = 0);
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);
@@ -129,5 +132,6 @@ cudaError_t octo_param_invlink(const DevParam* d_param, const double* d_theta, i
 size_t octo_hmc_state_doubles(int64_t n, int D);
 cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
-                             int (*logpost)(void*, const double*, double*, double*), void* user, int* rc_out);
+                             int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
+                             bool fused_leap, int* rc_out);
 

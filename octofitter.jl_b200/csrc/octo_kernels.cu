@@ -1026,7 +1026,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
 // reverse stage: S.aux holds d ll / d inputs of the 32 chains; S.flags bit 3 = chain is ok (valid and ll finite)
 __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
                                             double* __restrict__ g_t, int64_t chain0, int64_t n_chains, int64_t ldg, int w,
-                                            int W, int lane) {
+                                            int W, int lane, const HmcLeap& leap) {
     using namespace octo_param_dev;
     const int D = P.D, n_in = P.n_in, T = P.n_tperi;
 #ifdef OCTO_TIMING
@@ -1070,7 +1070,16 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
 #pragma unroll 1
         for (int j = w; j < D; j += W) {
             const double g = param_gather(P, j, healed ? 0.0 : S.gth[j * 32 + lane], S.th + lane, S.aux + lane, 32);
-            if (active) g_t[chain0 + lane + (int64_t)j * ldg] = ok ? g * S.dxdy[j * 32 + lane] : 0.0;
+            const double gv = ok ? g * S.dxdy[j * 32 + lane] : 0.0;
+            if (active) {
+                const int64_t at = chain0 + lane + (int64_t)j * ldg;
+                g_t[at] = gv;
+                if (leap.p) {                                        // the leapfrog update of this coordinate (octo_hmc.cu)
+                    const double pj = fma(leap.kick, gv, leap.p[at]);
+                    leap.p[at] = pj;
+                    if (leap.drift) leap.q[at] = fma(leap.eps * pj, leap.inv_mass[j], leap.q[at]);
+                }
+            }
         }
     }
     PTICK(4);
@@ -1105,7 +1114,7 @@ __global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : 
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
-              const double* __restrict__ pw_const) {
+              const double* __restrict__ pw_const, const HmcLeap leap) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -1323,7 +1332,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         if (P) {
             __syncthreads();
             OCTO_TICK();
-            param_backward(*P, m, s_in, PS, g_out, chain0, n_chains, ldg, w, W, lane);
+            param_backward(*P, m, s_in, PS, g_out, chain0, n_chains, ldg, w, W, lane, leap);
         }
     }
 #ifdef OCTO_TIMING
@@ -1366,7 +1375,8 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
 template <bool GRAD, int NPT, bool LAT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
-                            const DevParam* d_param, int post_mode, const double* d_pw_const, cudaStream_t st) {
+                            const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
+                            cudaStream_t st) {
     // programmatic dependent launch: the kernel lets the next launch on the stream be scheduled while it is still
     // running (griddepcontrol.launch_dependents) and itself waits for everything before it in the stream to complete
     // and become visible before it touches memory (griddepcontrol.wait) — stream semantics, minus the launch gap
@@ -1380,7 +1390,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
     cfg.numAttrs = 0;
 #endif
     return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
-                              post_mode, d_pw_const);
+                              post_mode, d_pw_const, leap);
 }
 
 // opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
@@ -1407,8 +1417,8 @@ cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
-                        cudaStream_t st) {
-#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, st
+                        const HmcLeap& leap, cudaStream_t st) {
+#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st
 #define OCTO_DISPATCH(NPT)                                                                                        \
     if (g.lat) return grad ? launch_t<true, NPT, true>(OCTO_ARGS) : launch_t<false, NPT, true>(OCTO_ARGS);         \
     return grad ? launch_t<true, NPT, false>(OCTO_ARGS) : launch_t<false, NPT, false>(OCTO_ARGS)

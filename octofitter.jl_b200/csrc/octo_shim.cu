@@ -232,7 +232,8 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
 // d_param != nullptr: fused parameterisation — d_in is θ_t, d_ll / d_g receive the log posterior and its gradient
 // post_mode 1 (with d_param): likelihood part only.  pointwise: value-only, one CTA row per epoch, d_ll is [n x E] (ld ldg).
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
-            int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false) {
+            int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false,
+            const HmcLeap* leap = nullptr) {
     LaunchGeom g = geometry(ctx, n, d_param != nullptr);
     if (pointwise) {
         if (ctx->m.n_epochs > 65535) return fail(OCTO_ERR_ARG, "pointwise evaluation supports at most 65535 epochs per call");
@@ -248,16 +249,17 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
         }
     }
     cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, post_mode,
-                                pointwise ? ctx->d_pw_const : nullptr, st);
+                                pointwise ? ctx->d_pw_const : nullptr, leap ? *leap : HmcLeap{}, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return OCTO_OK;
 }
 
 int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
-                    double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st, int post_mode = 0) {
+                    double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st, int post_mode = 0,
+                    const HmcLeap* leap = nullptr) {
     if (ctx->param_fused)     // one launch: θ_t -> inputs in K1's prologue, ∂/∂θ_t in its epilogue; no workspace
-        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param, post_mode);
+        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param, post_mode, false, leap);
     const int n_in = ctx->m.n_in;
     double* d_in = d_work;                      // [n x n_in]
     double* d_ll = d_work + (size_t)n * n_in;   // [n]
@@ -778,9 +780,9 @@ int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, d
 // ---- device-resident HMC explorer (octo_hmc.cu): the whole run is enqueued on one stream, one sync at the end
 namespace {
 struct HmcUser { OctoCtx* ctx; Workspace* w; int64_t n; };
-int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g) {
+int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g, const HmcLeap* leap) {
     HmcUser* u = (HmcUser*)user;
-    return logpost_enqueue(u->ctx, u->w, d_theta, u->n, u->n, d_lp, d_g, u->n, u->w->d_in, u->w->stream);
+    return logpost_enqueue(u->ctx, u->w, d_theta, u->n, u->n, d_lp, d_g, u->n, u->w->d_in, u->w->stream, 0, leap);
 }
 }  // namespace
 
@@ -815,10 +817,12 @@ int octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC setup"); break; }
         HmcUser user{ctx, w, n};
         int cb_rc = 0;
-        e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user, &cb_rc);
+        const bool fused_leap = ctx->param_fused && !getenv("OCTO_B200_HMC_SEPARATE_LEAP");
+        e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user,
+                             fused_leap, &cb_rc);
         if (cb_rc) { rc = cb_rc; cudaStreamSynchronize(w->stream); break; }
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC launch"); cudaStreamSynchronize(w->stream); break; }
-        ctx->launches.fetch_add((int64_t)n_iter * (n_leapfrog + 1) + 1, std::memory_order_relaxed);
+        ctx->launches.fetch_add((int64_t)n_iter * ((fused_leap ? 0 : n_leapfrog) + 1) + 1, std::memory_order_relaxed);
         if (theta_final) e = cudaMemcpy2DAsync(theta_final, (size_t)ld * sizeof(double), d_state, col, col, D, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && lp_final) e = cudaMemcpyAsync(lp_final, d_state + nD, col, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && accept_rate) e = cudaMemcpyAsync(accept_rate, d_acc, col, cudaMemcpyDeviceToHost, w->stream);

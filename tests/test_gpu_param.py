@@ -1,5 +1,7 @@
 """GPU tests of the device-side standard parameterisation (K0 forward/backward around K1): libocto_b200's
 octo_logpost_grad against the oracle and the mpmath goldens."""
+import os
+
 import numpy as np
 import pytest
 
@@ -371,6 +373,16 @@ def test_device_resident_hmc():
     assert np.array_equal(r1["theta"], r2["theta"]) and np.array_equal(r1["accept"], r2["accept"])
     r3 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=100)
     assert not np.array_equal(r1["theta"], r3["theta"])
+    # the leapfrog update folded into the log-posterior launch == the separate update kernel, bit for bit
+    n0 = model.kernel_launches
+    octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
+    assert model.kernel_launches - n0 == 7 * (L + 1) + 2         # L posterior launches + 1 turn per transition, + start, + final turn
+    os.environ["OCTO_B200_HMC_SEPARATE_LEAP"] = "1"
+    try:
+        r4 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
+    finally:
+        del os.environ["OCTO_B200_HMC_SEPARATE_LEAP"]
+    assert np.array_equal(r1["theta"], r4["theta"]) and np.array_equal(r1["logpost"], r4["logpost"])
     # a real run: 256 chains x 150 transitions x 12 leapfrogs, against the host-driven explorer
     th256 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((256, D))
     t0 = time.perf_counter()
