@@ -987,7 +987,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
             const OctoInputDef& d = P.defs[P.tperi_k[t]];
             if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
             double sn, cs;
-            sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
+            p_sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
             S.trig[(t * 9 + 2 * q) * 32 + lane] = sn; S.trig[(t * 9 + 2 * q + 1) * 32 + lane] = cs;
         }
         __syncthreads();

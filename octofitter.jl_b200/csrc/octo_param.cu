@@ -72,8 +72,8 @@ k_param_forward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMode
                 const bool ti = d.op == OCTO_IN_TPERI_TI;
                 double arg[8], trig[8];
                 for (int q = 0; q < (ti ? 8 : 7); ++q) arg[q] = S.in[d.a[q]];
-                sincos(arg[0], &trig[0], &trig[1]);
-                if (!ti) { sincos(arg[4], &trig[2], &trig[3]); sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]); }
+                p_sincos(arg[0], &trig[0], &trig[1]);
+                if (!ti) { p_sincos(arg[4], &trig[2], &trig[3]); p_sincos(arg[5], &trig[4], &trig[5]); p_sincos(arg[6], &trig[6], &trig[7]); }
                 double MA;
                 S.in[k] = tperi_value(m.c, d.value, arg, trig, &MA, ti);
             }
@@ -140,8 +140,8 @@ k_param_backward(const DevParam* __restrict__ Pp, const __grid_constant__ DevMod
             const int na = ti ? 8 : 7;
             double arg[8], trig[8], part[8], MA;
             for (int q = 0; q < na; ++q) arg[q] = S.in[d.a[q]];
-            sincos(arg[0], &trig[0], &trig[1]);
-            if (!ti) { sincos(arg[4], &trig[2], &trig[3]); sincos(arg[5], &trig[4], &trig[5]); sincos(arg[6], &trig[6], &trig[7]); }
+            p_sincos(arg[0], &trig[0], &trig[1]);
+            if (!ti) { p_sincos(arg[4], &trig[2], &trig[3]); p_sincos(arg[5], &trig[4], &trig[5]); p_sincos(arg[6], &trig[6], &trig[7]); }
             tperi_value(m.c, d.value, arg, trig, &MA, ti);
             tperi_reverse(m.c, arg, trig, MA, part, ti);
             const double gk = S.aux[k];
