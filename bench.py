@@ -316,6 +316,14 @@ def main():
     t0 = time.perf_counter()
     hres = octo.device_hmc(model_p, th_p, hmc_iters, step_size=1e-3, n_leapfrog=hmc_leap, inv_mass=im_p, seed=2, keep_samples=False)
     t_hmc = time.perf_counter() - t0
+    # C4-shaped parallel tempering on the same model: 64 replicas, every round 1 tempered transition of 8 leapfrogs +
+    # one swap round + re-evaluation, device-resident (octo_pt_hmc_run)
+    pt_n, pt_rounds, pt_leap = 64, 50, 8
+    lad = np.linspace(0.0, 1.0, pt_n) ** 3
+    octo.device_parallel_tempering(model_p, th_p[:pt_n], lad, 2, n_iter=1, n_leapfrog=pt_leap, step_size=1e-3, inv_mass=im_p, seed=3)
+    t0 = time.perf_counter()
+    pres = octo.device_parallel_tempering(model_p, th_p[:pt_n], lad, pt_rounds, n_iter=1, n_leapfrog=pt_leap, step_size=1e-3, inv_mass=im_p, seed=4)
+    t_pt = time.perf_counter() - t0
     clocks = sampler.stop()
 
     if world > 1:
@@ -374,6 +382,9 @@ def main():
                                "stream, one synchronisation at the end (wall clock of the call, copies included)" % (hmc_iters, hmc_leap, n),
                        "us_per_leapfrog": t_hmc / (hmc_iters * hmc_leap) * 1e6,
                        "value": pairs_step / world * hmc_iters * hmc_leap / t_hmc, "unit": "evals/s", "accept_rate": hres["accept_rate"]},
+        "pt_device": {"what": "octo_pt_hmc_run: %d replicas (C4's count) on the same tables, %d rounds of {1 tempered HMC transition x %d "
+                              "leapfrogs, even-odd swap round, re-evaluation}, one stream, one synchronisation" % (pt_n, pt_rounds, pt_leap),
+                      "us_per_round": t_pt / pt_rounds * 1e6, "mean_swap_accept": float(np.mean(pres["swap_accept"]))},
         "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -254,6 +254,18 @@ int  octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n_chains, int64
 int  octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n_chains, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
                   double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
                   double* theta_final, double* lp_final, double* accept_rate);
+/* Device-resident parallel tempering on top of the same explorer (the exploration phase of Pigeons' non-reversible PT,
+ * ext/OctofitterPigeonsExt: reference = the prior-only model, i.e. the prior terms of this model; target = the model):
+ * chain c starts on rung c of `ladder` (weights in [0, 1], ladder[n_chains-1] = 1 by convention); the tempered density
+ * of a chain is prior terms + beta * ln_like.  n_rounds rounds of { n_iter tempered HMC transitions, one deterministic
+ * even-odd swap round (the decisions of octo_pt_decide, same random stream), re-evaluation at the new weights }, all
+ * on one stream.  Swaps exchange rungs, not states.  Outputs (HOST, each may be NULL): final states, their tempered
+ * log posterior, raw ln_like, weight and rung per chain, swap acceptance counts per adjacent pair [n_chains - 1], the
+ * state of the chain on the last rung after every round [n_rounds x D], HMC acceptance rate per chain. */
+int  octo_pt_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n_chains, int64_t ld, const double* ladder, int32_t n_rounds,
+                     int32_t n_iter, int32_t n_leapfrog, double step_size, const double* inv_mass, uint64_t seed,
+                     double* theta_final, double* lp_final, double* ll_final, double* beta_final, int32_t* rung_final,
+                     double* swap_accept, double* cold_samples, double* accept_rate);
 /* the random numbers of transition `it` of chain `chain`: D standard normals (momentum, before the mass scaling) and the
  * uniform of the accept step */
 void octo_hmc_random(uint64_t seed, int64_t it, int64_t chain, int32_t D, double* z, double* u);

@@ -145,6 +145,7 @@ def load_library(path: str | None = None):
     lib.octo_loglike_theta.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_logp_pointwise.argtypes = [vp, vp, i64, i64, vp, i64]
     lib.octo_hmc_run.argtypes = [vp, vp, i64, i64, i32, i32, C.c_double, vp, C.c_uint64, vp, vp, vp, vp, vp]
+    lib.octo_pt_hmc_run.argtypes = [vp, vp, i64, i64, vp, i32, i32, i32, C.c_double, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.octo_hmc_random.argtypes = [C.c_uint64, i64, i64, i32, vp, vp]
     lib.octo_hmc_random.restype = None
     lib.octo_logpost_workspace.argtypes = [vp, i64]
@@ -182,6 +183,6 @@ def load_library(path: str | None = None):
 EXPORTED_SYMBOLS = (
     "octo_default_constants", "octo_abi_version", "octo_create", "octo_destroy", "octo_logp", "octo_logp_grad",
     "octo_logp_grad_device", "octo_set_parameterization", "octo_logpost_grad", "octo_logpost_workspace",
-    "octo_logpost_grad_device", "octo_loglike_theta", "octo_logp_pointwise", "octo_hmc_run", "octo_hmc_random", "octo_invlink", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
+    "octo_logpost_grad_device", "octo_loglike_theta", "octo_logp_pointwise", "octo_hmc_run", "octo_pt_hmc_run", "octo_hmc_random", "octo_invlink", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
     "octo_pt_decide", "octo_pt_finalize", "octo_last_error")

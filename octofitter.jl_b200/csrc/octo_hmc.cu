@@ -6,6 +6,8 @@
 // function of its arguments.  Arrays are column-major [n_chains x D] (chain fastest), one thread per chain.
 #include <math_constants.h>
 
+#include <vector>
+
 #include "octo_internal.h"
 
 namespace {
@@ -35,7 +37,20 @@ struct HmcBuf {
     double *inv_mass;                // [D]
     double *acc;                     // [n] accepted transitions
     double *out_theta, *out_lp;      // optional sample store [n_iter][n x D], [n_iter][n]
+    // parallel tempering (one chain per rung of the ladder): tempering weight and raw ln_like of every chain (current
+    // state and proposal), the ladder itself, who sits where, swap acceptance counts per adjacent pair
+    double *beta, *ll, *llp, *ladder, *swap_acc;
+    int32_t *rung_of_chain, *chain_of_rung;
 };
+
+// the uniform of octo_pt_decide (octo_shim.cu): the device-resident swap round takes the same decisions
+__host__ __device__ inline double pt_uniform_dev(uint64_t seed, uint64_t round, uint64_t pair) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (round * 0x100000001B3ULL + pair + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
 
 // accept/reject transition `it - 1` (it > 0), record the sample, then start transition `it` (it < n_iter):
 // fresh momentum, H0, first half kick and drift.
@@ -53,6 +68,7 @@ __global__ void k_hmc_turn(HmcBuf b, int64_t n, int D, int it, int n_iter, doubl
         if (accept) {
             for (int j = 0; j < D; ++j) { b.q[c + (int64_t)j * n] = b.qp[c + (int64_t)j * n]; b.g[c + (int64_t)j * n] = b.gp[c + (int64_t)j * n]; }
             b.lp[c] = lpp; b.acc[c] += 1.0;
+            if (b.ll) b.ll[c] = b.llp[c];
         }
         if (b.out_lp) b.out_lp[(int64_t)(it - 1) * n + c] = b.lp[c];
         if (b.out_theta) for (int j = 0; j < D; ++j) b.out_theta[((int64_t)(it - 1) * D + j) * n + c] = b.q[c + (int64_t)j * n];
@@ -87,6 +103,40 @@ __global__ void k_hmc_leap(HmcBuf b, int64_t n, int D, int last, double eps) {
     }
 }
 
+// One deterministic even-odd swap round (Pigeons' non-reversible scheme, as octo_pt_decide takes it on the host): pair i
+// = rungs (i, i+1), i of the round's parity.  With l_ref = lp - beta ll (prior terms) and l_target = l_ref + ll the
+// tempered density of a chain on rung k is (1 - beta_k) l_ref + beta_k l_target.  Swaps exchange rungs, not states;
+// afterwards the tempered log posterior of a swapped chain is stale and its gradient too: the caller re-evaluates.
+__global__ void k_pt_swap(HmcBuf b, int64_t n, int D, int64_t round, uint64_t seed, double* cold_out) {
+    pdl_sync();
+    const int i = (int)(round & 1) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 1 < n) {
+        const int ca = b.chain_of_rung[i], cb = b.chain_of_rung[i + 1];
+        const double bi = b.ladder[i], bj = b.ladder[i + 1];
+        const double ra = b.lp[ca] - b.beta[ca] * b.ll[ca], rb = b.lp[cb] - b.beta[cb] * b.ll[cb];      // l_ref
+        const double ta = ra + b.ll[ca], tb = rb + b.ll[cb];                                              // l_target
+        const double Vaj = (1.0 - bj) * ra + bj * ta, Vbi = (1.0 - bi) * rb + bi * tb;
+        const double Vai = (1.0 - bi) * ra + bi * ta, Vbj = (1.0 - bj) * rb + bj * tb;
+        const double log_ratio = (Vaj + Vbi) - (Vai + Vbj);
+        const double u = pt_uniform_dev(seed, (uint64_t)round, (uint64_t)i);
+        const bool acc = isfinite(log_ratio) ? (log(u) < log_ratio) : (log_ratio > 0);
+        if (acc) {
+            b.chain_of_rung[i] = cb; b.chain_of_rung[i + 1] = ca;
+            b.rung_of_chain[ca] = i + 1; b.rung_of_chain[cb] = i;
+            b.beta[ca] = bj; b.beta[cb] = bi;
+            b.swap_acc[i] += 1.0;
+        }
+    }
+}
+// the state of the chain on the last rung (beta = 1 by convention) after a round
+__global__ void k_pt_record(HmcBuf b, int64_t n, int D, int64_t round, double* cold_out) {
+    pdl_sync();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
+    const int c = b.chain_of_rung[n - 1];
+    cold_out[round * D + j] = b.q[c + (int64_t)j * n];
+}
+
 template <class... Args>
 cudaError_t launch_pdl(void (*kern)(Args...), int64_t n, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -101,39 +151,82 @@ cudaError_t launch_pdl(void (*kern)(Args...), int64_t n, cudaStream_t st, Args..
 }  // namespace
 
 // d_state: 2 * (2 n D + n) + n D + 3 n + D doubles laid out as HmcBuf expects (see octo_hmc_state_doubles)
-size_t octo_hmc_state_doubles(int64_t n, int D) { return (size_t)(2 * (2 * n * D + n) + n * D + 2 * n + D); }
+size_t octo_hmc_state_doubles(int64_t n, int D) { return (size_t)(2 * (2 * n * D + n) + n * D + 2 * n + D) + 6 * (size_t)n + 2; }
 
-// logpost(d_theta [n x D], d_lp, d_g) enqueues one log-posterior + gradient evaluation on `st`
-cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
-                             double* d_out_theta, double* d_out_lp, cudaStream_t st,
-                             int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
-                             bool fused_leap, int* rc_out) {
+static HmcBuf hmc_views(double* d_state, int64_t n, int D) {
     HmcBuf b;
     double* p = d_state;
     const size_t nD = (size_t)n * D;
     b.q = p; p += nD; b.lp = p; p += n; b.g = p; p += nD;
     b.qp = p; p += nD; b.lpp = p; p += n; b.gp = p; p += nD;
     b.p = p; p += nD; b.h0 = p; p += n; b.acc = p; p += n; b.inv_mass = p; p += D;
+    b.beta = p; p += n; b.ll = p; p += n; b.llp = p; p += n; b.ladder = p; p += n; b.swap_acc = p; p += n;
+    b.rung_of_chain = reinterpret_cast<int32_t*>(p); b.chain_of_rung = b.rung_of_chain + n;
+    b.out_theta = nullptr; b.out_lp = nullptr;
+    return b;
+}
+void octo_hmc_pt_views(double* d_state, int64_t n, int D, double** beta, double** ll, int32_t** rung_of_chain, double** swap_acc) {
+    const HmcBuf b = hmc_views(d_state, n, D);
+    *beta = b.beta; *ll = b.ll; *rung_of_chain = b.rung_of_chain; *swap_acc = b.swap_acc;
+}
+
+// logpost(d_theta [n x D], d_lp, d_g, leap) enqueues one log-posterior + gradient evaluation on `st`.
+// h_ladder != nullptr: parallel tempering — chain c starts on rung c with weight h_ladder[c]; the run is n_rounds
+// rounds of n_iter tempered HMC transitions followed by one swap round and a re-evaluation at the new weights; d_cold
+// [n_rounds x D] receives the state of the chain on the last rung after every round.  Needs the fused log posterior.
+cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
+                             double* d_out_theta, double* d_out_lp, cudaStream_t st,
+                             int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
+                             bool fused_leap, int* rc_out, const double* h_ladder, int n_rounds, double* d_cold) {
+    HmcBuf b = hmc_views(d_state, n, D);
     b.out_theta = d_out_theta; b.out_lp = d_out_lp;
+    const bool pt = h_ladder != nullptr;
+    if (!pt) { b.beta = nullptr; b.ll = nullptr; b.llp = nullptr; n_rounds = 1; }
     *rc_out = 0;
     cudaError_t e;
-    if ((*rc_out = logpost(user, b.q, b.lp, b.g, nullptr))) return cudaSuccess;   // state of the start
-    for (int it = 0; it <= n_iter; ++it) {
-        e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, seed);
+    if (pt) {
+        std::vector<double> hb(n);
+        std::vector<int32_t> id(2 * n);
+        for (int64_t c = 0; c < n; ++c) { hb[c] = h_ladder[c]; id[c] = (int32_t)c; id[n + c] = (int32_t)c; }
+        e = cudaMemcpyAsync(b.beta, hb.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b.ladder, hb.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b.rung_of_chain, id.data(), 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(b.swap_acc, 0, n * sizeof(double), st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);                         // the staging vectors are locals
         if (e != cudaSuccess) return e;
-        if (it == n_iter) break;
-        for (int l = 0; l < n_leapfrog; ++l) {
-            const int last = (int)(l == n_leapfrog - 1);
-            if (fused_leap) {        // the log-posterior launch applies the kick (and drift) itself: one launch per leapfrog
-                const HmcLeap leap{b.p, b.qp, b.inv_mass, eps, last ? 0.5 * eps : eps, !last, 0};
-                if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, &leap))) return cudaSuccess;
-                continue;
-            }
-            if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, nullptr))) return cudaSuccess;
-            e = launch_pdl(k_hmc_leap, n, st, b, n, D, last, eps);
+    }
+    const HmcLeap at_state{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, b.beta, b.ll};
+    for (int round = 0; round < n_rounds; ++round) {
+        // (re-)evaluate the current states at the current weights
+        if ((*rc_out = logpost(user, b.q, b.lp, b.g, pt ? &at_state : nullptr))) return cudaSuccess;
+        for (int it = 0; it <= n_iter; ++it) {
+            // transition counter `round * n_iter + it` keys the random stream; the sample store is per run, not per round
+            e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, (uint64_t)(seed + 0x51ED27ULL * (uint64_t)round));
             if (e != cudaSuccess) return e;
+            if (it == n_iter) break;
+            for (int l = 0; l < n_leapfrog; ++l) {
+                const int last = (int)(l == n_leapfrog - 1);
+                if (fused_leap) {    // the log-posterior launch applies the kick (and drift) itself: one launch per leapfrog
+                    const HmcLeap leap{b.p, b.qp, b.inv_mass, eps, last ? 0.5 * eps : eps, !last, 0, b.beta, b.llp};
+                    if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, &leap))) return cudaSuccess;
+                    continue;
+                }
+                const HmcLeap only_beta{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, b.beta, b.llp};
+                if ((*rc_out = logpost(user, b.qp, b.lpp, b.gp, pt ? &only_beta : nullptr))) return cudaSuccess;
+                e = launch_pdl(k_hmc_leap, n, st, b, n, D, last, eps);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        if (pt) {
+            e = launch_pdl(k_pt_swap, (n + 1) / 2, st, b, n, D, (int64_t)round, seed, d_cold);
+            if (e != cudaSuccess) return e;
+            if (d_cold) {
+                e = launch_pdl(k_pt_record, (int64_t)D, st, b, n, D, (int64_t)round, d_cold);
+                if (e != cudaSuccess) return e;
+            }
         }
     }
+    if (pt && (*rc_out = logpost(user, b.q, b.lp, b.g, &at_state))) return cudaSuccess;    // lp at the final weights
     return cudaSuccess;
 }
 

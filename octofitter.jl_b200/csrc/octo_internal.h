@@ -108,7 +108,9 @@ struct DevParam {
 
 // leapfrog update folded into the fused log-posterior launch (octo_hmc.cu): after the gradient of a chain is known,
 // p += kick * g and, unless it was the last leapfrog of the trajectory, q += eps * p * inv_mass.  p == nullptr: off.
-struct HmcLeap { double* p; double* q; const double* inv_mass; double eps, kick; int drift, pad; };
+// beta != nullptr: tempering — the likelihood part of chain c is scaled by beta[c] (log posterior = prior terms +
+// beta * ln_like, the path between Pigeons' prior-only reference and the target); ll_raw receives ln_like itself.
+struct HmcLeap { double* p; double* q; const double* inv_mass; double eps, kick; int drift, pad; const double* beta; double* ll_raw; };
 struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; };   // lat: the latency-tuned instantiation
 
 // kernels (octo_kernels.cu)
@@ -133,5 +135,8 @@ size_t octo_hmc_state_doubles(int64_t n, int D);
 cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
                              int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
-                             bool fused_leap, int* rc_out);
+                             bool fused_leap, int* rc_out, const double* h_ladder = nullptr, int n_rounds = 0,
+                             double* d_cold = nullptr);
+// after a tempered run: per-chain beta, rung of each chain, swap acceptance counts per adjacent pair (device pointers into the state)
+void octo_hmc_pt_views(double* d_state, int64_t n, int D, double** beta, double** ll, int32_t** rung_of_chain, double** swap_acc);
 

@@ -937,15 +937,16 @@ __device__ long long g_ptk[2][8];
 #else
 #define PTICK(i) do {} while (0)
 #endif
-struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *trig, *part, *lp, *extra; int* flags; };
+struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *trig, *part, *lp, *extra, *beta; int* flags; };
 __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
     ParamSmem S;
     S.th = base; S.dxdy = S.th + D * 32; S.gth = S.dxdy + D * 32; S.L = S.gth + D * 32; S.aux = S.L + D * 32;
     S.trig = S.aux + n_in * 32; S.part = S.trig + T * 9 * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
-    S.flags = reinterpret_cast<int*>(S.extra + 32);
+    S.beta = S.extra + 32;
+    S.flags = reinterpret_cast<int*>(S.beta + 32);
     return S;
 }
-__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 17 * T + 3) * 32; }
+__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 17 * T + 4) * 32; }
 
 __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
                                            int64_t ld, double* s_in, const ParamSmem& S, int* s_ok, int w, int W, int lane) {
@@ -1028,7 +1029,7 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
                                             double* __restrict__ g_t, int64_t chain0, int64_t n_chains, int64_t ldg, int w,
                                             int W, int lane, const HmcLeap& leap) {
     using namespace octo_param_dev;
-    const int D = P.D, n_in = P.n_in, T = P.n_tperi;
+    const int D = P.D, T = P.n_tperi;
 #ifdef OCTO_TIMING
     long long* ptk = g_ptk[1];
 #endif
@@ -1309,8 +1310,12 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         } else {                                               // log posterior (logdensitymodel.jl:110-146)
             const int fl = PS.flags[lane];
             const bool ok = (fl & 4) && isfinite(llv);
+            // tempering (octo_hmc.cu): the likelihood of chain c enters with weight beta[c]
+            const double bet = (leap.beta && active) ? leap.beta[chain0 + lane] : 1.0;
+            PS.beta[lane] = bet;
+            if (leap.ll_raw && active) leap.ll_raw[chain0 + lane] = ok ? llv : -CUDART_INF;
             // post_mode 1: the likelihood part alone, ln_like(system, arr2nt(θ)) incl. the UnitLengthPrior terms
-            const double like = PS.extra[lane] + llv;
+            const double like = PS.extra[lane] + bet * llv;
             if (active) ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? (post_mode == 1 ? like : PS.lp[lane] + like) : -CUDART_INF);
             PS.flags[lane] = fl | (ok ? 8 : 0);
         }
@@ -1326,7 +1331,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         for (int idx = threadIdx.x; idx < m.n_in * 32; idx += W * 32) {
             const int l = idx & 31;
             const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
-            if (P) PS.aux[idx] = (PS.flags[l] & 8) ? v : 0.0;
+            if (P) PS.aux[idx] = (PS.flags[l] & 8) ? PS.beta[l] * v : 0.0;
             else if (chain0 + l < n_chains) g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
         }
         if (P) {

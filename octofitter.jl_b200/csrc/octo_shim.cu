@@ -786,25 +786,33 @@ int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g, co
 }
 }  // namespace
 
-int octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
+namespace {
+// shared by octo_hmc_run (ladder == nullptr) and octo_pt_hmc_run
+int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
                  double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
-                 double* theta_final, double* lp_final, double* accept_rate) {
+                 double* theta_final, double* lp_final, double* accept_rate, const double* ladder, int32_t n_rounds,
+                 double* beta_final, int32_t* rung_final, double* swap_accept, double* cold_samples, double* ll_final) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
     if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
     if (!theta0 || n < 1 || ld < n || n_iter < 1 || n_leapfrog < 1 || !(step_size > 0)) return fail(OCTO_ERR_ARG, "bad arguments");
+    const bool pt = ladder != nullptr;
+    if (pt && !ctx->param_fused) return fail(OCTO_ERR_STATE, "tempering needs the fused log-posterior launch (not available for this model)");
+    if (pt && (n_rounds < 1 || n < 2)) return fail(OCTO_ERR_ARG, "parallel tempering needs >= 2 chains and >= 1 round");
+    if (pt) for (int64_t c = 0; c < n; ++c) if (!(ladder[c] >= 0.0 && ladder[c] <= 1.0)) return fail(OCTO_ERR_ARG, "ladder weights must lie in [0, 1]");
     const int D = ctx->param_D, n_in = ctx->m.n_in;
     if (inv_mass) for (int j = 0; j < D; ++j) if (!(inv_mass[j] > 0) || !std::isfinite(inv_mass[j])) return fail(OCTO_ERR_ARG, "inverse mass must be positive");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = lease(ctx);
     if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
     const size_t col = (size_t)n * sizeof(double), nD = (size_t)n * D;
-    double *d_state = nullptr, *d_ot = nullptr, *d_ol = nullptr;
+    double *d_state = nullptr, *d_ot = nullptr, *d_ol = nullptr, *d_cold = nullptr;
     int rc = OCTO_OK;
     do {
         if (!ctx->param_fused && (rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * D + 3)))) break;
         cudaError_t e = cudaMalloc((void**)&d_state, octo_hmc_state_doubles(n, D) * sizeof(double));
         if (e == cudaSuccess && theta_samples) e = cudaMalloc((void**)&d_ot, (size_t)n_iter * nD * sizeof(double));
         if (e == cudaSuccess && lp_samples) e = cudaMalloc((void**)&d_ol, (size_t)n_iter * col);
+        if (e == cudaSuccess && pt && cold_samples) e = cudaMalloc((void**)&d_cold, (size_t)n_rounds * D * sizeof(double));
         if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc (HMC state)"); break; }
         double* d_acc = d_state + 5 * nD + 3 * (size_t)n;
         double* d_im = d_acc + n;
@@ -819,24 +827,53 @@ int octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
         int cb_rc = 0;
         const bool fused_leap = ctx->param_fused && !getenv("OCTO_B200_HMC_SEPARATE_LEAP");
         e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user,
-                             fused_leap, &cb_rc);
+                             fused_leap, &cb_rc, ladder, pt ? n_rounds : 0, d_cold);
         if (cb_rc) { rc = cb_rc; cudaStreamSynchronize(w->stream); break; }
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC launch"); cudaStreamSynchronize(w->stream); break; }
-        ctx->launches.fetch_add((int64_t)n_iter * ((fused_leap ? 0 : n_leapfrog) + 1) + 1, std::memory_order_relaxed);
+        const int64_t rounds = pt ? n_rounds : 1;
+        ctx->launches.fetch_add(rounds * ((int64_t)n_iter * ((fused_leap ? 0 : n_leapfrog) + 1) + 1 + (pt ? 1 + (d_cold ? 1 : 0) : 0)),
+                                std::memory_order_relaxed);
         if (theta_final) e = cudaMemcpy2DAsync(theta_final, (size_t)ld * sizeof(double), d_state, col, col, D, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && lp_final) e = cudaMemcpyAsync(lp_final, d_state + nD, col, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && accept_rate) e = cudaMemcpyAsync(accept_rate, d_acc, col, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && theta_samples) e = cudaMemcpyAsync(theta_samples, d_ot, (size_t)n_iter * nD * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && lp_samples) e = cudaMemcpyAsync(lp_samples, d_ol, (size_t)n_iter * col, cudaMemcpyDeviceToHost, w->stream);
+        if (pt) {
+            double *d_beta, *d_ll, *d_swap; int32_t* d_rung;
+            octo_hmc_pt_views(d_state, n, D, &d_beta, &d_ll, &d_rung, &d_swap);
+            if (e == cudaSuccess && beta_final) e = cudaMemcpyAsync(beta_final, d_beta, col, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && ll_final) e = cudaMemcpyAsync(ll_final, d_ll, col, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && rung_final) e = cudaMemcpyAsync(rung_final, d_rung, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && swap_accept) e = cudaMemcpyAsync(swap_accept, d_swap, (size_t)(n - 1) * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && cold_samples) e = cudaMemcpyAsync(cold_samples, d_cold, (size_t)n_rounds * D * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC run"); break; }
-        if (accept_rate) for (int64_t c = 0; c < n; ++c) accept_rate[c] /= (double)n_iter;
+        if (accept_rate) for (int64_t c = 0; c < n; ++c) accept_rate[c] /= (double)(n_iter * rounds);
     } while (0);
     if (d_state) cudaFree(d_state);
     if (d_ot) cudaFree(d_ot);
     if (d_ol) cudaFree(d_ol);
+    if (d_cold) cudaFree(d_cold);
     release(ctx, w);
     return rc;
+}
+}  // namespace
+
+int octo_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
+                 double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
+                 double* theta_final, double* lp_final, double* accept_rate) {
+    return hmc_run_impl(ctx, theta0, n, ld, n_iter, n_leapfrog, step_size, inv_mass, seed, theta_samples, lp_samples, theta_final,
+                        lp_final, accept_rate, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int octo_pt_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, const double* ladder, int32_t n_rounds,
+                    int32_t n_iter, int32_t n_leapfrog, double step_size, const double* inv_mass, uint64_t seed,
+                    double* theta_final, double* lp_final, double* ll_final, double* beta_final, int32_t* rung_final,
+                    double* swap_accept, double* cold_samples, double* accept_rate) {
+    if (!ladder) return fail(OCTO_ERR_ARG, "ladder is null");
+    return hmc_run_impl(ctx, theta0, n, ld, n_iter, n_leapfrog, step_size, inv_mass, seed, nullptr, nullptr, theta_final, lp_final,
+                        accept_rate, ladder, n_rounds, beta_final, rung_final, swap_accept, cold_samples, ll_final);
 }
 
 int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {

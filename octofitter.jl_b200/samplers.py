@@ -79,6 +79,30 @@ def device_hmc(model, theta0, n_iter, *, step_size=0.02, n_leapfrog=16, inv_mass
             "n_gradient_calls": n_iter * n_leapfrog + 1}
 
 
+def device_parallel_tempering(model, theta0, ladder, n_rounds, *, n_iter=1, n_leapfrog=8, step_size=0.02, inv_mass=None, seed=0):
+    """Device-resident parallel tempering (C ABI `octo_pt_hmc_run`): chain c starts on rung c of `ladder`; every round
+    is n_iter tempered HMC transitions for all chains, one deterministic even-odd swap round and a re-evaluation at the
+    new weights, all enqueued on one stream.  Returns final states, tempered log posterior, raw ln_like, weight and rung
+    of every chain, swap acceptance rate per adjacent pair and the trace of the chain on the last rung."""
+    import ctypes as C
+    th = np.array(theta0, dtype=np.float64, order="F")
+    n, D = th.shape
+    lad = np.ascontiguousarray(ladder, dtype=np.float64)
+    assert lad.shape == (n,)
+    im = None if inv_mass is None else np.ascontiguousarray(inv_mass, dtype=np.float64)
+    th_f = np.empty((n, D), order="F"); lp = np.empty(n); ll = np.empty(n); beta = np.empty(n)
+    rung = np.empty(n, dtype=np.int32); swaps = np.empty(n - 1); cold = np.empty((n_rounds, D)); acc = np.empty(n)
+    p = lambda a: None if a is None else a.ctypes.data
+    model._check(model._lib.octo_pt_hmc_run(model._h, th.ctypes.data, n, n, lad.ctypes.data, int(n_rounds), int(n_iter),
+                                            int(n_leapfrog), float(step_size), p(im), C.c_uint64(int(seed)), th_f.ctypes.data,
+                                            lp.ctypes.data, ll.ctypes.data, beta.ctypes.data, rung.ctypes.data, swaps.ctypes.data,
+                                            cold.ctypes.data, acc.ctypes.data))
+    # pair i is proposed on the rounds of its parity
+    proposals = np.array([(n_rounds + (1 - (i & 1))) // 2 for i in range(n - 1)], dtype=np.float64)
+    return {"theta_final": th_f, "logpost_tempered": lp, "loglike": ll, "beta": beta, "rung": rung,
+            "swap_accept": swaps / np.maximum(proposals, 1.0), "swap_counts": swaps, "cold_trace": cold, "accept": acc}
+
+
 def hmc_random(model, seed, it, chain, D):
     """(z[D], u): the standard normals and the accept-step uniform `octo_hmc_run` uses for transition `it` of `chain`."""
     import ctypes as C

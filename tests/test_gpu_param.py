@@ -477,3 +477,51 @@ def test_octofit_recovers_the_fixture_orbit():
     between = lp_tail.mean(axis=0).var(); within = lp_tail.var(axis=0).mean()
     assert between < 0.5 * within
     model.close()
+
+
+def test_device_parallel_tempering():
+    """octo_pt_hmc_run.  (1) With every weight equal to 1 it is the plain explorer, bit for bit (tempering multiplies
+    by 1.0; equal-weight swaps always happen and change nothing).  (2) Frozen states with widely separated likelihoods:
+    the swap round takes the decisions of the even-odd rule.  (3) A real ladder on the reference's test model: rungs stay
+    a permutation, weights follow rungs, neighbours do swap, and the chain on the last rung ends at a plausible log
+    posterior."""
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(4)
+    params, lp0 = model.guess_starting_position(rng, N=60_000, batch=20_000)
+    start = model.link(params)
+    inv_mass = octo.diagonal_metric(model, start)
+    n, D = 32, spec.D
+    th0 = np.asfortranarray(start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((n, D)))
+    # (1)
+    plain = octo.device_hmc(model, th0, 6, step_size=0.1, n_leapfrog=5, inv_mass=inv_mass, seed=77)
+    ones = octo.device_parallel_tempering(model, th0, np.ones(n), 1, n_iter=6, n_leapfrog=5, step_size=0.1, inv_mass=inv_mass, seed=77)
+    assert np.array_equal(ones["theta_final"], plain["theta_final"]) and np.array_equal(ones["logpost_tempered"], plain["logpost_final"])
+    assert np.all(ones["swap_counts"][0::2] == 1) and np.all(ones["swap_counts"][1::2] == 0)          # round 0 pairs (0,1), (2,3), ...
+    assert sorted(ones["rung"]) == list(range(n)) and np.all(ones["beta"] == 1.0)
+    # (2) frozen states: chain c sits further from the start the larger c is => ln_like falls steeply with c
+    spread = np.linspace(0.0, 6.0, n)[:, None]
+    th_far = np.asfortranarray(start[None, :] + spread * np.sqrt(inv_mass)[None, :] * np.sign(rng.standard_normal((1, D))))
+    ladder = np.linspace(0.0, 1.0, n)
+    res = octo.device_parallel_tempering(model, th_far, ladder, 1, n_iter=1, n_leapfrog=1, step_size=1e-12, inv_mass=inv_mass, seed=5)
+    ll = res["loglike"]                  # the data likelihood alone: the UnitLengthPrior terms belong to the reference too
+    assert np.isfinite(ll).all() and np.all(np.diff(ll) < 0)
+    # tempered density = full posterior - (1 - beta) ln_like, at the weights the chains hold after the swap round
+    assert np.allclose(model.ℓπcallback(th_far) - res["logpost_tempered"], (1.0 - res["beta"]) * ll, rtol=1e-9, atol=1e-9)
+    for i in range(0, n - 1, 2):
+        log_ratio = (ladder[i] - ladder[i + 1]) * (ll[i + 1] - ll[i])
+        if abs(log_ratio) > 40:                                       # far from any uniform draw's log
+            assert res["swap_counts"][i] == (1.0 if log_ratio > 0 else 0.0), (i, log_ratio)
+    assert np.all(res["swap_counts"][1::2] == 0)
+    assert sorted(res["rung"]) == list(range(n)) and np.array_equal(res["beta"], ladder[res["rung"]])
+    # (3) a real run from scattered starts
+    th_pr = model.link(model.sample_priors(rng, n))
+    th_pr[-1] = start
+    ladder = np.linspace(0.0, 1.0, n) ** 3
+    out = octo.device_parallel_tempering(model, th_pr, ladder, 60, n_iter=2, n_leapfrog=10, step_size=0.1, inv_mass=inv_mass, seed=9)
+    assert sorted(out["rung"]) == list(range(n)) and np.array_equal(out["beta"], ladder[out["rung"]])
+    assert np.all((out["swap_accept"] >= 0) & (out["swap_accept"] <= 1)) and out["swap_accept"].mean() > 0.05
+    cold = int(np.argmax(out["rung"]))
+    assert out["beta"][cold] == 1.0 and np.isfinite(out["logpost_tempered"][cold]) and out["logpost_tempered"][cold] > lp0 - 40
+    assert np.array_equal(out["cold_trace"][-1], out["theta_final"][cold])
+    model.close()
