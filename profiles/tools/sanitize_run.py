@@ -48,4 +48,6 @@ spec, th = workloads.one_planet_with_priors(40, 30, 45, seed=2)
 m = octo.LogDensityModel(spec)
 r = octo.device_hmc(m, th, 3, step_size=1e-3, n_leapfrog=4, inv_mass=np.full(spec.D, 1e-4), seed=3)
 print("hmc", r["accept_rate"], float(r["logpost_final"][0]))
+pt = octo.device_parallel_tempering(m, th[:16], np.linspace(0, 1, 16), 3, n_iter=1, n_leapfrog=3, step_size=1e-3, inv_mass=np.full(spec.D, 1e-4), seed=5)
+print("pt", sorted(pt["rung"]) == list(range(16)), float(pt["swap_accept"].mean()))
 m.close()
