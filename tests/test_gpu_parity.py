@@ -515,3 +515,23 @@ def test_thiele_innes_planets_with_hgca_and_observable_prior(oracle_lib):
     with pytest.raises(octo.OctoError):
         rv = octo.StarAbsoluteRVObs(octo.Table(epoch=[5e4], rv=[1.0], σ_rv=[1.0]), name="rv", variables=["offset", "jitter"])
         octo.ModelSpec(octo.System(name="bad", variables=["M", "plx"], companions=[pc], observations=[rv]))
+
+
+def test_latency_and_throughput_instantiations_agree(oracle_lib, monkeypatch):
+    """Small grids run the latency-tuned instantiation of the kernel (no register cap, one CTA per SM, fewer epoch
+    splits), large ones the throughput instantiation; OCTO_B200_LATENCY=0 forces the latter.  Same results (different
+    summation trees: agreement to rounding), both against the oracle."""
+    import workloads
+    spec, x = workloads.config("C2")
+    x = x[:512]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("OCTO_B200_LATENCY", mode)
+        model = octo.LogDensityModel(spec)
+        out[mode] = model.ln_like_and_gradient(x) + (model.launch_geometry(512),)
+        model.close()
+    assert out["1"][2][:2] != out["0"][2][:2] and out["1"][2][0] * out["1"][2][1] <= 148     # fewer, fatter CTAs
+    ll_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(x, threads=4)
+    for mode in ("1", "0"):
+        assert rel_err(out[mode][0], ll_o).max() < LOGP_RTOL and grad_err(out[mode][1], g_o).max() < GRAD_RTOL
+    assert rel_err(out["1"][0], out["0"][0]).max() < 1e-13
