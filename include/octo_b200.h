@@ -241,7 +241,7 @@ int  octo_loglike_theta(OctoCtx* ctx, const double* theta_t, int64_t n_chains, i
 /* Per-epoch log-likelihoods of natural-space kernel inputs: out[chain + e * ldo] (e = 0 .. octo_total_epochs - 1, in
  * the order the tables were passed to octo_create) is ln_like of the model reduced to that single epoch, i.e. one
  * column per system of `generate_system_per_epoch` — the matrix `pointwise_like` builds
- * (src/cross-validation.jl:6-49, 453-497).  HOST buffers; n_chains * epochs <= 2e9 and epochs <= 65535 per call. */
+ * (src/cross-validation.jl:6-49, 453-497).  HOST buffers; n_chains * epochs <= 2e9 per call. */
 int  octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, double* out, int64_t ldo);
 /* A device-resident, chain-batched static-trajectory HMC explorer over the log-posterior launch: n_iter transitions of
  * n_leapfrog leapfrog steps (step_size, diagonal inverse mass inv_mass[D] or NULL = identity) for all n_chains in

@@ -1203,7 +1203,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
             int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
             if (pw_const) {      // pointwise mode: this CTA evaluates the single epoch blockIdx.y (warp 0)
-                const int ep = (int)blockIdx.y;
+                const int ep = (int)blockIdx.y + (post_mode >> 9);          // + first epoch of this chunk (grid.y <= 65535)
                 const bool mine = w == 0 && ep >= B.start && ep < B.start + B.n;
                 k0 = mine ? ep : 0; k1 = mine ? ep + 1 : 0;
             }

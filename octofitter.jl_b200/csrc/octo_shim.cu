@@ -233,12 +233,13 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
 // post_mode 1 (with d_param): likelihood part only.  pointwise: value-only, one CTA row per epoch, d_ll is [n x E] (ld ldg).
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
             int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false,
-            const HmcLeap* leap = nullptr) {
+            const HmcLeap* leap = nullptr, int64_t pw_e0 = 0, int64_t pw_n = 0) {
     LaunchGeom g = geometry(ctx, n, d_param != nullptr);
-    if (pointwise) {
-        if (ctx->m.n_epochs > 65535) return fail(OCTO_ERR_ARG, "pointwise evaluation supports at most 65535 epochs per call");
+    if (pointwise) {      // epochs [pw_e0, pw_e0 + pw_n) of the concatenated list, one CTA row each
+        if (pw_n < 1 || pw_n > 65535 || pw_e0 < 0 || pw_e0 + pw_n > ctx->m.n_epochs || pw_e0 >= (1 << 22)) return fail(OCTO_ERR_ARG, "bad pointwise chunk");
         const int W = ctx->warps > 4 ? 4 : ctx->warps;        // one warp does the epoch; the others only help the prologue
-        g.block = W * 32; g.gy = (int)ctx->m.n_epochs; g.smem = octo_smem_bytes(ctx->m, W); g.lat = false;
+        g.block = W * 32; g.gy = (int)pw_n; g.smem = octo_smem_bytes(ctx->m, W); g.lat = false;
+        post_mode |= (int)(pw_e0 << 9);
     }
     if (g.gy > 1 && !pointwise) {
         size_t need = (size_t)g.gx * g.gy * ctx->m.n_acc * 32;
@@ -249,7 +250,7 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
         }
     }
     cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, post_mode,
-                                pointwise ? ctx->d_pw_const : nullptr, leap ? *leap : HmcLeap{}, st);
+                                pointwise ? ctx->d_pw_const + pw_e0 : nullptr, leap ? *leap : HmcLeap{}, st);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return OCTO_OK;
@@ -768,7 +769,10 @@ int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, d
         if ((rc = ensure(&w->d_post, &w->cap_post, (size_t)n * E))) break;
         cudaError_t e = cudaMemcpy2DAsync(w->d_in, col, in, (size_t)ld * sizeof(double), col, n_in, cudaMemcpyHostToDevice, w->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if ((rc = enqueue(ctx, w, false, w->d_in, n, n, w->d_post, nullptr, n, w->stream, nullptr, 0, true))) break;
+        for (int64_t e0 = 0; e0 < E && !rc; e0 += 65535)        // grid.y is limited to 65535 rows: chunks of epochs
+            rc = enqueue(ctx, w, false, w->d_in, n, n, w->d_post + e0 * n, nullptr, n, w->stream, nullptr, 0, true, nullptr, e0,
+                         std::min<int64_t>(65535, E - e0));
+        if (rc) break;
         e = cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), w->d_post, col, col, (size_t)E, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "pointwise evaluation"); break; }

@@ -535,3 +535,18 @@ def test_latency_and_throughput_instantiations_agree(oracle_lib, monkeypatch):
     for mode in ("1", "0"):
         assert rel_err(out[mode][0], ll_o).max() < LOGP_RTOL and grad_err(out[mode][1], g_o).max() < GRAD_RTOL
     assert rel_err(out["1"][0], out["0"][0]).max() < 1e-13
+
+
+def test_pointwise_like_more_epochs_than_one_grid(oracle_lib):
+    """More than 65535 epochs: octo_logp_pointwise walks the epoch list in chunks.  The columns sum to ln_like and
+    spot-checked columns equal the oracle on the one-epoch model."""
+    import workloads
+    spec, x = workloads.one_planet(70_000, 0, 6, seed=8)
+    model = octo.LogDensityModel(spec)
+    LL, epochs = model.pointwise_like(x)
+    assert LL.shape == (6, 70_000) and np.all(np.diff(epochs) >= 0)
+    assert rel_err(LL.sum(axis=1), model.ln_like(x)).max() < 1e-11
+    consts = octo.default_constants()
+    for e in (0, 65_534, 65_535, 65_536, 69_999):
+        ll_o = oracle_lib.Oracle(_single_epoch_model(spec, e), consts).logp(x)
+        assert rel_err(LL[:, e], ll_o).max() < LOGP_RTOL, e
