@@ -106,6 +106,12 @@ struct DevParam {
     int16_t gat[2 * OCTO_PARAM_MAX];
 };
 
+// Tiny batches (a single chain, as the reference's samplers call the model): the inputs travel inside the kernel
+// parameters instead of through a host-to-device copy of their own (saves that copy's ~3 us of a ~26 us call).
+#define OCTO_INLINE_MAX 64
+#define OCTO_MODE_INLINE 256      // post_mode flag: read the inputs from the InlineIn parameter, column-major [n x cols], ld = n
+struct InlineIn { double v[OCTO_INLINE_MAX]; };
+
 // leapfrog update folded into the fused log-posterior launch (octo_hmc.cu): after the gradient of a chain is known,
 // p += kick * g and, unless it was the last leapfrog of the trajectory, q += eps * p * inv_mass.  p == nullptr: off.
 // beta != nullptr: tempering — the likelihood part of chain c is scaled by beta[c] (log posterior = prior terms +
@@ -117,7 +123,7 @@ struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; }; 
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
-                        const HmcLeap& leap, cudaStream_t stream);
+                        const HmcLeap& leap, cudaStream_t stream, const InlineIn* inl = nullptr);
 size_t octo_smem_bytes(const DevModel& m, int warps, int D = 0, int n_tperi = 0);
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int warps, int* ctas_per_sm);
 cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c);

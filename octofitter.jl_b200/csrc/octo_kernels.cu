@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : 
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
               unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
-              const double* __restrict__ pw_const, const HmcLeap leap) {
+              const double* __restrict__ pw_const, const HmcLeap leap, const __grid_constant__ InlineIn inl) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -1161,14 +1161,15 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     // ---- inputs of this CTA's chains into shared memory, with the finiteness check of logdensitymodel.jl:120-124;
     //      with a parameterisation `in` is θ_t and the inputs are derived here (param_forward)
     ParamSmem PS;
+    const double* inp = (post_mode & OCTO_MODE_INLINE) ? inl.v : in;       // tiny batches carry their inputs in the parameters
     if (P) {
         PS = param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi);
-        param_forward(*P, m, in, chain_of(lane), ld, s_in, PS, s_ok, w, W, lane);
+        param_forward(*P, m, inp, chain_of(lane), ld, s_in, PS, s_ok, w, W, lane);
     } else {
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * m.n_in; it += W * 32) {
             const int col = it % ncol, k = it / ncol;
-            const double v = in[chain_of(col) + (int64_t)k * ld];
+            const double v = inp[chain_of(col) + (int64_t)k * ld];
             s_in[it] = v;
             if (!isfinite(v)) s_ok[col] = 0;
         }
@@ -1181,7 +1182,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
         const int col = it % ncol, task = it / ncol;
         const bool ok = P ? prologue_task(m, task / 5, task % 5, s_in, col, 32, s_const + (task / 5) * PC_COUNT * 32, col)
-                          : prologue_task(m, task / 5, task % 5, in, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col);
+                          : prologue_task(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col);
         if (!ok) s_ok[col] = 0;
     }
     __syncthreads();
@@ -1381,7 +1382,7 @@ template <bool GRAD, int NPT, bool LAT>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
-                            cudaStream_t st) {
+                            cudaStream_t st, const InlineIn* inl) {
     // programmatic dependent launch: the kernel lets the next launch on the stream be scheduled while it is still
     // running (griddepcontrol.launch_dependents) and itself waits for everything before it in the stream to complete
     // and become visible before it touches memory (griddepcontrol.wait) — stream semantics, minus the launch gap
@@ -1394,8 +1395,9 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 #ifdef OCTO_NO_PDL
     cfg.numAttrs = 0;
 #endif
+    static const InlineIn none{};
     return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
-                              post_mode, d_pw_const, leap);
+                              inl ? (post_mode | OCTO_MODE_INLINE) : post_mode, d_pw_const, leap, inl ? *inl : none);
 }
 
 // opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
@@ -1422,8 +1424,8 @@ cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
-                        const HmcLeap& leap, cudaStream_t st) {
-#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st
+                        const HmcLeap& leap, cudaStream_t st, const InlineIn* inl) {
+#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl
 #define OCTO_DISPATCH(NPT)                                                                                        \
     if (g.lat) return grad ? launch_t<true, NPT, true>(OCTO_ARGS) : launch_t<false, NPT, true>(OCTO_ARGS);         \
     return grad ? launch_t<true, NPT, false>(OCTO_ARGS) : launch_t<false, NPT, false>(OCTO_ARGS)

@@ -233,7 +233,7 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
 // post_mode 1 (with d_param): likelihood part only.  pointwise: value-only, one CTA row per epoch, d_ll is [n x E] (ld ldg).
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
             int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false,
-            const HmcLeap* leap = nullptr, int64_t pw_e0 = 0, int64_t pw_n = 0) {
+            const HmcLeap* leap = nullptr, int64_t pw_e0 = 0, int64_t pw_n = 0, const InlineIn* inl = nullptr) {
     LaunchGeom g = geometry(ctx, n, d_param != nullptr);
     if (pointwise) {      // epochs [pw_e0, pw_e0 + pw_n) of the concatenated list, one CTA row each
         if (pw_n < 1 || pw_n > 65535 || pw_e0 < 0 || pw_e0 + pw_n > ctx->m.n_epochs || pw_e0 >= (1 << 22)) return fail(OCTO_ERR_ARG, "bad pointwise chunk");
@@ -250,7 +250,7 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
         }
     }
     cudaError_t e = octo_launch(ctx->m, g, grad, d_in, n, ld, d_ll, d_g, ldg, w->d_partial, w->d_tickets, d_param, post_mode,
-                                pointwise ? ctx->d_pw_const + pw_e0 : nullptr, leap ? *leap : HmcLeap{}, st);
+                                pointwise ? ctx->d_pw_const + pw_e0 : nullptr, leap ? *leap : HmcLeap{}, st, inl);
     if (e != cudaSuccess) return fail_cuda(e, "kernel launch");
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     return OCTO_OK;
@@ -258,9 +258,9 @@ int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n
 
 int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n, int64_t ld, double* d_lp,
                     double* d_g_t, int64_t ldg, double* d_work, cudaStream_t st, int post_mode = 0,
-                    const HmcLeap* leap = nullptr) {
+                    const HmcLeap* leap = nullptr, const InlineIn* inl = nullptr) {
     if (ctx->param_fused)     // one launch: θ_t -> inputs in K1's prologue, ∂/∂θ_t in its epilogue; no workspace
-        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param, post_mode, false, leap);
+        return enqueue(ctx, w, d_g_t != nullptr, d_theta, n, ld, d_lp, d_g_t, ldg, st, ctx->d_param, post_mode, false, leap, 0, 0, inl);
     const int n_in = ctx->m.n_in;
     double* d_in = d_work;                      // [n x n_in]
     double* d_ll = d_work + (size_t)n * n_in;   // [n]
@@ -307,8 +307,13 @@ int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, in
         double* d_ll = direct_out ? ll : d_y;
         double* d_g = direct_out ? g : d_y + n;
         const int64_t ldg = direct_out ? ld : n;
-        cudaError_t e;
-        if (pin_in) {
+        cudaError_t e = cudaSuccess;
+        // tiny batch: the inputs ride in the kernel parameters, no copy launch at all
+        InlineIn inl;
+        const bool inline_in = (size_t)n * nc <= OCTO_INLINE_MAX && (!post || ctx->param_fused);
+        if (inline_in) {
+            for (int k = 0; k < nc; ++k) memcpy(inl.v + (size_t)k * n, in + (size_t)k * ld, col);
+        } else if (pin_in) {
             e = (ld == n) ? cudaMemcpyAsync(d_x, in, col * nc, cudaMemcpyHostToDevice, w->stream)
                           : cudaMemcpy2DAsync(d_x, col, in, pitch, col, nc, cudaMemcpyHostToDevice, w->stream);
         } else {
@@ -317,8 +322,9 @@ int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, in
             e = cudaMemcpyAsync(d_x, w->h_in, col * nc, cudaMemcpyHostToDevice, w->stream);
         }
         if (e != cudaSuccess) { rc = fail_cuda(e, "H2D"); break; }
-        if (post) rc = logpost_enqueue(ctx, w, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->d_in, w->stream, post_mode);
-        else rc = enqueue(ctx, w, grad, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->stream);
+        const InlineIn* pinl = inline_in ? &inl : nullptr;
+        if (post) rc = logpost_enqueue(ctx, w, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->d_in, w->stream, post_mode, nullptr, pinl);
+        else rc = enqueue(ctx, w, grad, d_x, n, n, d_ll, grad ? d_g : nullptr, ldg, w->stream, nullptr, 0, false, nullptr, 0, 0, pinl);
         if (rc) break;
         if (!direct_out) {
             if ((rc = ensure(&w->h_out, &w->cap_hout, (size_t)n * (nc + 1), true))) break;
