@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define OCTO_ABI_VERSION 2
+#define OCTO_ABI_VERSION 3
 #define OCTO_MAX_PLANETS 4
 
 /* error codes */
@@ -295,8 +295,10 @@ int32_t octo_n_planets(const OctoCtx* ctx);
 int64_t octo_total_epochs(const OctoCtx* ctx);   /* E: length of the concatenated epoch list      */
 int32_t octo_device(const OctoCtx* ctx);
 int64_t octo_kernel_launches(const OctoCtx* ctx); /* kernels launched so far through this context */
-/* launch geometry chosen for a batch of n_chains: {grid.x = chain groups, grid.y = epoch splits, block, epochs per warp} */
-int  octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]);
+/* launch geometry chosen for a batch of n_chains: {grid.x = chain groups, grid.y = epoch splits across CTAs, block,
+ * epochs per (warp, sub-lane) unit, sub-lanes per chain inside a warp (1 = lane is chain; a chain group has 32 / that
+ * many chains), 1 if the latency-tuned instantiation (one CTA per SM) runs it} */
+int  octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[6]);
 
 /*
  * Parallel-tempering swap round (replaces the replica exchange Pigeons does over

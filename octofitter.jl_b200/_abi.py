@@ -167,7 +167,7 @@ def load_library(path: str | None = None):
     lib.octo_device.restype = i32
     lib.octo_kernel_launches.argtypes = [vp]
     lib.octo_kernel_launches.restype = i64
-    lib.octo_launch_geometry.argtypes = [vp, i64, C.POINTER(i32 * 4)]
+    lib.octo_launch_geometry.argtypes = [vp, i64, C.POINTER(i32 * 6)]
     lib.octo_pt_unique_id.argtypes = [vp]
     lib.octo_pt_init.argtypes = [vp, vp, i32, i32, i32, C.c_uint64]
     lib.octo_pt_swap_round.argtypes = [vp, vp, vp, vp, i64, vp]

@@ -9,21 +9,11 @@
 #include <vector>
 
 #include "octo_internal.h"
+#include "octo_hmc_dev.cuh"
 
 namespace {
 
-__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-__host__ __device__ inline double u01(uint64_t s) { return ((double)(s >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
-// stream of (seed, iteration): coordinate j of chain c draws from splitmix64(key ^ (c * K1 + j * K2))
-__host__ __device__ inline uint64_t hmc_key(uint64_t seed, uint64_t it) { return splitmix64(seed ^ splitmix64(it + 1)); }
-__host__ __device__ inline uint64_t hmc_draw(uint64_t key, uint64_t chain, uint64_t j) {
-    return splitmix64(key ^ (chain * 0x9E3779B97F4A7C15ULL + j * 0xD1B54A32D192ED03ULL));
-}
+using namespace octo_hmc_dev;
 
 __device__ __forceinline__ void pdl_sync() {
     asm volatile("griddepcontrol.launch_dependents;");
@@ -43,15 +33,6 @@ struct HmcBuf {
     int32_t *rung_of_chain, *chain_of_rung;
 };
 
-// the uniform of octo_pt_decide (octo_shim.cu): the device-resident swap round takes the same decisions
-__host__ __device__ inline double pt_uniform_dev(uint64_t seed, uint64_t round, uint64_t pair) {
-    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (round * 0x100000001B3ULL + pair + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z ^= z >> 31;
-    return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-}
-
 // accept/reject transition `it - 1` (it > 0), record the sample, then start transition `it` (it < n_iter):
 // fresh momentum, H0, first half kick and drift.
 __global__ void k_hmc_turn(HmcBuf b, int64_t n, int D, int it, int n_iter, double eps, uint64_t seed) {
@@ -61,11 +42,8 @@ __global__ void k_hmc_turn(HmcBuf b, int64_t n, int D, int it, int n_iter, doubl
     if (it > 0) {
         const double lpp = b.lpp[c];
         double kin = 0.0;
-        for (int j = 0; j < D; ++j) { const double pj = b.p[c + (int64_t)j * n]; kin += pj * pj * b.inv_mass[j]; }
-        const double h1 = -lpp + 0.5 * kin;
-        const double u = u01(hmc_draw(hmc_key(seed, it - 1), (uint64_t)c, (uint64_t)D));
-        const bool accept = isfinite(lpp) && (log(u) < b.h0[c] - h1);
-        if (accept) {
+        for (int j = 0; j < D; ++j) kin = __dadd_rn(kin, hmc_kin(b.p[c + (int64_t)j * n], b.inv_mass[j]));
+        if (hmc_accept(seed, it - 1, (uint64_t)c, D, b.h0[c], lpp, kin)) {
             for (int j = 0; j < D; ++j) { b.q[c + (int64_t)j * n] = b.qp[c + (int64_t)j * n]; b.g[c + (int64_t)j * n] = b.gp[c + (int64_t)j * n]; }
             b.lp[c] = lpp; b.acc[c] += 1.0;
             if (b.ll) b.ll[c] = b.llp[c];
@@ -77,16 +55,12 @@ __global__ void k_hmc_turn(HmcBuf b, int64_t n, int D, int it, int n_iter, doubl
     const uint64_t key = hmc_key(seed, it);
     double kin = 0.0;
     for (int j = 0; j < D; ++j) {
-        const uint64_t s = hmc_draw(key, (uint64_t)c, (uint64_t)j);
-        const double z = sqrt(-2.0 * log(u01(s))) * cospi(2.0 * u01(splitmix64(s)));      // Box-Muller
-        const double im = b.inv_mass[j];
-        double pj = z * rsqrt(im);                                                          // p ~ N(0, M), M = 1 / inv_mass
-        kin += pj * pj * im;
-        pj += 0.5 * eps * b.g[c + (int64_t)j * n];
-        b.p[c + (int64_t)j * n] = pj;
-        b.qp[c + (int64_t)j * n] = b.q[c + (int64_t)j * n] + eps * pj * im;
+        const HmcStart r = hmc_start(key, (uint64_t)c, j, b.inv_mass[j], eps, b.g[c + (int64_t)j * n], b.q[c + (int64_t)j * n]);
+        kin = __dadd_rn(kin, r.kin);
+        b.p[c + (int64_t)j * n] = r.p;
+        b.qp[c + (int64_t)j * n] = r.q;
     }
-    b.h0[c] = -b.lp[c] + 0.5 * kin;
+    b.h0[c] = hmc_h0(b.lp[c], kin);
 }
 
 // after a log-posterior launch on the proposal: (half) kick, and drift unless it was the last leapfrog
@@ -177,7 +151,8 @@ void octo_hmc_pt_views(double* d_state, int64_t n, int D, double** beta, double*
 cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int n_leapfrog, double eps, uint64_t seed,
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
                              int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
-                             bool fused_leap, int* rc_out, const double* h_ladder, int n_rounds, double* d_cold) {
+                             bool fused_leap, int* rc_out, const double* h_ladder, int n_rounds, double* d_cold,
+                             int (*resident)(void*, const ResidentArgs*)) {
     HmcBuf b = hmc_views(d_state, n, D);
     b.out_theta = d_out_theta; b.out_lp = d_out_lp;
     const bool pt = h_ladder != nullptr;
@@ -197,11 +172,20 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
     }
     const HmcLeap at_state{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, b.beta, b.ll};
     for (int round = 0; round < n_rounds; ++round) {
+        const uint64_t round_seed = (uint64_t)(seed + 0x51ED27ULL * (uint64_t)round);
+        if (resident) {
+            // trajectory-resident kernel: (re-)evaluation at the current weights and all n_iter transitions in ONE launch
+            ResidentArgs R;
+            R.q = b.q; R.lp = b.lp; R.g = b.g; R.acc = b.acc; R.inv_mass = b.inv_mass; R.out_theta = b.out_theta; R.out_lp = b.out_lp;
+            R.beta = pt ? b.beta : nullptr; R.ll = pt ? b.ll : nullptr; R.n = n; R.chain_offset = 0; R.D = D; R.n_iter = n_iter;
+            R.n_leapfrog = n_leapfrog; R.it0 = 0; R.eps = eps; R.seed = round_seed;
+            if ((*rc_out = resident(user, &R))) return cudaSuccess;
+        } else {
         // (re-)evaluate the current states at the current weights
         if ((*rc_out = logpost(user, b.q, b.lp, b.g, pt ? &at_state : nullptr))) return cudaSuccess;
         for (int it = 0; it <= n_iter; ++it) {
             // transition counter `round * n_iter + it` keys the random stream; the sample store is per run, not per round
-            e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, (uint64_t)(seed + 0x51ED27ULL * (uint64_t)round));
+            e = launch_pdl(k_hmc_turn, n, st, b, n, D, it, n_iter, eps, round_seed);
             if (e != cudaSuccess) return e;
             if (it == n_iter) break;
             for (int l = 0; l < n_leapfrog; ++l) {
@@ -216,6 +200,7 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
                 e = launch_pdl(k_hmc_leap, n, st, b, n, D, last, eps);
                 if (e != cudaSuccess) return e;
             }
+        }
         }
         if (pt) {
             e = launch_pdl(k_pt_swap, (n + 1) / 2, st, b, n, D, (int64_t)round, seed, d_cold);

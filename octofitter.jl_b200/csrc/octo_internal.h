@@ -49,6 +49,7 @@ struct DevBlock {
     int32_t slot_margin;                      // first of the margin accumulators (kind 3) or -1
     int32_t slot_obsprior;                    // first of the 4 observable-prior accumulators (OP_*) or -1
     double wgt, cum;                          // relative cost of one epoch of this table; Σ n*wgt of the tables before it
+    double wgt_lat, cum_lat;                  // the same for latency-bound launches (cost = length of the dependent chain of one pair)
 };
 
 // HGCAInstantaneousObs (kind 5): a handful of rows evaluated by the last CTA of a chain group (octo_kernels.cu, hgca_tail)
@@ -68,6 +69,7 @@ struct DevModel {
     double kappa;            // 2π * year2day / kepler_year_days * au2m * sec2year  (K = kappa * sqrt(M/a) * sin i / s)
     double c2a_per_plx;      // rad2as*1e3 / (1000*pc2au): mas per AU per mas of parallax
     double wtot;             // Σ n*wgt over all tables: warps split this, not the raw epoch count
+    double wtot_lat;         // Σ n*wgt_lat
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
     int32_t has_margin, pad0;    // any marginalised-RV or observable-prior table (their epilogue fold needs an extra barrier)
@@ -104,6 +106,9 @@ struct DevParam {
     // entry = input index | role << 8 (role 0: the parameter itself, 1: x of a UniformCircular pair, 2: y, 3: both)
     int16_t gat_start[OCTO_PARAM_MAX + 1];
     int16_t gat[2 * OCTO_PARAM_MAX];
+    // evaluation orders of the fused stage, most expensive item first (warps take items round-robin, so the expensive
+    // ones land on different warps in the first round): priors (invlink + log density), input definitions, gathers
+    uint8_t order_prior[OCTO_PARAM_MAX], order_input[OCTO_PARAM_MAX], order_gather[OCTO_PARAM_MAX];
 };
 
 // Tiny batches (a single chain, as the reference's samplers call the model): the inputs travel inside the kernel
@@ -117,7 +122,26 @@ struct InlineIn { double v[OCTO_INLINE_MAX]; };
 // beta != nullptr: tempering — the likelihood part of chain c is scaled by beta[c] (log posterior = prior terms +
 // beta * ln_like, the path between Pigeons' prior-only reference and the target); ll_raw receives ln_like itself.
 struct HmcLeap { double* p; double* q; const double* inv_mass; double eps, kick; int drift, pad; const double* beta; double* ll_raw; };
-struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; };   // lat: the latency-tuned instantiation
+// lat: the latency-tuned instantiation.  ch: chains per CTA = 32 / sub-lanes (octo_kernels.cu, "SUB-LANES"); gx counts
+// groups of ch chains; slice = epochs per (warp, sub-lane) unit
+struct LaunchGeom { int gx, gy, block, slice; size_t smem; bool lat = false; int ch = 32; };
+
+// trajectory-resident explorer (octo_kernels.cu, k_hmc_resident): arrays are column-major [n x D], chain fastest
+struct ResidentArgs {
+    double *q, *lp, *g;              // in/out: current states; out: their log posterior and gradient
+    double* acc;                     // [n] accepted transitions, incremented
+    const double* inv_mass;          // [D]
+    double *out_theta, *out_lp;      // optional sample stores [.. x D x n], [.. x n], rows it0 .. it0 + n_iter - 1
+    const double* beta;              // [n] tempering weights or nullptr
+    double* ll;                      // [n] raw ln_like of the current states (tempering) or nullptr
+    int64_t n, chain_offset;         // chains in this launch; global index of chain 0 (keys the random streams)
+    int32_t D, n_iter, n_leapfrog, it0;
+    double eps;
+    uint64_t seed;
+};
+size_t octo_resident_smem_bytes(const DevModel& m, int D, int n_tperi);
+cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin);
+cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int n_tperi, const ResidentArgs& R, int ch, cudaStream_t st);
 
 // kernels (octo_kernels.cu)
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
@@ -142,7 +166,7 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
                              int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
                              bool fused_leap, int* rc_out, const double* h_ladder = nullptr, int n_rounds = 0,
-                             double* d_cold = nullptr);
+                             double* d_cold = nullptr, int (*resident)(void*, const ResidentArgs*) = nullptr);
 // after a tempered run: per-chain beta, rung of each chain, swap acceptance counts per adjacent pair (device pointers into the state)
 void octo_hmc_pt_views(double* d_state, int64_t n, int D, double** beta, double** ll, int32_t** rung_of_chain, double** swap_acc);
 

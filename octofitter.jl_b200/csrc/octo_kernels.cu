@@ -19,6 +19,7 @@
 //   epilogue  -> one lane per chain maps the raw sums to ∂ll/∂(inputs) by the chain rule, writes coalesced rows
 #include "octo_internal.h"
 #include "octo_param_dev.cuh"
+#include "octo_hmc_dev.cuh"
 #include <math_constants.h>
 #include <cstdio>
 
@@ -30,6 +31,9 @@ constexpr int WMAX = OCTO_WARPS;   // warps per CTA (models whose accumulator sl
 #endif
 #ifndef OCTO_UNROLL
 #define OCTO_UNROLL 1            // epochs in flight per warp in the lean loops
+#endif
+#ifndef OCTO_LAT_ILP
+#define OCTO_LAT_ILP 2           // pairs in flight per lane in the lean loops of the latency-tuned instantiation / resident kernel
 #endif
 #define OCTO_PRAGMA(x) _Pragma(#x)
 #define OCTO_UNROLL_LOOP(n) OCTO_PRAGMA(unroll n)
@@ -185,11 +189,16 @@ __device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double 
 // MODE 0: RA/Dec table with fixed weights (no jitter / platescale / northangle) — the common case
 // MODE 1: RA/Dec table with a sampled jitter (per-pair covariance), no platescale / northangle
 // MODE 2: everything else (PA/sep tables, platescale, northangle), decided at run time
-template <bool GRAD, int NPT, int MODE>
+// Lean tables: the loop is branch-free — lanes past the end of their range evaluate neutral records (zero weights: every
+// contribution is an exact zero) — and, for ILP > 1 (latency-tuned launches), unrolled so that the dependent chains of
+// ILP consecutive pairs overlap in one thread.  Same sums, same bits as a loop that skips those lanes.
+template <bool GRAD, int NPT, int MODE, int ILP>
 __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
-                                        double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
+                                        double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     const int ip = B.planet;
     constexpr bool LEAN = (MODE == 0);
+    constexpr bool PAD = LEAN;
+    constexpr int UNR = (PAD && ILP > 1) ? ILP : OCTO_UNROLL;
     const bool pasep = (MODE == 2) && (B.kind == OCTO_KIND_ASTROM_PASEP);
     const bool jitm = (MODE == 1) || (MODE == 2 && B.jit);
     // involved planets: the observed one, then interior companions with a mass (relative-astrometry.jl:117-133)
@@ -237,19 +246,28 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
     // Epoch records [t, y1 | c1, y2 | c2, c3] are staged through shared memory 32 at a time: one coalesced
     // read-only load per lane (three 16-byte words), then every iteration reads its record as a broadcast LDS —
     // no global-load latency inside the dependent chain.
+    // With sub-lanes (ch < 32 chains per warp) every group of ch lanes walks its own range [k0, k1) through its own
+    // window of ch records; the trip counts are made warp-uniform (lanes past their range idle).
     const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
-    for (int kb = k0; kb < k1; kb += 32) {
-    const int nrec = min(32, k1 - kb);
+    const int col = lane & (ch - 1), sbase = lane - col;
+    for (int kb = k0;; kb += ch) {
+    const int nrec = max(0, min(ch, k1 - kb));
+    const int nmax = __reduce_max_sync(0xffffffffu, nrec);
+    if (nmax == 0) break;
     __syncwarp();
-    if (lane < nrec) {
-        const double2* src = tab + 3 * (int64_t)(kb + lane);
+    if (col < nrec) {
+        const double2* src = tab + 3 * (int64_t)(kb + col);
         const double2 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
         stage[3 * lane] = a0; stage[3 * lane + 1] = a1; stage[3 * lane + 2] = a2;
+    } else if (PAD) {
+        const double2 z = make_double2(0.0, 0.0);
+        stage[3 * lane] = z; stage[3 * lane + 1] = z; stage[3 * lane + 2] = z;
     }
     __syncwarp();
-    OCTO_UNROLL_LOOP(OCTO_UNROLL)
-    for (int j = 0; j < nrec; ++j) {
-        const double2 ra0 = stage[3 * j], ra1 = stage[3 * j + 1], ra2 = stage[3 * j + 2];
+#pragma unroll (UNR)
+    for (int j = 0; j < nmax; ++j) {
+        if (!PAD && j >= nrec) continue;
+        const double2 ra0 = stage[3 * (sbase + j)], ra1 = stage[3 * (sbase + j) + 1], ra2 = stage[3 * (sbase + j) + 2];
         const double t = ra0.x, y1 = ra0.y, e1 = ra1.x, y2 = ra1.y, e2 = ra2.x, e3 = ra2.y;
         double sE[NPT], cE[NPT], dt[NPT];
         double ra = 0.0, dec = 0.0, Mred = 0.0;
@@ -384,11 +402,13 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 // Radial-velocity segment (kinds 2, 3, 4).
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT, bool MARGIN, bool JIT>
+template <bool GRAD, int NPT, bool MARGIN, bool JIT, int ILP>
 __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
-                                    double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane) {
+                                    double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
     constexpr bool margin = MARGIN;
+    constexpr bool PAD = !MARGIN;                     // see seg_astrom
+    constexpr int UNR = (PAD && ILP > 1) ? ILP : OCTO_UNROLL;
     int pj[NPT]; double f[NPT], dmu[NPT]; Orb orb[NPT]; double Pc[NPT], Ps[NPT];
     int ni = 0;
     if (star) {   // every planet, reflex of the star: -mu * radvel (rv-absolute.jl:145-154)
@@ -434,18 +454,26 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         for (int a = 0; a < 5; ++a) { L[u][a] = 0.0; if constexpr (MARGIN) V[u][a] = 0.0; }
 
     const double2* __restrict__ tab = reinterpret_cast<const double2*>(m.tab);
-    for (int kb = k0; kb < k1; kb += 32) {
-    const int nrec = min(32, k1 - kb);
+    const int col = lane & (ch - 1), sbase = lane - col;       // sub-lanes: see seg_astrom
+    for (int kb = k0;; kb += ch) {
+    const int nrec = max(0, min(ch, k1 - kb));
+    const int nmax = __reduce_max_sync(0xffffffffu, nrec);
+    if (nmax == 0) break;
     __syncwarp();
-    if (lane < nrec) {
-        const double2* src = tab + 3 * (int64_t)(kb + lane);
+    if (col < nrec) {
+        const double2* src = tab + 3 * (int64_t)(kb + col);
         const double2 a0 = __ldg(src), a1 = __ldg(src + 1);
         stage[3 * lane] = a0; stage[3 * lane + 1] = a1;
+    } else if (PAD) {
+        const double2 z = make_double2(0.0, 0.0);
+        stage[3 * lane] = z; stage[3 * lane + 1] = z;
     }
     __syncwarp();
-    OCTO_UNROLL_LOOP(OCTO_UNROLL)
-    for (int j = 0; j < nrec; ++j) {
-        const double2 ra0 = stage[3 * j], ra1 = stage[3 * j + 1];
+#pragma unroll (UNR)
+    for (int j = 0; j < nmax; ++j) {
+        if (!PAD && j >= nrec) continue;
+        const bool valid = !PAD || j < nrec;
+        const double2 ra0 = stage[3 * (sbase + j)], ra1 = stage[3 * (sbase + j) + 1];
         const double t = ra0.x, y = ra0.y, e1 = ra1.x;
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
         double model = off;
@@ -460,10 +488,10 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         double iv;
         if constexpr (!JIT) iv = e1;             // 1/σ² precomputed; normalisation is in const_ll
         else {
-            const double var = e1 + j2;
-            iv = rcp_nr(var);
+            const double var = valid ? e1 + j2 : 1.0;
+            iv = valid ? rcp_nr(var) : 0.0;
             if constexpr (MARGIN) mLG += log(kc.two_pi * var);
-            else ll = fma(kc.mhalf, kc.log2pi + log(var), ll);
+            else { const double lt = fma(kc.mhalf, kc.log2pi + log(var), ll); ll = valid ? lt : ll; }
         }
         const double riv = r * iv;
         double g;                                 // d ll / d model
@@ -560,8 +588,10 @@ __device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const doub
 }
 
 // returns validity of what the task looked at
+// skip_tp: the fused parameterisation derives tp (θ_at_epoch_to_tperi) on another warp at the same time and stores it
+// itself; the size / mass / time task then leaves tp alone
 __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
-                              double* sc, int lane) {
+                              double* sc, int lane, bool skip_tp = false) {
     const bool ti = m.any_ti && m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
         if (ti) {            // no angles: neutral values for the slots the Campbell code reads
@@ -592,7 +622,7 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     // division and square root (KepOrbit ctor + orbitsolve: n = 2π / (√(a³/M)·kyd / y2d), MA = n / y2d · (t - tp)):
     // its last bit is multiplied by |MA| (thousands of radians for short periods), so anything else would cost
     // parity digits in exactly the regime where the problem is already ill-conditioned.
-    double tp = in[c + (int64_t)m.idx_tp[p] * ld];
+    double tp = skip_tp ? 0.0 : in[c + (int64_t)m.idx_tp[p] * ld];
     double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
     double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
     double a = ti ? ti_semimajor(m, p, in, c, ld, plx, sc, lane) : in[c + (int64_t)m.idx_a[p] * ld];
@@ -606,7 +636,7 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     const double Moa = M * inv_a;
     const double c2a = plx * m.c2a_per_plx;                     // rad2as*1e3 / (1000/plx * pc2au)  [mas/AU]
     sc[PC_nd * 32 + lane] = __ddiv_rn(n_yr, m.c.year2day);      // [rad/day]
-    sc[PC_tp * 32 + lane] = tp;
+    if (!skip_tp) sc[PC_tp * 32 + lane] = tp;
     sc[PC_a * 32 + lane] = a;          sc[PC_inv_a * 32 + lane] = inv_a;
     sc[PC_M * 32 + lane] = M;          sc[PC_inv_M * 32 + lane] = inv_M;
     sc[PC_plx * 32 + lane] = plx;      sc[PC_c2a * 32 + lane] = c2a; sc[PC_sc * 32 + lane] = a * c2a;
@@ -934,22 +964,30 @@ __device__ __noinline__ void hgca_tail(const DevModel& m, const DevHg& H, const 
 #ifdef OCTO_TIMING
 #define PTICK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ptk[i] = (long long)t_; } } while (0)
 __device__ long long g_ptk[2][8];
+__device__ long long g_tm_last[13];
+__device__ long long g_wtk[16][12];
+__device__ int g_quiet;      // set by the resident kernel: phase timings are printed once, at the end of the run
 #else
 #define PTICK(i) do {} while (0)
 #endif
-struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *trig, *part, *lp, *extra, *beta; int* flags; };
+// trig: per θ_at_epoch_to_tperi definition 16 slots — sin, cos of (θ, i, ω, Ω), the mean anomaly, then the reciprocals and
+// roots of its forward pass (tperi_mid `keep`); cir: [2][n_in] what circ_forward saves for the reverse pass
+constexpr int TRIG_SLOTS = 16;
+struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *cir, *trig, *part, *lp, *extra, *beta; int* flags; };
 __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
     ParamSmem S;
     S.th = base; S.dxdy = S.th + D * 32; S.gth = S.dxdy + D * 32; S.L = S.gth + D * 32; S.aux = S.L + D * 32;
-    S.trig = S.aux + n_in * 32; S.part = S.trig + T * 9 * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
+    S.cir = S.aux + n_in * 32;
+    S.trig = S.cir + 2 * n_in * 32; S.part = S.trig + T * TRIG_SLOTS * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
     S.beta = S.extra + 32;
     S.flags = reinterpret_cast<int*>(S.beta + 32);
     return S;
 }
-__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + n_in + 17 * T + 4) * 32; }
+__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + 3 * n_in + (TRIG_SLOTS + 8) * T + 4) * 32; }
 
 __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
-                                           int64_t ld, double* s_in, const ParamSmem& S, int* s_ok, int w, int W, int lane) {
+                                           int64_t ld, double* s_in, double* s_const, const ParamSmem& S, int* s_ok, int w, int W,
+                                           int lane) {
     using namespace octo_param_dev;
     const int D = P.D, n_in = P.n_in, T = P.n_tperi;
 #ifdef OCTO_TIMING
@@ -958,7 +996,8 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
     PTICK(0);
     // invlink + logpdf_with_trans
 #pragma unroll 1
-    for (int j = w; j < D; j += W) {
+    for (int jj = w; jj < D; jj += W) {
+        const int j = P.order_prior[jj];                              // expensive families first: they share the first round
         const double y = theta_t[c + (int64_t)j * ld];
         const bool fin = isfinite(y);
         const PriorEval r = prior_eval(P.priors[j].family, P.priors[j].p[0], P.pc[j], fin ? y : 0.0);
@@ -970,86 +1009,118 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
     PTICK(1);
     // derived inputs that depend on parameters only (arr2nt)
 #pragma unroll 1
-    for (int k = w; k < n_in; k += W) {
+    for (int kk = w; kk < n_in; kk += W) {
+        const int k = P.order_input[kk];
         const OctoInputDef& d = P.defs[k];
         double v = 0.0, ext = 0.0;
         if (d.op == OCTO_IN_PARAM) v = S.th[d.a[0] * 32 + lane];
         else if (d.op == OCTO_IN_CONST) v = d.value;
-        else if (d.op == OCTO_IN_CIRC) circ_forward(S.th[d.a[0] * 32 + lane], S.th[d.a[1] * 32 + lane], d.value, v, ext);
+        else if (d.op == OCTO_IN_CIRC) circ_forward(S.th[d.a[0] * 32 + lane], S.th[d.a[1] * 32 + lane], d.value, v, ext,
+                                                    &S.cir[k * 32 + lane], &S.cir[(n_in + k) * 32 + lane]);
         s_in[k * 32 + lane] = v; S.aux[k * 32 + lane] = ext;
     }
     __syncthreads();
     PTICK(2);
-    // θ_at_epoch_to_tperi: trigonometry of (θ, i, ω, Ω) as (definition, angle) items, then one warp per definition
-    if (T > 0) {
+    // One phase for two independent things: the trigonometry of θ_at_epoch_to_tperi — (definition, angle) items for
+    // (θ, i, ω, Ω) — and phase 1 of K1's prologue (five tasks per planet; none of them needs tp).  Items over warps.
+    {
+        const int n_trig = 4 * T, n_item = n_trig + 5 * m.n_planets;
 #pragma unroll 1
-        for (int it = w; it < 4 * T; it += W) {
-            const int t = it >> 2, q = it & 3;
-            const OctoInputDef& d = P.defs[P.tperi_k[t]];
-            if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
-            double sn, cs;
-            p_sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
-            S.trig[(t * 9 + 2 * q) * 32 + lane] = sn; S.trig[(t * 9 + 2 * q + 1) * 32 + lane] = cs;
+        for (int it = w; it < n_item; it += W) {
+            if (it < n_trig) {
+                const int t = it >> 2, q = it & 3;
+                const OctoInputDef& d = P.defs[P.tperi_k[t]];
+                if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
+                double sn, cs;
+                p_sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
+                S.trig[(t * TRIG_SLOTS + 2 * q) * 32 + lane] = sn; S.trig[(t * TRIG_SLOTS + 2 * q + 1) * 32 + lane] = cs;
+            } else {
+                const int task = it - n_trig, p = task / 5, kind = task % 5;
+                bool derived_tp = false;                                 // this planet's tp is one of the tperi definitions
+                for (int t = 0; t < T; ++t) derived_tp = derived_tp || P.tperi_k[t] == m.idx_tp[p];
+                if (!prologue_task(m, p, kind, s_in, lane, 32, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
+            }
         }
-        __syncthreads();
-        PTICK(3);
+    }
+    __syncthreads();
+    PTICK(3);
+    // Second phase, again independent things on different warps: one warp per θ_at_epoch_to_tperi definition (it hands
+    // tp to the planets that use it), the prologue's products (they do not involve tp) on the next warps, the ordered
+    // prior sums on the last warp.
 #pragma unroll 1
-        for (int t = w; t < T; t += W) {
-            const int k = P.tperi_k[t];
+    for (int it = w; it < T + m.n_planets; it += W) {
+        if (it < T) {
+            const int t = it, k = P.tperi_k[t];
             const OctoInputDef& d = P.defs[k];
             const bool ti = d.op == OCTO_IN_TPERI_TI;
             double arg[8], trig[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
+            for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * TRIG_SLOTS + q) * 32 + lane];
             double MA;
-            s_in[k * 32 + lane] = tperi_value(m.c, d.value, arg, trig, &MA, ti);
-            S.trig[(t * 9 + 8) * 32 + lane] = MA;
+            const double tp = tperi_value(m.c, d.value, arg, trig, &MA, ti, S.trig + (t * TRIG_SLOTS + 9) * 32 + lane, 32);
+            s_in[k * 32 + lane] = tp;
+            S.trig[(t * TRIG_SLOTS + 8) * 32 + lane] = MA;
+#pragma unroll 1
+            for (int p = 0; p < m.n_planets; ++p) if (m.idx_tp[p] == k) {
+                const bool fin = isfinite(tp);
+                s_const[(p * PC_COUNT + PC_tp) * 32 + lane] = fin ? tp : 0.0;
+                if (!fin) s_ok[lane] = 0;
+            }
+        } else {
+            const int p = it - T;
+            prologue_products(s_const + p * PC_COUNT * 32, lane, m.any_ti && m.basis[p] == OCTO_BASIS_THIELE_INNES);
         }
-        __syncthreads();
     }
     PTICK(4);
-    // ordered sums, "healing" of a non-finite prior term (variables.jl:1229-1236), validity
-    if (w == W - 1) {                                                // the last warp has no prologue task on small models
+    // ordered sums, "healing" of a non-finite prior term (variables.jl:1229-1236), validity — on the last warp, next to
+    // the warps above (the derived tp inputs are checked by the warp that computes them); the caller's barrier follows
+    if (w == W - 1) {
         double lp, extra;
-        const int fl = prior_sums(S.L + lane, S.aux + lane, s_in + lane, D, n_in, 32, !(S.flags[lane] & 16), lp, extra);
+        const int fl = prior_sums(S.L + lane, S.aux + lane, s_in + lane, D, n_in, 32, !(S.flags[lane] & 16), lp, extra, &P);
         S.lp[lane] = lp; S.extra[lane] = extra; S.flags[lane] = fl;
         if (!(fl & 4)) s_ok[lane] = 0;                               // K1 then returns -Inf / zero gradient
     }
     PTICK(5);
 #ifdef OCTO_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && !g_quiet)
         printf("  forward ns: priors +%lld inputs +%lld trig +%lld tperi +%lld sums +%lld\n", ptk[1] - ptk[0], ptk[2] - ptk[1], ptk[3] - ptk[2], ptk[4] - ptk[3], ptk[5] - ptk[4]);
 #endif
 }
 
 // reverse stage: S.aux holds d ll / d inputs of the 32 chains; S.flags bit 3 = chain is ok (valid and ll finite)
+// the 7 (8) partial derivatives of θ_at_epoch_to_tperi definition t w.r.t. its arguments (hand-derived reverse pass)
+__device__ __noinline__ void param_tperi_partials(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
+                                                  int t, int lane) {
+    using namespace octo_param_dev;
+    const OctoInputDef& d = P.defs[P.tperi_k[t]];
+    const bool ti = d.op == OCTO_IN_TPERI_TI;
+    double arg[8], trig[8], part[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * TRIG_SLOTS + q) * 32 + lane];
+    part[7] = 0.0;
+    tperi_reverse(m.c, arg, trig, S.trig[(t * TRIG_SLOTS + 8) * 32 + lane], part, ti, S.trig + (t * TRIG_SLOTS + 9) * 32 + lane, 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) S.part[(t * 8 + q) * 32 + lane] = part[q];
+}
+
 __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
-                                            double* __restrict__ g_t, int64_t chain0, int64_t n_chains, int64_t ldg, int w,
-                                            int W, int lane, const HmcLeap& leap) {
+                                            double* __restrict__ g_t, int64_t chain0, bool active, int64_t ldg, int w,
+                                            int W, int lane, const HmcLeap& leap, bool partials_done) {
     using namespace octo_param_dev;
     const int D = P.D, T = P.n_tperi;
 #ifdef OCTO_TIMING
     long long* ptk = g_ptk[1];
 #endif
     PTICK(0);
-    // the 7 partial derivatives of every θ_at_epoch_to_tperi: one warp per definition (hand-derived reverse pass)
+    if (!partials_done) {              // one warp per definition
 #pragma unroll 1
-    for (int t = w; t < T; t += W) {
-        const OctoInputDef& d = P.defs[P.tperi_k[t]];
-        const bool ti = d.op == OCTO_IN_TPERI_TI;
-        double arg[8], trig[8], part[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * 9 + q) * 32 + lane];
-        part[7] = 0.0;
-        tperi_reverse(m.c, arg, trig, S.trig[(t * 9 + 8) * 32 + lane], part, ti);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) S.part[(t * 8 + q) * 32 + lane] = part[q];
+        for (int t = w; t < T; t += W) param_tperi_partials(P, m, s_in, S, t, lane);
+        __syncthreads();
     }
-    __syncthreads();
     PTICK(1);
     if (w == 0) {                                                    // fold the tperi partials into ∂ll/∂inputs, last definition first
 #pragma unroll 1
@@ -1067,10 +1138,11 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
     PTICK(3);
     {                                                                // every parameter gathers its inputs: one warp per parameter
         const int fl = S.flags[lane];
-        const bool ok = fl & 8, healed = fl & 2, active = chain0 + lane < n_chains;
+        const bool ok = fl & 8, healed = fl & 2;
 #pragma unroll 1
-        for (int j = w; j < D; j += W) {
-            const double g = param_gather(P, j, healed ? 0.0 : S.gth[j * 32 + lane], S.th + lane, S.aux + lane, 32);
+        for (int jj = w; jj < D; jj += W) {
+            const int j = P.order_gather[jj];
+            const double g = param_gather(P, j, healed ? 0.0 : S.gth[j * 32 + lane], S.th + lane, S.aux + lane, 32, S.cir + lane);
             const double gv = ok ? g * S.dxdy[j * 32 + lane] : 0.0;
             if (active) {
                 const int64_t at = chain0 + lane + (int64_t)j * ldg;
@@ -1085,41 +1157,64 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
     }
     PTICK(4);
 #ifdef OCTO_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0)
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !g_quiet)
         printf("  backward ns: tperi +%lld accumulate +%lld barrier +%lld stores +%lld\n", ptk[1] - ptk[0], ptk[2] - ptk[1], ptk[3] - ptk[2], ptk[4] - ptk[3]);
 #endif
 }
 
-template <bool GRAD, int NPT>
+template <bool GRAD, int NPT, int ILP>
 __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
-                                            int64_t ld, int lane) {
+                                            int64_t ld, int lane, int ch) {
     if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
         const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0 && B.slot_obsprior < 0;
-        if (plain && !B.jit) seg_astrom<GRAD, NPT, 0>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
-        else if (plain) seg_astrom<GRAD, NPT, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
-        else seg_astrom<GRAD, NPT, 2>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        if (plain && !B.jit) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else if (plain) seg_astrom<GRAD, NPT, 1, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else seg_astrom<GRAD, NPT, 2, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-        seg_rv<GRAD, NPT, true, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        seg_rv<GRAD, NPT, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else if (B.jit) {
-        seg_rv<GRAD, NPT, false, true>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        seg_rv<GRAD, NPT, false, true, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else {
-        seg_rv<GRAD, NPT, false, false>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane);
+        seg_rv<GRAD, NPT, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     }
 }
 
-// LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
-// single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
-template <bool GRAD, int NPT, bool LAT>
-__global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : OCTO_MIN_CTAS)
-k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
-              double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
-              unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
-              const double* __restrict__ pw_const, const HmcLeap leap, const __grid_constant__ InlineIn inl) {
-    extern __shared__ double smem[];
+// Everything one evaluation needs beyond the model.  The same body serves the one-shot kernel (k_kepler_like: one
+// CTA per chain group x epoch split, pointers into global memory) and the trajectory-resident explorer
+// (octo_resident.cuh: one CTA per chain group loops over leapfrogs, pointers into its own shared memory).
+struct EvalArgs {
+    const double* in;            // [n_chains x n_in] kernel inputs, or θ_t [n_chains x D] with a parameterisation
+    int64_t n_chains, ld;
+    double* ll_out; double* g_out; int64_t ldg;
+    double* partial; unsigned int* tickets;
+    const DevParam* P; int post_mode; const double* pw_const;
+    HmcLeap leap;
+    int ch;                      // chains per CTA: 32 / sub-lanes (see below)
+    int64_t chain0;              // first chain of this CTA
+    int group, gy, by;           // chain-group index (ticket / partial slot), epoch splits, this CTA's split
+    bool lat_weights;            // split the epoch list by the latency cost model (DevBlock::wgt_lat)
+};
+
+// SUB-LANES.  The classic mapping is lane = chain (ch = 32).  When a batch has too few chains to fill the SMs that way,
+// a warp takes ch = 32/S chains and S "sub-lanes" per chain, each sub-lane walking its own contiguous epoch range: the
+// epoch split happens inside the warp instead of across CTAs (no partials through L2, no ticket, no second combine) and
+// a chain group shrinks to ch chains, so S times as many CTAs exist.  All per-chain shared-memory arrays keep their
+// [slot][32] shape and are REPLICATED across sub-lanes (lane l serves chain l mod ch): prologue, epilogue and the
+// parameterisation stages run unchanged, computing S identical copies; only global reads (chain index) and writes
+// (sub-lane 0 only) know about it.  Accumulators are folded over sub-lanes in sub-lane order right after the fixed-order
+// sum over warps, so results stay run-to-run bit-reproducible.
+// returns false when this CTA was not the last of its chain group to arrive (it has nothing more to do)
+template <bool GRAD, int NPT, int ILP>
+__device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, double* smem, const double* inl_v) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
     const int n_acc = m.n_acc;
+    const int ch = A.ch, col_c = lane & (ch - 1);
+    const int64_t n_chains = A.n_chains, ld = A.ld, ldg = A.ldg;
+    const DevParam* P = A.P;
+    const int post_mode = A.post_mode;
+    const double* pw_const = A.pw_const;
     double* s_const = smem;                                   // [P][PC_COUNT][32]
     double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
     double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
@@ -1131,21 +1226,19 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 #ifdef OCTO_TIMING
     long long tm[12]; int tmi = 0;
 #define OCTO_TICK() do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tm[tmi++] = (long long)t_; } } while (0)
+    // per-warp cycle stamps (clock64 of this SM) at named points, printed by the resident kernel
+#define OCTO_WTICK(i) do { if (lane == 0 && w < 16 && A.group == 0) g_wtk[w][i] = clock64(); } while (0)
 #else
 #define OCTO_TICK() do {} while (0)
+#define OCTO_WTICK(i) do {} while (0)
 #endif
-#ifndef OCTO_NO_PDL
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
+    OCTO_WTICK(0);
     OCTO_TICK();
-#ifdef OCTO_EMPTY
-    if (n_chains > 0) { if (threadIdx.x == 0 && blockIdx.y == 0) ll_out[blockIdx.x] = 0.0; return; }   // launch-floor probe
-#endif
-    // columns of the shared-memory arrays = chains of this CTA
+    // columns of the shared-memory arrays = chains of this CTA, replicated over sub-lanes
     constexpr int ncol = 32;
-    const int64_t chain0 = (int64_t)blockIdx.x * ncol;
-    auto chain_of = [&](int col) { const int64_t cc = chain0 + col; return cc < n_chains ? cc : n_chains - 1; };
+    const int64_t chain0 = A.chain0;
+    auto chain_of = [&](int col) { const int64_t cc = chain0 + (col & (ch - 1)); return cc < n_chains ? cc : n_chains - 1; };
+    const bool active = lane < ch && chain0 + lane < n_chains;      // lanes that own a chain's global outputs
 
     if (threadIdx.x < 32) {
         s_ok[threadIdx.x] = 1;
@@ -1161,10 +1254,10 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     // ---- inputs of this CTA's chains into shared memory, with the finiteness check of logdensitymodel.jl:120-124;
     //      with a parameterisation `in` is θ_t and the inputs are derived here (param_forward)
     ParamSmem PS;
-    const double* inp = (post_mode & OCTO_MODE_INLINE) ? inl.v : in;       // tiny batches carry their inputs in the parameters
+    const double* inp = (post_mode & OCTO_MODE_INLINE) ? inl_v : A.in;       // tiny batches carry their inputs in the parameters
     if (P) {
         PS = param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi);
-        param_forward(*P, m, inp, chain_of(lane), ld, s_in, PS, s_ok, w, W, lane);
+        param_forward(*P, m, inp, chain_of(lane), ld, s_in, s_const, PS, s_ok, w, W, lane);      // includes K1's prologue
     } else {
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * m.n_in; it += W * 32) {
@@ -1174,86 +1267,104 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             if (!isfinite(v)) s_ok[col] = 0;
         }
     }
-    OCTO_TICK();
+    OCTO_TICK(); OCTO_WTICK(1);
     // ---- prologue phase 1: the per-planet tasks, spread over all threads as (column, task) items.  Without a
     //      parameterisation they read global memory themselves (no barrier between the staging loop and this one:
     //      the load latency overlaps the first, cold pass through the task code)
+    if (!P) {
 #pragma unroll 1
-    for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
-        const int col = it % ncol, task = it / ncol;
-        const bool ok = P ? prologue_task(m, task / 5, task % 5, s_in, col, 32, s_const + (task / 5) * PC_COUNT * 32, col)
-                          : prologue_task(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col);
-        if (!ok) s_ok[col] = 0;
+        for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
+            const int col = it % ncol, task = it / ncol;
+            if (!prologue_task(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col)) s_ok[col] = 0;
+        }
+        __syncthreads();
+        // ---- phase 2: Thiele-Innes / RV products
+#pragma unroll 1
+        for (int it = threadIdx.x; it < ncol * m.n_planets; it += W * 32)
+            prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.any_ti && m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
     }
     __syncthreads();
-    // ---- phase 2: Thiele-Innes / RV products
-#pragma unroll 1
-    for (int it = threadIdx.x; it < ncol * m.n_planets; it += W * 32)
-        prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.any_ti && m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
-    __syncthreads();
-    OCTO_TICK();
+    OCTO_TICK(); OCTO_WTICK(2);
 
     {
-        // ---- this warp's contiguous range of the concatenated epoch list
-        const int64_t U = (int64_t)gridDim.y * W, u = (int64_t)blockIdx.y * W + w;
+        // ---- this warp's contiguous range of the concatenated epoch list: unit u of U.  With sub-lanes, the part of
+        //      every table inside the warp's range is divided evenly among the S sub-lanes (a warp whose range crosses
+        //      a table boundary keeps all its sub-lanes busy in both tables)
+        const int S = 32 / ch, sub = lane / ch;
+        const int64_t U = (int64_t)A.gy * W, u = (int64_t)A.by * W + w;
         // contiguous range of the COST-weighted epoch list (an RV+jitter epoch costs ~1.8 lean astrometry epochs)
-        const double w_lo = m.wtot * (double)u / (double)U, w_hi = (u + 1 == U) ? 2.0 * m.wtot + 1.0 : m.wtot * (double)(u + 1) / (double)U;
+        // (latency-bound launches weigh a pair by its dependent chain instead of its instruction count)
+        const double wtot = A.lat_weights ? m.wtot_lat : m.wtot;
+        const double w_lo = wtot * (double)u / (double)U, w_hi = (u + 1 == U) ? 2.0 * wtot + 1.0 : wtot * (double)(u + 1) / (double)U;
 #pragma unroll 1
         for (int b = 0; b < m.n_blocks; ++b) {
             const DevBlock& B = m.blocks[b];
-            int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - B.cum) / B.wgt)));
-            int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - B.cum) / B.wgt, 2.0e9))));
-            if (pw_const) {      // pointwise mode: this CTA evaluates the single epoch blockIdx.y (warp 0)
-                const int ep = (int)blockIdx.y + (post_mode >> 9);          // + first epoch of this chunk (grid.y <= 65535)
+            const double bcum = A.lat_weights ? B.cum_lat : B.cum, bwgt = A.lat_weights ? B.wgt_lat : B.wgt;
+            int k0 = B.start + min(B.n, max(0, (int)ceil((w_lo - bcum) / bwgt)));
+            int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - bcum) / bwgt, 2.0e9))));
+            if (S > 1) {
+                const int len = max(0, k1 - k0), base = k0;
+                k0 = base + (int)(((int64_t)len * sub) / S);
+                k1 = base + (int)(((int64_t)len * (sub + 1)) / S);
+            }
+            if (pw_const) {      // pointwise mode (ch = 32): this CTA evaluates the single epoch `by` (warp 0)
+                const int ep = A.by + (post_mode >> 9);                     // + first epoch of this chunk (grid.y <= 65535)
                 const bool mine = w == 0 && ep >= B.start && ep < B.start + B.n;
                 k0 = mine ? ep : 0; k1 = mine ? ep + 1 : 0;
             }
-            if (k0 >= k1) continue;
-            run_segment<GRAD, NPT>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane);
+            if (!__any_sync(0xffffffffu, k0 < k1)) continue;
+            run_segment<GRAD, NPT, ILP>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane, ch);
         }
     }
+    OCTO_WTICK(3);
     __syncthreads();
-    OCTO_TICK();
+    OCTO_TICK(); OCTO_WTICK(4);
 
-    // ---- CTA reduction over the 8 warps, fixed order
+    // ---- CTA reduction over the warps, fixed order; then the fold over sub-lanes, in sub-lane order, replicated
 #pragma unroll 1
     for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) {
         double v = s_acc[idx];
 #pragma unroll 8
         for (int ww = 1; ww < W; ++ww) v += s_acc[ww * n_acc * 32 + idx];
+        if (ch < 32) {
+            double t = __shfl_sync(0xffffffffu, v, col_c);
+            for (int sl = ch; sl < 32; sl += ch) t += __shfl_sync(0xffffffffu, v, sl + col_c);
+            v = t;
+        }
         s_red[idx] = v;
     }
+    OCTO_WTICK(5);
     __syncthreads();
-    OCTO_TICK();
+    OCTO_TICK(); OCTO_WTICK(6);
 
     // ---- K2: combine the epoch splits of this chain group: partials through L2 + a ticket; the last CTA to
     //      arrive sums them in split order (run-to-run bit-reproducible)
-    if (gridDim.y > 1 && !pw_const) {
-        double* mine = partial + ((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * n_acc * 32;
+    if (A.gy > 1 && !pw_const) {
+        double* mine = A.partial + ((int64_t)A.group * A.gy + A.by) * n_acc * 32;
 #pragma unroll 2
         for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) mine[idx] = s_red[idx];
         __threadfence();
         __syncthreads();
         OCTO_TICK();
         if (threadIdx.x == 0) {
-            const unsigned int prev = atomicAdd(&tickets[blockIdx.x], 1u);
-            s_last = (prev == gridDim.y - 1);
-            if (s_last) tickets[blockIdx.x] = 0;      // ready for the next launch on this workspace
+            const unsigned int prev = atomicAdd(&A.tickets[A.group], 1u);
+            s_last = (prev == (unsigned)A.gy - 1);
+            if (s_last) A.tickets[A.group] = 0;      // ready for the next launch on this workspace
         }
         __syncthreads();
         OCTO_TICK();
 #ifdef OCTO_TIMING
-        if (!s_last && threadIdx.x == 0 && blockIdx.x == 0)
-            printf("cta(0,%d) ns: start %lld inputs +%lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld\n", blockIdx.y,
+        if (!s_last && threadIdx.x == 0 && A.group == 0)
+            printf("cta(0,%d) ns: start %lld inputs +%lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld\n", A.by,
                    tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[6] - tm[5]);
 #endif
-        if (!s_last) return;
+        if (!s_last) return false;
         __threadfence();
-        const double* base = partial + (int64_t)blockIdx.x * gridDim.y * n_acc * 32;
+        const double* base = A.partial + (int64_t)A.group * A.gy * n_acc * 32;
         // every load of this thread (two accumulator cells x up to 16 splits) is issued before the first add: one
         // L2 round trip instead of four; additions stay in split order => same bits every run
         const int64_t stride = (int64_t)n_acc * 32;
-        const int ncell = n_use * 32, gy = (int)gridDim.y;
+        const int ncell = n_use * 32, gy = A.gy;
 #pragma unroll 1
         for (int idx0 = threadIdx.x; idx0 < ncell; idx0 += 2 * W * 32) {
             const int idx1 = idx0 + W * 32;
@@ -1293,36 +1404,42 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         for (int idx = threadIdx.x; idx < EPI_PARTS * n_g * 32; idx += W * 32) s_gp[idx] = 0.0;
     }
     __syncthreads();
+    OCTO_WTICK(7);
     if (m.has_margin) {
         if (w == 0) epilogue_margin<GRAD>(m, s_const, s_red, s_gp, s_in, lane, 32, lane, pw_const != nullptr);
         __syncthreads();
     }
+    // the partial derivatives of every θ_at_epoch_to_tperi depend on forward quantities only: the warps that have no
+    // gradient part compute them now instead of after the epilogue (param_backward then only folds them in)
+    const bool tperi_early = GRAD && P && P->n_tperi > 0 && W >= EPI_PARTS + 1 + P->n_tperi;
     if (GRAD) {
 #pragma unroll 1
         for (int part = w; part < EPI_PARTS; part += W) epilogue_part(part, m, s_const, s_red, s_gp + part * n_g * 32, lane);
+        if (tperi_early && w >= EPI_PARTS && w < EPI_PARTS + P->n_tperi) param_tperi_partials(*P, m, s_in, PS, w - EPI_PARTS, lane);
     }
     if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
-        const bool active = chain0 + lane < n_chains;
-        const double cll = pw_const ? pw_const[blockIdx.y] : m.const_ll;
+        const double cll = pw_const ? pw_const[A.by] : m.const_ll;
         const double llv = s_ok[lane] ? s_red[lane] + cll : -CUDART_INF;
         if (!P) {
             // pointwise mode: out[chain + epoch * ldg] = ln_like of the model reduced to that one epoch
-            if (active) ll_out[chain0 + lane + (pw_const ? (int64_t)blockIdx.y * ldg : 0)] = llv;
+            if (active) A.ll_out[chain0 + lane + (pw_const ? (int64_t)A.by * ldg : 0)] = llv;
         } else {                                               // log posterior (logdensitymodel.jl:110-146)
             const int fl = PS.flags[lane];
             const bool ok = (fl & 4) && isfinite(llv);
             // tempering (octo_hmc.cu): the likelihood of chain c enters with weight beta[c]
-            const double bet = (leap.beta && active) ? leap.beta[chain0 + lane] : 1.0;
+            const double bet = A.leap.beta ? A.leap.beta[chain_of(lane)] : 1.0;
             PS.beta[lane] = bet;
-            if (leap.ll_raw && active) leap.ll_raw[chain0 + lane] = ok ? llv : -CUDART_INF;
+            if (A.leap.ll_raw && active) A.leap.ll_raw[chain0 + lane] = ok ? llv : -CUDART_INF;
             // post_mode 1: the likelihood part alone, ln_like(system, arr2nt(θ)) incl. the UnitLengthPrior terms
             const double like = PS.extra[lane] + bet * llv;
-            if (active) ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? (post_mode == 1 ? like : PS.lp[lane] + like) : -CUDART_INF);
+            if (active) A.ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? ((post_mode & 255) == 1 ? like : PS.lp[lane] + like) : -CUDART_INF);
             PS.flags[lane] = fl | (ok ? 8 : 0);
         }
     }
+    OCTO_WTICK(8);
     if (GRAD) {
         __syncthreads();
+        OCTO_WTICK(9);
         const int ng = n_g * 32;
         if (m.any_ti) {
             if (w == 0) epilogue_ti_distribute(m, s_const, s_gp, ng, lane);
@@ -1333,23 +1450,184 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
             const int l = idx & 31;
             const double v = ((s_gp[idx] + s_gp[ng + idx]) + s_gp[2 * ng + idx]) + s_gp[3 * ng + idx];
             if (P) PS.aux[idx] = (PS.flags[l] & 8) ? PS.beta[l] * v : 0.0;
-            else if (chain0 + l < n_chains) g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
+            else if (l < ch && chain0 + l < n_chains) A.g_out[chain0 + l + (int64_t)(idx >> 5) * ldg] = s_ok[l] ? v : 0.0;
         }
         if (P) {
             __syncthreads();
-            OCTO_TICK();
-            param_backward(*P, m, s_in, PS, g_out, chain0, n_chains, ldg, w, W, lane, leap);
+            OCTO_TICK(); OCTO_WTICK(10);
+            param_backward(*P, m, s_in, PS, A.g_out, chain0, active, ldg, w, W, lane, A.leap, tperi_early);
         }
     }
+    OCTO_WTICK(11);
+
 #ifdef OCTO_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (threadIdx.x == 0 && A.group == 0 && A.gy > 1) {
         OCTO_TICK();
         printf("cta(0,%d) LAST ns: start %lld inputs +%lld prologue +%lld segments +%lld reduce +%lld write+fence +%lld ticket +%lld reads +%lld epilogue +%lld (+%lld) end %lld\n",
-               blockIdx.y, tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4],
+               A.by, tm[0] % 100000000, tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4],
                tm[6] - tm[5], tm[7] - tm[6], tm[8] - tm[7], P && GRAD ? tm[9] - tm[8] : 0LL, tm[tmi - 1] % 100000000);
     }
 #endif
+#ifdef OCTO_TIMING
+    if (threadIdx.x == 0 && A.group == 0 && A.gy == 1) { OCTO_TICK(); for (int i = 0; i < tmi && i < 12; ++i) g_tm_last[i] = tm[i]; g_tm_last[12] = tmi; }
+#endif
+    return true;
 }
+
+// LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
+// single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
+template <bool GRAD, int NPT, bool LAT>
+__global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : OCTO_MIN_CTAS)
+k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
+              double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
+              unsigned int* __restrict__ tickets, const DevParam* __restrict__ P, int post_mode,
+              const double* __restrict__ pw_const, const HmcLeap leap, int ch, const __grid_constant__ InlineIn inl) {
+    extern __shared__ double smem[];
+#ifndef OCTO_NO_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+#ifdef OCTO_EMPTY
+    if (n_chains > 0) { if (threadIdx.x == 0 && blockIdx.y == 0) ll_out[blockIdx.x] = 0.0; return; }   // launch-floor probe
+#endif
+    EvalArgs A;
+    A.in = in; A.n_chains = n_chains; A.ld = ld; A.ll_out = ll_out; A.g_out = g_out; A.ldg = ldg;
+    A.partial = partial; A.tickets = tickets; A.P = P; A.post_mode = post_mode; A.pw_const = pw_const; A.leap = leap;
+    A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
+    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : 1>(m, A, smem, inl.v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trajectory-resident HMC explorer (the loop of src/sampling.jl:412-423, batched).  Chain groups are
+// independent, so ONE CTA keeps the state of its ch chains (position, momentum, gradient, proposal) in shared memory
+// and runs n_iter transitions x n_leapfrog leapfrogs inside one launch, calling the same evaluation body as the
+// one-shot kernel on shared-memory pointers (the fused parameterisation applies the kick and the drift itself).  No
+// launch, no L2 round trip and no cold instruction fetch per leapfrog.  The epoch split of a chain group happens
+// inside the warps (sub-lanes), never across CTAs.  Same per-coordinate arithmetic as k_hmc_turn (octo_hmc_dev.cuh),
+// same summation orders as a one-shot launch of the same geometry: both explorers give identical bits.
+// ---------------------------------------------------------------------------------------------
+template <int NPT>
+__global__ void __launch_bounds__(OCTO_LAT_WARPS * 32, 1)
+k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ P, const ResidentArgs R, int ch, int eval_doubles) {
+    using namespace octo_hmc_dev;
+    extern __shared__ double smem[];
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int D = R.D, tid = threadIdx.x, nthr = blockDim.x;
+#ifdef OCTO_TIMING
+    g_quiet = 1;
+#endif
+    // state behind the evaluation body's own shared memory, [j][32] like everything else
+    double* s_q = smem + eval_doubles;
+    double* s_g = s_q + D * 32;
+    double* s_qp = s_g + D * 32;
+    double* s_gp = s_qp + D * 32;
+    double* s_p = s_gp + D * 32;
+    double* s_kin = s_p + D * 32;            // per-coordinate kinetic terms, summed per chain in coordinate order
+    double* s_lp = s_kin + D * 32;
+    double* s_lpp = s_lp + 32;
+    double* s_h0 = s_lpp + 32;
+    double* s_ll = s_h0 + 32;
+    double* s_llp = s_ll + 32;
+    double* s_beta = s_llp + 32;
+    double* s_acc = s_beta + 32;
+    double* s_im = s_acc + 32;               // [D]
+    const int64_t chain0 = (int64_t)blockIdx.x * ch;
+    const int nvalid = (int)min((int64_t)ch, R.n - chain0);
+    const bool tempered = R.beta != nullptr;
+    for (int it = tid; it < D * 32; it += nthr) {
+        const int col = it & 31, j = it >> 5;
+        s_q[it] = col < nvalid ? R.q[chain0 + col + (int64_t)j * R.n] : 0.0;
+    }
+    if (tid < D) s_im[tid] = R.inv_mass[tid];
+    if (tid < 32) {
+        s_beta[tid] = (tempered && tid < nvalid) ? R.beta[chain0 + tid] : 1.0;
+        s_acc[tid] = 0.0; s_ll[tid] = 0.0; s_llp[tid] = 0.0;
+    }
+    __syncthreads();
+
+    EvalArgs A;
+    A.n_chains = nvalid; A.ld = 32; A.ldg = 32; A.partial = nullptr; A.tickets = nullptr; A.P = P; A.post_mode = 0;
+    A.pw_const = nullptr; A.ch = ch; A.chain0 = 0; A.group = blockIdx.x; A.gy = 1; A.by = 0; A.lat_weights = true;
+    // fresh momentum, first half kick and drift: one (chain, coordinate) item per thread
+    auto start_transition = [&](int it) {
+        const uint64_t key = hmc_key(R.seed, (uint64_t)it);
+        for (int item = tid; item < D * 32; item += nthr) {
+            const int col = item & 31, j = item >> 5;
+            if (col >= nvalid) continue;
+            const HmcStart r = hmc_start(key, (uint64_t)(R.chain_offset + chain0 + col), j, s_im[j], R.eps, s_g[item], s_q[item]);
+            s_kin[item] = r.kin; s_p[item] = r.p; s_qp[item] = r.q;
+        }
+        __syncthreads();
+        if (tid < nvalid) {
+            double kin = 0.0;
+            for (int j = 0; j < D; ++j) kin = __dadd_rn(kin, s_kin[j * 32 + tid]);
+            s_h0[tid] = hmc_h0(s_lp[tid], kin);
+        }
+    };
+    // Metropolis step, sample store
+    auto finish_transition = [&](int it) {
+        if (tid < nvalid) {
+            double kin = 0.0;
+            for (int j = 0; j < D; ++j) kin = __dadd_rn(kin, hmc_kin(s_p[j * 32 + tid], s_im[j]));
+            const double lpp = s_lpp[tid];
+            const int64_t c = chain0 + tid;
+            if (hmc_accept(R.seed, it, (uint64_t)(R.chain_offset + c), D, s_h0[tid], lpp, kin)) {
+                for (int j = 0; j < D; ++j) { s_q[j * 32 + tid] = s_qp[j * 32 + tid]; s_g[j * 32 + tid] = s_gp[j * 32 + tid]; }
+                s_lp[tid] = lpp; s_acc[tid] += 1.0; s_ll[tid] = s_llp[tid];
+            }
+            if (R.out_lp) R.out_lp[(int64_t)(R.it0 + it) * R.n + c] = s_lp[tid];
+            if (R.out_theta) for (int j = 0; j < D; ++j) R.out_theta[((int64_t)(R.it0 + it) * D + j) * R.n + c] = s_q[j * 32 + tid];
+        }
+        __syncthreads();
+    };
+    // one call site of the evaluation body for every evaluation of the run (it = -1: the current states at the current
+    // weights, then the leapfrogs of every transition): its code is fetched once and stays in the instruction cache
+    for (int it = -1, l = 0;;) {
+        if (it < 0) {
+            A.in = s_q; A.ll_out = s_lp; A.g_out = s_g;
+            A.leap = HmcLeap{nullptr, nullptr, nullptr, 0.0, 0.0, 0, 0, tempered ? s_beta : nullptr, tempered ? s_ll : nullptr};
+        } else {
+            const bool last = l == R.n_leapfrog - 1;
+            A.in = s_qp; A.ll_out = s_lpp; A.g_out = s_gp;
+            A.leap = HmcLeap{s_p, s_qp, s_im, R.eps, last ? 0.5 * R.eps : R.eps, last ? 0 : 1, 0, tempered ? s_beta : nullptr, tempered ? s_llp : nullptr};
+        }
+        eval_cta<true, NPT, OCTO_LAT_ILP>(m, A, smem, nullptr);
+        __syncthreads();
+#ifdef OCTO_TIMING
+        if (blockIdx.x == 0 && tid == 0 && it == R.n_iter - 1 && l == R.n_leapfrog - 1) {
+            printf("resident eval ns:");
+            for (int i = 1; i < (int)g_tm_last[12]; ++i) printf(" +%lld", g_tm_last[i] - g_tm_last[i - 1]);
+            printf("  (forward, prologue, segments, reduce, [hgca], epilogue, backward)\n");
+            printf("  forward ns: priors +%lld inputs +%lld trig +%lld tperi +%lld sums +%lld\n", g_ptk[0][1] - g_ptk[0][0], g_ptk[0][2] - g_ptk[0][1], g_ptk[0][3] - g_ptk[0][2], g_ptk[0][4] - g_ptk[0][3], g_ptk[0][5] - g_ptk[0][4]);
+            printf("  backward ns: tperi +%lld accumulate +%lld barrier +%lld stores +%lld\n", g_ptk[1][1] - g_ptk[1][0], g_ptk[1][2] - g_ptk[1][1], g_ptk[1][3] - g_ptk[1][2], g_ptk[1][4] - g_ptk[1][3]);
+            printf("  per-warp cycles since warp 0's start: forward-done prologue-done segments-done barrier reduce-done barrier epilogue-start epilogue-done barrier backward-start end\n");
+            for (int ww = 0; ww < (int)(blockDim.x >> 5) && ww < 16; ++ww) {
+                printf("   warp %2d:", ww);
+                for (int i = 0; i < 12; ++i) printf(" %6lld", g_wtk[ww][i] - g_wtk[0][0]);
+                printf("\n");
+            }
+        }
+#endif
+        if (it >= 0 && ++l < R.n_leapfrog) continue;
+        if (it >= 0) finish_transition(it);
+        if (++it >= R.n_iter) break;
+        start_transition(it);
+        l = 0;
+    }
+    for (int item = tid; item < D * 32; item += nthr) {
+        const int col = item & 31, j = item >> 5;
+        if (col >= nvalid) continue;
+        R.q[chain0 + col + (int64_t)j * R.n] = s_q[item];
+        R.g[chain0 + col + (int64_t)j * R.n] = s_g[item];
+    }
+    if (tid < nvalid) {
+        R.lp[chain0 + tid] = s_lp[tid];
+        R.acc[chain0 + tid] += s_acc[tid];
+        if (R.ll) R.ll[chain0 + tid] = s_ll[tid];
+    }
+}
+
 
 __global__ void k_selftest_kepler(const double* __restrict__ MA, const double* __restrict__ e, int64_t n,
                                   double* __restrict__ sE, double* __restrict__ cE) {
@@ -1397,7 +1675,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 #endif
     static const InlineIn none{};
     return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
-                              inl ? (post_mode | OCTO_MODE_INLINE) : post_mode, d_pw_const, leap, inl ? *inl : none);
+                              inl ? (post_mode | OCTO_MODE_INLINE) : post_mode, d_pw_const, leap, g.ch, inl ? *inl : none);
 }
 
 // opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
@@ -1434,4 +1712,29 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
     OCTO_DISPATCH(4);
 #undef OCTO_DISPATCH
 #undef OCTO_ARGS
+}
+
+// ---- trajectory-resident explorer
+size_t octo_resident_smem_bytes(const DevModel& m, int D, int T) {
+    return octo_smem_bytes(m, OCTO_LAT_WARPS, D, T) + ((size_t)(6 * D + 7) * 32 + (size_t)D) * sizeof(double);
+}
+cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin) {
+    cudaError_t e = cudaFuncSetAttribute(k_hmc_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    return e;
+}
+cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int T, const ResidentArgs& R, int ch, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    const size_t eval_bytes = octo_smem_bytes(m, OCTO_LAT_WARPS, R.D, T);
+    cfg.gridDim = dim3((unsigned)((R.n + ch - 1) / ch)); cfg.blockDim = dim3(OCTO_LAT_WARPS * 32);
+    cfg.dynamicSmemBytes = octo_resident_smem_bytes(m, R.D, T); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int eval_doubles = (int)((eval_bytes + 7) / 8);
+    if (m.n_planets == 1) return cudaLaunchKernelEx(&cfg, k_hmc_resident<1>, m, d_param, R, ch, eval_doubles);
+    if (m.n_planets == 2) return cudaLaunchKernelEx(&cfg, k_hmc_resident<2>, m, d_param, R, ch, eval_doubles);
+    return cudaLaunchKernelEx(&cfg, k_hmc_resident<4>, m, d_param, R, ch, eval_doubles);
 }

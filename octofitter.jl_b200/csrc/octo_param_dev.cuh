@@ -70,38 +70,53 @@ static __device__ __noinline__ PriorEval prior_eval(int family, double mu, const
 
 // UniformCircular (src/variables.jl:279-299): angle = atan(y, x) / 2π · domain, plus the UnitLengthPrior term
 // LogNormal(0, 0.1) on √(x² + y²) (src/variables.jl:301-323)
-__device__ __forceinline__ void circ_forward(double x, double y, double domain, double& v, double& ext) {
+// Also hands out what the reverse pass needs of r² = x² + y² (its reciprocal and d(UnitLengthPrior)/d log r), so that
+// the fused stage does not evaluate the logarithm and the division a second time per parameter of the pair.
+__device__ __forceinline__ void circ_forward(double x, double y, double domain, double& v, double& ext, double* ir2_out = nullptr,
+                                             double* dfdlr_out = nullptr) {
     v = p_atan2(y, x) * (domain / kTwoPi);
-    const double lr = 0.5 * p_log(x * x + y * y);
+    const double r2 = x * x + y * y, l2 = p_log(r2);
+    const double lr = 0.5 * l2;
     ext = -lr - (-2.302585092994045684 /* log 0.1 */) - kHalfLog2Pi - lr * lr * 50.0;
+    if (ir2_out) { *ir2_out = 1.0 / r2; *dfdlr_out = -1.0 - 0.5 * l2 * 100.0; }
 }
 // gk = ∂/∂angle; returns the contributions to ∂/∂x and ∂/∂y (angle and UnitLengthPrior)
-__device__ __forceinline__ void circ_backward(double x, double y, double domain, double gk, double& gx, double& gy) {
-    const double r2 = x * x + y * y, ir2 = 1.0 / r2, sc = gk * (domain / kTwoPi);
-    const double dfdlr = -1.0 - 0.5 * p_log(r2) * 100.0;
+__device__ __forceinline__ void circ_backward_pre(double x, double y, double domain, double gk, double ir2, double dfdlr,
+                                                  double& gx, double& gy) {
+    const double sc = gk * (domain / kTwoPi);
     gx = (dfdlr * x - sc * y) * ir2;
     gy = (dfdlr * y + sc * x) * ir2;
+}
+__device__ __forceinline__ void circ_backward(double x, double y, double domain, double gk, double& gx, double& gy) {
+    const double r2 = x * x + y * y;
+    circ_backward_pre(x, y, domain, gk, 1.0 / r2, -1.0 - 0.5 * p_log(r2) * 100.0, gx, gy);
 }
 
 // ordered sum of the prior terms with the reference's "healing" of a non-finite term (variables.jl:1229-1236: the
 // sum stops at the first non-finite term and becomes -floatmax), the UnitLengthPrior terms, validity of the inputs.
 // flags: 1 = every θ_t finite, 2 = healed, 4 = valid.  `stride` = distance between consecutive entries.
+// skip_derived: the θ_at_epoch_to_tperi inputs are still being computed (by another warp, which checks them itself)
 __device__ __forceinline__ int prior_sums(const double* L, const double* aux, const double* in, int D, int n_in, int stride,
-                                          bool finite_in, double& lp, double& extra) {
+                                          bool finite_in, double& lp, double& extra, const DevParam* skip_derived = nullptr) {
     double sum = 0.0, ex = 0.0;
     bool bad = false, valid = true;
 #pragma unroll 4
     for (int j = 0; j < D; ++j) { const double v = L[j * stride]; bad = bad || !isfinite(v); sum += v; }
 #pragma unroll 4
-    for (int k = 0; k < n_in; ++k) { ex += aux[k * stride]; valid = valid && isfinite(in[k * stride]); }
+    for (int k = 0; k < n_in; ++k) {
+        ex += aux[k * stride];
+        const bool derived = skip_derived && (skip_derived->defs[k].op == OCTO_IN_TPERI || skip_derived->defs[k].op == OCTO_IN_TPERI_TI);
+        valid = valid && (derived || isfinite(in[k * stride]));
+    }
     lp = bad ? -DBL_MAX : sum; extra = ex;
     return (finite_in ? 1 : 0) | (bad ? 2 : 0) | ((valid && finite_in) ? 4 : 0);
 }
 
 // d lp / dθ_j before the invlink factor: the prior term (0 when healed) plus, last input first, every input that
 // reads parameter j (DevParam::gat).  aux = ∂ll/∂inputs after the θ_at_epoch_to_tperi contributions were folded in.
+// cir != nullptr: [2][n_in] (1/r², d prior/d log r) of the UniformCircular inputs, saved by the forward stage
 __device__ __forceinline__ double param_gather(const DevParam& P, int j, double g0, const double* th, const double* aux,
-                                               int stride) {
+                                               int stride, const double* cir = nullptr) {
     double g = g0;
 #pragma unroll 1
     for (int it = P.gat_start[j]; it < P.gat_start[j + 1]; ++it) {
@@ -110,7 +125,9 @@ __device__ __forceinline__ double param_gather(const DevParam& P, int j, double 
         else {
             const OctoInputDef& d = P.defs[k];
             double gx, gy;
-            circ_backward(th[d.a[0] * stride], th[d.a[1] * stride], d.value, aux[k * stride], gx, gy);
+            if (cir) circ_backward_pre(th[d.a[0] * stride], th[d.a[1] * stride], d.value, aux[k * stride], cir[k * stride],
+                                       cir[(P.n_in + k) * stride], gx, gy);
+            else circ_backward(th[d.a[0] * stride], th[d.a[1] * stride], d.value, aux[k * stride], gx, gy);
             if (role & 1) g += gx;
             if (role & 2) g += gy;
         }
@@ -125,14 +142,18 @@ __device__ __forceinline__ double param_gather(const DevParam& P, int j, double 
 //   sin/cos of the true anomaly come from (xr, yr) / r instead of sincos(atan2(yr, xr)).  Returns tp and the mean
 //   anomaly MA (the one transcendental the reverse pass needs).
 struct TperiMid { double A, B, F, G, idet, xr, yr, ir, snu, cnu, s, u, v, iw2, q, p, a, tu, tv, tw, alpha; };
-__device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const double* arg, const double* trig, bool ti) {
+// keep / reuse: the reciprocals and roots (7 values per lane, stride `ks` apart): the forward pass of the fused stage
+// stores them, its reverse pass reads them back instead of evaluating the divisions and square roots again
+__device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const double* arg, const double* trig, bool ti,
+                                              double* keep = nullptr, const double* reuse = nullptr, int ks = 0) {
     const double st = trig[0], ct = trig[1];
     const double M = arg[1], e = arg[2];
     TperiMid m;
     if (ti) {
         m.A = arg[4]; m.B = arg[5]; m.F = arg[6]; m.G = arg[7];
         m.tu = 0.5 * (m.A * m.A + m.B * m.B + m.F * m.F + m.G * m.G); m.tv = m.A * m.G - m.B * m.F;
-        m.tw = sqrt((m.tu + m.tv) * (m.tu - m.tv)); m.alpha = sqrt(m.tu + m.tw);
+        if (reuse) { m.tw = reuse[5 * ks]; m.alpha = reuse[6 * ks]; }
+        else { m.tw = sqrt((m.tu + m.tv) * (m.tu - m.tv)); m.alpha = sqrt(m.tu + m.tw); }
         m.a = m.alpha / arg[3];
     } else {
         const double ci = trig[3], sw = trig[4], cw = trig[5], sW = trig[6], cW = trig[7];
@@ -140,20 +161,24 @@ __device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const doub
         m.F = -(cW * sw) - sW * cw * ci; m.G = -(sW * sw) + cW * cw * ci;
         m.a = arg[3]; m.tu = m.tv = m.tw = m.alpha = 0.0;
     }
-    m.idet = 1.0 / (m.A * m.G - m.F * m.B);
+    m.idet = reuse ? reuse[0] : 1.0 / (m.A * m.G - m.F * m.B);
     m.xr = (m.G * ct - m.F * st) * m.idet; m.yr = (m.A * st - m.B * ct) * m.idet;
-    m.ir = rsqrt(m.xr * m.xr + m.yr * m.yr);
+    m.ir = reuse ? reuse[ks] : rsqrt(m.xr * m.xr + m.yr * m.yr);
     m.snu = m.yr * m.ir; m.cnu = m.xr * m.ir;
-    m.s = sqrt(1.0 - e * e);
+    m.s = reuse ? reuse[2 * ks] : sqrt(1.0 - e * e);
     m.u = -(m.s * m.snu); m.v = -e - m.cnu;
-    m.iw2 = 1.0 / (e * m.cnu + 1.0);
+    m.iw2 = reuse ? reuse[3 * ks] : 1.0 / (e * m.cnu + 1.0);
     m.q = e * m.s * m.snu * m.iw2;
-    m.p = sqrt(m.a * m.a * m.a / M) * (c.kepler_year_days / c.year2day);      // period [yr]
+    m.p = reuse ? reuse[4 * ks] : sqrt(m.a * m.a * m.a / M) * (c.kepler_year_days / c.year2day);      // period [yr]
+    if (keep) {
+        keep[0] = m.idet; keep[ks] = m.ir; keep[2 * ks] = m.s; keep[3 * ks] = m.iw2; keep[4 * ks] = m.p;
+        keep[5 * ks] = m.tw; keep[6 * ks] = m.alpha;
+    }
     return m;
 }
 static __device__ __noinline__ double tperi_value(const OctoConstants& c, double t_ref, const double* arg, const double* trig,
-                                              double* MA_out, bool ti) {
-    const TperiMid m = tperi_mid(c, arg, trig, ti);
+                                              double* MA_out, bool ti, double* keep = nullptr, int ks = 0) {
+    const TperiMid m = tperi_mid(c, arg, trig, ti, keep, nullptr, ks);
     const double MA = p_atan2(m.u, m.v) + kPi - m.q;
     *MA_out = MA;
     // n = 2π / period_yrs;  tp = t_ref - MA / n * year2day
@@ -163,10 +188,10 @@ static __device__ __noinline__ double tperi_value(const OctoConstants& c, double
 // (the forward intermediates are recomputed, MA comes from the forward pass); this replaced forward-mode dual
 // evaluations whose code size made the once-per-CTA reverse stage instruction-fetch bound.
 static __device__ __noinline__ void tperi_reverse(const OctoConstants& c, const double* arg, const double* trig, double MA,
-                                              double* grad, bool ti) {
+                                              double* grad, bool ti, const double* reuse = nullptr, int ks = 0) {
     const double st = trig[0], ct = trig[1];
     const double M = arg[1], e = arg[2];
-    const TperiMid m = tperi_mid(c, arg, trig, ti);
+    const TperiMid m = tperi_mid(c, arg, trig, ti, nullptr, reuse, ks);
     const double cc = c.year2day / kTwoPi;
     const double MAb = -m.p * cc, pb = -MA * cc;                 // tp = t_ref - MA p cc
     const double g_a = pb * 1.5 * m.p / m.a, g_M = -pb * 0.5 * m.p / M;

@@ -5,6 +5,7 @@
 // octo_create fails.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -67,6 +68,9 @@ struct OctoCtx {
     int warps = OCTO_WARPS;        // warps per CTA; halved until the model's accumulator slots fit in shared memory
     int slice_override = 0;
     int latency_mode = 1;          // OCTO_B200_LATENCY: 0 never, 1 automatic, 2 whenever the chain groups fit one per SM
+    int resident_mode = 1;         // OCTO_B200_RESIDENT: 0 = explorers never use the trajectory-resident kernel
+    int force[3] = {0, 0, 0};      // OCTO_B200_FORCE (experiments): sub-lanes, latency instantiation, epoch splits
+    int sublane_mode = 0;          // OCTO_B200_SUBLANES: 0 automatic, 1 never (lane = chain), 2..32 that many sub-lanes per chain
     // device-side parameterisation (N1)
     DevParam* d_param = nullptr;
     int param_D = 0, param_T = 0;
@@ -169,7 +173,8 @@ void free_ws(Workspace* w) {
 // grid: chain groups x epoch splits.  Small problems: as many splits as fill the resident CTA slots exactly once
 // (an integral number of waves, never below min_slice epochs per warp).  Large problems (>= 4 waves): ~32 epochs
 // per warp so the per-CTA prologue/epilogue is amortised and the hardware CTA scheduler balances the tail.
-LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
+// This is the lane = chain mapping on its own (ch = 32); geometry() below adds the sub-lane mapping for small batches.
+LaunchGeom geometry_classic(const OctoCtx* ctx, int64_t n_chains, bool fused) {
     LaunchGeom g;
     const int W = fused ? ctx->warps_fused : ctx->warps;
     g.block = W * 32;
@@ -229,12 +234,87 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false) {
     return g;
 }
 
+// Small batches (the chain groups of the classic mapping would leave SMs idle, or need the cross-CTA combine to fill
+// them): candidates (sub-lanes S, instantiation, epoch splits) whose grid is a single wave, ranked by a two-term cost
+// model measured on C2's timeline — dependent pair evaluations per (warp, sub-lane) unit x ~0.55 us, + ~3.5 us when
+// the splits of a chain group have to be combined through L2.  Larger batches keep the classic geometry.
+// sub_override: 0 = automatic, otherwise the sub-lane count to use (1 = classic mapping).
+LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, int sub_override = 0) {
+    if (sub_override == 0) sub_override = ctx->sublane_mode;
+    LaunchGeom best = geometry_classic(ctx, n_chains, fused);
+    const int64_t E = ctx->m.n_epochs;
+    const int W = fused ? ctx->warps_fused : ctx->warps;
+    const int64_t resident = (int64_t)ctx->n_sm * (fused ? ctx->ctas_per_sm_fused : ctx->ctas_per_sm);
+    const int D = fused ? ctx->param_D : 0, T = fused ? ctx->param_T : 0;
+    int Wl = (W == OCTO_WARPS) ? OCTO_LAT_WARPS : W;
+    if (octo_smem_bytes(ctx->m, Wl, D, T) > ctx->smem_optin) Wl = W;
+    if (ctx->force[0] > 0 && sub_override != 1 && E > 0) {       // experiments: OCTO_B200_FORCE="sub-lanes,latency,splits"
+        const int S = ctx->force[0], Wc = ctx->force[1] ? Wl : W;
+        best.ch = 32 / S; best.gx = (int)((n_chains + best.ch - 1) / best.ch); best.gy = ctx->force[2] > 0 ? ctx->force[2] : 1;
+        best.lat = ctx->force[1] != 0; best.block = Wc * 32;
+        best.smem = best.lat ? octo_smem_bytes(ctx->m, Wc, D, T) : (fused ? ctx->smem_fused : ctx->smem);
+        best.slice = (int)((E + (int64_t)best.gy * Wc * S - 1) / ((int64_t)best.gy * Wc * S));
+        return best;
+    }
+    if (sub_override == 1 || E < 1 || (sub_override == 0 && (n_chains + 31) / 32 >= resident)) return best;
+    // measured on C2 / C3 / C4 / 4096 x {10, 100, 316} (profiles/r02_geometry_sweep.txt): a lean-astrometry-equivalent
+    // pair costs a lane of the latency-tuned instantiation ~0.32 us (two pairs in flight), ~0.8 us in the throughput
+    // instantiation when two CTAs share the SM, which also has ~3 us more fixed cost per launch; the combine through L2
+    // costs ~3.5 us
+    const double t_it[2] = {0.80, 0.32}, t_k2 = 3.5, t_thr = 3.0;
+    const double ew[2] = {ctx->m.wtot > 0 ? ctx->m.wtot : 1.0, ctx->m.wtot_lat > 0 ? ctx->m.wtot_lat : 1.0};
+    auto cost = [&](int S, bool lat, int64_t gy) {
+        const int Wc = lat ? Wl : W;
+        return std::ceil(ew[lat ? 1 : 0] / (double)(gy * Wc * S)) * t_it[lat ? 1 : 0] + (gy > 1 ? t_k2 + 0.02 * (double)gy : 0.0) + (lat ? 0.0 : t_thr);
+    };
+    // the classic choice, priced by the same model (multi-wave grids pay per wave)
+    double best_cost;
+    {
+        const int64_t slots = best.lat ? ctx->n_sm : resident;
+        const double waves = std::ceil((double)best.gx * best.gy / (double)slots);
+        best_cost = waves * cost(1, best.lat, best.gy);
+        if (sub_override > 1) best_cost = 1e30;
+    }
+    for (int S = 1; S <= 32; S *= 2) {
+        if (sub_override > 1 && S != sub_override) continue;
+        const int ch = 32 / S;
+        const int64_t gx = (n_chains + ch - 1) / ch;
+        for (int lat = 1; lat >= 0; --lat) {
+            if (lat && ctx->latency_mode == 0) continue;
+            const int64_t slots = lat ? ctx->n_sm : resident;
+            if (gx > slots) continue;
+            const int Wc = lat ? Wl : W;
+            int64_t max_gy = slots / gx;
+            // no more units than twice the epochs (a unit may end up with nothing to do, never all but a few)
+            const int64_t cap = (2 * E) / ((int64_t)Wc * S);
+            if (max_gy > cap) max_gy = cap;
+            if (max_gy > 65535) max_gy = 65535;
+            if (max_gy < 1) { if (S > 1 && sub_override != S) continue; max_gy = 1; }
+            int64_t gy_c = 1; double c_c = cost(S, lat, 1);
+            for (int64_t gy = 2; gy <= max_gy; ++gy) {
+                const double c = cost(S, lat, gy);
+                if (c < c_c - 1e-9) { c_c = c; gy_c = gy; }
+            }
+            // a single wave is a latency play: beyond ~64 dependent pairs per lane the launch's fixed costs are amortised
+            // anyway and the multi-wave throughput geometry (more warps per SM, hardware load balancing) is the faster one
+            if (sub_override <= 1 && std::ceil(ew[lat ? 1 : 0] / (double)(gy_c * Wc * S)) > 64.0) continue;
+            if (c_c < best_cost - 1e-9) {
+                best_cost = c_c;
+                best.gx = (int)gx; best.gy = (int)gy_c; best.ch = ch; best.lat = lat != 0; best.block = Wc * 32;
+                best.smem = lat ? octo_smem_bytes(ctx->m, Wc, D, T) : (fused ? ctx->smem_fused : ctx->smem);
+                best.slice = (int)((E + gy_c * Wc * S - 1) / (gy_c * Wc * S));
+            }
+        }
+    }
+    return best;
+}
+
 // d_param != nullptr: fused parameterisation — d_in is θ_t, d_ll / d_g receive the log posterior and its gradient
 // post_mode 1 (with d_param): likelihood part only.  pointwise: value-only, one CTA row per epoch, d_ll is [n x E] (ld ldg).
 int enqueue(OctoCtx* ctx, Workspace* w, bool grad, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g,
             int64_t ldg, cudaStream_t st, const DevParam* d_param = nullptr, int post_mode = 0, bool pointwise = false,
             const HmcLeap* leap = nullptr, int64_t pw_e0 = 0, int64_t pw_n = 0, const InlineIn* inl = nullptr) {
-    LaunchGeom g = geometry(ctx, n, d_param != nullptr);
+    LaunchGeom g = geometry(ctx, n, d_param != nullptr, pointwise ? 1 : 0);
     if (pointwise) {      // epochs [pw_e0, pw_e0 + pw_n) of the concatenated list, one CTA row each
         if (pw_n < 1 || pw_n > 65535 || pw_e0 < 0 || pw_e0 + pw_n > ctx->m.n_epochs || pw_e0 >= (1 << 22)) return fail(OCTO_ERR_ARG, "bad pointwise chunk");
         const int W = ctx->warps > 4 ? 4 : ctx->warps;        // one warp does the epoch; the others only help the prologue
@@ -494,7 +574,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     m.n_epochs = E; m.n_acc = n_acc;
     for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN || m.blocks[b].slot_obsprior >= 0) m.has_margin = 1;
     // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
-    double cum = 0.0;
+    double cum = 0.0, cum_lat = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
         DevBlock& D = m.blocks[b];
         const bool astrom = D.kind <= OCTO_KIND_ASTROM_PASEP;
@@ -507,8 +587,14 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         D.wgt = w + 0.8 * (solves - 1);
         D.cum = cum;
         cum += D.wgt * D.n;
+        // latency-bound launches (one CTA per SM, a few pairs per lane): what counts is the dependent chain of one pair,
+        // measured on the resident kernel's timeline: lean astrometry 1340 cycles, RV + jitter 1870
+        const double wl = astrom ? (lean ? 1.0 : (plain ? 1.3 : 1.8)) : (D.kind == OCTO_KIND_RV_STAR_MARGIN ? 1.45 : (D.jit ? 1.4 : 1.05));
+        D.wgt_lat = wl + 0.8 * (solves - 1);
+        D.cum_lat = cum_lat;
+        cum_lat += D.wgt_lat * D.n;
     }
-    m.wtot = cum;
+    m.wtot = cum; m.wtot_lat = cum_lat;
 
     // host tables: t, y1, y2, c1, c2, c3 (see DevModel); chain-independent normalisation summed in long double
     // + padding: the kernels prefetch one lane-stride (<= 32*8 records) past the record they read
@@ -575,6 +661,17 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     }
     if (const char* s = getenv("OCTO_B200_SLICE")) ctx->slice_override = std::max(1, atoi(s));
     if (const char* s = getenv("OCTO_B200_LATENCY")) ctx->latency_mode = atoi(s);
+    if (const char* s = getenv("OCTO_B200_RESIDENT")) ctx->resident_mode = atoi(s);
+    if (const char* s = getenv("OCTO_B200_FORCE")) {
+        int a = 0, b = 0, c = 0;
+        if (sscanf(s, "%d,%d,%d", &a, &b, &c) == 3 && (a == 1 || a == 2 || a == 4 || a == 8 || a == 16 || a == 32) && c >= 1 && c <= 65535) {
+            ctx->force[0] = a; ctx->force[1] = b; ctx->force[2] = c;
+        }
+    }
+    if (const char* s = getenv("OCTO_B200_SUBLANES")) {
+        const int v = atoi(s);
+        if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->sublane_mode = v;
+    }
     ce = cudaMalloc((void**)&ctx->d_tables, T.size() * sizeof(double));
     if (ce != cudaSuccess) { delete ctx; return fail_cuda(ce, "cudaMalloc tables"); }
     ce = cudaMemcpy(ctx->d_tables, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -694,6 +791,24 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
         }
         P.gat_start[D] = (int16_t)n;
     }
+    // evaluation orders, most expensive first (stable): see DevParam
+    {
+        auto order_by = [](uint8_t* out, int n, const std::vector<int>& cost) {
+            std::vector<int> idx(n);
+            for (int i = 0; i < n; ++i) idx[i] = i;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+            for (int i = 0; i < n; ++i) out[i] = (uint8_t)idx[i];
+        };
+        std::vector<int> cp(D), ci(n_in), cg(D, 0);
+        for (int j = 0; j < D; ++j) {
+            const bool lb = std::isfinite(P.pc[j][0]), ub = std::isfinite(P.pc[j][1]);
+            cp[j] = (lb || ub ? 3 : 0) + (P.priors[j].family == OCTO_PRIOR_LOGUNIFORM ? 1 : 0) + (P.priors[j].family == OCTO_PRIOR_SINE ? 2 : 0);
+        }
+        for (int k = 0; k < n_in; ++k) ci[k] = P.defs[k].op == OCTO_IN_CIRC ? 3 : 0;
+        for (int j = 0; j < D; ++j)
+            for (int it = P.gat_start[j]; it < P.gat_start[j + 1]; ++it) cg[j] += (P.gat[it] >> 8) ? 3 : 1;
+        order_by(P.order_prior, D, cp); order_by(P.order_input, n_in, ci); order_by(P.order_gather, D, cg);
+    }
     // fused stage inside K1: needs every θ_at_epoch_to_tperi to depend on non-tperi inputs only (they are evaluated
     // together), at most OCTO_PARAM_TPERI_MAX of them, and the extra shared memory; otherwise K0f + K1 + K0b
     bool fusable = true;
@@ -721,6 +836,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
         ctx->smem_fused = smem_f; ctx->ctas_per_sm_fused = occ > 0 ? occ : 1;
         if (const char* e = getenv("OCTO_B200_CTAS_PER_SM")) ctx->ctas_per_sm_fused = std::max(1, atoi(e));
     }
+    if (fusable) CU(octo_resident_init(ctx->m, ctx->smem_optin));
     CU(octo_param_init(D, n_in));
     if (!ctx->d_param) CU(cudaMalloc((void**)&ctx->d_param, sizeof(DevParam)));
     CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
@@ -789,10 +905,28 @@ int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, d
 
 // ---- device-resident HMC explorer (octo_hmc.cu): the whole run is enqueued on one stream, one sync at the end
 namespace {
-struct HmcUser { OctoCtx* ctx; Workspace* w; int64_t n; };
+struct HmcUser { OctoCtx* ctx; Workspace* w; int64_t n; int ch; };
 int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g, const HmcLeap* leap) {
     HmcUser* u = (HmcUser*)user;
     return logpost_enqueue(u->ctx, u->w, d_theta, u->n, u->n, d_lp, d_g, u->n, u->w->d_in, u->w->stream, 0, leap);
+}
+int hmc_resident(void* user, const ResidentArgs* R) {
+    HmcUser* u = (HmcUser*)user;
+    cudaError_t e = octo_resident_launch(u->ctx->m, u->ctx->d_param, u->ctx->param_T, *R, u->ch, u->w->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "k_hmc_resident launch");
+    u->ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return OCTO_OK;
+}
+// chains per CTA of the trajectory-resident explorer: as many sub-lanes per chain as keep one CTA per SM busy (its chain
+// groups never split epochs across CTAs), never more (warp, sub-lane) units than twice the epochs; 0 = not available
+int resident_ch(const OctoCtx* ctx, int64_t n) {
+    if (!ctx->param_fused || ctx->resident_mode == 0) return 0;
+    if (octo_resident_smem_bytes(ctx->m, ctx->param_D, ctx->param_T) > ctx->smem_optin) return 0;
+    if (ctx->force[0] > 0) return 32 / ctx->force[0];
+    if (ctx->sublane_mode > 0) return 32 / ctx->sublane_mode;
+    int S = 1;
+    while (S < 32 && (n + (32 / (2 * S)) - 1) / (32 / (2 * S)) <= ctx->n_sm && (int64_t)OCTO_LAT_WARPS * 2 * S <= 2 * std::max<int64_t>(ctx->m.n_epochs, 1)) S *= 2;
+    return 32 / S;
 }
 }  // namespace
 
@@ -833,15 +967,18 @@ int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
         if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, col, w->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);          // `im` is a local
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC setup"); break; }
-        HmcUser user{ctx, w, n};
-        int cb_rc = 0;
         const bool fused_leap = ctx->param_fused && !getenv("OCTO_B200_HMC_SEPARATE_LEAP");
+        // the trajectory-resident kernel when the model allows it (fused parameterisation, shared memory)
+        const int rch = (fused_leap && !getenv("OCTO_B200_HMC_LAUNCH_PER_LEAPFROG")) ? resident_ch(ctx, n) : 0;
+        HmcUser user{ctx, w, n, rch};
+        int cb_rc = 0;
         e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user,
-                             fused_leap, &cb_rc, ladder, pt ? n_rounds : 0, d_cold);
+                             fused_leap, &cb_rc, ladder, pt ? n_rounds : 0, d_cold, rch > 0 ? hmc_resident : nullptr);
         if (cb_rc) { rc = cb_rc; cudaStreamSynchronize(w->stream); break; }
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC launch"); cudaStreamSynchronize(w->stream); break; }
         const int64_t rounds = pt ? n_rounds : 1;
-        ctx->launches.fetch_add(rounds * ((int64_t)n_iter * ((fused_leap ? 0 : n_leapfrog) + 1) + 1 + (pt ? 1 + (d_cold ? 1 : 0) : 0)),
+        // helper kernels (the log-posterior launches and the resident launches count themselves)
+        ctx->launches.fetch_add(rounds * ((rch > 0 ? 0 : (int64_t)n_iter * ((fused_leap ? 0 : n_leapfrog) + 1) + 1) + (pt ? 1 + (d_cold ? 1 : 0) : 0)),
                                 std::memory_order_relaxed);
         if (theta_final) e = cudaMemcpy2DAsync(theta_final, (size_t)ld * sizeof(double), d_state, col, col, D, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess && lp_final) e = cudaMemcpyAsync(lp_final, d_state + nD, col, cudaMemcpyDeviceToHost, w->stream);
@@ -953,10 +1090,10 @@ int32_t octo_n_planets(const OctoCtx* ctx) { return ctx ? ctx->m.n_planets : -1;
 int64_t octo_total_epochs(const OctoCtx* ctx) { return ctx ? ctx->m.n_epochs : -1; }
 int32_t octo_device(const OctoCtx* ctx) { return ctx ? ctx->device : -1; }
 int64_t octo_kernel_launches(const OctoCtx* ctx) { return ctx ? ctx->launches.load() : -1; }
-int octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[4]) {
+int octo_launch_geometry(const OctoCtx* ctx, int64_t n_chains, int32_t out[6]) {
     if (!ctx || !out || n_chains < 1) return fail(OCTO_ERR_ARG, "bad argument");
     LaunchGeom g = geometry(ctx, n_chains);
-    out[0] = g.gx; out[1] = g.gy; out[2] = g.block; out[3] = g.slice;
+    out[0] = g.gx; out[1] = g.gy; out[2] = g.block; out[3] = g.slice; out[4] = 32 / g.ch; out[5] = g.lat ? 1 : 0;
     return OCTO_OK;
 }
 

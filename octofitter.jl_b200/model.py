@@ -549,7 +549,11 @@ class LogDensityModel:
 
     def launch_geometry(self, n_chains):
         """(grid.x = chain groups, grid.y = epoch splits, block, epochs per warp) — see octo_launch_geometry."""
-        out = (C.c_int32 * 4)()
+        return self.launch_geometry_full(n_chains)[:4]
+
+    def launch_geometry_full(self, n_chains):
+        """(grid.x, grid.y, block, epochs per unit, sub-lanes per chain, latency instantiation?)"""
+        out = (C.c_int32 * 6)()
         self._lib.octo_launch_geometry(self._h, int(n_chains), C.byref(out))
         return tuple(out)
 

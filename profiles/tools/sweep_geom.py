@@ -1,0 +1,57 @@
+"""Launch-geometry experiments: time one workload under forced (sub-lanes, instantiation, epoch splits) geometries.
+    python profiles/tools/sweep_geom.py C2 | 4096x100 | C4 | C1 | post   [steps]
+Back-to-back steps on one stream between one event pair, every step its own input set (pool > L2), like bench.py."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np, torch
+import workloads
+
+
+def run(name, steps, force):
+    if force is None: os.environ.pop("OCTO_B200_FORCE", None)
+    else: os.environ["OCTO_B200_FORCE"] = force
+    import octofitter_jl_b200 as octo
+    post = False
+    if name == "post":
+        spec, x = workloads.one_planet_with_priors(100, 100, 1024, seed=2); post = True
+    elif "x" in name:
+        n, E = (int(v) for v in name.split("x")); spec, x = workloads.one_planet(E, 0, n, seed=5)
+    else:
+        spec, x = workloads.config(name)
+    model = octo.LogDensityModel(spec)
+    n, nc = x.shape
+    set_bytes = 8 * n * (2 * nc + 1)
+    n_sets = min(4096, max(8, int(1.5 * 126 * 2**20 / set_bytes) + 1))
+    d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda().unsqueeze(0) * (1 + 1e-7 * torch.arange(n_sets, dtype=torch.float64, device="cuda"))[:, None, None]
+    d_ll = torch.empty((n_sets, n), dtype=torch.float64, device="cuda"); d_g = torch.empty((n_sets, nc, n), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    lib, h = model._lib, model._h
+    def step(k):
+        k %= n_sets
+        a = (d_in.data_ptr() + k * n * nc * 8, d_ll.data_ptr() + k * n * 8, d_g.data_ptr() + k * n * nc * 8)
+        rc = lib.octo_logpost_grad_device(h, a[0], n, n, a[1], a[2], None, st) if post else lib.octo_logp_grad_device(h, a[0], n, n, a[1], a[2], st)
+        assert rc == 0, lib.octo_last_error()
+    for k in range(10): step(k)
+    torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(steps): step(10 + rep * steps + k)
+        b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) / steps * 1e3)
+    geom = model.launch_geometry_full(n) if not post else None
+    model.close()
+    return best, geom
+
+
+if __name__ == "__main__":
+    name = sys.argv[1]; steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    cands = [None] + [f"{S},{lat},{gy}" for S in (1, 2, 4, 8, 16) for lat in (1, 0) for gy in (1, 2, 3, 4)]
+    if len(sys.argv) > 3: cands = sys.argv[3:]
+    for f in cands:
+        try:
+            us, geom = run(name, steps, f)
+            print(f"{name} force={f}: {us:.2f} us/step geom={geom}", flush=True)
+        except Exception as e:
+            print(f"{name} force={f}: failed {str(e)[:100]}", flush=True)

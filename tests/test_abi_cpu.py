@@ -28,7 +28,8 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(octo.EXPORTED_SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.octo_abi_version() == 2
+    hdr_version = int(re.search(r"#define OCTO_ABI_VERSION (\d+)", hdr).group(1))
+    assert lib.octo_abi_version() == hdr_version == 3
 
 
 def test_struct_sizes_match_header():

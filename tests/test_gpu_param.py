@@ -164,7 +164,9 @@ def test_batched_parallel_tempering_single_rank():
 @pytest.mark.parametrize("name", post_cases())
 def test_fused_parameterisation_equals_standalone_kernels(name, monkeypatch):
     """The parameterisation fused into K1 (one launch) and the stand-alone K0 forward / backward kernels share their
-    device functions and summation orders: identical bits, for valid, invalid and "healed" chains alike."""
+    device functions and summation orders: they agree to rounding (1e-12) for valid chains — the fused stage reuses
+    intermediates of its forward pass (reciprocals, roots, log r² of a UniformCircular pair) where the stand-alone
+    reverse kernel recomputes them, so the last bits may differ — and exactly on invalid and "healed" chains."""
     d, spec, consts = load_post(name)
     rng = np.random.default_rng(21)
     th = np.array(d["theta_t"])[None, :] + 0.1 * rng.standard_normal((131, spec.D))
@@ -181,7 +183,11 @@ def test_fused_parameterisation_equals_standalone_kernels(name, monkeypatch):
         lib.octo_destroy(h)
     assert out["1"][3] == 1 and out["0"][3] == 3
     for a, b in zip(out["1"][:3], out["0"][:3]):
-        assert np.array_equal(a, b, equal_nan=True)
+        fin = np.isfinite(b)
+        assert np.array_equal(fin, np.isfinite(a)) and np.array_equal(a[~fin], b[~fin], equal_nan=True)
+        scale = np.where(fin, np.abs(b), 0.0).max(axis=-1, keepdims=True) if b.ndim == 2 else np.abs(b)
+        with np.errstate(invalid="ignore"):
+            assert np.all(np.abs(a - b)[fin] <= 1e-12 * np.broadcast_to(np.maximum(scale, 1e-300), b.shape)[fin])
     assert np.array_equal(out["1"][0], out["1"][2], equal_nan=True)
     assert np.isneginf(out["1"][0][[5, 9]]).all() and (out["1"][1][[5, 9]] == 0).all()
 
@@ -267,7 +273,9 @@ def test_loglike_of_theta_and_rejection_sampler(oracle_lib, monkeypatch):
         # lp = prior part + likelihood part
         lp = model.ℓπcallback(th)
         assert np.all(lp[fin] <= res[fuse][fin] + 200.0)
-    assert np.array_equal(res["1"], res["0"], equal_nan=True)
+    # fused and stand-alone evaluate the tables under different launch geometries (summation orders): rounding apart
+    fin = np.isfinite(res["0"])
+    assert np.array_equal(fin, np.isfinite(res["1"])) and rel_err(res["1"][fin], res["0"][fin]).max() < 1e-13
     monkeypatch.setenv("OCTO_B200_FUSE_PARAM", "1")
     model = octo.LogDensityModel(spec)
     out = octo.octofit_rejection(model, np.random.default_rng(5), draws=200_000, batch=50_000)
@@ -373,16 +381,25 @@ def test_device_resident_hmc():
     assert np.array_equal(r1["theta"], r2["theta"]) and np.array_equal(r1["accept"], r2["accept"])
     r3 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=100)
     assert not np.array_equal(r1["theta"], r3["theta"])
-    # the leapfrog update folded into the log-posterior launch == the separate update kernel, bit for bit
+    # the whole run is ONE launch of the trajectory-resident kernel
     n0 = model.kernel_launches
     octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
-    assert model.kernel_launches - n0 == 7 * (L + 1) + 2         # L posterior launches + 1 turn per transition, + start, + final turn
-    os.environ["OCTO_B200_HMC_SEPARATE_LEAP"] = "1"
+    assert model.kernel_launches - n0 == 1
+    # launch-per-leapfrog explorer: the leapfrog update folded into the log-posterior launch == the separate update
+    # kernel, bit for bit
+    os.environ["OCTO_B200_HMC_LAUNCH_PER_LEAPFROG"] = "1"
     try:
+        n0 = model.kernel_launches
+        r5 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
+        assert model.kernel_launches - n0 == 7 * (L + 1) + 2         # L posterior launches + 1 turn per transition, + start, + final turn
+        os.environ["OCTO_B200_HMC_SEPARATE_LEAP"] = "1"
         r4 = octo.device_hmc(model, th0, 7, step_size=eps, n_leapfrog=L, inv_mass=inv_mass, seed=99)
     finally:
-        del os.environ["OCTO_B200_HMC_SEPARATE_LEAP"]
-    assert np.array_equal(r1["theta"], r4["theta"]) and np.array_equal(r1["logpost"], r4["logpost"])
+        del os.environ["OCTO_B200_HMC_LAUNCH_PER_LEAPFROG"]
+        os.environ.pop("OCTO_B200_HMC_SEPARATE_LEAP", None)
+    assert np.array_equal(r5["theta"], r4["theta"]) and np.array_equal(r5["logpost"], r4["logpost"])
+    # and it agrees with the resident kernel to rounding (identical bits when both use the same geometry: test_gpu_resident.py)
+    assert np.allclose(r1["theta"], r5["theta"], rtol=1e-9, atol=1e-11) and np.array_equal(r1["accept"], r5["accept"])
     # a real run: 256 chains x 150 transitions x 12 leapfrogs, against the host-driven explorer
     th256 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((256, D))
     t0 = time.perf_counter()

@@ -180,8 +180,10 @@ def test_leading_dimension_and_single_chain(oracle_lib):
     model.close()
 
 
-def test_epoch_split_geometry_consistent(oracle_lib):
-    """Many epochs, few chains: the grid splits epochs across CTAs (K2 path) and still matches."""
+def test_epoch_split_geometry_consistent(oracle_lib, monkeypatch):
+    """Many epochs, few chains, lane = chain mapping: the grid splits epochs across CTAs (K2 path) and still matches.
+    (By default such a batch now splits its epochs over sub-lanes inside the warps: tests/test_gpu_sublanes.py.)"""
+    monkeypatch.setenv("OCTO_B200_SUBLANES", "1")
     spec, x = workloads.one_planet(3000, 0, 40, seed=9)
     model = octo.LogDensityModel(spec)
     gx, gy, block, slice_ = model.launch_geometry(40)
@@ -193,7 +195,9 @@ def test_epoch_split_geometry_consistent(oracle_lib):
     model.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"OCTO_B200_SLICE": "1"}, {"OCTO_B200_SLICE": "40"}, {"OCTO_B200_CTAS_PER_SM": "1"}])
+@pytest.mark.parametrize("env", [{}, {"OCTO_B200_SUBLANES": "1"}, {"OCTO_B200_SUBLANES": "1", "OCTO_B200_SLICE": "1"},
+                                 {"OCTO_B200_SUBLANES": "1", "OCTO_B200_SLICE": "40"},
+                                 {"OCTO_B200_SUBLANES": "1", "OCTO_B200_CTAS_PER_SM": "1"}, {"OCTO_B200_FORCE": "2,0,3"}])
 def test_launch_geometry_knobs_do_not_change_results(oracle_lib, env, monkeypatch):
     """Different epoch-split geometries (slice length, resident-CTA target) on C2 and the 2-planet C3."""
     for k, v in env.items():
@@ -436,14 +440,15 @@ def test_hgca_many_chains_and_split_geometry(oracle_lib):
     x[3, d["input_names"].index("b.e")] = -0.1                  # invalid chain
     ora = oracle_lib.Oracle(packed, consts)
     ll_o, g_o = ora.logp_grad(x, threads=4)
-    for slice_env in (None, "2"):
-        if slice_env:
-            os.environ["OCTO_B200_SLICE"] = slice_env
+    # default geometry; lane = chain with epoch splits across CTAs (the L2 combine before the HGCA tail); sub-lanes with splits
+    for env in ({}, {"OCTO_B200_SUBLANES": "1", "OCTO_B200_SLICE": "2"}, {"OCTO_B200_FORCE": "1,1,3"}, {"OCTO_B200_FORCE": "4,0,2"}):
+        os.environ.update(env)
         try:
             h = C.c_void_p()
             assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 0, lib.octo_last_error()
         finally:
-            os.environ.pop("OCTO_B200_SLICE", None)
+            for k in env:
+                os.environ.pop(k, None)
         assert lib.octo_total_epochs(h) == 6                        # the astrometry table only
         ll = np.empty(n); g = np.empty((n, n_in), order="F"); llv = np.empty(n)
         assert lib.octo_logp_grad(h, x.ctypes.data, n, n, ll.ctypes.data, g.ctypes.data) == 0, lib.octo_last_error()
