@@ -323,6 +323,33 @@ int  octo_pt_init(OctoCtx* ctx, const void* nccl_unique_id, int32_t rank, int32_
  */
 int  octo_pt_swap_round(OctoCtx* ctx, const double* ll_pair, const double* beta,
                         int32_t* chain_of_replica, int64_t round, int32_t* accepted);
+/*
+ * The same round in stream order, nothing returns to the host (the "K3 fused with ncclAllGather on the same stream" of
+ * SURVEY.md §2): d_ll_pair_local [n_replicas_local x 2] is on the DEVICE (written by the caller's evaluation on
+ * `stream`); one ncclAllGather on `stream`, then one kernel in which every rank takes every decision.  The rung
+ * assignment lives on the device, replicated on every rank, and is updated in place: d_ladder [R] weights per rung
+ * (ascending), d_chain_of_rung [R] / d_rung_of_chain [R] inverse permutations (start: identity), d_swap_count [R]
+ * accepted swaps per adjacent pair (accumulated).  d_beta_local [n_replicas_local] (may be NULL) receives the new
+ * weight of every local replica that swapped.  Same decisions as octo_pt_decide given the same values and seed.
+ */
+int  octo_pt_swap_round_device(OctoCtx* ctx, const double* d_ll_pair_local, const double* d_ladder,
+                               int32_t* d_chain_of_rung, int32_t* d_rung_of_chain, double* d_swap_count,
+                               double* d_beta_local, int64_t round, void* stream);
+/*
+ * octo_pt_hmc_run with the ladder SHARDED over the ranks of octo_pt_init (one process per GPU, replicas block-
+ * partitioned: this rank's n_local chains are chains [rank n_local, (rank + 1) n_local) of R = world n_local).
+ * Collective.  Per round and rank, all on one stream with no host involvement: one launch of the trajectory-resident
+ * explorer on the local chains (it also packs their (l_ref, l_target)), ONE ncclAllGather of R x 2 float64, one
+ * decision kernel (every rank decides every pair and re-weights its own chains), the record of the last rung.
+ * ladder_all [R]; theta0 / outputs are this rank's chains, except swap_accept [R - 1] and cold_samples [n_rounds x D]
+ * (identical on every rank; the rows are summed over ranks at the end of the run: one ncclAllReduce).  With the same
+ * seed the swap history and every chain are bit-identical to octo_pt_hmc_run of all R replicas on one GPU (chain groups
+ * are sized by R, and the result of a chain does not depend on its neighbours).
+ */
+int  octo_pt_hmc_run_dist(OctoCtx* ctx, const double* theta0_local, int64_t n_local, int64_t ld, const double* ladder_all,
+                          int32_t n_rounds, int32_t n_iter, int32_t n_leapfrog, double step_size, const double* inv_mass,
+                          uint64_t seed, double* theta_final, double* lp_final, double* ll_final, double* beta_final,
+                          int32_t* rung_final, double* swap_accept, double* cold_samples, double* accept_rate);
 /* The decision step alone (pure host code, no CUDA/NCCL): ll_pair_all is [n_replicas_total x 2]. */
 int  octo_pt_decide(const double* ll_pair_all, const double* beta, int32_t* chain_of_replica,
                     int32_t n_replicas_total, int64_t round, uint64_t seed, int32_t* accepted);

@@ -171,6 +171,8 @@ def load_library(path: str | None = None):
     lib.octo_pt_unique_id.argtypes = [vp]
     lib.octo_pt_init.argtypes = [vp, vp, i32, i32, i32, C.c_uint64]
     lib.octo_pt_swap_round.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.octo_pt_swap_round_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.octo_pt_hmc_run_dist.argtypes = [vp, vp, i64, i64, vp, i32, i32, i32, C.c_double, vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.octo_pt_decide.argtypes = [vp, vp, vp, i32, i64, C.c_uint64, vp]
     lib.octo_pt_finalize.argtypes = [vp]
     lib.octo_pt_finalize.restype = None
@@ -185,4 +187,4 @@ EXPORTED_SYMBOLS = (
     "octo_logp_grad_device", "octo_set_parameterization", "octo_logpost_grad", "octo_logpost_workspace",
     "octo_logpost_grad_device", "octo_loglike_theta", "octo_logp_pointwise", "octo_hmc_run", "octo_pt_hmc_run", "octo_hmc_random", "octo_invlink", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
-    "octo_pt_decide", "octo_pt_finalize", "octo_last_error")
+    "octo_pt_decide", "octo_pt_finalize", "octo_pt_swap_round_device", "octo_pt_hmc_run_dist", "octo_last_error")

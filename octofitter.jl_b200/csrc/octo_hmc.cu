@@ -87,11 +87,10 @@ __global__ void k_pt_swap(HmcBuf b, int64_t n, int D, int64_t round, uint64_t se
     if (i + 1 < n) {
         const int ca = b.chain_of_rung[i], cb = b.chain_of_rung[i + 1];
         const double bi = b.ladder[i], bj = b.ladder[i + 1];
-        const double ra = b.lp[ca] - b.beta[ca] * b.ll[ca], rb = b.lp[cb] - b.beta[cb] * b.ll[cb];      // l_ref
-        const double ta = ra + b.ll[ca], tb = rb + b.ll[cb];                                              // l_target
-        const double Vaj = (1.0 - bj) * ra + bj * ta, Vbi = (1.0 - bi) * rb + bi * tb;
-        const double Vai = (1.0 - bi) * ra + bi * ta, Vbj = (1.0 - bj) * rb + bj * tb;
-        const double log_ratio = (Vaj + Vbi) - (Vai + Vbj);
+        double ra, ta, rb, tb;                                                 // l_ref, l_target of the two chains
+        pt_pair(b.lp[ca], b.beta[ca], b.ll[ca], ra, ta);
+        pt_pair(b.lp[cb], b.beta[cb], b.ll[cb], rb, tb);
+        const double log_ratio = pt_log_ratio(ra, ta, rb, tb, bi, bj);
         const double u = pt_uniform_dev(seed, (uint64_t)round, (uint64_t)i);
         const bool acc = isfinite(log_ratio) ? (log(u) < log_ratio) : (log_ratio > 0);
         if (acc) {
@@ -109,6 +108,40 @@ __global__ void k_pt_record(HmcBuf b, int64_t n, int D, int64_t round, double* c
     if (j >= D) return;
     const int c = b.chain_of_rung[n - 1];
     cold_out[round * D + j] = b.q[c + (int64_t)j * n];
+}
+
+// ---- the ladder sharded over ranks (one process per GPU; octo_pt_hmc_run_dist): every rank holds n_local chains
+// [chain0, chain0 + n_local) of the R, the all-gathered (l_ref, l_target) pairs of all R, and a replica of the rung
+// assignment.  Every rank takes all the decisions (same inputs, same arithmetic, same counter-based uniforms => same
+// outcome everywhere, no second exchange) and updates the weights of its own chains.
+__global__ void k_pt_swap_dist(PtDist d, double* beta_local, int64_t chain0, int64_t n_local, int R, int64_t round, uint64_t seed) {
+    pdl_sync();
+    const int i = (int)(round & 1) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 1 < R) {
+        const int ca = d.chain_of_rung[i], cb = d.chain_of_rung[i + 1];
+        const double bi = d.ladder[i], bj = d.ladder[i + 1];
+        const double log_ratio = pt_log_ratio(d.pairs_all[2 * ca], d.pairs_all[2 * ca + 1], d.pairs_all[2 * cb], d.pairs_all[2 * cb + 1], bi, bj);
+        const double u = pt_uniform_dev(seed, (uint64_t)round, (uint64_t)i);
+        const bool acc = isfinite(log_ratio) ? (log(u) < log_ratio) : (log_ratio > 0);
+        if (acc) {
+            d.chain_of_rung[i] = cb; d.chain_of_rung[i + 1] = ca;
+            d.rung_of_chain[ca] = i + 1; d.rung_of_chain[cb] = i;
+            if (ca >= chain0 && ca < chain0 + n_local) beta_local[ca - chain0] = bj;
+            if (cb >= chain0 && cb < chain0 + n_local) beta_local[cb - chain0] = bi;
+            d.swap_acc[i] += 1.0;
+        }
+    }
+}
+// the state of the chain on the last rung after a round: written by the rank that holds it, zero elsewhere (summed over
+// ranks at the end of the run)
+__global__ void k_pt_record_dist(PtDist d, const double* q_local, int64_t chain0, int64_t n_local, int R, int D, int64_t round,
+                                 double* cold_out) {
+    pdl_sync();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
+    const int c = d.chain_of_rung[R - 1];
+    const bool mine = c >= chain0 && c < chain0 + n_local;
+    cold_out[round * D + j] = mine ? q_local[(c - chain0) + (int64_t)j * n_local] : 0.0;
 }
 
 template <class... Args>
@@ -152,17 +185,30 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
                              int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
                              bool fused_leap, int* rc_out, const double* h_ladder, int n_rounds, double* d_cold,
-                             int (*resident)(void*, const ResidentArgs*)) {
+                             int (*resident)(void*, const ResidentArgs*), const PtDistRun* dist) {
     HmcBuf b = hmc_views(d_state, n, D);
     b.out_theta = d_out_theta; b.out_lp = d_out_lp;
     const bool pt = h_ladder != nullptr;
+    if (dist && (!pt || !resident)) { *rc_out = -1; return cudaSuccess; }
     if (!pt) { b.beta = nullptr; b.ll = nullptr; b.llp = nullptr; n_rounds = 1; }
     *rc_out = 0;
     cudaError_t e;
     if (pt) {
         std::vector<double> hb(n);
         std::vector<int32_t> id(2 * n);
-        for (int64_t c = 0; c < n; ++c) { hb[c] = h_ladder[c]; id[c] = (int32_t)c; id[n + c] = (int32_t)c; }
+        // sharded: h_ladder is the whole ladder [R]; this rank's chains start on rungs chain0 .. chain0 + n - 1
+        const int64_t c0 = dist ? dist->chain0 : 0;
+        for (int64_t c = 0; c < n; ++c) { hb[c] = h_ladder[c0 + c]; id[c] = (int32_t)c; id[n + c] = (int32_t)c; }
+        if (dist) {
+            std::vector<int32_t> idR(2 * (size_t)dist->R);
+            for (int r = 0; r < dist->R; ++r) { idR[r] = r; idR[dist->R + r] = r; }
+            e = cudaMemcpyAsync(dist->d.ladder, h_ladder, dist->R * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dist->d.chain_of_rung, idR.data(), dist->R * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dist->d.rung_of_chain, idR.data(), dist->R * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(dist->d.swap_acc, 0, dist->R * sizeof(double), st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+        }
         e = cudaMemcpyAsync(b.beta, hb.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(b.ladder, hb.data(), n * sizeof(double), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(b.rung_of_chain, id.data(), 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
@@ -177,8 +223,9 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
             // trajectory-resident kernel: (re-)evaluation at the current weights and all n_iter transitions in ONE launch
             ResidentArgs R;
             R.q = b.q; R.lp = b.lp; R.g = b.g; R.acc = b.acc; R.inv_mass = b.inv_mass; R.out_theta = b.out_theta; R.out_lp = b.out_lp;
-            R.beta = pt ? b.beta : nullptr; R.ll = pt ? b.ll : nullptr; R.n = n; R.chain_offset = 0; R.D = D; R.n_iter = n_iter;
-            R.n_leapfrog = n_leapfrog; R.it0 = 0; R.eps = eps; R.seed = round_seed;
+            R.beta = pt ? b.beta : nullptr; R.ll = pt ? b.ll : nullptr; R.n = n; R.chain_offset = dist ? dist->chain0 : 0; R.D = D;
+            R.n_iter = n_iter; R.n_leapfrog = n_leapfrog; R.it0 = 0; R.eps = eps; R.seed = round_seed;
+            R.pair_out = dist ? dist->d.pairs_local : nullptr;
             if ((*rc_out = resident(user, &R))) return cudaSuccess;
         } else {
         // (re-)evaluate the current states at the current weights
@@ -202,7 +249,16 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
             }
         }
         }
-        if (pt) {
+        if (dist) {
+            // one all-gather of (l_ref, l_target) per round on this stream, then every rank decides every pair
+            if ((*rc_out = dist->allgather(dist->user, dist->d.pairs_local, dist->d.pairs_all, (size_t)n * 2))) return cudaSuccess;
+            e = launch_pdl(k_pt_swap_dist, (int64_t)(dist->R + 1) / 2, st, dist->d, b.beta, dist->chain0, n, dist->R, (int64_t)round, seed);
+            if (e != cudaSuccess) return e;
+            if (d_cold) {
+                e = launch_pdl(k_pt_record_dist, (int64_t)D, st, dist->d, (const double*)b.q, dist->chain0, n, dist->R, D, (int64_t)round, d_cold);
+                if (e != cudaSuccess) return e;
+            }
+        } else if (pt) {
             e = launch_pdl(k_pt_swap, (n + 1) / 2, st, b, n, D, (int64_t)round, seed, d_cold);
             if (e != cudaSuccess) return e;
             if (d_cold) {
@@ -213,6 +269,12 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
     }
     if (pt && (*rc_out = logpost(user, b.q, b.lp, b.g, &at_state))) return cudaSuccess;    // lp at the final weights
     return cudaSuccess;
+}
+
+// one sharded swap decision step on its own (octo_pt_swap_round_device): d.pairs_all already gathered on `st`
+cudaError_t octo_pt_swap_dist_launch(const PtDist& d, double* d_beta_local, int64_t chain0, int64_t n_local, int R, int64_t round,
+                                     uint64_t seed, cudaStream_t st) {
+    return launch_pdl(k_pt_swap_dist, (int64_t)(R + 1) / 2, st, d, d_beta_local, chain0, n_local, R, round, seed);
 }
 
 // host twin of the random stream (tests reproduce a transition with it)

@@ -29,6 +29,19 @@ __host__ __device__ inline double pt_uniform_dev(uint64_t seed, uint64_t round, 
 }
 
 #ifdef __CUDACC__
+// Parallel tempering: what a chain contributes to a swap decision — l_ref = lp - beta ll (the prior terms) and
+// l_target = l_ref + ll — and the log acceptance ratio of exchanging the rungs (weights bi, bj) of chains a and b.
+// Shared by the single-GPU swap kernel, the resident kernel's epilogue (which packs the pair for the all-gather) and the
+// sharded swap kernel: identical roundings everywhere, hence identical decisions.
+__device__ __forceinline__ void pt_pair(double lp, double beta, double ll, double& l_ref, double& l_target) {
+    l_ref = fma(-beta, ll, lp);
+    l_target = __dadd_rn(l_ref, ll);
+}
+__device__ __forceinline__ double pt_log_ratio(double ra, double ta, double rb, double tb, double bi, double bj) {
+    const double Vaj = fma(bj, ta, __dmul_rn(__dadd_rn(1.0, -bj), ra)), Vbi = fma(bi, tb, __dmul_rn(__dadd_rn(1.0, -bi), rb));
+    const double Vai = fma(bi, ta, __dmul_rn(__dadd_rn(1.0, -bi), ra)), Vbj = fma(bj, tb, __dmul_rn(__dadd_rn(1.0, -bj), rb));
+    return __dadd_rn(__dadd_rn(Vaj, Vbi), -__dadd_rn(Vai, Vbj));
+}
 // Start of a transition, coordinate j of chain c: fresh momentum p ~ N(0, 1/inv_mass) (Box-Muller), its kinetic term
 // p² inv_mass (BEFORE the kick), then the first half kick with the current gradient g and the first drift from q.
 struct HmcStart { double kin, p, q; };

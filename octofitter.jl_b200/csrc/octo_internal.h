@@ -138,6 +138,14 @@ struct ResidentArgs {
     int32_t D, n_iter, n_leapfrog, it0;
     double eps;
     uint64_t seed;
+    double* pair_out;                // [n x 2] (l_ref, l_target) of the final states for a sharded swap round, or nullptr
+};
+// sharded parallel tempering (octo_hmc.cu): replicated rung assignment + the all-gathered pairs, all on the device
+struct PtDist { double *pairs_all, *pairs_local, *ladder, *swap_acc; int32_t *chain_of_rung, *rung_of_chain; };
+struct PtDistRun {
+    PtDist d; int R; int64_t chain0;
+    int (*allgather)(void* user, const double* d_send, double* d_recv, size_t count);   // enqueues on the run's stream
+    void* user;
 };
 size_t octo_resident_smem_bytes(const DevModel& m, int D, int n_tperi);
 cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin);
@@ -166,7 +174,10 @@ cudaError_t octo_hmc_enqueue(double* d_state, int64_t n, int D, int n_iter, int 
                              double* d_out_theta, double* d_out_lp, cudaStream_t st,
                              int (*logpost)(void*, const double*, double*, double*, const HmcLeap*), void* user,
                              bool fused_leap, int* rc_out, const double* h_ladder = nullptr, int n_rounds = 0,
-                             double* d_cold = nullptr, int (*resident)(void*, const ResidentArgs*) = nullptr);
+                             double* d_cold = nullptr, int (*resident)(void*, const ResidentArgs*) = nullptr,
+                             const PtDistRun* dist = nullptr);
+cudaError_t octo_pt_swap_dist_launch(const PtDist& d, double* d_beta_local, int64_t chain0, int64_t n_local, int R, int64_t round,
+                                     uint64_t seed, cudaStream_t st);
 // after a tempered run: per-chain beta, rung of each chain, swap acceptance counts per adjacent pair (device pointers into the state)
 void octo_hmc_pt_views(double* d_state, int64_t n, int D, double** beta, double** ll, int32_t** rung_of_chain, double** swap_acc);
 

@@ -1625,6 +1625,11 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
         R.lp[chain0 + tid] = s_lp[tid];
         R.acc[chain0 + tid] += s_acc[tid];
         if (R.ll) R.ll[chain0 + tid] = s_ll[tid];
+        if (R.pair_out) {                 // what this chain contributes to the swap round that follows
+            double l_ref, l_target;
+            pt_pair(s_lp[tid], s_beta[tid], s_ll[tid], l_ref, l_target);
+            R.pair_out[2 * (chain0 + tid)] = l_ref; R.pair_out[2 * (chain0 + tid) + 1] = l_target;
+        }
     }
 }
 

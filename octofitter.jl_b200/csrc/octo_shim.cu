@@ -47,6 +47,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, Id128, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -112,9 +113,10 @@ int load_nccl() {
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.CommDestroy)
         return fail(OCTO_ERR_NCCL, "libnccl is missing required symbols");
     g_nccl.h = h;
     return OCTO_OK;
@@ -906,6 +908,16 @@ int octo_logp_pointwise(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, d
 // ---- device-resident HMC explorer (octo_hmc.cu): the whole run is enqueued on one stream, one sync at the end
 namespace {
 struct HmcUser { OctoCtx* ctx; Workspace* w; int64_t n; int ch; };
+// one all-gather of `count` doubles per rank on the run's stream (sharded parallel tempering); a single rank copies
+int hmc_allgather(void* user, const double* d_send, double* d_recv, size_t count) {
+    HmcUser* u = (HmcUser*)user;
+    if (u->ctx->pt_world > 1) {
+        int r = g_nccl.AllGather(d_send, d_recv, count, /*ncclFloat64*/ 8, u->ctx->nccl_comm, u->w->stream);
+        return r ? fail_nccl(r, "ncclAllGather") : OCTO_OK;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_recv, d_send, count * sizeof(double), cudaMemcpyDeviceToDevice, u->w->stream);
+    return e == cudaSuccess ? OCTO_OK : fail_cuda(e, "pair copy");
+}
 int hmc_logpost(void* user, const double* d_theta, double* d_lp, double* d_g, const HmcLeap* leap) {
     HmcUser* u = (HmcUser*)user;
     return logpost_enqueue(u->ctx, u->w, d_theta, u->n, u->n, d_lp, d_g, u->n, u->w->d_in, u->w->stream, 0, leap);
@@ -935,21 +947,25 @@ namespace {
 int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int32_t n_iter, int32_t n_leapfrog,
                  double step_size, const double* inv_mass, uint64_t seed, double* theta_samples, double* lp_samples,
                  double* theta_final, double* lp_final, double* accept_rate, const double* ladder, int32_t n_rounds,
-                 double* beta_final, int32_t* rung_final, double* swap_accept, double* cold_samples, double* ll_final) {
+                 double* beta_final, int32_t* rung_final, double* swap_accept, double* cold_samples, double* ll_final,
+                 bool sharded = false) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    // sharded: this rank's n chains are chains [rank n, (rank + 1) n) of R = world n; `ladder` has R entries
+    const int64_t R = sharded ? n * ctx->pt_world : n, chain0 = sharded ? n * ctx->pt_rank : 0;
+    if (sharded && (!ctx->pt_stream || ctx->pt_local != n)) return fail(OCTO_ERR_STATE, "octo_pt_init has not been called with this number of local replicas");
     if (!ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
     if (!theta0 || n < 1 || ld < n || n_iter < 1 || n_leapfrog < 1 || !(step_size > 0)) return fail(OCTO_ERR_ARG, "bad arguments");
     const bool pt = ladder != nullptr;
     if (pt && !ctx->param_fused) return fail(OCTO_ERR_STATE, "tempering needs the fused log-posterior launch (not available for this model)");
-    if (pt && (n_rounds < 1 || n < 2)) return fail(OCTO_ERR_ARG, "parallel tempering needs >= 2 chains and >= 1 round");
-    if (pt) for (int64_t c = 0; c < n; ++c) if (!(ladder[c] >= 0.0 && ladder[c] <= 1.0)) return fail(OCTO_ERR_ARG, "ladder weights must lie in [0, 1]");
+    if (pt && (n_rounds < 1 || R < 2)) return fail(OCTO_ERR_ARG, "parallel tempering needs >= 2 chains and >= 1 round");
+    if (pt) for (int64_t c = 0; c < R; ++c) if (!(ladder[c] >= 0.0 && ladder[c] <= 1.0)) return fail(OCTO_ERR_ARG, "ladder weights must lie in [0, 1]");
     const int D = ctx->param_D, n_in = ctx->m.n_in;
     if (inv_mass) for (int j = 0; j < D; ++j) if (!(inv_mass[j] > 0) || !std::isfinite(inv_mass[j])) return fail(OCTO_ERR_ARG, "inverse mass must be positive");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = lease(ctx);
     if (!w) return fail(OCTO_ERR_CUDA, "cannot create stream");
     const size_t col = (size_t)n * sizeof(double), nD = (size_t)n * D;
-    double *d_state = nullptr, *d_ot = nullptr, *d_ol = nullptr, *d_cold = nullptr;
+    double *d_state = nullptr, *d_ot = nullptr, *d_ol = nullptr, *d_cold = nullptr, *d_dist = nullptr;
     int rc = OCTO_OK;
     do {
         if (!ctx->param_fused && (rc = ensure(&w->d_in, &w->cap_in, (size_t)n * (2 * n_in + 1 + 3 * D + 3)))) break;
@@ -968,12 +984,26 @@ int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);          // `im` is a local
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC setup"); break; }
         const bool fused_leap = ctx->param_fused && !getenv("OCTO_B200_HMC_SEPARATE_LEAP");
-        // the trajectory-resident kernel when the model allows it (fused parameterisation, shared memory)
-        const int rch = (fused_leap && !getenv("OCTO_B200_HMC_LAUNCH_PER_LEAPFROG")) ? resident_ch(ctx, n) : 0;
+        // the trajectory-resident kernel when the model allows it (fused parameterisation, shared memory); a sharded
+        // ladder sizes its chain groups by the total replica count, so that every chain sees the arithmetic it would
+        // see in a single-GPU run of all R replicas
+        const int rch = (fused_leap && (sharded || !getenv("OCTO_B200_HMC_LAUNCH_PER_LEAPFROG"))) ? resident_ch(ctx, R) : 0;
         HmcUser user{ctx, w, n, rch};
+        PtDistRun dist{};
+        if (sharded) {
+            if (rch <= 0) { rc = fail(OCTO_ERR_STATE, "the sharded ladder needs the trajectory-resident explorer (not available for this model)"); break; }
+            // [pairs_all 2R | pairs_local 2n | ladder R | swap_acc R | chain_of_rung R (int32) | rung_of_chain R (int32)]
+            e = cudaMalloc((void**)&d_dist, (size_t)(2 * R + 2 * n + 2 * R + R + 2) * sizeof(double));
+            if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc (sharded tempering)"); break; }
+            dist.d.pairs_all = d_dist; dist.d.pairs_local = d_dist + 2 * R; dist.d.ladder = dist.d.pairs_local + 2 * n;
+            dist.d.swap_acc = dist.d.ladder + R;
+            dist.d.chain_of_rung = reinterpret_cast<int32_t*>(dist.d.swap_acc + R); dist.d.rung_of_chain = dist.d.chain_of_rung + R;
+            dist.R = (int)R; dist.chain0 = chain0; dist.allgather = hmc_allgather; dist.user = &user;
+        }
         int cb_rc = 0;
         e = octo_hmc_enqueue(d_state, n, D, n_iter, n_leapfrog, step_size, seed, d_ot, d_ol, w->stream, hmc_logpost, &user,
-                             fused_leap, &cb_rc, ladder, pt ? n_rounds : 0, d_cold, rch > 0 ? hmc_resident : nullptr);
+                             fused_leap, &cb_rc, ladder, pt ? n_rounds : 0, d_cold, rch > 0 ? hmc_resident : nullptr,
+                             sharded ? &dist : nullptr);
         if (cb_rc) { rc = cb_rc; cudaStreamSynchronize(w->stream); break; }
         if (e != cudaSuccess) { rc = fail_cuda(e, "HMC launch"); cudaStreamSynchronize(w->stream); break; }
         const int64_t rounds = pt ? n_rounds : 1;
@@ -988,10 +1018,17 @@ int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
         if (pt) {
             double *d_beta, *d_ll, *d_swap; int32_t* d_rung;
             octo_hmc_pt_views(d_state, n, D, &d_beta, &d_ll, &d_rung, &d_swap);
+            if (sharded) {
+                d_swap = dist.d.swap_acc; d_rung = dist.d.rung_of_chain + chain0;
+                if (cold_samples && ctx->pt_world > 1) {      // every round's row was written by the rank that held the chain
+                    int r = g_nccl.AllReduce(d_cold, d_cold, (size_t)n_rounds * D, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, w->stream);
+                    if (r) { rc = fail_nccl(r, "ncclAllReduce"); cudaStreamSynchronize(w->stream); break; }
+                }
+            }
             if (e == cudaSuccess && beta_final) e = cudaMemcpyAsync(beta_final, d_beta, col, cudaMemcpyDeviceToHost, w->stream);
             if (e == cudaSuccess && ll_final) e = cudaMemcpyAsync(ll_final, d_ll, col, cudaMemcpyDeviceToHost, w->stream);
             if (e == cudaSuccess && rung_final) e = cudaMemcpyAsync(rung_final, d_rung, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, w->stream);
-            if (e == cudaSuccess && swap_accept) e = cudaMemcpyAsync(swap_accept, d_swap, (size_t)(n - 1) * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess && swap_accept) e = cudaMemcpyAsync(swap_accept, d_swap, (size_t)(R - 1) * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
             if (e == cudaSuccess && cold_samples) e = cudaMemcpyAsync(cold_samples, d_cold, (size_t)n_rounds * D * sizeof(double), cudaMemcpyDeviceToHost, w->stream);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
@@ -1002,6 +1039,7 @@ int hmc_run_impl(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, int3
     if (d_ot) cudaFree(d_ot);
     if (d_ol) cudaFree(d_ol);
     if (d_cold) cudaFree(d_cold);
+    if (d_dist) cudaFree(d_dist);
     release(ctx, w);
     return rc;
 }
@@ -1021,6 +1059,15 @@ int octo_pt_hmc_run(OctoCtx* ctx, const double* theta0, int64_t n, int64_t ld, c
     if (!ladder) return fail(OCTO_ERR_ARG, "ladder is null");
     return hmc_run_impl(ctx, theta0, n, ld, n_iter, n_leapfrog, step_size, inv_mass, seed, nullptr, nullptr, theta_final, lp_final,
                         accept_rate, ladder, n_rounds, beta_final, rung_final, swap_accept, cold_samples, ll_final);
+}
+
+int octo_pt_hmc_run_dist(OctoCtx* ctx, const double* theta0_local, int64_t n_local, int64_t ld, const double* ladder_all,
+                         int32_t n_rounds, int32_t n_iter, int32_t n_leapfrog, double step_size, const double* inv_mass,
+                         uint64_t seed, double* theta_final, double* lp_final, double* ll_final, double* beta_final,
+                         int32_t* rung_final, double* swap_accept, double* cold_samples, double* accept_rate) {
+    if (!ladder_all) return fail(OCTO_ERR_ARG, "ladder is null");
+    return hmc_run_impl(ctx, theta0_local, n_local, ld, n_iter, n_leapfrog, step_size, inv_mass, seed, nullptr, nullptr, theta_final,
+                        lp_final, accept_rate, ladder_all, n_rounds, beta_final, rung_final, swap_accept, cold_samples, ll_final, true);
 }
 
 int octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* theta_nat) {
@@ -1183,6 +1230,29 @@ int octo_pt_swap_round(OctoCtx* ctx, const double* ll_pair, const double* beta, 
         return octo_pt_decide(ctx->h_gather, beta, chain_of_replica, R, round, ctx->pt_seed, accepted);
     }
     return octo_pt_decide(ll_pair, beta, chain_of_replica, R, round, ctx->pt_seed, accepted);
+}
+
+// Device-ordered swap round: the local (l_ref, l_target) pairs are already on the device; one
+// ncclAllGather on `stream`, then the decision kernel on the gathered buffer, no host synchronisation.  The rung
+// assignment lives on the device, replicated on every rank (every rank takes every decision).
+int octo_pt_swap_round_device(OctoCtx* ctx, const double* d_ll_pair_local, const double* d_ladder, int32_t* d_chain_of_rung,
+                              int32_t* d_rung_of_chain, double* d_swap_count, double* d_beta_local, int64_t round, void* stream) {
+    if (!ctx || !ctx->pt_stream) return fail(OCTO_ERR_STATE, "octo_pt_init has not been called");
+    if (!d_ll_pair_local || !d_ladder || !d_chain_of_rung || !d_rung_of_chain || !d_swap_count) return fail(OCTO_ERR_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const int nl = ctx->pt_local, R = nl * ctx->pt_world;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->pt_world > 1) {
+        int r = g_nccl.AllGather(d_ll_pair_local, ctx->d_gather, (size_t)nl * 2, /*ncclFloat64*/ 8, ctx->nccl_comm, st);
+        if (r) return fail_nccl(r, "ncclAllGather");
+    } else {
+        CU(cudaMemcpyAsync(ctx->d_gather, d_ll_pair_local, (size_t)nl * 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    PtDist d{ctx->d_gather, nullptr, const_cast<double*>(d_ladder), d_swap_count, d_chain_of_rung, d_rung_of_chain};
+    cudaError_t e = octo_pt_swap_dist_launch(d, d_beta_local, (int64_t)ctx->pt_rank * nl, d_beta_local ? nl : 0, R, round, ctx->pt_seed, st);
+    if (e != cudaSuccess) return fail_cuda(e, "k_pt_swap_dist launch");
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return OCTO_OK;
 }
 
 void octo_pt_finalize(OctoCtx* ctx) {

@@ -33,6 +33,10 @@ class ParallelTempering:
         self.backend = backend
         self._lib = lib if lib is not None else _abi.load_library()
         self._model = model
+        if backend == "local" and model is not None:        # single rank with a context: device-ordered rounds work too
+            rc = self._lib.octo_pt_init(model._h, None, 0, 1, self.n_local, self.seed)
+            if rc:
+                raise RuntimeError(self._lib.octo_last_error().decode())
         if backend == "nccl":
             if model is None:
                 raise ValueError("backend 'nccl' needs a LogDensityModel (its context owns the communicator)")
@@ -83,6 +87,30 @@ class ParallelTempering:
         self.round += 1
         return acc[: self.R - 1]
 
+    def swap_round_device(self, d_pair_local, state, stream=0):
+        """The same round in stream order (C ABI `octo_pt_swap_round_device`, backends "nccl" / "local" with a model):
+        `d_pair_local` is the DEVICE address of this rank's [n_local x 2] (l_ref, l_target); `state` is a dict of device
+        addresses {"ladder", "chain_of_rung", "rung_of_chain", "swap_count", "beta_local"} (see `device_swap_state`).
+        One all-gather and one decision kernel are enqueued on `stream`; nothing is synchronised."""
+        if self._model is None:
+            raise ValueError("swap_round_device needs a LogDensityModel (its context owns the communicator)")
+        rc = self._lib.octo_pt_swap_round_device(self._model._h, int(d_pair_local), state["ladder"], state["chain_of_rung"],
+                                                 state["rung_of_chain"], state["swap_count"], state.get("beta_local"),
+                                                 self.round, int(stream) if stream else None)
+        if rc:
+            raise RuntimeError(self._lib.octo_last_error().decode())
+        self.round += 1
+
+    def device_swap_state(self, torch, device):
+        """Device-resident rung assignment for `swap_round_device` (replicated on every rank): torch tensors plus the
+        address dict the call takes."""
+        t = {"ladder": torch.tensor(self.beta, dtype=torch.float64, device=device),
+             "chain_of_rung": torch.arange(self.R, dtype=torch.int32, device=device),
+             "rung_of_chain": torch.arange(self.R, dtype=torch.int32, device=device),
+             "swap_count": torch.zeros(self.R, dtype=torch.float64, device=device),
+             "beta_local": torch.tensor(self.beta[self.local_slice], dtype=torch.float64, device=device)}
+        return t, {k: v.data_ptr() for k, v in t.items()}
+
     def close(self):
-        if self.backend == "nccl" and self._model is not None and self._model._h:
+        if self._model is not None and self._model._h:
             self._lib.octo_pt_finalize(self._model._h)

@@ -103,6 +103,32 @@ def device_parallel_tempering(model, theta0, ladder, n_rounds, *, n_iter=1, n_le
             "swap_accept": swaps / np.maximum(proposals, 1.0), "swap_counts": swaps, "cold_trace": cold, "accept": acc}
 
 
+def device_parallel_tempering_dist(model, pt, theta0_local, ladder_all, n_rounds, *, n_iter=1, n_leapfrog=8, step_size=0.02,
+                                   inv_mass=None, seed=0):
+    """`device_parallel_tempering` with the ladder sharded over the ranks of `pt` (an `octo.ParallelTempering` with
+    backend "nccl" — one process per GPU — or "local"): C ABI `octo_pt_hmc_run_dist`.  Collective: every rank calls it
+    with its own replicas (chains [rank n_local, (rank + 1) n_local) of the R) and the same full ladder.  Per round one
+    resident-explorer launch, one ncclAllGather of R x 2 float64 and one decision kernel, all in stream order.  Returns
+    this rank's chains plus the (replicated) swap statistics and the trace of the last rung."""
+    import ctypes as C
+    th = np.array(theta0_local, dtype=np.float64, order="F")
+    n, D = th.shape
+    lad = np.ascontiguousarray(ladder_all, dtype=np.float64)
+    R = n * pt.world
+    assert lad.shape == (R,) and n == pt.n_local
+    im = None if inv_mass is None else np.ascontiguousarray(inv_mass, dtype=np.float64)
+    th_f = np.empty((n, D), order="F"); lp = np.empty(n); ll = np.empty(n); beta = np.empty(n)
+    rung = np.empty(n, dtype=np.int32); swaps = np.empty(R - 1); cold = np.empty((n_rounds, D)); acc = np.empty(n)
+    p = lambda a: None if a is None else a.ctypes.data
+    model._check(model._lib.octo_pt_hmc_run_dist(model._h, th.ctypes.data, n, n, lad.ctypes.data, int(n_rounds), int(n_iter),
+                                                 int(n_leapfrog), float(step_size), p(im), C.c_uint64(int(seed)), th_f.ctypes.data,
+                                                 lp.ctypes.data, ll.ctypes.data, beta.ctypes.data, rung.ctypes.data, swaps.ctypes.data,
+                                                 cold.ctypes.data, acc.ctypes.data))
+    proposals = np.array([(n_rounds + (1 - (i & 1))) // 2 for i in range(R - 1)], dtype=np.float64)
+    return {"theta_final": th_f, "logpost_tempered": lp, "loglike": ll, "beta": beta, "rung": rung,
+            "swap_accept": swaps / np.maximum(proposals, 1.0), "swap_counts": swaps, "cold_trace": cold, "accept": acc}
+
+
 def hmc_random(model, seed, it, chain, D):
     """(z[D], u): the standard normals and the accept-step uniform `octo_hmc_run` uses for transition `it` of `chain`."""
     import ctypes as C

@@ -84,3 +84,52 @@ def test_resident_automatic_geometry_two_planets_and_ragged_batch():
         assert np.allclose(res["theta_final"], ref["theta_final"], rtol=1e-8, atol=1e-10)
         assert np.array_equal(res["accept"], ref["accept"])
     model.close()
+
+
+def test_sharded_ladder_entry_point_single_rank_equals_plain_run():
+    """octo_pt_hmc_run_dist on a single rank (world = 1: the all-gather degenerates to a copy) takes the same decisions
+    and moves every chain exactly like octo_pt_hmc_run — the pair packing in the resident kernel, the decision kernel on
+    the gathered buffer and the replicated rung assignment are the code the multi-GPU run uses (tests/test_gpu_multi.py)."""
+    spec_p, th_p = workloads.one_planet_with_priors(100, 100, 64, seed=2)
+    model = octo.LogDensityModel(spec_p)
+    lad = np.linspace(0.0, 1.0, 64) ** 3
+    kw = dict(n_iter=2, n_leapfrog=4, step_size=1e-3, inv_mass=np.full(spec_p.D, 1e-4), seed=11)
+    ref = octo.device_parallel_tempering(model, th_p, lad, 12, **kw)
+    pt = octo.ParallelTempering(64, seed=11, beta=lad, backend="local", model=model)
+    res = octo.device_parallel_tempering_dist(model, pt, th_p, lad, 12, **kw)
+    for k in ref:
+        if isinstance(ref[k], np.ndarray):
+            assert np.array_equal(res[k], ref[k]), k
+    assert res["swap_counts"].sum() > 0
+    pt.close(); model.close()
+
+
+def test_device_ordered_swap_round_matches_host_decisions():
+    """octo_pt_swap_round_device (pairs on the device, decisions in stream order, no host sync) against the pure-host
+    octo_pt_decide fed with the same values: same acceptances, same rung assignment, round after round."""
+    import torch
+    spec, x = workloads.config("C4")
+    R = x.shape[0]
+    model = octo.LogDensityModel(spec)
+    lad = np.linspace(0.0, 1.0, R) ** 2
+    dev = octo.ParallelTempering(R, seed=5, beta=lad, backend="local", model=model)
+    host = octo.ParallelTempering(R, seed=5, beta=lad, backend="local")
+    tens, addr = dev.device_swap_state(torch, "cuda")
+    rng = np.random.default_rng(3)
+    st = torch.cuda.current_stream()
+    d_pairs = []
+    expect = []
+    for rnd in range(40):
+        ref, tgt = rng.normal(-30, 3, R), rng.normal(-80, 25, R)
+        pair = torch.tensor(np.stack([ref, tgt], axis=1), dtype=torch.float64, device="cuda")
+        d_pairs.append(pair)
+        dev.swap_round_device(pair.data_ptr(), addr, st.cuda_stream)          # enqueued only
+        host.swap_round(ref, tgt)
+        expect.append(host.chain_of_replica.copy())
+    torch.cuda.synchronize()
+    rung_of_chain = tens["rung_of_chain"].cpu().numpy()
+    assert np.array_equal(rung_of_chain, expect[-1])
+    assert np.array_equal(tens["chain_of_rung"].cpu().numpy()[rung_of_chain], np.arange(R))
+    assert np.array_equal(tens["beta_local"].cpu().numpy(), lad[rung_of_chain])
+    assert tens["swap_count"].sum().item() > 0
+    dev.close(); model.close()
