@@ -12,7 +12,10 @@ independent, no data-path collective) => weak scaling; value = all ranks' pairs 
 
 `value`: inputs resident in HBM, one kernel per step, K steps launched back to back between one pair of CUDA
 events on the launching stream (barrier + synchronize on both sides); every step reads its own input set from a
-pool larger than L2, so no step finds its inputs cached.  `roofline.kernel_ms_isolated` is the latency of one cold
+pool larger than L2, so no step finds its inputs cached.  The region is measured N_REGIONS times and the median is
+reported (all regions are listed).  `roofline.frac` counts EXECUTED FP64 flop (profiles/sass_flops.json).
+N > 1 additionally runs BASELINE's C4 — 64 tempered replicas sharded over the ranks with the NCCL swap — and reports it
+under `pt_nccl`.  `roofline.kernel_ms_isolated` is the latency of one cold
 launch (own event pair, whole L2 flushed before it).  `e2e`: the same metric through the public host API (`LogDensityModel.
 ln_like_and_gradient` -> C ABI `octo_logp_grad`) with HOST buffers: pack + H2D + kernel + D2H inside the
 timed region, wall clock around K synchronous calls.
@@ -35,12 +38,24 @@ sys.path.insert(0, ROOT)
 # add/mul = 1, div = 8, sqrt = 8, cbrt = 24, sincos = 48, log = 24): one Kepler solve = 75 + 7*8 + 8 + 24 + 2*48 =
 # 259; astrometry projection + chi^2 + adjoint = 49; RV = 45 + div + log = 77.  The roofline's `achieved` uses this.
 L2_BYTES = 126 * 1024 * 1024       # B200 L2
+N_REGIONS = 11                     # timed regions of K steps each; the median is reported
+WORKLOAD = "C2: 1 planet, 100 RA/Dec astrometry + 100 star-RV (offset, jitter) epochs x 1024 chains per GPU"
 F_ALG = {"astrom": 308.0, "rv": 336.0, "extra_solve": 259.0}
 # EXECUTED FP64 flop per pair of THIS kernel, from ncu SASS counts (DFMA = 2, DMUL/DADD = 1; profiles/r01_*):
 # the FP32 Markley starter, the branch-free sincos/rcp and the single sincos per solve make it ~1.8x leaner than
 # the algorithmic figure.  Reported next to the roofline as `executed`.
-F_EXEC = {"astrom": 150.0, "rv": 207.0}      # astrometry: 55 DFMA + 27 DMUL + 13 DADD; RV+jitter: 76 + 36 + 19 (+ libm log)
+F_EXEC_FALLBACK = {"astrom": 150.0, "astrom_jitter": 305.0, "rv": 143.0, "rv_jitter": 206.0, "rv_margin": 219.0}
 FP64_PEAK_FALLBACK_TFLOPS = 37.2     # nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz, used only if the probe fails
+
+
+def executed_flop_table():
+    """EXECUTED FP64 flop per pair of this build's epoch loops (2 DFMA + DMUL + DADD), counted from the library's SASS by
+    profiles/tools/sass_flops.py (run by __graft_entry__.build()).  This is what `roofline.frac` is made of."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "sass_flops.json")))["kernels"]["thr"]
+        return {k: v["flop"] for k, v in d.items()}, "profiles/sass_flops.json (SASS op counts of this build)"
+    except Exception:
+        return dict(F_EXEC_FALLBACK), "fallback constants (profiles/sass_flops.json missing)"
 
 
 def parse():
@@ -125,11 +140,89 @@ def flops_per_launch(spec, n_chains, table=None):
     fl = 0.0
     for b in spec.block_dicts:
         kind = "astrom" if b["kind"] <= 1 else "rv"
+        if "rv_jitter" in table:            # the executed-flop table distinguishes the specialised loops
+            jit = b.get("idx_jitter", -1) >= 0
+            kind = ("astrom_jitter" if jit else "astrom") if b["kind"] <= 1 else ("rv_margin" if b["kind"] == 3 else ("rv_jitter" if jit else "rv"))
         n_solves = P if b["kind"] in (2, 3) else 1 + sum(1 for j, pl in enumerate(spec.layout_dict["planets"])
                                                          if j != b["planet"] and pl.get("mass", -1) >= 0)
         extra = table.get("extra_solve", 0.85 * table[kind])
         fl += len(b["epoch"]) * (table[kind] + (n_solves - 1) * extra)
     return fl * n_chains
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the C2 launch from the committed `ncu --set full` capture of this
+    round (profiles/r02_ncu_c2.json, written by profiles/tools/ncu_summary.py --json), per launch; None when absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_c2.json")))
+        return d["dram_bytes_read"] + d["dram_bytes_write"], "profiles/r02_ncu_c2.json (ncu --set full of the C2 launch)"
+    except Exception:
+        return None, "no ncu capture committed for this build"
+
+
+def c4_parallel_tempering(octo, workloads, torch, dist, rank, world, local, rounds=60):
+    """BASELINE config C4 across the ranks of this run: 64 tempered replicas block-partitioned over the GPUs.
+    (a) host-API swap rounds through libocto_b200's own NCCL all-gather (octo_pt_swap_round), every decision checked
+        against octo_pt_decide fed with the values gathered independently over torch.distributed;
+    (b) the device-ordered run (octo_pt_hmc_run_dist: resident explorer + ncclAllGather + decision kernel per round, no host
+        in the loop), checked against the single-GPU run of all 64 replicas on rank 0 (octo_pt_hmc_run)."""
+    R = 64
+    nl = R // world
+    spec, x = workloads.config("C4")
+    model = octo.LogDensityModel(spec, device=local)
+    lad = np.linspace(0.0, 1.0, R) ** 2
+    pt = octo.ParallelTempering(R, rank=rank, world=world, seed=21, beta=lad, backend="nccl", model=model)
+    check = octo.ParallelTempering(R, seed=21, beta=lad, backend="local")
+    rng = np.random.default_rng(7)
+    ref_all = rng.normal(-30, 3, R)
+    ok, t_rounds = True, []
+    xs = np.asfortranarray(x[pt.local_slice])
+    for rnd in range(rounds):
+        xs[:, spec.column("b.a")] *= 1.0 + 1e-4 * np.cos(rnd + np.arange(nl))          # the states move between rounds
+        tgt = model.ln_like(xs)
+        t0 = time.perf_counter()
+        acc = pt.swap_round(ref_all[pt.local_slice], tgt)
+        t_rounds.append(time.perf_counter() - t0)
+        parts = [torch.empty(nl, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(tgt).cuda())
+        acc0 = check.swap_round(ref_all, torch.cat(parts).cpu().numpy())
+        ok = ok and np.array_equal(acc, acc0) and np.array_equal(pt.chain_of_replica, check.chain_of_replica)
+    pt.close(); model.close()
+    # (b) device-ordered, with the standard priors attached
+    spec_p, th_p = workloads.one_planet_with_priors(100, 0, R, seed=4)
+    model_p = octo.LogDensityModel(spec_p, device=local)
+    ptd = octo.ParallelTempering(R, rank=rank, world=world, seed=22, beta=lad, backend="nccl", model=model_p)
+    im = np.full(spec_p.D, 1e-4)
+    kw = dict(n_iter=1, n_leapfrog=8, step_size=1e-3, inv_mass=im)
+    octo.device_parallel_tempering_dist(model_p, ptd, th_p[ptd.local_slice], lad, 3, seed=1, **kw)
+    dist.barrier()
+    t0 = time.perf_counter()
+    res = octo.device_parallel_tempering_dist(model_p, ptd, th_p[ptd.local_slice], lad, rounds, seed=2, **kw)
+    t_dist = time.perf_counter() - t0
+    same, t_single = True, None
+    if rank == 0:
+        octo.device_parallel_tempering(model_p, th_p, lad, 3, seed=1, **kw)
+        t0 = time.perf_counter()
+        one = octo.device_parallel_tempering(model_p, th_p, lad, rounds, seed=2, **kw)
+        t_single = time.perf_counter() - t0
+        same = bool(np.array_equal(one["swap_counts"], res["swap_counts"]) and np.array_equal(one["cold_trace"], res["cold_trace"])
+                    and np.array_equal(one["theta_final"][:nl], res["theta_final"]))
+    ptd.close(); model_p.close()
+    # (the first round pays NCCL's lazy connection set-up: reported separately)
+    tt = torch.tensor([float(np.median(t_rounds[1:])), t_dist, 0.0 if ok else 1.0, t_rounds[0]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    return {"what": "C4: 64 tempered replicas, %d per GPU on %d GPUs, %d rounds" % (nl, world, rounds),
+            "ranks": world, "replicas_per_rank": nl, "rounds": rounds,
+            "host_api": {"us_per_round": float(tt[0]) * 1e6, "first_round_us": float(tt[3]) * 1e6, "decisions_match_octo_pt_decide": bool(tt[2] == 0.0),
+                         "what": "octo_pt_swap_round: host pairs -> H2D -> ncclAllGather (inside libocto_b200) -> D2H -> decisions; "
+                                 "checked every round against octo_pt_decide on values gathered over torch.distributed"},
+            "device_ordered": {"us_per_round": float(tt[1]) / rounds * 1e6, "us_per_round_single_gpu_all_replicas": t_single / rounds * 1e6,
+                               "identical_to_single_gpu_run": same, "mean_swap_accept": float(np.mean(res["swap_accept"])),
+                               "what": "octo_pt_hmc_run_dist: per round {resident explorer: 1 tempered HMC transition x 8 leapfrogs, "
+                                       "ncclAllGather of 64 x 2 float64, decision kernel on every rank}, one stream, one "
+                                       "synchronisation per run; wall clock of the call, max over ranks"}}
 
 
 def cpu_baseline(spec, x, threads, budget_s=12.0):
@@ -166,9 +259,10 @@ def run_reference(args):
     spec, x = workloads.config("C2")
     threads = oracle_py.max_threads()
     orc = oracle_py.Oracle(spec.packed, octo.default_constants())
-    for _ in range(max(1, min(args.warmup, 3))):
+    warm = max(3, args.warmup)
+    for _ in range(min(warm, 20)):           # (a CPU pass needs no more warm-up than that; the line reports the flag's value)
         orc.logp_grad(x, threads=threads)
-    steps = max(1, min(args.steps, 50))
+    steps = max(1, min(args.steps, 2000))
     t0 = time.perf_counter()
     for _ in range(steps):
         orc.logp_grad(x, threads=threads)
@@ -176,9 +270,10 @@ def run_reference(args):
     pairs = x.shape[0] * spec.total_epochs
     v = pairs / dt
     line = {"impl": "reference", "metric": "epoch*chain logp-grad evals/s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 1 planet, 100 astrometry + 100 star-RV epochs x 1024 chains (rank 0 only)"},
+            "config": {"workload": WORKLOAD, "chains_per_gpu": int(x.shape[0]), "epochs": int(spec.total_epochs), "n_in": int(spec.n_in),
+                       "note": "CPU arm: rank 0 only, one batch of 1024 chains per step on all host threads"},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} passes over the full batch ({x.shape[0]} chains x {spec.total_epochs} epochs)"},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,7 +298,7 @@ def time_device(model, d_in, d_ll, d_g, n, steps, warmup, torch, flush, grad=Tru
     return np.array([a.elapsed_time(b) for a, b in ev])      # ms
 
 
-def time_stream(model, d_in_all, d_ll_all, d_g_all, n, steps, warmup, torch, flush):
+def time_stream(model, d_in_all, d_ll_all, d_g_all, n, steps, warmup, torch, flush, first=0, barrier=None):
     """The timed region of the contract: `steps` launches back to back on the launching stream between ONE pair of
     CUDA events.  Every launch reads its own input set and writes its own output set; the pool of sets is larger than
     L2 and L2 is flushed once before the region, so no step finds its inputs cached (observation tables and code
@@ -214,13 +309,15 @@ def time_stream(model, d_in_all, d_ll_all, d_g_all, n, steps, warmup, torch, flu
     # make the host, not the GPU, the bottleneck of a 14 us step)
     base = (d_in_all.data_ptr(), d_ll_all.data_ptr(), d_g_all.data_ptr())
     stride = (d_in_all[0].numel() * 8, d_ll_all[0].numel() * 8, d_g_all[0].numel() * 8)
-    ptrs = [tuple(b0 + (k % n_sets) * s0 for b0, s0 in zip(base, stride)) for k in range(warmup + steps)]
+    ptrs = [tuple(b0 + ((first + k) % n_sets) * s0 for b0, s0 in zip(base, stride)) for k in range(warmup + steps)]
     lib, h, sh = model._lib, model._h, st.cuda_stream
     for k in range(warmup):
         model.enqueue_device(ptrs[k][0], n, n, ptrs[k][1], ptrs[k][2], sh)
     torch.cuda.synchronize()
     flush.zero_()
     torch.cuda.synchronize()
+    if barrier:
+        barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(st)
     for k in range(warmup, warmup + steps):
@@ -229,6 +326,8 @@ def time_stream(model, d_in_all, d_ll_all, d_g_all, n, steps, warmup, torch, flu
             raise RuntimeError(lib.octo_last_error().decode())
     b.record(st)
     torch.cuda.synchronize()
+    if barrier:
+        barrier()
     return a.elapsed_time(b)            # ms for all steps
 
 
@@ -270,17 +369,24 @@ def main():
     d_g_all = torch.empty((n_sets, n_in, n), dtype=torch.float64, device="cuda")
 
     sampler = ClockSampler(local)
-    launches0 = model.kernel_launches
+    barrier = dist.barrier if world > 1 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    t_region_ms = time_stream(model, d_in_all, d_ll_all, d_g_all, n, args.steps, warm, torch, flush)
+    # The timed region of the contract — exactly K steps between one event pair, barrier + synchronize on both sides —
+    # measured N_REGIONS times (a 20-step region of a 14 us step is a 0.3 ms sample); the line reports the MEDIAN region
+    # (max over ranks per region) and lists them all.
+    launches0 = model.kernel_launches
+    regions = [time_stream(model, d_in_all, d_ll_all, d_g_all, n, args.steps, warm if r == 0 else 3, torch, flush,
+                           first=r * (args.steps + 3), barrier=barrier) for r in range(N_REGIONS)]
+    launches = (model.kernel_launches - launches0 - warm - 3 * (N_REGIONS - 1)) // N_REGIONS
     torch.cuda.synchronize()
     if world > 1:
-        dist.barrier()
-    launches = model.kernel_launches - launches0 - warm
-    t_dev = t_region_ms * 1e-3
+        rt = torch.tensor(regions, dtype=torch.float64, device="cuda")
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        regions = [float(v) for v in rt]
+    t_dev = float(np.median(regions)) * 1e-3
     # secondary: every launch alone between its own event pair, L2 flushed before each (latency of one cold call)
     ms = time_device(model, d_in, d_ll, d_g, n, max(20, args.steps // 4), 3, torch, None if args.no_flush else flush)
     ms_val = time_device(model, d_in, d_ll, d_g, n, max(20, args.steps // 4), 3, torch, None if args.no_flush else flush, grad=False)
@@ -334,40 +440,51 @@ def main():
     clocks = sampler.stop()
 
     if world > 1:
-        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+        t_e2e = float(tt[0])
+    pt_nccl = c4_parallel_tempering(octo, workloads, torch, dist, rank, world, local) if world > 1 else None
     # sanity: device path and host path agree (set 0 of the pool is the workload itself)
     if not os.environ.get("OCTO_B200_LIB"):
         assert np.array_equal(d_ll.cpu().numpy(), ll_h), "device-resident and host-API results differ"
-        if warm + args.steps <= n_sets or n_sets == 1:
-            assert np.array_equal(d_ll_all[0].cpu().numpy(), ll_h), "timed-region results differ from the host API's"
+        assert np.array_equal(d_ll_all[0].cpu().numpy(), ll_h), "timed-region results differ from the host API's"
 
     if rank == 0:
         pairs_step = n * E * world
         value = pairs_step * args.steps / t_dev
         kern_ms = t_dev / args.steps * 1e3          # average launch duration over the timed region
         peak, peak_how = fp64_peak(local)
-        fl = flops_per_launch(spec, n)
-        achieved = fl / (kern_ms * 1e-3) / 1e12
+        f_exec, f_exec_how = executed_flop_table()
+        fl_exec = flops_per_launch(spec, n, f_exec)             # EXECUTED FP64 flop of one launch: what the roofline fraction is
+        fl_model = flops_per_launch(spec, n)                    # SURVEY's libm-style planning figure, secondary
+        achieved = fl_exec / (kern_ms * 1e-3) / 1e12
         hbm_peak, hbm_how = measured_hbm()
+        traffic, traffic_how = ncu_traffic()
         alg_bytes = 8.0 * (n * n_in * 2 + n) + 8.0 * 6 * E
         line = {
             "metric": "epoch*chain logp-grad evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3,
+            "regions": {"n": N_REGIONS, "ms_per_step": [r / args.steps for r in regions], "reported": "median",
+                        "what": "each region = exactly K steps between one CUDA-event pair (barrier + synchronize on both sides, max "
+                                "over ranks); consecutive steps are INDEPENDENT evaluations (own input and output sets) launched back "
+                                "to back on one stream - the throughput of a batch of independent evaluations, not the latency of a "
+                                "dependent chain (that is hmc_device.us_per_leapfrog)"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: 1 planet, 100 RA/Dec astrometry + 100 star-RV (offset, jitter) epochs x 1024 chains per GPU",
-                       "chains_per_gpu": n, "epochs": E, "n_in": n_in, "launch_geometry": list(model.launch_geometry(n)),
+            "config": {"workload": WORKLOAD, "chains_per_gpu": n, "epochs": E, "n_in": n_in, "launch_geometry": list(model.launch_geometry(n)),
                        "l2": "inputs larger than L2: every timed step reads its own input set and writes its own output set "
                              "(pool of %d sets, %.0f MB > 126 MB L2; one 256 MiB flush before the timed region); the 9.6 KB "
                              "observation tables and the code stay cached, as across a sampler's evaluations" % (n_sets, n_sets * set_bytes / 1e6),
                        "timing": "one CUDA event pair on the launching stream around the K back-to-back launches, barrier + "
                                  "synchronize on both sides, max over ranks; value = pairs x K / region"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         # dram__bytes_read + write of this launch from the committed ncu capture (profiles/r01_ncu_summary.txt)
-                         "traffic": 195840, "peak_source": peak_how, "flop_per_pair": F_ALG,
-                         "executed": {"tflops": flops_per_launch(spec, n, F_EXEC) / (kern_ms * 1e-3) / 1e12,
-                                      "flop_per_pair": F_EXEC, "how": "ncu SASS op counts, see profiles/"},
+                         "what": "EXECUTED FP64 flop of one launch (2 DFMA + DMUL + DADD per pair, counted from this build's SASS) / "
+                                 "the kernel's average launch duration over the timed region / measured DFMA peak",
+                         "flop_per_pair": {k: f_exec[k] for k in ("astrom", "rv_jitter") if k in f_exec}, "flop_source": f_exec_how,
+                         "traffic": traffic, "traffic_source": traffic_how, "peak_source": peak_how,
+                         "frac_cost_model": fl_model / (kern_ms * 1e-3) / 1e12 / peak,
+                         "cost_model": {"tflops": fl_model / (kern_ms * 1e-3) / 1e12, "flop_per_pair": F_ALG,
+                                        "what": "SURVEY.md 8(d) planning weights (libm-style: sincos = 48, div = 8, ...): flop the "
+                                                "kernel does NOT execute; kept as the secondary figure"},
                          "kernel_ms": kern_ms,
                          "kernel_ms_isolated": {"mean": float(np.mean(ms)), "min": float(ms.min()),
                                                 "what": "each launch alone between its own event pair, L2 (code and tables "
@@ -393,6 +510,7 @@ def main():
                               "leapfrogs, even-odd swap round, re-evaluation}, one stream, one synchronisation" % (pt_n, pt_rounds, pt_leap),
                       "us_per_round": t_pt / pt_rounds * 1e6, "mean_swap_accept": float(np.mean(pres["swap_accept"]))},
         "gpu_launches": int(launches),
+        **({"pt_nccl": pt_nccl} if pt_nccl else {}),
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
