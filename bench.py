@@ -110,6 +110,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_host_thread(local_rank, local_world):
+    """Give every rank its own slice of the host cores (all ranks of a box otherwise share one affinity mask and their
+    launch threads migrate and contend: the e2e path is host-bound)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // max(1, local_world))
+        mine = cpus[local_rank * per:(local_rank + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
+
+
 def fp64_peak(device):
     """Measured FP64 FMA peak (TFLOP/s) — MEASURED_PEAKS.json has no FP64 entry."""
     so = os.path.join(ROOT, "profiles", "tools", "libfp64_peak.so")
@@ -345,6 +358,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    pin_host_thread(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -401,7 +415,30 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ll_h, g_h = model.ln_like_and_gradient(x_pin, out=out)
+    t_e2e_sync = time.perf_counter() - t0
+    # the same steps through the asynchronous halves of the call (octo_logp_grad_begin / octo_wait), DEPTH independent
+    # evaluations in flight: every step still copies its inputs host -> device and its (ll, gradient) device -> host
+    # inside the timed region; the copies of one step overlap the kernel of another
+    DEPTH = 3
+    slots = [(model.pinned_empty(x.shape), (model.pinned_empty(n), model.pinned_empty((n, n_in)))) for _ in range(DEPTH)]
+    for xi, _ in slots:
+        xi[...] = x
+    def pipelined(k_steps):
+        pend = []
+        for k in range(k_steps):
+            xi, oi = slots[k % DEPTH]
+            if len(pend) == DEPTH:
+                pend.pop(0).wait()
+            pend.append(model.ln_like_and_gradient_begin(xi, out=oi))
+        for h in pend:
+            h.wait()
+    pipelined(max(3, min(args.warmup, 10)))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pipelined(args.steps)
     t_e2e = time.perf_counter() - t0
+    assert np.array_equal(slots[0][1][0], ll_h) and np.array_equal(slots[(args.steps - 1) % DEPTH][1][1], g_h)
     # the same call with ordinary (pageable) numpy arrays, staged through the library's pinned buffers
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -494,9 +531,13 @@ def main():
             "e2e": {"value": pairs_step * args.steps / t_e2e, "unit": "evals/s",
                     "h2d_bytes_per_step": n * n_in * 8, "d2h_bytes_per_step": n * (n_in + 1) * 8,
                     "ms_per_step": t_e2e / args.steps * 1e3,
+                    "ms_per_step_synchronous_call": t_e2e_sync / args.steps * 1e3,
                     "ms_per_step_pageable_host_arrays": t_e2e_pageable / args.steps * 1e3,
-                    "api": "LogDensityModel.ln_like_and_gradient(pinned host ndarray, out=pinned) -> C ABI octo_logp_grad: "
-                           "H2D + kernel + D2H + stream sync per step"},
+                    "in_flight": DEPTH,
+                    "api": "LogDensityModel.ln_like_and_gradient_begin(pinned host ndarray, out=pinned).wait() -> C ABI "
+                           "octo_logp_grad_begin / octo_wait, %d independent evaluations in flight: every step does its own H2D of the "
+                           "inputs, kernel, D2H of (ll, gradient); `ms_per_step_synchronous_call` is one blocking octo_logp_grad "
+                           "per step (the latency of a single call)" % DEPTH},
             "value_only": {"what": "K1v, logp without gradient (Pigeons slice sampler / prior search), same workload, device-resident",
                        "value": n * E * world / (float(np.mean(ms_val)) * 1e-3), "unit": "evals/s", "ms_per_step": float(np.mean(ms_val))},
         "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "

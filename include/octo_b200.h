@@ -184,6 +184,20 @@ int  octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld
                     double* ll, double* g_in);
 
 /*
+ * The same two calls split in two, so that the caller overlaps its own host work with the GPU: the Julia glue evaluates
+ * the "rest" model (priors, user likelihoods: ForwardDiff on the CPU) between begin and wait, and a batch of independent
+ * evaluations keeps several tickets in flight (copy-in of one overlaps the kernel of another; each ticket has a stream
+ * of its own).  begin enqueues copy-in, kernel and copy-out and returns at once; `in` must stay untouched and `ll` /
+ * `g_in` unread until octo_wait(ticket) returned (it also frees the ticket).  octo_ready: 1 finished, 0 still running,
+ * negative on error — never blocks.  g_in may be NULL (value only).  Buffers from octo_alloc_pinned avoid staging.
+ */
+typedef struct OctoTicket OctoTicket;
+int  octo_logp_grad_begin(OctoCtx* ctx, const double* in, int64_t n_chains, int64_t ld, double* ll, double* g_in,
+                          OctoTicket** ticket);
+int  octo_ready(OctoTicket* ticket);
+int  octo_wait(OctoTicket* ticket);
+
+/*
  * ---- Standard parameterisation on the device ------------------------------------------------
  * Optional: describe how the sampler's unconstrained vector θ_t (length D) maps to natural-space parameters, their
  * priors, and the kernel inputs, and the library evaluates the whole log-posterior of the standard model families
@@ -226,6 +240,9 @@ int  octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D,
 /* θ_t: HOST column-major [n_chains x D] (leading dimension ld); lp[n_chains]; g_t [n_chains x D] or NULL.
  * What `ℓπcallback` / `∇ℓπcallback` return (src/logdensitymodel.jl:110-146, 169-177) for such a model. */
 int  octo_logpost_grad(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* lp, double* g_t);
+/* asynchronous half of octo_logpost_grad (see octo_logp_grad_begin); finish with octo_wait */
+int  octo_logpost_grad_begin(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* lp, double* g_t,
+                             OctoTicket** ticket);
 /* Same on DEVICE buffers, enqueued on `stream`; d_work is caller-provided scratch of
  * octo_logpost_workspace(ctx, n_chains) bytes.  Normally the parameterisation runs inside the likelihood kernel
  * (one launch; the workspace size is 0 and d_work may be NULL); models the fused stage cannot hold (more than 8

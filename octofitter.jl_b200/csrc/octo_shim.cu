@@ -357,13 +357,24 @@ int logpost_enqueue(OctoCtx* ctx, Workspace* w, const double* d_theta, int64_t n
     return OCTO_OK;
 }
 
-// One synchronous evaluation with host buffers.  post = false: `in` are the kernel inputs [n x n_in] (octo_logp[_grad]);
-// post = true: θ_t [n x D] -> log posterior (octo_logpost_grad).  Gradient columns = input columns in both cases.
-// post_mode 1 (post only, value-only): the likelihood part, ln_like(system, arr2nt(invlink(θ_t))).
-int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g,
-             int post_mode = 0) {
+// One evaluation with host buffers, in two halves so that callers can overlap their own work (or further evaluations)
+// with it: begin_host leases a workspace (a stream of its own) and enqueues copy-in, kernel(s) and copy-out;
+// finish_host waits for that stream, hands staged results to the caller's buffers and returns the workspace to the pool.
+// post = false: `in` are the kernel inputs [n x n_in] (octo_logp[_grad]); post = true: θ_t [n x D] -> log posterior
+// (octo_logpost_grad).  Gradient columns = input columns in both cases.  post_mode 1 (post only, value-only): the
+// likelihood part, ln_like(system, arr2nt(invlink(θ_t))).
+struct Pending {
+    OctoCtx* ctx = nullptr; Workspace* w = nullptr;
+    bool staged_out = false, grad = false;
+    double *ll = nullptr, *g = nullptr;
+    int64_t n = 0, ld = 0; int nc = 0;
+};
+
+int begin_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g,
+               int post_mode, Pending* P) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");
     if (post && !ctx->d_param) return fail(OCTO_ERR_STATE, "octo_set_parameterization has not been called");
+    P->ctx = ctx; P->w = nullptr; P->n = n;
     if (n == 0) return OCTO_OK;
     if (!in || !ll || (grad && !g) || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
     CU(cudaSetDevice(ctx->device));
@@ -413,15 +424,33 @@ int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, in
             e = cudaMemcpyAsync(w->h_out, d_ll, col * (grad ? nc + 1 : 1), cudaMemcpyDeviceToHost, w->stream);
             if (e != cudaSuccess) { rc = fail_cuda(e, "D2H"); break; }
         }
-        e = cudaStreamSynchronize(w->stream);
-        if (e != cudaSuccess) { rc = fail_cuda(e, "kernel execution"); break; }
-        if (!direct_out) {
-            memcpy(ll, w->h_out, col);
-            if (grad) for (int k = 0; k < nc; ++k) memcpy(g + (size_t)k * ld, w->h_out + n + (size_t)k * n, col);
-        }
+        P->w = w; P->staged_out = !direct_out; P->grad = grad; P->ll = ll; P->g = g; P->ld = ld; P->nc = nc;
     } while (0);
-    release(ctx, w);
+    if (rc) { cudaStreamSynchronize(w->stream); release(ctx, w); }
     return rc;
+}
+
+int finish_host(Pending* P) {
+    if (!P->w) return OCTO_OK;                         // empty batch
+    Workspace* w = P->w;
+    int rc = OCTO_OK;
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) rc = fail_cuda(e, "kernel execution");
+    else if (P->staged_out) {
+        const size_t col = (size_t)P->n * sizeof(double);
+        memcpy(P->ll, w->h_out, col);
+        if (P->grad) for (int k = 0; k < P->nc; ++k) memcpy(P->g + (size_t)k * P->ld, w->h_out + P->n + (size_t)k * P->n, col);
+    }
+    release(P->ctx, w);
+    P->w = nullptr;
+    return rc;
+}
+
+int run_host(OctoCtx* ctx, bool post, bool grad, const double* in, int64_t n, int64_t ld, double* ll, double* g,
+             int post_mode = 0) {
+    Pending P;
+    if (int rc = begin_host(ctx, post, grad, in, n, ld, ll, g, post_mode, &P)) return rc;
+    return finish_host(&P);
 }
 
 }  // namespace
@@ -706,6 +735,40 @@ void octo_destroy(OctoCtx* ctx) {
 
 int octo_logp(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll) { return run_host(ctx, false, false, in, n, ld, ll, nullptr); }
 int octo_logp_grad(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll, double* g) { return run_host(ctx, false, true, in, n, ld, ll, g); }
+
+// ---- asynchronous halves of the host-buffer entry points
+struct OctoTicket { Pending p; };
+
+static int begin_ticket(OctoCtx* ctx, bool post, const double* in, int64_t n, int64_t ld, double* out, double* g, OctoTicket** ticket) {
+    if (!ticket) return fail(OCTO_ERR_ARG, "ticket is null");
+    *ticket = nullptr;
+    OctoTicket* t = new OctoTicket();
+    if (int rc = begin_host(ctx, post, g != nullptr, in, n, ld, out, g, 0, &t->p)) { delete t; return rc; }
+    *ticket = t;
+    return OCTO_OK;
+}
+int octo_logp_grad_begin(OctoCtx* ctx, const double* in, int64_t n, int64_t ld, double* ll, double* g_in, OctoTicket** ticket) {
+    return begin_ticket(ctx, false, in, n, ld, ll, g_in, ticket);
+}
+int octo_logpost_grad_begin(OctoCtx* ctx, const double* theta_t, int64_t n, int64_t ld, double* lp, double* g_t, OctoTicket** ticket) {
+    return begin_ticket(ctx, true, theta_t, n, ld, lp, g_t, ticket);
+}
+int octo_ready(OctoTicket* t) {
+    if (!t) return -OCTO_ERR_ARG;
+    if (!t->p.w) return 1;
+    cudaError_t e = cudaStreamQuery(t->p.w->stream);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    fail_cuda(e, "cudaStreamQuery");
+    return -OCTO_ERR_CUDA;
+}
+int octo_wait(OctoTicket* t) {
+    if (!t) return fail(OCTO_ERR_ARG, "null ticket");
+    if (t->p.ctx) cudaSetDevice(t->p.ctx->device);
+    const int rc = finish_host(&t->p);
+    delete t;
+    return rc;
+}
 
 int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t ld, double* d_ll, double* d_g, void* stream) {
     if (!ctx) return fail(OCTO_ERR_ARG, "null context");

@@ -498,6 +498,23 @@ def _ptr(a):
     return getattr(a, "_octo_ptr", None) or a.ctypes.data
 
 
+class _Pending:
+    """An evaluation in flight (octo_*_begin): keeps the buffers alive; `ready()` polls, `wait()` blocks and returns."""
+
+    def __init__(self, model, ticket, bufs, single):
+        self._model, self._t, self._bufs, self._single = model, ticket, bufs, single
+
+    def ready(self):
+        return self._t is None or self._model._lib.octo_ready(self._t) != 0
+
+    def wait(self):
+        if self._t is not None:
+            t, self._t = self._t, None
+            self._model._check(self._model._lib.octo_wait(t))
+        _, a, g = self._bufs
+        return (a[0], g[0]) if self._single else (a, g)
+
+
 class LogDensityModel:
     """The sampler-facing surface for the offloaded terms (src/logdensitymodel.jl:5-24, 252-256),
     backed by libocto_b200.so on one CUDA device."""
@@ -607,6 +624,33 @@ class LogDensityModel:
                 raise ValueError("out must be (ll[n], g[n, n_in]) with g column-major")
         self._check(self._lib.octo_logp_grad(self._h, _ptr(x), n, n, _ptr(ll), _ptr(g)))
         return (ll[0], g[0]) if single else (ll, g)
+
+    def ln_like_and_gradient_begin(self, theta, out=None):
+        """Asynchronous half of `ln_like_and_gradient` (C ABI `octo_logp_grad_begin`): enqueues copy-in, kernel and
+        copy-out on a stream of its own and returns a handle at once; `handle.wait()` returns (ll, g).  Several handles
+        may be in flight: a batch of independent evaluations overlaps the copies of one with the kernel of another, and a
+        sampler can do its host-side work (priors, Jacobians) while the GPU evaluates."""
+        x, single = self._as_in(theta)
+        n = x.shape[0]
+        if out is None:
+            ll, g = np.empty(n), np.empty((n, self.n_in), order="F")
+        else:
+            ll, g = out
+        t = C.c_void_p()
+        self._check(self._lib.octo_logp_grad_begin(self._h, _ptr(x), n, n, _ptr(ll), _ptr(g), C.byref(t)))
+        return _Pending(self, t, (x, ll, g), single)
+
+    def ℓπcallback_grad_begin(self, theta_t, out=None):
+        """Asynchronous half of `ℓπcallback_grad` (C ABI `octo_logpost_grad_begin`)."""
+        th, single = self._as_theta(theta_t)
+        n = th.shape[0]
+        if out is None:
+            lp, g = np.empty(n), np.empty((n, self.D), order="F")
+        else:
+            lp, g = out
+        t = C.c_void_p()
+        self._check(self._lib.octo_logpost_grad_begin(self._h, _ptr(th), n, n, _ptr(lp), _ptr(g), C.byref(t)))
+        return _Pending(self, t, (th, lp, g), single)
 
     # -- sampler-facing surface when the model was given priors (src/logdensitymodel.jl:110-146, 169-177, 252-256)
     def _as_theta(self, theta_t):

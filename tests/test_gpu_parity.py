@@ -555,3 +555,39 @@ def test_pointwise_like_more_epochs_than_one_grid(oracle_lib):
     for e in (0, 65_534, 65_535, 65_536, 69_999):
         ll_o = oracle_lib.Oracle(_single_epoch_model(spec, e), consts).logp(x)
         assert rel_err(LL[:, e], ll_o).max() < LOGP_RTOL, e
+
+
+def test_asynchronous_halves_of_the_host_call(oracle_lib):
+    """octo_logp_grad_begin / octo_ready / octo_wait (and the log-posterior pair): several evaluations in flight on
+    their own streams give the bits of the blocking calls; pageable and pinned buffers; an empty batch."""
+    import ctypes as C
+    spec, x = workloads.config("C2")
+    model = octo.LogDensityModel(spec)
+    ref = model.ln_like_and_gradient(x)
+    xs = [np.asfortranarray(x[: 1024 - 37 * k]) for k in range(5)]
+    pend = [model.ln_like_and_gradient_begin(xi) for xi in xs]
+    for xi, h in zip(xs, pend):
+        ll, g = h.wait()
+        assert h.ready()
+        assert np.array_equal(ll, ref[0][: xi.shape[0]]) and np.array_equal(g, ref[1][: xi.shape[0]])
+    xp = model.pinned_empty(x.shape); xp[...] = x
+    out = (model.pinned_empty(x.shape[0]), model.pinned_empty(x.shape))
+    h = model.ln_like_and_gradient_begin(xp, out=out)
+    ll, g = h.wait()
+    assert np.array_equal(ll, ref[0]) and np.array_equal(g, ref[1])
+    t = C.c_void_p()
+    assert model._lib.octo_logp_grad_begin(model._h, None, 0, 0, None, None, C.byref(t)) == 0
+    assert model._lib.octo_ready(t) == 1 and model._lib.octo_wait(t) == 0
+    assert model._lib.octo_logp_grad_begin(model._h, None, 5, 5, None, None, C.byref(t)) != 0      # bad buffers
+    model.close()
+    import helpers
+    spec_p = octo.ModelSpec(helpers.reference_test_system())
+    mp_ = octo.LogDensityModel(spec_p)
+    rng = np.random.default_rng(2)
+    th = rng.normal(0, 0.8, (65, 11)); th[:, 1] = np.log(50.0 - 0.1) + 1e-3 * rng.standard_normal(65)
+    lp0, g0 = mp_.ℓπcallback_grad(th)
+    hs = [mp_.ℓπcallback_grad_begin(th) for _ in range(3)]
+    for h in hs:
+        lp, g = h.wait()
+        assert np.array_equal(lp, lp0) and np.array_equal(g, g0)
+    mp_.close()
