@@ -26,6 +26,8 @@
  *    an N x n_in Matrix{Float64} and makes chain the coalesced index on device.
  *  - Every entry point returns 0 on success, non-zero on error; the message is
  *    in octo_last_error() (thread-local). No C++ exception crosses the ABI.
+ *  - Tables are validated at octo_create: non-finite epochs / data, uncertainties that are not finite and > 0, or
+ *    |cor| > 1 - 1e-5 (the reference ctor's own check) are OCTO_ERR_ARG — they would make every chain NaN.
  *  - Numerical invalidity is NOT an error: a chain whose inputs are non-finite
  *    or have e outside [0,1), a <= 0, M <= 0 or plx <= 0 gets ll = -Inf and a
  *    zero gradient row (reference: non-finite θ => -Inf, logdensitymodel.jl:120-124;
@@ -300,6 +302,11 @@ void  octo_free_pinned(void* p);
  * synchronises. g_in may be NULL for value only. */
 int  octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n_chains, int64_t ld,
                            double* d_ll, double* d_g_in, void* stream);
+
+/* The device-buffer entry points keep a small workspace (cross-CTA partials, tickets) per caller stream; calls on one
+ * stream may come from several host threads (enqueueing is serialised per stream).  Release it before destroying the
+ * stream — a recycled stream handle would inherit it.  Waits for the stream's pending work. */
+int  octo_release_stream(OctoCtx* ctx, void* stream);
 
 /* Diagnostic: run only the device Kepler solve (rem2pi + Markley) on n (mean anomaly, e) pairs
  * and return sin E, cos E.  HOST buffers.  Used by the test-suite to probe e -> 1, M -> 0, |M| = pi. */

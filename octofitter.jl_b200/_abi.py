@@ -139,6 +139,7 @@ def load_library(path: str | None = None):
     lib.octo_destroy.restype = None
     lib.octo_logp.argtypes = [vp, vp, i64, i64, vp]
     lib.octo_logp_grad.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.octo_release_stream.argtypes = [vp, vp]
     lib.octo_logp_grad_begin.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(vp)]
     lib.octo_logpost_grad_begin.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(vp)]
     lib.octo_ready.argtypes = [vp]
@@ -191,4 +192,4 @@ EXPORTED_SYMBOLS = (
     "octo_logp_grad_device", "octo_set_parameterization", "octo_logpost_grad", "octo_logpost_workspace",
     "octo_logpost_grad_device", "octo_loglike_theta", "octo_logp_pointwise", "octo_hmc_run", "octo_pt_hmc_run", "octo_hmc_random", "octo_invlink", "octo_alloc_pinned", "octo_free_pinned", "octo_selftest_kepler", "octo_n_in", "octo_n_planets", "octo_total_epochs", "octo_device",
     "octo_kernel_launches", "octo_launch_geometry", "octo_pt_unique_id", "octo_pt_init", "octo_pt_swap_round",
-    "octo_pt_decide", "octo_pt_finalize", "octo_pt_swap_round_device", "octo_pt_hmc_run_dist", "octo_logp_grad_begin", "octo_logpost_grad_begin", "octo_ready", "octo_wait", "octo_last_error")
+    "octo_pt_decide", "octo_pt_finalize", "octo_pt_swap_round_device", "octo_pt_hmc_run_dist", "octo_logp_grad_begin", "octo_logpost_grad_begin", "octo_ready", "octo_wait", "octo_release_stream", "octo_last_error")

@@ -38,6 +38,7 @@ struct Workspace {
     size_t cap_theta = 0, cap_post = 0;
     size_t cap_in = 0, cap_ll = 0, cap_g = 0, cap_partial = 0, cap_tickets = 0, cap_hin = 0, cap_hout = 0;
     bool busy = false;
+    std::mutex mu;        // device-buffer entry points: two host threads may enqueue on the same caller stream
 };
 
 // minimal NCCL surface, resolved with dlopen so the library has no link-time NCCL dependency
@@ -649,11 +650,20 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         const bool astrom = (B.kind <= OCTO_KIND_ASTROM_PASEP);
         for (int k = 0; k < B.n_epochs; ++k) {
             const size_t o = (size_t)D.start + k;
+            // a zero / negative / non-finite uncertainty or a non-finite datum would turn EVERY chain into NaN without an
+            // error (inf weights, NaN normalisation): refuse the table instead
+            const bool fin = std::isfinite(B.epoch[k]) && std::isfinite(B.y1[k]) && std::isfinite(B.s1[k]) && B.s1[k] > 0.0 &&
+                             (!astrom || (std::isfinite(B.y2[k]) && std::isfinite(B.s2[k]) && B.s2[k] > 0.0));
+            if (!fin) {
+                delete ctx;
+                return fail(OCTO_ERR_ARG, "table " + std::to_string(b) + ", row " + std::to_string(k) + ": epochs and data must be finite, uncertainties finite and > 0");
+            }
             t[o] = B.epoch[k]; y1[o] = B.y1[k];
             if (astrom) {
                 y2[o] = B.y2[k];
                 const double s1 = B.s1[k], s2 = B.s2[k], cor = D.has_cor ? B.cor[k] : 0.0;
-                if (std::fabs(cor) >= 1.0) { delete ctx; return fail(OCTO_ERR_ARG, "|cor| >= 1 (relative-astrometry.jl:69-71)"); }
+                // the reference ctor rejects |cor| > 1 - 1e-5 ("may not be well-specified", relative-astrometry.jl:69-71)
+                if (!(std::fabs(cor) <= 1.0 - 1e-5)) { delete ctx; return fail(OCTO_ERR_ARG, "|cor| > 1 - 1e-5 (relative-astrometry.jl:69-71)"); }
                 if (B.kind == OCTO_KIND_ASTROM_RADEC && D.idx_platescale < 0 && D.idx_northangle < 0) {
                     // the reference pushes the data through atan/hypot/cos/sin even with platescale = 1,
                     // northangle = 0 (relative-astrometry.jl:209-213): reproduce that <= 2 ulp perturbation here
@@ -776,7 +786,26 @@ int octo_logp_grad_device(OctoCtx* ctx, const double* d_in, int64_t n, int64_t l
     if (!d_in || !d_ll || n < 0 || ld < n) return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);   // partial buffer + tickets of this stream
+    std::lock_guard<std::mutex> lk(w->mu);                        // growing them and launching is one critical section
     return enqueue(ctx, w, d_g != nullptr, d_in, n, ld, d_ll, d_g, ld, (cudaStream_t)stream);
+}
+
+// drop the workspace the device-buffer entry points keep for a caller stream (call it before destroying the stream: a
+// recycled stream handle would otherwise inherit it).  Waits for the stream's pending work first.
+int octo_release_stream(OctoCtx* ctx, void* stream) {
+    if (!ctx) return fail(OCTO_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    Workspace* w = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t i = 0; i < ctx->stream_ws.size(); ++i)
+            if (ctx->stream_ws[i].first == (cudaStream_t)stream) { w = ctx->stream_ws[i].second; ctx->stream_ws.erase(ctx->stream_ws.begin() + i); break; }
+    }
+    if (!w) return OCTO_OK;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    { std::lock_guard<std::mutex> lk(w->mu); }
+    free_ws(w);
+    return OCTO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -926,6 +955,7 @@ int octo_logpost_grad_device(OctoCtx* ctx, const double* d_theta, int64_t n, int
         return fail(OCTO_ERR_ARG, "bad buffers / leading dimension");
     CU(cudaSetDevice(ctx->device));
     Workspace* w = stream_workspace(ctx, (cudaStream_t)stream);
+    std::lock_guard<std::mutex> lk(w->mu);
     return logpost_enqueue(ctx, w, d_theta, n, ld, d_lp, d_g_t, ld, (double*)d_work, (cudaStream_t)stream);
 }
 

@@ -145,8 +145,9 @@ def octofit(model, rng=None, *, n_chains=256, adaptation=300, iterations=300, ta
     step size + a metric estimated in expanding windows).  Here `n_chains` chains of static-trajectory HMC run in
     lockstep on the device (`octo_hmc_run`): start = best of `n_init` prior draws (guess_starting_position,
     src/initialization.jl:14-66) plus a small scatter; adaptation = `windows` expanding windows, after each of which the
-    diagonal inverse mass is set to the pooled per-coordinate variance of the window's draws and the step size is
-    rescaled towards `target_accept`; then `iterations` sampling transitions.  Returns a dict like the reference's chain:
+    diagonal inverse mass is set to the pooled per-coordinate variance of ALL the window's draws and the step size is
+    rescaled towards `target_accept`, then a short terminal window that re-tunes the step size at the final metric (as
+    Stan's does); then `iterations` sampling transitions.  Returns a dict like the reference's chain:
     `theta_t` / `theta` (natural space) [iterations, n_chains, D], `logpost`, `names`, and an `info` dict with the
     acceptance rate, the adapted step size / inverse mass and the gradient-call count."""
     rng = np.random.default_rng() if rng is None else rng
@@ -159,29 +160,34 @@ def octofit(model, rng=None, *, n_chains=256, adaptation=300, iterations=300, ta
     eps, calls = 0.1, 0
     # expanding windows (Stan: each twice the previous); every window ends with a metric and step-size update
     sizes = np.maximum(1, (adaptation * 2.0 ** np.arange(windows) / (2.0 ** windows - 1)).astype(int))
+    def tune(n_it, tag, sub):
+        nonlocal th, eps, calls
+        r = device_hmc(model, th, n_it, step_size=eps, n_leapfrog=n_leapfrog, inv_mass=inv_mass, seed=seed + 1000 * tag + sub)
+        calls += r["n_gradient_calls"]
+        th = r["theta_final"]
+        eps *= float(np.clip(np.exp(1.5 * (r["accept_rate"] - target_accept)), 0.5, 2.0))
+        if verbosity >= 2:
+            print(f"adapt window {tag}.{sub}: {n_it} it, accept {r['accept_rate']:.2f}, step {eps:.3g}")
+        return r
     for k, w in enumerate(sizes):
-        # a few short runs inside the window tune the step size at the current metric
-        for sub in range(3):
-            n_it = max(1, int(w) // 3)
-            r = device_hmc(model, th, n_it, step_size=eps, n_leapfrog=n_leapfrog, inv_mass=inv_mass, seed=seed + 1000 * k + sub)
-            calls += r["n_gradient_calls"]
-            th = r["theta_final"]
-            acc = r["accept_rate"]
-            eps *= float(np.clip(np.exp(1.5 * (acc - target_accept)), 0.5, 2.0))
-            if verbosity >= 2:
-                print(f"adapt window {k}.{sub}: {n_it} it, accept {acc:.2f}, step {eps:.3g}")
-        draws = r["theta"].reshape(-1, D)
+        # a few short runs inside the window tune the step size at the current metric; the metric update at the end of
+        # the window pools the draws of ALL of them
+        pooled = [tune(max(1, int(w) // 3), k, sub)["theta"].reshape(-1, D) for sub in range(3)]
+        draws = np.concatenate(pooled, axis=0)
         var = draws.var(axis=0)
         if np.all(np.isfinite(var)) and np.all(var > 0):
             # Stan's regularisation of the variance estimate
             nw = draws.shape[0]
             inv_mass = (nw / (nw + 5.0)) * var + 1e-3 * (5.0 / (nw + 5.0))
+    # terminal fast window (Stan's): the step size was tuned for the previous metric — re-tune it at the final one
+    for sub in range(3):
+        tune(max(2, int(sizes[0])), windows, sub)
     r = device_hmc(model, th, iterations, step_size=eps, n_leapfrog=n_leapfrog, inv_mass=inv_mass, seed=seed + 999_983)
     calls += r["n_gradient_calls"]
     theta_t = r["theta"]
     nat = model.invlink(theta_t.reshape(-1, D)).reshape(theta_t.shape)
     return {"theta_t": theta_t, "theta": nat, "logpost": r["logpost"], "names": model.spec.theta_names,
-            "info": {"sampler": "device_hmc", "n_chains": n_chains, "adaptation": int(sizes.sum()), "iterations": iterations,
+            "info": {"sampler": "device_hmc", "n_chains": n_chains, "adaptation": int(sizes.sum()) + 3 * max(2, int(sizes[0])), "iterations": iterations,
                      "accept_rate": r["accept_rate"], "step_size": eps, "inv_mass": inv_mass, "n_leapfrog": n_leapfrog,
                      "n_gradient_calls": calls, "seed": seed}}
 

@@ -591,3 +591,61 @@ def test_asynchronous_halves_of_the_host_call(oracle_lib):
         lp, g = h.wait()
         assert np.array_equal(lp, lp0) and np.array_equal(g, g0)
     mp_.close()
+
+
+def test_tables_are_validated_at_create():
+    """A zero / negative / non-finite uncertainty, a non-finite datum or epoch, |cor| > 1 - 1e-5 (the reference ctor's own
+    check, relative-astrometry.jl:69-71) are refused with OCTO_ERR_ARG instead of turning every chain into NaN."""
+    import ctypes as C
+    lib = octo.load_library()
+    consts = octo.default_constants()
+    base = dict(epoch=[50000.0, 50100.0], ra=[100.0, 90.0], dec=[-50.0, -40.0], σ_ra=[2.0, 2.0], σ_dec=[3.0, 3.0])
+    for col, bad in (("σ_ra", 0.0), ("σ_dec", -1.0), ("σ_ra", np.nan), ("ra", np.inf), ("epoch", np.nan), ("cor", 0.999995)):
+        cols = dict(base); cols.setdefault("cor", [0.0, 0.0])
+        cols[col] = [cols[col][0], bad]
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tab = {k: np.asarray(v, dtype=np.float64) for k, v in cols.items()}
+        layout = {"n_in": 8, "planets": [{"M": 0, "plx": 1, "a": 2, "e": 3, "i": 4, "w": 5, "W": 6, "tp": 7, "mass": -1}]}
+        blk = {"kind": 0, "planet": 0, "epoch": tab["epoch"], "y1": tab["ra"], "y2": tab["dec"], "s1": tab["σ_ra"], "s2": tab["σ_dec"], "cor": tab["cor"]}
+        packed = octo.pack(layout, [blk])
+        h = C.c_void_p()
+        rc = lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h))
+        assert rc == 1 and not h.value, (col, bad)
+        assert b"table 0" in lib.octo_last_error() or b"cor" in lib.octo_last_error()
+    # the RV uncertainty too
+    blk = {"kind": 2, "planet": -1, "epoch": [50000.0], "y1": [3.0], "s1": [0.0], "idx_offset": -1, "idx_jitter": -1}
+    layout = {"n_in": 9, "planets": [{"M": 0, "plx": 1, "a": 2, "e": 3, "i": 4, "w": 5, "W": 6, "tp": 7, "mass": 8}]}
+    packed = octo.pack(layout, [blk])
+    h = C.c_void_p()
+    assert lib.octo_create(C.byref(consts), C.byref(packed.layout), packed.blocks, packed.n_blocks, 0, C.byref(h)) == 1
+
+
+def test_release_stream_and_threads_sharing_a_caller_stream():
+    """Device-buffer entry point: several host threads enqueue on the SAME caller stream (serialised per stream by the
+    library); octo_release_stream drops the stream's workspace."""
+    import threading
+    import torch
+    spec, x = workloads.one_planet(600, 0, 40, seed=9)        # few chains, many epochs: uses the per-stream partial buffer
+    model = octo.LogDensityModel(spec)
+    ref = model.ln_like_and_gradient(x)
+    n, n_in = x.shape
+    d_in = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    st = torch.cuda.Stream()
+    outs = [(torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty((n_in, n), dtype=torch.float64, device="cuda")) for _ in range(6)]
+
+    def work(k):
+        for _ in range(25):
+            model.enqueue_device(d_in.data_ptr(), n, n, outs[k][0].data_ptr(), outs[k][1].data_ptr(), st.cuda_stream)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    [t.start() for t in th]; [t.join() for t in th]
+    st.synchronize()
+    for ll, g in outs:
+        assert np.array_equal(ll.cpu().numpy(), ref[0]) and np.array_equal(g.cpu().numpy().T, ref[1])
+    assert model._lib.octo_release_stream(model._h, st.cuda_stream) == 0
+    assert model._lib.octo_release_stream(model._h, st.cuda_stream) == 0          # idempotent
+    model.enqueue_device(d_in.data_ptr(), n, n, outs[0][0].data_ptr(), outs[0][1].data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(outs[0][0].cpu().numpy(), ref[0])
+    model.close()
