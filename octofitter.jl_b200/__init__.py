@@ -14,6 +14,6 @@ from .model import (Normal, Uniform, LogUniform, Sine, truncated, UniformCircula
                     StarAbsoluteRVLikelihood, MarginalizedStarAbsoluteRVObs, MarginalizedStarAbsoluteRVLikelihood,
                     PlanetRelativeRVObs, PlanetRelativeRVLikelihood, Planet, System, ModelSpec, LogDensityModel, OctoError)
 from .pt import ParallelTempering
-from .samplers import batched_hmc, batched_parallel_tempering, device_hmc, device_parallel_tempering, device_parallel_tempering_dist, diagonal_metric, hmc_random, octofit, octofit_rejection
+from .samplers import batched_hmc, batched_parallel_tempering, batched_slice_sampler, batched_slice_parallel_tempering, device_hmc, device_parallel_tempering, device_parallel_tempering_dist, diagonal_metric, hmc_random, octofit, octofit_rejection
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -668,12 +668,45 @@ class LogDensityModel:
             raise ValueError(f"expected (n_chains, {self.D}) unconstrained parameters, got {th.shape}")
         return np.asfortranarray(th), single
 
+    # -- non-epoch terms that stay on the host: UserLikelihood / DirectLLObs (src/variables.jl:332-451),
+    #    PlanetOrderPrior / NonCrossingPrior / HillStabilityPrior (src/likelihoods/prior-*.jl) are arbitrary user code in
+    #    the reference; here they are host callbacks added to the device posterior
+    def add_host_term(self, fn):
+        """Register `fn(theta_nat) -> (value[n], grad_nat[n, D])`: a per-chain log-density term of the NATURAL-space
+        parameters (rows of `invlink(θ_t)`, the order of `theta_names`) evaluated on the host, e.g. a `UserLikelihood`
+        or a planet-order prior; `grad_nat` may be None for terms only used value-only.  `ℓπcallback[_grad]` add it (and
+        its gradient through the bijectors) to the device result; with the asynchronous halves of the call it is evaluated
+        while the GPU works."""
+        if self.spec.priors is None:
+            raise OctoError("host terms are added to the device posterior: build the model with priors")
+        self._host_terms = getattr(self, "_host_terms", []) + [fn]
+
+    def _host_value_grad(self, th, grad):
+        """Σ host terms at θ_t (and ∇ w.r.t. θ_t: the natural-space gradient times d invlink / d θ_t, by central
+        differences of the monotone scalar bijectors — they are elementwise)."""
+        nat = self.invlink(th)
+        val = np.zeros(th.shape[0]); g = np.zeros(th.shape) if grad else None
+        for fn in self._host_terms:
+            v, gn = fn(nat)
+            val += np.asarray(v, dtype=np.float64)
+            if grad:
+                if gn is None:
+                    raise OctoError("a host term without gradient cannot be used by ℓπcallback_grad")
+                g += np.asarray(gn, dtype=np.float64)
+        if grad:
+            h = 1e-6 * np.maximum(1.0, np.abs(th))
+            dxdy = (self.invlink(th + h) - self.invlink(th - h)) / (2 * h)
+            g = g * dxdy
+        return val, g
+
     def ℓπcallback(self, theta_t):
         """log-posterior of the unconstrained vector(s) θ_t: priors + bijector Jacobians + likelihood, on device."""
         th, single = self._as_theta(theta_t)
         n = th.shape[0]
         lp = np.empty(n)
         self._check(self._lib.octo_logpost_grad(self._h, th.ctypes.data, n, n, lp.ctypes.data, None))
+        if getattr(self, "_host_terms", None):
+            lp = lp + self._host_value_grad(th, False)[0]
         return lp[0] if single else lp
 
     def ℓπcallback_grad(self, theta_t, out=None):
@@ -687,6 +720,17 @@ class LogDensityModel:
             lp, g = out
             if lp.shape != (n,) or g.shape != (n, self.D) or not g.flags.f_contiguous:
                 raise ValueError("out must be (lp[n], g[n, D]) with g column-major")
+        if getattr(self, "_host_terms", None):
+            # device evaluation in flight while the host evaluates its own terms (octo_logpost_grad_begin / octo_wait)
+            t = C.c_void_p()
+            self._check(self._lib.octo_logpost_grad_begin(self._h, _ptr(th), n, n, _ptr(lp), _ptr(g), C.byref(t)))
+            try:
+                hv, hg = self._host_value_grad(th, True)
+            finally:
+                self._check(self._lib.octo_wait(t))
+            ok = np.isfinite(lp)
+            lp += np.where(ok, hv, 0.0); g += np.where(ok[:, None], hg, 0.0)
+            return (lp[0], g[0]) if single else (lp, g)
         self._check(self._lib.octo_logpost_grad(self._h, _ptr(th), n, n, _ptr(lp), _ptr(g)))
         return (lp[0], g[0]) if single else (lp, g)
 

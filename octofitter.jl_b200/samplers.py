@@ -233,6 +233,97 @@ def batched_parallel_tempering(model, model_ref_logp, pt, theta0, n_rounds, *, s
     return {"theta": th, "swap_accept": np.array(swaps)}
 
 
+def batched_slice_sampler(model, theta0, n_iter, *, rng=None, w=10.0, max_steps=20, n_passes=3, beta=None, keep_samples=True):
+    """Replica-batched, VALUE-ONLY slice sampler over the device log posterior: the explorer the reference gives Pigeons
+    (`Pigeons.default_explorer(::LogDensityModel) = SliceSampler()`, ext/OctofitterPigeonsExt:70-72; Pigeons' defaults
+    w = 10, n_passes = 3).  All replicas move in lockstep: one iteration is `n_passes` sweeps over the D coordinates; a
+    coordinate update is Neal (2003) slice sampling — vertical level, interval by stepping out (at most `max_steps`
+    expansions; Pigeons doubles, which needs an extra acceptance test per proposal — same invariant distribution), then
+    shrinkage — and every evaluation of the interval ends / proposals of ALL replicas is ONE value-only launch (K1v).
+
+    beta: per-replica tempering weights (None = 1): replica r targets prior terms + beta_r * ln_like, the path Pigeons
+    tempers along.  Returns theta [n_iter, n, D] (if kept), the final states, their tempered density, raw ln_like and
+    the number of batched evaluations."""
+    rng = np.random.default_rng() if rng is None else rng
+    th = np.array(theta0, dtype=np.float64, order="F")
+    n, D = th.shape
+    bet = None if beta is None else np.asarray(beta, dtype=np.float64)
+    evals = 0
+
+    def density(q):
+        """tempered log density and raw ln_like of a [m, D] batch (rows beyond n cycle over the replicas)"""
+        nonlocal evals
+        evals += 1
+        lp = model.ℓπcallback(np.asfortranarray(q))
+        if bet is None:
+            return lp, None
+        ll = model.ln_like_of_theta(np.asfortranarray(q))
+        b = np.resize(bet, q.shape[0])
+        with np.errstate(invalid="ignore"):
+            out = np.where(np.isfinite(lp) & np.isfinite(ll), lp - (1.0 - b) * ll, -np.inf)
+        return out, ll
+    cur, cur_ll = density(th)
+    if not np.all(np.isfinite(cur)):
+        raise ValueError("slice sampling needs finite starting densities")
+    out = np.empty((n_iter, n, D)) if keep_samples else None
+    for it in range(n_iter):
+        for _ in range(n_passes):
+            for j in range(D):
+                y = cur - rng.exponential(size=n)                     # log of the vertical level
+                x0 = th[:, j].copy()
+                L = x0 - w * rng.uniform(size=n); R = L + w
+                # stepping out: both ends of every replica in one launch, until they are outside the slice
+                J = np.floor(max_steps * rng.uniform(size=n)).astype(int); K = (max_steps - 1) - J
+                growL, growR = np.ones(n, bool), np.ones(n, bool)
+                while growL.any() or growR.any():
+                    q = np.concatenate([th, th], axis=0)
+                    q[:n, j] = L; q[n:, j] = R
+                    f, _ = density(q)
+                    insideL, insideR = f[:n] > y, f[n:] > y
+                    growL &= insideL & (J > 0); growR &= insideR & (K > 0)
+                    L = np.where(growL, L - w, L); J = J - growL
+                    R = np.where(growR, R + w, R); K = K - growR
+                # shrinkage: propose inside [L, R], shrink towards x0 on rejection
+                todo = np.ones(n, bool)
+                new_x, new_f, new_ll = x0.copy(), cur.copy(), None if cur_ll is None else cur_ll.copy()
+                for _shrink in range(200):
+                    if not todo.any():
+                        break
+                    x1 = L + rng.uniform(size=n) * (R - L)
+                    q = th.copy(); q[:, j] = np.where(todo, x1, x0)
+                    f, fl = density(q)
+                    ok = todo & (f > y)
+                    new_x = np.where(ok, x1, new_x); new_f = np.where(ok, f, new_f)
+                    if fl is not None:
+                        new_ll = np.where(ok, fl, new_ll)
+                    todo &= ~ok
+                    L = np.where(todo & (x1 < x0), x1, L); R = np.where(todo & (x1 >= x0), x1, R)
+                th[:, j] = new_x; cur = new_f
+                if new_ll is not None:
+                    cur_ll = new_ll
+        if keep_samples:
+            out[it] = th
+    return {"theta": out, "theta_final": th, "logdensity": cur, "loglike": cur_ll, "n_evaluations": evals}
+
+
+def batched_slice_parallel_tempering(model, pt, theta0, n_rounds, *, rng=None, w=10.0, n_passes=3, max_steps=20):
+    """The Pigeons-shaped workload with its real explorer: every round, each LOCAL replica of this rank takes one
+    slice-sampling iteration at the weight it currently holds (value-only launches, all local replicas per launch),
+    then one deterministic even-odd swap round over all ranks (`octo.ParallelTempering.swap_round`: the library's
+    ncclAllGather of (l_ref, l_target) when `pt` was built with backend "nccl").  Swaps exchange weights, not states."""
+    rng = np.random.default_rng() if rng is None else rng
+    th = np.array(theta0, dtype=np.float64, order="F")
+    assert th.shape[0] == pt.n_local
+    swaps, evals = [], 0
+    for rnd in range(n_rounds):
+        r = batched_slice_sampler(model, th, 1, rng=rng, w=w, n_passes=n_passes, max_steps=max_steps, beta=pt.local_betas(),
+                                  keep_samples=False)
+        th = r["theta_final"]; evals += r["n_evaluations"]
+        lp = model.ℓπcallback(np.asfortranarray(th)); ll = r["loglike"]
+        swaps.append(pt.swap_round(lp - ll, lp))          # l_ref = prior terms, l_target = l_ref + ln_like
+    return {"theta": th, "swap_accept": np.array(swaps), "n_evaluations": evals}
+
+
 def octofit_rejection(model, rng=None, *, draws=100_000, batch=65536, verbosity=0):
     """Rejection sampling from the prior, batched on the device (octofit_rejection, src/sampling.jl:168-258).
 

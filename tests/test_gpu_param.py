@@ -542,3 +542,85 @@ def test_device_parallel_tempering():
     assert out["beta"][cold] == 1.0 and np.isfinite(out["logpost_tempered"][cold]) and out["logpost_tempered"][cold] > lp0 - 40
     assert np.array_equal(out["cold_trace"][-1], out["theta_final"][cold])
     model.close()
+
+
+def test_host_terms_next_to_the_device_posterior(oracle_lib):
+    """non-epoch terms that are arbitrary user code in the reference — a `UserLikelihood`
+    (`mass_ratio ~ Normal`, src/variables.jl:332-380) and a planet-order prior (src/likelihoods/prior-planet-order.jl) —
+    as host callbacks next to the device posterior: value and gradient of the full posterior against oracle + numpy."""
+    import workloads
+    spec, th = workloads.one_planet_with_priors(60, 40, 90, seed=5)
+    model = octo.LogDensityModel(spec)
+    names = list(spec.theta_names)
+    ja, jm, jM = names.index("b.a"), names.index("b.mass"), names.index("M")
+
+    def user_likelihood(nat):                 # (mass * mjup2msol / M) ~ Normal(0.008, 0.002)
+        q = nat[:, jm] * 0.0009545942339693249 / nat[:, jM]
+        z = (q - 0.008) / 0.002
+        g = np.zeros_like(nat)
+        g[:, jm] = -z / 0.002 * 0.0009545942339693249 / nat[:, jM]
+        g[:, jM] = z / 0.002 * q / nat[:, jM]
+        return -0.5 * z * z - np.log(0.002) - 0.5 * np.log(2 * np.pi), g
+
+    def order_prior(nat):                     # smooth stand-in for `a_b < 30 AU` ordering constraints: log-sigmoid wall
+        u = (30.0 - nat[:, ja]) / 0.5
+        g = np.zeros_like(nat)
+        g[:, ja] = -(1.0 / (1.0 + np.exp(u))) / 0.5
+        return -np.log1p(np.exp(-u)), g
+    lp0, g0 = model.ℓπcallback_grad(th)
+    model.add_host_term(user_likelihood); model.add_host_term(order_prior)
+    lp, g = model.ℓπcallback_grad(th)
+    lpv = model.ℓπcallback(th)
+    lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), th, threads=4)
+    nat = oracle_lib.invlink(spec, th)
+    v1, gn1 = user_likelihood(nat); v2, gn2 = order_prior(nat)
+    # d natural / d θ_t of the elementwise bijectors, by differences of the oracle's invlink
+    h = 1e-6 * np.maximum(1.0, np.abs(th))
+    dxdy = (oracle_lib.invlink(spec, th + h) - oracle_lib.invlink(spec, th - h)) / (2 * h)
+    assert rel_err(lp, lp_o + v1 + v2).max() < LOGP_RTOL and rel_err(lpv, lp_o + v1 + v2).max() < LOGP_RTOL
+    assert grad_err(g, g_o + (gn1 + gn2) * dxdy).max() < 1e-7
+    assert np.array_equal(lp0, model.ℓπcallback_grad(th)[0] - (v1 + v2)) or rel_err(lp0 + v1 + v2, lp).max() < 1e-13
+    model.close()
+
+
+def test_batched_slice_sampler_and_tempering_with_it():
+    """The value-only explorer the reference gives Pigeons (SliceSampler), replica-batched over K1v: (1) at tempering
+    weight 0 the target is the prior-only reference model, whose marginals are known exactly: started from prior draws
+    the sampler must keep reproducing them (invariance) — Uniform(0, 100), Uniform(0, 0.99), Sine, truncated Normal;
+    (2) at weight 1, started on the posterior, the log density stays where HMC's is; (3) tempered with
+    `ParallelTempering` swaps the cold rung stays on the posterior and swaps are accepted."""
+    spec = octo.ModelSpec(reference_test_system())
+    model = octo.LogDensityModel(spec)
+    rng = np.random.default_rng(12)
+    names = list(spec.theta_names)
+    n = 512
+    th_prior = model.link(model.sample_priors(rng, n))
+    n0 = model.kernel_launches
+    sl = octo.batched_slice_sampler(model, th_prior, 6, rng=rng, w=2.0, beta=np.zeros(n))
+    assert sl["n_evaluations"] > 6 * 3 * spec.D * 2 and model.kernel_launches - n0 >= sl["n_evaluations"]
+    nat = model.invlink(sl["theta"][-1])
+    a, e, inc, M = (nat[:, names.index(k)] for k in ("b.a", "b.e", "b.i", "M"))
+    se = lambda sd: 4.0 * sd / np.sqrt(n)                                # 4 sigma of the sample mean
+    assert abs(a.mean() - 50.0) < se(28.9) and abs(a.std() - 28.87) < 3.0
+    assert abs(e.mean() - 0.495) < se(0.286) and abs(inc.mean() - np.pi / 2) < se(0.68)
+    assert abs(M.mean() - 1.2) < se(0.1) and abs(M.std() - 0.1) < 0.02
+    # (2) posterior: start from HMC draws, the density level is kept
+    params, _ = model.guess_starting_position(rng, N=60_000, batch=20_000)
+    start = model.link(params)
+    inv_mass = octo.diagonal_metric(model, start)
+    th0 = start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((128, spec.D))
+    hmc = octo.device_hmc(model, th0, 200, step_size=0.15, n_leapfrog=12, inv_mass=inv_mass, seed=3)
+    post = hmc["theta"][-1]
+    sp = octo.batched_slice_sampler(model, post, 8, rng=rng, w=1.0)
+    assert np.all(np.isfinite(sp["logdensity"]))
+    assert abs(np.median(sp["logdensity"]) - np.median(hmc["logpost"][-1])) < 3.0
+    # (3) tempering: 16 replicas; the cold replica stays on the posterior, swaps happen
+    R = 16
+    lad = np.linspace(0.0, 1.0, R) ** 3
+    pt = octo.ParallelTempering(R, seed=4, beta=lad, backend="local")
+    res = octo.batched_slice_parallel_tempering(model, pt, post[:R], 12, rng=rng, w=1.0)
+    assert res["swap_accept"].sum() > 0
+    cold = int(np.argmax(pt.chain_of_replica == R - 1))
+    lp_cold = model.ℓπcallback(res["theta"][cold])
+    assert lp_cold > np.median(hmc["logpost"][-1]) - 25.0
+    model.close()
