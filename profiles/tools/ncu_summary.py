@@ -1,5 +1,7 @@
-"""Summarise an `ncu --page raw --csv` dump: duration, occupancy, pipe utilisation, top stall reasons."""
+"""Summarise an `ncu --page raw --csv` dump: duration, occupancy, pipe utilisation, top stall reasons.
+    ncu_summary.py raw.csv [--json out.json]     (--json: the first kernel's key numbers, read by bench.py for `roofline.traffic`)"""
 import csv
+import json
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
@@ -38,3 +40,18 @@ for r in rows[2:]:
                 continue
             if v > 4:
                 print('  PIPE %-64s %.1f' % (k, v))
+
+if "--json" in sys.argv:
+    d = dict(zip(h, rows[2]))
+    num = lambda k: float(d[k].replace(",", "")) if d.get(k) not in (None, "", "n/a") else None
+    unit = dict(zip(h, rows[1]))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    out = {"kernel": d["Kernel Name"], "grid": d["Grid Size"], "block": d["Block Size"],
+           "duration_us": num("gpu__time_duration.sum") * {"us": 1.0, "ms": 1e3, "ns": 1e-3}.get(unit.get("gpu__time_duration.sum", "us"), 1.0),
+           "dram_bytes_read": num("dram__bytes_read.sum") * scale.get(unit.get("dram__bytes_read.sum", "byte"), 1.0),
+           "dram_bytes_write": num("dram__bytes_write.sum") * scale.get(unit.get("dram__bytes_write.sum", "byte"), 1.0),
+           "registers": num("launch__registers_per_thread"),
+           "fp64_pipe_pct": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active")}
+    json.dump(out, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)

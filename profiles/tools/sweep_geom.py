@@ -14,8 +14,10 @@ def run(name, steps, force):
     post = False
     if name == "post":
         spec, x = workloads.one_planet_with_priors(100, 100, 1024, seed=2); post = True
-    elif "x" in name:
-        n, E = (int(v) for v in name.split("x")); spec, x = workloads.one_planet(E, 0, n, seed=5)
+    elif "x" in name:          # "4096x100": astrometry epochs; "4096x0+20000": astrometry + star-RV (offset, jitter) epochs
+        n, E = name.split("x"); n = int(n)
+        na, nr = (int(v) for v in E.split("+")) if "+" in E else (int(E), 0)
+        spec, x = workloads.one_planet(na, nr, n, seed=5)
     else:
         spec, x = workloads.config(name)
     model = octo.LogDensityModel(spec)
