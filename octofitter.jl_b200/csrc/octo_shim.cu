@@ -269,10 +269,12 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
     }
     if (sub_override == 1 || E < 1 || (sub_override == 0 && (n_chains + 31) / 32 >= resident)) return best;
     // measured on C2 / C3 / C4 / 4096 x {10, 100, 316} (profiles/r02_geometry_sweep.txt): a lean-astrometry-equivalent
-    // pair costs a lane of the latency-tuned instantiation ~0.32 us (two pairs in flight), ~0.8 us in the throughput
-    // instantiation when two CTAs share the SM, which also has ~3 us more fixed cost per launch; the combine through L2
-    // costs ~3.5 us
-    const double t_it[2] = {0.80, 0.32}, t_k2 = 3.5, t_thr = 3.0;
+    // pair costs a lane of the latency-tuned instantiation ~0.32 us (two pairs in flight), ~0.65 us in the throughput
+    // instantiation (two CTAs share the SM: the same pairs per SM and microsecond), which also has ~3 us more fixed cost
+    // per launch; the combine through L2 costs ~3.5 us.  The lane = chain choice above is priced by the same model, so a
+    // single wave of the latency instantiation is taken exactly when it is the faster one (it leaves SMs idle when the
+    // chain groups do not fill them: 4096 chains x 1e5 epochs stay multi-wave, x 3162 epochs do not)
+    const double t_it[2] = {0.65, 0.32}, t_k2 = 3.5, t_thr = 3.0;
     const double ew[2] = {ctx->m.wtot > 0 ? ctx->m.wtot : 1.0, ctx->m.wtot_lat > 0 ? ctx->m.wtot_lat : 1.0};
     auto cost = [&](int S, bool lat, int64_t gy) {
         const int Wc = lat ? Wl : W;
@@ -282,7 +284,9 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
     double best_cost;
     {
         const int64_t slots = best.lat ? ctx->n_sm : resident;
-        const double waves = std::ceil((double)best.gx * best.gy / (double)slots);
+        // (whole waves up to four, then the hardware's CTA scheduler evens the tail out: fractional)
+        double waves = (double)best.gx * best.gy / (double)slots;
+        if (waves < 4.0) waves = std::ceil(waves);
         best_cost = waves * cost(1, best.lat, best.gy);
         if (sub_override > 1) best_cost = 1e30;
     }
@@ -306,9 +310,6 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
                 const double c = cost(S, lat, gy);
                 if (c < c_c - 1e-9) { c_c = c; gy_c = gy; }
             }
-            // a single wave is a latency play: beyond ~64 dependent pairs per lane the launch's fixed costs are amortised
-            // anyway and the multi-wave throughput geometry (more warps per SM, hardware load balancing) is the faster one
-            if (sub_override <= 1 && std::ceil(ew[lat ? 1 : 0] / (double)(gy_c * Wc * S)) > 64.0) continue;
             if (c_c < best_cost - 1e-9) {
                 best_cost = c_c;
                 best.gx = (int)gx; best.gy = (int)gy_c; best.ch = ch; best.lat = lat != 0; best.block = Wc * 32;
