@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define OCTO_ABI_VERSION 3
+#define OCTO_ABI_VERSION 4
 #define OCTO_MAX_PLANETS 4
 
 /* error codes */
@@ -101,7 +101,7 @@ typedef struct OctoConstants {
  * the reference default (jitter 0, platescale 1, northangle 0, offset 0;
  * relative-astrometry.jl:170-172, rv-absolute.jl:139,181). Kind 3 requires
  * idx_jitter >= 0 (rv-absolute-margin.jl:149 reads θ_obs.jitter unconditionally).
- * Only the default trend_function (identically zero) is supported.
+ * trend_function: identically zero by default; trends linear in the observation variables via n_trend / trend_basis below.
  */
 typedef struct OctoObsBlock {
     int32_t kind;
@@ -125,6 +125,16 @@ typedef struct OctoObsBlock {
     int32_t idx_pmdec;
     int32_t reserved;
     const double* aux;     /* kind 5 only: the 15 catalogue numbers, see OCTO_KIND_HGCA_INSTANT */
+    /* kinds 2, 3, 4: `trend_function(θ_obs, epoch)` (rv-absolute.jl:143, rv-absolute-margin.jl:111, rv-relative.jl:131)
+     * when it is LINEAR in the observation variables — polynomials in time with coefficient variables, fixed-period
+     * sinusoids with amplitude variables, the docs' `θ_obs.trend_slope * (epoch - 57000)`:
+     *     trend(θ_obs, t_k) = trend_const[k] + Σ_v in[idx_trend[v]] * trend_basis[v * n_epochs + k],  v < n_trend <= 3
+     * trend_const may be NULL (zero).  n_trend = 0 and trend_const = NULL: the default zero trend.  The caller obtains
+     * the basis by probing the closure (unit vectors in θ_obs) and must keep anything non-linear in Julia. */
+    int32_t n_trend;
+    int32_t idx_trend[3];
+    const double* trend_basis;
+    const double* trend_const;
 } OctoObsBlock;
 
 /*

@@ -9,7 +9,8 @@
 # `Octofitter.AbstractObs` with an `ln_like(obs, ctx)` method (src/variables.jl:87-134, docs/src/custom-likelihood.md):
 #
 #   * every observation the kernel supports (PlanetRelAstromObs incl. the ObsPriorAstromONeil2019 wrapper,
-#     StarAbsoluteRVObs / MarginalizedStarAbsoluteRVObs / PlanetRelativeRVObs without GP and with a zero trend,
+#     StarAbsoluteRVObs / MarginalizedStarAbsoluteRVObs / PlanetRelativeRVObs without GP and with a trend_function that is
+#     zero or linear in the observation variables (probed),
 #     HGCAInstantaneousObs; planets on Visual{KepOrbit} or ThieleInnesOrbit) is replaced by a `BlankLikelihood` that keeps
 #     its priors and derived variables — exactly what `prior_only_model` does (src/cross-validation.jl:60-99) — so D, the
 #     parameter order and arr2nt are unchanged;
@@ -38,7 +39,7 @@ import Octofitter: Planet, System, BlankLikelihood, Priors, Derived, normalizena
 
 const LIB = get(ENV, "OCTO_B200_LIB", joinpath(@__DIR__, "..", "octofitter.jl_b200", "lib", "libocto_b200.so"))
 const MAXP = 4
-const OCTO_ABI_VERSION = 3
+const OCTO_ABI_VERSION = 4
 
 # ------------------------------------------------------------------------------------------------------------------
 # ABI structs (field for field as include/octo_b200.h; layout checked by tests/test_julia_glue_cpu.py)
@@ -76,6 +77,10 @@ struct OctoObsBlock
     idx_pmdec::Int32
     reserved::Int32
     aux::Ptr{Cdouble}
+    n_trend::Int32
+    idx_trend::NTuple{3,Int32}
+    trend_basis::Ptr{Cdouble}
+    trend_const::Ptr{Cdouble}
 end
 
 struct OctoLayout
@@ -135,20 +140,46 @@ end
 # ------------------------------------------------------------------------------------------------------------------
 # What can be offloaded
 # ------------------------------------------------------------------------------------------------------------------
-"`trend_function(θ_obs, epoch)` of an RV observation is identically zero (the default closure cannot be recognised by
-identity: rv-absolute.jl:69, rv-absolute-margin.jl:52, rv-relative.jl:64).  Probed with random observation variables at
-every epoch of the table; any non-zero or failing evaluation keeps the observation in Julia."
-function has_zero_trend(obs, θ_obs)
-    hasproperty(obs, :trend_function) || return true
-    rng = Random.Xoshiro(0x0c70)
+"""
+    probe_trend(obs, θ_obs) -> (names, basis, constant) | nothing
+
+`trend_function(θ_obs, epoch)` of an RV observation (rv-absolute.jl:69,143; rv-absolute-margin.jl:52,111;
+rv-relative.jl:64,131) is an arbitrary closure; the default one cannot be recognised by identity.  It is PROBED: the
+constant part b₀(t) = f(0, t), one basis b_v(t) = f(e_v, t) - b₀(t) per observation variable, then a linearity check at
+random points.  Linear in at most three variables (none of them offset / jitter) — the docs' `θ_obs.trend_slope *
+(epoch - 57000)`, polynomials, fixed-period sinusoids — is offloaded as per-epoch basis values; the zero trend gives
+`(Symbol[], zeros(0, n), nothing)`; anything else (`nothing`) keeps the observation in Julia.
+"""
+function probe_trend(obs, θ_obs)
+    ep = collect(Float64, obs.table.epoch); n = length(ep)
+    hasproperty(obs, :trend_function) || return (Symbol[], zeros(0, n), nothing)
+    f = obs.trend_function
+    ks = keys(θ_obs)
+    at(vals) = NamedTuple{ks}(Tuple(vals))
     try
-        for _ in 1:4
-            θr = map(_ -> 10 * randn(rng), θ_obs)                       # same field names, arbitrary values
-            all(t -> iszero(obs.trend_function(θr, t)), obs.table.epoch) || return false
+        z = zeros(length(ks))
+        b0 = [Float64(f(at(z), t)) for t in ep]
+        names = Symbol[]; rows = Vector{Float64}[]
+        for (j, k) in enumerate(ks)
+            e = copy(z); e[j] = 1.0
+            b = [Float64(f(at(e), t)) for t in ep] .- b0
+            any(!iszero, b) && (push!(names, k); push!(rows, b))
         end
-        return true
+        (length(names) <= 3 && !(:offset in names) && !(:jitter in names)) || return nothing
+        rng = Random.Xoshiro(0x0c70)
+        for _ in 1:4
+            θr = 10 .* randn(rng, length(ks))
+            lin = copy(b0)
+            for (nm, b) in zip(names, rows)
+                lin .+= θr[findfirst(==(nm), ks)] .* b
+            end
+            got = [Float64(f(at(θr), t)) for t in ep]
+            all(isapprox.(got, lin; rtol=1e-11, atol=1e-11 * max(1.0, maximum(abs, lin; init=0.0)))) || return nothing
+        end
+        B = isempty(rows) ? zeros(0, n) : permutedims(reduce(hcat, rows))          # n_trend x n
+        return (names, B, any(!iszero, b0) ? b0 : nothing)
     catch
-        return false
+        return nothing
     end
 end
 
@@ -170,11 +201,11 @@ function kind_of(obs, θ_obs)
     elseif T === :PlanetRelAstromObs
         return hasproperty(obs.table, :pa) && hasproperty(obs.table, :sep) ? Int32(1) : Int32(0)
     elseif T === :StarAbsoluteRVObs
-        return (isnothing(obs.gaussian_process) && has_zero_trend(obs, θ_obs)) ? Int32(2) : Int32(-1)
+        return (isnothing(obs.gaussian_process) && !isnothing(probe_trend(obs, θ_obs))) ? Int32(2) : Int32(-1)
     elseif T === :MarginalizedStarAbsoluteRVObs
-        return has_zero_trend(obs, θ_obs) ? Int32(3) : Int32(-1)
+        return !isnothing(probe_trend(obs, θ_obs)) ? Int32(3) : Int32(-1)
     elseif T === :PlanetRelativeRVObs
-        return (isnothing(obs.gaussian_process) && has_zero_trend(obs, θ_obs)) ? Int32(4) : Int32(-1)
+        return (isnothing(obs.gaussian_process) && !isnothing(probe_trend(obs, θ_obs))) ? Int32(4) : Int32(-1)
     elseif T === :HGCAInstantaneousObs
         return KIND_HGCA
     end
@@ -309,7 +340,8 @@ function build_context(system::System, θ0; device::Integer=0)
             end...))
             ep = f64(tbl.epoch); y1 = f64(code)
             push!(blocks, OctoObsBlock(k, Int32(-1), length(ep), 0, ptr(ep), ptr(y1), ptr(nothing), ptr(nothing), ptr(nothing),
-                                       ptr(nothing), -1, -1, -1, -1, 0, col((:pmra,)), col((:pmdec,)), 0, ptr(aux)))
+                                       ptr(nothing), -1, -1, -1, -1, 0, col((:pmra,)), col((:pmdec,)), 0, ptr(aux),
+                                       0, (Int32(-1), Int32(-1), Int32(-1)), Ptr{Cdouble}(0), Ptr{Cdouble}(0)))
             push!(offloaded, obs); return
         end
         tbl = nameof(typeof(obs)) === :ObsPriorAstromONeil2019 ? obs.wrapped_like.table : obs.table
@@ -321,10 +353,20 @@ function build_context(system::System, θ0; device::Integer=0)
         cor = (astrom && hasproperty(tbl, :cor)) ? f64(tbl.cor) : nothing
         (k == 3 && !hasproperty(θobs, :jitter)) && return                # the reference reads θ_obs.jitter unconditionally
         (k in (2, 3)) && !all(i -> idx[:mass][i] >= 0, 1:P) && return
+        # RV: the trend closure as basis values (probe_trend; kind_of already made sure it is linear)
+        n_tr = Int32(0); idx_tr = (Int32(-1), Int32(-1), Int32(-1)); tb = tc = nothing
+        if !astrom
+            tnames, TB, t0 = probe_trend(obs, θobs)
+            n_tr = Int32(length(tnames))
+            idx_tr = ntuple(i -> i <= n_tr ? v(tnames[i]) : Int32(-1), 3)
+            n_tr > 0 && (tb = f64(vec(permutedims(TB))))               # row-major [n_trend x n_epochs]
+            isnothing(t0) || (tc = f64(t0))
+        end
         push!(blocks, OctoObsBlock(k, Int32(ip - 1), length(ep), isnothing(cor) ? 0 : 1, ptr(ep), ptr(y1), ptr(y2), ptr(s1),
                                    ptr(s2), ptr(cor), v(:jitter), astrom ? v(:platescale) : Int32(-1),
                                    astrom ? v(:northangle) : Int32(-1), astrom ? Int32(-1) : v(:offset),
-                                   Int32(nameof(typeof(obs)) === :ObsPriorAstromONeil2019), -1, -1, 0, Ptr{Cdouble}(0)))
+                                   Int32(nameof(typeof(obs)) === :ObsPriorAstromONeil2019), -1, -1, 0, Ptr{Cdouble}(0),
+                                   n_tr, idx_tr, ptr(tb), ptr(tc)))
         push!(offloaded, obs)
     end
     # the reference's summation order: planet observations first, then system observations (system.jl:223-236)

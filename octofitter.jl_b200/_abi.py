@@ -36,7 +36,8 @@ class OctoObsBlock(C.Structure):
                 ("epoch", _pd), ("y1", _pd), ("y2", _pd), ("s1", _pd), ("s2", _pd), ("cor", _pd),
                 ("idx_jitter", C.c_int32), ("idx_platescale", C.c_int32),
                 ("idx_northangle", C.c_int32), ("idx_offset", C.c_int32), ("obs_prior", C.c_int32), ("idx_pmra", C.c_int32),
-                ("idx_pmdec", C.c_int32), ("reserved", C.c_int32), ("aux", _pd)]
+                ("idx_pmdec", C.c_int32), ("reserved", C.c_int32), ("aux", _pd),
+                ("n_trend", C.c_int32), ("idx_trend", C.c_int32 * 3), ("trend_basis", _pd), ("trend_const", _pd)]
 
 
 _i4 = C.c_int32 * OCTO_MAX_PLANETS
@@ -97,13 +98,16 @@ def pack(layout_dict: dict, block_dicts: list) -> PackedModel:
     keep, blocks = [], []
     for bd in block_dicts:
         cols = {}
-        for k in ("epoch", "y1", "y2", "s1", "s2", "cor", "aux"):
+        for k in ("epoch", "y1", "y2", "s1", "s2", "cor", "aux", "trend_basis", "trend_const"):
             v = bd.get(k)
             cols[k] = None if v is None else np.ascontiguousarray(np.asarray(v, dtype=np.float64))
         keep.append(cols)
         n = len(cols["epoch"])
+        idx_trend = [int(v) for v in bd.get("idx_trend", [])]
+        if cols["trend_basis"] is not None and cols["trend_basis"].shape != (len(idx_trend), n):
+            raise ValueError("trend_basis must be [n_trend x n_epochs]")
         for k, v in cols.items():
-            if k != "aux" and v is not None and len(v) != n:
+            if k not in ("aux", "trend_basis") and v is not None and len(v) != n:
                 raise ValueError("The columns in the input data do not all have the same length")
         blocks.append(OctoObsBlock(
             int(bd["kind"]), int(bd.get("planet", -1)), n, 0 if cols["cor"] is None else 1,
@@ -111,7 +115,9 @@ def pack(layout_dict: dict, block_dicts: list) -> PackedModel:
             _dptr(cols["cor"]),
             int(bd.get("idx_jitter", -1)), int(bd.get("idx_platescale", -1)),
             int(bd.get("idx_northangle", -1)), int(bd.get("idx_offset", -1)), int(bd.get("obs_prior", 0)),
-            int(bd.get("idx_pmra", -1)), int(bd.get("idx_pmdec", -1)), 0, _dptr(cols["aux"])))
+            int(bd.get("idx_pmra", -1)), int(bd.get("idx_pmdec", -1)), 0, _dptr(cols["aux"]),
+            len(idx_trend), (C.c_int32 * 3)(*(idx_trend + [-1] * (3 - len(idx_trend)))), _dptr(cols["trend_basis"]),
+            _dptr(cols["trend_const"])))
     return PackedModel(L, blocks, keep)
 
 

@@ -48,6 +48,9 @@ struct DevBlock {
     int32_t slot_jitter, slot_platescale, slot_northangle, slot_offset;   // accumulator slots (or -1)
     int32_t slot_margin;                      // first of the margin accumulators (kind 3) or -1
     int32_t slot_obsprior;                    // first of the 4 observable-prior accumulators (OP_*) or -1
+    // RV tables: trend linear in n_trend observation variables (coefficient columns idx_trend, per-epoch basis values in the
+    // record's spare slots y2, c2, c3); accumulator slot per variable (marginalised RV: two consecutive slots, Σ g b and Σ b/var)
+    int32_t n_trend, idx_trend[3], slot_trend[3], pad_trend;
     double wgt, cum;                          // relative cost of one epoch of this table; Σ n*wgt of the tables before it
     double wgt_lat, cum_lat;                  // the same for latency-bound launches (cost = length of the dependent chain of one pair)
 };
@@ -85,7 +88,7 @@ struct DevModel {
     int32_t n_hg, any_ti;         // any_ti: some planet uses the Thiele-Innes basis
     DevHg hg[OCTO_MAX_HGCA];
     // device table, one 48-byte record per epoch of the concatenated list: [t, y1, c1, y2, c2, c3]
-    //   astrometry: c1,c2,c3 = w11,w12,w22 (no jitter) | σ1², σ2², cor (jitter);   RV: c1 = 1/σ² | σ² (y2,c2,c3 unused)
+    //   astrometry: c1,c2,c3 = w11,w12,w22 (no jitter) | σ1², σ2², cor (jitter);   RV: c1 = 1/σ² | σ², (y2,c2,c3) = trend basis values
     const double* tab;
 };
 

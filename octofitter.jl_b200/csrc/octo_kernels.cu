@@ -447,6 +447,11 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
     const double jit = JIT ? in[c + (int64_t)B.idx_jitter * ld] : 0.0;
     const double off = (B.idx_offset >= 0 && !margin) ? in[c + (int64_t)B.idx_offset * ld] : 0.0;
     const double j2 = jit * jit;
+    // trend_function linear in <= 3 observation variables: coefficients per chain, basis values in the record
+    const int tn = B.n_trend;
+    double tc[3] = {0.0, 0.0, 0.0}, gT[3] = {0.0, 0.0, 0.0}, vT[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int v = 0; v < 3; ++v) if (v < tn) tc[v] = in[c + (int64_t)B.idx_trend[v] * ld];
 
     double ll = 0.0, g_jit = 0.0, g_off = 0.0;
     double mA = 0.0, mS1 = 0.0, mC = 0.0, mLG = 0.0, mR2 = 0.0, mR1 = 0.0, mQ = 0.0;
@@ -467,9 +472,11 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         const double2* src = tab + 3 * (int64_t)(kb + col);
         const double2 a0 = __ldg(src), a1 = __ldg(src + 1);
         stage[3 * lane] = a0; stage[3 * lane + 1] = a1;
+        if (tn > 1) stage[3 * lane + 2] = __ldg(src + 2);
     } else if (PAD) {
         const double2 z = make_double2(0.0, 0.0);
         stage[3 * lane] = z; stage[3 * lane + 1] = z;
+        if (tn > 1) stage[3 * lane + 2] = z;
     }
     __syncwarp();
 #pragma unroll (UNR)
@@ -480,6 +487,15 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         const double t = ra0.x, y = ra0.y, e1 = ra1.x;
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
         double model = off;
+        double tb1 = 0.0, tb2 = 0.0;
+        if (tn > 0) {
+            model = fma(tc[0], ra1.y, model);
+            if (tn > 1) {
+                const double2 ra2 = stage[3 * (sbase + j) + 2];
+                tb1 = ra2.x; tb2 = ra2.y;
+                model = fma(tc[1], tb1, model); model = fma(tc[2], tb2, model);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
             kepler_sincos(orb[u], t, dt[u], sE[u], cE[u]);
@@ -506,6 +522,10 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             ll = fma(kc.mhalf * r, riv, ll);
             g = riv;
             if (GRAD) { g_off += g; if constexpr (JIT) g_jit = fma(fma(r, riv, -kc.one), iv, g_jit); }
+        }
+        if (GRAD && tn > 0) {                      // d model / d coefficient = basis value
+            gT[0] = fma(g, ra1.y, gT[0]); gT[1] = fma(g, tb1, gT[1]); gT[2] = fma(g, tb2, gT[2]);
+            if constexpr (MARGIN) { vT[0] = fma(iv, ra1.y, vT[0]); vT[1] = fma(iv, tb1, vT[1]); vT[2] = fma(iv, tb2, vT[2]); }
         }
         if (GRAD) {
 #pragma unroll
@@ -539,6 +559,11 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         if (!margin) {
             if (B.slot_jitter >= 0) acc_add(acc, B.slot_jitter, lane, g_jit * jit);
             if (B.slot_offset >= 0) acc_add(acc, B.slot_offset, lane, g_off);
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v) if (v < tn) {
+            acc_add(acc, B.slot_trend[v], lane, gT[v]);
+            if constexpr (MARGIN) acc_add(acc, B.slot_trend[v] + 1, lane, vT[v]);
         }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) if (u < ni) {
@@ -722,6 +747,8 @@ __device__ __noinline__ void epilogue_margin(const DevModel& m, const double* s_
             const double R2 = R[(s0 + MA_R2) * 32 + lane], R1 = R[(s0 + MA_R1) * 32 + lane], Q = R[(s0 + MA_Q) * 32 + lane];
             const double jit = in[c + (int64_t)B.idx_jitter * ld];
             gp0[B.idx_jitter * 32 + lane] += 2.0 * jit * (-A + R2 - 2.0 * rbar * R1 + rbar * rbar * Q + Q / A);
+            for (int v = 0; v < B.n_trend; ++v)
+                gp0[B.idx_trend[v] * 32 + lane] += R[B.slot_trend[v] * 32 + lane] - 2.0 * rbar * R[(B.slot_trend[v] + 1) * 32 + lane];
 #pragma unroll 1
             for (int p = 0; p < m.n_planets; ++p) {
                 const int v0 = s0 + MA_COUNT + p * MV_COUNT;
@@ -780,6 +807,7 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
             if (B.slot_platescale >= 0) gp[B.idx_platescale * 32 + lane] += R[B.slot_platescale * 32 + lane];
             if (B.slot_northangle >= 0) gp[B.idx_northangle * 32 + lane] += R[B.slot_northangle * 32 + lane];
             if (B.slot_offset >= 0) gp[B.idx_offset * 32 + lane] += R[B.slot_offset * 32 + lane];
+            for (int v = 0; v < B.n_trend; ++v) gp[B.idx_trend[v] * 32 + lane] += R[B.slot_trend[v] * 32 + lane];
         }
 #pragma unroll 1
         for (int h = 0; h < m.n_hg; ++h) {

@@ -272,8 +272,8 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
     // pair costs a lane of the latency-tuned instantiation ~0.32 us (two pairs in flight), ~0.65 us in the throughput
     // instantiation (two CTAs share the SM: the same pairs per SM and microsecond), which also has ~3 us more fixed cost
     // per launch; the combine through L2 costs ~3.5 us.  The lane = chain choice above is priced by the same model, so a
-    // single wave of the latency instantiation is taken exactly when it is the faster one (it leaves SMs idle when the
-    // chain groups do not fill them: 4096 chains x 1e5 epochs stay multi-wave, x 3162 epochs do not)
+    // single wave of the latency instantiation is taken when the model says it is the faster one, up to 128 dependent
+    // pairs per lane (see below)
     const double t_it[2] = {0.65, 0.32}, t_k2 = 3.5, t_thr = 3.0;
     const double ew[2] = {ctx->m.wtot > 0 ? ctx->m.wtot : 1.0, ctx->m.wtot_lat > 0 ? ctx->m.wtot_lat : 1.0};
     auto cost = [&](int S, bool lat, int64_t gy) {
@@ -310,6 +310,10 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
                 const double c = cost(S, lat, gy);
                 if (c < c_c - 1e-9) { c_c = c; gy_c = gy; }
             }
+            // a single wave is a latency play: the calibration above holds for a few dozen dependent pairs per lane; for
+            // long loops the throughput instantiation (16 warps per SM) is as fast on lean astrometry and 30 % faster on
+            // the radial-velocity loops (4096 x 20000 RV + jitter: 1077 vs 1643 us), so stop considering it there
+            if (sub_override <= 1 && std::ceil(ew[lat ? 1 : 0] / (double)(gy_c * Wc * S)) > 128.0) continue;
             if (c_c < best_cost - 1e-9) {
                 best_cost = c_c;
                 best.gx = (int)gx; best.gy = (int)gy_c; best.ch = ch; best.lat = lat != 0; best.block = Wc * 32;
@@ -558,13 +562,29 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
         D.idx_jitter = B.idx_jitter; D.idx_offset = (B.kind == OCTO_KIND_RV_STAR_MARGIN || astrom) ? -1 : B.idx_offset;
         D.idx_platescale = astrom ? B.idx_platescale : -1; D.idx_northangle = astrom ? B.idx_northangle : -1;
         D.slot_jitter = D.slot_platescale = D.slot_northangle = D.slot_offset = D.slot_margin = D.slot_obsprior = -1;
+        D.n_trend = 0;
+        for (int v = 0; v < 3; ++v) { D.idx_trend[v] = -1; D.slot_trend[v] = -1; }
+        if (B.n_trend != 0 || B.trend_const) {
+            if (astrom) return bad("trend_function belongs to the radial-velocity kinds");
+            if (B.n_trend < 0 || B.n_trend > 3) return bad("at most 3 trend variables");
+            if (B.n_trend > 0 && B.n_epochs > 0 && !B.trend_basis) return bad("n_trend set but trend_basis is null");
+            for (int v = 0; v < B.n_trend; ++v) {
+                if (!col_ok(B.idx_trend[v], false)) return bad("trend variable column out of range");
+                for (int k = 0; k < B.n_epochs; ++k) if (!std::isfinite(B.trend_basis[(size_t)v * B.n_epochs + k])) return bad("non-finite trend basis value");
+                D.idx_trend[v] = B.idx_trend[v];
+            }
+            if (B.trend_const) for (int k = 0; k < B.n_epochs; ++k) if (!std::isfinite(B.trend_const[k])) return bad("non-finite trend constant");
+            D.n_trend = B.n_trend;
+        }
         if (B.obs_prior) {
             if (!astrom) return bad("the observable-based prior is offloaded for relative astrometry only (prior-observable.jl:78-137)");
             D.slot_obsprior = n_acc; n_acc += OP_COUNT;
         }
         if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
             D.slot_margin = n_acc; n_acc += MA_COUNT + MV_COUNT * L->n_planets;
+            for (int v = 0; v < D.n_trend; ++v) { D.slot_trend[v] = n_acc; n_acc += 2; }
         } else {
+            for (int v = 0; v < D.n_trend; ++v) D.slot_trend[v] = n_acc++;
             if (D.idx_jitter >= 0) D.slot_jitter = n_acc++;
             if (D.idx_offset >= 0) D.slot_offset = n_acc++;
         }
@@ -686,6 +706,11 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
                     cll += term; pwc[o] = (double)term;
                 } else { c1[o] = s1 * s1; c2[o] = s2 * s2; c3[o] = cor; }
             } else {
+                // trend: the constant part leaves the data, the basis values of the (<= 3) coefficients ride in the record
+                if (B.trend_const) y1[o] = B.y1[k] - B.trend_const[k];
+                if (D.n_trend > 0) y2[o] = B.trend_basis[k];
+                if (D.n_trend > 1) c2[o] = B.trend_basis[(size_t)B.n_epochs + k];
+                if (D.n_trend > 2) c3[o] = B.trend_basis[2 * (size_t)B.n_epochs + k];
                 const double s = B.s1[k];
                 if (!D.jit) {
                     const long double term = -0.5L * (log2pi + std::log((long double)s * s));

@@ -246,18 +246,53 @@ class HGCAInstantaneousObs(AbstractObs):
 
 
 class _RVObs(AbstractObs):
+    """`trend_function(θ_obs, epoch)` as in the reference (rv-absolute.jl:69,143; rv-absolute-margin.jl:52,111;
+    rv-relative.jl:64,131): any callable that is LINEAR in the observation variables — the docs' example
+    `θ_obs.trend_slope * (epoch - 57000)`, polynomials with coefficient variables, fixed-period sinusoids with amplitude
+    variables.  Its coefficient variables (at most three) are listed in `variables` next to offset / jitter.  The closure
+    is probed here (unit vectors in θ_obs, then a linearity check at random points) and handed to the kernel as per-epoch
+    basis values; anything non-linear is refused — in Julia such an observation simply stays on the host."""
+
     def __init__(self, observations, *, name, variables=None, trend_function=None, gaussian_process=None):
         self.name = str(name)
         if gaussian_process is not None:
             raise ValueError("gaussian_process likelihoods are out of scope for the offloaded path "
                              "(SURVEY.md §2: celerite GP branch stays in the reference)")
-        if trend_function is not None:
-            raise ValueError("only the default (zero) trend_function is supported by the offloaded path")
         table = _check_table(observations, name)
         if not set(rv_cols) <= set(table):
             raise ValueError(f"Expected columns {rv_cols}")
         self.table = table
+        self.trend = None
+        specs = _norm_variables(self.default_variables if variables is None else variables)
+        if trend_function is not None:
+            self.trend = self._probe_trend(trend_function, [n for n, _ in specs])
+            self.allowed_variables = tuple(self.allowed_variables) + tuple(self.trend[0])
         self._set_variables(self.default_variables if variables is None else variables)
+
+    def _probe_trend(self, f, names):
+        from types import SimpleNamespace
+        ep = self.table["epoch"]
+        ev = lambda th: np.array([float(f(SimpleNamespace(**th), t)) for t in ep], dtype=np.float64)
+        zero = {n: 0.0 for n in names}
+        b0 = ev(zero)
+        basis = {}
+        for n in names:
+            bn = ev({**zero, n: 1.0}) - b0
+            if np.any(bn != 0.0):
+                basis[n] = bn
+        rng = np.random.default_rng(0)
+        for _ in range(4):
+            th = {n: 10.0 * rng.standard_normal() for n in names}
+            lin = b0 + sum(th[n] * basis[n] for n in basis)
+            got = ev(th)
+            if not np.allclose(got, lin, rtol=1e-11, atol=1e-11 * max(1.0, float(np.abs(lin).max(initial=0.0)))):
+                raise ValueError("trend_function is not linear in the observation variables: not offloadable "
+                                 "(the reference evaluates such a trend on the host)")
+        if len(basis) > 3:
+            raise ValueError("at most three trend coefficient variables are offloaded")
+        if any(n in ("offset", "jitter") for n in basis):
+            raise ValueError("a trend_function that reads offset / jitter is not offloaded")
+        return list(basis), (np.stack([basis[n] for n in basis]) if basis else np.zeros((0, len(ep)))), (b0 if np.any(b0 != 0.0) else None)
 
     def _columns(self):
         t = self.table
@@ -479,10 +514,15 @@ class ModelSpec:
     def _block(o, ip, obs_cols):
         ep, y1, y2, s1, s2, cor = o._columns()
         g = lambda v: obs_cols.get((id(o), v), -1)
-        return {"kind": o.kind, "planet": ip, "epoch": ep, "y1": y1, "y2": y2, "s1": s1, "s2": s2, "cor": cor,
-                "idx_jitter": g("jitter"), "idx_platescale": g("platescale"),
-                "idx_northangle": g("northangle"), "idx_offset": g("offset"), "name": o.name,
-                "obs_prior": int(getattr(o, "obs_prior", 0))}
+        blk = {"kind": o.kind, "planet": ip, "epoch": ep, "y1": y1, "y2": y2, "s1": s1, "s2": s2, "cor": cor,
+               "idx_jitter": g("jitter"), "idx_platescale": g("platescale"),
+               "idx_northangle": g("northangle"), "idx_offset": g("offset"), "name": o.name,
+               "obs_prior": int(getattr(o, "obs_prior", 0))}
+        trend = getattr(o, "trend", None)
+        if trend is not None:
+            names, basis, const = trend
+            blk.update(idx_trend=[g(n) for n in names], trend_basis=basis if len(names) else None, trend_const=const)
+        return blk
 
 
 class _PinnedArray(np.ndarray):

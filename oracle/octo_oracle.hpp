@@ -292,6 +292,15 @@ inline bool chain_valid(const OctoLayout& L, const double* in, int64_t ld, int64
 // a1: one chain of ln_like_generated.  T = double (value) or Dual<N> (value + gradient).
 // `X` holds the n_in inputs already lifted to T.
 // ---------------------------------------------------------------------------------------
+// trend_function(θ_obs, epoch_k) of an RV observation, for trends linear in the observation variables (the ABI's
+// representation of the closure; rv-absolute.jl:143, rv-absolute-margin.jl:111, rv-relative.jl:131)
+template <class T, class XT>
+inline T trend(const OctoObsBlock& B, const XT& X, int k, int n) {
+    T tr(B.trend_const ? B.trend_const[k] : 0.0);
+    for (int v = 0; v < B.n_trend; ++v) tr += X[B.idx_trend[v]] * B.trend_basis[(size_t)v * n + k];
+    return tr;
+}
+
 template <class T>
 inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoObsBlock* blocks, int n_blocks,
                        const T* X) {
@@ -393,7 +402,8 @@ inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
             const bool margin = (B.kind == OCTO_KIND_RV_STAR_MARGIN);
             T A(0.0), Bq(0.0), C(0.0), acc(0.0);
             for (int k = 0; k < n; ++k) {
-                T rv_model = margin ? T(0.0) : offset;       // trend_function ≡ 0
+                T rv_model = margin ? T(0.0) : offset;
+                rv_model += trend<T>(B, X, k, n);               // rv-absolute.jl:143, rv-absolute-margin.jl:111
                 for (int p = 0; p < P; ++p) {
                     T m = X[L.idx_mass[p]] * c.mjup2msol;
                     rv_model += radvel(orb[p], sols[(size_t)p * E + start[b] + k], m);
@@ -414,6 +424,7 @@ inline T ln_like_chain(const OctoConstants& c, const OctoLayout& L, const OctoOb
             T acc(0.0);
             for (int k = 0; k < n; ++k) {
                 T rv_model = offset;
+                rv_model += trend<T>(B, X, k, n);               // rv-relative.jl:131
                 rv_model += radvel(orb[ip], sols[(size_t)ip * E + start[b] + k]);
                 for (int j = 0; j < P; ++j) {
                     if (value(orb[j].a) < value(orb[ip].a)) {

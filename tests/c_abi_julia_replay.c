@@ -21,6 +21,8 @@ typedef struct {
     const double *epoch, *y1, *y2, *s1, *s2, *cor;
     int32_t idx_jitter, idx_platescale, idx_northangle, idx_offset, obs_prior, idx_pmra, idx_pmdec, reserved;
     const double* aux;
+    int32_t n_trend, idx_trend[3];
+    const double *trend_basis, *trend_const;
 } JlObsBlock;
 typedef struct {
     int32_t n_planets, n_in;
@@ -35,7 +37,8 @@ static int layout_ok(void) {
     int ok = sizeof(JlConstants) == sizeof(OctoConstants) && sizeof(JlObsBlock) == sizeof(OctoObsBlock) &&
              sizeof(JlLayout) == sizeof(OctoLayout) && sizeof(JlPrior) == sizeof(OctoPrior) && sizeof(JlInputDef) == sizeof(OctoInputDef);
     ok = ok && SAME(JlObsBlock, OctoObsBlock, epoch) && SAME(JlObsBlock, OctoObsBlock, cor) && SAME(JlObsBlock, OctoObsBlock, idx_jitter) &&
-         SAME(JlObsBlock, OctoObsBlock, obs_prior) && SAME(JlObsBlock, OctoObsBlock, idx_pmra) && SAME(JlObsBlock, OctoObsBlock, aux);
+         SAME(JlObsBlock, OctoObsBlock, obs_prior) && SAME(JlObsBlock, OctoObsBlock, idx_pmra) && SAME(JlObsBlock, OctoObsBlock, aux) &&
+         SAME(JlObsBlock, OctoObsBlock, n_trend) && SAME(JlObsBlock, OctoObsBlock, idx_trend) && SAME(JlObsBlock, OctoObsBlock, trend_const);
     ok = ok && SAME(JlLayout, OctoLayout, idx_plx) && SAME(JlLayout, OctoLayout, idx_mass) && SAME(JlLayout, OctoLayout, basis) &&
          SAME(JlLayout, OctoLayout, idx_G) && SAME(JlPrior, OctoPrior, p) && SAME(JlInputDef, OctoInputDef, a) && SAME(JlInputDef, OctoInputDef, value);
     return ok;
@@ -83,7 +86,7 @@ int main(int argc, char** argv) {
     JlObsBlock B; memset(&B, 0, sizeof B);
     B.kind = 0; B.planet = 0; B.n_epochs = 8; B.has_cor = 1;
     B.epoch = ep; B.y1 = ra; B.y2 = dec; B.s1 = sg; B.s2 = sg; B.cor = cr;
-    B.idx_jitter = B.idx_platescale = B.idx_northangle = B.idx_offset = -1; B.obs_prior = 0; B.idx_pmra = B.idx_pmdec = -1;
+    B.idx_jitter = B.idx_platescale = B.idx_northangle = B.idx_offset = -1; B.obs_prior = 0; B.idx_pmra = B.idx_pmdec = -1; B.n_trend = 0; B.idx_trend[0] = B.idx_trend[1] = B.idx_trend[2] = -1;
     JlLayout L; memset(&L, 0, sizeof L);
     L.n_planets = 1; L.n_in = N_IN;
     for (int p = 0; p < 4; ++p) {

@@ -29,13 +29,13 @@ def test_header_symbols_are_exported(lib):
     for s in declared:
         assert hasattr(lib, s), s
     hdr_version = int(re.search(r"#define OCTO_ABI_VERSION (\d+)", hdr).group(1))
-    assert lib.octo_abi_version() == hdr_version == 3
+    assert lib.octo_abi_version() == hdr_version == 4
 
 
 def test_struct_sizes_match_header():
     assert C.sizeof(octo.OctoConstants) == 7 * 8
     assert C.sizeof(octo.OctoLayout) == 4 * (2 + 14 * 4)
-    assert C.sizeof(octo.OctoObsBlock) == 4 * 4 + 6 * 8 + 8 * 4 + 8
+    assert C.sizeof(octo.OctoObsBlock) == 4 * 4 + 6 * 8 + 8 * 4 + 8 + 4 * 4 + 2 * 8
 
 
 def test_default_constants(lib):

@@ -98,8 +98,9 @@ def test_every_ccall_matches_a_prototype_of_the_header():
 
 def test_glue_offloads_only_what_the_kernel_implements():
     """a custom trend_function or a non-Visual{KepOrbit} orbit must keep the observation in Julia."""
-    assert "has_zero_trend" in JL and re.search(r"StarAbsoluteRVObs\n\s+return \(isnothing\(obs\.gaussian_process\) && has_zero_trend", JL)
-    assert re.search(r"MarginalizedStarAbsoluteRVObs\n\s+return has_zero_trend", JL)
+    assert "function probe_trend(obs, θ_obs)" in JL
+    assert re.search(r"StarAbsoluteRVObs\n\s+return \(isnothing\(obs\.gaussian_process\) && !isnothing\(probe_trend", JL)
+    assert re.search(r"MarginalizedStarAbsoluteRVObs\n\s+return !isnothing\(probe_trend", JL)
     assert "basis_of(pl)" in JL and "AbsoluteVisual" in JL
     # the model type handed to the samplers is the reference's own
     assert "Octofitter.LogDensityModel(b200_system(system; device); kwargs...)" in JL
