@@ -51,3 +51,36 @@ print("hmc", r["accept_rate"], float(r["logpost_final"][0]))
 pt = octo.device_parallel_tempering(m, th[:16], np.linspace(0, 1, 16), 3, n_iter=1, n_leapfrog=3, step_size=1e-3, inv_mass=np.full(spec.D, 1e-4), seed=5)
 print("pt", sorted(pt["rung"]) == list(range(16)), float(pt["swap_accept"].mean()))
 m.close()
+# ---- round 2: sub-lane geometries (with and without epoch splits across CTAs), the launch-per-leapfrog explorer next to the
+#      trajectory-resident kernel, the sharded-ladder entry point on one rank, the asynchronous halves, a linear trend
+for force in ("4,1,1", "8,0,2", "32,1,1", "1,0,3"):
+    os.environ["OCTO_B200_FORCE"] = force
+    spec, x = workloads.config("C3")
+    m = octo.LogDensityModel(spec)
+    ll, g = m.ln_like_and_gradient(x[:21]); v = m.ln_like(x[:21])
+    print("force", force, m.launch_geometry_full(21), float(ll[0]), np.isfinite(g).all(), float(v[0]) == float(ll[0]))
+    m.close()
+os.environ.pop("OCTO_B200_FORCE")
+spec, th = workloads.one_planet_with_priors(40, 30, 45, seed=2)
+m = octo.LogDensityModel(spec)
+im = np.full(spec.D, 1e-4)
+os.environ["OCTO_B200_HMC_LAUNCH_PER_LEAPFROG"] = "1"
+r = octo.device_hmc(m, th, 2, step_size=1e-3, n_leapfrog=3, inv_mass=im, seed=3)
+os.environ.pop("OCTO_B200_HMC_LAUNCH_PER_LEAPFROG")
+print("hmc launch-per-leapfrog", r["accept_rate"])
+ptl = octo.ParallelTempering(16, seed=5, beta=np.linspace(0, 1, 16), backend="local", model=m)
+pd = octo.device_parallel_tempering_dist(m, ptl, th[:16], np.linspace(0, 1, 16), 3, n_iter=1, n_leapfrog=3, step_size=1e-3, inv_mass=im, seed=5)
+print("pt sharded entry (1 rank)", sorted(pd["rung"]) == list(range(16)), np.array_equal(pd["swap_counts"], pt["swap_counts"]))
+hs = [m.ℓπcallback_grad_begin(th) for _ in range(3)]
+print("async", [float(h.wait()[0][0]) for h in hs])
+ptl.close(); m.close()
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_gpu_trend as T
+for kind, nt in (("star", 3), ("margin", 2), ("planet", 1)):
+    system, prefix = T._system(kind, nt, n_ep=30)
+    spec = octo.ModelSpec(system)
+    x = T._inputs(spec, prefix, 19, seed=1)
+    m = octo.LogDensityModel(spec)
+    ll, g = m.ln_like_and_gradient(x)
+    print("trend", kind, nt, float(ll[0]), np.isfinite(g).all())
+    m.close()
