@@ -3,7 +3,7 @@
 import os, sys, importlib.util
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-lib = os.path.join(ROOT, "octofitter.jl_b200", "lib", "libocto_timing.so")
+lib = os.environ.get("OCTO_TIMING_LIB") or os.path.join(ROOT, "octofitter.jl_b200", "lib", "libocto_timing.so")
 if not os.path.exists(lib):
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "octofitter.jl_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
