@@ -405,7 +405,8 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 // Radial-velocity segment (kinds 2, 3, 4).
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, int NPT, bool MARGIN, bool JIT, int ILP>
+// TREND: the table has a linear trend_function (its own instantiations: the lean loops do not carry the terms)
+template <bool GRAD, int NPT, bool MARGIN, bool JIT, bool TREND, int ILP>
 __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                     double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
@@ -448,7 +449,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
     const double off = (B.idx_offset >= 0 && !margin) ? in[c + (int64_t)B.idx_offset * ld] : 0.0;
     const double j2 = jit * jit;
     // trend_function linear in <= 3 observation variables: coefficients per chain, basis values in the record
-    const int tn = B.n_trend;
+    const int tn = TREND ? B.n_trend : 0;
     double tc[3] = {0.0, 0.0, 0.0}, gT[3] = {0.0, 0.0, 0.0}, vT[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int v = 0; v < 3; ++v) if (v < tn) tc[v] = in[c + (int64_t)B.idx_trend[v] * ld];
@@ -472,11 +473,11 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         const double2* src = tab + 3 * (int64_t)(kb + col);
         const double2 a0 = __ldg(src), a1 = __ldg(src + 1);
         stage[3 * lane] = a0; stage[3 * lane + 1] = a1;
-        if (tn > 1) stage[3 * lane + 2] = __ldg(src + 2);
+        if (TREND && tn > 1) stage[3 * lane + 2] = __ldg(src + 2);
     } else if (PAD) {
         const double2 z = make_double2(0.0, 0.0);
         stage[3 * lane] = z; stage[3 * lane + 1] = z;
-        if (tn > 1) stage[3 * lane + 2] = z;
+        if (TREND && tn > 1) stage[3 * lane + 2] = z;
     }
     __syncwarp();
 #pragma unroll (UNR)
@@ -488,7 +489,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
         double sE[NPT], cE[NPT], dt[NPT], rD[NPT], rv[NPT];
         double model = off;
         double tb1 = 0.0, tb2 = 0.0;
-        if (tn > 0) {
+        if (TREND && tn > 0) {
             model = fma(tc[0], ra1.y, model);
             if (tn > 1) {
                 const double2 ra2 = stage[3 * (sbase + j) + 2];
@@ -523,7 +524,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             g = riv;
             if (GRAD) { g_off += g; if constexpr (JIT) g_jit = fma(fma(r, riv, -kc.one), iv, g_jit); }
         }
-        if (GRAD && tn > 0) {                      // d model / d coefficient = basis value
+        if (GRAD && TREND && tn > 0) {             // d model / d coefficient = basis value
             gT[0] = fma(g, ra1.y, gT[0]); gT[1] = fma(g, tb1, gT[1]); gT[2] = fma(g, tb2, gT[2]);
             if constexpr (MARGIN) { vT[0] = fma(iv, ra1.y, vT[0]); vT[1] = fma(iv, tb1, vT[1]); vT[2] = fma(iv, tb2, vT[2]); }
         }
@@ -561,7 +562,7 @@ __device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0
             if (B.slot_offset >= 0) acc_add(acc, B.slot_offset, lane, g_off);
         }
 #pragma unroll
-        for (int v = 0; v < 3; ++v) if (v < tn) {
+        for (int v = 0; v < 3; ++v) if (TREND && v < tn) {
             acc_add(acc, B.slot_trend[v], lane, gT[v]);
             if constexpr (MARGIN) acc_add(acc, B.slot_trend[v] + 1, lane, vT[v]);
         }
@@ -1202,12 +1203,16 @@ __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B
         if (plain && !B.jit) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
         else if (plain) seg_astrom<GRAD, NPT, 1, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
         else seg_astrom<GRAD, NPT, 2, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+    } else if (B.n_trend > 0) {
+        if (B.kind == OCTO_KIND_RV_STAR_MARGIN) seg_rv<GRAD, NPT, true, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else if (B.jit) seg_rv<GRAD, NPT, false, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else seg_rv<GRAD, NPT, false, false, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-        seg_rv<GRAD, NPT, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        seg_rv<GRAD, NPT, true, true, false, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else if (B.jit) {
-        seg_rv<GRAD, NPT, false, true, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        seg_rv<GRAD, NPT, false, true, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     } else {
-        seg_rv<GRAD, NPT, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        seg_rv<GRAD, NPT, false, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
     }
 }
 

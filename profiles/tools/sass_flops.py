@@ -90,8 +90,8 @@ def main():
     res = {"how": "profiles/tools/sass_flops.py: FP64 instructions of the epoch loops in the SASS of libocto_b200.so, per pair "
                   "(flop = 2 DFMA + DMUL + DADD)", "kernels": {}}
     want = {"thr": "k_kepler_likeILb1ELi1ELb0E", "lat": "k_kepler_likeILb1ELi1ELb1E"}
-    kinds = {"astrom": "seg_astrom<true, 1, 0,", "astrom_jitter": "seg_astrom<true, 1, 1,", "rv": "seg_rv<true, 1, false, false,",
-             "rv_jitter": "seg_rv<true, 1, false, true,", "rv_margin": "seg_rv<true, 1, true, true,"}
+    kinds = {"astrom": "seg_astrom<true, 1, 0,", "astrom_jitter": "seg_astrom<true, 1, 1,", "rv": "seg_rv<true, 1, false, false, false,",
+             "rv_jitter": "seg_rv<true, 1, false, true, false,", "rv_margin": "seg_rv<true, 1, true, true, false,"}
     for tag, key in want.items():
         sec = [v for k, v in secs.items() if key in k]
         if not sec:
