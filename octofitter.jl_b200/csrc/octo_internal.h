@@ -75,7 +75,8 @@ struct DevModel {
     double wtot_lat;         // Σ n*wgt_lat
     double const_ll;         // Σ of the chain-independent normalisation terms of tables without free jitter
     int32_t n_planets, n_in, n_blocks, n_acc;
-    int32_t has_margin, pad0;    // any marginalised-RV or observable-prior table (their epilogue fold needs an extra barrier)
+    int32_t has_margin, lean;    // any marginalised-RV or observable-prior table (their epilogue fold needs an extra barrier);
+                                 // lean: only lean tables and Campbell planets — the kernels compiled without the rest (octo_kernels.cu)
     int64_t n_epochs;
     int32_t idx_plx[OCTO_MAX_PLANETS], idx_a[OCTO_MAX_PLANETS], idx_e[OCTO_MAX_PLANETS], idx_i[OCTO_MAX_PLANETS],
             idx_w[OCTO_MAX_PLANETS], idx_W[OCTO_MAX_PLANETS], idx_tp[OCTO_MAX_PLANETS], idx_M[OCTO_MAX_PLANETS],

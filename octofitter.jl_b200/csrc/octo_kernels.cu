@@ -619,9 +619,10 @@ __device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const doub
 // returns validity of what the task looked at
 // skip_tp: the fused parameterisation derives tp (θ_at_epoch_to_tperi) on another warp at the same time and stores it
 // itself; the size / mass / time task then leaves tp alone
+template <bool LEAN>
 __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
                               double* sc, int lane, bool skip_tp = false) {
-    const bool ti = m.any_ti && m.basis[p] == OCTO_BASIS_THIELE_INNES;
+    const bool ti = (!LEAN && m.any_ti) && m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
         if (ti) {            // no angles: neutral values for the slots the Campbell code reads
             const int ks = kind == 0 ? PC_sini : (kind == 1 ? PC_sinw : PC_sinW);
@@ -797,6 +798,7 @@ __device__ __noinline__ void epilogue_ti_distribute(const DevModel& m, const dou
     }
 }
 
+template <bool LEAN>
 __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const double* s_const, const double* R, double* gp,
                                            int lane) {
     if (part == 0) {
@@ -811,7 +813,7 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
             for (int v = 0; v < B.n_trend; ++v) gp[B.idx_trend[v] * 32 + lane] += R[B.slot_trend[v] * 32 + lane];
         }
 #pragma unroll 1
-        for (int h = 0; h < m.n_hg; ++h) {
+        for (int h = 0; !LEAN && h < m.n_hg; ++h) {
             gp[m.hg[h].idx_pmra * 32 + lane] += R[m.hg[h].slot_pmra * 32 + lane];
             gp[m.hg[h].idx_pmdec * 32 + lane] += R[m.hg[h].slot_pmdec * 32 + lane];
         }
@@ -823,7 +825,7 @@ __device__ __noinline__ void epilogue_part(int part, const DevModel& m, const do
         auto C = [&](int k) { return sc[k * 32 + lane]; };
         auto Rp = [&](int a) { return R[slot_planet(p, a) * 32 + lane]; };
         const double e = C(PC_e), s = C(PC_s), inv_s = C(PC_inv_s), inv_a = C(PC_inv_a), inv_M = C(PC_inv_M);
-        if (m.any_ti && part < 3 && m.basis[p] == OCTO_BASIS_THIELE_INNES) {
+        if ((!LEAN && m.any_ti) && part < 3 && m.basis[p] == OCTO_BASIS_THIELE_INNES) {
             if (part == 1) epilogue_ti_astrom(m, p, sc, R, gp, lane);
             continue;
         }
@@ -1017,6 +1019,7 @@ __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, i
 }
 __host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + 3 * n_in + (TRIG_SLOTS + 8) * T + 4) * 32; }
 
+template <bool LEAN>
 __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
                                            int64_t ld, double* s_in, double* s_const, const ParamSmem& S, int* s_ok, int w, int W,
                                            int lane) {
@@ -1070,7 +1073,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
                 const int task = it - n_trig, p = task / 5, kind = task % 5;
                 bool derived_tp = false;                                 // this planet's tp is one of the tperi definitions
                 for (int t = 0; t < T; ++t) derived_tp = derived_tp || P.tperi_k[t] == m.idx_tp[p];
-                if (!prologue_task(m, p, kind, s_in, lane, 32, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
+                if (!prologue_task<LEAN>(m, p, kind, s_in, lane, 32, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
             }
         }
     }
@@ -1102,7 +1105,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
             }
         } else {
             const int p = it - T;
-            prologue_products(s_const + p * PC_COUNT * 32, lane, m.any_ti && m.basis[p] == OCTO_BASIS_THIELE_INNES);
+            prologue_products(s_const + p * PC_COUNT * 32, lane, (!LEAN && m.any_ti) && m.basis[p] == OCTO_BASIS_THIELE_INNES);
         }
     }
     PTICK(4);
@@ -1194,10 +1197,16 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
 #endif
 }
 
-template <bool GRAD, int NPT, int ILP>
+template <bool GRAD, int NPT, int ILP, bool LEAN>
 __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
                                             int64_t ld, int lane, int ch) {
+    if constexpr (LEAN) {
+        if (B.kind <= OCTO_KIND_ASTROM_PASEP) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else if (B.jit) seg_rv<GRAD, NPT, false, true, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        else seg_rv<GRAD, NPT, false, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+        return;
+    }
     if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
         const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0 && B.slot_obsprior < 0;
         if (plain && !B.jit) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
@@ -1241,7 +1250,7 @@ struct EvalArgs {
 // (sub-lane 0 only) know about it.  Accumulators are folded over sub-lanes in sub-lane order right after the fixed-order
 // sum over warps, so results stay run-to-run bit-reproducible.
 // returns false when this CTA was not the last of its chain group to arrive (it has nothing more to do)
-template <bool GRAD, int NPT, int ILP>
+template <bool GRAD, int NPT, int ILP, bool LEAN>
 __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, double* smem, const double* inl_v) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -1281,7 +1290,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
         if (P) param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi).flags[threadIdx.x] = 0;
     }
     // the value-only kernel of a model without non-linear folds (marginalised RV, observable prior) needs one sum: ll
-    const int n_use = (!GRAD && !m.has_margin) ? 1 : n_acc;
+    const int n_use = (!GRAD && !(!LEAN && m.has_margin)) ? 1 : n_acc;
     double* acc = s_acc + w * n_acc * 32;
 #pragma unroll 4
     for (int s = 0; s < n_use; ++s) acc[s * 32 + lane] = 0.0;
@@ -1293,7 +1302,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
     const double* inp = (post_mode & OCTO_MODE_INLINE) ? inl_v : A.in;       // tiny batches carry their inputs in the parameters
     if (P) {
         PS = param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi);
-        param_forward(*P, m, inp, chain_of(lane), ld, s_in, s_const, PS, s_ok, w, W, lane);      // includes K1's prologue
+        param_forward<LEAN>(*P, m, inp, chain_of(lane), ld, s_in, s_const, PS, s_ok, w, W, lane);      // includes K1's prologue
     } else {
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * m.n_in; it += W * 32) {
@@ -1311,13 +1320,13 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
             const int col = it % ncol, task = it / ncol;
-            if (!prologue_task(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col)) s_ok[col] = 0;
+            if (!prologue_task<LEAN>(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col)) s_ok[col] = 0;
         }
         __syncthreads();
         // ---- phase 2: Thiele-Innes / RV products
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * m.n_planets; it += W * 32)
-            prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, m.any_ti && m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
+            prologue_products(s_const + (it / ncol) * PC_COUNT * 32, it % ncol, (!LEAN && m.any_ti) && m.basis[it / ncol] == OCTO_BASIS_THIELE_INNES);
     }
     __syncthreads();
     OCTO_TICK(); OCTO_WTICK(2);
@@ -1349,7 +1358,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
                 k0 = mine ? ep : 0; k1 = mine ? ep + 1 : 0;
             }
             if (!__any_sync(0xffffffffu, k0 < k1)) continue;
-            run_segment<GRAD, NPT, ILP>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane, ch);
+            run_segment<GRAD, NPT, ILP, LEAN>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane, ch);
         }
     }
     OCTO_WTICK(3);
@@ -1428,7 +1437,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 
     OCTO_TICK();
     // ---- HGCA tables: evaluated here, on the complete sums (not in pointwise mode: they are not part of the epoch list)
-    if (m.n_hg > 0 && !pw_const) {
+    if (!LEAN && m.n_hg > 0 && !pw_const) {
 #pragma unroll 1
         for (int h = 0; h < m.n_hg; ++h) hgca_tail<GRAD>(m, m.hg[h], s_const, s_red, s_acc, s_in, n_acc, w, W, lane);
     }
@@ -1441,7 +1450,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
     }
     __syncthreads();
     OCTO_WTICK(7);
-    if (m.has_margin) {
+    if ((!LEAN && m.has_margin)) {
         if (w == 0) epilogue_margin<GRAD>(m, s_const, s_red, s_gp, s_in, lane, 32, lane, pw_const != nullptr);
         __syncthreads();
     }
@@ -1450,7 +1459,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
     const bool tperi_early = GRAD && P && P->n_tperi > 0 && W >= EPI_PARTS + 1 + P->n_tperi;
     if (GRAD) {
 #pragma unroll 1
-        for (int part = w; part < EPI_PARTS; part += W) epilogue_part(part, m, s_const, s_red, s_gp + part * n_g * 32, lane);
+        for (int part = w; part < EPI_PARTS; part += W) epilogue_part<LEAN>(part, m, s_const, s_red, s_gp + part * n_g * 32, lane);
         if (tperi_early && w >= EPI_PARTS && w < EPI_PARTS + P->n_tperi) param_tperi_partials(*P, m, s_in, PS, w - EPI_PARTS, lane);
     }
     if (w == W - 1) {                                          // ll: a warp without a gradient part when W = 8
@@ -1477,7 +1486,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
         __syncthreads();
         OCTO_WTICK(9);
         const int ng = n_g * 32;
-        if (m.any_ti) {
+        if ((!LEAN && m.any_ti)) {
             if (w == 0) epilogue_ti_distribute(m, s_const, s_gp, ng, lane);
             __syncthreads();
         }
@@ -1510,9 +1519,13 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
     return true;
 }
 
+// LEAN = the model is made of the lean tables only (plain RA/Dec astrometry without jitter, RV with or without jitter;
+// no marginalised RV, trend, observable prior, HGCA or Thiele-Innes planet — DevModel::lean): those kernels do not carry the
+// code of the other tables.  Not a matter of tidiness: in the latency regime the SAME executed instructions ran 6-13 %
+// slower or faster depending on how much never-executed code the kernel's text section held (instruction fetch).
 // LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
 // single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
-template <bool GRAD, int NPT, bool LAT>
+template <bool GRAD, int NPT, bool LAT, bool LEAN>
 __global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
@@ -1530,7 +1543,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     A.in = in; A.n_chains = n_chains; A.ld = ld; A.ll_out = ll_out; A.g_out = g_out; A.ldg = ldg;
     A.partial = partial; A.tickets = tickets; A.P = P; A.post_mode = post_mode; A.pw_const = pw_const; A.leap = leap;
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
-    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP>(m, A, smem, inl.v);
+    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN>(m, A, smem, inl.v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1542,7 +1555,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 // inside the warps (sub-lanes), never across CTAs.  Same per-coordinate arithmetic as k_hmc_turn (octo_hmc_dev.cuh),
 // same summation orders as a one-shot launch of the same geometry: both explorers give identical bits.
 // ---------------------------------------------------------------------------------------------
-template <int NPT>
+template <int NPT, bool LEAN>
 __global__ void __launch_bounds__(OCTO_LAT_WARPS * 32, 1)
 k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ P, const ResidentArgs R, int ch, int eval_doubles) {
     using namespace octo_hmc_dev;
@@ -1628,7 +1641,7 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
             A.in = s_qp; A.ll_out = s_lpp; A.g_out = s_gp;
             A.leap = HmcLeap{s_p, s_qp, s_im, R.eps, last ? 0.5 * R.eps : R.eps, last ? 0 : 1, 0, tempered ? s_beta : nullptr, tempered ? s_llp : nullptr};
         }
-        eval_cta<true, NPT, OCTO_LAT_ILP>(m, A, smem, nullptr);
+        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN>(m, A, smem, nullptr);
         __syncthreads();
 #ifdef OCTO_TIMING
         if (blockIdx.x == 0 && tid == 0 && it == R.n_iter - 1 && l == R.n_leapfrog - 1) {
@@ -1697,7 +1710,7 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 
-template <bool GRAD, int NPT, bool LAT>
+template <bool GRAD, int NPT, bool LAT, bool LEAN>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
@@ -1715,7 +1728,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
     cfg.numAttrs = 0;
 #endif
     static const InlineIn none{};
-    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
+    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT, LEAN>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
                               inl ? (post_mode | OCTO_MODE_INLINE) : post_mode, d_pw_const, leap, g.ch, inl ? *inl : none);
 }
 
@@ -1724,16 +1737,19 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 // gradient kernel this model dispatches to (drives the launch geometry)
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
     cudaError_t e;
-#define OCTO_ATTR(G, N)                                                                                            \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);   \
-    if (e != cudaSuccess) return e;                                                                                \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);    \
+#define OCTO_ATTR1(G, N, L, Q)                                                                                     \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N, L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);    \
     if (e != cudaSuccess) return e
+#define OCTO_ATTR(G, N) OCTO_ATTR1(G, N, false, false); OCTO_ATTR1(G, N, true, false); OCTO_ATTR1(G, N, false, true); OCTO_ATTR1(G, N, true, true)
     OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
 #undef OCTO_ATTR
-    if (m.n_planets == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 1, false>, W * 32, smem_bytes);
-    else if (m.n_planets == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 2, false>, W * 32, smem_bytes);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, 4, false>, W * 32, smem_bytes);
+#undef OCTO_ATTR1
+#define OCTO_OCC(N) (m.lean ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, true>, W * 32, smem_bytes) \
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, false>, W * 32, smem_bytes))
+    if (m.n_planets == 1) e = OCTO_OCC(1);
+    else if (m.n_planets == 2) e = OCTO_OCC(2);
+    else e = OCTO_OCC(4);
+#undef OCTO_OCC
     return e;
 }
 
@@ -1745,13 +1761,15 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
                         const HmcLeap& leap, cudaStream_t st, const InlineIn* inl) {
 #define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl
-#define OCTO_DISPATCH(NPT)                                                                                        \
-    if (g.lat) return grad ? launch_t<true, NPT, true>(OCTO_ARGS) : launch_t<false, NPT, true>(OCTO_ARGS);         \
-    return grad ? launch_t<true, NPT, false>(OCTO_ARGS) : launch_t<false, NPT, false>(OCTO_ARGS)
+#define OCTO_DISPATCH2(NPT, L)                                                                                    \
+    if (g.lat) return grad ? launch_t<true, NPT, true, L>(OCTO_ARGS) : launch_t<false, NPT, true, L>(OCTO_ARGS);   \
+    return grad ? launch_t<true, NPT, false, L>(OCTO_ARGS) : launch_t<false, NPT, false, L>(OCTO_ARGS)
+#define OCTO_DISPATCH(NPT) if (m.lean) { OCTO_DISPATCH2(NPT, true); } else { OCTO_DISPATCH2(NPT, false); }
     if (m.n_planets == 1) { OCTO_DISPATCH(1); }
     if (m.n_planets == 2) { OCTO_DISPATCH(2); }
     OCTO_DISPATCH(4);
 #undef OCTO_DISPATCH
+#undef OCTO_DISPATCH2
 #undef OCTO_ARGS
 }
 
@@ -1760,9 +1778,10 @@ size_t octo_resident_smem_bytes(const DevModel& m, int D, int T) {
     return octo_smem_bytes(m, OCTO_LAT_WARPS, D, T) + ((size_t)(6 * D + 7) * 32 + (size_t)D) * sizeof(double);
 }
 cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin) {
-    cudaError_t e = cudaFuncSetAttribute(k_hmc_resident<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaError_t e = cudaSuccess;
+#define OCTO_ATTR(N, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin)
+    OCTO_ATTR(1, false); OCTO_ATTR(2, false); OCTO_ATTR(4, false); OCTO_ATTR(1, true); OCTO_ATTR(2, true); OCTO_ATTR(4, true);
+#undef OCTO_ATTR
     return e;
 }
 cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int T, const ResidentArgs& R, int ch, cudaStream_t st) {
@@ -1775,7 +1794,10 @@ cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     const int eval_doubles = (int)((eval_bytes + 7) / 8);
-    if (m.n_planets == 1) return cudaLaunchKernelEx(&cfg, k_hmc_resident<1>, m, d_param, R, ch, eval_doubles);
-    if (m.n_planets == 2) return cudaLaunchKernelEx(&cfg, k_hmc_resident<2>, m, d_param, R, ch, eval_doubles);
-    return cudaLaunchKernelEx(&cfg, k_hmc_resident<4>, m, d_param, R, ch, eval_doubles);
+#define OCTO_RES(N) (m.lean ? cudaLaunchKernelEx(&cfg, k_hmc_resident<N, true>, m, d_param, R, ch, eval_doubles) \
+                            : cudaLaunchKernelEx(&cfg, k_hmc_resident<N, false>, m, d_param, R, ch, eval_doubles))
+    if (m.n_planets == 1) return OCTO_RES(1);
+    if (m.n_planets == 2) return OCTO_RES(2);
+    return OCTO_RES(4);
+#undef OCTO_RES
 }

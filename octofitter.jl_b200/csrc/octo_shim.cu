@@ -634,6 +634,13 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
     }
     m.n_epochs = E; m.n_acc = n_acc;
     for (int b = 0; b < n_blocks; ++b) if (m.blocks[b].kind == OCTO_KIND_RV_STAR_MARGIN || m.blocks[b].slot_obsprior >= 0) m.has_margin = 1;
+    m.lean = (m.n_hg == 0 && !m.any_ti && !getenv("OCTO_B200_NO_LEAN")) ? 1 : 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        const DevBlock& D = m.blocks[b];
+        const bool astrom = D.kind <= OCTO_KIND_ASTROM_PASEP;
+        if (astrom ? !(D.kind == OCTO_KIND_ASTROM_RADEC && !D.jit && D.idx_platescale < 0 && D.idx_northangle < 0 && D.slot_obsprior < 0)
+                   : (D.kind == OCTO_KIND_RV_STAR_MARGIN || D.n_trend > 0)) m.lean = 0;
+    }
     // cost model for the epoch split (instructions per epoch of each specialised loop, relative to lean astrometry)
     double cum = 0.0, cum_lat = 0.0;
     for (int b = 0; b < n_blocks; ++b) {
