@@ -1250,16 +1250,21 @@ struct EvalArgs {
 // (sub-lane 0 only) know about it.  Accumulators are folded over sub-lanes in sub-lane order right after the fixed-order
 // sum over warps, so results stay run-to-run bit-reproducible.
 // returns false when this CTA was not the last of its chain group to arrive (it has nothing more to do)
-template <bool GRAD, int NPT, int ILP, bool LEAN>
+// FL (flavour): what the caller knows at compile time, so that the instantiation does not carry the other paths' code —
+// 0 nothing; 1 no parameterisation stage (A.P == nullptr); 2 with one; 3 the resident explorer: with one, a single epoch
+// split (no L2 combine), no pointwise mode, inputs never inline
+template <bool GRAD, int NPT, int ILP, bool LEAN, int FL>
 __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, double* smem, const double* inl_v) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
     const int n_acc = m.n_acc;
     const int ch = A.ch, col_c = lane & (ch - 1);
     const int64_t n_chains = A.n_chains, ld = A.ld, ldg = A.ldg;
-    const DevParam* P = A.P;
-    const int post_mode = A.post_mode;
-    const double* pw_const = A.pw_const;
+    const DevParam* P = FL == 1 ? nullptr : A.P;
+    if (FL >= 2) __builtin_assume(P != nullptr);
+    const int post_mode = FL == 3 ? 0 : A.post_mode;
+    const double* pw_const = FL == 3 ? nullptr : A.pw_const;
+    const int n_split = FL == 3 ? 1 : A.gy;                   // epoch splits of a chain group across CTAs
     double* s_const = smem;                                   // [P][PC_COUNT][32]
     double* s_acc = s_const + m.n_planets * PC_COUNT * 32;    // [W][n_acc][32]
     double* s_red = s_acc + W * n_acc * 32;                   // [n_acc][32]
@@ -1336,7 +1341,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
         //      every table inside the warp's range is divided evenly among the S sub-lanes (a warp whose range crosses
         //      a table boundary keeps all its sub-lanes busy in both tables)
         const int S = 32 / ch, sub = lane / ch;
-        const int64_t U = (int64_t)A.gy * W, u = (int64_t)A.by * W + w;
+        const int64_t U = (int64_t)n_split * W, u = (int64_t)A.by * W + w;
         // contiguous range of the COST-weighted epoch list (an RV+jitter epoch costs ~1.8 lean astrometry epochs)
         // (latency-bound launches weigh a pair by its dependent chain instead of its instruction count)
         const double wtot = A.lat_weights ? m.wtot_lat : m.wtot;
@@ -1384,8 +1389,8 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 
     // ---- K2: combine the epoch splits of this chain group: partials through L2 + a ticket; the last CTA to
     //      arrive sums them in split order (run-to-run bit-reproducible)
-    if (A.gy > 1 && !pw_const) {
-        double* mine = A.partial + ((int64_t)A.group * A.gy + A.by) * n_acc * 32;
+    if (n_split > 1 && !pw_const) {
+        double* mine = A.partial + ((int64_t)A.group * n_split + A.by) * n_acc * 32;
 #pragma unroll 2
         for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) mine[idx] = s_red[idx];
         __threadfence();
@@ -1393,7 +1398,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
         OCTO_TICK();
         if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(&A.tickets[A.group], 1u);
-            s_last = (prev == (unsigned)A.gy - 1);
+            s_last = (prev == (unsigned)n_split - 1);
             if (s_last) A.tickets[A.group] = 0;      // ready for the next launch on this workspace
         }
         __syncthreads();
@@ -1405,11 +1410,11 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 #endif
         if (!s_last) return false;
         __threadfence();
-        const double* base = A.partial + (int64_t)A.group * A.gy * n_acc * 32;
+        const double* base = A.partial + (int64_t)A.group * n_split * n_acc * 32;
         // every load of this thread (two accumulator cells x up to 16 splits) is issued before the first add: one
         // L2 round trip instead of four; additions stay in split order => same bits every run
         const int64_t stride = (int64_t)n_acc * 32;
-        const int ncell = n_use * 32, gy = A.gy;
+        const int ncell = n_use * 32, gy = n_split;
 #pragma unroll 1
         for (int idx0 = threadIdx.x; idx0 < ncell; idx0 += 2 * W * 32) {
             const int idx1 = idx0 + W * 32;
@@ -1525,7 +1530,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 // slower or faster depending on how much never-executed code the kernel's text section held (instruction fetch).
 // LAT = latency-tuned instantiation: no register cap (one CTA per SM, no spills) for launches whose whole grid is a
 // single wave of at most one CTA per SM; the other instantiation keeps two CTAs per SM resident for throughput.
-template <bool GRAD, int NPT, bool LAT, bool LEAN>
+template <bool GRAD, int NPT, bool LAT, bool LEAN, int FL>
 __global__ void __launch_bounds__((LAT ? OCTO_LAT_WARPS : WMAX) * 32, LAT ? 1 : OCTO_MIN_CTAS)
 k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in, int64_t n_chains, int64_t ld,
               double* __restrict__ ll_out, double* __restrict__ g_out, int64_t ldg, double* __restrict__ partial,
@@ -1543,7 +1548,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     A.in = in; A.n_chains = n_chains; A.ld = ld; A.ll_out = ll_out; A.g_out = g_out; A.ldg = ldg;
     A.partial = partial; A.tickets = tickets; A.P = P; A.post_mode = post_mode; A.pw_const = pw_const; A.leap = leap;
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
-    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN>(m, A, smem, inl.v);
+    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN, FL>(m, A, smem, inl.v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1641,7 +1646,7 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
             A.in = s_qp; A.ll_out = s_lpp; A.g_out = s_gp;
             A.leap = HmcLeap{s_p, s_qp, s_im, R.eps, last ? 0.5 * R.eps : R.eps, last ? 0 : 1, 0, tempered ? s_beta : nullptr, tempered ? s_llp : nullptr};
         }
-        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN>(m, A, smem, nullptr);
+        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN, 3>(m, A, smem, nullptr);
         __syncthreads();
 #ifdef OCTO_TIMING
         if (blockIdx.x == 0 && tid == 0 && it == R.n_iter - 1 && l == R.n_leapfrog - 1) {
@@ -1710,7 +1715,7 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 
-template <bool GRAD, int NPT, bool LAT, bool LEAN>
+template <bool GRAD, int NPT, bool LAT, bool LEAN, int FL>
 static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
                             double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
                             const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
@@ -1728,7 +1733,7 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
     cfg.numAttrs = 0;
 #endif
     static const InlineIn none{};
-    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT, LEAN>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
+    return cudaLaunchKernelEx(&cfg, k_kepler_like<GRAD, NPT, LAT, LEAN, FL>, m, d_in, n, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param,
                               inl ? (post_mode | OCTO_MODE_INLINE) : post_mode, d_pw_const, leap, g.ch, inl ? *inl : none);
 }
 
@@ -1737,15 +1742,16 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 // gradient kernel this model dispatches to (drives the launch geometry)
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
     cudaError_t e;
-#define OCTO_ATTR1(G, N, L, Q)                                                                                     \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N, L, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);    \
+#define OCTO_ATTR1(G, N, L, Q, F)                                                                                  \
+    e = cudaFuncSetAttribute(k_kepler_like<G, N, L, Q, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin); \
     if (e != cudaSuccess) return e
-#define OCTO_ATTR(G, N) OCTO_ATTR1(G, N, false, false); OCTO_ATTR1(G, N, true, false); OCTO_ATTR1(G, N, false, true); OCTO_ATTR1(G, N, true, true)
+#define OCTO_ATTR(G, N) OCTO_ATTR1(G, N, false, false, 0); OCTO_ATTR1(G, N, true, false, 0); OCTO_ATTR1(G, N, false, true, 1); \
+    OCTO_ATTR1(G, N, true, true, 1); OCTO_ATTR1(G, N, false, true, 2); OCTO_ATTR1(G, N, true, true, 2)
     OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
 #undef OCTO_ATTR
 #undef OCTO_ATTR1
-#define OCTO_OCC(N) (m.lean ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, true>, W * 32, smem_bytes) \
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, false>, W * 32, smem_bytes))
+#define OCTO_OCC(N) (m.lean ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, true, 1>, W * 32, smem_bytes) \
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, false, 0>, W * 32, smem_bytes))
     if (m.n_planets == 1) e = OCTO_OCC(1);
     else if (m.n_planets == 2) e = OCTO_OCC(2);
     else e = OCTO_OCC(4);
@@ -1761,10 +1767,14 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
                         const HmcLeap& leap, cudaStream_t st, const InlineIn* inl) {
 #define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl
-#define OCTO_DISPATCH2(NPT, L)                                                                                    \
-    if (g.lat) return grad ? launch_t<true, NPT, true, L>(OCTO_ARGS) : launch_t<false, NPT, true, L>(OCTO_ARGS);   \
-    return grad ? launch_t<true, NPT, false, L>(OCTO_ARGS) : launch_t<false, NPT, false, L>(OCTO_ARGS)
-#define OCTO_DISPATCH(NPT) if (m.lean) { OCTO_DISPATCH2(NPT, true); } else { OCTO_DISPATCH2(NPT, false); }
+#define OCTO_DISPATCH2(NPT, L, F)                                                                                 \
+    if (g.lat) return grad ? launch_t<true, NPT, true, L, F>(OCTO_ARGS) : launch_t<false, NPT, true, L, F>(OCTO_ARGS);   \
+    return grad ? launch_t<true, NPT, false, L, F>(OCTO_ARGS) : launch_t<false, NPT, false, L, F>(OCTO_ARGS)
+    // lean models: separate instantiations with and without the parameterisation stage (see eval_cta, FL)
+#define OCTO_DISPATCH(NPT)                                                                                         \
+    if (m.lean && d_param) { OCTO_DISPATCH2(NPT, true, 2); }                                                        \
+    else if (m.lean) { OCTO_DISPATCH2(NPT, true, 1); }                                                              \
+    else { OCTO_DISPATCH2(NPT, false, 0); }
     if (m.n_planets == 1) { OCTO_DISPATCH(1); }
     if (m.n_planets == 2) { OCTO_DISPATCH(2); }
     OCTO_DISPATCH(4);
