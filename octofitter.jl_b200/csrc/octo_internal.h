@@ -155,7 +155,18 @@ size_t octo_resident_smem_bytes(const DevModel& m, int D, int n_tperi);
 cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin);
 cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int n_tperi, const ResidentArgs& R, int ch, cudaStream_t st);
 
-// kernels (octo_kernels.cu)
+// kernels (octo_kernels.cu).  The file is compiled once per planet-count instantiation (1, 2, 4 planets per table loop);
+// each object exports its entry points through one of these
+struct OctoNptEntry {
+    cudaError_t (*attr)(size_t smem_optin);
+    cudaError_t (*occupancy)(const DevModel& m, int warps, size_t smem_bytes, int* ctas_per_sm);
+    cudaError_t (*launch)(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains, int64_t ld,
+                          double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
+                          const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
+                          cudaStream_t stream, const InlineIn* inl);
+    cudaError_t (*resident)(const DevModel& m, const cudaLaunchConfig_t* cfg, const DevParam* d_param, const ResidentArgs& R,
+                            int ch, int eval_doubles);
+};
 cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,

@@ -196,7 +196,7 @@ __device__ __forceinline__ void acc_add(double* acc, int slot, int lane, double 
 // contribution is an exact zero) — and, for ILP > 1 (latency-tuned launches), unrolled so that the dependent chains of
 // ILP consecutive pairs overlap in one thread.  Same sums, same bits as a loop that skips those lanes.
 template <bool GRAD, int NPT, int MODE, int ILP>
-__device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+__device__ __forceinline__ void seg_astrom(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                         double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     const int ip = B.planet;
     constexpr bool LEAN = (MODE == 0);
@@ -407,7 +407,7 @@ __device__ __noinline__ void seg_astrom(const DevModel& m, const DevBlock& B, in
 // ---------------------------------------------------------------------------------------------
 // TREND: the table has a linear trend_function (its own instantiations: the lean loops do not carry the terms)
 template <bool GRAD, int NPT, bool MARGIN, bool JIT, bool TREND, int ILP>
-__device__ __noinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+__device__ __forceinline__ void seg_rv(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                     double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     const bool star = (B.kind != OCTO_KIND_RV_PLANET_REL);
     constexpr bool margin = MARGIN;
@@ -620,7 +620,7 @@ __device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const doub
 // skip_tp: the fused parameterisation derives tp (θ_at_epoch_to_tperi) on another warp at the same time and stores it
 // itself; the size / mass / time task then leaves tp alone
 template <bool LEAN>
-__device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
+__device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
                               double* sc, int lane, bool skip_tp = false) {
     const bool ti = (!LEAN && m.any_ti) && m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
@@ -675,7 +675,7 @@ __device__ __noinline__ bool prologue_task(const DevModel& m, int p, int kind, c
     return ok;
 }
 
-__device__ __noinline__ void prologue_products(double* sc, int lane, bool ti) {
+__device__ __forceinline__ void prologue_products(double* sc, int lane, bool ti) {
     if (ti) {      // ra = X B + sinE s G, dec = X A + sinE s F [mas]; no radial velocity for this basis
         const double s = sc[PC_s * 32 + lane];
         sc[PC_Bh * 32 + lane] = sc[PC_B * 32 + lane]; sc[PC_Gs * 32 + lane] = s * sc[PC_G * 32 + lane];
@@ -799,7 +799,7 @@ __device__ __noinline__ void epilogue_ti_distribute(const DevModel& m, const dou
 }
 
 template <bool LEAN>
-__device__ __noinline__ void epilogue_part(int part, const DevModel& m, const double* s_const, const double* R, double* gp,
+__device__ __forceinline__ void epilogue_part(int part, const DevModel& m, const double* s_const, const double* R, double* gp,
                                            int lane) {
     if (part == 0) {
 #pragma unroll 1
@@ -1020,7 +1020,7 @@ __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, i
 __host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + 3 * n_in + (TRIG_SLOTS + 8) * T + 4) * 32; }
 
 template <bool LEAN>
-__device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
+__device__ __forceinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
                                            int64_t ld, double* s_in, double* s_const, const ParamSmem& S, int* s_ok, int w, int W,
                                            int lane) {
     using namespace octo_param_dev;
@@ -1126,7 +1126,7 @@ __device__ __noinline__ void param_forward(const DevParam& P, const DevModel& m,
 
 // reverse stage: S.aux holds d ll / d inputs of the 32 chains; S.flags bit 3 = chain is ok (valid and ll finite)
 // the 7 (8) partial derivatives of θ_at_epoch_to_tperi definition t w.r.t. its arguments (hand-derived reverse pass)
-__device__ __noinline__ void param_tperi_partials(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
+__device__ __forceinline__ void param_tperi_partials(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
                                                   int t, int lane) {
     using namespace octo_param_dev;
     const OctoInputDef& d = P.defs[P.tperi_k[t]];
@@ -1142,7 +1142,7 @@ __device__ __noinline__ void param_tperi_partials(const DevParam& P, const DevMo
     for (int q = 0; q < 8; ++q) S.part[(t * 8 + q) * 32 + lane] = part[q];
 }
 
-__device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
+__device__ __forceinline__ void param_backward(const DevParam& P, const DevModel& m, const double* s_in, const ParamSmem& S,
                                             double* __restrict__ g_t, int64_t chain0, bool active, int64_t ldg, int w,
                                             int W, int lane, const HmcLeap& leap, bool partials_done) {
     using namespace octo_param_dev;
@@ -1197,32 +1197,67 @@ __device__ __noinline__ void param_backward(const DevParam& P, const DevModel& m
 #endif
 }
 
-template <bool GRAD, int NPT, int ILP, bool LEAN>
+// INLINE OR OUT OF LINE.  A call to an out-of-line device function costs its caller the spill of every live register
+// around the call plus a break in the instruction stream (the callee's first lines are fetched only once the call
+// issues).  Measured on B200 with everything else equal (profiles/tools/ab.sh): with all stages of the
+// evaluation inline the resident explorer went 17.2 -> 13.6 us per leapfrog and C2 12.3 -> 10.2 us per step.  So: the
+// lean loops are inline everywhere (throughput instantiation, 4096 x 20000: astrometry / RV+jitter 1.173e11 / 8.46e10 evals/s
+// with the astrometry loop out of line, 1.204e11 / 8.20e10 with the RV loops out of line, 1.179e11 / 8.61e10 with both
+// inline: within 4 %, -DOCTO_THR_ASTROM_INLINE / -DOCTO_THR_RV_INLINE); the loops of the less common tables are always
+// out of line (they would only bloat every kernel).
+template <bool GRAD, int NPT, int MODE, int ILP>
+__device__ __noinline__ void seg_astrom_ool(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+                                            double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
+    seg_astrom<GRAD, NPT, MODE, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+}
+template <bool GRAD, int NPT, bool MARGIN, bool JIT, bool TREND, int ILP>
+__device__ __noinline__ void seg_rv_ool(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
+                                        double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
+    seg_rv<GRAD, NPT, MARGIN, JIT, TREND, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+}
+#ifndef OCTO_THR_ASTROM_INLINE
+#define OCTO_THR_ASTROM_INLINE 1
+#endif
+#ifndef OCTO_THR_RV_INLINE
+#define OCTO_THR_RV_INLINE 1
+#endif
+
+// INL: the latency-tuned instantiations (and the resident explorer)
+template <bool GRAD, int NPT, int ILP, bool LEAN, bool INL>
 __device__ __forceinline__ void run_segment(const DevModel& m, const DevBlock& B, int k0, int k1, const double* s_const,
                                             double* acc, double2* stage, const double* __restrict__ in, int64_t c,
                                             int64_t ld, int lane, int ch) {
-    if constexpr (LEAN) {
-        if (B.kind <= OCTO_KIND_ASTROM_PASEP) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else if (B.jit) seg_rv<GRAD, NPT, false, true, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else seg_rv<GRAD, NPT, false, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+#define OCTO_SEG_ARGS m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch
+#ifdef OCTO_SEG_ALL_OOL      // analysis build (profiles/tools/sass_flops.py): every table loop as a subroutine of its own
+    constexpr bool AI = false, RI = false;
+#else
+    constexpr bool AI = INL || OCTO_THR_ASTROM_INLINE, RI = INL || OCTO_THR_RV_INLINE;
+#endif
+    const bool astrom = B.kind <= OCTO_KIND_ASTROM_PASEP;
+    const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0 && B.slot_obsprior < 0;
+    if (LEAN || (astrom ? (plain && !B.jit) : (B.n_trend == 0 && B.kind != OCTO_KIND_RV_STAR_MARGIN))) {      // the lean loops
+        if (astrom) {
+            if constexpr (AI) seg_astrom<GRAD, NPT, 0, ILP>(OCTO_SEG_ARGS); else seg_astrom_ool<GRAD, NPT, 0, ILP>(OCTO_SEG_ARGS);
+        } else if (B.jit) {
+            if constexpr (RI) seg_rv<GRAD, NPT, false, true, false, ILP>(OCTO_SEG_ARGS); else seg_rv_ool<GRAD, NPT, false, true, false, ILP>(OCTO_SEG_ARGS);
+        } else {
+            if constexpr (RI) seg_rv<GRAD, NPT, false, false, false, ILP>(OCTO_SEG_ARGS); else seg_rv_ool<GRAD, NPT, false, false, false, ILP>(OCTO_SEG_ARGS);
+        }
         return;
     }
-    if (B.kind <= OCTO_KIND_ASTROM_PASEP) {
-        const bool plain = B.kind == OCTO_KIND_ASTROM_RADEC && B.idx_platescale < 0 && B.idx_northangle < 0 && B.slot_obsprior < 0;
-        if (plain && !B.jit) seg_astrom<GRAD, NPT, 0, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else if (plain) seg_astrom<GRAD, NPT, 1, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else seg_astrom<GRAD, NPT, 2, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-    } else if (B.n_trend > 0) {
-        if (B.kind == OCTO_KIND_RV_STAR_MARGIN) seg_rv<GRAD, NPT, true, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else if (B.jit) seg_rv<GRAD, NPT, false, true, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-        else seg_rv<GRAD, NPT, false, false, true, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-    } else if (B.kind == OCTO_KIND_RV_STAR_MARGIN) {
-        seg_rv<GRAD, NPT, true, true, false, 1>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-    } else if (B.jit) {
-        seg_rv<GRAD, NPT, false, true, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
-    } else {
-        seg_rv<GRAD, NPT, false, false, false, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
+    if constexpr (!LEAN) {
+        if (astrom) {
+            if (plain) seg_astrom_ool<GRAD, NPT, 1, 1>(OCTO_SEG_ARGS);
+            else seg_astrom_ool<GRAD, NPT, 2, 1>(OCTO_SEG_ARGS);
+        } else if (B.n_trend > 0) {
+            if (B.kind == OCTO_KIND_RV_STAR_MARGIN) seg_rv_ool<GRAD, NPT, true, true, true, 1>(OCTO_SEG_ARGS);
+            else if (B.jit) seg_rv_ool<GRAD, NPT, false, true, true, 1>(OCTO_SEG_ARGS);
+            else seg_rv_ool<GRAD, NPT, false, false, true, 1>(OCTO_SEG_ARGS);
+        } else {
+            seg_rv_ool<GRAD, NPT, true, true, false, 1>(OCTO_SEG_ARGS);
+        }
     }
+#undef OCTO_SEG_ARGS
 }
 
 // Everything one evaluation needs beyond the model.  The same body serves the one-shot kernel (k_kepler_like: one
@@ -1253,7 +1288,7 @@ struct EvalArgs {
 // FL (flavour): what the caller knows at compile time, so that the instantiation does not carry the other paths' code —
 // 0 nothing; 1 no parameterisation stage (A.P == nullptr); 2 with one; 3 the resident explorer: with one, a single epoch
 // split (no L2 combine), no pointwise mode, inputs never inline
-template <bool GRAD, int NPT, int ILP, bool LEAN, int FL>
+template <bool GRAD, int NPT, int ILP, bool LEAN, int FL, bool INL>
 __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, double* smem, const double* inl_v) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int W = blockDim.x >> 5;                            // 8 unless the model needed a smaller CTA
@@ -1363,7 +1398,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
                 k0 = mine ? ep : 0; k1 = mine ? ep + 1 : 0;
             }
             if (!__any_sync(0xffffffffu, k0 < k1)) continue;
-            run_segment<GRAD, NPT, ILP, LEAN>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane, ch);
+            run_segment<GRAD, NPT, ILP, LEAN, INL>(m, B, k0, k1, s_const, acc, s_stage + w * 96, s_in, lane, 32, lane, ch);
         }
     }
     OCTO_WTICK(3);
@@ -1548,7 +1583,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     A.in = in; A.n_chains = n_chains; A.ld = ld; A.ll_out = ll_out; A.g_out = g_out; A.ldg = ldg;
     A.partial = partial; A.tickets = tickets; A.P = P; A.post_mode = post_mode; A.pw_const = pw_const; A.leap = leap;
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
-    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN, FL>(m, A, smem, inl.v);
+    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN, FL, LAT>(m, A, smem, inl.v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1646,7 +1681,7 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
             A.in = s_qp; A.ll_out = s_lpp; A.g_out = s_gp;
             A.leap = HmcLeap{s_p, s_qp, s_im, R.eps, last ? 0.5 * R.eps : R.eps, last ? 0 : 1, 0, tempered ? s_beta : nullptr, tempered ? s_llp : nullptr};
         }
-        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN, 3>(m, A, smem, nullptr);
+        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN, 3, true>(m, A, smem, nullptr);
         __syncthreads();
 #ifdef OCTO_TIMING
         if (blockIdx.x == 0 && tid == 0 && it == R.n_iter - 1 && l == R.n_leapfrog - 1) {
@@ -1702,24 +1737,18 @@ __global__ void k_selftest_kepler(const double* __restrict__ MA, const double* _
 
 }  // namespace
 
-cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c) {
-    k_selftest_kepler<<<(unsigned)((n + 255) / 256), 256>>>(d_MA, d_e, n, d_s, d_c);
-    return cudaGetLastError();
-}
-
-// D > 0: with the fused parameterisation stage (D parameters, T θ_at_epoch_to_tperi definitions)
-size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
-    size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * (m.n_in + m.n_planets) * 32;      // the epilogue's gradient parts reuse the accumulator area
-    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
-    if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32;
-    return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
-}
-
+// ---------------------------------------------------------------------------------------------
+// Host side.  build.py compiles this file once per planet-count instantiation (-DOCTO_NPT=1, 2, 4: three objects, in
+// parallel — one object with every instantiation takes > 5 minutes) and per lean / full kernel family (-DOCTO_LEANSEL); each
+// object exports its entry points as an OctoNptEntry, and the (1 planet, full) object also holds the dispatchers.  Without
+// -DOCTO_NPT everything is one object.
+// ---------------------------------------------------------------------------------------------
+namespace {
 template <bool GRAD, int NPT, bool LAT, bool LEAN, int FL>
-static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
-                            double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
-                            const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
-                            cudaStream_t st, const InlineIn* inl) {
+cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double* d_in, int64_t n, int64_t ld,
+                     double* d_ll, double* d_g, int64_t ldg, double* d_partial, unsigned int* d_tickets,
+                     const DevParam* d_param, int post_mode, const double* d_pw_const, const HmcLeap& leap,
+                     cudaStream_t st, const InlineIn* inl) {
     // programmatic dependent launch: the kernel lets the next launch on the stream be scheduled while it is still
     // running (griddepcontrol.launch_dependents) and itself waits for everything before it in the stream to complete
     // and become visible before it touches memory (griddepcontrol.wait) — stream semantics, minus the launch gap
@@ -1738,25 +1767,113 @@ static cudaError_t launch_t(const DevModel& m, const LaunchGeom& g, const double
 }
 
 // opt every instantiation in to the device's full dynamic shared memory (a per-function, process-wide attribute:
-// contexts of different sizes must not shrink it for each other), and report the resident CTAs per SM of the
-// gradient kernel this model dispatches to (drives the launch geometry)
-cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
+// contexts of different sizes must not shrink it for each other)
+template <int NPT, bool LEAN>
+cudaError_t npt_attr(size_t smem_optin) {
     cudaError_t e;
-#define OCTO_ATTR1(G, N, L, Q, F)                                                                                  \
-    e = cudaFuncSetAttribute(k_kepler_like<G, N, L, Q, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin); \
+#define OCTO_ATTR1(G, L, F)                                                                                          \
+    e = cudaFuncSetAttribute(k_kepler_like<G, NPT, L, LEAN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin); \
     if (e != cudaSuccess) return e
-#define OCTO_ATTR(G, N) OCTO_ATTR1(G, N, false, false, 0); OCTO_ATTR1(G, N, true, false, 0); OCTO_ATTR1(G, N, false, true, 1); \
-    OCTO_ATTR1(G, N, true, true, 1); OCTO_ATTR1(G, N, false, true, 2); OCTO_ATTR1(G, N, true, true, 2)
-    OCTO_ATTR(true, 1); OCTO_ATTR(false, 1); OCTO_ATTR(true, 2); OCTO_ATTR(false, 2); OCTO_ATTR(true, 4); OCTO_ATTR(false, 4);
-#undef OCTO_ATTR
+    if constexpr (LEAN) { OCTO_ATTR1(true, false, 1); OCTO_ATTR1(true, true, 1); OCTO_ATTR1(true, false, 2); OCTO_ATTR1(true, true, 2);
+                          OCTO_ATTR1(false, false, 1); OCTO_ATTR1(false, true, 1); OCTO_ATTR1(false, false, 2); OCTO_ATTR1(false, true, 2); }
+    else { OCTO_ATTR1(true, false, 0); OCTO_ATTR1(true, true, 0); OCTO_ATTR1(false, false, 0); OCTO_ATTR1(false, true, 0); }
 #undef OCTO_ATTR1
-#define OCTO_OCC(N) (m.lean ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, true, 1>, W * 32, smem_bytes) \
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, N, false, false, 0>, W * 32, smem_bytes))
-    if (m.n_planets == 1) e = OCTO_OCC(1);
-    else if (m.n_planets == 2) e = OCTO_OCC(2);
-    else e = OCTO_OCC(4);
-#undef OCTO_OCC
-    return e;
+    return cudaFuncSetAttribute(k_hmc_resident<NPT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+}
+// resident CTAs per SM of the gradient kernel (throughput instantiation) this model dispatches to: drives the launch geometry
+template <int NPT, bool LEAN>
+cudaError_t npt_occupancy(const DevModel&, int W, size_t smem_bytes, int* ctas_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_kepler_like<true, NPT, false, LEAN, LEAN ? 1 : 0>, W * 32, smem_bytes);
+}
+template <int NPT, bool LEAN>
+cudaError_t npt_launch(const DevModel& m, const LaunchGeom& g, bool grad, const double* d_in, int64_t n_chains,
+                       int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
+                       unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
+                       const HmcLeap& leap, cudaStream_t st, const InlineIn* inl) {
+#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl
+#define OCTO_DISPATCH2(F)                                                                                         \
+    if (g.lat) return grad ? launch_t<true, NPT, true, LEAN, F>(OCTO_ARGS) : launch_t<false, NPT, true, LEAN, F>(OCTO_ARGS);   \
+    return grad ? launch_t<true, NPT, false, LEAN, F>(OCTO_ARGS) : launch_t<false, NPT, false, LEAN, F>(OCTO_ARGS)
+    // lean models: separate instantiations with and without the parameterisation stage (see eval_cta, FL)
+    if constexpr (LEAN) {
+        if (d_param) { OCTO_DISPATCH2(2); }
+        OCTO_DISPATCH2(1);
+    } else {
+        OCTO_DISPATCH2(0);
+    }
+#undef OCTO_DISPATCH2
+#undef OCTO_ARGS
+}
+template <int NPT, bool LEAN>
+cudaError_t npt_resident(const DevModel& m, const cudaLaunchConfig_t* cfg, const DevParam* d_param, const ResidentArgs& R, int ch, int eval_doubles) {
+    return cudaLaunchKernelEx(cfg, k_hmc_resident<NPT, LEAN>, m, d_param, R, ch, eval_doubles);
+}
+#define OCTO_ENTRY(N, L) {&npt_attr<N, L>, &npt_occupancy<N, L>, &npt_launch<N, L>, &npt_resident<N, L>}
+}  // namespace
+
+// which instantiations this object holds: all of them, or (build.py) -DOCTO_NPT=1|2|4 -DOCTO_LEANSEL=0|1
+#ifdef OCTO_NPT
+#define OCTO_HAS(N, L) (OCTO_NPT == N && OCTO_LEANSEL == L)
+#else
+#define OCTO_HAS(N, L) 1
+#endif
+#ifdef OCTO_NPT_ONLY1                // tuning builds (profiles/tools/ab.sh): one-planet kernels only
+#define OCTO_HAS_MULTI(N, L) 0
+#else
+#define OCTO_HAS_MULTI(N, L) OCTO_HAS(N, L)
+#endif
+#if OCTO_HAS(1, 0)
+extern const OctoNptEntry octo_entry_n1_full = OCTO_ENTRY(1, false);
+#endif
+#if OCTO_HAS(1, 1)
+extern const OctoNptEntry octo_entry_n1_lean = OCTO_ENTRY(1, true);
+#endif
+#if OCTO_HAS_MULTI(2, 0)
+extern const OctoNptEntry octo_entry_n2_full = OCTO_ENTRY(2, false);
+#endif
+#if OCTO_HAS_MULTI(2, 1)
+extern const OctoNptEntry octo_entry_n2_lean = OCTO_ENTRY(2, true);
+#endif
+#if OCTO_HAS_MULTI(4, 0)
+extern const OctoNptEntry octo_entry_n4_full = OCTO_ENTRY(4, false);
+#endif
+#if OCTO_HAS_MULTI(4, 1)
+extern const OctoNptEntry octo_entry_n4_lean = OCTO_ENTRY(4, true);
+#endif
+
+#if OCTO_HAS(1, 0)                   // this object also holds the dispatchers
+#ifdef OCTO_NPT_ONLY1
+extern const OctoNptEntry octo_entry_n2_full = {nullptr, nullptr, nullptr, nullptr}, octo_entry_n2_lean = {nullptr, nullptr, nullptr, nullptr};
+extern const OctoNptEntry octo_entry_n4_full = {nullptr, nullptr, nullptr, nullptr}, octo_entry_n4_lean = {nullptr, nullptr, nullptr, nullptr};
+#endif
+extern const OctoNptEntry octo_entry_n1_lean, octo_entry_n2_full, octo_entry_n2_lean, octo_entry_n4_full, octo_entry_n4_lean;
+static const OctoNptEntry& entry_of(const DevModel& m) {
+    if (m.n_planets == 1) return m.lean ? octo_entry_n1_lean : octo_entry_n1_full;
+    if (m.n_planets == 2) return m.lean ? octo_entry_n2_lean : octo_entry_n2_full;
+    return m.lean ? octo_entry_n4_lean : octo_entry_n4_full;
+}
+
+cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, int64_t n, double* d_s, double* d_c) {
+    k_selftest_kepler<<<(unsigned)((n + 255) / 256), 256>>>(d_MA, d_e, n, d_s, d_c);
+    return cudaGetLastError();
+}
+
+// D > 0: with the fused parameterisation stage (D parameters, T θ_at_epoch_to_tperi definitions)
+size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
+    size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * (m.n_in + m.n_planets) * 32;      // the epilogue's gradient parts reuse the accumulator area
+    size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
+    if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32;
+    return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
+}
+
+cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
+    for (const OctoNptEntry* en : {&octo_entry_n1_full, &octo_entry_n1_lean, &octo_entry_n2_full, &octo_entry_n2_lean, &octo_entry_n4_full, &octo_entry_n4_lean}) {
+        if (!en->attr) continue;
+        const cudaError_t e = en->attr(smem_optin);
+        if (e != cudaSuccess) return e;
+    }
+    const OctoNptEntry& en = entry_of(m);
+    return en.occupancy ? en.occupancy(m, W, smem_bytes, ctas_per_sm) : cudaErrorNotSupported;
 }
 
 // d_param != nullptr: d_in is θ_t [n x D], d_ll receives the log posterior (post_mode 1: its likelihood part) and d_g
@@ -1766,34 +1883,16 @@ cudaError_t octo_launch(const DevModel& m, const LaunchGeom& g, bool grad, const
                         int64_t ld, double* d_ll, double* d_g, int64_t ldg, double* d_partial,
                         unsigned int* d_tickets, const DevParam* d_param, int post_mode, const double* d_pw_const,
                         const HmcLeap& leap, cudaStream_t st, const InlineIn* inl) {
-#define OCTO_ARGS m, g, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl
-#define OCTO_DISPATCH2(NPT, L, F)                                                                                 \
-    if (g.lat) return grad ? launch_t<true, NPT, true, L, F>(OCTO_ARGS) : launch_t<false, NPT, true, L, F>(OCTO_ARGS);   \
-    return grad ? launch_t<true, NPT, false, L, F>(OCTO_ARGS) : launch_t<false, NPT, false, L, F>(OCTO_ARGS)
-    // lean models: separate instantiations with and without the parameterisation stage (see eval_cta, FL)
-#define OCTO_DISPATCH(NPT)                                                                                         \
-    if (m.lean && d_param) { OCTO_DISPATCH2(NPT, true, 2); }                                                        \
-    else if (m.lean) { OCTO_DISPATCH2(NPT, true, 1); }                                                              \
-    else { OCTO_DISPATCH2(NPT, false, 0); }
-    if (m.n_planets == 1) { OCTO_DISPATCH(1); }
-    if (m.n_planets == 2) { OCTO_DISPATCH(2); }
-    OCTO_DISPATCH(4);
-#undef OCTO_DISPATCH
-#undef OCTO_DISPATCH2
-#undef OCTO_ARGS
+    const OctoNptEntry& en = entry_of(m);
+    if (!en.launch) return cudaErrorNotSupported;
+    return en.launch(m, g, grad, d_in, n_chains, ld, d_ll, d_g, ldg, d_partial, d_tickets, d_param, post_mode, d_pw_const, leap, st, inl);
 }
 
 // ---- trajectory-resident explorer
 size_t octo_resident_smem_bytes(const DevModel& m, int D, int T) {
     return octo_smem_bytes(m, OCTO_LAT_WARPS, D, T) + ((size_t)(6 * D + 7) * 32 + (size_t)D) * sizeof(double);
 }
-cudaError_t octo_resident_init(const DevModel& m, size_t smem_optin) {
-    cudaError_t e = cudaSuccess;
-#define OCTO_ATTR(N, L) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hmc_resident<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin)
-    OCTO_ATTR(1, false); OCTO_ATTR(2, false); OCTO_ATTR(4, false); OCTO_ATTR(1, true); OCTO_ATTR(2, true); OCTO_ATTR(4, true);
-#undef OCTO_ATTR
-    return e;
-}
+cudaError_t octo_resident_init(const DevModel&, size_t) { return cudaSuccess; }      // attributes: octo_kernels_init
 cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int T, const ResidentArgs& R, int ch, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     const size_t eval_bytes = octo_smem_bytes(m, OCTO_LAT_WARPS, R.D, T);
@@ -1803,11 +1902,8 @@ cudaError_t octo_resident_launch(const DevModel& m, const DevParam* d_param, int
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const int eval_doubles = (int)((eval_bytes + 7) / 8);
-#define OCTO_RES(N) (m.lean ? cudaLaunchKernelEx(&cfg, k_hmc_resident<N, true>, m, d_param, R, ch, eval_doubles) \
-                            : cudaLaunchKernelEx(&cfg, k_hmc_resident<N, false>, m, d_param, R, ch, eval_doubles))
-    if (m.n_planets == 1) return OCTO_RES(1);
-    if (m.n_planets == 2) return OCTO_RES(2);
-    return OCTO_RES(4);
-#undef OCTO_RES
+    const OctoNptEntry& en = entry_of(m);
+    if (!en.resident) return cudaErrorNotSupported;
+    return en.resident(m, &cfg, d_param, R, ch, (int)((eval_bytes + 7) / 8));
 }
+#endif   // dispatchers

@@ -14,13 +14,13 @@ namespace octo_param_dev {
 
 constexpr double kTwoPi = 6.283185307179586477, kPi = 3.14159265358979323846, kHalfLog2Pi = 0.91893853320467274178;
 
-// libm behind out-of-line wrappers: every call site of the parameterisation stage shares one copy of exp / log /
-// atan2 / sincos.  The stage runs once per CTA and is bound by instruction fetch (≈ 12 cycles per instruction executed
-// for the first time), so code that is fetched once instead of at each of its ~15 call sites is time saved.
-static __device__ __noinline__ double p_exp(double x) { return exp(x); }
-static __device__ __noinline__ double p_log(double x) { return log(x); }
-static __device__ __noinline__ double p_atan2(double y, double x) { return atan2(y, x); }
-static __device__ __noinline__ void p_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+// libm wrappers (one place to change how the parameterisation stage calls exp / log / atan2 / sincos).  Inline: round 1
+// kept one out-of-line copy for all ~15 call sites (smaller code, no difference then); with the stage itself inline the
+// calls cost 3.5 % of a leapfrog (register spills around each call, see octo_kernels.cu "INLINE OR OUT OF LINE").
+static __device__ __forceinline__ double p_exp(double x) { return exp(x); }
+static __device__ __forceinline__ double p_log(double x) { return log(x); }
+static __device__ __forceinline__ double p_atan2(double y, double x) { return atan2(y, x); }
+static __device__ __forceinline__ void p_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 
 struct PriorEval { double x, dxdy, L, dLdx; };
 
@@ -28,7 +28,7 @@ struct PriorEval { double x, dxdy, L, dLdx; };
 // pc = per-prior constants prepared by octo_set_parameterization (DevParam::pc):
 //   [0] lower bound, [1] upper bound (±Inf when open), [2] the constant part of the log density
 //   (Normal: -log σ - ½log 2π - log(Φ(β)-Φ(α)); Uniform: -log(b-a); LogUniform: -log(log(b/a))), [3] 1/(hi-lo), [4] 1/σ
-static __device__ __noinline__ PriorEval prior_eval(int family, double mu, const double* __restrict__ pc, double y) {
+static __device__ __forceinline__ PriorEval prior_eval(int family, double mu, const double* __restrict__ pc, double y) {
     PriorEval r;
     const double lo = pc[0], hi = pc[1];
     const bool lb = isfinite(lo), ub = isfinite(hi);
@@ -176,7 +176,7 @@ __device__ __forceinline__ TperiMid tperi_mid(const OctoConstants& c, const doub
     }
     return m;
 }
-static __device__ __noinline__ double tperi_value(const OctoConstants& c, double t_ref, const double* arg, const double* trig,
+static __device__ __forceinline__ double tperi_value(const OctoConstants& c, double t_ref, const double* arg, const double* trig,
                                               double* MA_out, bool ti, double* keep = nullptr, int ks = 0) {
     const TperiMid m = tperi_mid(c, arg, trig, ti, keep, nullptr, ks);
     const double MA = p_atan2(m.u, m.v) + kPi - m.q;
@@ -187,7 +187,7 @@ static __device__ __noinline__ double tperi_value(const OctoConstants& c, double
 // hand-derived reverse pass: grad[q] = ∂tp/∂arg[q] (7 entries, or 8 for the Thiele-Innes branch).  Cheap arithmetic only
 // (the forward intermediates are recomputed, MA comes from the forward pass); this replaced forward-mode dual
 // evaluations whose code size made the once-per-CTA reverse stage instruction-fetch bound.
-static __device__ __noinline__ void tperi_reverse(const OctoConstants& c, const double* arg, const double* trig, double MA,
+static __device__ __forceinline__ void tperi_reverse(const OctoConstants& c, const double* arg, const double* trig, double MA,
                                               double* grad, bool ti, const double* reuse = nullptr, int ks = 0) {
     const double st = trig[0], ct = trig[1];
     const double M = arg[1], e = arg[2];
