@@ -483,7 +483,8 @@ def main():
     pt_nccl = c4_parallel_tempering(octo, workloads, torch, dist, rank, world, local) if world > 1 else None
     # sanity: device path and host path agree (set 0 of the pool is the workload itself)
     if not os.environ.get("OCTO_B200_LIB"):
-        assert np.array_equal(d_ll.cpu().numpy(), ll_h), "device-resident and host-API results differ"
+        # (d_ll was last written by the value-only kernel: its own instantiation, same sums to the last bit or two)
+        assert np.allclose(d_ll.cpu().numpy(), ll_h, rtol=1e-13, atol=0), "device-resident and host-API results differ"
         assert np.array_equal(d_ll_all[0].cpu().numpy(), ll_h), "timed-region results differ from the host API's"
 
     if rank == 0:

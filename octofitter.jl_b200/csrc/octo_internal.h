@@ -10,7 +10,7 @@
 #define OCTO_WARPS 8              // warps per CTA: each warp owns one contiguous epoch range
 #endif
 #ifndef OCTO_LAT_WARPS
-#define OCTO_LAT_WARPS 8          // warps per CTA of the latency-tuned instantiation (one CTA per SM)
+#define OCTO_LAT_WARPS 12         // warps per CTA of the latency-tuned instantiation (one CTA per SM, <= 168 registers); 6 / 8 / 10 / 12 / 14 / 16 measured: C2 12.0 / 9.8 / 9.8 / 8.9 / 9.6 / 9.2 us per step
 #endif
 #define OCTO_LANES 32             // lanes = chains of one chain group
 #define OCTO_MIN_SLICE 2          // fewest epochs worth giving a warp

@@ -1007,6 +1007,10 @@ __device__ int g_quiet;      // set by the resident kernel: phase timings are pr
 // trig: per θ_at_epoch_to_tperi definition 16 slots — sin, cos of (θ, i, ω, Ω), the mean anomaly, then the reciprocals and
 // roots of its forward pass (tperi_mid `keep`); cir: [2][n_in] what circ_forward saves for the reverse pass
 constexpr int TRIG_SLOTS = 16;
+// DevParam staged in shared memory (the last kParamWords doubles of the evaluation's area): the parameterisation stages
+// chase order -> prior / definition -> operand indices several times per phase, each a dependent L2 round trip (~300 cycles)
+// when read from global memory — ~1.5 us of a 12 us leapfrog
+constexpr int kParamWords = (int)((sizeof(DevParam) + 7) / 8);
 struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *cir, *trig, *part, *lp, *extra, *beta; int* flags; };
 __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
     ParamSmem S;
@@ -1269,6 +1273,7 @@ struct EvalArgs {
     double* ll_out; double* g_out; int64_t ldg;
     double* partial; unsigned int* tickets;
     const DevParam* P; int post_mode; const double* pw_const;
+    DevParam* P_smem;            // where the CTA keeps its copy of *P (FL 3: already filled by the caller), or nullptr
     HmcLeap leap;
     int ch;                      // chains per CTA: 32 / sub-lanes (see below)
     int64_t chain0;              // first chain of this CTA
@@ -1295,8 +1300,14 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
     const int n_acc = m.n_acc;
     const int ch = A.ch, col_c = lane & (ch - 1);
     const int64_t n_chains = A.n_chains, ld = A.ld, ldg = A.ldg;
-    const DevParam* P = FL == 1 ? nullptr : A.P;
-    if (FL >= 2) __builtin_assume(P != nullptr);
+    const DevParam* Pg = FL == 1 ? nullptr : A.P;              // in global memory
+    if (FL >= 2) __builtin_assume(Pg != nullptr);
+    if (FL != 3 && Pg && A.P_smem) {                          // stage it (visible after the barrier below)
+        const double* src = reinterpret_cast<const double*>(Pg);
+        double* dst = reinterpret_cast<double*>(A.P_smem);
+        for (int i = threadIdx.x; i < kParamWords; i += blockDim.x) dst[i] = src[i];
+    }
+    const DevParam* P = (Pg && A.P_smem) ? A.P_smem : Pg;
     const int post_mode = FL == 3 ? 0 : A.post_mode;
     const double* pw_const = FL == 3 ? nullptr : A.pw_const;
     const int n_split = FL == 3 ? 1 : A.gy;                   // epoch splits of a chain group across CTAs
@@ -1327,7 +1338,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 
     if (threadIdx.x < 32) {
         s_ok[threadIdx.x] = 1;
-        if (P) param_smem(s_in + m.n_in * 32, m.n_in, P->D, P->n_tperi).flags[threadIdx.x] = 0;
+        if (Pg) param_smem(s_in + m.n_in * 32, m.n_in, Pg->D, Pg->n_tperi).flags[threadIdx.x] = 0;      // (the copy is not visible yet)
     }
     // the value-only kernel of a model without non-linear folds (marginalised RV, observable prior) needs one sum: ll
     const int n_use = (!GRAD && !(!LEAN && m.has_margin)) ? 1 : n_acc;
@@ -1375,7 +1386,8 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
         // ---- this warp's contiguous range of the concatenated epoch list: unit u of U.  With sub-lanes, the part of
         //      every table inside the warp's range is divided evenly among the S sub-lanes (a warp whose range crosses
         //      a table boundary keeps all its sub-lanes busy in both tables)
-        const int S = 32 / ch, sub = lane / ch;
+        const int lch = 31 - __clz(ch);                                // ch and S are powers of two: shifts, not divisions
+        const int S = 32 >> lch, sub = lane >> lch;
         const int64_t U = (int64_t)n_split * W, u = (int64_t)A.by * W + w;
         // contiguous range of the COST-weighted epoch list (an RV+jitter epoch costs ~1.8 lean astrometry epochs)
         // (latency-bound launches weigh a pair by its dependent chain instead of its instruction count)
@@ -1389,8 +1401,9 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
             int k1 = B.start + min(B.n, max(0, (int)ceil(fmin((w_hi - bcum) / bwgt, 2.0e9))));
             if (S > 1) {
                 const int len = max(0, k1 - k0), base = k0;
-                k0 = base + (int)(((int64_t)len * sub) / S);
-                k1 = base + (int)(((int64_t)len * (sub + 1)) / S);
+                const int sh = 5 - lch;                                     // log2 S (no 64-bit division subroutine)
+                k0 = base + (int)(((int64_t)len * sub) >> sh);
+                k1 = base + (int)(((int64_t)len * (sub + 1)) >> sh);
             }
             if (pw_const) {      // pointwise mode (ch = 32): this CTA evaluates the single epoch `by` (warp 0)
                 const int ep = A.by + (post_mode >> 9);                     // + first epoch of this chunk (grid.y <= 65535)
@@ -1516,7 +1529,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
             PS.beta[lane] = bet;
             if (A.leap.ll_raw && active) A.leap.ll_raw[chain0 + lane] = ok ? llv : -CUDART_INF;
             // post_mode 1: the likelihood part alone, ln_like(system, arr2nt(θ)) incl. the UnitLengthPrior terms
-            const double like = PS.extra[lane] + bet * llv;
+            const double like = fma(bet, llv, PS.extra[lane]);
             if (active) A.ll_out[chain0 + lane] = !(fl & 1) ? -CUDART_INF : (ok ? ((post_mode & 255) == 1 ? like : PS.lp[lane] + like) : -CUDART_INF);
             PS.flags[lane] = fl | (ok ? 8 : 0);
         }
@@ -1582,6 +1595,12 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     EvalArgs A;
     A.in = in; A.n_chains = n_chains; A.ld = ld; A.ll_out = ll_out; A.g_out = g_out; A.ldg = ldg;
     A.partial = partial; A.tickets = tickets; A.P = P; A.post_mode = post_mode; A.pw_const = pw_const; A.leap = leap;
+    A.P_smem = nullptr;
+    if (FL != 1 && P) {
+        unsigned dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        A.P_smem = reinterpret_cast<DevParam*>(smem + (dyn >> 3) - kParamWords);
+    }
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
     eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN, FL, LAT>(m, A, smem, inl.v);
 }
@@ -1629,6 +1648,8 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
         s_q[it] = col < nvalid ? R.q[chain0 + col + (int64_t)j * R.n] : 0.0;
     }
     if (tid < D) s_im[tid] = R.inv_mass[tid];
+    DevParam* sP = reinterpret_cast<DevParam*>(smem + eval_doubles - kParamWords);      // staged once for the whole run
+    for (int i = tid; i < kParamWords; i += nthr) reinterpret_cast<double*>(sP)[i] = reinterpret_cast<const double*>(P)[i];
     if (tid < 32) {
         s_beta[tid] = (tempered && tid < nvalid) ? R.beta[chain0 + tid] : 1.0;
         s_acc[tid] = 0.0; s_ll[tid] = 0.0; s_llp[tid] = 0.0;
@@ -1636,7 +1657,7 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
     __syncthreads();
 
     EvalArgs A;
-    A.n_chains = nvalid; A.ld = 32; A.ldg = 32; A.partial = nullptr; A.tickets = nullptr; A.P = P; A.post_mode = 0;
+    A.n_chains = nvalid; A.ld = 32; A.ldg = 32; A.partial = nullptr; A.tickets = nullptr; A.P = P; A.P_smem = sP; A.post_mode = 0;
     A.pw_const = nullptr; A.ch = ch; A.chain0 = 0; A.group = blockIdx.x; A.gy = 1; A.by = 0; A.lat_weights = true;
     // fresh momentum, first half kick and drift: one (chain, coordinate) item per thread
     auto start_transition = [&](int it) {
@@ -1862,7 +1883,7 @@ cudaError_t octo_selftest_kepler_launch(const double* d_MA, const double* d_e, i
 size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
     size_t acc = (size_t)W * m.n_acc * 32, gp = (size_t)EPI_PARTS * (m.n_in + m.n_planets) * 32;      // the epilogue's gradient parts reuse the accumulator area
     size_t d = (size_t)m.n_planets * PC_COUNT * 32 + (acc > gp ? acc : gp) + (size_t)m.n_acc * 32 + (size_t)m.n_in * 32;
-    if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32;
+    if (D > 0) d += param_smem_doubles(m.n_in, D, T) + 32 + kParamWords;         // + the CTA's own copy of DevParam (at the end)
     return d * sizeof(double) + (size_t)W * 96 * sizeof(double2) + (size_t)32 * sizeof(int);
 }
 

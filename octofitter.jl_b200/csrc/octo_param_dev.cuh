@@ -58,7 +58,7 @@ static __device__ __forceinline__ PriorEval prior_eval(int family, double mu, co
     switch (family) {
         case OCTO_PRIOR_NORMAL: case OCTO_PRIOR_TRUNCNORMAL: {
             const double z = (x - mu) * pc[4];
-            lp = -0.5 * z * z + pc[2]; dlp = -z * pc[4]; break;
+            lp = fma(-0.5 * z, z, pc[2]); dlp = -z * pc[4]; break;       // (explicit: see circ_forward)
         }
         case OCTO_PRIOR_LOGUNIFORM: lp = -p_log(x) + pc[2]; dlp = -1.0 / x; break;
         case OCTO_PRIOR_SINE: { double sn, cs; p_sincos(x, &sn, &cs); lp = p_log(sn * 0.5); dlp = cs / sn; break; }
@@ -75,9 +75,12 @@ static __device__ __forceinline__ PriorEval prior_eval(int family, double mu, co
 __device__ __forceinline__ void circ_forward(double x, double y, double domain, double& v, double& ext, double* ir2_out = nullptr,
                                              double* dfdlr_out = nullptr) {
     v = p_atan2(y, x) * (domain / kTwoPi);
-    const double r2 = x * x + y * y, l2 = p_log(r2);
+    // explicit fma / rounded products wherever a*b+c appears on a value-only path: the stage is inlined into several
+    // kernels, and left to the compiler each instantiation may contract differently (a last-bit difference in lp between
+    // the resident explorer and the launch-per-leapfrog one)
+    const double r2 = fma(x, x, y * y), l2 = p_log(r2);
     const double lr = 0.5 * l2;
-    ext = -lr - (-2.302585092994045684 /* log 0.1 */) - kHalfLog2Pi - lr * lr * 50.0;
+    ext = fma(-lr * lr, 50.0, -lr - (-2.302585092994045684 /* log 0.1 */) - kHalfLog2Pi);
     if (ir2_out) { *ir2_out = 1.0 / r2; *dfdlr_out = -1.0 - 0.5 * l2 * 100.0; }
 }
 // gk = ∂/∂angle; returns the contributions to ∂/∂x and ∂/∂y (angle and UnitLengthPrior)

@@ -485,7 +485,7 @@ def test_every_observation_kind_in_one_model(oracle_lib, n_planets):
     assert rel_err(ll, ll_o).max() < LOGP_RTOL and grad_err(g, g_o).max() < GRAD_RTOL
     assert rel_err(model.ln_like(x), ll_o).max() < LOGP_RTOL
     geom = model.launch_geometry(70)
-    assert geom[2] in (64, 128, 256)
+    assert geom[2] in (64, 128, 256, 384)          # 384: the latency-tuned instantiation (12 warps)
 
 
 def test_thiele_innes_planets_with_hgca_and_observable_prior(oracle_lib):

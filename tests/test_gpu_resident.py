@@ -1,7 +1,10 @@
 """The trajectory-resident HMC kernel (k_hmc_resident: a chain group's whole run — transitions x leapfrogs — inside one
 launch, state in shared memory) against the launch-per-leapfrog explorer it replaces.  With both on the same geometry
-(same sub-lane count, same CTA width, no epoch splits across CTAs) the two must agree BIT FOR BIT: same evaluation
-body, same per-coordinate arithmetic (octo_hmc_dev.cuh), same counter-based random streams."""
+(same sub-lane count, same CTA width, no epoch splits across CTAs) the two must produce the same TRAJECTORIES bit for bit —
+positions, gradients, accept decisions: same evaluation body, same per-coordinate arithmetic (octo_hmc_dev.cuh), same
+counter-based random streams.  The log-posterior VALUES they report may differ in the last bit (relative 2e-16 seen):
+since round 2 the evaluation is inlined into each kernel and the compiler contracts a*b+c on the value-only path
+per instantiation (building with -fmad=false makes them identical again, at +4 % per leapfrog)."""
 import os
 
 import numpy as np
@@ -12,6 +15,14 @@ import workloads
 from helpers import reference_test_system
 
 pytestmark = pytest.mark.gpu
+
+
+def _same(res, ref, keys):
+    for k in keys:
+        if k.startswith("logpost"):
+            np.testing.assert_allclose(res[k], ref[k], rtol=4e-15, atol=0, err_msg=k)
+        else:
+            assert np.array_equal(res[k], ref[k]), k
 
 
 def _both(model, th0, n_iter, **kw):
@@ -39,15 +50,13 @@ def test_resident_equals_launch_per_leapfrog_bit_for_bit(monkeypatch, force):
     inv_mass = octo.diagonal_metric(model, start)
     th0 = np.asfortranarray(start[None, :] + 0.1 * np.sqrt(inv_mass)[None, :] * rng.standard_normal((77, spec.D)))
     res, ref = _both(model, th0, 9, step_size=0.15, n_leapfrog=5, inv_mass=inv_mass, seed=99)
-    for k in ("theta", "logpost", "theta_final", "logpost_final", "accept"):
-        assert np.array_equal(res[k], ref[k]), k
+    _same(res, ref, ("theta", "logpost", "theta_final", "logpost_final", "accept"))
     assert 0.3 < res["accept_rate"] <= 1.0
     model.close()
     spec_p, th_p = workloads.one_planet_with_priors(100, 100, 200, seed=2)
     model = octo.LogDensityModel(spec_p)
     res, ref = _both(model, th_p, 4, step_size=1e-3, n_leapfrog=6, inv_mass=np.full(spec_p.D, 1e-4), seed=5)
-    for k in ("theta", "logpost", "theta_final", "logpost_final", "accept"):
-        assert np.array_equal(res[k], ref[k]), k
+    _same(res, ref, ("theta", "logpost", "theta_final", "logpost_final", "accept"))
     model.close()
 
 
