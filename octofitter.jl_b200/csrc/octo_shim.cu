@@ -66,12 +66,17 @@ struct OctoCtx {
     std::vector<Workspace*> pool;                                  // host-buffer calls: leased per call
     std::vector<std::pair<cudaStream_t, Workspace*>> stream_ws;    // device-buffer calls: one per caller stream
     std::atomic<int64_t> launches{0};
+    struct GeomEntry { int64_t n; bool fused; int sub; int param_gen; LaunchGeom g; };
+    std::mutex geom_mu;
+    std::vector<GeomEntry> geom_cache;                             // geometry(): results by batch size
+    int param_gen = 0;                                             // bumped by octo_set_parameterization (fused shared-memory sizes change)
     int ctas_per_sm = 2;
     int warps = OCTO_WARPS;        // warps per CTA; halved until the model's accumulator slots fit in shared memory
     int slice_override = 0;
     int latency_mode = 1;          // OCTO_B200_LATENCY: 0 never, 1 automatic, 2 whenever the chain groups fit one per SM
     int resident_mode = 1;         // OCTO_B200_RESIDENT: 0 = explorers never use the trajectory-resident kernel
     int force[3] = {0, 0, 0};      // OCTO_B200_FORCE (experiments): sub-lanes, latency instantiation, epoch splits
+    double lat_cap = 300.0;        // OCTO_B200_LAT_CAP: most dependent pairs per lane a single wave of the latency instantiation may get
     int sublane_mode = 0;          // OCTO_B200_SUBLANES: 0 automatic, 1 never (lane = chain), 2..32 that many sub-lanes per chain
     // device-side parameterisation (N1)
     DevParam* d_param = nullptr;
@@ -250,7 +255,7 @@ LaunchGeom geometry_classic(const OctoCtx* ctx, int64_t n_chains, bool fused) {
 // model measured on C2's timeline — dependent pair evaluations per (warp, sub-lane) unit x ~0.55 us, + ~3.5 us when
 // the splits of a chain group have to be combined through L2.  Larger batches keep the classic geometry.
 // sub_override: 0 = automatic, otherwise the sub-lane count to use (1 = classic mapping).
-LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, int sub_override = 0) {
+LaunchGeom geometry_search(const OctoCtx* ctx, int64_t n_chains, bool fused, int sub_override) {
     if (sub_override == 0) sub_override = ctx->sublane_mode;
     LaunchGeom best = geometry_classic(ctx, n_chains, fused);
     const int64_t E = ctx->m.n_epochs;
@@ -268,13 +273,13 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
         return best;
     }
     if (sub_override == 1 || E < 1 || (sub_override == 0 && (n_chains + 31) / 32 >= resident)) return best;
-    // measured on C2 / C3 / C4 / 4096 x {10, 100, 316} (profiles/r02_geometry_sweep.txt): a lean-astrometry-equivalent
-    // pair costs a lane of the latency-tuned instantiation ~0.32 us (two pairs in flight), ~0.65 us in the throughput
-    // instantiation (two CTAs share the SM: the same pairs per SM and microsecond), which also has ~3 us more fixed cost
-    // per launch; the combine through L2 costs ~3.5 us.  The lane = chain choice above is priced by the same model, so a
+    // measured on C1 - C4 / 4096 x {10 ... 3162} / RV tables (profiles/r02_geometry_sweep.txt): a lean-astrometry-equivalent
+    // pair costs a lane of the latency-tuned instantiation ~0.42 us (12 warps, two pairs in flight), ~0.63 us in the throughput
+    // instantiation (two CTAs share the SM), which also has ~0.5 us more fixed cost per launch; the combine through L2 costs
+    // ~3.5 us.  The lane = chain choice above is priced by the same model, so a
     // single wave of the latency instantiation is taken when the model says it is the faster one, up to 128 dependent
     // pairs per lane (see below)
-    const double t_it[2] = {0.65, 0.32}, t_k2 = 3.5, t_thr = 3.0;
+    const double t_it[2] = {0.63, 0.42}, t_k2 = 3.5, t_thr = 0.5;
     const double ew[2] = {ctx->m.wtot > 0 ? ctx->m.wtot : 1.0, ctx->m.wtot_lat > 0 ? ctx->m.wtot_lat : 1.0};
     auto cost = [&](int S, bool lat, int64_t gy) {
         const int Wc = lat ? Wl : W;
@@ -310,10 +315,10 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
                 const double c = cost(S, lat, gy);
                 if (c < c_c - 1e-9) { c_c = c; gy_c = gy; }
             }
-            // a single wave is a latency play: the calibration above holds for a few dozen dependent pairs per lane; for
-            // long loops the throughput instantiation (16 warps per SM) is as fast on lean astrometry and 30 % faster on
-            // the radial-velocity loops (4096 x 20000 RV + jitter: 1077 vs 1643 us), so stop considering it there
-            if (sub_override <= 1 && std::ceil(ew[lat ? 1 : 0] / (double)(gy_c * Wc * S)) > 128.0) continue;
+            // a single wave is a latency play: for long loops the throughput instantiation (16 warps per SM) catches up —
+            // 4096 x 3162 lean astrometry (264 pairs per lane): 115 vs 124 us, x 10000: 352 vs 347; RV + jitter (weight
+            // 1.5): x 3162 171 vs 166, x 10000 521 vs 479 — so stop considering it beyond 300 weighted pairs per lane
+            if (sub_override <= 1 && std::ceil(ew[lat ? 1 : 0] / (double)(gy_c * Wc * S)) > ctx->lat_cap) continue;
             if (c_c < best_cost - 1e-9) {
                 best_cost = c_c;
                 best.gx = (int)gx; best.gy = (int)gy_c; best.ch = ch; best.lat = lat != 0; best.block = Wc * 32;
@@ -323,6 +328,21 @@ LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, in
         }
     }
     return best;
+}
+
+// the search runs once per (batch size, fused, override): samplers call with the same batch size millions of times
+LaunchGeom geometry(const OctoCtx* ctx, int64_t n_chains, bool fused = false, int sub_override = 0) {
+    OctoCtx* c = const_cast<OctoCtx*>(ctx);
+    {
+        std::lock_guard<std::mutex> lk(c->geom_mu);
+        for (const auto& e : c->geom_cache)
+            if (e.n == n_chains && e.fused == fused && e.sub == sub_override && e.param_gen == c->param_gen) return e.g;
+    }
+    const LaunchGeom g = geometry_search(ctx, n_chains, fused, sub_override);
+    std::lock_guard<std::mutex> lk(c->geom_mu);
+    if (c->geom_cache.size() >= 16) c->geom_cache.erase(c->geom_cache.begin());
+    c->geom_cache.push_back({n_chains, fused, sub_override, c->param_gen, g});
+    return g;
 }
 
 // d_param != nullptr: fused parameterisation — d_in is θ_t, d_ll / d_g receive the log posterior and its gradient
@@ -750,6 +770,7 @@ int octo_create(const OctoConstants* consts, const OctoLayout* L, const OctoObsB
             ctx->force[0] = a; ctx->force[1] = b; ctx->force[2] = c;
         }
     }
+    if (const char* s = getenv("OCTO_B200_LAT_CAP")) { const double v = atof(s); if (v >= 1.0) ctx->lat_cap = v; }
     if (const char* s = getenv("OCTO_B200_SUBLANES")) {
         const int v = atoi(s);
         if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) ctx->sublane_mode = v;
@@ -977,6 +998,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
     CU(cudaMemcpy(ctx->d_param, &P, sizeof(DevParam), cudaMemcpyHostToDevice));
     ctx->param_D = D; ctx->param_T = P.n_tperi;
     ctx->param_fused = fusable;
+    { std::lock_guard<std::mutex> lk(ctx->geom_mu); ++ctx->param_gen; ctx->geom_cache.clear(); }
     return OCTO_OK;
 }
 
