@@ -582,10 +582,11 @@ def sweep(octo, workloads, torch, peak, device):
         steps = 20 if E <= 10000 else 5
         ms = time_device(model, d_in, d_ll, d_g, n, steps, 3, torch, flush)
         kms = float(np.mean(ms))
-        fl = flops_per_launch(spec, n)
+        fl = flops_per_launch(spec, n, executed_flop_table()[0])          # EXECUTED flop (SASS counts), like roofline.frac
+        fl_model = flops_per_launch(spec, n)                               # SURVEY's planning weights: secondary
         rec = {"epochs": E, "chains": n, "kernel_ms": kms, "evals_per_s": n * E / (kms * 1e-3),
                "fp64_tflops": fl / (kms * 1e-3) / 1e12, "frac_fp64_peak": fl / (kms * 1e-3) / 1e12 / peak,
-               "geometry": list(model.launch_geometry(n))}
+               "frac_cost_model": fl_model / (kms * 1e-3) / 1e12 / peak, "geometry": list(model.launch_geometry_full(n))}
         out.write(json.dumps(rec) + "\n"); out.flush()
         print("sweep", json.dumps(rec), file=sys.stderr)
         model.close()

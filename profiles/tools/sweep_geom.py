@@ -49,7 +49,7 @@ def run(name, steps, force):
 
 if __name__ == "__main__":
     name = sys.argv[1]; steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-    run(name, 15000 if "x" not in name or int(name.split("x")[1].split("+")[0] or 0) < 2000 else 200, None)      # discarded: keeps the GPU busy long enough for the clocks to ramp up
+    run(name, 15000 if steps >= 100 else 10 * steps, None)      # discarded: keeps the GPU busy long enough for the clocks to ramp up
     cands = [None] + [f"{S},{lat},{gy}" for S in (1, 2, 4, 8, 16) for lat in (1, 0) for gy in (1, 2, 3, 4)]
     if len(sys.argv) > 3: cands = sys.argv[3:]
     for f in cands:
