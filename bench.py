@@ -412,10 +412,21 @@ def main():
         model.ln_like_and_gradient(x_pin, out=out)
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ll_h, g_h = model.ln_like_and_gradient(x_pin, out=out)
-    t_e2e_sync = time.perf_counter() - t0
+    # (host-timed regions of K steps are a few milliseconds: like the device regions, N_REGIONS of them, median reported)
+    def host_regions(fn):
+        ts = []
+        for _ in range(N_REGIONS):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), ts
+    def sync_steps():
+        global_out = None
+        for _ in range(args.steps):
+            global_out = model.ln_like_and_gradient(x_pin, out=out)
+        return global_out
+    ll_h, g_h = sync_steps()
+    t_e2e_sync, _ = host_regions(sync_steps)
     # the same steps through the asynchronous halves of the call (octo_logp_grad_begin / octo_wait), DEPTH independent
     # evaluations in flight: every step still copies its inputs host -> device and its (ll, gradient) device -> host
     # inside the timed region; the copies of one step overlap the kernel of another
@@ -435,9 +446,7 @@ def main():
     pipelined(max(3, min(args.warmup, 10)))
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    pipelined(args.steps)
-    t_e2e = time.perf_counter() - t0
+    t_e2e, e2e_regions = host_regions(lambda: pipelined(args.steps))
     assert np.array_equal(slots[0][1][0], ll_h) and np.array_equal(slots[(args.steps - 1) % DEPTH][1][1], g_h)
     # the same call with ordinary (pageable) numpy arrays, staged through the library's pinned buffers
     t0 = time.perf_counter()
@@ -535,10 +544,12 @@ def main():
                     "ms_per_step_synchronous_call": t_e2e_sync / args.steps * 1e3,
                     "ms_per_step_pageable_host_arrays": t_e2e_pageable / args.steps * 1e3,
                     "in_flight": DEPTH,
+                    "regions_ms_per_step": [t / args.steps * 1e3 for t in e2e_regions],
                     "api": "LogDensityModel.ln_like_and_gradient_begin(pinned host ndarray, out=pinned).wait() -> C ABI "
-                           "octo_logp_grad_begin / octo_wait, %d independent evaluations in flight: every step does its own H2D of the "
-                           "inputs, kernel, D2H of (ll, gradient); `ms_per_step_synchronous_call` is one blocking octo_logp_grad "
-                           "per step (the latency of a single call)" % DEPTH},
+                           "octo_logp_grad_begin / octo_wait, %d independent evaluations in flight: every step moves its own inputs host -> device "
+                           "and its (ll, gradient) device -> host inside the timed region — page-locked buffers of this size are read and "
+                           "written by the kernel in place over PCIe (no separate copy launches; OCTO_B200_ZEROCOPY_MAX=0 restores the "
+                           "H2D copy); `ms_per_step_synchronous_call` is one blocking octo_logp_grad per step (the latency of a single call)" % DEPTH},
             "value_only": {"what": "K1v, logp without gradient (Pigeons slice sampler / prior search), same workload, device-resident",
                        "value": n * E * world / (float(np.mean(ms_val)) * 1e-3), "unit": "evals/s", "ms_per_step": float(np.mean(ms_val))},
         "logpost_e2e": {"what": "full log-posterior + gradient w.r.t. the unconstrained vector (priors, bijectors, UniformCircular, "

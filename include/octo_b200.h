@@ -302,8 +302,11 @@ void octo_hmc_random(uint64_t seed, int64_t it, int64_t chain, int32_t D, double
 int  octo_invlink(OctoCtx* ctx, const double* theta_t, int64_t n_chains, int64_t ld, double* theta_nat);
 
 /* Page-locked host memory for the HOST-buffer entry points.  Buffers that come from octo_alloc_pinned
- * are copied to/from the device directly (no staging copy); any other host pointer works too and is
- * staged through the context's own pinned buffers.  Returns NULL on failure (see octo_last_error). */
+ * need no staging copy: outputs are written by the kernel straight into them, inputs of up to 512 KB (environment
+ * OCTO_B200_ZEROCOPY_MAX, bytes) are read by the kernel in place over PCIe and larger ones are copied to the device by
+ * the copy engine.  Like any asynchronous copy: do not touch the buffers of an octo_*_begin call before its octo_wait.
+ * Any other host pointer works too and is staged through the context's own pinned buffers.  Returns NULL on failure
+ * (see octo_last_error). */
 void* octo_alloc_pinned(size_t bytes);
 void  octo_free_pinned(void* p);
 

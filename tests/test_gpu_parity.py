@@ -542,6 +542,36 @@ def test_latency_and_throughput_instantiations_agree(oracle_lib, monkeypatch):
     assert rel_err(out["1"][0], out["0"][0]).max() < 1e-13
 
 
+@pytest.mark.parametrize("post", [False, True], ids=["likelihood", "fused-posterior"])
+def test_lean_and_full_kernel_families_agree(oracle_lib, monkeypatch, post):
+    """A model made of plain RA/Dec astrometry and RV tables runs the LEAN kernel family (compiled without the code of
+    the other tables: round 2); OCTO_B200_NO_LEAN=1 sends it through the full kernels.  Same sums in
+    the same order — agreement to rounding (the compiler contracts per instantiation) — and both against the oracle;
+    in both launch regimes (C2-sized: latency instantiation with sub-lanes; 4096 x 400: throughput, multi-wave)."""
+    import workloads
+    cases = [workloads.one_planet_with_priors(100, 100, 600, seed=3)] if post else \
+            [workloads.config("C2"), workloads.one_planet(200, 200, 4096, seed=9)]
+    for spec, x in cases:
+        out = {}
+        for mode in ("0", "1"):
+            if mode == "1":
+                monkeypatch.setenv("OCTO_B200_NO_LEAN", "1")
+            else:
+                monkeypatch.delenv("OCTO_B200_NO_LEAN", raising=False)
+            model = octo.LogDensityModel(spec)
+            out[mode] = model.ℓπcallback_grad(x) if post else model.ln_like_and_gradient(x)
+            model.close()
+        assert rel_err(out["0"][0], out["1"][0]).max() < 1e-13
+        assert grad_err(out["0"][1], out["1"][1]).max() < 1e-11
+        pick = np.arange(0, x.shape[0], max(1, x.shape[0] // 64))
+        if post:
+            lp_o, g_o = oracle_lib.logpost(spec, octo.default_constants(), x[pick], threads=4)
+        else:
+            lp_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(np.asfortranarray(x[pick]), threads=4)
+        for mode in ("0", "1"):
+            assert rel_err(out[mode][0][pick], lp_o).max() < LOGP_RTOL and grad_err(out[mode][1][pick], g_o).max() < GRAD_RTOL
+
+
 def test_pointwise_like_more_epochs_than_one_grid(oracle_lib):
     """More than 65535 epochs: octo_logp_pointwise walks the epoch list in chunks.  The columns sum to ln_like and
     spot-checked columns equal the oracle on the one-epoch model."""
