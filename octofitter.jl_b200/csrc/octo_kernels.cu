@@ -1219,6 +1219,10 @@ __device__ __noinline__ void seg_rv_ool(const DevModel& m, const DevBlock& B, in
                                         double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     seg_rv<GRAD, NPT, MARGIN, JIT, TREND, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
 }
+#ifndef OCTO_ILP1_FROM_NPT
+#define OCTO_ILP1_FROM_NPT 2       // table loops of kernels with at least this many planets keep ONE pair in flight per lane: two pairs x
+                                   // several orbits spill (C3 20.2 -> 17.5 us per step, 3 lean planets 30.5 -> 26.9, 4: 48.5 -> 46.7)
+#endif
 #ifndef OCTO_THR_ASTROM_INLINE
 #define OCTO_THR_ASTROM_INLINE 1
 #endif
@@ -1602,7 +1606,7 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
         A.P_smem = reinterpret_cast<DevParam*>(smem + (dyn >> 3) - kParamWords);
     }
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
-    eval_cta<GRAD, NPT, LAT ? OCTO_LAT_ILP : OCTO_THR_ILP, LEAN, FL, LAT>(m, A, smem, inl.v);
+    eval_cta<GRAD, NPT, (NPT >= OCTO_ILP1_FROM_NPT) ? 1 : (LAT ? OCTO_LAT_ILP : OCTO_THR_ILP), LEAN, FL, LAT>(m, A, smem, inl.v);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1702,7 +1706,7 @@ k_hmc_resident(const __grid_constant__ DevModel m, const DevParam* __restrict__ 
             A.in = s_qp; A.ll_out = s_lpp; A.g_out = s_gp;
             A.leap = HmcLeap{s_p, s_qp, s_im, R.eps, last ? 0.5 * R.eps : R.eps, last ? 0 : 1, 0, tempered ? s_beta : nullptr, tempered ? s_llp : nullptr};
         }
-        eval_cta<true, NPT, OCTO_LAT_ILP, LEAN, 3, true>(m, A, smem, nullptr);
+        eval_cta<true, NPT, (NPT >= OCTO_ILP1_FROM_NPT) ? 1 : OCTO_LAT_ILP, LEAN, 3, true>(m, A, smem, nullptr);
         __syncthreads();
 #ifdef OCTO_TIMING
         if (blockIdx.x == 0 && tid == 0 && it == R.n_iter - 1 && l == R.n_leapfrog - 1) {

@@ -8,7 +8,7 @@ import torch
 import octofitter_jl_b200 as octo
 import workloads
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
-spec, x = workloads.config(cfg)
+spec, x = workloads.k_planets_lean(int(cfg[1]), 1024, seed=7) if cfg[0] == "L" else workloads.config(cfg)      # "L3": 3 planets, lean tables
 n = x.shape[0]
 model = octo.LogDensityModel(spec)
 sets = [torch.from_numpy(np.ascontiguousarray((x * (1 + 1e-9 * k)).T)).cuda() for k in range(8)]

@@ -117,6 +117,30 @@ def two_planet(n_chains, seed, n_b=200, n_c=150, n_rv=150):
     return spec, _chains(spec, truth, n_chains, rng)
 
 
+def k_planets_lean(k, n_chains, seed, n_ep=60, n_rv=80):
+    """k planets (2..4), only lean tables: plain RA/Dec astrometry on every planet (with the reflex of the inner massive
+    ones) and star RV with offset and jitter — the multi-planet instantiations of the lean kernel family."""
+    rng = np.random.default_rng(seed)
+    els = [dict(a=3.0 * 1.9 ** j, e=0.05 + 0.07 * j, i=0.9 + 0.05 * j, w=0.4 + 0.9 * j, W=1.8 + 0.1 * j,
+                tp=50000.0 + 300.0 * j, M=1.2, plx=40.0, mass=(3.0 + 2 * j)) for j in range(k)]
+    truth = {"M": 1.2, "plx": 40.0, "rv.offset": 20.0, "rv.jitter": 3.0}
+    planets, names = [], "bcde"
+    for j, el in enumerate(els):
+        P = _state(el, [0.0])[3]
+        ep = np.linspace(50000.0 + 7 * j, 50000.0 + min(0.8 * P, 9000.0), n_ep + 3 * j)
+        tab = _astrom_table(el, ep, rng, sigma=3.0, others=[o for o in els if o["a"] < el["a"]])
+        planets.append(octo.Planet(name=names[j], variables=["a", "e", "i", "ω", "Ω", "tp", "mass"],
+                                   observations=[octo.PlanetRelAstromObs(tab, name=f"cam{j}")]))
+        truth.update({f"{names[j]}.{q}": el[v] for q, v in (("a", "a"), ("e", "e"), ("i", "i"), ("ω", "w"), ("Ω", "W"), ("tp", "tp"), ("mass", "mass"))})
+    ep_r = np.linspace(50005.0, 52000.0, n_rv)
+    rv = sum(-el["mass"] * MJUP2MSOL / el["M"] * _state(el, ep_r)[2] for el in els)
+    rvo = octo.StarAbsoluteRVObs(octo.Table(epoch=ep_r, rv=20.0 + rv + np.hypot(5, 3) * rng.standard_normal(n_rv),
+                                            σ_rv=np.full(n_rv, 5.0)), name="rv")
+    system = octo.System(name="lean%d" % k, variables=["M", "plx"], companions=planets, observations=[rvo])
+    spec = octo.ModelSpec(system)
+    return spec, _chains(spec, truth, n_chains, rng)
+
+
 def config(name):
     """BASELINE.json configs by name: C1..C4; C5 via one_planet(E, 0, 4096, 5 + k)."""
     if name == "C1":
