@@ -14,8 +14,8 @@ NVCC_LFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompi
 
 
 def _compile_and_link(out, defines, log_path=None):
-    """octo_kernels.cu is compiled once per planet-count instantiation and kernel family (-DOCTO_NPT=1|2|4
-    -DOCTO_LEANSEL=0|1) — those six objects and the other sources in parallel — then everything is linked into one shared library."""
+    """octo_kernels.cu is compiled once per planet-count instantiation and kernel family (-DOCTO_NPT=1|2|3|4
+    -DOCTO_LEANSEL=0|1) — those eight objects and the other sources in parallel — then everything is linked into one shared library."""
     import tempfile
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -23,7 +23,7 @@ def _compile_and_link(out, defines, log_path=None):
     # (source, extra flags, object); the kernel objects are built from one-line wrapper sources so that each embedded
     # cubin has its own name (cuobjdump -xelf, profiles/tools/sass_flops.py); line info still points at csrc/octo_kernels.cu
     units = [("octo_kernels_n%d_%s.cu" % (k, "lean" if l else "full"), ["-DOCTO_NPT=%d" % k, "-DOCTO_LEANSEL=%d" % l, "-I", CSRC], None)
-             for k in ((1,) if only1 else (1, 2, 4)) for l in (0, 1)]
+             for k in ((1,) if only1 else (1, 2, 3, 4)) for l in (0, 1)]
     units += [(os.path.join(CSRC, s), [], None) for s in SOURCES if s != "octo_kernels.cu"]
     with tempfile.TemporaryDirectory() as tmp:
         for i, (src, extra, _) in enumerate(units):

@@ -1763,7 +1763,7 @@ __global__ void k_selftest_kepler(const double* __restrict__ MA, const double* _
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// Host side.  build.py compiles this file once per planet-count instantiation (-DOCTO_NPT=1, 2, 4: three objects, in
+// Host side.  build.py compiles this file once per planet-count instantiation (-DOCTO_NPT=1, 2, 3, 4: four objects, in
 // parallel — one object with every instantiation takes > 5 minutes) and per lean / full kernel family (-DOCTO_LEANSEL); each
 // object exports its entry points as an OctoNptEntry, and the (1 planet, full) object also holds the dispatchers.  Without
 // -DOCTO_NPT everything is one object.
@@ -1836,7 +1836,7 @@ cudaError_t npt_resident(const DevModel& m, const cudaLaunchConfig_t* cfg, const
 #define OCTO_ENTRY(N, L) {&npt_attr<N, L>, &npt_occupancy<N, L>, &npt_launch<N, L>, &npt_resident<N, L>}
 }  // namespace
 
-// which instantiations this object holds: all of them, or (build.py) -DOCTO_NPT=1|2|4 -DOCTO_LEANSEL=0|1
+// which instantiations this object holds: all of them, or (build.py) -DOCTO_NPT=1|2|3|4 -DOCTO_LEANSEL=0|1
 #ifdef OCTO_NPT
 #define OCTO_HAS(N, L) (OCTO_NPT == N && OCTO_LEANSEL == L)
 #else
@@ -1859,6 +1859,12 @@ extern const OctoNptEntry octo_entry_n2_full = OCTO_ENTRY(2, false);
 #if OCTO_HAS_MULTI(2, 1)
 extern const OctoNptEntry octo_entry_n2_lean = OCTO_ENTRY(2, true);
 #endif
+#if OCTO_HAS_MULTI(3, 0)
+extern const OctoNptEntry octo_entry_n3_full = OCTO_ENTRY(3, false);
+#endif
+#if OCTO_HAS_MULTI(3, 1)
+extern const OctoNptEntry octo_entry_n3_lean = OCTO_ENTRY(3, true);
+#endif
 #if OCTO_HAS_MULTI(4, 0)
 extern const OctoNptEntry octo_entry_n4_full = OCTO_ENTRY(4, false);
 #endif
@@ -1869,12 +1875,15 @@ extern const OctoNptEntry octo_entry_n4_lean = OCTO_ENTRY(4, true);
 #if OCTO_HAS(1, 0)                   // this object also holds the dispatchers
 #ifdef OCTO_NPT_ONLY1
 extern const OctoNptEntry octo_entry_n2_full = {nullptr, nullptr, nullptr, nullptr}, octo_entry_n2_lean = {nullptr, nullptr, nullptr, nullptr};
+extern const OctoNptEntry octo_entry_n3_full = {nullptr, nullptr, nullptr, nullptr}, octo_entry_n3_lean = {nullptr, nullptr, nullptr, nullptr};
 extern const OctoNptEntry octo_entry_n4_full = {nullptr, nullptr, nullptr, nullptr}, octo_entry_n4_lean = {nullptr, nullptr, nullptr, nullptr};
 #endif
-extern const OctoNptEntry octo_entry_n1_lean, octo_entry_n2_full, octo_entry_n2_lean, octo_entry_n4_full, octo_entry_n4_lean;
+extern const OctoNptEntry octo_entry_n1_lean, octo_entry_n2_full, octo_entry_n2_lean, octo_entry_n3_full, octo_entry_n3_lean, octo_entry_n4_full,
+    octo_entry_n4_lean;
 static const OctoNptEntry& entry_of(const DevModel& m) {
     if (m.n_planets == 1) return m.lean ? octo_entry_n1_lean : octo_entry_n1_full;
     if (m.n_planets == 2) return m.lean ? octo_entry_n2_lean : octo_entry_n2_full;
+    if (m.n_planets == 3) return m.lean ? octo_entry_n3_lean : octo_entry_n3_full;
     return m.lean ? octo_entry_n4_lean : octo_entry_n4_full;
 }
 
@@ -1892,7 +1901,8 @@ size_t octo_smem_bytes(const DevModel& m, int W, int D, int T) {
 }
 
 cudaError_t octo_kernels_init(const DevModel& m, size_t smem_bytes, size_t smem_optin, int W, int* ctas_per_sm) {
-    for (const OctoNptEntry* en : {&octo_entry_n1_full, &octo_entry_n1_lean, &octo_entry_n2_full, &octo_entry_n2_lean, &octo_entry_n4_full, &octo_entry_n4_lean}) {
+    for (const OctoNptEntry* en : {&octo_entry_n1_full, &octo_entry_n1_lean, &octo_entry_n2_full, &octo_entry_n2_lean, &octo_entry_n3_full,
+                                   &octo_entry_n3_lean, &octo_entry_n4_full, &octo_entry_n4_lean}) {
         if (!en->attr) continue;
         const cudaError_t e = en->attr(smem_optin);
         if (e != cudaSuccess) return e;
