@@ -1607,6 +1607,13 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
     }
     A.ch = ch; A.chain0 = (int64_t)blockIdx.x * ch; A.group = blockIdx.x; A.gy = gridDim.y; A.by = blockIdx.y; A.lat_weights = LAT;
     eval_cta<GRAD, NPT, (NPT >= OCTO_ILP1_FROM_NPT) ? 1 : (LAT ? OCTO_LAT_ILP : OCTO_THR_ILP), LEAN, FL, LAT>(m, A, smem, inl.v);
+#ifdef OCTO_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0 && gridDim.y == 1 && !g_quiet) {      // single-split launch: phase stamps of CTA 0
+        const long long* t = g_tm_last;
+        printf("cta 0 ns (gy = 1): inputs/forward +%lld prologue +%lld segments +%lld reduce +%lld [hgca] +%lld epilogue +%lld%s +%lld\n",
+               t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], P && GRAD ? " backward" : "", t[12] > 7 ? t[7] - t[6] : 0LL);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
