@@ -1219,6 +1219,10 @@ __device__ __noinline__ void seg_rv_ool(const DevModel& m, const DevBlock& B, in
                                         double* acc, double2* stage, const double* __restrict__ in, int64_t c, int64_t ld, int lane, int ch) {
     seg_rv<GRAD, NPT, MARGIN, JIT, TREND, ILP>(m, B, k0, k1, s_const, acc, stage, in, c, ld, lane, ch);
 }
+#ifndef OCTO_REDUCE_UNROLL
+#define OCTO_REDUCE_UNROLL 8
+#endif
+constexpr int kReduceUnroll = OCTO_REDUCE_UNROLL;
 #ifndef OCTO_ILP1_FROM_NPT
 #define OCTO_ILP1_FROM_NPT 2       // table loops of kernels with at least this many planets keep ONE pair in flight per lane: two pairs x
                                    // several orbits spill (C3 20.2 -> 17.5 us per step, 3 lean planets 30.5 -> 26.9, 4: 48.5 -> 46.7)
@@ -1426,7 +1430,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 #pragma unroll 1
     for (int idx = threadIdx.x; idx < n_use * 32; idx += W * 32) {
         double v = s_acc[idx];
-#pragma unroll 8
+#pragma unroll (kReduceUnroll)
         for (int ww = 1; ww < W; ++ww) v += s_acc[ww * n_acc * 32 + idx];
         if (ch < 32) {
             double t = __shfl_sync(0xffffffffu, v, col_c);
