@@ -993,7 +993,7 @@ __device__ __noinline__ void hgca_tail(const DevModel& m, const DevHg& H, const 
 // forward stage for its 32 chains (lane = chain; WARPS stride over parameters / inputs / tperi items, so a prior
 // family or input definition is warp-uniform), the last CTA of a chain group runs the reverse stage after the
 // epilogue.  Same device functions and the same summation orders as the stand-alone K0 kernels (octo_param.cu):
-// both paths give the same bits.  All arrays are [index][32 lanes].
+// both paths agree to rounding (tests: 1e-12).  All arrays are [index][32 lanes].
 // ---------------------------------------------------------------------------------------------
 #ifdef OCTO_TIMING
 #define PTICK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ptk[i] = (long long)t_; } } while (0)
@@ -1625,9 +1625,10 @@ k_kepler_like(const __grid_constant__ DevModel m, const double* __restrict__ in,
 // independent, so ONE CTA keeps the state of its ch chains (position, momentum, gradient, proposal) in shared memory
 // and runs n_iter transitions x n_leapfrog leapfrogs inside one launch, calling the same evaluation body as the
 // one-shot kernel on shared-memory pointers (the fused parameterisation applies the kick and the drift itself).  No
-// launch, no L2 round trip and no cold instruction fetch per leapfrog.  The epoch split of a chain group happens
-// inside the warps (sub-lanes), never across CTAs.  Same per-coordinate arithmetic as k_hmc_turn (octo_hmc_dev.cuh),
-// same summation orders as a one-shot launch of the same geometry: both explorers give identical bits.
+// launch and no L2 round trip per leapfrog.  The epoch split of a chain group happens inside the warps (sub-lanes),
+// never across CTAs.  Same per-coordinate arithmetic as k_hmc_turn (octo_hmc_dev.cuh), same summation orders as a
+// one-shot launch of the same geometry: both explorers produce the same trajectories bit for bit (the log-posterior
+// values they report may differ in the last bit: each kernel inlines the evaluation and is contracted on its own).
 // ---------------------------------------------------------------------------------------------
 template <int NPT, bool LEAN>
 __global__ void __launch_bounds__(OCTO_LAT_WARPS * 32, 1)

@@ -1,5 +1,6 @@
 // octo_param_dev.cuh — device functions of the standard parameterisation, shared by the fused
-// path inside K1 (octo_kernels.cu) and the stand-alone K0 kernels (octo_param.cu) so that both produce the same bits.
+// path inside K1 (octo_kernels.cu) and the stand-alone K0 kernels (octo_param.cu): one source for both (they agree to
+// rounding — every kernel inlines these functions and the compiler contracts a*b+c per instantiation).
 //
 // Reference semantics: invlink (src/variables.jl:1449-1493), logpdf_with_trans / ln_prior_transformed
 // (src/variables.jl:1205-1369), UniformCircular + UnitLengthPrior (src/variables.jl:279-323),
