@@ -84,3 +84,22 @@ for kind, nt in (("star", 3), ("margin", 2), ("planet", 1)):
     ll, g = m.ln_like_and_gradient(x)
     print("trend", kind, nt, float(ll[0]), np.isfinite(g).all())
     m.close()
+# ---- page-locked buffers: inputs read by the kernel in place (zero-copy), outputs written in place; a 3-planet lean model
+#      (the 3-planet instantiation) and the copy path for comparison
+import workloads as W2
+for name, mk in (("C2", lambda: W2.config("C2")), ("lean3", lambda: W2.k_planets_lean(3, 40, seed=7))):
+    spec, x = mk()
+    x = x[:40]
+    res = {}
+    for zmax in ("524288", "0"):
+        os.environ["OCTO_B200_ZEROCOPY_MAX"] = zmax
+        m = octo.LogDensityModel(spec)
+        xp = m.pinned_empty(x.shape); xp[...] = x
+        out = (m.pinned_empty(x.shape[0]), m.pinned_empty(x.shape))
+        ll, g = m.ln_like_and_gradient(xp, out=out)
+        hs = [m.ln_like_and_gradient_begin(xp, out=out) for _ in range(2)]
+        for h in hs: h.wait()
+        res[zmax] = (ll.copy(), g.copy())
+        m.close()
+    os.environ.pop("OCTO_B200_ZEROCOPY_MAX")
+    print("pinned", name, float(res["0"][0][0]), np.array_equal(res["0"][0], res["524288"][0]), np.array_equal(res["0"][1], res["524288"][1]))

@@ -572,6 +572,45 @@ def test_lean_and_full_kernel_families_agree(oracle_lib, monkeypatch, post):
             assert rel_err(out[mode][0][pick], lp_o).max() < LOGP_RTOL and grad_err(out[mode][1][pick], g_o).max() < GRAD_RTOL
 
 
+def test_pinned_inputs_read_in_place_match_the_copy_path(monkeypatch):
+    """Page-locked inputs up to OCTO_B200_ZEROCOPY_MAX bytes are read by the kernel in place (no H2D copy launch);
+    larger ones, or with the knob at 0, go through the copy engine.  Same kernel, same inputs: identical bits — blocking
+    call, asynchronous halves, log posterior, a leading dimension larger than the batch."""
+    import workloads
+    spec, th = workloads.one_planet_with_priors(60, 40, 300, seed=8)
+    out = {}
+    for zmax in ("524288", "0", "1000"):          # in place / always copy / in place only for tiny inputs (here: copy)
+        monkeypatch.setenv("OCTO_B200_ZEROCOPY_MAX", zmax)
+        model = octo.LogDensityModel(spec)
+        thp = model.pinned_empty(th.shape)
+        thp[...] = th
+        o1 = (model.pinned_empty(300), model.pinned_empty(th.shape))
+        lp, g = model.ℓπcallback_grad(thp, out=o1)
+        lp, g = lp.copy(), g.copy()
+        hs = [model.ℓπcallback_grad_begin(thp, out=(model.pinned_empty(300), model.pinned_empty(th.shape))) for _ in range(3)]
+        rs = [h.wait() for h in hs]
+        for r in rs:
+            assert np.array_equal(r[0], lp) and np.array_equal(r[1], g)
+        out[zmax] = (lp, g)
+        model.close()
+    for z in ("0", "1000"):
+        assert np.array_equal(out["524288"][0], out[z][0]) and np.array_equal(out["524288"][1], out[z][1])
+    # likelihood entry point with ld > n through the C ABI
+    spec2, x2 = workloads.config("C2")
+    res = {}
+    for zmax in ("524288", "0"):
+        monkeypatch.setenv("OCTO_B200_ZEROCOPY_MAX", zmax)
+        model = octo.LogDensityModel(spec2)
+        n, ld, k = 200, 256, spec2.n_in
+        xin = model.pinned_empty((ld, k)); xin[:n] = x2[:n]; xin[n:] = np.nan
+        ll = model.pinned_empty(n); gg = model.pinned_empty((ld, k))
+        assert model._lib.octo_logp_grad(model._h, xin.ctypes.data, n, ld, ll.ctypes.data, gg.ctypes.data) == 0
+        res[zmax] = (ll.copy(), gg[:n].copy())
+        model.close()
+    assert np.array_equal(res["0"][0], res["524288"][0]) and np.array_equal(res["0"][1], res["524288"][1])
+    assert np.isfinite(res["0"][0]).all()
+
+
 def test_pointwise_like_more_epochs_than_one_grid(oracle_lib):
     """More than 65535 epochs: octo_logp_pointwise walks the epoch list in chunks.  The columns sum to ln_like and
     spot-checked columns equal the oracle on the one-epoch model."""
