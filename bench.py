@@ -469,7 +469,7 @@ def main():
     model_p.ℓπcallback_grad(thp, out=out_p)
     post_launches = model_p._lib.octo_kernel_launches(model_p._h) - n0
     # the same log posterior driven by the device-resident HMC explorer (octo_hmc_run): whole run on one stream
-    hmc_iters, hmc_leap = 20, 10
+    hmc_iters, hmc_leap = 100, 10            # (a 1000-leapfrog call: its fixed ~150 us of allocation, copies and the final sync are 0.15 us per leapfrog)
     im_p = np.full(spec_p.D, 1e-4)
     octo.device_hmc(model_p, th_p, 2, step_size=1e-3, n_leapfrog=hmc_leap, inv_mass=im_p, seed=1, keep_samples=False)
     t0 = time.perf_counter()
@@ -477,7 +477,7 @@ def main():
     t_hmc = time.perf_counter() - t0
     # C4-shaped parallel tempering on the same model: 64 replicas, every round 1 tempered transition of 8 leapfrogs +
     # one swap round + re-evaluation, device-resident (octo_pt_hmc_run)
-    pt_n, pt_rounds, pt_leap = 64, 50, 8
+    pt_n, pt_rounds, pt_leap = 64, 200, 8
     lad = np.linspace(0.0, 1.0, pt_n) ** 3
     octo.device_parallel_tempering(model_p, th_p[:pt_n], lad, 2, n_iter=1, n_leapfrog=pt_leap, step_size=1e-3, inv_mass=im_p, seed=3)
     t0 = time.perf_counter()
