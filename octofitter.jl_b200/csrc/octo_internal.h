@@ -113,6 +113,10 @@ struct DevParam {
     // evaluation orders of the fused stage, most expensive item first (warps take items round-robin, so the expensive
     // ones land on different warps in the first round): priors (invlink + log density), input definitions, gathers
     uint8_t order_prior[OCTO_PARAM_MAX], order_input[OCTO_PARAM_MAX], order_gather[OCTO_PARAM_MAX];
+    // inputs whose sine and cosine the evaluation needs (inclination / ω / Ω of a planet, the four angles of a
+    // θ_at_epoch_to_tperi definition): the fused stage of the lean kernels produces them together with the input itself —
+    // for a UniformCircular pair with domain 2π as (y, x) / r, without atan2 and sincos (octo_kernels.cu, param_forward)
+    uint8_t in_trig[OCTO_PARAM_MAX];
 };
 
 // Tiny batches (a single chain, as the reference's samplers call the model): the inputs travel inside the kernel

@@ -605,10 +605,7 @@ __device__ __forceinline__ double rsqrt_nr(double x) {      // 1/sqrt(x), x > 0 
 // ThieleInnesOrbit: a = sqrt(u + sqrt((u+v)(u-v))) / plx (src/parameterizations.jl:14-18); the constants and the pieces
 // of that formula are kept for the projection and the chain rule (in slots this basis does not otherwise use).
 // Out of line: models without such planets never fetch this code.
-__device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const double* __restrict__ in, int64_t c, int64_t ld,
-                                            double plx, double* sc, int lane) {
-    const double A = in[c + (int64_t)m.idx_A[p] * ld], B = in[c + (int64_t)m.idx_B[p] * ld];
-    const double F = in[c + (int64_t)m.idx_F[p] * ld], G = in[c + (int64_t)m.idx_G[p] * ld];
+__device__ __noinline__ double ti_semimajor(double A, double B, double F, double G, double plx, double* sc, int lane) {
     const double u = 0.5 * (A * A + B * B + F * F + G * G), v = A * G - B * F;
     const double wq = sqrt((u + v) * (u - v)), alpha = sqrt(u + wq);
     sc[PC_A * 32 + lane] = A; sc[PC_B * 32 + lane] = B; sc[PC_F * 32 + lane] = F; sc[PC_G * 32 + lane] = G;
@@ -619,9 +616,10 @@ __device__ __noinline__ double ti_semimajor(const DevModel& m, int p, const doub
 // returns validity of what the task looked at
 // skip_tp: the fused parameterisation derives tp (θ_at_epoch_to_tperi) on another warp at the same time and stores it
 // itself; the size / mass / time task then leaves tp alone
-template <bool LEAN>
-__device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind, const double* __restrict__ in, int64_t c, int64_t ld,
-                              double* sc, int lane, bool skip_tp = false) {
+// rd(k): the value of kernel input k for this lane's chain (global memory, the staged inputs, or — fused stage, before the
+// inputs are staged — straight from the parameter it is defined by)
+template <bool LEAN, class RD>
+__device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind, RD rd, double* sc, int lane, bool skip_tp = false) {
     const bool ti = (!LEAN && m.any_ti) && m.basis[p] == OCTO_BASIS_THIELE_INNES;
     if (kind < 3) {
         if (ti) {            // no angles: neutral values for the slots the Campbell code reads
@@ -630,7 +628,7 @@ __device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind
             return true;
         }
         const int idx = kind == 0 ? m.idx_i[p] : (kind == 1 ? m.idx_w[p] : m.idx_W[p]);
-        const double x = in[c + (int64_t)idx * ld];
+        const double x = rd(idx);
         const bool ok = isfinite(x) && fabs(x) < 1e9;
         double sn, cs;
         sincos_any(ok ? x : 0.0, sn, cs);
@@ -639,7 +637,7 @@ __device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind
         return ok;
     }
     if (kind == 3) {          // eccentricity chain
-        double e = in[c + (int64_t)m.idx_e[p] * ld];
+        double e = rd(m.idx_e[p]);
         const bool ok = isfinite(e) && (e >= 0.0) && (e < 1.0);
         if (!ok) e = 0.1;
         const double s2 = fma(-e, e, 1.0);
@@ -652,10 +650,10 @@ __device__ __forceinline__ bool prologue_task(const DevModel& m, int p, int kind
     // division and square root (KepOrbit ctor + orbitsolve: n = 2π / (√(a³/M)·kyd / y2d), MA = n / y2d · (t - tp)):
     // its last bit is multiplied by |MA| (thousands of radians for short periods), so anything else would cost
     // parity digits in exactly the regime where the problem is already ill-conditioned.
-    double tp = skip_tp ? 0.0 : in[c + (int64_t)m.idx_tp[p] * ld];
-    double M = in[c + (int64_t)m.idx_M[p] * ld], plx = in[c + (int64_t)m.idx_plx[p] * ld];
-    double mass = m.idx_mass[p] >= 0 ? in[c + (int64_t)m.idx_mass[p] * ld] : 0.0;
-    double a = ti ? ti_semimajor(m, p, in, c, ld, plx, sc, lane) : in[c + (int64_t)m.idx_a[p] * ld];
+    double tp = skip_tp ? 0.0 : rd(m.idx_tp[p]);
+    double M = rd(m.idx_M[p]), plx = rd(m.idx_plx[p]);
+    double mass = m.idx_mass[p] >= 0 ? rd(m.idx_mass[p]) : 0.0;
+    double a = ti ? ti_semimajor(rd(m.idx_A[p]), rd(m.idx_B[p]), rd(m.idx_F[p]), rd(m.idx_G[p]), plx, sc, lane) : rd(m.idx_a[p]);
     const bool fin = isfinite(a) && isfinite(tp) && isfinite(M) && isfinite(plx) && isfinite(mass);
     const bool ok = fin && (a > 0.0) && (M > 0.0) && (plx > 0.0);
     if (!ok) { a = 1.0; tp = 0.0; M = 1.0; plx = 1.0; mass = 0.0; }
@@ -1006,22 +1004,26 @@ __device__ int g_quiet;      // set by the resident kernel: phase timings are pr
 #endif
 // trig: per θ_at_epoch_to_tperi definition 16 slots — sin, cos of (θ, i, ω, Ω), the mean anomaly, then the reciprocals and
 // roots of its forward pass (tperi_mid `keep`); cir: [2][n_in] what circ_forward saves for the reverse pass
+#ifndef OCTO_EARLY_TRIG
+#define OCTO_EARLY_TRIG 1        // lean kernels: sines / cosines together with the inputs, prologue chains in the same phase (param_forward)
+#endif
 constexpr int TRIG_SLOTS = 16;
 // DevParam staged in shared memory (the last kParamWords doubles of the evaluation's area): the parameterisation stages
 // chase order -> prior / definition -> operand indices several times per phase, each a dependent L2 round trip (~300 cycles)
 // when read from global memory — ~1.5 us of a 12 us leapfrog
 constexpr int kParamWords = (int)((sizeof(DevParam) + 7) / 8);
-struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *cir, *trig, *part, *lp, *extra, *beta; int* flags; };
+struct ParamSmem { double *th, *dxdy, *gth, *L, *aux, *cir, *cs, *trig, *part, *lp, *extra, *beta; int* flags; };
 __device__ __forceinline__ ParamSmem param_smem(double* base, int n_in, int D, int T) {
     ParamSmem S;
     S.th = base; S.dxdy = S.th + D * 32; S.gth = S.dxdy + D * 32; S.L = S.gth + D * 32; S.aux = S.L + D * 32;
     S.cir = S.aux + n_in * 32;
-    S.trig = S.cir + 2 * n_in * 32; S.part = S.trig + T * TRIG_SLOTS * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
+    S.cs = S.cir + 2 * n_in * 32;                              // [2][n_in]: sine, cosine of the inputs that are angles (DevParam::in_trig)
+    S.trig = S.cs + 2 * n_in * 32; S.part = S.trig + T * TRIG_SLOTS * 32; S.lp = S.part + T * 8 * 32; S.extra = S.lp + 32;
     S.beta = S.extra + 32;
     S.flags = reinterpret_cast<int*>(S.beta + 32);
     return S;
 }
-__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + 3 * n_in + (TRIG_SLOTS + 8) * T + 4) * 32; }
+__host__ __device__ inline size_t param_smem_doubles(int n_in, int D, int T) { return (size_t)(4 * D + 5 * n_in + (TRIG_SLOTS + 8) * T + 4) * 32; }
 
 template <bool LEAN>
 __device__ __forceinline__ void param_forward(const DevParam& P, const DevModel& m, const double* __restrict__ theta_t, int64_t c,
@@ -1046,43 +1048,102 @@ __device__ __forceinline__ void param_forward(const DevParam& P, const DevModel&
     }
     __syncthreads();
     PTICK(1);
-    // derived inputs that depend on parameters only (arr2nt)
-#pragma unroll 1
-    for (int kk = w; kk < n_in; kk += W) {
-        const int k = P.order_input[kk];
-        const OctoInputDef& d = P.defs[k];
-        double v = 0.0, ext = 0.0;
-        if (d.op == OCTO_IN_PARAM) v = S.th[d.a[0] * 32 + lane];
-        else if (d.op == OCTO_IN_CONST) v = d.value;
-        else if (d.op == OCTO_IN_CIRC) circ_forward(S.th[d.a[0] * 32 + lane], S.th[d.a[1] * 32 + lane], d.value, v, ext,
-                                                    &S.cir[k * 32 + lane], &S.cir[(n_in + k) * 32 + lane]);
-        s_in[k * 32 + lane] = v; S.aux[k * 32 + lane] = ext;
-    }
-    __syncthreads();
-    PTICK(2);
-    // One phase for two independent things: the trigonometry of θ_at_epoch_to_tperi — (definition, angle) items for
-    // (θ, i, ω, Ω) — and phase 1 of K1's prologue (five tasks per planet; none of them needs tp).  Items over warps.
-    {
-        const int n_trig = 4 * T, n_item = n_trig + 5 * m.n_planets;
+    if constexpr (LEAN && OCTO_EARLY_TRIG) {
+        // LEAN kernels (Campbell planets only).  ONE phase for: the derived inputs (arr2nt), the sines and cosines the
+        // evaluation needs of them (DevParam::in_trig) — for a UniformCircular pair with the full circle as its domain
+        // simply (y, x) / r: no atan2, no sincos; the angle itself is used nowhere in this kernel — and the two heavy
+        // prologue chains of every planet, which read their inputs straight from the parameters that define them (the
+        // host only fuses a lean model whose e, a, M, plx, mass are parameters or constants).  Round 1 - 2a had three
+        // barrier-separated phases here (inputs; trigonometry of tperi + prologue tasks): 1.3k + 0.7k cycles -> ~1.0k.
+        const int np = m.n_planets, n_item = 2 * np + n_in;
+        auto rd_param = [&](int k) { const OctoInputDef& d = P.defs[k]; return d.op == OCTO_IN_PARAM ? S.th[d.a[0] * 32 + lane] : d.value; };
 #pragma unroll 1
         for (int it = w; it < n_item; it += W) {
-            if (it < n_trig) {
-                const int t = it >> 2, q = it & 3;
-                const OctoInputDef& d = P.defs[P.tperi_k[t]];
-                if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
-                double sn, cs;
-                p_sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
-                S.trig[(t * TRIG_SLOTS + 2 * q) * 32 + lane] = sn; S.trig[(t * TRIG_SLOTS + 2 * q + 1) * 32 + lane] = cs;
-            } else {
-                const int task = it - n_trig, p = task / 5, kind = task % 5;
-                bool derived_tp = false;                                 // this planet's tp is one of the tperi definitions
+            if (it < 2 * np) {
+                const int p = it >> 1, kind = 4 - (it & 1);
+                bool derived_tp = false;
                 for (int t = 0; t < T; ++t) derived_tp = derived_tp || P.tperi_k[t] == m.idx_tp[p];
-                if (!prologue_task<LEAN>(m, p, kind, s_in, lane, 32, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
+                if (!prologue_task<LEAN>(m, p, kind, rd_param, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
+                continue;
+            }
+            const int k = P.order_input[it - 2 * np];
+            const OctoInputDef& d = P.defs[k];
+            const bool trig = P.in_trig[k] != 0;
+            double v = 0.0, ext = 0.0, sn = 0.0, cs = 1.0;
+            bool ok = true;
+            if (d.op == OCTO_IN_CIRC) {
+                const double x = S.th[d.a[0] * 32 + lane], y = S.th[d.a[1] * 32 + lane];
+                if (trig && d.value == octo_param_dev::kTwoPi) {
+                    const double r2 = fma(x, x, y * y), l2 = p_log(r2), lr = 0.5 * l2;
+                    ext = fma(-lr * lr, 50.0, -lr - (-2.302585092994045684 /* log 0.1 */) - kHalfLog2Pi);      // circ_forward's UnitLengthPrior term
+                    const double ir2 = 1.0 / r2;
+                    S.cir[k * 32 + lane] = ir2; S.cir[(n_in + k) * 32 + lane] = -1.0 - 0.5 * l2 * 100.0;
+                    const bool pos = r2 > 0.0 && isfinite(r2);
+                    const double ir = pos ? rsqrt_nr(r2) : 0.0;
+                    sn = y * ir; cs = pos ? x * ir : 1.0;                  // atan2(0, 0) = 0
+                    v = r2 - r2;                                           // stands for the angle in the validity checks: 0, or NaN
+                } else {
+                    circ_forward(x, y, d.value, v, ext, &S.cir[k * 32 + lane], &S.cir[(n_in + k) * 32 + lane]);
+                    if (trig) sincos_any(isfinite(v) ? v : 0.0, sn, cs);
+                }
+            } else if (d.op == OCTO_IN_PARAM || d.op == OCTO_IN_CONST) {
+                v = d.op == OCTO_IN_PARAM ? S.th[d.a[0] * 32 + lane] : d.value;
+                if (trig) { ok = isfinite(v) && fabs(v) < 1e9; sincos_any(ok ? v : 0.0, sn, cs); }
+            }
+            s_in[k * 32 + lane] = v; S.aux[k * 32 + lane] = ext;
+            if (trig) {
+                S.cs[k * 32 + lane] = sn; S.cs[(n_in + k) * 32 + lane] = cs;
+#pragma unroll 1
+                for (int p = 0; p < np; ++p) {                           // the planets that use this angle
+                    double* sc = s_const + p * PC_COUNT * 32;
+                    if (k == m.idx_i[p]) { sc[PC_sini * 32 + lane] = sn; sc[PC_cosi * 32 + lane] = cs; if (!ok) s_ok[lane] = 0; }
+                    if (k == m.idx_w[p]) { sc[PC_sinw * 32 + lane] = sn; sc[PC_cosw * 32 + lane] = cs; if (!ok) s_ok[lane] = 0; }
+                    if (k == m.idx_W[p]) { sc[PC_sinW * 32 + lane] = sn; sc[PC_cosW * 32 + lane] = cs; if (!ok) s_ok[lane] = 0; }
+                }
             }
         }
+        __syncthreads();
+        PTICK(2);
+        PTICK(3);
+    } else {
+    // derived inputs that depend on parameters only (arr2nt)
+#pragma unroll 1
+        for (int kk = w; kk < n_in; kk += W) {
+            const int k = P.order_input[kk];
+            const OctoInputDef& d = P.defs[k];
+            double v = 0.0, ext = 0.0;
+            if (d.op == OCTO_IN_PARAM) v = S.th[d.a[0] * 32 + lane];
+            else if (d.op == OCTO_IN_CONST) v = d.value;
+            else if (d.op == OCTO_IN_CIRC) circ_forward(S.th[d.a[0] * 32 + lane], S.th[d.a[1] * 32 + lane], d.value, v, ext,
+                                                        &S.cir[k * 32 + lane], &S.cir[(n_in + k) * 32 + lane]);
+            s_in[k * 32 + lane] = v; S.aux[k * 32 + lane] = ext;
+        }
+        __syncthreads();
+        PTICK(2);
+        // One phase for two independent things: the trigonometry of θ_at_epoch_to_tperi — (definition, angle) items for
+        // (θ, i, ω, Ω) — and phase 1 of K1's prologue (five tasks per planet; none of them needs tp).  Items over warps.
+        {
+            const int n_trig = 4 * T, n_item = n_trig + 5 * m.n_planets;
+#pragma unroll 1
+            for (int it = w; it < n_item; it += W) {
+                if (it < n_trig) {
+                    const int t = it >> 2, q = it & 3;
+                    const OctoInputDef& d = P.defs[P.tperi_k[t]];
+                    if (d.op == OCTO_IN_TPERI_TI && q > 0) continue;          // Thiele-Innes: only θ is an angle
+                    double sn, cs;
+                    p_sincos(s_in[d.a[q == 0 ? 0 : 3 + q] * 32 + lane], &sn, &cs);
+                    S.trig[(t * TRIG_SLOTS + 2 * q) * 32 + lane] = sn; S.trig[(t * TRIG_SLOTS + 2 * q + 1) * 32 + lane] = cs;
+                } else {
+                    const int task = it - n_trig, p = task / 5, kind = task % 5;
+                    bool derived_tp = false;                                 // this planet's tp is one of the tperi definitions
+                    for (int t = 0; t < T; ++t) derived_tp = derived_tp || P.tperi_k[t] == m.idx_tp[p];
+                    if (!prologue_task<LEAN>(m, p, kind, [&](int k) { return s_in[k * 32 + lane]; }, s_const + p * PC_COUNT * 32, lane, derived_tp)) s_ok[lane] = 0;
+                }
+            }
+        }
+        __syncthreads();
+        PTICK(3);
     }
-    __syncthreads();
-    PTICK(3);
     // Second phase, again independent things on different warps: one warp per θ_at_epoch_to_tperi definition (it hands
     // tp to the planets that use it), the prologue's products (they do not involve tp) on the next warps, the ordered
     // prior sums on the last warp.
@@ -1095,8 +1156,17 @@ __device__ __forceinline__ void param_forward(const DevParam& P, const DevModel&
             double arg[8], trig[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) arg[q] = (q < 7 || ti) ? s_in[d.a[q] * 32 + lane] : 0.0;
+            if constexpr (LEAN && OCTO_EARLY_TRIG) {                  // sines / cosines of (θ, i, ω, Ω) came with the inputs; kept for the reverse pass
 #pragma unroll
-            for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * TRIG_SLOTS + q) * 32 + lane];
+                for (int q = 0; q < 4; ++q) {
+                    const int ak = d.a[q == 0 ? 0 : 3 + q];
+                    trig[2 * q] = S.cs[ak * 32 + lane]; trig[2 * q + 1] = S.cs[(n_in + ak) * 32 + lane];
+                    S.trig[(t * TRIG_SLOTS + 2 * q) * 32 + lane] = trig[2 * q]; S.trig[(t * TRIG_SLOTS + 2 * q + 1) * 32 + lane] = trig[2 * q + 1];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) trig[q] = S.trig[(t * TRIG_SLOTS + q) * 32 + lane];
+            }
             double MA;
             const double tp = tperi_value(m.c, d.value, arg, trig, &MA, ti, S.trig + (t * TRIG_SLOTS + 9) * 32 + lane, 32);
             s_in[k * 32 + lane] = tp;
@@ -1379,7 +1449,7 @@ __device__ __forceinline__ bool eval_cta(const DevModel& m, const EvalArgs& A, d
 #pragma unroll 1
         for (int it = threadIdx.x; it < ncol * 5 * m.n_planets; it += W * 32) {
             const int col = it % ncol, task = it / ncol;
-            if (!prologue_task<LEAN>(m, task / 5, task % 5, inp, chain_of(col), ld, s_const + (task / 5) * PC_COUNT * 32, col)) s_ok[col] = 0;
+            if (!prologue_task<LEAN>(m, task / 5, task % 5, [&](int k) { return inp[chain_of(col) + (int64_t)k * ld]; }, s_const + (task / 5) * PC_COUNT * 32, col)) s_ok[col] = 0;
         }
         __syncthreads();
         // ---- phase 2: Thiele-Innes / RV products

@@ -957,6 +957,27 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
         }
         P.gat_start[D] = (int16_t)n;
     }
+    // lean kernels (Campbell planets, lean tables): which inputs need their sine / cosine, and what their fused stage
+    // assumes about the other orbital elements (octo_kernels.cu, param_forward)
+    memset(P.in_trig, 0, sizeof(P.in_trig));
+    bool lean_ok = true;
+    {
+        const DevModel& m = ctx->m;
+        auto plain = [&](int k) { return k >= 0 && (P.defs[k].op == OCTO_IN_PARAM || P.defs[k].op == OCTO_IN_CONST); };
+        auto angle = [&](int k) { return plain(k) || (k >= 0 && P.defs[k].op == OCTO_IN_CIRC); };
+        for (int p = 0; p < m.n_planets && m.lean; ++p) {
+            for (int k : {m.idx_i[p], m.idx_w[p], m.idx_W[p]}) { if (angle(k)) P.in_trig[k] = 1; else lean_ok = false; }
+            for (int k : {m.idx_e[p], m.idx_a[p], m.idx_M[p], m.idx_plx[p]}) if (!plain(k)) lean_ok = false;
+            if (m.idx_mass[p] >= 0 && !plain(m.idx_mass[p])) lean_ok = false;
+            const int ktp = m.idx_tp[p];
+            if (!(plain(ktp) || (ktp >= 0 && P.defs[ktp].op == OCTO_IN_TPERI))) lean_ok = false;
+        }
+        for (int k = 0; k < n_in && m.lean; ++k) {
+            if (P.defs[k].op == OCTO_IN_TPERI_TI) lean_ok = false;
+            if (P.defs[k].op != OCTO_IN_TPERI) continue;
+            for (int q : {0, 4, 5, 6}) { const int a = P.defs[k].a[q]; if (angle(a)) P.in_trig[a] = 1; else lean_ok = false; }
+        }
+    }
     // evaluation orders, most expensive first (stable): see DevParam
     {
         auto order_by = [](uint8_t* out, int n, const std::vector<int>& cost) {
@@ -970,7 +991,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
             const bool lb = std::isfinite(P.pc[j][0]), ub = std::isfinite(P.pc[j][1]);
             cp[j] = (lb || ub ? 3 : 0) + (P.priors[j].family == OCTO_PRIOR_LOGUNIFORM ? 1 : 0) + (P.priors[j].family == OCTO_PRIOR_SINE ? 2 : 0);
         }
-        for (int k = 0; k < n_in; ++k) ci[k] = P.defs[k].op == OCTO_IN_CIRC ? 3 : 0;
+        for (int k = 0; k < n_in; ++k) ci[k] = P.defs[k].op == OCTO_IN_CIRC ? 3 : (P.in_trig[k] ? 2 : 0);
         for (int j = 0; j < D; ++j)
             for (int it = P.gat_start[j]; it < P.gat_start[j + 1]; ++it) cg[j] += (P.gat[it] >> 8) ? 3 : 1;
         order_by(P.order_prior, D, cp); order_by(P.order_input, n_in, ci); order_by(P.order_gather, D, cg);
@@ -988,6 +1009,7 @@ int octo_set_parameterization(OctoCtx* ctx, const OctoPrior* priors, int32_t D, 
         if (P.n_tperi < OCTO_PARAM_TPERI_MAX) P.tperi_k[P.n_tperi] = k;
         if (++P.n_tperi > OCTO_PARAM_TPERI_MAX) { fusable = false; P.n_tperi = OCTO_PARAM_TPERI_MAX; }
     }
+    if (ctx->m.lean && !lean_ok) fusable = false;          // (an element derived in an unusual way: the stand-alone stage handles it)
     if (const char* e = getenv("OCTO_B200_FUSE_PARAM")) if (atoi(e) == 0) fusable = false;
     CU(cudaSetDevice(ctx->device));
     int wf = ctx->warps;
