@@ -572,6 +572,27 @@ def test_lean_and_full_kernel_families_agree(oracle_lib, monkeypatch, post):
             assert rel_err(out[mode][0][pick], lp_o).max() < LOGP_RTOL and grad_err(out[mode][1][pick], g_o).max() < GRAD_RTOL
 
 
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_lean_multi_planet_kernels(oracle_lib, k):
+    """2, 3 and 4 planets with lean tables only (plain RA/Dec astrometry with the reflex of the inner planets, star RV
+    with offset and jitter): the multi-planet instantiations of the LEAN kernel family (one pair in flight per lane), in
+    the latency regime (70 chains: sub-lanes) and in the throughput regime (6000 chains: lane = chain, two CTAs per SM)."""
+    import workloads
+    for n in (70, 6000):
+        spec, x = workloads.k_planets_lean(k, n, seed=20 + k)
+        model = octo.LogDensityModel(spec)
+        ll, g = model.ln_like_and_gradient(x)
+        llv = model.ln_like(x)
+        geom = model.launch_geometry_full(n)
+        model.close()
+        assert geom[5] == (1 if n == 70 else 0), geom
+        pick = np.arange(n) if n == 70 else np.r_[0:40, n // 2:n // 2 + 40, n - 40:n]
+        ll_o, g_o = oracle_lib.Oracle(spec.packed, octo.default_constants()).logp_grad(np.asfortranarray(x[pick]), threads=4)
+        assert np.isfinite(ll_o).all()
+        assert rel_err(ll[pick], ll_o).max() < LOGP_RTOL and grad_err(g[pick], g_o).max() < GRAD_RTOL
+        assert rel_err(llv[pick], ll_o).max() < LOGP_RTOL
+
+
 def test_pinned_inputs_read_in_place_match_the_copy_path(monkeypatch):
     """Page-locked inputs up to OCTO_B200_ZEROCOPY_MAX bytes are read by the kernel in place (no H2D copy launch);
     larger ones, or with the knob at 0, go through the copy engine.  Same kernel, same inputs: identical bits — blocking
